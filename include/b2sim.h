@@ -1,0 +1,114 @@
+/* b2sim.h — C ABI of the B200-native batched physics step (libb2sim.so).
+ *
+ * Drop-in boundary: these entry points are what mjlab's `Simulation` class
+ * (reference src/mjlab/sim/sim.py:94-198) needs from its physics backend. In the reference
+ * that backend is the Python package mujoco_warp, reached from four call sites:
+ *   mjwarp.put_model  sim.py:110      -> b2_create (model upload)
+ *   mjwarp.put_data   sim.py:113-119  -> b2_create (nworld / nconmax / njmax sizing, Data alloc)
+ *   mjwarp.step       sim.py:136,195  -> b2_step / b2_step_n
+ *   mjwarp.forward    sim.py:139,187  -> b2_forward
+ * plus the zero-copy field access that WarpBridge/TorchArray provide (sim_data.py:15-229)
+ *   getattr(wp_data, name) / wp.to_torch -> b2_get_field
+ * and the per-world model tiling of sim/randomization.py:20-55
+ *   expand_model_fields -> b2_expand_model_field.
+ * No torch types cross this boundary: plain pointers, sizes and a CUDA stream handle.
+ * All functions return 0 on success, non-zero on error (message via b2_last_error()).
+ * Nothing in b2_step/b2_forward allocates, synchronises or touches the host: they only enqueue
+ * kernels on the given stream and are CUDA-graph capturable.
+ */
+#ifndef B2SIM_H_
+#define B2SIM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- model description handed in by the host (compiled by mjlab_b200.compiler) ---------- */
+enum { B2_F64 = 0, B2_I32 = 1, B2_F32 = 2 };
+
+typedef struct B2Array {
+  const char* name; /* mjModel-style field name, e.g. "body_pos", "nq", "opt_timestep" */
+  int32_t dtype;    /* B2_F64 or B2_I32 */
+  int64_t n;        /* number of elements */
+  const void* data; /* host pointer, valid during b2_create only */
+} B2Array;
+
+typedef struct B2ModelDesc {
+  int32_t narray;
+  const B2Array* arrays;
+  double gravity[3];
+} B2ModelDesc;
+
+/* ---- tensor view returned for a Data / Model field ---------------------------------------- */
+enum { B2_DATA = 0, B2_MODEL = 1 };
+
+typedef struct B2Tensor {
+  void* ptr;         /* device pointer */
+  int32_t dtype;     /* B2_F32 or B2_I32 */
+  int32_t ndim;      /* <= 4; shape[0] == nworld for Data and for expanded Model fields, else 1 */
+  int64_t shape[4];
+  int64_t stride[4]; /* in elements; rows are padded to 16 B so they can be bulk-copied (TMA) */
+  int32_t device;    /* CUDA ordinal */
+} B2Tensor;
+
+typedef struct B2Stats {
+  int32_t ncon_max, ncon_cap;   /* max contacts in any world / per-world capacity */
+  int32_t nefc_max, nefc_cap;   /* max constraint rows in any world / njmax */
+  int32_t overflow_worlds;      /* worlds that hit a capacity (contacts truncated, in pair order) */
+  int32_t niter_max;            /* max Newton iterations used by any world in the last step */
+  double ncon_mean, nefc_mean, niter_mean;
+} B2Stats;
+
+typedef struct b2_sim b2_sim;
+
+/* Create a simulation: uploads the model, allocates Data for `nworld` worlds on `cuda_device`,
+ * initialises qpos=qpos0 and runs one forward pass so every derived field is valid
+ * (reference sim.py:106-107 relies on a forwarded MjData).
+ *   ncon_per_world <= 0 : default capacity; njmax <= 0 : default.  */
+int b2_create(const B2ModelDesc* model, int nworld, int ncon_per_world, int njmax,
+              int cuda_device, b2_sim** out);
+int b2_destroy(b2_sim* sim);
+
+/* Zero-copy view of a field. Pointers stay valid for the lifetime of the sim, except that
+ * b2_expand_model_field re-points the named Model field (the step kernels read model fields
+ * through a pointer table in device memory, so already-captured CUDA graphs stay valid). */
+int b2_get_field(b2_sim* sim, int which, const char* name, B2Tensor* out);
+int b2_num_fields(b2_sim* sim, int which);
+const char* b2_field_name(b2_sim* sim, int which, int index);
+
+/* Tile a Model field to a real leading nworld dimension (reference randomization.py:20-55). */
+int b2_expand_model_field(b2_sim* sim, const char* name, void* cuda_stream, B2Tensor* out);
+
+/* Options: "iterations", "ls_iterations", "tolerance", "ls_tolerance", "ls_parallel",
+ * "timestep", "integrator", "debug_outputs". */
+int b2_set_option(b2_sim* sim, const char* key, double value);
+int b2_get_option(b2_sim* sim, const char* key, double* value);
+
+/* The hot path. */
+int b2_step(b2_sim* sim, void* cuda_stream);              /* mjwarp.step    */
+int b2_forward(b2_sim* sim, void* cuda_stream);           /* mjwarp.forward */
+int b2_step_n(b2_sim* sim, int n, void* cuda_stream);     /* n sub-steps with ctrl held (decimation) */
+
+/* End-to-end call with HOST buffers (pinned or pageable): copies `ctrl` (nworld*nu floats, row
+ * stride nu) to the device, runs `nsubstep` steps, copies qpos (nworld*nq) and qvel (nworld*nv)
+ * back; asynchronous on `cuda_stream` when the host buffers are pinned. NULL outputs are skipped. */
+int b2_step_host(b2_sim* sim, const float* ctrl_host, int nsubstep, float* qpos_host,
+                 float* qvel_host, void* cuda_stream);
+
+/* Diagnostics (synchronises `cuda_stream`). */
+int b2_stats(b2_sim* sim, void* cuda_stream, B2Stats* out);
+/* Number of kernels this library has launched for `sim` since creation. */
+int64_t b2_launch_count(b2_sim* sim);
+/* Algorithmic bytes of one step for the roofline: solver stage and whole step,
+ * evaluated with the mean nefc of the last step. */
+int b2_algorithmic_bytes(b2_sim* sim, void* cuda_stream, double* solver_bytes, double* step_bytes);
+
+const char* b2_last_error(void);
+const char* b2_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2SIM_H_ */

@@ -1,0 +1,1447 @@
+// b2_kernel.cuh — fused batched forward-dynamics step, one warp per environment (sm_100a).
+//
+// Replaces mjwarp.step / mjwarp.forward (reference call sites src/mjlab/sim/sim.py:136,139,187,195;
+// pipeline order per SURVEY.md Appendix A.1).  Design:
+//   * one warp owns one environment for the whole step; 4 warps per CTA, no block-level barriers;
+//   * the environment's state vectors are bulk-copied global->shared with cp.async.bulk + mbarrier
+//     (TMA 1-D) and every intermediate (poses, spatial inertias, joint-space inertia, contacts,
+//     solver scratch) lives in that warp's shared-memory block — nothing but inputs/outputs touches HBM;
+//   * the constraint Jacobian is never materialised: contacts of one body pair share a 6x6 block
+//     A_g = sum_c S_c W_c S_c^T that is projected through the motion vectors (cdof) of the dofs
+//     between the two bodies, so H = M + J^T D J, J v and J^T f cost O(ndof_chain^2) per body pair;
+//   * Newton with exact 1-D line search, dense packed Cholesky with a balanced (i,j)-pair schedule.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "b2_types.h"
+
+#define FULL 0xffffffffu
+#define MINVAL 1e-15f
+#define MINIMP 0.0001f
+#define MAXIMP 0.9999f
+#define MINMU 1e-5f
+
+namespace b2 {
+
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ float dot3(const float* a, const float* b) {
+  return a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+}
+__device__ __forceinline__ void cross3(float* r, const float* a, const float* b) {
+  float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+__device__ __forceinline__ float normalize3(float* a) {
+  float n = sqrtf(dot3(a, a));
+  if (n < MINVAL) { a[0] = 1.f; a[1] = 0.f; a[2] = 0.f; return n; }
+  float inv = 1.f / n;
+  a[0] *= inv; a[1] *= inv; a[2] *= inv;
+  return n;
+}
+__device__ __forceinline__ void normalize4(float* q) {
+  float n = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  if (n < MINVAL) { q[0] = 1.f; q[1] = q[2] = q[3] = 0.f; return; }
+  float inv = 1.f / n;
+  q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv;
+}
+__device__ __forceinline__ void mulquat(float* r, const float* a, const float* b) {
+  float w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  float x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  float y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  float z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  r[0] = w; r[1] = x; r[2] = y; r[3] = z;
+}
+// r = R(q) v
+__device__ __forceinline__ void rotq(float* r, const float* q, const float* v) {
+  float t[3], u[3];
+  cross3(t, q + 1, v);
+  t[0] *= 2.f; t[1] *= 2.f; t[2] *= 2.f;
+  cross3(u, q + 1, t);
+  r[0] = v[0] + q[0] * t[0] + u[0];
+  r[1] = v[1] + q[0] * t[1] + u[1];
+  r[2] = v[2] + q[0] * t[2] + u[2];
+}
+__device__ __forceinline__ void quat2mat(float* m, const float* q) {
+  float q00 = q[0] * q[0], q11 = q[1] * q[1], q22 = q[2] * q[2], q33 = q[3] * q[3];
+  float q01 = q[0] * q[1], q02 = q[0] * q[2], q03 = q[0] * q[3];
+  float q12 = q[1] * q[2], q13 = q[1] * q[3], q23 = q[2] * q[3];
+  m[0] = q00 + q11 - q22 - q33; m[4] = q00 - q11 + q22 - q33; m[8] = q00 - q11 - q22 + q33;
+  m[1] = 2.f * (q12 - q03); m[2] = 2.f * (q13 + q02);
+  m[3] = 2.f * (q12 + q03); m[5] = 2.f * (q23 - q01);
+  m[6] = 2.f * (q13 - q02); m[7] = 2.f * (q23 + q01);
+}
+__device__ __forceinline__ void mul_inert_vec(float* r, const float* i, const float* v) {
+  r[0] = i[0] * v[0] + i[3] * v[1] + i[4] * v[2] - i[8] * v[4] + i[7] * v[5];
+  r[1] = i[3] * v[0] + i[1] * v[1] + i[5] * v[2] + i[8] * v[3] - i[6] * v[5];
+  r[2] = i[4] * v[0] + i[5] * v[1] + i[2] * v[2] - i[7] * v[3] + i[6] * v[4];
+  r[3] = i[8] * v[1] - i[7] * v[2] + i[9] * v[3];
+  r[4] = i[6] * v[2] - i[8] * v[0] + i[9] * v[4];
+  r[5] = i[7] * v[0] - i[6] * v[1] + i[9] * v[5];
+}
+__device__ __forceinline__ void cross_motion(float* r, const float* vel, const float* v) {
+  r[0] = -vel[2] * v[1] + vel[1] * v[2];
+  r[1] = vel[2] * v[0] - vel[0] * v[2];
+  r[2] = -vel[1] * v[0] + vel[0] * v[1];
+  r[3] = -vel[2] * v[4] + vel[1] * v[5] - vel[5] * v[1] + vel[4] * v[2];
+  r[4] = vel[2] * v[3] - vel[0] * v[5] + vel[5] * v[0] - vel[3] * v[2];
+  r[5] = -vel[1] * v[3] + vel[0] * v[4] - vel[4] * v[0] + vel[3] * v[1];
+}
+__device__ __forceinline__ void cross_force(float* r, const float* vel, const float* f) {
+  r[0] = -vel[2] * f[1] + vel[1] * f[2] - vel[5] * f[4] + vel[4] * f[5];
+  r[1] = vel[2] * f[0] - vel[0] * f[2] + vel[5] * f[3] - vel[3] * f[5];
+  r[2] = -vel[1] * f[0] + vel[0] * f[1] - vel[4] * f[3] + vel[3] * f[4];
+  r[3] = -vel[2] * f[4] + vel[1] * f[5];
+  r[4] = vel[2] * f[3] - vel[0] * f[5];
+  r[5] = -vel[1] * f[3] + vel[0] * f[4];
+}
+__device__ __forceinline__ float dot6(const float* a, const float* b) {
+  return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
+}
+__device__ __forceinline__ int tri(int i, int j) { return (i * (i + 1) >> 1) + j; }  // j <= i
+
+// ---- TMA 1-D bulk copy + mbarrier (PTX) -------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes,
+                                         unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+               "r"(smem_u32(src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+#define MP(arr) (m.arr.p + (size_t)w * m.arr.stride)
+
+// ---- dense packed Cholesky (lower, row-major packed) in shared memory ---------------------------
+// Balanced schedule: the trailing-triangle update of step k runs over a precomputed list of (i,j)
+// pairs ordered by descending j, so every lane gets the same number of pairs.
+__device__ __forceinline__ void chol_factor(float* A, float* invdiag, int n, int ntri,
+                                            const unsigned short* __restrict__ coldesc, int lane) {
+  for (int k = 0; k < n; k++) {
+    float akk = A[tri(k, k)];
+    float d = sqrtf(fmaxf(akk, MINVAL));
+    float inv = 1.f / d;
+    for (int i = k + 1 + lane; i < n; i += 32) A[tri(i, k)] *= inv;
+    if (lane == 0) { A[tri(k, k)] = d; invdiag[k] = inv; }
+    __syncwarp();
+    int mtr = n - k - 1;
+    int np = mtr * (mtr + 1) >> 1;
+    for (int p = lane; p < np; p += 32) {
+      unsigned short e = coldesc[p];
+      int i = e & 0xff, j = e >> 8;
+      A[tri(i, j)] -= A[tri(i, k)] * A[tri(j, k)];
+    }
+    __syncwarp();
+  }
+  (void)ntri;
+}
+// x <- (L L^T)^-1 x, x in shared memory (n <= 64). Values are held in registers during the sweeps.
+__device__ __forceinline__ void chol_solve(const float* L, const float* invdiag, float* x, int n,
+                                           int lane) {
+  float x0 = lane < n ? x[lane] : 0.f;
+  float x1 = lane + 32 < n ? x[lane + 32] : 0.f;
+  for (int k = 0; k < n; k++) {
+    float xk = __shfl_sync(FULL, k < 32 ? x0 : x1, k & 31) * invdiag[k];
+    if (lane == k) x0 = xk;
+    if (lane + 32 == k) x1 = xk;
+    if (lane > k && lane < n) x0 -= L[tri(lane, k)] * xk;
+    if (lane + 32 > k && lane + 32 < n) x1 -= L[tri(lane + 32, k)] * xk;
+  }
+  for (int k = n - 1; k >= 0; k--) {
+    float xk = __shfl_sync(FULL, k < 32 ? x0 : x1, k & 31) * invdiag[k];
+    if (lane == k) x0 = xk;
+    if (lane + 32 == k) x1 = xk;
+    if (lane < k) x0 -= L[tri(k, lane)] * xk;
+    if (lane + 32 < k) x1 -= L[tri(k, lane + 32)] * xk;
+  }
+  if (lane < n) x[lane] = x0;
+  if (lane + 32 < n) x[lane + 32] = x1;
+  __syncwarp();
+}
+// y = M x for packed symmetric M (both in shared memory)
+__device__ __forceinline__ void symv(const float* M, const float* x, float* y, int n, int lane) {
+  for (int i = lane; i < n; i += 32) {
+    float t = 0.f;
+    for (int j = 0; j <= i; j++) t += M[tri(i, j)] * x[j];
+    for (int j = i + 1; j < n; j++) t += M[tri(j, i)] * x[j];
+    y[i] = t;
+  }
+  __syncwarp();
+}
+
+// ---- narrowphase primitives (engine_collision_primitive.c semantics) ----
+struct RawCon {
+  float dist, pos[3], n[3], yh[3];
+};
+__device__ __forceinline__ int sphere_sphere(RawCon& c, float margin, const float* p1, float r1,
+                                             const float* p2, float r2) {
+  float dif[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+  float cd = sqrtf(dot3(dif, dif));
+  if (cd > margin + r1 + r2) return 0;
+  c.dist = cd - r1 - r2;
+  normalize3(dif);
+  for (int k = 0; k < 3; k++) {
+    c.n[k] = dif[k];
+    c.pos[k] = p1[k] + dif[k] * (r1 + 0.5f * c.dist);
+    c.yh[k] = 0.f;
+  }
+  return 1;
+}
+__device__ __forceinline__ int plane_sphere(RawCon& c, float margin, const float* pp, const float* pn,
+                                            const float* sp, float r) {
+  float dif[3] = {sp[0] - pp[0], sp[1] - pp[1], sp[2] - pp[2]};
+  float cd = dot3(dif, pn);
+  if (cd > margin + r) return 0;
+  c.dist = cd - r;
+  for (int k = 0; k < 3; k++) {
+    c.n[k] = pn[k];
+    c.pos[k] = sp[k] - pn[k] * (r + 0.5f * c.dist);
+    c.yh[k] = 0.f;
+  }
+  return 1;
+}
+__device__ __forceinline__ void make_frame(float* f /*9: n, yhint -> n,t1,t2*/) {
+  normalize3(f);
+  if (sqrtf(dot3(f + 3, f + 3)) < 0.5f) {
+    f[3] = f[4] = f[5] = 0.f;
+    if (f[1] < 0.5f && f[1] > -0.5f) f[4] = 1.f; else f[5] = 1.f;
+  }
+  float t = dot3(f, f + 3);
+  f[3] -= t * f[0]; f[4] -= t * f[1]; f[5] -= t * f[2];
+  normalize3(f + 3);
+  cross3(f + 6, f, f + 3);
+}
+
+}  // namespace b2
+
+// ==================================================================================================
+// The kernel
+// ==================================================================================================
+template <bool STEP>
+__global__ void __launch_bounds__(32 * B2_WARPS_PER_CTA, 2)
+b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevData dd) {
+  using namespace b2;
+  extern __shared__ __align__(16) float smem_all[];
+  __shared__ __align__(8) unsigned long long bars[B2_WARPS_PER_CTA];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * B2_WARPS_PER_CTA + warp;
+  if (w >= dd.nworld) return;
+  const Layout& L = m.lay;
+  float* s = smem_all + (size_t)warp * L.total;
+  const int nq = m.nq, nv = m.nv, nu = m.nu, nb = m.nbody, njnt = m.njnt;
+  const int MC = L.maxcon, NLC = L.nlimcap;
+
+  // ---------------- phase 0: TMA bulk load of this environment's state -------------------------
+  float* qpos = s + L.qpos; float* qvel = s + L.qvel; float* ctrl = s + L.ctrl;
+  float* qacc_ws = s + L.qacc_ws; float* qfrc_applied = s + L.qfrc_applied; float* xfrc = s + L.xfrc;
+  {
+    unsigned long long* bar = &bars[warp];
+    if (lane == 0) {
+      mbar_init(bar, 1);
+      uint32_t bytes = 4u * (dd.qpos.stride + dd.qvel.stride + dd.ctrl.stride +
+                             dd.qacc_warmstart.stride + dd.qfrc_applied.stride + dd.xfrc_applied.stride);
+      mbar_expect(bar, bytes);
+      bulk_g2s(qpos, dd.qpos.p + (size_t)w * dd.qpos.stride, 4u * dd.qpos.stride, bar);
+      bulk_g2s(qvel, dd.qvel.p + (size_t)w * dd.qvel.stride, 4u * dd.qvel.stride, bar);
+      if (dd.ctrl.stride) bulk_g2s(ctrl, dd.ctrl.p + (size_t)w * dd.ctrl.stride, 4u * dd.ctrl.stride, bar);
+      bulk_g2s(qacc_ws, dd.qacc_warmstart.p + (size_t)w * dd.qacc_warmstart.stride, 4u * dd.qacc_warmstart.stride, bar);
+      bulk_g2s(qfrc_applied, dd.qfrc_applied.p + (size_t)w * dd.qfrc_applied.stride, 4u * dd.qfrc_applied.stride, bar);
+      bulk_g2s(xfrc, dd.xfrc_applied.p + (size_t)w * dd.xfrc_applied.stride, 4u * dd.xfrc_applied.stride, bar);
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+  }
+
+  float* xpos = s + L.xpos; float* xquat = s + L.xquat; float* xipos = s + L.xipos;
+  float* scom = s + L.scom; float* xanchor = s + L.xanchor; float* xaxis = s + L.xaxis;
+  float* cinert = s + L.cinert; float* crb = s + L.crb; float* cdof = s + L.cdof;
+  float* cdofdot = s + L.cdofdot; float* cvel = s + L.cvel; float* cacc = s + L.cacc;
+  float* Mq = s + L.M; float* H = s + L.H; float* invdiag = s + L.invdiag;
+  float* qfrc_smooth = s + L.qfrc_smooth; float* qacc_smooth = s + L.qacc_smooth;
+  float* qacc = s + L.qacc; float* Ma = s + L.Ma; float* grad = s + L.grad;
+  float* search = s + L.search; float* Mv = s + L.Mv; float* qfrc_c = s + L.qfrc_c;
+  float* tmpv = s + L.tmpv; float* actf = s + L.actf;
+
+  // ---------------- phase 1: kinematics (lane per body, private walk down its ancestor chain) ----
+  {
+    const float* body_pos = MP(body_pos); const float* body_quat = MP(body_quat);
+    const float* jnt_pos = MP(jnt_pos); const float* jnt_axis = MP(jnt_axis);
+    const float* qpos0 = MP(qpos0);
+    const float* body_ipos = MP(body_ipos);
+    for (int b = lane; b < nb; b += 32) {
+      float pos[3] = {0.f, 0.f, 0.f}, quat[4] = {1.f, 0.f, 0.f, 0.f};
+      int depth = m.body_depth[b];
+      for (int k = 0; k < depth; k++) {
+        int c = m.body_chain[b * m.maxdepth + k];
+        int jn = m.body_jntnum[c], ja = m.body_jntadr[c];
+        bool last = (k == depth - 1);
+        if (jn == 1 && m.jnt_type[ja] == JNT_FREE) {
+          int a = m.jnt_qposadr[ja];
+          pos[0] = qpos[a]; pos[1] = qpos[a + 1]; pos[2] = qpos[a + 2];
+          quat[0] = qpos[a + 3]; quat[1] = qpos[a + 4]; quat[2] = qpos[a + 5]; quat[3] = qpos[a + 6];
+          normalize4(quat);
+          if (last) {
+            xanchor[3 * ja] = pos[0]; xanchor[3 * ja + 1] = pos[1]; xanchor[3 * ja + 2] = pos[2];
+            float ax[3]; rotq(ax, quat, jnt_axis + 3 * ja);
+            xaxis[3 * ja] = ax[0]; xaxis[3 * ja + 1] = ax[1]; xaxis[3 * ja + 2] = ax[2];
+          }
+        } else {
+          float t[3], q2[4];
+          rotq(t, quat, body_pos + 3 * c);
+          pos[0] += t[0]; pos[1] += t[1]; pos[2] += t[2];
+          mulquat(q2, quat, body_quat + 4 * c);
+          quat[0] = q2[0]; quat[1] = q2[1]; quat[2] = q2[2]; quat[3] = q2[3];
+          for (int j = ja; j < ja + jn; j++) {
+            float anchor[3], axis[3];
+            rotq(anchor, quat, jnt_pos + 3 * j);
+            anchor[0] += pos[0]; anchor[1] += pos[1]; anchor[2] += pos[2];
+            rotq(axis, quat, jnt_axis + 3 * j);
+            if (last) {
+              xanchor[3 * j] = anchor[0]; xanchor[3 * j + 1] = anchor[1]; xanchor[3 * j + 2] = anchor[2];
+              xaxis[3 * j] = axis[0]; xaxis[3 * j + 1] = axis[1]; xaxis[3 * j + 2] = axis[2];
+            }
+            int qa = m.jnt_qposadr[j];
+            float dq = qpos[qa] - qpos0[qa];
+            if (m.jnt_type[j] == JNT_SLIDE) {
+              pos[0] += axis[0] * dq; pos[1] += axis[1] * dq; pos[2] += axis[2] * dq;
+            } else {
+              float sn, cs;
+              sincosf(0.5f * dq, &sn, &cs);
+              float ql[4] = {cs, jnt_axis[3 * j] * sn, jnt_axis[3 * j + 1] * sn, jnt_axis[3 * j + 2] * sn};
+              mulquat(q2, quat, ql);
+              quat[0] = q2[0]; quat[1] = q2[1]; quat[2] = q2[2]; quat[3] = q2[3];
+              rotq(t, quat, jnt_pos + 3 * j);
+              pos[0] = anchor[0] - t[0]; pos[1] = anchor[1] - t[1]; pos[2] = anchor[2] - t[2];
+            }
+          }
+        }
+        normalize4(quat);
+      }
+      xpos[3 * b] = pos[0]; xpos[3 * b + 1] = pos[1]; xpos[3 * b + 2] = pos[2];
+      xquat[4 * b] = quat[0]; xquat[4 * b + 1] = quat[1]; xquat[4 * b + 2] = quat[2]; xquat[4 * b + 3] = quat[3];
+      float t[3], mat[9];
+      rotq(t, quat, body_ipos + 3 * b);
+      xipos[3 * b] = pos[0] + t[0]; xipos[3 * b + 1] = pos[1] + t[1]; xipos[3 * b + 2] = pos[2] + t[2];
+      quat2mat(mat, quat);
+      float* gx = dd.xmat.p + (size_t)w * dd.xmat.stride + 9 * b;
+#pragma unroll
+      for (int k = 0; k < 9; k++) gx[k] = mat[k];
+    }
+  }
+  __syncwarp();
+
+  // geom / site world poses -> global (and shared for collidable geoms)
+  float* gpose = s + L.gpose;
+  {
+    const float* geom_pos = MP(geom_pos); const float* geom_quat = MP(geom_quat);
+    float* gxp = dd.geom_xpos.p + (size_t)w * dd.geom_xpos.stride;
+    float* gxm = dd.geom_xmat.p + (size_t)w * dd.geom_xmat.stride;
+    for (int g = lane; g < m.ngeom; g += 32) {
+      int b = m.geom_bodyid[g];
+      float p[3], q[4], mat[9];
+      rotq(p, xquat + 4 * b, geom_pos + 3 * g);
+      p[0] += xpos[3 * b]; p[1] += xpos[3 * b + 1]; p[2] += xpos[3 * b + 2];
+      mulquat(q, xquat + 4 * b, geom_quat + 4 * g);
+      quat2mat(mat, q);
+      gxp[3 * g] = p[0]; gxp[3 * g + 1] = p[1]; gxp[3 * g + 2] = p[2];
+#pragma unroll
+      for (int k = 0; k < 9; k++) gxm[9 * g + k] = mat[k];
+      int cs = m.geom_cslot[g];
+      if (cs >= 0) {
+        float* gp = gpose + 12 * cs;
+        gp[0] = p[0]; gp[1] = p[1]; gp[2] = p[2];
+#pragma unroll
+        for (int k = 0; k < 9; k++) gp[3 + k] = mat[k];
+      }
+    }
+    const float* site_pos = MP(site_pos); const float* site_quat = MP(site_quat);
+    float* sxp = dd.site_xpos.p + (size_t)w * dd.site_xpos.stride;
+    float* sxm = dd.site_xmat.p + (size_t)w * dd.site_xmat.stride;
+    for (int g = lane; g < m.nsite; g += 32) {
+      int b = m.site_bodyid[g];
+      float p[3], q[4], mat[9];
+      rotq(p, xquat + 4 * b, site_pos + 3 * g);
+      mulquat(q, xquat + 4 * b, site_quat + 4 * g);
+      quat2mat(mat, q);
+      sxp[3 * g] = p[0] + xpos[3 * b]; sxp[3 * g + 1] = p[1] + xpos[3 * b + 1]; sxp[3 * g + 2] = p[2] + xpos[3 * b + 2];
+#pragma unroll
+      for (int k = 0; k < 9; k++) sxm[9 * g + k] = mat[k];
+    }
+  }
+
+  // ---------------- phase 2: subtree com, spatial inertias, motion vectors -----------------------
+  {
+    const float* mass = MP(body_mass); const float* sub = MP(body_subtreemass);
+    for (int b = lane; b < nb; b += 32) {
+      float acc[3] = {0.f, 0.f, 0.f};
+      for (int d = 0; d < nb; d++) {
+        if (m.body_ancmask[d] >> b & 1ull) {
+          float md = mass[d];
+          acc[0] += md * xipos[3 * d]; acc[1] += md * xipos[3 * d + 1]; acc[2] += md * xipos[3 * d + 2];
+        }
+      }
+      if (sub[b] < MINVAL) { acc[0] = xipos[3 * b]; acc[1] = xipos[3 * b + 1]; acc[2] = xipos[3 * b + 2]; }
+      else { float inv = 1.f / sub[b]; acc[0] *= inv; acc[1] *= inv; acc[2] *= inv; }
+      scom[3 * b] = acc[0]; scom[3 * b + 1] = acc[1]; scom[3 * b + 2] = acc[2];
+    }
+  }
+  __syncwarp();
+  // Internal reference point c0 = com of the whole world (subtree_com[0]); all cdof / cinert / cvel
+  // are expressed about c0 (MuJoCo uses subtree_com[root]; results are identical, cvel is converted
+  // on output).
+  const float c0[3] = {scom[0], scom[1], scom[2]};
+  {
+    const float* mass = MP(body_mass); const float* inertia = MP(body_inertia);
+    const float* body_iquat = MP(body_iquat);
+    for (int b = lane; b < nb; b += 32) {
+      float q[4], mat[9], dif[3];
+      mulquat(q, xquat + 4 * b, body_iquat + 4 * b);
+      quat2mat(mat, q);
+      dif[0] = xipos[3 * b] - c0[0]; dif[1] = xipos[3 * b + 1] - c0[1]; dif[2] = xipos[3 * b + 2] - c0[2];
+      float ms = mass[b];
+      const float* in = inertia + 3 * b;
+      float t[9];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+          t[3 * i + j] = mat[3 * i] * in[0] * mat[3 * j] + mat[3 * i + 1] * in[1] * mat[3 * j + 1] +
+                         mat[3 * i + 2] * in[2] * mat[3 * j + 2];
+      float* ci = cinert + 10 * b;
+      if (b == 0) {
+#pragma unroll
+        for (int k = 0; k < 10; k++) ci[k] = 0.f;
+      } else {
+        ci[0] = t[0] + ms * (dif[1] * dif[1] + dif[2] * dif[2]);
+        ci[1] = t[4] + ms * (dif[0] * dif[0] + dif[2] * dif[2]);
+        ci[2] = t[8] + ms * (dif[0] * dif[0] + dif[1] * dif[1]);
+        ci[3] = t[1] - ms * dif[0] * dif[1];
+        ci[4] = t[2] - ms * dif[0] * dif[2];
+        ci[5] = t[5] - ms * dif[1] * dif[2];
+        ci[6] = ms * dif[0]; ci[7] = ms * dif[1]; ci[8] = ms * dif[2]; ci[9] = ms;
+      }
+    }
+    for (int j = lane; j < njnt; j += 32) {
+      int b = m.jnt_bodyid[j], da = m.jnt_dofadr[j], ty = m.jnt_type[j];
+      float off[3] = {c0[0] - xanchor[3 * j], c0[1] - xanchor[3 * j + 1], c0[2] - xanchor[3 * j + 2]};
+      if (ty == JNT_FREE) {
+        float mat[9];
+        quat2mat(mat, xquat + 4 * b);
+        for (int k = 0; k < 3; k++) {
+          float* c = cdof + 6 * (da + k);
+          c[0] = c[1] = c[2] = 0.f; c[3] = c[4] = c[5] = 0.f; c[3 + k] = 1.f;
+          float ax[3] = {mat[k], mat[3 + k], mat[6 + k]};
+          float* r = cdof + 6 * (da + 3 + k);
+          r[0] = ax[0]; r[1] = ax[1]; r[2] = ax[2];
+          cross3(r + 3, ax, off);
+        }
+      } else if (ty == JNT_SLIDE) {
+        float* c = cdof + 6 * da;
+        c[0] = c[1] = c[2] = 0.f;
+        c[3] = xaxis[3 * j]; c[4] = xaxis[3 * j + 1]; c[5] = xaxis[3 * j + 2];
+      } else {
+        float* c = cdof + 6 * da;
+        c[0] = xaxis[3 * j]; c[1] = xaxis[3 * j + 1]; c[2] = xaxis[3 * j + 2];
+        cross3(c + 3, xaxis + 3 * j, off);
+      }
+    }
+  }
+  __syncwarp();
+
+  // ---------------- phase 3: composite inertias -> joint-space inertia M (packed lower) ----------
+  for (int b = lane; b < nb; b += 32) {
+    float acc[10];
+#pragma unroll
+    for (int k = 0; k < 10; k++) acc[k] = 0.f;
+    for (int d = 1; d < nb; d++) {
+      if (m.body_ancmask[d] >> b & 1ull) {
+#pragma unroll
+        for (int k = 0; k < 10; k++) acc[k] += cinert[10 * d + k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 10; k++) crb[10 * b + k] = acc[k];
+  }
+  for (int i = lane; i < m.ntri; i += 32) Mq[i] = 0.f;
+  __syncwarp();
+  {
+    const float* arm = MP(dof_armature);
+    for (int i = lane; i < nv; i += 32) {
+      float buf[6];
+      mul_inert_vec(buf, crb + 10 * m.dof_bodyid[i], cdof + 6 * i);
+      for (int j = i; j >= 0; j = m.dof_parentid[j]) Mq[tri(i, j)] = dot6(cdof + 6 * j, buf);
+      Mq[tri(i, i)] += arm[i];
+    }
+  }
+  __syncwarp();
+
+  // ---------------- phase 4: velocities, bias forces, actuation, qfrc_smooth ----------------------
+  for (int b = lane; b < nb; b += 32) {
+    float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, snap[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    unsigned long long mask = m.body_dofmask[b];
+    int own0 = m.body_dofadr[b];
+    while (mask) {
+      int d = __ffsll((long long)mask) - 1;
+      mask &= mask - 1;
+      const float* c = cdof + 6 * d;
+      if (own0 >= 0 && d >= own0) {
+        int j = m.dof_jntid[d];
+        int off = d - m.jnt_dofadr[j];
+        float* cd = cdofdot + 6 * d;
+        if (m.jnt_type[j] == JNT_FREE) {
+          if (off < 3) { cd[0] = cd[1] = cd[2] = cd[3] = cd[4] = cd[5] = 0.f; }
+          else {
+            if (off == 3) { for (int k = 0; k < 6; k++) snap[k] = v[k]; }
+            cross_motion(cd, snap, c);
+          }
+        } else cross_motion(cd, v, c);
+      }
+      float qd = qvel[d];
+#pragma unroll
+      for (int k = 0; k < 6; k++) v[k] += c[k] * qd;
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) cvel[6 * b + k] = v[k];
+    // output cvel in MuJoCo's convention: linear part at subtree_com[root]
+    int r = m.body_rootid[b];
+    float dr[3] = {scom[3 * r] - c0[0], scom[3 * r + 1] - c0[1], scom[3 * r + 2] - c0[2]}, t[3];
+    cross3(t, v, dr);
+    float* gc = dd.cvel.p + (size_t)w * dd.cvel.stride + 6 * b;
+    gc[0] = v[0]; gc[1] = v[1]; gc[2] = v[2];
+    gc[3] = v[3] + t[0]; gc[4] = v[4] + t[1]; gc[5] = v[5] + t[2];
+  }
+  __syncwarp();
+  for (int b = lane; b < nb; b += 32) {
+    float a[6] = {0.f, 0.f, 0.f, -m.gravity[0], -m.gravity[1], -m.gravity[2]};
+    unsigned long long mask = m.body_dofmask[b];
+    while (mask) {
+      int d = __ffsll((long long)mask) - 1;
+      mask &= mask - 1;
+      float qd = qvel[d];
+#pragma unroll
+      for (int k = 0; k < 6; k++) a[k] += cdofdot[6 * d + k] * qd;
+    }
+    float t[6], t1[6], t2[6];
+    mul_inert_vec(t, cinert + 10 * b, cvel + 6 * b);
+    cross_force(t1, cvel + 6 * b, t);
+    mul_inert_vec(t2, cinert + 10 * b, a);
+    // net external wrench on the body about c0: xfrc_applied (force at xipos) minus bias wrench
+    const float* xf = xfrc + 6 * b;
+    float arm[3] = {xipos[3 * b] - c0[0], xipos[3 * b + 1] - c0[1], xipos[3 * b + 2] - c0[2]}, tq[3];
+    cross3(tq, arm, xf);
+    float* cf = cacc + 6 * b;  // region reused: [bias wrench]
+    float* cx = crb + 6 * b;   // region reused: [applied wrench]
+    if (b == 0) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) { cf[k] = 0.f; cx[k] = 0.f; }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 6; k++) cf[k] = t2[k] + t1[k];
+      cx[0] = tq[0] + xf[3]; cx[1] = tq[1] + xf[4]; cx[2] = tq[2] + xf[5];
+      cx[3] = xf[0]; cx[4] = xf[1]; cx[5] = xf[2];
+    }
+  }
+  for (int i = lane; i < nv; i += 32) tmpv[i] = 0.f;  // qfrc_actuator
+  __syncwarp();
+  {
+    const float* gp = MP(actuator_gainprm); const float* bp = MP(actuator_biasprm);
+    const float* cr = MP(actuator_ctrlrange); const float* fr = MP(actuator_forcerange);
+    const float* gear = MP(actuator_gear);
+    float* gaf = dd.actuator_force.p + (size_t)w * dd.actuator_force.stride;
+    for (int a = lane; a < nu; a += 32) {
+      int j = m.actuator_trnid[a];
+      float g = gear[a];
+      float len = qpos[m.jnt_qposadr[j]] * g, vel = qvel[m.jnt_dofadr[j]] * g;
+      float c = ctrl[a];
+      if (m.actuator_ctrllimited[a]) c = fminf(fmaxf(c, cr[2 * a]), cr[2 * a + 1]);
+      float f = gp[10 * a] * c + bp[10 * a] + bp[10 * a + 1] * len + bp[10 * a + 2] * vel;
+      if (m.actuator_forcelimited[a]) f = fminf(fmaxf(f, fr[2 * a]), fr[2 * a + 1]);
+      actf[a] = f;
+      gaf[a] = f;
+      atomicAdd(&tmpv[m.jnt_dofadr[j]], g * f);  // one actuator per dof in practice; exact either way
+    }
+  }
+  __syncwarp();
+  {
+    const float* damp = MP(dof_damping); const float* stiff = MP(jnt_stiffness);
+    const float* qpos0 = MP(qpos0);
+    for (int i = lane; i < nv; i += 32) {
+      float sb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, sx[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int b = 1; b < nb; b++) {
+        if (m.body_dofmask[b] >> i & 1ull) {
+#pragma unroll
+          for (int k = 0; k < 6; k++) { sb[k] += cacc[6 * b + k]; sx[k] += crb[6 * b + k]; }
+        }
+      }
+      float bias = dot6(cdof + 6 * i, sb);
+      float passive = -damp[i] * qvel[i];
+      int j = m.dof_jntid[i];
+      if (m.jnt_type[j] != JNT_FREE && stiff[j] != 0.f)
+        passive -= stiff[j] * (qpos[m.jnt_qposadr[j]] - qpos0[m.jnt_qposadr[j]]);
+      float fs = passive - bias + qfrc_applied[i] + tmpv[i] + dot6(cdof + 6 * i, sx);
+      qfrc_smooth[i] = fs;
+      qacc_smooth[i] = fs;
+      if (m.debug) {
+        dd.qfrc_bias.p[(size_t)w * dd.qfrc_bias.stride + i] = bias;
+        dd.qfrc_smooth.p[(size_t)w * dd.qfrc_smooth.stride + i] = fs;
+      }
+    }
+  }
+  __syncwarp();
+  if (m.debug) {
+    float* gM = dd.qM.p + (size_t)w * dd.qM.stride;
+    for (int p = lane; p < nv * nv; p += 32) {
+      int i = p / nv, j = p % nv;
+      gM[p] = i >= j ? Mq[tri(i, j)] : Mq[tri(j, i)];
+    }
+  }
+
+  // ---------------- phase 5: collision (static pair table, bounding-sphere filter, primitives) ----
+  float* con = s + L.contacts;   // overlays the smooth-only regions (cinert, crb, cdofdot, cacc, ...)
+  float* lim = s + L.limits;
+  int* gstart = (int*)(s + L.gstart);
+  unsigned* gmask_lo = (unsigned*)(s + L.gmask_lo);
+  unsigned* gmask_hi = (unsigned*)(s + L.gmask_hi);
+  int ncon = 0, overflow = 0;
+  {
+    int* pairlist = (int*)(s + L.pairlist);
+    const float* rb = MP(geom_rbound); const float* gmar = MP(geom_margin);
+    int ncand = 0;
+    for (int p0 = 0; p0 < m.npair; p0 += 32) {
+      int p = p0 + lane;
+      bool hit = false;
+      if (p < m.npair) {
+        int g1 = m.pair_geom1[p], g2 = m.pair_geom2[p];
+        const float* a = gpose + 12 * m.geom_cslot[g1];
+        const float* b = gpose + 12 * m.geom_cslot[g2];
+        float margin = fmaxf(gmar[g1], gmar[g2]);
+        float dif[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+        if (m.geom_type[g1] == G_PLANE) {
+          float n[3] = {a[3 + 2], a[3 + 5], a[3 + 8]};
+          hit = dot3(dif, n) <= margin + rb[g2];
+        } else {
+          float bound = margin + rb[g1] + rb[g2];
+          hit = dot3(dif, dif) <= bound * bound;
+        }
+      }
+      unsigned bal = __ballot_sync(FULL, hit);
+      if (hit) {
+        int slot = ncand + __popc(bal & ((1u << lane) - 1u));
+        if (slot < L.maxpair) pairlist[slot] = p;
+      }
+      ncand += __popc(bal);
+    }
+    if (ncand > L.maxpair) { ncand = L.maxpair; overflow = 1; }
+    __syncwarp();
+    const float* gsize = MP(geom_size); const float* ggap = MP(geom_gap);
+    const float* gfri = MP(geom_friction); const float* gsolref = MP(geom_solref);
+    const float* gsolimp = MP(geom_solimp); const float* gsolmix = MP(geom_solmix);
+    const float* inv = MP(body_invweight0);
+    float* g_dist = dd.contact_dist.p + (size_t)w * dd.contact_dist.stride;
+    float* g_pos = dd.contact_pos.p + (size_t)w * dd.contact_pos.stride;
+    float* g_frame = dd.contact_frame.p + (size_t)w * dd.contact_frame.stride;
+    int* g_geom = dd.contact_geom.p + (size_t)w * dd.contact_geom.stride;
+    for (int q0 = 0; q0 < ncand; q0 += 32) {
+      int qi = q0 + lane;
+      RawCon rc[4];
+      int n = 0, g1 = 0, g2 = 0;
+      float margin = 0.f;
+      if (qi < ncand) {
+        int p = pairlist[qi];
+        g1 = m.pair_geom1[p]; g2 = m.pair_geom2[p];
+        int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
+        const float* a = gpose + 12 * m.geom_cslot[g1];
+        const float* b = gpose + 12 * m.geom_cslot[g2];
+        margin = fmaxf(gmar[g1], gmar[g2]);
+        const float* s1 = gsize + 3 * g1; const float* s2 = gsize + 3 * g2;
+        if (t1 == G_PLANE) {
+          float pn[3] = {a[3 + 2], a[3 + 5], a[3 + 8]};
+          if (t2 == G_SPHERE) n = plane_sphere(rc[0], margin, a, pn, b, s2[0]);
+          else if (t2 == G_CAPSULE) {
+            float ax[3] = {b[3 + 2], b[3 + 5], b[3 + 8]}, e[3];
+            e[0] = b[0] + ax[0] * s2[1]; e[1] = b[1] + ax[1] * s2[1]; e[2] = b[2] + ax[2] * s2[1];
+            if (plane_sphere(rc[n], margin, a, pn, e, s2[0])) { rc[n].yh[0] = ax[0]; rc[n].yh[1] = ax[1]; rc[n].yh[2] = ax[2]; n++; }
+            e[0] = b[0] - ax[0] * s2[1]; e[1] = b[1] - ax[1] * s2[1]; e[2] = b[2] - ax[2] * s2[1];
+            if (plane_sphere(rc[n], margin, a, pn, e, s2[0])) { rc[n].yh[0] = ax[0]; rc[n].yh[1] = ax[1]; rc[n].yh[2] = ax[2]; n++; }
+          } else if (t2 == G_BOX) {
+            float dif[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+            float dist = dot3(dif, pn);
+            for (int i = 0; i < 8 && n < 4; i++) {
+              float v[3] = {(i & 1) ? s2[0] : -s2[0], (i & 2) ? s2[1] : -s2[1], (i & 4) ? s2[2] : -s2[2]};
+              float cr[3] = {b[3] * v[0] + b[4] * v[1] + b[5] * v[2], b[6] * v[0] + b[7] * v[1] + b[8] * v[2],
+                             b[9] * v[0] + b[10] * v[1] + b[11] * v[2]};
+              float ld = dot3(pn, cr);
+              if (dist + ld > margin || ld > 0.f) continue;
+              rc[n].dist = dist + ld;
+              for (int k = 0; k < 3; k++) {
+                rc[n].pos[k] = b[k] + cr[k] - pn[k] * (0.5f * rc[n].dist);
+                rc[n].n[k] = pn[k]; rc[n].yh[k] = 0.f;
+              }
+              n++;
+            }
+          }
+        } else if (t1 == G_SPHERE && t2 == G_SPHERE) {
+          n = sphere_sphere(rc[0], margin, a, s1[0], b, s2[0]);
+        } else if (t1 == G_SPHERE && t2 == G_CAPSULE) {
+          float ax[3] = {b[3 + 2], b[3 + 5], b[3 + 8]};
+          float vec[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};
+          float x = fminf(fmaxf(dot3(ax, vec), -s2[1]), s2[1]);
+          float pt[3] = {b[0] + ax[0] * x, b[1] + ax[1] * x, b[2] + ax[2] * x};
+          n = sphere_sphere(rc[0], margin, a, s1[0], pt, s2[0]);
+        } else if (t1 == G_CAPSULE && t2 == G_CAPSULE) {
+          float a1[3] = {a[3 + 2], a[3 + 5], a[3 + 8]}, a2[3] = {b[3 + 2], b[3 + 5], b[3 + 8]};
+          float dif[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};
+          float ma = dot3(a1, a1), mb = -dot3(a1, a2), mc = dot3(a2, a2);
+          float u = -dot3(a1, dif), v = dot3(a2, dif);
+          float det = ma * mc - mb * mb;
+          float len1 = s1[1], len2 = s2[1];
+          if (fabsf(det) >= MINVAL) {
+            float x1 = (mc * u - mb * v) / det, x2 = (ma * v - mb * u) / det;
+            if (x1 > len1) { x1 = len1; x2 = (v - mb * len1) / mc; }
+            else if (x1 < -len1) { x1 = -len1; x2 = (v + mb * len1) / mc; }
+            if (x2 > len2) { x2 = len2; x1 = (u - mb * len2) / ma; }
+            else if (x2 < -len2) { x2 = -len2; x1 = (u + mb * len2) / ma; }
+            x1 = fminf(fmaxf(x1, -len1), len1);
+            float v1[3] = {a[0] + a1[0] * x1, a[1] + a1[1] * x1, a[2] + a1[2] * x1};
+            float v2[3] = {b[0] + a2[0] * x2, b[1] + a2[1] * x2, b[2] + a2[2] * x2};
+            n = sphere_sphere(rc[0], margin, v1, s1[0], v2, s2[0]);
+          } else {
+            for (int e = 0; e < 2; e++) {
+              float x1 = e ? -len1 : len1;
+              float v1[3] = {a[0] + a1[0] * x1, a[1] + a1[1] * x1, a[2] + a1[2] * x1};
+              float t[3] = {v1[0] - b[0], v1[1] - b[1], v1[2] - b[2]};
+              float x2 = fminf(fmaxf(dot3(a2, t), -len2), len2);
+              float v2[3] = {b[0] + a2[0] * x2, b[1] + a2[1] * x2, b[2] + a2[2] * x2};
+              n += sphere_sphere(rc[n], margin, v1, s1[0], v2, s2[0]);
+            }
+          }
+        }
+      }
+      // deterministic compaction in (pair order, contact index) order
+      int incl = n;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+      }
+      int base = ncon + incl - n;
+      int tot = __shfl_sync(FULL, incl, 31);
+      if (n > 0) {
+        // contact parameters (mj_contactParam)
+        int condim; float fri0, solref[2], solimp[5];
+        int pr1 = m.geom_priority[g1], pr2 = m.geom_priority[g2];
+        if (pr1 != pr2) {
+          int g = pr1 > pr2 ? g1 : g2;
+          condim = m.geom_condim[g]; fri0 = gfri[3 * g];
+          solref[0] = gsolref[2 * g]; solref[1] = gsolref[2 * g + 1];
+          for (int k = 0; k < 5; k++) solimp[k] = gsolimp[5 * g + k];
+        } else {
+          condim = max(m.geom_condim[g1], m.geom_condim[g2]);
+          fri0 = fmaxf(gfri[3 * g1], gfri[3 * g2]);
+          float m1 = gsolmix[g1], m2 = gsolmix[g2], mix;
+          if (m1 >= MINVAL && m2 >= MINVAL) mix = m1 / (m1 + m2);
+          else if (m1 < MINVAL && m2 < MINVAL) mix = 0.5f;
+          else mix = m1 < MINVAL ? 0.f : 1.f;
+          if (gsolref[2 * g1] > 0.f && gsolref[2 * g2] > 0.f) {
+            solref[0] = mix * gsolref[2 * g1] + (1.f - mix) * gsolref[2 * g2];
+            solref[1] = mix * gsolref[2 * g1 + 1] + (1.f - mix) * gsolref[2 * g2 + 1];
+          } else {
+            solref[0] = fminf(gsolref[2 * g1], gsolref[2 * g2]);
+            solref[1] = fminf(gsolref[2 * g1 + 1], gsolref[2 * g2 + 1]);
+          }
+          for (int k = 0; k < 5; k++) solimp[k] = mix * gsolimp[5 * g1 + k] + (1.f - mix) * gsolimp[5 * g2 + k];
+        }
+        float mu = fmaxf(fri0, MINMU);
+        float incm = margin - fmaxf(ggap[g1], ggap[g2]);
+        int b1 = m.geom_bodyid[g1], b2 = m.geom_bodyid[g2];
+        // impedance / reference parameters (mj_makeImpedance; pos = dist, margin = includemargin)
+        float dmin = fminf(fmaxf(solimp[0], MINIMP), MAXIMP), dmax = fminf(fmaxf(solimp[1], MINIMP), MAXIMP);
+        float width = fmaxf(solimp[2], MINVAL), mid = fminf(fmaxf(solimp[3], MINIMP), MAXIMP);
+        float power = fmaxf(solimp[4], 1.f);
+        float K, B;
+        if (solref[0] > 0.f) {
+          float tc = fmaxf(solref[0], 2.f * m.timestep), dr = solref[1];
+          K = 1.f / fmaxf(MINVAL, dmax * dmax * tc * tc * dr * dr);
+          B = 2.f / fmaxf(MINVAL, dmax * tc);
+        } else { K = -solref[0] / (dmax * dmax); B = -solref[1] / dmax; }
+        float tran = inv[2 * b1] + inv[2 * b2];
+        for (int i = 0; i < n; i++) {
+          int c = base + i;
+          if (c >= MC) break;
+          float fr[9] = {rc[i].n[0], rc[i].n[1], rc[i].n[2], rc[i].yh[0], rc[i].yh[1], rc[i].yh[2], 0.f, 0.f, 0.f};
+          make_frame(fr);
+          g_dist[c] = rc[i].dist;
+          for (int k = 0; k < 3; k++) g_pos[3 * c + k] = rc[i].pos[k];
+          for (int k = 0; k < 9; k++) g_frame[9 * c + k] = fr[k];
+          g_geom[2 * c] = g1; g_geom[2 * c + 1] = g2;
+          float r[3] = {rc[i].pos[0] - c0[0], rc[i].pos[1] - c0[1], rc[i].pos[2] - c0[2]};
+          for (int mm = 0; mm < 3; mm++) {
+            float t[3];
+            cross3(t, r, fr + 3 * mm);
+            con[(CS0 + 6 * mm + 0) * MC + c] = t[0]; con[(CS0 + 6 * mm + 1) * MC + c] = t[1];
+            con[(CS0 + 6 * mm + 2) * MC + c] = t[2];
+            con[(CS0 + 6 * mm + 3) * MC + c] = fr[3 * mm]; con[(CS0 + 6 * mm + 4) * MC + c] = fr[3 * mm + 1];
+            con[(CS0 + 6 * mm + 5) * MC + c] = fr[3 * mm + 2];
+          }
+          float x = fabsf(rc[i].dist - incm) / width, imp;
+          if (x >= 1.f) imp = dmax;
+          else if (x <= 0.f) imp = dmin;
+          else {
+            float y;
+            if (power == 1.f) y = x;
+            else if (x <= mid) y = powf(x, power) / powf(mid, power - 1.f);
+            else y = 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f);
+            imp = dmin + y * (dmax - dmin);
+          }
+          // R: frictionless -> (1-imp)/imp*tran ; pyramidal -> 2 mu'^2 * (1-imp)/imp*tran*(1+mu^2)
+          float diag = condim == 1 ? tran : tran * (1.f + mu * mu);
+          float R = fmaxf(MINVAL, (1.f - imp) * diag / imp);
+          if (condim > 1) { float mup = mu * rsqrtf(m.impratio); R = fmaxf(MINVAL, 2.f * mup * mup * R); }
+          bool excluded = !(rc[i].dist < incm);
+          con[CDIST * MC + c] = rc[i].dist;
+          con[CMU * MC + c] = mu;
+          con[CD * MC + c] = excluded ? 0.f : 1.f / R;
+          con[CKI * MC + c] = K * imp * (rc[i].dist - incm);
+          con[CB * MC + c] = B;
+          ((int*)con)[CINFO * MC + c] = b1 | (b2 << 8) | ((excluded ? 0 : condim) << 16);
+        }
+      }
+      ncon += tot;
+    }
+    if (ncon > MC) { ncon = MC; overflow = 1; }
+  }
+  __syncwarp();
+
+  // ---------------- phase 6: joint-limit rows, body-pair groups ----------------------------------
+  int nlim = 0;
+  {
+    const float* range = MP(jnt_range); const float* jmar = MP(jnt_margin);
+    const float* jsolref = MP(jnt_solref); const float* jsolimp = MP(jnt_solimp);
+    const float* dinv = MP(dof_invweight0);
+    for (int j0 = 0; j0 < njnt; j0 += 32) {
+      int j = j0 + lane;
+      int side = 0; float dist = 0.f;
+      if (j < njnt && m.jnt_limited[j] && m.jnt_type[j] != JNT_FREE) {
+        float value = qpos[m.jnt_qposadr[j]];
+        float dlo = value - range[2 * j], dhi = range[2 * j + 1] - value;
+        if (dlo < jmar[j]) { side = -1; dist = dlo; }
+        else if (dhi < jmar[j]) { side = 1; dist = dhi; }
+        // (both sides active at once needs range width < 2*margin; not representable here)
+      }
+      unsigned bal = __ballot_sync(FULL, side != 0);
+      if (side != 0) {
+        int r = nlim + __popc(bal & ((1u << lane) - 1u));
+        if (r < NLC) {
+          int dof = m.jnt_dofadr[j];
+          const float* si = jsolimp + 5 * j;
+          float dmin = fminf(fmaxf(si[0], MINIMP), MAXIMP), dmax = fminf(fmaxf(si[1], MINIMP), MAXIMP);
+          float width = fmaxf(si[2], MINVAL), mid = fminf(fmaxf(si[3], MINIMP), MAXIMP), power = fmaxf(si[4], 1.f);
+          float x = fabsf(dist - jmar[j]) / width, imp;
+          if (x >= 1.f) imp = dmax;
+          else if (x <= 0.f) imp = dmin;
+          else {
+            float y;
+            if (power == 1.f) y = x;
+            else if (x <= mid) y = powf(x, power) / powf(mid, power - 1.f);
+            else y = 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f);
+            imp = dmin + y * (dmax - dmin);
+          }
+          float K, B;
+          if (jsolref[2 * j] > 0.f) {
+            float tc = fmaxf(jsolref[2 * j], 2.f * m.timestep), dr = jsolref[2 * j + 1];
+            K = 1.f / fmaxf(MINVAL, dmax * dmax * tc * tc * dr * dr);
+            B = 2.f / fmaxf(MINVAL, dmax * tc);
+          } else { K = -jsolref[2 * j] / (dmax * dmax); B = -jsolref[2 * j + 1] / dmax; }
+          float R = fmaxf(MINVAL, (1.f - imp) * dinv[dof] / imp);
+          float Jd = -(float)side;
+          float vel = Jd * qvel[dof];
+          ((int*)lim)[LINFO * NLC + r] = dof | ((side > 0 ? 1 : 0) << 16);
+          lim[LD * NLC + r] = 1.f / R;
+          lim[LAREF * NLC + r] = -B * vel - K * imp * (dist - jmar[j]);
+        }
+      }
+      nlim += __popc(bal);
+    }
+    if (nlim > NLC) { nlim = NLC; overflow = 1; }
+  }
+  // groups = maximal runs of contacts with the same (b1,b2); group dof set = chain(b1) xor chain(b2)
+  int ngroup = 0;
+  for (int c00 = 0; c00 < ncon; c00 += 32) {
+    int c = c00 + lane;
+    bool start = false;
+    int key = 0;
+    if (c < ncon) {
+      key = ((int*)con)[CINFO * MC + c] & 0xffff;
+      start = (c == 0) || ((((int*)con)[CINFO * MC + c - 1] & 0xffff) != key);
+    }
+    unsigned bal = __ballot_sync(FULL, start);
+    int before = ngroup + __popc(bal & ((1u << lane) - 1u));
+    if (c < ncon) {
+      int g = start ? before : before - 1;
+      ((int*)con)[CGRP * MC + c] = g;
+      if (start) {
+        gstart[g] = c;
+        unsigned long long mk = m.body_dofmask[key & 0xff] ^ m.body_dofmask[key >> 8];
+        gmask_lo[g] = (unsigned)mk; gmask_hi[g] = (unsigned)(mk >> 32);
+      }
+    }
+    ngroup += __popc(bal);
+  }
+  if (lane == 0) gstart[ngroup] = ncon;
+  __syncwarp();
+  int nefc = nlim;
+  {
+    int cnt = 0;
+    for (int c = lane; c < ncon; c += 32) {
+      int dim = ((int*)con)[CINFO * MC + c] >> 16;
+      cnt += dim == 0 ? 0 : (dim == 1 ? 1 : 2 * (dim - 1));
+    }
+    cnt = (int)wsum((float)cnt);
+    nefc += cnt;
+  }
+
+  // ---- J x for all rows: dst field <- J x (contacts: 4 rows, or row 0 only for condim 1) --------
+  float* gV = s + L.gV;
+  auto mulJ = [&](const float* x, int dstc, int dstl) {
+    // group relative spatial velocity: lanes (gi, comp), 5 groups per pass
+    for (int g0 = 0; g0 < ngroup; g0 += 5) {
+      int gi = lane / 6, comp = lane - 6 * gi, g = g0 + gi;
+      if (gi < 5 && g < ngroup) {
+        int key = ((int*)con)[CINFO * MC + gstart[g]] & 0xffff;
+        unsigned long long m2 = m.body_dofmask[key >> 8];
+        unsigned long long mk = ((unsigned long long)gmask_hi[g] << 32) | gmask_lo[g];
+        float acc = 0.f;
+        while (mk) {
+          int d = __ffsll((long long)mk) - 1;
+          mk &= mk - 1;
+          float sg = (m2 >> d & 1ull) ? 1.f : -1.f;
+          acc += sg * cdof[6 * d + comp] * x[d];
+        }
+        gV[6 * g + comp] = acc;
+      }
+    }
+    __syncwarp();
+    for (int c = lane; c < ncon; c += 32) {
+      const float* V = gV + 6 * ((int*)con)[CGRP * MC + c];
+      float a3[3];
+#pragma unroll
+      for (int mm = 0; mm < 3; mm++) {
+        float t = 0.f;
+#pragma unroll
+        for (int a = 0; a < 6; a++) t += con[(CS0 + 6 * mm + a) * MC + c] * V[a];
+        a3[mm] = t;
+      }
+      float mu = con[CMU * MC + c];
+      int dim = ((int*)con)[CINFO * MC + c] >> 16;
+      if (dim == 1) {
+        con[(dstc + 0) * MC + c] = a3[0];
+        con[(dstc + 1) * MC + c] = 0.f; con[(dstc + 2) * MC + c] = 0.f; con[(dstc + 3) * MC + c] = 0.f;
+      } else {
+        con[(dstc + 0) * MC + c] = a3[0] + mu * a3[1];
+        con[(dstc + 1) * MC + c] = a3[0] - mu * a3[1];
+        con[(dstc + 2) * MC + c] = a3[0] + mu * a3[2];
+        con[(dstc + 3) * MC + c] = a3[0] - mu * a3[2];
+      }
+    }
+    for (int r = lane; r < nlim; r += 32) {
+      int info = ((int*)lim)[LINFO * NLC + r];
+      float Jd = (info >> 16) ? -1.f : 1.f;
+      lim[dstl * NLC + r] = Jd * x[info & 0xffff];
+    }
+    __syncwarp();
+  };
+  // cost of the constraint rows for residuals stored in (fc, fl); optionally subtract aref first
+  auto rows_sub_aref_cost = [&](int fc, int fl) -> float {
+    float cost = 0.f;
+    for (int c = lane; c < ncon; c += 32) {
+      int dim = ((int*)con)[CINFO * MC + c] >> 16;
+      float D = con[CD * MC + c];
+      int nr = dim == 0 ? 0 : (dim == 1 ? 1 : 4);
+      for (int r = 0; r < 4; r++) {
+        float v = con[(fc + r) * MC + c] - con[(CAREF0 + r) * MC + c];
+        if (r >= nr) v = 0.f;
+        con[(fc + r) * MC + c] = v;
+        if (v < 0.f) cost += 0.5f * D * v * v;
+      }
+    }
+    for (int r = lane; r < nlim; r += 32) {
+      float v = lim[fl * NLC + r] - lim[LAREF * NLC + r];
+      lim[fl * NLC + r] = v;
+      if (v < 0.f) cost += 0.5f * lim[LD * NLC + r] * v * v;
+    }
+    __syncwarp();
+    return wsum(cost);
+  };
+
+  // aref for contact rows: -B*vel_row - K*imp*(pos-margin)
+  if (nefc > 0) {
+    mulJ(qvel, CJV0, LJV);
+    for (int c = lane; c < ncon; c += 32) {
+      float B = con[CB * MC + c], ki = con[CKI * MC + c];
+#pragma unroll
+      for (int r = 0; r < 4; r++) con[(CAREF0 + r) * MC + c] = -B * con[(CJV0 + r) * MC + c] - ki;
+    }
+    __syncwarp();
+  }
+
+  // ---------------- phase 7: unconstrained acceleration -------------------------------------------
+  for (int i = lane; i < m.ntri; i += 32) H[i] = Mq[i];
+  __syncwarp();
+  chol_factor(H, invdiag, nv, m.ntri, m.tri_coldesc, lane);
+  chol_solve(H, invdiag, qacc_smooth, nv, lane);
+  if (m.debug)
+    for (int i = lane; i < nv; i += 32) dd.qacc_smooth.p[(size_t)w * dd.qacc_smooth.stride + i] = qacc_smooth[i];
+
+  // ---------------- phase 8: Newton solver (primal, exact line search) ----------------------------
+  int niter = 0;
+  float cost = 0.f;
+  if (nefc == 0) {
+    for (int i = lane; i < nv; i += 32) { qacc[i] = qacc_smooth[i]; qfrc_c[i] = 0.f; }
+    __syncwarp();
+  } else {
+    // warm start: qacc_warmstart unless qacc_smooth is cheaper (mj_fwdConstraint)
+    symv(Mq, qacc_ws, Ma, nv, lane);
+    mulJ(qacc_ws, CJAR0, LJAR);
+    float cw = rows_sub_aref_cost(CJAR0, LJAR);
+    float gs = 0.f;
+    for (int i = lane; i < nv; i += 32) gs += (Ma[i] - qfrc_smooth[i]) * (qacc_ws[i] - qacc_smooth[i]);
+    cw += 0.5f * wsum(gs);
+    mulJ(qacc_smooth, CJV0, LJV);
+    float csm = rows_sub_aref_cost(CJV0, LJV);
+    bool use_smooth = cw > csm;
+    for (int i = lane; i < nv; i += 32) qacc[i] = use_smooth ? qacc_smooth[i] : qacc_ws[i];
+    __syncwarp();
+    if (use_smooth) {
+      for (int i = lane; i < nv; i += 32) Ma[i] = qfrc_smooth[i];  // M * qacc_smooth
+      for (int c = lane; c < ncon; c += 32)
+#pragma unroll
+        for (int r = 0; r < 4; r++) con[(CJAR0 + r) * MC + c] = con[(CJV0 + r) * MC + c];
+      for (int r = lane; r < nlim; r += 32) lim[LJAR * NLC + r] = lim[LJV * NLC + r];
+      __syncwarp();
+    }
+    const float scale = 1.f / (m.meaninertia * (float)max(1, nv));
+    float* gA = s + L.gA; float* gu = s + L.gu; int* glist = (int*)(s + L.glist);
+    float oldcost = 0.f;
+    bool first = true;
+    while (true) {
+      // ---- constraint update: forces, cost, qfrc_constraint = J^T f --------------------------
+      float cst = 0.f;
+      for (int c = lane; c < ncon; c += 32) {
+        float D = con[CD * MC + c], mu = con[CMU * MC + c];
+        int dim = ((int*)con)[CINFO * MC + c] >> 16;
+        float f[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          float v = con[(CJAR0 + r) * MC + c];
+          f[r] = v < 0.f ? -D * v : 0.f;
+          if (v < 0.f) cst += 0.5f * D * v * v;
+        }
+        float F0, F1, F2;
+        if (dim == 1) { F0 = f[0]; F1 = 0.f; F2 = 0.f; }
+        else { F0 = f[0] + f[1] + f[2] + f[3]; F1 = mu * (f[0] - f[1]); F2 = mu * (f[2] - f[3]); }
+        con[(CJV0 + 0) * MC + c] = F0; con[(CJV0 + 1) * MC + c] = F1; con[(CJV0 + 2) * MC + c] = F2;
+      }
+      for (int i = lane; i < nv; i += 32) qfrc_c[i] = 0.f;
+      __syncwarp();
+      for (int r = lane; r < nlim; r += 32) {
+        float v = lim[LJAR * NLC + r];
+        if (v < 0.f) {
+          float D = lim[LD * NLC + r];
+          cst += 0.5f * D * v * v;
+          int info = ((int*)lim)[LINFO * NLC + r];
+          atomicAdd(&qfrc_c[info & 0xffff], ((info >> 16) ? -1.f : 1.f) * (-D * v));
+        }
+      }
+      // group wrench: W_g = sum_c sum_m F_m S_m  (lanes (gi, comp))
+      for (int g0 = 0; g0 < ngroup; g0 += 5) {
+        int gi = lane / 6, comp = lane - 6 * gi, g = g0 + gi;
+        if (gi < 5 && g < ngroup) {
+          float acc = 0.f;
+          for (int c = gstart[g]; c < gstart[g + 1]; c++)
+            acc += con[(CJV0 + 0) * MC + c] * con[(CS0 + comp) * MC + c] +
+                   con[(CJV0 + 1) * MC + c] * con[(CS0 + 6 + comp) * MC + c] +
+                   con[(CJV0 + 2) * MC + c] * con[(CS0 + 12 + comp) * MC + c];
+          gV[6 * g + comp] = acc;
+        }
+      }
+      __syncwarp();
+      for (int i = lane; i < nv; i += 32) {
+        float acc = qfrc_c[i];
+        for (int g = 0; g < ngroup; g++) {
+          unsigned word = i < 32 ? gmask_lo[g] : gmask_hi[g];
+          if (word >> (i & 31) & 1u) {
+            int key = ((int*)con)[CINFO * MC + gstart[g]] & 0xffff;
+            float sg = (m.body_dofmask[key >> 8] >> i & 1ull) ? 1.f : -1.f;
+            acc += sg * dot6(cdof + 6 * i, gV + 6 * g);
+          }
+        }
+        qfrc_c[i] = acc;
+      }
+      __syncwarp();
+      float gg = 0.f, gn = 0.f;
+      for (int i = lane; i < nv; i += 32) {
+        float g = Ma[i] - qfrc_smooth[i] - qfrc_c[i];
+        grad[i] = g;
+        gn += g * g;
+        gg += (Ma[i] - qfrc_smooth[i]) * (qacc[i] - qacc_smooth[i]);
+      }
+      cost = wsum(cst) + 0.5f * wsum(gg);
+      gn = wsum(gn);
+      if (!first) {
+        float improvement = scale * (oldcost - cost), gradient = scale * sqrtf(gn);
+        if (improvement < m.tolerance || gradient < m.tolerance) break;
+      }
+      if (niter >= m.iterations) break;
+      first = false;
+      // ---- Hessian H = M + J^T D_active J via per-body-pair 6x6 blocks -------------------------
+      for (int i = lane; i < m.ntri; i += 32) H[i] = Mq[i];
+      __syncwarp();
+      for (int r = lane; r < nlim; r += 32) {
+        if (lim[LJAR * NLC + r] < 0.f) {
+          int d = ((int*)lim)[LINFO * NLC + r] & 0xffff;
+          atomicAdd(&H[tri(d, d)], lim[LD * NLC + r]);
+        }
+      }
+      for (int g = 0; g < ngroup; g++) {
+        // A (6x6 symmetric, 21 entries), lane e owns entry (a,b)
+        if (lane < 21) {
+          int a = 0, e = lane;
+          while (e >= 6 - a) { e -= 6 - a; a++; }
+          int b = a + e;
+          float acc = 0.f;
+          for (int c = gstart[g]; c < gstart[g + 1]; c++) {
+            float D = con[CD * MC + c], mu = con[CMU * MC + c];
+            int dim = ((int*)con)[CINFO * MC + c] >> 16;
+            float w0 = con[(CJAR0 + 0) * MC + c] < 0.f ? D : 0.f;
+            float sa0 = con[(CS0 + a) * MC + c], sb0 = con[(CS0 + b) * MC + c];
+            if (dim == 1) { acc += w0 * sa0 * sb0; continue; }
+            float w1 = con[(CJAR0 + 1) * MC + c] < 0.f ? D : 0.f;
+            float w2 = con[(CJAR0 + 2) * MC + c] < 0.f ? D : 0.f;
+            float w3 = con[(CJAR0 + 3) * MC + c] < 0.f ? D : 0.f;
+            float sa1 = con[(CS0 + 6 + a) * MC + c], sb1 = con[(CS0 + 6 + b) * MC + c];
+            float sa2 = con[(CS0 + 12 + a) * MC + c], sb2 = con[(CS0 + 12 + b) * MC + c];
+            float W00 = w0 + w1 + w2 + w3, W01 = mu * (w0 - w1), W02 = mu * (w2 - w3);
+            float W11 = mu * mu * (w0 + w1), W22 = mu * mu * (w2 + w3);
+            acc += W00 * sa0 * sb0 + W01 * (sa0 * sb1 + sa1 * sb0) + W02 * (sa0 * sb2 + sa2 * sb0) +
+                   W11 * sa1 * sb1 + W22 * sa2 * sb2;
+          }
+          gA[a * 6 + b] = acc;
+          gA[b * 6 + a] = acc;
+        }
+        // dof list of the group (ascending) with signs folded into u and v
+        unsigned lo = gmask_lo[g], hi = gmask_hi[g];
+        int nlo = __popc(lo), ns = nlo + __popc(hi);
+        if (lo >> lane & 1u) glist[__popc(lo & ((1u << lane) - 1u))] = lane;
+        if (hi >> lane & 1u) glist[nlo + __popc(hi & ((1u << lane) - 1u))] = 32 + lane;
+        __syncwarp();
+        int key = ((int*)con)[CINFO * MC + gstart[g]] & 0xffff;
+        unsigned long long m2 = m.body_dofmask[key >> 8];
+        for (int a = lane; a < ns; a += 32) {
+          int d = glist[a];
+          float sg = (m2 >> d & 1ull) ? 1.f : -1.f;
+          const float* c = cdof + 6 * d;
+#pragma unroll
+          for (int k = 0; k < 6; k++) {
+            float t = 0.f;
+#pragma unroll
+            for (int l = 0; l < 6; l++) t += gA[k * 6 + l] * c[l];
+            gu[6 * a + k] = sg * t;
+          }
+        }
+        __syncwarp();
+        int np = ns * (ns + 1) >> 1;
+        for (int p = lane; p < np; p += 32) {
+          unsigned short e = m.tri_rowmajor[p];
+          int a = e & 0xff, b = e >> 8;  // a >= b
+          int db = glist[b];
+          float sgb = (m2 >> db & 1ull) ? 1.f : -1.f;
+          H[tri(glist[a], db)] += sgb * dot6(gu + 6 * a, cdof + 6 * db);
+        }
+        __syncwarp();
+      }
+      chol_factor(H, invdiag, nv, m.ntri, m.tri_coldesc, lane);
+      for (int i = lane; i < nv; i += 32) search[i] = -grad[i];
+      __syncwarp();
+      chol_solve(H, invdiag, search, nv, lane);
+      // ---- exact line search along `search` --------------------------------------------------
+      symv(Mq, search, Mv, nv, lane);
+      mulJ(search, CJV0, LJV);
+      float g1 = 0.f, g2 = 0.f, sn = 0.f;
+      for (int i = lane; i < nv; i += 32) {
+        g1 += search[i] * (Ma[i] - qfrc_smooth[i]);
+        g2 += 0.5f * search[i] * Mv[i];
+        sn += search[i] * search[i];
+      }
+      g1 = wsum(g1); g2 = wsum(g2); sn = sqrtf(wsum(sn));
+      if (sn < MINVAL) break;
+      float gtol = m.tolerance * m.ls_tolerance * sn / scale;
+      auto ls_eval = [&](float al, float& d0, float& d1) {
+        float a0 = 0.f, a1 = 0.f;
+        for (int c = lane; c < ncon; c += 32) {
+          float D = con[CD * MC + c];
+#pragma unroll
+          for (int r = 0; r < 4; r++) {
+            float jv = con[(CJV0 + r) * MC + c];
+            float x = con[(CJAR0 + r) * MC + c] + al * jv;
+            if (x < 0.f) { a0 += D * x * jv; a1 += D * jv * jv; }
+          }
+        }
+        for (int r = lane; r < nlim; r += 32) {
+          float jv = lim[LJV * NLC + r];
+          float x = lim[LJAR * NLC + r] + al * jv;
+          if (x < 0.f) { float D = lim[LD * NLC + r]; a0 += D * x * jv; a1 += D * jv * jv; }
+        }
+        d0 = wsum(a0) + g1 + 2.f * al * g2;
+        d1 = fmaxf(wsum(a1) + 2.f * g2, MINVAL);
+      };
+      float alpha = 0.f, d0, d1;
+      ls_eval(0.f, d0, d1);
+      if (d0 < 0.f) {
+        float lo_a = 0.f, hi_a = -1.f;  // hi_a < 0: no upper bracket yet
+        alpha = -d0 / d1;
+        for (int it = 0; it < m.ls_iterations; it++) {
+          ls_eval(alpha, d0, d1);
+          if (fabsf(d0) < gtol) break;
+          if (d0 < 0.f) lo_a = alpha; else hi_a = alpha;
+          float nxt = alpha - d0 / d1;
+          if (hi_a >= 0.f && !(nxt > lo_a && nxt < hi_a)) nxt = 0.5f * (lo_a + hi_a);
+          if (nxt == alpha) break;
+          alpha = nxt;
+        }
+      }
+      if (alpha == 0.f) break;
+      for (int i = lane; i < nv; i += 32) { qacc[i] += alpha * search[i]; Ma[i] += alpha * Mv[i]; }
+      for (int c = lane; c < ncon; c += 32)
+#pragma unroll
+        for (int r = 0; r < 4; r++) con[(CJAR0 + r) * MC + c] += alpha * con[(CJV0 + r) * MC + c];
+      for (int r = lane; r < nlim; r += 32) lim[LJAR * NLC + r] += alpha * lim[LJV * NLC + r];
+      __syncwarp();
+      oldcost = cost;
+      niter++;
+    }
+  }
+
+  // ---------------- phase 9: contact forces, sensors -----------------------------------------------
+  {
+    float* g_force = dd.contact_force.p + (size_t)w * dd.contact_force.stride;
+    for (int c = lane; c < ncon; c += 32) {
+      float D = con[CD * MC + c], mu = con[CMU * MC + c];
+      int dim = ((int*)con)[CINFO * MC + c] >> 16;
+      float f[4];
+#pragma unroll
+      for (int r = 0; r < 4; r++) { float v = con[(CJAR0 + r) * MC + c]; f[r] = (nefc > 0 && v < 0.f) ? -D * v : 0.f; }
+      float F0, F1, F2;
+      if (dim == 0) { F0 = F1 = F2 = 0.f; }
+      else if (dim == 1) { F0 = f[0]; F1 = F2 = 0.f; }
+      else { F0 = f[0] + f[1] + f[2] + f[3]; F1 = mu * (f[0] - f[1]); F2 = mu * (f[2] - f[3]); }
+      con[(CJV0 + 0) * MC + c] = F0; con[(CJV0 + 1) * MC + c] = F1; con[(CJV0 + 2) * MC + c] = F2;
+      g_force[3 * c] = F0; g_force[3 * c + 1] = F1; g_force[3 * c + 2] = F2;
+    }
+    __syncwarp();
+    float* sd = dd.sensordata.p + (size_t)w * dd.sensordata.stride;
+    const float* g_pos = dd.contact_pos.p + (size_t)w * dd.contact_pos.stride;
+    const int* g_geom = dd.contact_geom.p + (size_t)w * dd.contact_geom.stride;
+    for (int sidx = 0; sidx < m.nsensor; sidx++) {
+      int dataspec = m.sensor_intprm[3 * sidx], reduce = m.sensor_intprm[3 * sidx + 1], num = m.sensor_intprm[3 * sidx + 2];
+      int adr = m.sensor_adr[sidx], sdim = m.sensor_dim[sidx];
+      int slot = sdim / max(num, 1);
+      int ot = m.sensor_objtype[sidx], oi = m.sensor_objid[sidx];
+      int rt = m.sensor_reftype[sidx], ri = m.sensor_refid[sidx];
+      for (int k = lane; k < sdim; k += 32) sd[adr + k] = 0.f;
+      int nmatch = 0;
+      float net[3] = {0.f, 0.f, 0.f}, wp[3] = {0.f, 0.f, 0.f}, wsm = 0.f;
+      for (int c00 = 0; c00 < ncon; c00 += 32) {
+        int c = c00 + lane;
+        int dir = 0;
+        if (c < ncon && (((int*)con)[CINFO * MC + c] >> 16) != 0) {
+          int g1 = g_geom[2 * c], g2 = g_geom[2 * c + 1];
+          auto match = [&](int type, int id, int geom) -> bool {
+            if (type < 0) return true;
+            int b = m.geom_bodyid[geom];
+            if (type == OBJ_GEOM) return geom == id;
+            if (type == OBJ_BODY) return b == id;
+            if (type == OBJ_XBODY) return (m.body_ancmask[b] >> id & 1ull) != 0ull;
+            return false;
+          };
+          if (match(ot, oi, g1) && match(rt, ri, g2)) dir = 1;
+          else if (match(ot, oi, g2) && match(rt, ri, g1)) dir = -1;
+        }
+        unsigned bal = __ballot_sync(FULL, dir != 0);
+        if (dir != 0) {
+          float F0 = con[(CJV0 + 0) * MC + c], F1 = con[(CJV0 + 1) * MC + c], F2 = con[(CJV0 + 2) * MC + c];
+          float fw[3];
+          for (int k = 0; k < 3; k++)
+            fw[k] = dir * (con[(CS0 + 3 + k) * MC + c] * F0 + con[(CS0 + 9 + k) * MC + c] * F1 + con[(CS0 + 15 + k) * MC + c] * F2);
+          if (reduce == 3) {
+            float mag = sqrtf(dot3(fw, fw));
+            for (int k = 0; k < 3; k++) { net[k] += fw[k]; wp[k] += mag * g_pos[3 * c + k]; }
+            wsm += mag;
+          } else if (reduce == 0) {
+            int idx = nmatch + __popc(bal & ((1u << lane) - 1u));
+            if (idx < num) {
+              float* q = sd + adr + idx * slot;
+              int a = 0;
+              if (dataspec & 1) a++;
+              if (dataspec & 2) { q[a] = F0; q[a + 1] = dir * F1; q[a + 2] = dir * F2; a += 3; }
+              if (dataspec & 4) a += 3;
+              if (dataspec & 8) q[a++] = con[CDIST * MC + c];
+              if (dataspec & 16) { for (int k = 0; k < 3; k++) q[a + k] = g_pos[3 * c + k]; a += 3; }
+              if (dataspec & 32) { for (int k = 0; k < 3; k++) q[a + k] = dir * con[(CS0 + 3 + k) * MC + c]; a += 3; }
+            }
+          }
+        }
+        nmatch += __popc(bal);
+      }
+      __syncwarp();
+      if (reduce == 3) {
+        for (int k = 0; k < 3; k++) { net[k] = wsum(net[k]); wp[k] = wsum(wp[k]); }
+        wsm = wsum(wsm);
+        if (nmatch > 0 && lane == 0) {
+          int a = 0;
+          if (dataspec & 1) sd[adr + a++] = (float)nmatch;
+          if (dataspec & 2) { for (int k = 0; k < 3; k++) sd[adr + a + k] = net[k]; a += 3; }
+          if (dataspec & 4) a += 3;
+          if (dataspec & 8) sd[adr + a++] = 0.f;
+          if (dataspec & 16) { for (int k = 0; k < 3; k++) sd[adr + a + k] = wsm > 0.f ? wp[k] / wsm : 0.f; a += 3; }
+          if (dataspec & 32) { float nn[3] = {net[0], net[1], net[2]}; normalize3(nn); for (int k = 0; k < 3; k++) sd[adr + a + k] = nn[k]; }
+        }
+      } else if (reduce == 0 && (dataspec & 1)) {
+        int filled = min(nmatch, num);
+        for (int i = lane; i < filled; i += 32) sd[adr + i * slot] = (float)nmatch;
+      }
+    }
+  }
+
+  // ---------------- phase 10: integrate (implicitfast / Euler), write state ------------------------
+  float* gq = dd.qpos.p + (size_t)w * dd.qpos.stride;
+  float* gv = dd.qvel.p + (size_t)w * dd.qvel.stride;
+  if (STEP) {
+    const float h = m.timestep;
+    const float* damp = MP(dof_damping); const float* bp = MP(actuator_biasprm);
+    const float* fr = MP(actuator_forcerange); const float* gear = MP(actuator_gear);
+    for (int i = lane; i < m.ntri; i += 32) H[i] = Mq[i];
+    __syncwarp();
+    for (int i = lane; i < nv; i += 32) H[tri(i, i)] += h * damp[i];
+    __syncwarp();
+    if (m.integrator == INT_IMPLICITFAST) {
+      for (int a = lane; a < nu; a += 32) {
+        float bv = bp[10 * a + 2];
+        if (bv == 0.f) continue;
+        if (m.actuator_forcelimited[a]) {
+          float f = actf[a];
+          if (f <= fr[2 * a] || f >= fr[2 * a + 1]) continue;
+        }
+        int dof = m.jnt_dofadr[m.actuator_trnid[a]];
+        atomicAdd(&H[tri(dof, dof)], -h * gear[a] * gear[a] * bv);
+      }
+    }
+    bool anydamp = false;
+    for (int i = lane; i < nv; i += 32) anydamp |= damp[i] > 0.f;
+    anydamp = __any_sync(FULL, anydamp);
+    if (m.integrator == INT_IMPLICITFAST || anydamp) {
+      for (int i = lane; i < nv; i += 32) tmpv[i] = qfrc_smooth[i] + qfrc_c[i];
+      __syncwarp();
+      chol_factor(H, invdiag, nv, m.ntri, m.tri_coldesc, lane);
+      chol_solve(H, invdiag, tmpv, nv, lane);
+    } else {
+      for (int i = lane; i < nv; i += 32) tmpv[i] = qacc[i];
+      __syncwarp();
+    }
+    for (int i = lane; i < nv; i += 32) qvel[i] += h * tmpv[i];
+    __syncwarp();
+    for (int j = lane; j < njnt; j += 32) {
+      int qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j];
+      if (m.jnt_type[j] == JNT_FREE) {
+        qpos[qa] += h * qvel[da]; qpos[qa + 1] += h * qvel[da + 1]; qpos[qa + 2] += h * qvel[da + 2];
+        float v[3] = {qvel[da + 3], qvel[da + 4], qvel[da + 5]};
+        float n = sqrtf(dot3(v, v));
+        float q[4] = {qpos[qa + 3], qpos[qa + 4], qpos[qa + 5], qpos[qa + 6]};
+        if (n > MINVAL) {
+          float sn, cs;
+          sincosf(0.5f * h * n, &sn, &cs);
+          float inv = sn / n;
+          float qr[4] = {cs, v[0] * inv, v[1] * inv, v[2] * inv}, qn[4];
+          mulquat(qn, q, qr);
+          q[0] = qn[0]; q[1] = qn[1]; q[2] = qn[2]; q[3] = qn[3];
+        }
+        normalize4(q);
+        qpos[qa + 3] = q[0]; qpos[qa + 4] = q[1]; qpos[qa + 5] = q[2]; qpos[qa + 6] = q[3];
+      } else qpos[qa] += h * qvel[da];
+    }
+    __syncwarp();
+    if (lane == 0) dd.time.p[(size_t)w * dd.time.stride] += h;
+    float* gws = dd.qacc_warmstart.p + (size_t)w * dd.qacc_warmstart.stride;
+    for (int i = lane; i < nv; i += 32) gws[i] = qacc[i];
+  }
+  // outputs that live contiguously in shared memory leave through bulk (TMA) stores
+  {
+    float* gqa = dd.qacc.p + (size_t)w * dd.qacc.stride;
+    for (int i = lane; i < nv; i += 32) gqa[i] = qacc[i];
+    if (m.debug) {
+      float* gfc = dd.qfrc_constraint.p + (size_t)w * dd.qfrc_constraint.stride;
+      for (int i = lane; i < nv; i += 32) gfc[i] = qfrc_c[i];
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (STEP) {
+        bulk_s2g(gq, qpos, 4u * dd.qpos.stride);
+        bulk_s2g(gv, qvel, 4u * dd.qvel.stride);
+      }
+      bulk_s2g(dd.xpos.p + (size_t)w * dd.xpos.stride, xpos, 4u * dd.xpos.stride);
+      bulk_s2g(dd.xquat.p + (size_t)w * dd.xquat.stride, xquat, 4u * dd.xquat.stride);
+      bulk_s2g(dd.xipos.p + (size_t)w * dd.xipos.stride, xipos, 4u * dd.xipos.stride);
+      bulk_s2g(dd.subtree_com.p + (size_t)w * dd.subtree_com.stride, scom, 4u * dd.subtree_com.stride);
+      bulk_commit_wait();
+    }
+    if (lane == 0) {
+      dd.ncon.p[(size_t)w * dd.ncon.stride] = ncon;
+      dd.nefc.p[(size_t)w * dd.nefc.stride] = nefc;
+      dd.solver_niter.p[(size_t)w * dd.solver_niter.stride] = niter;
+      dd.overflow.p[(size_t)w * dd.overflow.stride] = overflow;
+      dd.solver_cost.p[(size_t)w * dd.solver_cost.stride] = cost;
+    }
+  }
+}

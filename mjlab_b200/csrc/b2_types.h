@@ -1,0 +1,99 @@
+// b2_types.h — device-side model / data / shared-memory layout descriptors (internal).
+#pragma once
+#include <stdint.h>
+
+#define B2_WARPS_PER_CTA 2
+#define B2_MAX_FIELDS 96
+
+enum { JNT_FREE = 0, JNT_BALL = 1, JNT_SLIDE = 2, JNT_HINGE = 3 };
+enum { G_PLANE = 0, G_SPHERE = 2, G_CAPSULE = 3, G_BOX = 6, G_MESH = 7 };
+enum { OBJ_BODY = 1, OBJ_XBODY = 2, OBJ_GEOM = 5 };
+enum { INT_EULER = 0, INT_IMPLICITFAST = 3 };
+
+// A float model array; `stride` is the per-world stride in floats (0 = shared by all worlds).
+struct FArr {
+  const float* p;
+  int stride;
+  int n;
+};
+
+// Per-world Data array: base pointer + row stride in elements (rows padded to 16 B).
+struct DArr {
+  float* p;
+  int stride;
+  int n;
+};
+struct IArr {
+  int* p;
+  int stride;
+  int n;
+};
+
+// Per-contact SoA fields inside the per-env shared-memory block (index f*maxcon + c).
+enum {
+  CS0 = 0,        // 18 floats: S_m[a] at CS0 + m*6 + a; S_m = [r x e_m ; e_m], e_0 = normal
+  CDIST = 18, CMU, CD, CKI, CB, CINFO, CGRP,
+  CAREF0, CAREF1, CAREF2, CAREF3,
+  CJAR0, CJAR1, CJAR2, CJAR3,
+  CJV0, CJV1, CJV2, CJV3,
+  C_NFIELD  // 37
+};
+// Per-limit-row SoA fields (index f*nlimcap + r).
+enum { LINFO = 0, LD, LAREF, LJAR, LJV, L_NFIELD };
+
+// Offsets (in floats) of every region of one environment's shared-memory block.
+struct Layout {
+  int total;  // floats per env (multiple of 4)
+  // bulk-loaded inputs (16 B aligned)
+  int qpos, qvel, ctrl, qacc_ws, qfrc_applied, xfrc;
+  // kinematics
+  int xpos, xquat, xipos, scom, xanchor, xaxis;
+  // smooth dynamics
+  int cinert, crb, cdof, cdofdot, cvel, cacc;
+  int M, H, invdiag;
+  int qfrc_smooth, qacc_smooth, qacc, Ma, grad, search, Mv, qfrc_c, tmpv, actf;
+  // collision / constraints (overlaid on smooth-only regions)
+  int gpose, pairlist, contacts, limits, gstart, gmask_lo, gmask_hi, gV, glist, gA, gu;
+  int sens;
+  int maxcon, nlimcap, maxpair;
+};
+
+struct DevModel {
+  int nq, nv, nu, nbody, njnt, ngeom, nsite, nsensor, nsensordata, npair, ncg, maxdepth;
+  int ntri;  // nv*(nv+1)/2
+  int maxcon, njmax;
+  int integrator, iterations, ls_iterations, debug;
+  float timestep, tolerance, ls_tolerance, impratio, meaninertia;
+  float gravity[3];
+  // integer tables
+  const int *body_parentid, *body_rootid, *body_jntadr, *body_jntnum, *body_dofadr, *body_dofnum;
+  const int *body_chain, *body_depth;
+  const unsigned long long *body_dofmask, *body_ancmask;
+  const int *jnt_type, *jnt_qposadr, *jnt_dofadr, *jnt_bodyid, *jnt_limited;
+  const int *dof_bodyid, *dof_jntid, *dof_parentid;
+  const int *geom_type, *geom_bodyid, *geom_condim, *geom_priority, *geom_cslot, *cgeom;
+  const int *site_bodyid;
+  const int *actuator_trnid, *actuator_ctrllimited, *actuator_forcelimited;
+  const int *pair_geom1, *pair_geom2;
+  const int *sensor_objtype, *sensor_objid, *sensor_reftype, *sensor_refid, *sensor_intprm;
+  const int *sensor_adr, *sensor_dim;
+  const unsigned short *tri_rowmajor, *tri_coldesc;
+  // float arrays (expandable per world)
+  FArr body_pos, body_quat, body_ipos, body_iquat, body_mass, body_subtreemass, body_inertia,
+      body_invweight0, jnt_pos, jnt_axis, jnt_range, jnt_solref, jnt_solimp, jnt_margin,
+      jnt_stiffness, dof_armature, dof_damping, dof_frictionloss, dof_invweight0, geom_size,
+      geom_pos, geom_quat, geom_friction, geom_solref, geom_solimp, geom_solmix, geom_margin,
+      geom_gap, geom_rbound, geom_rgba, site_pos, site_quat, actuator_gainprm, actuator_biasprm,
+      actuator_ctrlrange, actuator_forcerange, actuator_gear, qpos0;
+  Layout lay;
+};
+
+struct DevData {
+  int nworld;
+  DArr qpos, qvel, ctrl, qacc_warmstart, qfrc_applied, xfrc_applied, act;
+  DArr qacc, xpos, xquat, xmat, xipos, subtree_com, cvel, geom_xpos, geom_xmat, site_xpos,
+      site_xmat, sensordata, actuator_force, time;
+  DArr qfrc_bias, qfrc_smooth, qacc_smooth, qfrc_constraint, qM;
+  DArr contact_dist, contact_pos, contact_frame, contact_force, solver_cost;
+  IArr ncon, nefc, solver_niter, contact_geom, overflow;
+};

@@ -1,0 +1,588 @@
+// b2sim.cu — libb2sim.so: C ABI (include/b2sim.h) around the fused sm_100a step kernel.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/b2sim.h"
+#include "b2_kernel.cuh"
+
+static thread_local std::string g_err;
+static int fail(const std::string& msg) {
+  g_err = msg;
+  return 1;
+}
+#define CUDA_OK(expr)                                                                     \
+  do {                                                                                    \
+    cudaError_t e_ = (expr);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(std::string(#expr) + ": " + cudaGetErrorString(e_));                    \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+struct Field {
+  std::string name;
+  void* ptr = nullptr;
+  int dtype = B2_F32;
+  int ndim = 1;
+  int64_t shape[4] = {1, 1, 1, 1};
+  int64_t stride[4] = {0, 0, 0, 1};
+  FArr* farr = nullptr;  // model float arrays: where the kernel reads the pointer from
+  int64_t n = 0;         // elements per world
+};
+
+struct b2_sim {
+  int device = 0;
+  int nworld = 0;
+  DevModel hm;
+  DevData hd;
+  std::vector<Field> data_fields, model_fields;
+  std::vector<void*> allocs;
+  int64_t launches = 0;
+  size_t smem_bytes = 0;
+  std::map<std::string, std::vector<double>> mf;  // host copy of float model arrays
+  std::map<std::string, std::vector<int>> mi;
+};
+
+static int pad4(int n) { return (n + 3) & ~3; }
+
+template <typename T>
+static int dev_upload(b2_sim* s, const std::vector<T>& h, const T** out) {
+  void* p = nullptr;
+  size_t bytes = sizeof(T) * std::max<size_t>(h.size(), 1);
+  CUDA_OK(cudaMalloc(&p, bytes));
+  s->allocs.push_back(p);
+  if (!h.empty()) CUDA_OK(cudaMemcpy(p, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice));
+  *out = (const T*)p;
+  return 0;
+}
+
+__global__ void b2_tile_kernel(const float* __restrict__ src, float* __restrict__ dst, int n,
+                               long long total) {
+  long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid < total) dst[tid] = src[tid % n];
+}
+__global__ void b2_init_rows_kernel(float* dst, int stride, const float* __restrict__ src, int n,
+                                    int nworld) {
+  long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid < (long long)nworld * n) dst[(tid / n) * stride + (tid % n)] = src[tid % n];
+}
+
+// inner shapes of model float fields: dims after the (broadcast) world dimension
+struct ShapeSpec { const char* name; int second; };  // second = trailing dim (0 -> 1-D)
+static const ShapeSpec kModelShapes[] = {
+    {"body_pos", 3}, {"body_quat", 4}, {"body_ipos", 3}, {"body_iquat", 4}, {"body_mass", 0},
+    {"body_subtreemass", 0}, {"body_inertia", 3}, {"body_invweight0", 2}, {"jnt_pos", 3},
+    {"jnt_axis", 3}, {"jnt_range", 2}, {"jnt_solref", 2}, {"jnt_solimp", 5}, {"jnt_margin", 0},
+    {"jnt_stiffness", 0}, {"dof_armature", 0}, {"dof_damping", 0}, {"dof_frictionloss", 0},
+    {"dof_invweight0", 0}, {"geom_size", 3}, {"geom_pos", 3}, {"geom_quat", 4},
+    {"geom_friction", 3}, {"geom_solref", 2}, {"geom_solimp", 5}, {"geom_solmix", 0},
+    {"geom_margin", 0}, {"geom_gap", 0}, {"geom_rbound", 0}, {"geom_rgba", 4}, {"site_pos", 3},
+    {"site_quat", 4}, {"actuator_gainprm", 10}, {"actuator_biasprm", 10},
+    {"actuator_ctrlrange", 2}, {"actuator_forcerange", 2}, {"actuator_gear", 0}, {"qpos0", 0}};
+
+static FArr* model_farr(DevModel& m, const std::string& name) {
+#define F_(x) if (name == #x) return &m.x;
+  F_(body_pos) F_(body_quat) F_(body_ipos) F_(body_iquat) F_(body_mass) F_(body_subtreemass)
+  F_(body_inertia) F_(body_invweight0) F_(jnt_pos) F_(jnt_axis) F_(jnt_range) F_(jnt_solref)
+  F_(jnt_solimp) F_(jnt_margin) F_(jnt_stiffness) F_(dof_armature) F_(dof_damping)
+  F_(dof_frictionloss) F_(dof_invweight0) F_(geom_size) F_(geom_pos) F_(geom_quat)
+  F_(geom_friction) F_(geom_solref) F_(geom_solimp) F_(geom_solmix) F_(geom_margin) F_(geom_gap)
+  F_(geom_rbound) F_(geom_rgba) F_(site_pos) F_(site_quat) F_(actuator_gainprm)
+  F_(actuator_biasprm) F_(actuator_ctrlrange) F_(actuator_forcerange) F_(actuator_gear) F_(qpos0)
+#undef F_
+  return nullptr;
+}
+
+static int add_data(b2_sim* s, const char* name, DArr* arr, int n, int second = 0) {
+  int stride = pad4(std::max(n, 0));
+  if (stride == 0) stride = 4;
+  void* p = nullptr;
+  size_t bytes = sizeof(float) * (size_t)s->nworld * stride;
+  CUDA_OK(cudaMalloc(&p, bytes));
+  CUDA_OK(cudaMemset(p, 0, bytes));
+  s->allocs.push_back(p);
+  arr->p = (float*)p; arr->stride = stride; arr->n = n;
+  Field f;
+  f.name = name; f.ptr = p; f.dtype = B2_F32; f.n = n;
+  if (second > 0) {
+    f.ndim = 3; f.shape[0] = s->nworld; f.shape[1] = n / second; f.shape[2] = second;
+    f.stride[0] = stride; f.stride[1] = second; f.stride[2] = 1;
+  } else {
+    f.ndim = 2; f.shape[0] = s->nworld; f.shape[1] = n;
+    f.stride[0] = stride; f.stride[1] = 1;
+  }
+  s->data_fields.push_back(f);
+  return 0;
+}
+static int add_idata(b2_sim* s, const char* name, IArr* arr, int n, int second = 0) {
+  int stride = pad4(std::max(n, 1));
+  void* p = nullptr;
+  size_t bytes = sizeof(int) * (size_t)s->nworld * stride;
+  CUDA_OK(cudaMalloc(&p, bytes));
+  CUDA_OK(cudaMemset(p, 0, bytes));
+  s->allocs.push_back(p);
+  arr->p = (int*)p; arr->stride = stride; arr->n = n;
+  Field f;
+  f.name = name; f.ptr = p; f.dtype = B2_I32; f.n = n;
+  if (second > 0) {
+    f.ndim = 3; f.shape[0] = s->nworld; f.shape[1] = n / second; f.shape[2] = second;
+    f.stride[0] = stride; f.stride[1] = second; f.stride[2] = 1;
+  } else if (n == 1) {
+    f.ndim = 1; f.shape[0] = s->nworld; f.stride[0] = stride;
+  } else {
+    f.ndim = 2; f.shape[0] = s->nworld; f.shape[1] = n; f.stride[0] = stride; f.stride[1] = 1;
+  }
+  s->data_fields.push_back(f);
+  return 0;
+}
+
+static int launch(b2_sim* s, bool step, cudaStream_t st) {
+  int grid = (s->nworld + B2_WARPS_PER_CTA - 1) / B2_WARPS_PER_CTA;
+  if (step)
+    b2_step_kernel<true><<<grid, 32 * B2_WARPS_PER_CTA, s->smem_bytes, st>>>(s->hm, s->hd);
+  else
+    b2_step_kernel<false><<<grid, 32 * B2_WARPS_PER_CTA, s->smem_bytes, st>>>(s->hm, s->hd);
+  s->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" {
+
+const char* b2_last_error(void) { return g_err.c_str(); }
+const char* b2_version(void) { return "b2sim 0.1.0 (sm_100a)"; }
+
+int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax, int cuda_device,
+              b2_sim** out) {
+  if (!desc || !out || nworld <= 0) return fail("b2_create: bad arguments");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("b2_create: no CUDA device available (this library has no CPU path)");
+  if (cuda_device < 0 || cuda_device >= ndev) return fail("b2_create: bad cuda_device");
+  DeviceGuard guard(cuda_device);
+  b2_sim* s = new b2_sim();
+  s->device = cuda_device;
+  s->nworld = nworld;
+  for (int i = 0; i < desc->narray; i++) {
+    const B2Array& a = desc->arrays[i];
+    if (a.dtype == B2_I32) {
+      s->mi[a.name] = std::vector<int>((const int32_t*)a.data, (const int32_t*)a.data + a.n);
+    } else if (a.dtype == B2_F64) {
+      s->mf[a.name] = std::vector<double>((const double*)a.data, (const double*)a.data + a.n);
+    } else {
+      delete s;
+      return fail("b2_create: unsupported array dtype");
+    }
+  }
+  auto geti = [&](const char* k) -> int {
+    if (s->mi.count(k)) return s->mi[k].empty() ? 0 : s->mi[k][0];
+    if (s->mf.count(k)) return (int)s->mf[k][0];
+    return 0;
+  };
+  auto getf = [&](const char* k) -> double {
+    if (s->mf.count(k)) return s->mf[k][0];
+    if (s->mi.count(k)) return s->mi[k][0];
+    return 0.0;
+  };
+  DevModel& m = s->hm;
+  memset(&m, 0, sizeof(m));
+  m.nq = geti("nq"); m.nv = geti("nv"); m.nu = geti("nu"); m.nbody = geti("nbody");
+  m.njnt = geti("njnt"); m.ngeom = geti("ngeom"); m.nsite = geti("nsite");
+  m.nsensor = geti("nsensor"); m.nsensordata = geti("nsensordata"); m.npair = geti("npair");
+  m.ntri = m.nv * (m.nv + 1) / 2;
+  if (m.nv > 64 || m.nbody > 64) { delete s; return fail("b2_create: nv and nbody must be <= 64"); }
+  if (m.nv < 1) { delete s; return fail("b2_create: model has no degrees of freedom"); }
+  m.integrator = geti("opt_integrator"); m.iterations = geti("opt_iterations");
+  m.ls_iterations = geti("opt_ls_iterations"); m.debug = 0;
+  m.timestep = (float)getf("opt_timestep"); m.tolerance = (float)getf("opt_tolerance");
+  m.ls_tolerance = (float)getf("opt_ls_tolerance"); m.impratio = (float)getf("opt_impratio");
+  m.meaninertia = (float)getf("stat_meaninertia");
+  for (int k = 0; k < 3; k++) m.gravity[k] = (float)desc->gravity[k];
+  if (geti("opt_cone") != 0) { delete s; return fail("b2_create: only pyramidal cones are supported"); }
+  if (geti("opt_solver") != 2) { delete s; return fail("b2_create: only the Newton solver is implemented"); }
+  m.maxcon = ncon_per_world > 0 ? std::min(ncon_per_world, 255) : 48;
+  m.njmax = njmax > 0 ? njmax : 300;
+
+  // ---- derived integer tables ---------------------------------------------------------------
+  const std::vector<int>& parent = s->mi["body_parentid"];
+  const std::vector<int>& dofadr = s->mi["body_dofadr"];
+  const std::vector<int>& dofnum = s->mi["body_dofnum"];
+  int nb = m.nbody;
+  std::vector<int> depth(nb, 0);
+  std::vector<unsigned long long> dofmask(nb, 0ull), ancmask(nb, 0ull);
+  int maxdepth = 1;
+  ancmask[0] = 1ull;
+  for (int b = 1; b < nb; b++) {
+    depth[b] = depth[parent[b]] + 1;
+    maxdepth = std::max(maxdepth, depth[b]);
+    dofmask[b] = dofmask[parent[b]];
+    for (int k = 0; k < dofnum[b]; k++) dofmask[b] |= 1ull << (dofadr[b] + k);
+    ancmask[b] = ancmask[parent[b]] | (1ull << b);
+  }
+  std::vector<int> chain((size_t)nb * maxdepth, 0);
+  for (int b = 1; b < nb; b++) {
+    int c = b;
+    for (int k = depth[b] - 1; k >= 0; k--) { chain[(size_t)b * maxdepth + k] = c; c = parent[c]; }
+  }
+  m.maxdepth = maxdepth;
+  std::vector<int> cslot(m.ngeom, -1), cgeom;
+  for (int p = 0; p < m.npair; p++) {
+    for (int g : {s->mi["pair_geom1"][p], s->mi["pair_geom2"][p]})
+      if (cslot[g] < 0) { cslot[g] = (int)cgeom.size(); cgeom.push_back(g); }
+  }
+  m.ncg = (int)cgeom.size();
+  std::vector<unsigned short> trow(std::max(m.ntri, 1)), tcol(std::max(m.ntri, 1));
+  {
+    int p = 0;
+    for (int i = 0; i < m.nv; i++) for (int j = 0; j <= i; j++) trow[p++] = (unsigned short)(i | (j << 8));
+    p = 0;
+    for (int j = m.nv - 1; j >= 0; j--) for (int i = j; i < m.nv; i++) tcol[p++] = (unsigned short)(i | (j << 8));
+  }
+  int rc = 0;
+#define UPI(field, key) rc |= dev_upload<int>(s, s->mi[key], &m.field)
+  UPI(body_parentid, "body_parentid"); UPI(body_rootid, "body_rootid"); UPI(body_jntadr, "body_jntadr");
+  UPI(body_jntnum, "body_jntnum"); UPI(body_dofadr, "body_dofadr"); UPI(body_dofnum, "body_dofnum");
+  UPI(jnt_type, "jnt_type"); UPI(jnt_qposadr, "jnt_qposadr"); UPI(jnt_dofadr, "jnt_dofadr");
+  UPI(jnt_bodyid, "jnt_bodyid"); UPI(jnt_limited, "jnt_limited"); UPI(dof_bodyid, "dof_bodyid");
+  UPI(dof_jntid, "dof_jntid"); UPI(dof_parentid, "dof_parentid"); UPI(geom_type, "geom_type");
+  UPI(geom_bodyid, "geom_bodyid"); UPI(geom_condim, "geom_condim"); UPI(geom_priority, "geom_priority");
+  UPI(site_bodyid, "site_bodyid"); UPI(actuator_trnid, "actuator_trnid");
+  UPI(actuator_ctrllimited, "actuator_ctrllimited"); UPI(actuator_forcelimited, "actuator_forcelimited");
+  UPI(pair_geom1, "pair_geom1"); UPI(pair_geom2, "pair_geom2"); UPI(sensor_objtype, "sensor_objtype");
+  UPI(sensor_objid, "sensor_objid"); UPI(sensor_reftype, "sensor_reftype");
+  UPI(sensor_refid, "sensor_refid"); UPI(sensor_intprm, "sensor_intprm"); UPI(sensor_adr, "sensor_adr");
+  UPI(sensor_dim, "sensor_dim");
+#undef UPI
+  rc |= dev_upload<int>(s, depth, &m.body_depth);
+  rc |= dev_upload<int>(s, chain, &m.body_chain);
+  rc |= dev_upload<unsigned long long>(s, dofmask, &m.body_dofmask);
+  rc |= dev_upload<unsigned long long>(s, ancmask, &m.body_ancmask);
+  rc |= dev_upload<int>(s, cslot, &m.geom_cslot);
+  rc |= dev_upload<int>(s, cgeom, &m.cgeom);
+  rc |= dev_upload<unsigned short>(s, trow, &m.tri_rowmajor);
+  rc |= dev_upload<unsigned short>(s, tcol, &m.tri_coldesc);
+  if (rc) { b2_destroy(s); return 1; }
+  // supported sensor set: contact sensors with data in {found,force,dist,pos,normal}, reduce none/netforce
+  for (int i = 0; i < m.nsensor; i++) {
+    int ds = s->mi["sensor_intprm"][3 * i], rd = s->mi["sensor_intprm"][3 * i + 1];
+    if ((ds & ~(1 | 2 | 8 | 16 | 32)) || (rd != 0 && rd != 3)) {
+      b2_destroy(s);
+      return fail("b2_create: contact sensor data/reduce combination not implemented");
+    }
+  }
+  // int model fields visible to callers
+  auto add_imodel = [&](const char* name, const int* p, int n) {
+    Field f; f.name = name; f.ptr = (void*)p; f.dtype = B2_I32; f.ndim = 1; f.shape[0] = n; f.stride[0] = 1; f.n = n;
+    s->model_fields.push_back(f);
+  };
+  add_imodel("geom_bodyid", m.geom_bodyid, m.ngeom); add_imodel("site_bodyid", m.site_bodyid, m.nsite);
+  add_imodel("body_parentid", m.body_parentid, nb); add_imodel("body_rootid", m.body_rootid, nb);
+  add_imodel("jnt_type", m.jnt_type, m.njnt); add_imodel("jnt_qposadr", m.jnt_qposadr, m.njnt);
+  add_imodel("jnt_dofadr", m.jnt_dofadr, m.njnt); add_imodel("dof_bodyid", m.dof_bodyid, m.nv);
+  add_imodel("geom_type", m.geom_type, m.ngeom); add_imodel("geom_condim", m.geom_condim, m.ngeom);
+  add_imodel("geom_priority", m.geom_priority, m.ngeom);
+  add_imodel("actuator_trnid", m.actuator_trnid, m.nu);
+
+  // ---- float model arrays (fp32 on device; shared by all worlds until expanded) -----------------
+  for (const ShapeSpec& sp : kModelShapes) {
+    const std::vector<double>& h = s->mf[sp.name];
+    std::vector<float> hf(h.begin(), h.end());
+    const float* p = nullptr;
+    if (dev_upload<float>(s, hf, &p)) { b2_destroy(s); return 1; }
+    FArr* fa = model_farr(m, sp.name);
+    fa->p = p; fa->stride = 0; fa->n = (int)hf.size();
+    Field f; f.name = sp.name; f.ptr = (void*)p; f.dtype = B2_F32; f.farr = fa; f.n = (int64_t)hf.size();
+    if (sp.second > 0) {
+      f.ndim = 3; f.shape[0] = nworld; f.shape[1] = (int64_t)hf.size() / sp.second; f.shape[2] = sp.second;
+      f.stride[0] = 0; f.stride[1] = sp.second; f.stride[2] = 1;
+    } else {
+      f.ndim = 2; f.shape[0] = nworld; f.shape[1] = (int64_t)hf.size(); f.stride[0] = 0; f.stride[1] = 1;
+    }
+    s->model_fields.push_back(f);
+  }
+
+  // ---- data -------------------------------------------------------------------------------------
+  DevData& d = s->hd;
+  memset(&d, 0, sizeof(d));
+  d.nworld = nworld;
+  int nq = m.nq, nv = m.nv, nu = m.nu, ng = m.ngeom, ns = m.nsite, mc = m.maxcon;
+  rc = 0;
+  rc |= add_data(s, "qpos", &d.qpos, nq); rc |= add_data(s, "qvel", &d.qvel, nv);
+  rc |= add_data(s, "ctrl", &d.ctrl, nu); rc |= add_data(s, "qacc_warmstart", &d.qacc_warmstart, nv);
+  rc |= add_data(s, "qfrc_applied", &d.qfrc_applied, nv);
+  rc |= add_data(s, "xfrc_applied", &d.xfrc_applied, 6 * nb, 6);
+  rc |= add_data(s, "act", &d.act, 0);
+  rc |= add_data(s, "qacc", &d.qacc, nv); rc |= add_data(s, "xpos", &d.xpos, 3 * nb, 3);
+  rc |= add_data(s, "xquat", &d.xquat, 4 * nb, 4); rc |= add_data(s, "xmat", &d.xmat, 9 * nb, 9);
+  rc |= add_data(s, "xipos", &d.xipos, 3 * nb, 3); rc |= add_data(s, "subtree_com", &d.subtree_com, 3 * nb, 3);
+  rc |= add_data(s, "cvel", &d.cvel, 6 * nb, 6); rc |= add_data(s, "geom_xpos", &d.geom_xpos, 3 * ng, 3);
+  rc |= add_data(s, "geom_xmat", &d.geom_xmat, 9 * ng, 9); rc |= add_data(s, "site_xpos", &d.site_xpos, 3 * ns, 3);
+  rc |= add_data(s, "site_xmat", &d.site_xmat, 9 * ns, 9);
+  rc |= add_data(s, "sensordata", &d.sensordata, m.nsensordata);
+  rc |= add_data(s, "actuator_force", &d.actuator_force, nu); rc |= add_data(s, "time", &d.time, 1);
+  rc |= add_data(s, "qfrc_bias", &d.qfrc_bias, nv); rc |= add_data(s, "qfrc_smooth", &d.qfrc_smooth, nv);
+  rc |= add_data(s, "qacc_smooth", &d.qacc_smooth, nv);
+  rc |= add_data(s, "qfrc_constraint", &d.qfrc_constraint, nv);
+  rc |= add_data(s, "qM", &d.qM, nv * nv, nv);
+  rc |= add_data(s, "contact_dist", &d.contact_dist, mc); rc |= add_data(s, "contact_pos", &d.contact_pos, 3 * mc, 3);
+  rc |= add_data(s, "contact_frame", &d.contact_frame, 9 * mc, 9);
+  rc |= add_data(s, "contact_force", &d.contact_force, 3 * mc, 3);
+  rc |= add_data(s, "solver_cost", &d.solver_cost, 1);
+  rc |= add_idata(s, "ncon", &d.ncon, 1); rc |= add_idata(s, "nefc", &d.nefc, 1);
+  rc |= add_idata(s, "solver_niter", &d.solver_niter, 1);
+  rc |= add_idata(s, "contact_geom", &d.contact_geom, 2 * mc, 2);
+  rc |= add_idata(s, "overflow", &d.overflow, 1);
+  if (rc) { b2_destroy(s); return 1; }
+  // time is exposed as a 1-D (nworld,) tensor
+  for (Field& f : s->data_fields)
+    if (f.name == "time" || f.name == "solver_cost") { f.ndim = 1; }
+
+  // ---- shared-memory layout (floats per environment) -------------------------------------------
+  Layout& L = m.lay;
+  int off = 0;
+  auto alloc = [&](int n) { int o = off; off += pad4(std::max(n, 1)); return o; };
+  L.maxcon = mc;
+  L.nlimcap = pad4(std::max(m.njnt, 1));
+  L.maxpair = 128;
+  L.qpos = alloc(d.qpos.stride); L.qvel = alloc(d.qvel.stride); L.ctrl = alloc(d.ctrl.stride);
+  L.qacc_ws = alloc(d.qacc_warmstart.stride); L.qfrc_applied = alloc(d.qfrc_applied.stride);
+  L.xpos = alloc(d.xpos.stride); L.xquat = alloc(d.xquat.stride); L.xipos = alloc(d.xipos.stride);
+  L.scom = alloc(d.subtree_com.stride);
+  L.cdof = alloc(6 * nv); L.M = alloc(m.ntri);
+  int hsize = std::max(m.ntri, 12 * m.ncg + L.maxpair);
+  L.H = alloc(hsize); L.gpose = L.H; L.pairlist = L.H + 12 * m.ncg;
+  L.invdiag = alloc(nv);
+  L.qfrc_smooth = alloc(nv); L.qacc_smooth = alloc(nv); L.qacc = alloc(nv); L.Ma = alloc(nv);
+  L.grad = alloc(nv); L.search = alloc(nv); L.Mv = alloc(nv); L.qfrc_c = alloc(nv); L.tmpv = alloc(nv);
+  L.actf = alloc(nu);
+  int ubase = off;
+  // union A: smooth-dynamics-only regions
+  L.xfrc = alloc(d.xfrc_applied.stride); L.xanchor = alloc(3 * m.njnt); L.xaxis = alloc(3 * m.njnt);
+  L.cinert = alloc(10 * nb); L.crb = alloc(10 * nb); L.cdofdot = alloc(6 * nv); L.cvel = alloc(6 * nb);
+  L.cacc = alloc(6 * nb);
+  int endA = off;
+  off = ubase;
+  // union B: constraint / solver regions
+  L.contacts = alloc(C_NFIELD * mc); L.limits = alloc(L_NFIELD * L.nlimcap); L.gstart = alloc(mc + 1);
+  L.gmask_lo = alloc(mc); L.gmask_hi = alloc(mc); L.gV = alloc(6 * mc); L.glist = alloc(64);
+  L.gA = alloc(36); L.gu = alloc(6 * nv); L.sens = off;
+  int endB = off;
+  L.total = pad4(std::max(endA, endB));
+  s->smem_bytes = sizeof(float) * (size_t)L.total * B2_WARPS_PER_CTA;
+  if (s->smem_bytes > 227 * 1024) {
+    b2_destroy(s);
+    return fail("b2_create: model too large for the per-environment shared-memory block");
+  }
+  {
+    cudaError_t e1 = cudaFuncSetAttribute(b2_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes);
+    cudaError_t e2 = cudaFuncSetAttribute(b2_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+      b2_destroy(s);
+      return fail(std::string("cudaFuncSetAttribute(max dynamic smem): ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    }
+  }
+  // qpos <- qpos0 in every world, then one forward pass so all derived fields are valid
+  {
+    long long total = (long long)nworld * nq;
+    b2_init_rows_kernel<<<(unsigned)((total + 255) / 256), 256>>>(d.qpos.p, d.qpos.stride, m.qpos0.p, nq, nworld);
+    s->launches++;
+    if (launch(s, false, 0)) { b2_destroy(s); return 1; }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      std::string msg = std::string("b2_create: initial forward failed: ") + cudaGetErrorString(e);
+      b2_destroy(s);
+      return fail(msg);
+    }
+  }
+  *out = s;
+  return 0;
+}
+
+int b2_destroy(b2_sim* s) {
+  if (!s) return 0;
+  DeviceGuard guard(s->device);
+  for (void* p : s->allocs) cudaFree(p);
+  delete s;
+  return 0;
+}
+
+static Field* find_field(b2_sim* s, int which, const char* name) {
+  std::vector<Field>& v = which == B2_DATA ? s->data_fields : s->model_fields;
+  for (Field& f : v)
+    if (f.name == name) return &f;
+  return nullptr;
+}
+static void fill_tensor(b2_sim* s, const Field& f, B2Tensor* out) {
+  out->ptr = f.ptr; out->dtype = f.dtype; out->ndim = f.ndim; out->device = s->device;
+  for (int k = 0; k < 4; k++) { out->shape[k] = f.shape[k]; out->stride[k] = f.stride[k]; }
+}
+
+int b2_get_field(b2_sim* s, int which, const char* name, B2Tensor* out) {
+  if (!s || !name || !out) return fail("b2_get_field: bad arguments");
+  Field* f = find_field(s, which, name);
+  if (!f) return fail(std::string("b2_get_field: unknown field '") + name + "'");
+  fill_tensor(s, *f, out);
+  return 0;
+}
+int b2_num_fields(b2_sim* s, int which) {
+  return (int)(which == B2_DATA ? s->data_fields.size() : s->model_fields.size());
+}
+const char* b2_field_name(b2_sim* s, int which, int index) {
+  std::vector<Field>& v = which == B2_DATA ? s->data_fields : s->model_fields;
+  if (index < 0 || index >= (int)v.size()) return nullptr;
+  return v[index].name.c_str();
+}
+
+int b2_expand_model_field(b2_sim* s, const char* name, void* stream, B2Tensor* out) {
+  if (!s || !name) return fail("b2_expand_model_field: bad arguments");
+  Field* f = find_field(s, B2_MODEL, name);
+  if (!f || !f->farr) return fail(std::string("b2_expand_model_field: '") + name + "' is not an expandable model field");
+  DeviceGuard guard(s->device);
+  if (f->farr->stride == 0 && s->nworld > 1) {
+    int n = f->farr->n;
+    void* p = nullptr;
+    long long total = (long long)s->nworld * n;
+    CUDA_OK(cudaMalloc(&p, sizeof(float) * (size_t)total));
+    s->allocs.push_back(p);
+    b2_tile_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(f->farr->p, (float*)p, n, total);
+    s->launches++;
+    CUDA_OK(cudaGetLastError());
+    f->farr->p = (const float*)p; f->farr->stride = n;
+    f->ptr = p; f->stride[0] = n;
+  }
+  if (out) fill_tensor(s, *f, out);
+  return 0;
+}
+
+int b2_set_option(b2_sim* s, const char* key, double v) {
+  if (!s || !key) return fail("b2_set_option: bad arguments");
+  std::string k = key;
+  DevModel& m = s->hm;
+  if (k == "iterations") m.iterations = (int)v;
+  else if (k == "ls_iterations") m.ls_iterations = (int)v;
+  else if (k == "tolerance") m.tolerance = (float)v;
+  else if (k == "ls_tolerance") m.ls_tolerance = (float)v;
+  else if (k == "timestep") m.timestep = (float)v;
+  else if (k == "integrator") m.integrator = (int)v;
+  else if (k == "debug_outputs") m.debug = (int)v;
+  else if (k == "ls_parallel") { /* accepted for API parity; the line search here is exact */ }
+  else return fail("b2_set_option: unknown option '" + k + "'");
+  return 0;
+}
+int b2_get_option(b2_sim* s, const char* key, double* v) {
+  if (!s || !key || !v) return fail("b2_get_option: bad arguments");
+  std::string k = key;
+  const DevModel& m = s->hm;
+  if (k == "iterations") *v = m.iterations;
+  else if (k == "ls_iterations") *v = m.ls_iterations;
+  else if (k == "tolerance") *v = m.tolerance;
+  else if (k == "ls_tolerance") *v = m.ls_tolerance;
+  else if (k == "timestep") *v = m.timestep;
+  else if (k == "integrator") *v = m.integrator;
+  else if (k == "debug_outputs") *v = m.debug;
+  else if (k == "smem_bytes_per_env") *v = 4.0 * m.lay.total;
+  else if (k == "maxcon") *v = m.maxcon;
+  else return fail("b2_get_option: unknown option '" + k + "'");
+  return 0;
+}
+
+int b2_step(b2_sim* s, void* stream) {
+  if (!s) return fail("b2_step: null sim");
+  DeviceGuard guard(s->device);
+  return launch(s, true, (cudaStream_t)stream);
+}
+int b2_forward(b2_sim* s, void* stream) {
+  if (!s) return fail("b2_forward: null sim");
+  DeviceGuard guard(s->device);
+  return launch(s, false, (cudaStream_t)stream);
+}
+int b2_step_n(b2_sim* s, int n, void* stream) {
+  if (!s) return fail("b2_step_n: null sim");
+  DeviceGuard guard(s->device);
+  for (int i = 0; i < n; i++)
+    if (launch(s, true, (cudaStream_t)stream)) return 1;
+  return 0;
+}
+
+int b2_step_host(b2_sim* s, const float* ctrl_host, int nsubstep, float* qpos_host, float* qvel_host,
+                 void* stream) {
+  if (!s) return fail("b2_step_host: null sim");
+  DeviceGuard guard(s->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const DevModel& m = s->hm; const DevData& d = s->hd;
+  if (ctrl_host && m.nu > 0)
+    CUDA_OK(cudaMemcpy2DAsync(d.ctrl.p, sizeof(float) * d.ctrl.stride, ctrl_host, sizeof(float) * m.nu,
+                              sizeof(float) * m.nu, s->nworld, cudaMemcpyHostToDevice, st));
+  for (int i = 0; i < nsubstep; i++)
+    if (launch(s, true, st)) return 1;
+  if (qpos_host)
+    CUDA_OK(cudaMemcpy2DAsync(qpos_host, sizeof(float) * m.nq, d.qpos.p, sizeof(float) * d.qpos.stride,
+                              sizeof(float) * m.nq, s->nworld, cudaMemcpyDeviceToHost, st));
+  if (qvel_host)
+    CUDA_OK(cudaMemcpy2DAsync(qvel_host, sizeof(float) * m.nv, d.qvel.p, sizeof(float) * d.qvel.stride,
+                              sizeof(float) * m.nv, s->nworld, cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+int b2_stats(b2_sim* s, void* stream, B2Stats* out) {
+  if (!s || !out) return fail("b2_stats: bad arguments");
+  DeviceGuard guard(s->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const DevData& d = s->hd;
+  size_t n = (size_t)s->nworld;
+  std::vector<int> ncon(n * d.ncon.stride), nefc(n * d.nefc.stride), nit(n * d.solver_niter.stride), ovf(n * d.overflow.stride);
+  CUDA_OK(cudaStreamSynchronize(st));
+  CUDA_OK(cudaMemcpy(ncon.data(), d.ncon.p, sizeof(int) * ncon.size(), cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(nefc.data(), d.nefc.p, sizeof(int) * nefc.size(), cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(nit.data(), d.solver_niter.p, sizeof(int) * nit.size(), cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(ovf.data(), d.overflow.p, sizeof(int) * ovf.size(), cudaMemcpyDeviceToHost));
+  memset(out, 0, sizeof(*out));
+  out->ncon_cap = s->hm.maxcon; out->nefc_cap = s->hm.njmax;
+  double sc = 0, se = 0, si = 0;
+  for (size_t w = 0; w < n; w++) {
+    int c = ncon[w * d.ncon.stride], e = nefc[w * d.nefc.stride], it = nit[w * d.solver_niter.stride];
+    out->ncon_max = std::max(out->ncon_max, c); out->nefc_max = std::max(out->nefc_max, e);
+    out->niter_max = std::max(out->niter_max, it);
+    out->overflow_worlds += ovf[w * d.overflow.stride] ? 1 : 0;
+    sc += c; se += e; si += it;
+  }
+  out->ncon_mean = sc / n; out->nefc_mean = se / n; out->niter_mean = si / n;
+  return 0;
+}
+
+int64_t b2_launch_count(b2_sim* s) { return s ? s->launches : 0; }
+
+int b2_algorithmic_bytes(b2_sim* s, void* stream, double* solver_bytes, double* step_bytes) {
+  B2Stats st;
+  if (b2_stats(s, stream, &st)) return 1;
+  const DevModel& m = s->hm;
+  double nv = m.nv, nefc = st.nefc_mean;
+  // BASELINE.md §4 / SURVEY.md §8d: solver stage with J resident in HBM (the reference formulation)
+  double solver = 4.0 * (nefc * nv + 3.0 * nefc + nv * nv + 5.0 * nv);
+  // whole step: state in/out + consumer-visible kinematics (what this kernel actually moves)
+  double in = m.nq + m.nv + m.nu + m.nv + m.nv + 6.0 * m.nbody;
+  double outb = m.nq + 3.0 * m.nv + m.nu + m.nsensordata + (3 + 4 + 9 + 3 + 3 + 6) * (double)m.nbody +
+                12.0 * m.ngeom + 12.0 * m.nsite;
+  if (solver_bytes) *solver_bytes = solver * s->nworld;
+  if (step_bytes) *step_bytes = 4.0 * (in + outb) * s->nworld;
+  return 0;
+}
+
+}  // extern "C"
