@@ -1,0 +1,337 @@
+"""bench.py — env-steps/s of the B200-native physics step on BASELINE.json's headline workload.
+
+Workload (BASELINE.json configs[1]): Unitree G1 velocity-tracking on flat
+terrain, 4096 envs per GPU, random-action agent (``2*U(0,1)-1``, reference ``scripts/play.py:167-169``),
+dt 0.005 s, decimation 4, Newton <=10 iterations / <=20 line-search iterations, implicitfast,
+pyramidal cones, foot-friction domain randomisation, resets on fall (>70 deg) or time-out, pushes.
+
+One "step" = one environment step = ctrl write + 4 physics sub-steps (4 launches of the fused step
+kernel) + mask-based partial reset + one forward pass + the (torch) MDP glue of
+``VelocityFlatEnv.step``.  ``value`` uses device-resident actions; ``e2e`` feeds actions from pinned
+host memory and reads reward/done/obs back every step.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--envs E]
+  torchrun --nproc-per-node N bench.py --gpus N ...      (one rank per GPU, weak scaling)
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+WORKLOAD = ("Unitree G1 velocity-tracking flat, {envs} envs/GPU, random-action agent, decimation 4, "
+            "dt 0.005, Newton<=10 it / ls<=20, implicitfast, pyramidal, foot-friction DR, resets+pushes")
+
+
+def _peaks():
+  p = ROOT / "MEASURED_PEAKS.json"
+  if p.exists():
+    return float(json.loads(p.read_text())["hbm_gbs"]), "measured"
+  return 6650.0, "fallback"
+
+
+class ClockSampler:
+  """nvidia-smi clock/throttle sampling during the timed region (B200_PROFILING.md recipe)."""
+
+  Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+       "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+       "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, index: int):
+    self.index = index
+    self.proc = None
+    self.path = None
+
+  def start(self):
+    try:
+      self.path = tempfile.mktemp(suffix=".csv")
+      self.proc = subprocess.Popen(
+        ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+         "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+    except Exception:
+      self.proc = None
+
+  def stop(self):
+    if self.proc is None:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=5)
+    except Exception:
+      self.proc.kill()
+    sm, smax, reasons = [], [], set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    try:
+      for line in open(self.path):
+        f = [x.strip() for x in line.split(",")]
+        if len(f) < 9:
+          continue
+        sm.append(float(f[1]))
+        smax.append(float(f[2]))
+        for k, nm in enumerate(names):
+          if f[5 + k].lower().startswith("active"):
+            reasons.add(nm)
+    except Exception:
+      pass
+    if not sm:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+    sm.sort()
+    return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+            "samples": len(sm)}
+
+
+def cpu_reference_throughput(nthreads: int | None, budget_env_steps: int = 4, envs_per_thread: int = 24):
+  """env-steps/s of the CPU port (oracle, fp32, OpenMP over envs) on a bounded sample of the same
+  workload: keyframe + reset noise states, random actions, 4 sub-steps per env step."""
+  import numpy as np
+
+  from mjlab_b200.asset_zoo import g1, load_compiled
+  from oracle.oracle import Oracle
+
+  m = load_compiled("g1_flat")
+  probe = Oracle(m, nworld=1, precision="f32")
+  cores = nthreads or probe.max_threads()
+  n = max(cores * envs_per_thread, 8)
+  o = Oracle(m, nworld=n, maxcon=48, precision="f32")
+  rng = np.random.default_rng(42)
+  key = m.keys["robot/init_state"]
+  qpos = np.tile(key["qpos"], (n, 1))
+  qpos[:, 0:2] += rng.uniform(-0.5, 0.5, (n, 2))
+  yaw = rng.uniform(-3.14, 3.14, n)
+  qpos[:, 3], qpos[:, 6] = np.cos(yaw / 2), np.sin(yaw / 2)
+  o.qpos[:] = qpos
+  names = [x.split("/")[-1] for x in m.names["joint"][1:]]
+  import re
+  scale = np.array([next((v for p, v in g1.ACTION_SCALE.items() if re.match(p, nm)), 0.5) for nm in names])
+  # settle onto the ground first (untimed) so the sample has the contact load of the real workload
+  o.ctrl[:] = key["ctrl"]
+  for _ in range(40):
+    o.step(cores)
+  t0 = time.perf_counter()
+  for _ in range(budget_env_steps):
+    o.ctrl[:] = key["ctrl"] + scale * rng.uniform(-1, 1, (n, len(names)))
+    for _ in range(4):
+      o.step(cores)
+  dt = time.perf_counter() - t0
+  return {
+    "value": n * budget_env_steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+    "sample": f"{n} envs x {budget_env_steps} env-steps (x4 sub-steps), fp32 restated CPU oracle "
+              f"(not C-MuJoCo, not mujoco_warp-CPU), OpenMP static over envs, {dt:.1f} s",
+  }
+
+
+def run_reference(args):
+  """--impl reference: the reference's physics cannot be installed here (mujoco / mujoco_warp /
+  warp wheels absent, no network), so this arm times the CPU port of the same path on
+  all host cores.  Rank 0 only."""
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return
+  t0 = time.perf_counter()
+  vals = []
+  for _ in range(args.warmup + args.steps):
+    vals.append(cpu_reference_throughput(None, budget_env_steps=1, envs_per_thread=8))
+  timed = vals[args.warmup:]
+  v = sum(x["value"] for x in timed) / len(timed)
+  cb = dict(timed[-1])
+  cb["value"] = v
+  n_envs = int(cb["sample"].split()[0])
+  line = {
+    "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+    "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_envs / v,
+    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+    "data": "synthetic", "config": {"workload": WORKLOAD.format(envs=args.envs),
+                                     "note": "CPU port on host cores; each step a bounded sample"},
+    "cpu_baseline": cb,
+    "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    "wall_s": time.perf_counter() - t0,
+  }
+  print(json.dumps(line))
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=50)
+  ap.add_argument("--warmup", type=int, default=10)
+  ap.add_argument("--impl", default="b200")
+  ap.add_argument("--envs", type=int, default=4096)
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--no-flush", action="store_true")
+  args = ap.parse_args()
+  if args.impl == "reference":
+    return run_reference(args)
+
+  import torch
+  import torch.distributed as dist
+
+  from mjlab_b200.envs import VelocityEnvCfg, VelocityFlatEnv
+
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  torch.cuda.set_device(local)
+  dev = f"cuda:{local}"
+  if world > 1:
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device(dev))
+  W = max(args.warmup, 3)
+  K = args.steps
+  env = VelocityFlatEnv(VelocityEnvCfg(num_envs=args.envs, seed=42 + rank), device=dev)
+  n, nu = env.num_envs, env.nu
+  gen = torch.Generator(device=dev)
+  gen.manual_seed(1234 + rank)
+  flush_buf = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+  from mjlab_b200.dist import EnvLogGather
+
+  # the one collective of the data-parallel path: per-env (reward, done) to rank 0 for logging
+  gather_logs = EnvLogGather(n, dev)
+
+  def run(kind: str, steps: int, timed: bool):
+    """kind: 'device' (actions resident) or 'host' (pinned host actions, results read back)."""
+    ev = []
+    phys_ms = 0.0
+    host_actions = None
+    if kind == "host":
+      host_actions = [(torch.rand((n, nu)) * 2 - 1).pin_memory() for _ in range(steps)]
+      out_r = torch.empty(n, pin_memory=True)
+      out_d = torch.empty((n, 2), dtype=torch.bool).pin_memory()
+      out_o = None
+    for k in range(steps):
+      if flush_buf is not None:
+        flush_buf.zero_()
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record()
+      if kind == "host":
+        action = host_actions[k].to(dev, non_blocking=True)
+      else:
+        action = torch.rand((n, nu), generator=gen, device=dev) * 2 - 1
+      obs, reward, terminated, truncated, _ = env.step(action)
+      gather_logs(reward, terminated, truncated)
+      if kind == "host":
+        out_r.copy_(reward, non_blocking=True)
+        out_d.copy_(torch.stack([terminated, truncated], dim=1), non_blocking=True)
+        if out_o is None:
+          out_o = torch.empty(obs.shape, pin_memory=True)
+        out_o.copy_(obs, non_blocking=True)
+        e1.record()
+        e1.synchronize()  # the caller consumes the result before issuing the next action
+      else:
+        e1.record()
+      ev.append((e0, e1))
+    torch.cuda.synchronize()
+    total = sum(a.elapsed_time(b) for a, b in ev)
+    return total, (n * nu * 4, n * 4 + n * 2 + (obs.numel() * 4)) if kind == "host" else None
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  def maxr(x: float) -> float:
+    if world == 1:
+      return x
+    t = torch.tensor([x], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+  # ---- physics-kernel timing hook: events around the 4 sub-step launches ---------------------------
+  phys_events = []
+  orig_step_n = env.sim.step_n
+
+  def timed_step_n(k):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    orig_step_n(k)
+    b.record()
+    phys_events.append((a, b, k))
+
+  run("device", W, False)  # warm-up (untimed)
+  env.sim.step_n = timed_step_n
+  sampler = ClockSampler(local)
+  launches0 = env.sim.launch_count()
+  barrier()
+  if rank == 0:
+    sampler.start()
+  wall0 = time.perf_counter()
+  total_ms, _ = run("device", K, True)
+  barrier()
+  wall = time.perf_counter() - wall0
+  clocks = sampler.stop() if rank == 0 else None
+  launches = env.sim.launch_count() - launches0
+  total_ms = maxr(total_ms)
+  kern_ms = sum(a.elapsed_time(b) for a, b, _ in phys_events) / max(sum(k for _, _, k in phys_events), 1)
+  kern_ms = maxr(kern_ms)
+  st = env.sim.stats()
+  import ctypes
+  sb, wb = ctypes.c_double(), ctypes.c_double()
+  env.sim._lib.b2_algorithmic_bytes(env.sim._h, env.sim._stream(), ctypes.byref(sb), ctypes.byref(wb))
+  env.sim.step_n = orig_step_n
+
+  # ---- end-to-end through host buffers -----------------------------------------------------------
+  run("host", W, False)
+  barrier()
+  e2e_ms, (h2d, d2h) = run("host", K, True)
+  barrier()
+  e2e_ms = maxr(e2e_ms)
+
+  if rank == 0:
+    peak, which = _peaks()
+    value = world * n * K / (total_ms * 1e-3)
+    e2e = world * n * K / (e2e_ms * 1e-3)
+    achieved = wb.value / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / "step_kernel_traffic.json"
+    if tp.exists():
+      traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+    line = {
+      "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+      "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+      "dtype": "f32", "data": "synthetic",
+      "config": {
+        "workload": WORKLOAD.format(envs=n), "envs_per_gpu": n, "decimation": 4,
+        "parallelism": f"dp{world} (envs sharded, no physics coupling; one all-gather of reward/done)",
+        "l2": "flushed between timed steps (256 MiB memset, untimed)" if flush_buf is not None else "not flushed",
+        "mean_ncon": st.ncon_mean, "mean_nefc": st.nefc_mean, "mean_newton_iters": st.niter_mean,
+        "overflow_worlds": st.overflow_worlds,
+      },
+      "clocks": clocks,
+      "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+              "ms_per_step": e2e_ms / K},
+      "gpu_launches": int(launches),
+      "roofline": {
+        "kernel": "b2_step_kernel<true> (fused physics sub-step)", "bound": "hbm",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "peak_source": which, "traffic": traffic, "kernel_ms": kern_ms,
+        "algorithmic_bytes_per_launch": wb.value,
+        "note": "whole-step minimal traffic (state in/out + consumer-visible kinematics); the kernel is "
+                "latency/ALU bound, the constraint Jacobian never exists in HBM",
+        "solver_formula_gbs": sb.value / (kern_ms * 1e-3) / 1e9,
+      },
+      "physics_only_env_steps_per_sec": world * n / (4 * kern_ms * 1e-3),
+      "wall_s": wall,
+    }
+    if not args.no_cpu_baseline and world == 1:
+      try:
+        line["cpu_baseline"] = cpu_reference_throughput(None)
+      except Exception as e:  # the oracle is test infrastructure; never fail the bench on it
+        line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
+                                "sample": f"failed: {e}"}
+    print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+  main()

@@ -1,0 +1,186 @@
+"""Slim velocity-tracking flat-terrain environment: the *caller* of the hot path.
+
+Follows the control flow of the reference's ``ManagerBasedRlEnv.step``
+(``src/mjlab/envs/manager_based_rl_env.py:106-147``) for the velocity task
+(``tasks/velocity/velocity_env_cfg.py``): process action -> ``decimation`` x {write ctrl,
+``sim.step``} -> terminations -> rewards -> reset terminated envs + ``sim.forward`` -> commands
+-> interval push event -> observations.  The manager/term machinery is not rebuilt (out of scope,
+SURVEY.md §2 rows 6-8); terms are fused torch expressions and resets are mask-based so the step
+has no host synchronisation.
+"""
+
+from __future__ import annotations
+
+import math
+import re
+from dataclasses import dataclass, field
+
+import torch
+
+from mjlab_b200.asset_zoo import g1, go1, load_compiled
+from mjlab_b200.sim import MujocoCfg, Simulation, SimulationCfg
+
+
+@dataclass
+class VelocityEnvCfg:
+  robot: str = "g1"
+  num_envs: int = 4096
+  decimation: int = 4                      # velocity_env_cfg.py:271
+  episode_length_s: float = 20.0           # :272
+  fall_angle: float = math.radians(70.0)   # :241-243
+  push_interval_s: tuple = (1.0, 3.0)      # :156-161
+  push_vel: float = 0.5                    # flat_env_cfg.py:20-24
+  friction_range: tuple = (0.3, 1.2)       # :162-172
+  env_spacing: float = 2.5
+  seed: int = 42
+  sim: SimulationCfg = field(
+    default_factory=lambda: SimulationCfg(
+      nconmax=140_000, njmax=300,
+      mujoco=MujocoCfg(timestep=0.005, iterations=10, ls_iterations=20),
+    )
+  )
+
+
+def _resolve(pattern_map: dict, names: list[str], default: float) -> list[float]:
+  out = []
+  for n in names:
+    for pat, v in pattern_map.items():
+      if re.match(pat, n):
+        out.append(v)
+        break
+    else:
+      out.append(default)
+  return out
+
+
+def quat_rotate_inverse(q: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+  w, u = q[:, 0:1], q[:, 1:4]
+  t = 2.0 * torch.cross(u, v, dim=-1)
+  return v - w * t + torch.cross(u, t, dim=-1)
+
+
+class VelocityFlatEnv:
+  def __init__(self, cfg: VelocityEnvCfg, device: str = "cuda:0", model=None):
+    self.cfg = cfg
+    self.device = device
+    zoo = g1 if cfg.robot == "g1" else go1
+    self.model = model if model is not None else load_compiled(f"{cfg.robot}_flat")
+    m = self.model
+    self.num_envs = cfg.num_envs
+    self.sim = Simulation(cfg.num_envs, cfg.sim, m, device)
+    self.nq, self.nv, self.nu = int(m.nq), int(m.nv), int(m.nu)
+    self.step_dt = cfg.decimation * float(m.opt_timestep)
+    self.max_episode_length = math.ceil(cfg.episode_length_s / self.step_dt)
+    dev = torch.device(device)
+    self.gen = torch.Generator(device=dev)
+    self.gen.manual_seed(cfg.seed)
+    key = m.keys["robot/init_state"]
+    f32 = dict(dtype=torch.float32, device=dev)
+    self.default_qpos = torch.tensor(key["qpos"], **f32)
+    self.default_joint_pos = self.default_qpos[7:].clone()
+    jnames = [n.split("/")[-1] for n in m.names["joint"][1:]]
+    self.action_scale = torch.tensor(_resolve(zoo.ACTION_SCALE, jnames, 0.5), **f32)
+    rng = torch.tensor(m.jnt_range[1:], **f32)
+    mid, half = rng.mean(dim=1), 0.5 * (rng[:, 1] - rng[:, 0]) * 0.9  # soft limits (entity.py:372-380)
+    self.soft_lo, self.soft_hi = mid - half, mid + half
+    # env origins on a grid (terrain_importer.py:203-223 for the flat case)
+    n = cfg.num_envs
+    cols = math.ceil(math.sqrt(n))
+    idx = torch.arange(n, device=dev)
+    self.env_origins = torch.stack(
+      [(idx // cols - (cols - 1) / 2) * cfg.env_spacing, (idx % cols - (cols - 1) / 2) * cfg.env_spacing,
+       torch.zeros(n, device=dev)], dim=1).float()
+    # startup domain randomisation: foot friction (events.py:212-265 'abs' on geom_friction[:, feet, 0])
+    self.sim.expand_model_fields(["geom_friction"])
+    foot_ids = torch.tensor(
+      [m.names["geom"].index(f"robot/{g}") for g in zoo.FOOT_GEOMS], device=dev, dtype=torch.long
+    )
+    lo, hi = cfg.friction_range
+    mu = torch.rand((n, len(foot_ids)), generator=self.gen, device=dev) * (hi - lo) + lo
+    self.sim.model.geom_friction[:, foot_ids, 0] = mu
+    self.episode_length_buf = torch.zeros(n, dtype=torch.long, device=dev)
+    self.last_action = torch.zeros(n, self.nu, **f32)
+    self.command = torch.zeros(n, 3, **f32)
+    self.command_time_left = torch.zeros(n, **f32)
+    self.push_time_left = torch.zeros(n, **f32)
+    self._sample_timers(torch.ones(n, dtype=torch.bool, device=dev))
+    self.reset()
+
+  # -- helpers -----------------------------------------------------------------------------------
+  def _rand(self, *shape):
+    return torch.rand(shape, generator=self.gen, device=self.device)
+
+  def _sample_timers(self, mask):
+    lo, hi = self.cfg.push_interval_s
+    self.push_time_left = torch.where(mask, self._rand(self.num_envs) * (hi - lo) + lo, self.push_time_left)
+
+  def _reset_where(self, mask: torch.Tensor) -> None:
+    """reset_root_state_uniform + reset_joints_by_scale (envs/mdp/events.py:43-124) for masked envs."""
+    d = self.sim.data
+    n = self.num_envs
+    qpos = self.default_qpos.expand(n, -1).clone()
+    qpos[:, 0:2] += (self._rand(n, 2) - 0.5) + self.env_origins[:, 0:2]
+    yaw = (self._rand(n) * 2 - 1) * 3.14
+    qpos[:, 3] = torch.cos(0.5 * yaw)
+    qpos[:, 6] = torch.sin(0.5 * yaw)
+    qpos[:, 7:] = torch.minimum(torch.maximum(qpos[:, 7:], self.soft_lo), self.soft_hi)
+    mk = mask.unsqueeze(1)
+    d.qpos[:] = torch.where(mk, qpos, d.qpos[:])
+    d.qvel[:] = torch.where(mk, torch.zeros_like(d.qvel[:]), d.qvel[:])
+    d.ctrl[:] = torch.where(mk, self.default_joint_pos.expand(n, -1), d.ctrl[:])
+    self.episode_length_buf = torch.where(mask, torch.zeros_like(self.episode_length_buf), self.episode_length_buf)
+    self.last_action = torch.where(mk, torch.zeros_like(self.last_action), self.last_action)
+    # command resample (UniformVelocityCommand, velocity_env_cfg.py:66-83)
+    cmd = torch.stack([self._rand(n) * 2 - 1, self._rand(n) - 0.5, self._rand(n) * 2 - 1], dim=1)
+    self.command = torch.where(mk, cmd, self.command)
+
+  def observations(self) -> torch.Tensor:
+    d = self.sim.data
+    q = d.qpos[:, 3:7]
+    lin_b = quat_rotate_inverse(q, d.qvel[:, 0:3])
+    grav = torch.tensor([0.0, 0.0, -1.0], device=self.device).expand(self.num_envs, 3)
+    return torch.cat(
+      [lin_b, d.qvel[:, 3:6], quat_rotate_inverse(q, grav), d.qpos[:, 7:] - self.default_joint_pos,
+       d.qvel[:, 6:], self.last_action, self.command], dim=1)
+
+  # -- API ---------------------------------------------------------------------------------------
+  def reset(self):
+    self._reset_where(torch.ones(self.num_envs, dtype=torch.bool, device=self.device))
+    self.sim.forward()
+    return self.observations()
+
+  def step(self, action: torch.Tensor):
+    cfg, d = self.cfg, self.sim.data
+    # JointPositionAction: target = default + scale * action (joint_actions.py:85-103)
+    d.ctrl[:] = self.default_joint_pos + self.action_scale * action
+    self.sim.step_n(cfg.decimation)
+    self.episode_length_buf += 1
+    q = d.qpos[:, 3:7]
+    grav_b = quat_rotate_inverse(
+      q, torch.tensor([0.0, 0.0, -1.0], device=self.device).expand(self.num_envs, 3))
+    terminated = torch.acos((-grav_b[:, 2]).clamp(-1.0, 1.0)) > cfg.fall_angle  # bad_orientation
+    truncated = self.episode_length_buf >= self.max_episode_length              # time_out
+    # rewards (velocity_env_cfg.py:183-214): tracking, posture, limits, action rate
+    lin_b = quat_rotate_inverse(q, d.qvel[:, 0:3])
+    r_lin = torch.exp(-((self.command[:, :2] - lin_b[:, :2]) ** 2).sum(1) / 0.25)
+    r_ang = torch.exp(-((self.command[:, 2] - d.qvel[:, 5]) ** 2) / 0.25)
+    jp = d.qpos[:, 7:]
+    r_pose = torch.exp(-((jp - self.default_joint_pos) ** 2).mean(1) / 0.09)
+    r_lim = -((self.soft_lo - jp).clamp(min=0) + (jp - self.soft_hi).clamp(min=0)).sum(1)
+    r_rate = -0.1 * ((action - self.last_action) ** 2).sum(1)
+    reward = (r_lin + r_ang + r_pose + r_lim + r_rate) * self.step_dt
+    self.last_action = action
+    done = terminated | truncated
+    # partial reset + forward (manager_based_rl_env.py:128-132), mask-based: no host sync
+    self._reset_where(done)
+    self.sim.forward()
+    # interval event: push_by_setting_velocity (events.py:127-143)
+    self.push_time_left -= self.step_dt
+    push = self.push_time_left <= 0
+    pv = (self._rand(self.num_envs, 2) * 2 - 1) * cfg.push_vel
+    d.qvel[:, 0:2] = torch.where(push.unsqueeze(1), pv, d.qvel[:, 0:2])
+    self._sample_timers(push)
+    return self.observations(), reward, terminated, truncated, {}
+
+  def close(self):
+    self.sim.close()

@@ -4,8 +4,9 @@ from pathlib import Path
 import pytest
 
 ROOT = Path(__file__).resolve().parents[1]
-if str(ROOT) not in sys.path:
-  sys.path.insert(0, str(ROOT))
+for p_ in (str(ROOT), str(ROOT / "tests")):
+  if p_ not in sys.path:
+    sys.path.insert(0, p_)
 
 
 def pytest_configure(config):

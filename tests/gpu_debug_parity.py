@@ -7,7 +7,8 @@ sys.path.insert(0, ".")
 from mjlab_b200.asset_zoo import load_compiled
 from mjlab_b200.sim import Simulation, SimulationCfg
 from oracle.oracle import Oracle
-from tests.util import load_oracle, load_sim, make_states, relerr
+sys.path.insert(0, "tests")
+from util import load_oracle, load_sim, make_states, relerr
 
 name = sys.argv[1] if len(sys.argv) > 1 else "g1_flat"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 64

@@ -1,0 +1,186 @@
+"""Boundary contract on the GPU: what the reference pins in tests/test_sim_data.py,
+tests/test_entity.py:292-388, tests/smoke_test.py:21-22 and tests/test_nan_guard.py, restated
+against our Simulation."""
+
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BOX_XML = """
+<mujoco>
+  <worldbody>
+    <body name="box" pos="0 0 1">
+      <freejoint name="free"/>
+      <geom name="box_geom" type="box" size="0.1 0.1 0.1" mass="1.0"/>
+    </body>
+  </worldbody>
+</mujoco>
+"""
+
+
+def _box_sim(n=3):
+  from mjlab_b200.compiler import Spec
+  from mjlab_b200.sim import Simulation, SimulationCfg
+
+  m = Spec.from_string(BOX_XML).compile()
+  return Simulation(n, SimulationCfg(), m, "cuda:0"), m
+
+
+def test_time_zero_and_derived_fields_valid_after_construction(g1_model):
+  from mjlab_b200.sim import Simulation, SimulationCfg
+
+  sim = Simulation(2, SimulationCfg(), g1_model, "cuda:0")
+  assert float(sim.data.time[0]) == 0.0  # tests/smoke_test.py:22
+  assert sim.data.nworld == 2
+  # forward ran at qpos0: pelvis at its XML height, kinematics populated
+  assert float(sim.data.xpos[0, 2, 2]) == pytest.approx(0.793, abs=1e-5)
+  assert float(sim.data.xquat[0, 2, 0]) == pytest.approx(1.0)
+  sim.close()
+
+
+def test_bridge_is_read_only_and_views_share_memory():
+  sim, _ = _box_sim()
+  with pytest.raises(AttributeError, match="Cannot set attribute"):
+    sim.data.qpos = torch.zeros(1)
+  q = sim.data.qpos
+  assert q is sim.data.qpos  # wrapper cache
+  ptr = q.data_ptr()
+  q[:] = 7.0
+  assert q.data_ptr() == ptr  # slice-assign keeps the address (CUDA-graph safety)
+  assert float(sim.wp_data.qpos[1, 0]) == 7.0
+  assert torch.sum(q).item() == pytest.approx(7.0 * 3 * 7)  # torch functions accept the wrapper
+  assert ((q + 1)[0, 0]).item() == 8.0
+  sim.close()
+
+
+def test_free_fall_and_applied_wrench_qualitative():
+  """tests/test_entity.py:292-330: gravity pulls down; +x force moves +x; z torque spins about z."""
+  sim, m = _box_sim(3)
+  sim.step()
+  assert (sim.data.qvel[:, 2] < 0).all()
+  sim.data.qvel[:] = 0
+  sim.data.xfrc_applied[:, 1, 0] = 10.0
+  x0 = sim.data.qpos[:, 0].clone()
+  for _ in range(10):
+    sim.step()
+  assert (sim.data.qpos[:, 0] > x0).all()
+  sim.data.xfrc_applied[:] = 0
+  sim.data.qvel[:] = 0
+  sim.data.xfrc_applied[:, 1, 5] = 1.0
+  for _ in range(10):
+    sim.step()
+  w = sim.data.qvel[0, 3:6].abs()
+  assert w[2] > 5 * max(w[0], w[1])
+  # a huge force does not produce NaN (tests/test_entity.py:378-388)
+  sim.data.xfrc_applied[:, 1, 0] = 1e6
+  sim.step()
+  assert torch.isfinite(sim.data.qpos[:]).all()
+  sim.close()
+
+
+def test_free_fall_matches_analytic():
+  sim, m = _box_sim(1)
+  sim.data.qpos[:, 2] = 5.0
+  n = 50
+  for _ in range(n):
+    sim.step()
+  h = float(m.opt_timestep)
+  # semi-implicit Euler: v_k = -g k h, z_k = z0 - g h^2 k(k+1)/2
+  assert float(sim.data.qvel[0, 2]) == pytest.approx(-9.81 * n * h, rel=1e-5)
+  assert float(sim.data.qpos[0, 2]) == pytest.approx(5.0 - 9.81 * h * h * n * (n + 1) / 2, rel=1e-5)
+  sim.close()
+
+
+def test_nan_guard_dumps_once(tmp_path):
+  from mjlab_b200.compiler import Spec
+  from mjlab_b200.sim import Simulation, SimulationCfg
+  from mjlab_b200.utils.nan_guard import NanGuardCfg
+
+  m = Spec.from_string(BOX_XML).compile()
+  cfg = SimulationCfg(nan_guard=NanGuardCfg(enabled=True, output_dir=str(tmp_path)))
+  sim = Simulation(4, cfg, m, "cuda:0")
+  sim.step()
+  assert not list(tmp_path.glob("*.npz"))
+  sim.data.qpos[1, 0] = float("nan")  # fault injection as in tests/test_nan_guard.py:70
+  sim.step()
+  dumps = list(tmp_path.glob("*.npz"))
+  assert len(dumps) == 1
+  z = np.load(dumps[0])
+  assert 1 in z["nan_env_ids"]
+  sim.step()
+  assert len(list(tmp_path.glob("*.npz"))) == 1
+  sim.close()
+
+
+def test_c_abi_host_buffer_step(g1_model):
+  """b2_step_host: host ctrl in, qpos/qvel out, equals the device-side path."""
+  from mjlab_b200.sim import Simulation, SimulationCfg
+
+  n = 16
+  a = Simulation(n, SimulationCfg(), g1_model, "cuda:0")
+  b = Simulation(n, SimulationCfg(), g1_model, "cuda:0")
+  key = g1_model.keys["robot/init_state"]
+  for s in (a, b):
+    s.data.qpos[:] = torch.tensor(key["qpos"], device="cuda:0", dtype=torch.float32)
+  ctrl = (np.tile(key["ctrl"], (n, 1)) + 0.1).astype(np.float32)
+  nq, nv = int(g1_model.nq), int(g1_model.nv)
+  qpos = np.zeros((n, nq), np.float32)
+  qvel = np.zeros((n, nv), np.float32)
+  stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+  rc = a._lib.b2_step_host(a._h, ctrl.ctypes.data_as(ctypes.c_void_p), 4,
+                           qpos.ctypes.data_as(ctypes.c_void_p), qvel.ctypes.data_as(ctypes.c_void_p), stream)
+  assert rc == 0
+  torch.cuda.synchronize()
+  b.data.ctrl[:] = torch.tensor(ctrl, device="cuda:0")
+  b.step_n(4)
+  torch.cuda.synchronize()
+  assert (qpos == b.data.qpos[:].cpu().numpy()).all()
+  assert (qvel == b.data.qvel[:].cpu().numpy()).all()
+  assert a.launch_count() >= 4
+  a.close()
+  b.close()
+
+
+def test_cuda_graph_replay_matches_eager(g1_model):
+  from mjlab_b200.sim import Simulation, SimulationCfg
+  from util import load_sim, make_states
+
+  st = make_states(g1_model, 8, seed=3)
+  a = Simulation(8, SimulationCfg(), g1_model, "cuda:0")
+  b = Simulation(8, SimulationCfg(), g1_model, "cuda:0")
+  b.use_cuda_graph = True
+  b.create_graph()
+  load_sim(a, st)
+  load_sim(b, st)
+  for _ in range(3):
+    a.step()
+    b.step()
+  b.expand_model_fields(["geom_friction"])  # graphs are re-captured lazily after expansion
+  a.expand_model_fields(["geom_friction"])
+  a.step()
+  b.step()
+  torch.cuda.synchronize()
+  assert (a.data.qpos[:] == b.data.qpos[:]).all()
+  a.close()
+  b.close()
+
+
+def test_velocity_env_runs_and_resets():
+  from mjlab_b200.envs import VelocityEnvCfg, VelocityFlatEnv
+
+  env = VelocityFlatEnv(VelocityEnvCfg(num_envs=64), device="cuda:0")
+  obs = env.reset()
+  assert obs.shape == (64, 3 + 3 + 3 + 29 + 29 + 29 + 3)
+  total_done = 0
+  for _ in range(60):
+    a = torch.rand((64, 29), device="cuda:0") * 2 - 1
+    obs, r, term, trunc, _ = env.step(a)
+    total_done += int(term.sum())
+  assert torch.isfinite(obs).all() and torch.isfinite(r).all()
+  assert total_done > 0  # random actions make G1 fall within ~1 s; those envs were reset
+  assert (env.sim.data.qpos[:, 2] > 0.2).all()
+  env.close()

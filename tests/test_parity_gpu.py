@@ -1,0 +1,221 @@
+"""CUDA path vs CPU oracle (fp64) through the public boundary (Simulation -> C ABI -> kernel).
+
+Tolerances (written here as the north_star requires): one forward / one step from identical
+states, norm-wise relative error per env, fp32 engine vs fp64 oracle:
+  kinematics / inertia / bias forces      1e-5
+  unconstrained acceleration              1e-4   (35x35 fp32 Cholesky)
+  constrained acceleration, state after a step   1e-3 worst env, 1e-4 median
+Contacts (count, geoms, order) must be identical; integer outputs are bit-exact.
+"""
+
+import numpy as np
+import pytest
+import torch
+
+from util import load_oracle, load_sim, make_states, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def T(x):
+  return x[:].detach().cpu().numpy()
+
+
+def _pair(model, n, seed, **kw):
+  from mjlab_b200.sim import Simulation, SimulationCfg
+  from oracle.oracle import Oracle
+
+  sim = Simulation(n, SimulationCfg(), model, "cuda:0")
+  sim.set_option("debug_outputs", 1)
+  o = Oracle(model, nworld=n, maxcon=int(sim.get_option("maxcon")))
+  st = make_states(model, n, seed=seed, **kw)
+  load_oracle(o, st)
+  load_sim(sim, st)
+  return sim, o, st
+
+
+@pytest.mark.parametrize("name", ["g1_flat", "go1_flat", "g1_tracking_flat"])
+def test_forward_parity(name):
+  from mjlab_b200.asset_zoo import load_compiled
+
+  m = load_compiled(name)
+  n = 96
+  sim, o, _ = _pair(m, n, seed=11)
+  o.forward()
+  sim.forward()
+  torch.cuda.synchronize()
+  d = sim.data
+  assert (T(d.ncon).ravel() == o.ncon.ravel()).all()
+  assert (T(d.nefc).ravel() == o.nefc.ravel()).all()
+  nc = o.ncon.ravel()
+  cg, og = T(d.contact_geom), o.contact_geom.reshape(n, -1, 2)
+  for w in range(n):
+    assert (cg[w, : nc[w]] == og[w, : nc[w]]).all()
+  tight = ["xpos", "xquat", "xmat", "xipos", "subtree_com", "cvel", "geom_xpos", "geom_xmat",
+           "site_xpos", "site_xmat", "actuator_force", "qfrc_bias", "qfrc_smooth", "qM"]
+  for f in tight:
+    e = relerr(T(getattr(d, f)).reshape(n, -1), o.field(f).reshape(n, -1)).max()
+    assert e < 1e-5, (f, e)
+  assert relerr(T(d.qacc_smooth), o.qacc_smooth).max() < 1e-4
+  e = relerr(T(d.qacc), o.qacc)
+  assert e.max() < 1e-3 and np.median(e) < 1e-4, (e.max(), np.median(e))
+  e = relerr(T(d.qfrc_constraint), o.qfrc_constraint)
+  assert e.max() < 1e-3, e.max()
+  # contact outputs
+  for w in range(n):
+    k = nc[w]
+    if k:
+      assert np.abs(T(d.contact_dist)[w, :k] - o.contact_dist[w, :k]).max() < 1e-5
+      assert np.abs(T(d.contact_pos)[w, :k].ravel() - o.contact_pos[w, : 3 * k]).max() < 1e-4
+      cf = np.abs(T(d.contact_force)[w, :k].ravel() - o.contact_force[w, : 3 * k]).max()
+      assert cf < 1e-3 * max(1.0, np.abs(o.contact_force[w]).max()), cf
+  assert np.abs(T(d.sensordata) - o.sensordata).max() < 1e-3
+  sim.close()
+
+
+@pytest.mark.parametrize("name", ["g1_flat", "go1_flat"])
+def test_step_parity(name):
+  from mjlab_b200.asset_zoo import load_compiled
+
+  m = load_compiled(name)
+  n = 96
+  sim, o, _ = _pair(m, n, seed=5)
+  o.step()
+  sim.step()
+  torch.cuda.synchronize()
+  d = sim.data
+  for f, tol in (("qpos", 1e-5), ("qvel", 1e-3), ("qacc_warmstart", 1e-3)):
+    e = relerr(T(getattr(d, f)), o.field(f))
+    assert e.max() < tol, (f, e.max())
+  assert np.allclose(T(d.time), float(m.opt_timestep))
+  # a short rollout stays close (contact dynamics diverge slowly; 5 steps only)
+  for _ in range(4):
+    o.step()
+    sim.step()
+  torch.cuda.synchronize()
+  assert np.median(relerr(T(d.qpos), o.qpos)) < 1e-5
+  assert np.median(relerr(T(d.qvel), o.qvel)) < 1e-3
+  sim.close()
+
+
+def test_go1_single_env_zero_action(go1_model):
+  """BASELINE.json configs[0]: single-env Go1 flat, zero-action agent."""
+  from mjlab_b200.sim import Simulation, SimulationCfg
+  from oracle.oracle import Oracle
+
+  m = go1_model
+  sim = Simulation(1, SimulationCfg(), m, "cuda:0")
+  o = Oracle(m, nworld=1, maxcon=int(sim.get_option("maxcon")))
+  key = m.keys["robot/init_state"]
+  sim.data.qpos[:] = torch.tensor(key["qpos"], device="cuda:0", dtype=torch.float32)
+  o.qpos[:] = key["qpos"]
+  # zero action -> ctrl = default joint pos (use_default_offset=True, velocity_env_cfg.py:56-62)
+  sim.data.ctrl[:] = torch.tensor(key["ctrl"], device="cuda:0", dtype=torch.float32)
+  o.ctrl[:] = key["ctrl"]
+  for _ in range(40):
+    sim.step()
+    o.step()
+  torch.cuda.synchronize()
+  assert relerr(T(sim.data.qpos), o.qpos).max() < 1e-3
+  assert 0.2 < float(sim.data.qpos[0, 2]) < 0.35  # standing on its feet
+  assert int(sim.data.ncon[0]) >= 4
+  sim.close()
+
+
+def test_euler_integrator_parity(g1_model):
+  sim, o, st = _pair(g1_model, 32, seed=9)
+  sim.set_option("integrator", 0)
+  o.set_option("integrator", 0)
+  o.step()
+  sim.step()
+  torch.cuda.synchronize()
+  assert relerr(T(sim.data.qvel), o.qvel).max() < 1e-3
+  sim.close()
+
+
+def test_applied_forces_parity(g1_model):
+  sim, o, st = _pair(g1_model, 32, seed=21)
+  rng = np.random.default_rng(0)
+  nb, nv = int(g1_model.nbody), int(g1_model.nv)
+  xf = np.zeros((32, nb, 6))
+  xf[:, 2:, :] = rng.uniform(-20, 20, (32, nb - 2, 6)) * (rng.uniform(size=(32, nb - 2, 1)) < 0.3)
+  qf = rng.uniform(-5, 5, (32, nv))
+  sim.data.xfrc_applied[:] = torch.tensor(xf, device="cuda:0", dtype=torch.float32)
+  sim.data.qfrc_applied[:] = torch.tensor(qf, device="cuda:0", dtype=torch.float32)
+  o.xfrc_applied[:] = xf.reshape(32, -1)
+  o.qfrc_applied[:] = qf
+  o.forward()
+  sim.forward()
+  torch.cuda.synchronize()
+  assert relerr(T(sim.data.qfrc_smooth), o.qfrc_smooth).max() < 1e-5
+  assert relerr(T(sim.data.qacc), o.qacc).max() < 1e-3
+  sim.close()
+
+
+def test_bitwise_determinism(g1_model):
+  from mjlab_b200.sim import Simulation, SimulationCfg
+
+  outs = []
+  for _ in range(2):
+    sim = Simulation(64, SimulationCfg(), g1_model, "cuda:0")
+    load_sim(sim, make_states(g1_model, 64, seed=2))
+    for _ in range(10):
+      sim.step()
+    torch.cuda.synchronize()
+    outs.append((T(sim.data.qpos).copy(), T(sim.data.qvel).copy(), T(sim.data.contact_geom).copy()))
+    sim.close()
+  for a, b in zip(outs[0], outs[1]):
+    assert (a == b).all()  # contact order and every float are reproducible (upstream is not)
+
+
+def test_full_size_properties(g1_model):
+  """BASELINE.json configs[1] size (4096 envs): size-independent properties."""
+  from mjlab_b200.sim import Simulation, SimulationCfg
+
+  n = 4096
+  sim = Simulation(n, SimulationCfg(nconmax=140_000, njmax=300), g1_model, "cuda:0")
+  st = make_states(g1_model, n, seed=7, z_range=(-0.01, 0.02), tilt=0.05, joint_noise=0.05, vel=0.1)
+  load_sim(sim, st)
+  for _ in range(20):
+    sim.step()
+  torch.cuda.synchronize()
+  d = sim.data
+  assert torch.isfinite(d.qpos[:]).all() and torch.isfinite(d.qvel[:]).all()
+  assert torch.allclose(d.qpos[:, 3:7].norm(dim=1), torch.ones(n, device="cuda:0"), atol=1e-5)
+  assert torch.allclose(d.time[:], torch.full((n,), 20 * 0.005, device="cuda:0"), atol=1e-5)
+  # replicated envs give replicated results: env w and env w + n/2 loaded with the same state
+  st2 = {k: np.concatenate([v[: n // 2], v[: n // 2]]) for k, v in st.items()}
+  load_sim(sim, st2)
+  for _ in range(5):
+    sim.step()
+  torch.cuda.synchronize()
+  assert (d.qpos[: n // 2] == d.qpos[n // 2 :]).all()
+  # contact normal forces are non-negative and sensors count ground contacts of the feet
+  assert (d.contact_force[:, :, 0] >= 0).all()
+  s = sim.stats()
+  assert s.overflow_worlds == 0 and s.ncon_max <= s.ncon_cap
+  sim.close()
+
+
+def test_domain_randomization_fields(g1_model):
+  """expand_model_fields + per-world write (reference tests/test_domain_randomization.py)."""
+  from mjlab_b200.sim import Simulation, SimulationCfg
+
+  sim = Simulation(4, SimulationCfg(), g1_model, "cuda:0")
+  with pytest.raises(ValueError, match="Fields not found in model"):
+    sim.expand_model_fields(["not_a_field"])
+  assert sim.model.geom_friction.shape == (4, int(g1_model.ngeom), 3)
+  sim.expand_model_fields(["geom_friction", "body_mass", "dof_damping"])
+  gf = sim.model.geom_friction
+  assert gf.stride(0) == int(g1_model.ngeom) * 3
+  gf[2, :, 0] = 0.123
+  assert float(sim.model.geom_friction[2, 5, 0]) == pytest.approx(0.123)
+  assert float(sim.model.geom_friction[1, 5, 0]) != pytest.approx(0.123)
+  # friction actually changes the physics of that world only
+  load_sim(sim, {k: np.repeat(v[:1], 4, 0) for k, v in make_states(g1_model, 1, seed=4, z_range=(-0.02, -0.02), vel=1.0).items()})
+  sim.step()
+  torch.cuda.synchronize()
+  qv = T(sim.data.qvel)
+  assert np.abs(qv[0] - qv[1]).max() == 0.0
+  assert np.abs(qv[0] - qv[2]).max() > 0.0
+  sim.close()
