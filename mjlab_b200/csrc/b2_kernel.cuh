@@ -154,58 +154,90 @@ __device__ __forceinline__ void fence_async_smem() {
 
 #define MP(arr) (m.arr.p + (size_t)w * m.arr.stride)
 
+#ifdef B2_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[32];
+#define PHASE_MARK(id)                                                        \
+  do {                                                                        \
+    __syncwarp();                                                             \
+    long long now_ = clock64();                                               \
+    if (lane == 0) atomicAdd(&g_phase_cycles[id], (unsigned long long)(now_ - tphase_)); \
+    tphase_ = now_;                                                           \
+  } while (0)
+#else
+#define PHASE_MARK(id)
+#endif
+
 // ---- dense packed Cholesky (lower, row-major packed) in shared memory ---------------------------
 // Balanced schedule: the trailing-triangle update of step k runs over a precomputed list of (i,j)
-// pairs ordered by descending j, so every lane gets the same number of pairs.
-__device__ __forceinline__ void chol_factor(float* A, float* invdiag, int n, int ntri,
-                                            const unsigned short* __restrict__ coldesc, int lane) {
+// pairs ordered by descending j, so every lane gets the same number of pairs.  Each table word packs
+// the row bases of i and j and the column j: rb_i | rb_j << 11 | j << 22.
+__device__ __noinline__ void chol_factor(float* A, float* invdiag, int n,
+                                         const unsigned* __restrict__ coldesc, int lane) {
+  #pragma unroll 1
   for (int k = 0; k < n; k++) {
-    float akk = A[tri(k, k)];
-    float d = sqrtf(fmaxf(akk, MINVAL));
-    float inv = 1.f / d;
-    for (int i = k + 1 + lane; i < n; i += 32) A[tri(i, k)] *= inv;
-    if (lane == 0) { A[tri(k, k)] = d; invdiag[k] = inv; }
+    int rk = k * (k + 1) >> 1;
+    float akk = A[rk + k];
+    float inv = rsqrtf(fmaxf(akk, MINVAL));
+    #pragma unroll 1
+    for (int i = k + 1 + lane; i < n; i += 32) A[(i * (i + 1) >> 1) + k] *= inv;
+    if (lane == 0) { A[rk + k] = akk * inv; invdiag[k] = inv; }
     __syncwarp();
     int mtr = n - k - 1;
     int np = mtr * (mtr + 1) >> 1;
-    for (int p = lane; p < np; p += 32) {
-      unsigned short e = coldesc[p];
-      int i = e & 0xff, j = e >> 8;
-      A[tri(i, j)] -= A[tri(i, k)] * A[tri(j, k)];
+    int p = lane;
+    for (; p + 32 < np; p += 64) {
+      unsigned e0 = coldesc[p], e1 = coldesc[p + 32];
+      int ri0 = e0 & 0x7ff, rj0 = (e0 >> 11) & 0x7ff, j0 = e0 >> 22;
+      int ri1 = e1 & 0x7ff, rj1 = (e1 >> 11) & 0x7ff, j1 = e1 >> 22;
+      float a0 = A[ri0 + k], b0 = A[rj0 + k], a1 = A[ri1 + k], b1 = A[rj1 + k];
+      float c0 = A[ri0 + j0], c1 = A[ri1 + j1];
+      A[ri0 + j0] = c0 - a0 * b0;
+      A[ri1 + j1] = c1 - a1 * b1;
+    }
+    if (p < np) {
+      unsigned e0 = coldesc[p];
+      int ri0 = e0 & 0x7ff, rj0 = (e0 >> 11) & 0x7ff, j0 = e0 >> 22;
+      A[ri0 + j0] -= A[ri0 + k] * A[rj0 + k];
     }
     __syncwarp();
   }
-  (void)ntri;
 }
 // x <- (L L^T)^-1 x, x in shared memory (n <= 64). Values are held in registers during the sweeps.
-__device__ __forceinline__ void chol_solve(const float* L, const float* invdiag, float* x, int n,
-                                           int lane) {
+__device__ __noinline__ void chol_solve(const float* L, const float* invdiag, float* x, int n,
+                                        int lane) {
   float x0 = lane < n ? x[lane] : 0.f;
   float x1 = lane + 32 < n ? x[lane + 32] : 0.f;
+  const int r0 = lane * (lane + 1) >> 1, r1 = (lane + 32) * (lane + 33) >> 1;
+  #pragma unroll 1
   for (int k = 0; k < n; k++) {
     float xk = __shfl_sync(FULL, k < 32 ? x0 : x1, k & 31) * invdiag[k];
     if (lane == k) x0 = xk;
     if (lane + 32 == k) x1 = xk;
-    if (lane > k && lane < n) x0 -= L[tri(lane, k)] * xk;
-    if (lane + 32 > k && lane + 32 < n) x1 -= L[tri(lane + 32, k)] * xk;
+    if (lane > k && lane < n) x0 -= L[r0 + k] * xk;
+    if (lane + 32 > k && lane + 32 < n) x1 -= L[r1 + k] * xk;
   }
   for (int k = n - 1; k >= 0; k--) {
     float xk = __shfl_sync(FULL, k < 32 ? x0 : x1, k & 31) * invdiag[k];
+    int rk = k * (k + 1) >> 1;
     if (lane == k) x0 = xk;
     if (lane + 32 == k) x1 = xk;
-    if (lane < k) x0 -= L[tri(k, lane)] * xk;
-    if (lane + 32 < k) x1 -= L[tri(k, lane + 32)] * xk;
+    if (lane < k) x0 -= L[rk + lane] * xk;
+    if (lane + 32 < k) x1 -= L[rk + lane + 32] * xk;
   }
   if (lane < n) x[lane] = x0;
   if (lane + 32 < n) x[lane + 32] = x1;
   __syncwarp();
 }
 // y = M x for packed symmetric M (both in shared memory)
-__device__ __forceinline__ void symv(const float* M, const float* x, float* y, int n, int lane) {
+__device__ __noinline__ void symv(const float* M, const float* x, float* y, int n, int lane) {
+  #pragma unroll 1
   for (int i = lane; i < n; i += 32) {
     float t = 0.f;
-    for (int j = 0; j <= i; j++) t += M[tri(i, j)] * x[j];
-    for (int j = i + 1; j < n; j++) t += M[tri(j, i)] * x[j];
+    int ri = i * (i + 1) >> 1;
+    #pragma unroll 1
+    for (int j = 0; j <= i; j++) t += M[ri + j] * x[j];
+    int idx = ri + i + i + 1;  // tri(i+1, i)
+    for (int j = i + 1; j < n; j++) { t += M[idx] * x[j]; idx += j + 1; }
     y[i] = t;
   }
   __syncwarp();
@@ -254,13 +286,92 @@ __device__ __forceinline__ void make_frame(float* f /*9: n, yhint -> n,t1,t2*/) 
   cross3(f + 6, f, f + 3);
 }
 
+// dst rows (+)= J x for every constraint row: contacts (4 pyramid rows, or row 0 for condim 1) and
+// joint limits.  J is never formed: per body-pair group g the relative spatial velocity
+// V_g = sum_{d in chain(b2) xor chain(b1)} (+-) cdof_d x_d is shared by all contacts of the group.
+__device__ __noinline__ void mulJ(const float* x, int dstc, int dstl, bool accumulate, float* con,
+                                  float* lim, const int* gstart, float* gV, const float* cdof,
+                                  const unsigned long long* __restrict__ dofmask, int ncon, int nlim,
+                                  int ngroup, int MC, int NLC, int lane) {
+  #pragma unroll 1
+  for (int g0 = 0; g0 < ngroup; g0 += 5) {
+    int gi = lane / 6, comp = lane - 6 * gi, g = g0 + gi;
+    if (gi < 5 && g < ngroup) {
+      int key = ((int*)con)[CINFO * MC + gstart[g]] & 0xffff;
+      unsigned long long m2 = dofmask[key >> 8];
+      unsigned long long mk = dofmask[key & 0xff] ^ m2;
+      float acc = 0.f;
+      while (mk) {
+        int d = __ffsll((long long)mk) - 1;
+        mk &= mk - 1;
+        float v = cdof[6 * d + comp] * x[d];
+        acc += (m2 >> d & 1ull) ? v : -v;
+      }
+      gV[6 * g + comp] = acc;
+    }
+  }
+  __syncwarp();
+  #pragma unroll 1
+  for (int c = lane; c < ncon; c += 32) {
+    const float* V = gV + 6 * ((int*)con)[CGRP * MC + c];
+    float a3[3];
+#pragma unroll
+    for (int mm = 0; mm < 3; mm++) {
+      float t = 0.f;
+#pragma unroll
+      for (int a = 0; a < 6; a++) t += con[(CS0 + 6 * mm + a) * MC + c] * V[a];
+      a3[mm] = t;
+    }
+    float mu = con[CMU * MC + c];
+    int dim = ((int*)con)[CINFO * MC + c] >> 16 & 0xf;
+    float r0, r1, r2, r3;
+    if (dim == 1) { r0 = a3[0]; r1 = r2 = r3 = 0.f; }
+    else if (dim == 0) { r0 = r1 = r2 = r3 = 0.f; }
+    else { r0 = a3[0] + mu * a3[1]; r1 = a3[0] - mu * a3[1]; r2 = a3[0] + mu * a3[2]; r3 = a3[0] - mu * a3[2]; }
+    if (accumulate) {
+      con[(dstc + 0) * MC + c] += r0; con[(dstc + 1) * MC + c] += r1;
+      con[(dstc + 2) * MC + c] += r2; con[(dstc + 3) * MC + c] += r3;
+    } else {
+      con[(dstc + 0) * MC + c] = r0; con[(dstc + 1) * MC + c] = r1;
+      con[(dstc + 2) * MC + c] = r2; con[(dstc + 3) * MC + c] = r3;
+    }
+  }
+  #pragma unroll 1
+  for (int r = lane; r < nlim; r += 32) {
+    int info = ((int*)lim)[LINFO * NLC + r];
+    float v = ((info >> 16 & 1) ? -1.f : 1.f) * x[info & 0xffff];
+    if (accumulate) lim[dstl * NLC + r] += v; else lim[dstl * NLC + r] = v;
+  }
+  __syncwarp();
+}
+// sum over rows of 0.5*D*min(r,0)^2 for the residuals stored in field (fc, fl)
+__device__ __noinline__ float rows_cost(int fc, int fl, const float* con, const float* lim, int ncon,
+                                        int nlim, int MC, int NLC, int lane) {
+  float cost = 0.f;
+  #pragma unroll 1
+  for (int c = lane; c < ncon; c += 32) {
+    float D = con[CD * MC + c];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      float v = con[(fc + r) * MC + c];
+      if (v < 0.f) cost += 0.5f * D * v * v;
+    }
+  }
+  #pragma unroll 1
+  for (int r = lane; r < nlim; r += 32) {
+    float v = lim[fl * NLC + r];
+    if (v < 0.f) cost += 0.5f * lim[LD * NLC + r] * v * v;
+  }
+  return wsum(cost);
+}
+
 }  // namespace b2
 
 // ==================================================================================================
 // The kernel
 // ==================================================================================================
 template <bool STEP>
-__global__ void __launch_bounds__(32 * B2_WARPS_PER_CTA, 2)
+__global__ void __launch_bounds__(32 * B2_WARPS_PER_CTA, 6)
 b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevData dd) {
   using namespace b2;
   extern __shared__ __align__(16) float smem_all[];
@@ -269,6 +380,9 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   const int w = blockIdx.x * B2_WARPS_PER_CTA + warp;
   if (w >= dd.nworld) return;
   const Layout& L = m.lay;
+#ifdef B2_PHASE_TIMING
+  long long tphase_ = clock64();
+#endif
   float* s = smem_all + (size_t)warp * L.total;
   const int nq = m.nq, nv = m.nv, nu = m.nu, nb = m.nbody, njnt = m.njnt;
   const int MC = L.maxcon, NLC = L.nlimcap;
@@ -294,6 +408,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     mbar_wait(bar, 0);
   }
 
+  PHASE_MARK(0);
   float* xpos = s + L.xpos; float* xquat = s + L.xquat; float* xipos = s + L.xipos;
   float* scom = s + L.scom; float* xanchor = s + L.xanchor; float* xaxis = s + L.xaxis;
   float* cinert = s + L.cinert; float* crb = s + L.crb; float* cdof = s + L.cdof;
@@ -310,9 +425,11 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     const float* jnt_pos = MP(jnt_pos); const float* jnt_axis = MP(jnt_axis);
     const float* qpos0 = MP(qpos0);
     const float* body_ipos = MP(body_ipos);
+    #pragma unroll 1
     for (int b = lane; b < nb; b += 32) {
       float pos[3] = {0.f, 0.f, 0.f}, quat[4] = {1.f, 0.f, 0.f, 0.f};
       int depth = m.body_depth[b];
+      #pragma unroll 1
       for (int k = 0; k < depth; k++) {
         int c = m.body_chain[b * m.maxdepth + k];
         int jn = m.body_jntnum[c], ja = m.body_jntadr[c];
@@ -372,12 +489,14 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   }
   __syncwarp();
 
+  PHASE_MARK(1);
   // geom / site world poses -> global (and shared for collidable geoms)
   float* gpose = s + L.gpose;
   {
     const float* geom_pos = MP(geom_pos); const float* geom_quat = MP(geom_quat);
     float* gxp = dd.geom_xpos.p + (size_t)w * dd.geom_xpos.stride;
     float* gxm = dd.geom_xmat.p + (size_t)w * dd.geom_xmat.stride;
+    #pragma unroll 1
     for (int g = lane; g < m.ngeom; g += 32) {
       int b = m.geom_bodyid[g];
       float p[3], q[4], mat[9];
@@ -399,6 +518,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     const float* site_pos = MP(site_pos); const float* site_quat = MP(site_quat);
     float* sxp = dd.site_xpos.p + (size_t)w * dd.site_xpos.stride;
     float* sxm = dd.site_xmat.p + (size_t)w * dd.site_xmat.stride;
+    #pragma unroll 1
     for (int g = lane; g < m.nsite; g += 32) {
       int b = m.site_bodyid[g];
       float p[3], q[4], mat[9];
@@ -411,11 +531,14 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     }
   }
 
+  PHASE_MARK(2);
   // ---------------- phase 2: subtree com, spatial inertias, motion vectors -----------------------
   {
     const float* mass = MP(body_mass); const float* sub = MP(body_subtreemass);
+    #pragma unroll 1
     for (int b = lane; b < nb; b += 32) {
       float acc[3] = {0.f, 0.f, 0.f};
+      #pragma unroll 1
       for (int d = 0; d < nb; d++) {
         if (m.body_ancmask[d] >> b & 1ull) {
           float md = mass[d];
@@ -432,9 +555,20 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   // are expressed about c0 (MuJoCo uses subtree_com[root]; results are identical, cvel is converted
   // on output).
   const float c0[3] = {scom[0], scom[1], scom[2]};
+  {  // body poses / coms leave now (coalesced); their shared-memory home is recycled after phase 4
+    float* g0 = dd.xpos.p + (size_t)w * dd.xpos.stride;
+    float* g1 = dd.xquat.p + (size_t)w * dd.xquat.stride;
+    float* g2 = dd.xipos.p + (size_t)w * dd.xipos.stride;
+    float* g3 = dd.subtree_com.p + (size_t)w * dd.subtree_com.stride;
+    #pragma unroll 1
+    for (int i = lane; i < 3 * nb; i += 32) { g0[i] = xpos[i]; g2[i] = xipos[i]; g3[i] = scom[i]; }
+    #pragma unroll 1
+    for (int i = lane; i < 4 * nb; i += 32) g1[i] = xquat[i];
+  }
   {
     const float* mass = MP(body_mass); const float* inertia = MP(body_inertia);
     const float* body_iquat = MP(body_iquat);
+    #pragma unroll 1
     for (int b = lane; b < nb; b += 32) {
       float q[4], mat[9], dif[3];
       mulquat(q, xquat + 4 * b, body_iquat + 4 * b);
@@ -463,6 +597,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         ci[6] = ms * dif[0]; ci[7] = ms * dif[1]; ci[8] = ms * dif[2]; ci[9] = ms;
       }
     }
+    #pragma unroll 1
     for (int j = lane; j < njnt; j += 32) {
       int b = m.jnt_bodyid[j], da = m.jnt_dofadr[j], ty = m.jnt_type[j];
       float off[3] = {c0[0] - xanchor[3 * j], c0[1] - xanchor[3 * j + 1], c0[2] - xanchor[3 * j + 2]};
@@ -490,11 +625,14 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   }
   __syncwarp();
 
+  PHASE_MARK(3);
   // ---------------- phase 3: composite inertias -> joint-space inertia M (packed lower) ----------
+  #pragma unroll 1
   for (int b = lane; b < nb; b += 32) {
     float acc[10];
 #pragma unroll
     for (int k = 0; k < 10; k++) acc[k] = 0.f;
+    #pragma unroll 1
     for (int d = 1; d < nb; d++) {
       if (m.body_ancmask[d] >> b & 1ull) {
 #pragma unroll
@@ -504,10 +642,12 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
 #pragma unroll
     for (int k = 0; k < 10; k++) crb[10 * b + k] = acc[k];
   }
+  #pragma unroll 1
   for (int i = lane; i < m.ntri; i += 32) Mq[i] = 0.f;
   __syncwarp();
   {
     const float* arm = MP(dof_armature);
+    #pragma unroll 1
     for (int i = lane; i < nv; i += 32) {
       float buf[6];
       mul_inert_vec(buf, crb + 10 * m.dof_bodyid[i], cdof + 6 * i);
@@ -517,7 +657,9 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   }
   __syncwarp();
 
+  PHASE_MARK(4);
   // ---------------- phase 4: velocities, bias forces, actuation, qfrc_smooth ----------------------
+  #pragma unroll 1
   for (int b = lane; b < nb; b += 32) {
     float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, snap[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     unsigned long long mask = m.body_dofmask[b];
@@ -553,6 +695,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     gc[3] = v[3] + t[0]; gc[4] = v[4] + t[1]; gc[5] = v[5] + t[2];
   }
   __syncwarp();
+  #pragma unroll 1
   for (int b = lane; b < nb; b += 32) {
     float a[6] = {0.f, 0.f, 0.f, -m.gravity[0], -m.gravity[1], -m.gravity[2]};
     unsigned long long mask = m.body_dofmask[b];
@@ -583,6 +726,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       cx[3] = xf[0]; cx[4] = xf[1]; cx[5] = xf[2];
     }
   }
+  #pragma unroll 1
   for (int i = lane; i < nv; i += 32) tmpv[i] = 0.f;  // qfrc_actuator
   __syncwarp();
   {
@@ -590,6 +734,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     const float* cr = MP(actuator_ctrlrange); const float* fr = MP(actuator_forcerange);
     const float* gear = MP(actuator_gear);
     float* gaf = dd.actuator_force.p + (size_t)w * dd.actuator_force.stride;
+    #pragma unroll 1
     for (int a = lane; a < nu; a += 32) {
       int j = m.actuator_trnid[a];
       float g = gear[a];
@@ -607,8 +752,10 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   {
     const float* damp = MP(dof_damping); const float* stiff = MP(jnt_stiffness);
     const float* qpos0 = MP(qpos0);
+    #pragma unroll 1
     for (int i = lane; i < nv; i += 32) {
       float sb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, sx[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      #pragma unroll 1
       for (int b = 1; b < nb; b++) {
         if (m.body_dofmask[b] >> i & 1ull) {
 #pragma unroll
@@ -632,23 +779,24 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   __syncwarp();
   if (m.debug) {
     float* gM = dd.qM.p + (size_t)w * dd.qM.stride;
+    #pragma unroll 1
     for (int p = lane; p < nv * nv; p += 32) {
       int i = p / nv, j = p % nv;
       gM[p] = i >= j ? Mq[tri(i, j)] : Mq[tri(j, i)];
     }
   }
 
+  PHASE_MARK(5);
   // ---------------- phase 5: collision (static pair table, bounding-sphere filter, primitives) ----
   float* con = s + L.contacts;   // overlays the smooth-only regions (cinert, crb, cdofdot, cacc, ...)
   float* lim = s + L.limits;
   int* gstart = (int*)(s + L.gstart);
-  unsigned* gmask_lo = (unsigned*)(s + L.gmask_lo);
-  unsigned* gmask_hi = (unsigned*)(s + L.gmask_hi);
   int ncon = 0, overflow = 0;
   {
     int* pairlist = (int*)(s + L.pairlist);
     const float* rb = MP(geom_rbound); const float* gmar = MP(geom_margin);
     int ncand = 0;
+    #pragma unroll 1
     for (int p0 = 0; p0 < m.npair; p0 += 32) {
       int p = p0 + lane;
       bool hit = false;
@@ -683,6 +831,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     float* g_pos = dd.contact_pos.p + (size_t)w * dd.contact_pos.stride;
     float* g_frame = dd.contact_frame.p + (size_t)w * dd.contact_frame.stride;
     int* g_geom = dd.contact_geom.p + (size_t)w * dd.contact_geom.stride;
+    #pragma unroll 1
     for (int q0 = 0; q0 < ncand; q0 += 32) {
       int qi = q0 + lane;
       RawCon rc[4];
@@ -807,6 +956,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
           B = 2.f / fmaxf(MINVAL, dmax * tc);
         } else { K = -solref[0] / (dmax * dmax); B = -solref[1] / dmax; }
         float tran = inv[2 * b1] + inv[2 * b2];
+        #pragma unroll 1
         for (int i = 0; i < n; i++) {
           int c = base + i;
           if (c >= MC) break;
@@ -831,8 +981,8 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
           else {
             float y;
             if (power == 1.f) y = x;
-            else if (x <= mid) y = powf(x, power) / powf(mid, power - 1.f);
-            else y = 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f);
+            else if (x <= mid) y = __powf(x, power) / __powf(mid, power - 1.f);
+            else y = 1.f - __powf(1.f - x, power) / __powf(1.f - mid, power - 1.f);
             imp = dmin + y * (dmax - dmin);
           }
           // R: frictionless -> (1-imp)/imp*tran ; pyramidal -> 2 mu'^2 * (1-imp)/imp*tran*(1+mu^2)
@@ -854,12 +1004,14 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   }
   __syncwarp();
 
+  PHASE_MARK(6);
   // ---------------- phase 6: joint-limit rows, body-pair groups ----------------------------------
   int nlim = 0;
   {
     const float* range = MP(jnt_range); const float* jmar = MP(jnt_margin);
     const float* jsolref = MP(jnt_solref); const float* jsolimp = MP(jnt_solimp);
     const float* dinv = MP(dof_invweight0);
+    #pragma unroll 1
     for (int j0 = 0; j0 < njnt; j0 += 32) {
       int j = j0 + lane;
       int side = 0; float dist = 0.f;
@@ -884,8 +1036,8 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
           else {
             float y;
             if (power == 1.f) y = x;
-            else if (x <= mid) y = powf(x, power) / powf(mid, power - 1.f);
-            else y = 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f);
+            else if (x <= mid) y = __powf(x, power) / __powf(mid, power - 1.f);
+            else y = 1.f - __powf(1.f - x, power) / __powf(1.f - mid, power - 1.f);
             imp = dmin + y * (dmax - dmin);
           }
           float K, B;
@@ -908,6 +1060,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   }
   // groups = maximal runs of contacts with the same (b1,b2); group dof set = chain(b1) xor chain(b2)
   int ngroup = 0;
+  #pragma unroll 1
   for (int c00 = 0; c00 < ncon; c00 += 32) {
     int c = c00 + lane;
     bool start = false;
@@ -921,11 +1074,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     if (c < ncon) {
       int g = start ? before : before - 1;
       ((int*)con)[CGRP * MC + c] = g;
-      if (start) {
-        gstart[g] = c;
-        unsigned long long mk = m.body_dofmask[key & 0xff] ^ m.body_dofmask[key >> 8];
-        gmask_lo[g] = (unsigned)mk; gmask_hi[g] = (unsigned)(mk >> 32);
-      }
+      if (start) gstart[g] = c;
     }
     ngroup += __popc(bal);
   }
@@ -934,130 +1083,82 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   int nefc = nlim;
   {
     int cnt = 0;
+    #pragma unroll 1
     for (int c = lane; c < ncon; c += 32) {
-      int dim = ((int*)con)[CINFO * MC + c] >> 16;
+      int dim = ((int*)con)[CINFO * MC + c] >> 16 & 0xf;
       cnt += dim == 0 ? 0 : (dim == 1 ? 1 : 2 * (dim - 1));
     }
     cnt = (int)wsum((float)cnt);
     nefc += cnt;
   }
 
-  // ---- J x for all rows: dst field <- J x (contacts: 4 rows, or row 0 only for condim 1) --------
   float* gV = s + L.gV;
-  auto mulJ = [&](const float* x, int dstc, int dstl) {
-    // group relative spatial velocity: lanes (gi, comp), 5 groups per pass
-    for (int g0 = 0; g0 < ngroup; g0 += 5) {
-      int gi = lane / 6, comp = lane - 6 * gi, g = g0 + gi;
-      if (gi < 5 && g < ngroup) {
-        int key = ((int*)con)[CINFO * MC + gstart[g]] & 0xffff;
-        unsigned long long m2 = m.body_dofmask[key >> 8];
-        unsigned long long mk = ((unsigned long long)gmask_hi[g] << 32) | gmask_lo[g];
-        float acc = 0.f;
-        while (mk) {
-          int d = __ffsll((long long)mk) - 1;
-          mk &= mk - 1;
-          float sg = (m2 >> d & 1ull) ? 1.f : -1.f;
-          acc += sg * cdof[6 * d + comp] * x[d];
-        }
-        gV[6 * g + comp] = acc;
-      }
-    }
-    __syncwarp();
-    for (int c = lane; c < ncon; c += 32) {
-      const float* V = gV + 6 * ((int*)con)[CGRP * MC + c];
-      float a3[3];
-#pragma unroll
-      for (int mm = 0; mm < 3; mm++) {
-        float t = 0.f;
-#pragma unroll
-        for (int a = 0; a < 6; a++) t += con[(CS0 + 6 * mm + a) * MC + c] * V[a];
-        a3[mm] = t;
-      }
-      float mu = con[CMU * MC + c];
-      int dim = ((int*)con)[CINFO * MC + c] >> 16;
-      if (dim == 1) {
-        con[(dstc + 0) * MC + c] = a3[0];
-        con[(dstc + 1) * MC + c] = 0.f; con[(dstc + 2) * MC + c] = 0.f; con[(dstc + 3) * MC + c] = 0.f;
-      } else {
-        con[(dstc + 0) * MC + c] = a3[0] + mu * a3[1];
-        con[(dstc + 1) * MC + c] = a3[0] - mu * a3[1];
-        con[(dstc + 2) * MC + c] = a3[0] + mu * a3[2];
-        con[(dstc + 3) * MC + c] = a3[0] - mu * a3[2];
-      }
-    }
-    for (int r = lane; r < nlim; r += 32) {
-      int info = ((int*)lim)[LINFO * NLC + r];
-      float Jd = (info >> 16) ? -1.f : 1.f;
-      lim[dstl * NLC + r] = Jd * x[info & 0xffff];
-    }
-    __syncwarp();
-  };
-  // cost of the constraint rows for residuals stored in (fc, fl); optionally subtract aref first
-  auto rows_sub_aref_cost = [&](int fc, int fl) -> float {
-    float cost = 0.f;
-    for (int c = lane; c < ncon; c += 32) {
-      int dim = ((int*)con)[CINFO * MC + c] >> 16;
-      float D = con[CD * MC + c];
-      int nr = dim == 0 ? 0 : (dim == 1 ? 1 : 4);
-      for (int r = 0; r < 4; r++) {
-        float v = con[(fc + r) * MC + c] - con[(CAREF0 + r) * MC + c];
-        if (r >= nr) v = 0.f;
-        con[(fc + r) * MC + c] = v;
-        if (v < 0.f) cost += 0.5f * D * v * v;
-      }
-    }
-    for (int r = lane; r < nlim; r += 32) {
-      float v = lim[fl * NLC + r] - lim[LAREF * NLC + r];
-      lim[fl * NLC + r] = v;
-      if (v < 0.f) cost += 0.5f * lim[LD * NLC + r] * v * v;
-    }
-    __syncwarp();
-    return wsum(cost);
-  };
-
-  // aref for contact rows: -B*vel_row - K*imp*(pos-margin)
+#define MULJ(x, dc, dl, acc) mulJ(x, dc, dl, acc, con, lim, gstart, gV, cdof, m.body_dofmask, ncon, nlim, ngroup, MC, NLC, lane)
+  // CJAR <- -aref = B*vel_row + K*imp*(pos-margin) for contact rows (0 for unused rows)
   if (nefc > 0) {
-    mulJ(qvel, CJV0, LJV);
+    MULJ(qvel, CJV0, LJV, false);
+    #pragma unroll 1
     for (int c = lane; c < ncon; c += 32) {
       float B = con[CB * MC + c], ki = con[CKI * MC + c];
+      int dim = ((int*)con)[CINFO * MC + c] >> 16 & 0xf;
+      int nr = dim == 0 ? 0 : (dim == 1 ? 1 : 4);
 #pragma unroll
-      for (int r = 0; r < 4; r++) con[(CAREF0 + r) * MC + c] = -B * con[(CJV0 + r) * MC + c] - ki;
+      for (int r = 0; r < 4; r++) con[(CJAR0 + r) * MC + c] = r < nr ? B * con[(CJV0 + r) * MC + c] + ki : 0.f;
     }
+    #pragma unroll 1
+    for (int r = lane; r < nlim; r += 32) lim[LJAR * NLC + r] = -lim[LAREF * NLC + r];
     __syncwarp();
   }
 
+  PHASE_MARK(7);
   // ---------------- phase 7: unconstrained acceleration -------------------------------------------
+  #pragma unroll 1
   for (int i = lane; i < m.ntri; i += 32) H[i] = Mq[i];
   __syncwarp();
-  chol_factor(H, invdiag, nv, m.ntri, m.tri_coldesc, lane);
+  chol_factor(H, invdiag, nv, m.tri_coldesc, lane);
   chol_solve(H, invdiag, qacc_smooth, nv, lane);
   if (m.debug)
+    #pragma unroll 1
     for (int i = lane; i < nv; i += 32) dd.qacc_smooth.p[(size_t)w * dd.qacc_smooth.stride + i] = qacc_smooth[i];
 
+  PHASE_MARK(8);
   // ---------------- phase 8: Newton solver (primal, exact line search) ----------------------------
   int niter = 0;
   float cost = 0.f;
   if (nefc == 0) {
+    #pragma unroll 1
     for (int i = lane; i < nv; i += 32) { qacc[i] = qacc_smooth[i]; qfrc_c[i] = 0.f; }
     __syncwarp();
   } else {
     // warm start: qacc_warmstart unless qacc_smooth is cheaper (mj_fwdConstraint)
     symv(Mq, qacc_ws, Ma, nv, lane);
-    mulJ(qacc_ws, CJAR0, LJAR);
-    float cw = rows_sub_aref_cost(CJAR0, LJAR);
+    MULJ(qacc_smooth, CJV0, LJV, false);
+    #pragma unroll 1
+    for (int c = lane; c < ncon; c += 32)
+#pragma unroll
+      for (int r = 0; r < 4; r++) con[(CJV0 + r) * MC + c] += con[(CJAR0 + r) * MC + c];
+    #pragma unroll 1
+    for (int r = lane; r < nlim; r += 32) lim[LJV * NLC + r] += lim[LJAR * NLC + r];
+    __syncwarp();
+    float csm = rows_cost(CJV0, LJV, con, lim, ncon, nlim, MC, NLC, lane);
+    MULJ(qacc_ws, CJAR0, LJAR, true);
+    float cw = rows_cost(CJAR0, LJAR, con, lim, ncon, nlim, MC, NLC, lane);
     float gs = 0.f;
+    #pragma unroll 1
     for (int i = lane; i < nv; i += 32) gs += (Ma[i] - qfrc_smooth[i]) * (qacc_ws[i] - qacc_smooth[i]);
     cw += 0.5f * wsum(gs);
-    mulJ(qacc_smooth, CJV0, LJV);
-    float csm = rows_sub_aref_cost(CJV0, LJV);
     bool use_smooth = cw > csm;
+    #pragma unroll 1
     for (int i = lane; i < nv; i += 32) qacc[i] = use_smooth ? qacc_smooth[i] : qacc_ws[i];
     __syncwarp();
     if (use_smooth) {
+      #pragma unroll 1
       for (int i = lane; i < nv; i += 32) Ma[i] = qfrc_smooth[i];  // M * qacc_smooth
+      #pragma unroll 1
       for (int c = lane; c < ncon; c += 32)
 #pragma unroll
         for (int r = 0; r < 4; r++) con[(CJAR0 + r) * MC + c] = con[(CJV0 + r) * MC + c];
+      #pragma unroll 1
       for (int r = lane; r < nlim; r += 32) lim[LJAR * NLC + r] = lim[LJV * NLC + r];
       __syncwarp();
     }
@@ -1066,35 +1167,49 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     float oldcost = 0.f;
     bool first = true;
     while (true) {
-      // ---- constraint update: forces, cost, qfrc_constraint = J^T f --------------------------
+      // ---- constraint update: forces, cost, active set, qfrc_constraint = J^T f ---------------
       float cst = 0.f;
+      bool changed = false;
+      #pragma unroll 1
       for (int c = lane; c < ncon; c += 32) {
         float D = con[CD * MC + c], mu = con[CMU * MC + c];
-        int dim = ((int*)con)[CINFO * MC + c] >> 16;
+        int info = ((int*)con)[CINFO * MC + c];
+        int dim = info >> 16 & 0xf;
         float f[4];
+        int act = 0;
 #pragma unroll
         for (int r = 0; r < 4; r++) {
           float v = con[(CJAR0 + r) * MC + c];
-          f[r] = v < 0.f ? -D * v : 0.f;
-          if (v < 0.f) cst += 0.5f * D * v * v;
+          bool on = v < 0.f;
+          f[r] = on ? -D * v : 0.f;
+          if (on) { cst += 0.5f * D * v * v; act |= 1 << r; }
         }
+        changed |= act != (info >> 20 & 0xf);
+        ((int*)con)[CINFO * MC + c] = (info & 0xfffff) | (act << 20);
         float F0, F1, F2;
         if (dim == 1) { F0 = f[0]; F1 = 0.f; F2 = 0.f; }
         else { F0 = f[0] + f[1] + f[2] + f[3]; F1 = mu * (f[0] - f[1]); F2 = mu * (f[2] - f[3]); }
         con[(CJV0 + 0) * MC + c] = F0; con[(CJV0 + 1) * MC + c] = F1; con[(CJV0 + 2) * MC + c] = F2;
       }
+      #pragma unroll 1
       for (int i = lane; i < nv; i += 32) qfrc_c[i] = 0.f;
       __syncwarp();
+      #pragma unroll 1
       for (int r = lane; r < nlim; r += 32) {
         float v = lim[LJAR * NLC + r];
-        if (v < 0.f) {
+        int info = ((int*)lim)[LINFO * NLC + r];
+        int act = v < 0.f ? 1 : 0;
+        changed |= act != (info >> 20 & 1);
+        ((int*)lim)[LINFO * NLC + r] = (info & 0xfffff) | (act << 20);
+        if (act) {
           float D = lim[LD * NLC + r];
           cst += 0.5f * D * v * v;
-          int info = ((int*)lim)[LINFO * NLC + r];
-          atomicAdd(&qfrc_c[info & 0xffff], ((info >> 16) ? -1.f : 1.f) * (-D * v));
+          atomicAdd(&qfrc_c[info & 0xffff], ((info >> 16 & 1) ? -1.f : 1.f) * (-D * v));
         }
       }
+      changed = __any_sync(FULL, changed);
       // group wrench: W_g = sum_c sum_m F_m S_m  (lanes (gi, comp))
+      #pragma unroll 1
       for (int g0 = 0; g0 < ngroup; g0 += 5) {
         int gi = lane / 6, comp = lane - 6 * gi, g = g0 + gi;
         if (gi < 5 && g < ngroup) {
@@ -1107,20 +1222,24 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         }
       }
       __syncwarp();
+      #pragma unroll 1
       for (int i = lane; i < nv; i += 32) {
         float acc = qfrc_c[i];
+        #pragma unroll 1
         for (int g = 0; g < ngroup; g++) {
-          unsigned word = i < 32 ? gmask_lo[g] : gmask_hi[g];
-          if (word >> (i & 31) & 1u) {
-            int key = ((int*)con)[CINFO * MC + gstart[g]] & 0xffff;
-            float sg = (m.body_dofmask[key >> 8] >> i & 1ull) ? 1.f : -1.f;
-            acc += sg * dot6(cdof + 6 * i, gV + 6 * g);
+          int key = ((int*)con)[CINFO * MC + gstart[g]] & 0xffff;
+          unsigned long long m2 = m.body_dofmask[key >> 8];
+          unsigned long long mk = m.body_dofmask[key & 0xff] ^ m2;
+          if (mk >> i & 1ull) {
+            float v = dot6(cdof + 6 * i, gV + 6 * g);
+            acc += (m2 >> i & 1ull) ? v : -v;
           }
         }
         qfrc_c[i] = acc;
       }
       __syncwarp();
       float gg = 0.f, gn = 0.f;
+      #pragma unroll 1
       for (int i = lane; i < nv; i += 32) {
         float g = Ma[i] - qfrc_smooth[i] - qfrc_c[i];
         grad[i] = g;
@@ -1132,18 +1251,26 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       if (!first) {
         float improvement = scale * (oldcost - cost), gradient = scale * sqrtf(gn);
         if (improvement < m.tolerance || gradient < m.tolerance) break;
+        // Exact termination: the cost is one quadratic per active set, and a Newton step with exact
+        // line search lands on that quadratic's minimiser; if the active set did not change across
+        // the move, the new point is the minimiser of the true (convex) cost.
+        if (!changed) break;
       }
       if (niter >= m.iterations) break;
       first = false;
+      PHASE_MARK(12);
       // ---- Hessian H = M + J^T D_active J via per-body-pair 6x6 blocks -------------------------
+      #pragma unroll 1
       for (int i = lane; i < m.ntri; i += 32) H[i] = Mq[i];
       __syncwarp();
+      #pragma unroll 1
       for (int r = lane; r < nlim; r += 32) {
         if (lim[LJAR * NLC + r] < 0.f) {
           int d = ((int*)lim)[LINFO * NLC + r] & 0xffff;
           atomicAdd(&H[tri(d, d)], lim[LD * NLC + r]);
         }
       }
+      #pragma unroll 1
       for (int g = 0; g < ngroup; g++) {
         // A (6x6 symmetric, 21 entries), lane e owns entry (a,b)
         if (lane < 21) {
@@ -1153,13 +1280,12 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
           float acc = 0.f;
           for (int c = gstart[g]; c < gstart[g + 1]; c++) {
             float D = con[CD * MC + c], mu = con[CMU * MC + c];
-            int dim = ((int*)con)[CINFO * MC + c] >> 16;
-            float w0 = con[(CJAR0 + 0) * MC + c] < 0.f ? D : 0.f;
+            int info = ((int*)con)[CINFO * MC + c];
+            int dim = info >> 16 & 0xf, act = info >> 20 & 0xf;
+            float w0 = (act & 1) ? D : 0.f;
             float sa0 = con[(CS0 + a) * MC + c], sb0 = con[(CS0 + b) * MC + c];
             if (dim == 1) { acc += w0 * sa0 * sb0; continue; }
-            float w1 = con[(CJAR0 + 1) * MC + c] < 0.f ? D : 0.f;
-            float w2 = con[(CJAR0 + 2) * MC + c] < 0.f ? D : 0.f;
-            float w3 = con[(CJAR0 + 3) * MC + c] < 0.f ? D : 0.f;
+            float w1 = (act & 2) ? D : 0.f, w2 = (act & 4) ? D : 0.f, w3 = (act & 8) ? D : 0.f;
             float sa1 = con[(CS0 + 6 + a) * MC + c], sb1 = con[(CS0 + 6 + b) * MC + c];
             float sa2 = con[(CS0 + 12 + a) * MC + c], sb2 = con[(CS0 + 12 + b) * MC + c];
             float W00 = w0 + w1 + w2 + w3, W01 = mu * (w0 - w1), W02 = mu * (w2 - w3);
@@ -1170,14 +1296,16 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
           gA[a * 6 + b] = acc;
           gA[b * 6 + a] = acc;
         }
-        // dof list of the group (ascending) with signs folded into u and v
-        unsigned lo = gmask_lo[g], hi = gmask_hi[g];
+        // dof list of the group (ascending) with signs folded into u
+        int key = ((int*)con)[CINFO * MC + gstart[g]] & 0xffff;
+        unsigned long long m2 = m.body_dofmask[key >> 8];
+        unsigned long long mk = m.body_dofmask[key & 0xff] ^ m2;
+        unsigned lo = (unsigned)mk, hi = (unsigned)(mk >> 32);
         int nlo = __popc(lo), ns = nlo + __popc(hi);
         if (lo >> lane & 1u) glist[__popc(lo & ((1u << lane) - 1u))] = lane;
         if (hi >> lane & 1u) glist[nlo + __popc(hi & ((1u << lane) - 1u))] = 32 + lane;
         __syncwarp();
-        int key = ((int*)con)[CINFO * MC + gstart[g]] & 0xffff;
-        unsigned long long m2 = m.body_dofmask[key >> 8];
+        #pragma unroll 1
         for (int a = lane; a < ns; a += 32) {
           int d = glist[a];
           float sg = (m2 >> d & 1ull) ? 1.f : -1.f;
@@ -1192,23 +1320,28 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         }
         __syncwarp();
         int np = ns * (ns + 1) >> 1;
+        #pragma unroll 1
         for (int p = lane; p < np; p += 32) {
           unsigned short e = m.tri_rowmajor[p];
           int a = e & 0xff, b = e >> 8;  // a >= b
-          int db = glist[b];
-          float sgb = (m2 >> db & 1ull) ? 1.f : -1.f;
-          H[tri(glist[a], db)] += sgb * dot6(gu + 6 * a, cdof + 6 * db);
+          int da = glist[a], db = glist[b];
+          float v = dot6(gu + 6 * a, cdof + 6 * db);
+          H[(da * (da + 1) >> 1) + db] += (m2 >> db & 1ull) ? v : -v;
         }
         __syncwarp();
       }
-      chol_factor(H, invdiag, nv, m.ntri, m.tri_coldesc, lane);
+      PHASE_MARK(13);
+      chol_factor(H, invdiag, nv, m.tri_coldesc, lane);
+      #pragma unroll 1
       for (int i = lane; i < nv; i += 32) search[i] = -grad[i];
       __syncwarp();
       chol_solve(H, invdiag, search, nv, lane);
+      PHASE_MARK(14);
       // ---- exact line search along `search` --------------------------------------------------
       symv(Mq, search, Mv, nv, lane);
-      mulJ(search, CJV0, LJV);
+      MULJ(search, CJV0, LJV, false);
       float g1 = 0.f, g2 = 0.f, sn = 0.f;
+      #pragma unroll 1
       for (int i = lane; i < nv; i += 32) {
         g1 += search[i] * (Ma[i] - qfrc_smooth[i]);
         g2 += 0.5f * search[i] * Mv[i];
@@ -1217,9 +1350,36 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       g1 = wsum(g1); g2 = wsum(g2); sn = sqrtf(wsum(sn));
       if (sn < MINVAL) break;
       float gtol = m.tolerance * m.ls_tolerance * sn / scale;
+      // each lane keeps its rows in registers for the whole search (<= 2 contacts + 1 limit per lane)
+      float lsD[3], lsJ[9], lsV[9];
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        int c = lane + 32 * q;
+        bool ok = c < ncon;
+        lsD[q] = ok ? con[CD * MC + c] : 0.f;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          lsJ[4 * q + r] = ok ? con[(CJAR0 + r) * MC + c] : 0.f;
+          lsV[4 * q + r] = ok ? con[(CJV0 + r) * MC + c] : 0.f;
+        }
+      }
+      {
+        bool ok = lane < nlim;
+        lsD[2] = ok ? lim[LD * NLC + lane] : 0.f;
+        lsJ[8] = ok ? lim[LJAR * NLC + lane] : 0.f;
+        lsV[8] = ok ? lim[LJV * NLC + lane] : 0.f;
+      }
       auto ls_eval = [&](float al, float& d0, float& d1) {
         float a0 = 0.f, a1 = 0.f;
-        for (int c = lane; c < ncon; c += 32) {
+#pragma unroll
+        for (int q = 0; q < 9; q++) {
+          float D = lsD[q < 8 ? (q >> 2) : 2];
+          float x = lsJ[q] + al * lsV[q];
+          if (x < 0.f) { a0 += D * x * lsV[q]; a1 += D * lsV[q] * lsV[q]; }
+        }
+        // rows beyond the register window (ncon > 64 or nlim > 32)
+        #pragma unroll 1
+        for (int c = lane + 64; c < ncon; c += 32) {
           float D = con[CD * MC + c];
 #pragma unroll
           for (int r = 0; r < 4; r++) {
@@ -1228,7 +1388,8 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
             if (x < 0.f) { a0 += D * x * jv; a1 += D * jv * jv; }
           }
         }
-        for (int r = lane; r < nlim; r += 32) {
+        #pragma unroll 1
+        for (int r = lane + 32; r < nlim; r += 32) {
           float jv = lim[LJV * NLC + r];
           float x = lim[LJAR * NLC + r] + al * jv;
           if (x < 0.f) { float D = lim[LD * NLC + r]; a0 += D * x * jv; a1 += D * jv * jv; }
@@ -1236,11 +1397,13 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         d0 = wsum(a0) + g1 + 2.f * al * g2;
         d1 = fmaxf(wsum(a1) + 2.f * g2, MINVAL);
       };
+      PHASE_MARK(15);
       float alpha = 0.f, d0, d1;
       ls_eval(0.f, d0, d1);
       if (d0 < 0.f) {
         float lo_a = 0.f, hi_a = -1.f;  // hi_a < 0: no upper bracket yet
         alpha = -d0 / d1;
+        #pragma unroll 1
         for (int it = 0; it < m.ls_iterations; it++) {
           ls_eval(alpha, d0, d1);
           if (fabsf(d0) < gtol) break;
@@ -1251,11 +1414,15 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
           alpha = nxt;
         }
       }
+      PHASE_MARK(16);
       if (alpha == 0.f) break;
+      #pragma unroll 1
       for (int i = lane; i < nv; i += 32) { qacc[i] += alpha * search[i]; Ma[i] += alpha * Mv[i]; }
+      #pragma unroll 1
       for (int c = lane; c < ncon; c += 32)
 #pragma unroll
         for (int r = 0; r < 4; r++) con[(CJAR0 + r) * MC + c] += alpha * con[(CJV0 + r) * MC + c];
+      #pragma unroll 1
       for (int r = lane; r < nlim; r += 32) lim[LJAR * NLC + r] += alpha * lim[LJV * NLC + r];
       __syncwarp();
       oldcost = cost;
@@ -1263,12 +1430,14 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     }
   }
 
+  PHASE_MARK(9);
   // ---------------- phase 9: contact forces, sensors -----------------------------------------------
   {
     float* g_force = dd.contact_force.p + (size_t)w * dd.contact_force.stride;
+    #pragma unroll 1
     for (int c = lane; c < ncon; c += 32) {
       float D = con[CD * MC + c], mu = con[CMU * MC + c];
-      int dim = ((int*)con)[CINFO * MC + c] >> 16;
+      int dim = ((int*)con)[CINFO * MC + c] >> 16 & 0xf;
       float f[4];
 #pragma unroll
       for (int r = 0; r < 4; r++) { float v = con[(CJAR0 + r) * MC + c]; f[r] = (nefc > 0 && v < 0.f) ? -D * v : 0.f; }
@@ -1283,19 +1452,22 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     float* sd = dd.sensordata.p + (size_t)w * dd.sensordata.stride;
     const float* g_pos = dd.contact_pos.p + (size_t)w * dd.contact_pos.stride;
     const int* g_geom = dd.contact_geom.p + (size_t)w * dd.contact_geom.stride;
+    #pragma unroll 1
     for (int sidx = 0; sidx < m.nsensor; sidx++) {
       int dataspec = m.sensor_intprm[3 * sidx], reduce = m.sensor_intprm[3 * sidx + 1], num = m.sensor_intprm[3 * sidx + 2];
       int adr = m.sensor_adr[sidx], sdim = m.sensor_dim[sidx];
       int slot = sdim / max(num, 1);
       int ot = m.sensor_objtype[sidx], oi = m.sensor_objid[sidx];
       int rt = m.sensor_reftype[sidx], ri = m.sensor_refid[sidx];
+      #pragma unroll 1
       for (int k = lane; k < sdim; k += 32) sd[adr + k] = 0.f;
       int nmatch = 0;
       float net[3] = {0.f, 0.f, 0.f}, wp[3] = {0.f, 0.f, 0.f}, wsm = 0.f;
+      #pragma unroll 1
       for (int c00 = 0; c00 < ncon; c00 += 32) {
         int c = c00 + lane;
         int dir = 0;
-        if (c < ncon && (((int*)con)[CINFO * MC + c] >> 16) != 0) {
+        if (c < ncon && (((int*)con)[CINFO * MC + c] >> 16 & 0xf) != 0) {
           int g1 = g_geom[2 * c], g2 = g_geom[2 * c + 1];
           auto match = [&](int type, int id, int geom) -> bool {
             if (type < 0) return true;
@@ -1349,11 +1521,13 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         }
       } else if (reduce == 0 && (dataspec & 1)) {
         int filled = min(nmatch, num);
+        #pragma unroll 1
         for (int i = lane; i < filled; i += 32) sd[adr + i * slot] = (float)nmatch;
       }
     }
   }
 
+  PHASE_MARK(10);
   // ---------------- phase 10: integrate (implicitfast / Euler), write state ------------------------
   float* gq = dd.qpos.p + (size_t)w * dd.qpos.stride;
   float* gv = dd.qvel.p + (size_t)w * dd.qvel.stride;
@@ -1361,11 +1535,14 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     const float h = m.timestep;
     const float* damp = MP(dof_damping); const float* bp = MP(actuator_biasprm);
     const float* fr = MP(actuator_forcerange); const float* gear = MP(actuator_gear);
+    #pragma unroll 1
     for (int i = lane; i < m.ntri; i += 32) H[i] = Mq[i];
     __syncwarp();
+    #pragma unroll 1
     for (int i = lane; i < nv; i += 32) H[tri(i, i)] += h * damp[i];
     __syncwarp();
     if (m.integrator == INT_IMPLICITFAST) {
+      #pragma unroll 1
       for (int a = lane; a < nu; a += 32) {
         float bv = bp[10 * a + 2];
         if (bv == 0.f) continue;
@@ -1378,19 +1555,24 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       }
     }
     bool anydamp = false;
+    #pragma unroll 1
     for (int i = lane; i < nv; i += 32) anydamp |= damp[i] > 0.f;
     anydamp = __any_sync(FULL, anydamp);
     if (m.integrator == INT_IMPLICITFAST || anydamp) {
+      #pragma unroll 1
       for (int i = lane; i < nv; i += 32) tmpv[i] = qfrc_smooth[i] + qfrc_c[i];
       __syncwarp();
-      chol_factor(H, invdiag, nv, m.ntri, m.tri_coldesc, lane);
+      chol_factor(H, invdiag, nv, m.tri_coldesc, lane);
       chol_solve(H, invdiag, tmpv, nv, lane);
     } else {
+      #pragma unroll 1
       for (int i = lane; i < nv; i += 32) tmpv[i] = qacc[i];
       __syncwarp();
     }
+    #pragma unroll 1
     for (int i = lane; i < nv; i += 32) qvel[i] += h * tmpv[i];
     __syncwarp();
+    #pragma unroll 1
     for (int j = lane; j < njnt; j += 32) {
       int qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j];
       if (m.jnt_type[j] == JNT_FREE) {
@@ -1413,14 +1595,17 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     __syncwarp();
     if (lane == 0) dd.time.p[(size_t)w * dd.time.stride] += h;
     float* gws = dd.qacc_warmstart.p + (size_t)w * dd.qacc_warmstart.stride;
+    #pragma unroll 1
     for (int i = lane; i < nv; i += 32) gws[i] = qacc[i];
   }
   // outputs that live contiguously in shared memory leave through bulk (TMA) stores
   {
     float* gqa = dd.qacc.p + (size_t)w * dd.qacc.stride;
+    #pragma unroll 1
     for (int i = lane; i < nv; i += 32) gqa[i] = qacc[i];
     if (m.debug) {
       float* gfc = dd.qfrc_constraint.p + (size_t)w * dd.qfrc_constraint.stride;
+      #pragma unroll 1
       for (int i = lane; i < nv; i += 32) gfc[i] = qfrc_c[i];
     }
     fence_async_smem();
@@ -1430,12 +1615,9 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         bulk_s2g(gq, qpos, 4u * dd.qpos.stride);
         bulk_s2g(gv, qvel, 4u * dd.qvel.stride);
       }
-      bulk_s2g(dd.xpos.p + (size_t)w * dd.xpos.stride, xpos, 4u * dd.xpos.stride);
-      bulk_s2g(dd.xquat.p + (size_t)w * dd.xquat.stride, xquat, 4u * dd.xquat.stride);
-      bulk_s2g(dd.xipos.p + (size_t)w * dd.xipos.stride, xipos, 4u * dd.xipos.stride);
-      bulk_s2g(dd.subtree_com.p + (size_t)w * dd.subtree_com.stride, scom, 4u * dd.subtree_com.stride);
       bulk_commit_wait();
     }
+    PHASE_MARK(11);
     if (lane == 0) {
       dd.ncon.p[(size_t)w * dd.ncon.stride] = ncon;
       dd.nefc.p[(size_t)w * dd.nefc.stride] = nefc;

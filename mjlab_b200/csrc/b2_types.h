@@ -2,7 +2,9 @@
 #pragma once
 #include <stdint.h>
 
+#ifndef B2_WARPS_PER_CTA
 #define B2_WARPS_PER_CTA 2
+#endif
 #define B2_MAX_FIELDS 96
 
 enum { JNT_FREE = 0, JNT_BALL = 1, JNT_SLIDE = 2, JNT_HINGE = 3 };
@@ -33,10 +35,9 @@ struct IArr {
 enum {
   CS0 = 0,        // 18 floats: S_m[a] at CS0 + m*6 + a; S_m = [r x e_m ; e_m], e_0 = normal
   CDIST = 18, CMU, CD, CKI, CB, CINFO, CGRP,
-  CAREF0, CAREF1, CAREF2, CAREF3,
   CJAR0, CJAR1, CJAR2, CJAR3,
   CJV0, CJV1, CJV2, CJV3,
-  C_NFIELD  // 37
+  C_NFIELD  // 33
 };
 // Per-limit-row SoA fields (index f*nlimcap + r).
 enum { LINFO = 0, LD, LAREF, LJAR, LJV, L_NFIELD };
@@ -53,7 +54,7 @@ struct Layout {
   int M, H, invdiag;
   int qfrc_smooth, qacc_smooth, qacc, Ma, grad, search, Mv, qfrc_c, tmpv, actf;
   // collision / constraints (overlaid on smooth-only regions)
-  int gpose, pairlist, contacts, limits, gstart, gmask_lo, gmask_hi, gV, glist, gA, gu;
+  int gpose, pairlist, contacts, limits, gstart, gV, glist, gA, gu;
   int sens;
   int maxcon, nlimcap, maxpair;
 };
@@ -77,7 +78,8 @@ struct DevModel {
   const int *pair_geom1, *pair_geom2;
   const int *sensor_objtype, *sensor_objid, *sensor_reftype, *sensor_refid, *sensor_intprm;
   const int *sensor_adr, *sensor_dim;
-  const unsigned short *tri_rowmajor, *tri_coldesc;
+  const unsigned short* tri_rowmajor;
+  const unsigned* tri_coldesc;
   // float arrays (expandable per world)
   FArr body_pos, body_quat, body_ipos, body_iquat, body_mass, body_subtreemass, body_inertia,
       body_invweight0, jnt_pos, jnt_axis, jnt_range, jnt_solref, jnt_solimp, jnt_margin,

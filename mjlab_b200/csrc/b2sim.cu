@@ -169,6 +169,20 @@ extern "C" {
 const char* b2_last_error(void) { return g_err.c_str(); }
 const char* b2_version(void) { return "b2sim 0.1.0 (sm_100a)"; }
 
+// Debug builds (-DB2_PHASE_TIMING): cumulative per-phase cycles (sum over warps); reset on read.
+int b2_phase_cycles(unsigned long long* out32) {
+#ifdef B2_PHASE_TIMING
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out32, b2::g_phase_cycles, sizeof(unsigned long long) * 32);
+  unsigned long long z[32] = {0};
+  cudaMemcpyToSymbol(b2::g_phase_cycles, z, sizeof(z));
+  return 0;
+#else
+  (void)out32;
+  return 1;
+#endif
+}
+
 int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax, int cuda_device,
               b2_sim** out) {
   if (!desc || !out || nworld <= 0) return fail("b2_create: bad arguments");
@@ -248,12 +262,15 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
       if (cslot[g] < 0) { cslot[g] = (int)cgeom.size(); cgeom.push_back(g); }
   }
   m.ncg = (int)cgeom.size();
-  std::vector<unsigned short> trow(std::max(m.ntri, 1)), tcol(std::max(m.ntri, 1));
+  std::vector<unsigned short> trow(std::max(m.ntri, 1));
+  std::vector<unsigned> tcol(std::max(m.ntri, 1));
   {
     int p = 0;
     for (int i = 0; i < m.nv; i++) for (int j = 0; j <= i; j++) trow[p++] = (unsigned short)(i | (j << 8));
     p = 0;
-    for (int j = m.nv - 1; j >= 0; j--) for (int i = j; i < m.nv; i++) tcol[p++] = (unsigned short)(i | (j << 8));
+    for (int j = m.nv - 1; j >= 0; j--)
+      for (int i = j; i < m.nv; i++)
+        tcol[p++] = (unsigned)(i * (i + 1) / 2) | ((unsigned)(j * (j + 1) / 2) << 11) | ((unsigned)j << 22);
   }
   int rc = 0;
 #define UPI(field, key) rc |= dev_upload<int>(s, s->mi[key], &m.field)
@@ -277,7 +294,7 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
   rc |= dev_upload<int>(s, cslot, &m.geom_cslot);
   rc |= dev_upload<int>(s, cgeom, &m.cgeom);
   rc |= dev_upload<unsigned short>(s, trow, &m.tri_rowmajor);
-  rc |= dev_upload<unsigned short>(s, tcol, &m.tri_coldesc);
+  rc |= dev_upload<unsigned>(s, tcol, &m.tri_coldesc);
   if (rc) { b2_destroy(s); return 1; }
   // supported sensor set: contact sensors with data in {found,force,dist,pos,normal}, reduce none/netforce
   for (int i = 0; i < m.nsensor; i++) {
@@ -363,8 +380,6 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
   L.maxpair = 128;
   L.qpos = alloc(d.qpos.stride); L.qvel = alloc(d.qvel.stride); L.ctrl = alloc(d.ctrl.stride);
   L.qacc_ws = alloc(d.qacc_warmstart.stride); L.qfrc_applied = alloc(d.qfrc_applied.stride);
-  L.xpos = alloc(d.xpos.stride); L.xquat = alloc(d.xquat.stride); L.xipos = alloc(d.xipos.stride);
-  L.scom = alloc(d.subtree_com.stride);
   L.cdof = alloc(6 * nv); L.M = alloc(m.ntri);
   int hsize = std::max(m.ntri, 12 * m.ncg + L.maxpair);
   L.H = alloc(hsize); L.gpose = L.H; L.pairlist = L.H + 12 * m.ncg;
@@ -373,16 +388,17 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
   L.grad = alloc(nv); L.search = alloc(nv); L.Mv = alloc(nv); L.qfrc_c = alloc(nv); L.tmpv = alloc(nv);
   L.actf = alloc(nu);
   int ubase = off;
-  // union A: smooth-dynamics-only regions
-  L.xfrc = alloc(d.xfrc_applied.stride); L.xanchor = alloc(3 * m.njnt); L.xaxis = alloc(3 * m.njnt);
+  // union A: regions that are dead once the smooth dynamics (phases 1-4) are done
+  L.xfrc = alloc(d.xfrc_applied.stride);
+  L.xpos = alloc(3 * nb); L.xquat = alloc(4 * nb); L.xipos = alloc(3 * nb); L.scom = alloc(3 * nb);
+  L.xanchor = alloc(3 * m.njnt); L.xaxis = alloc(3 * m.njnt);
   L.cinert = alloc(10 * nb); L.crb = alloc(10 * nb); L.cdofdot = alloc(6 * nv); L.cvel = alloc(6 * nb);
   L.cacc = alloc(6 * nb);
   int endA = off;
   off = ubase;
   // union B: constraint / solver regions
   L.contacts = alloc(C_NFIELD * mc); L.limits = alloc(L_NFIELD * L.nlimcap); L.gstart = alloc(mc + 1);
-  L.gmask_lo = alloc(mc); L.gmask_hi = alloc(mc); L.gV = alloc(6 * mc); L.glist = alloc(64);
-  L.gA = alloc(36); L.gu = alloc(6 * nv); L.sens = off;
+  L.gV = alloc(6 * mc); L.glist = alloc(64); L.gA = alloc(36); L.gu = alloc(6 * nv); L.sens = off;
   int endB = off;
   L.total = pad4(std::max(endA, endB));
   s->smem_bytes = sizeof(float) * (size_t)L.total * B2_WARPS_PER_CTA;

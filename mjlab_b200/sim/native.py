@@ -9,7 +9,9 @@ import numpy as np
 
 from mjlab_b200.compiler.compile import MODEL_ARRAYS, MODEL_SCALARS_F, MODEL_SCALARS_I
 
-LIB_PATH = Path(__file__).resolve().parents[1] / "csrc" / "libb2sim.so"
+import os
+
+LIB_PATH = Path(os.environ.get("B2SIM_LIB", Path(__file__).resolve().parents[1] / "csrc" / "libb2sim.so"))
 
 
 class B2Array(ctypes.Structure):

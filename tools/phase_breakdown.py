@@ -1,0 +1,28 @@
+"""Per-phase cycle breakdown of the step kernel (needs the -DB2_PHASE_TIMING variant:
+B2SIM_LIB=mjlab_b200/csrc/variants/libb2sim_timing.so python tools/phase_breakdown.py)."""
+import ctypes, sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import torch
+from mjlab_b200.envs import VelocityEnvCfg, VelocityFlatEnv
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+env = VelocityFlatEnv(VelocityEnvCfg(num_envs=n), device="cuda:0")
+g = torch.Generator(device="cuda:0"); g.manual_seed(0)
+for _ in range(60):
+  env.step(torch.rand((n, 29), generator=g, device="cuda:0") * 2 - 1)
+sim = env.sim
+buf = (ctypes.c_ulonglong * 32)()
+sim._lib.b2_phase_cycles(buf)  # reset
+K = 20
+for _ in range(K): sim.step()
+torch.cuda.synchronize()
+assert sim._lib.b2_phase_cycles(buf) == 0, "library built without -DB2_PHASE_TIMING"
+names = ["load(TMA)", "kinematics", "geom/site poses", "com/cinert/cdof", "crb+M", "vel/rne/act/qfrc_smooth",
+         "collision", "limits/groups/aref", "chol(M)+qacc_smooth", "solver total(excl sub)", "sensors/forces",
+         "integrate+store", "  newton: update(J^T f, cost)", "  newton: H assembly", "  newton: chol+solve",
+         "  newton: symv+mulJ", "  newton: line search"]
+tot = sum(buf[i] for i in range(17))
+st = sim.stats()
+print(f"mean newton iters {st.niter_mean:.2f}, mean ncon {st.ncon_mean:.1f}; cycles per env-step (warp-serial): {tot / (K * n):.0f}")
+for i, nm in enumerate(names):
+  print(f"{nm:34s} {buf[i] / (K * n):10.0f} cyc/env  {100.0 * buf[i] / tot:5.1f}%")
