@@ -72,8 +72,9 @@ int b2_create(const B2ModelDesc* model, int nworld, int ncon_per_world, int njma
 int b2_destroy(b2_sim* sim);
 
 /* Zero-copy view of a field. Pointers stay valid for the lifetime of the sim, except that
- * b2_expand_model_field re-points the named Model field (the step kernels read model fields
- * through a pointer table in device memory, so already-captured CUDA graphs stay valid). */
+ * b2_expand_model_field re-points the named Model field.  The model-pointer table travels to the
+ * kernels as a by-value launch parameter, so CUDA graphs captured before an expansion must be
+ * re-captured (mjlab does: manager_based_rl_env.py:102-104; our Simulation does it lazily). */
 int b2_get_field(b2_sim* sim, int which, const char* name, B2Tensor* out);
 int b2_num_fields(b2_sim* sim, int which);
 const char* b2_field_name(b2_sim* sim, int which, int index);
@@ -90,6 +91,10 @@ int b2_get_option(b2_sim* sim, const char* key, double* value);
 int b2_step(b2_sim* sim, void* cuda_stream);              /* mjwarp.step    */
 int b2_forward(b2_sim* sim, void* cuda_stream);           /* mjwarp.forward */
 int b2_step_n(b2_sim* sim, int n, void* cuda_stream);     /* n sub-steps with ctrl held (decimation) */
+/* forward() restricted to the worlds whose byte in `world_mask_dev` (device pointer, nworld bytes,
+ * e.g. a torch.bool tensor) is non-zero: the partial-reset forward of manager_based_rl_env.py:128-132
+ * without recomputing worlds that were not reset. */
+int b2_forward_masked(b2_sim* sim, const unsigned char* world_mask_dev, void* cuda_stream);
 
 /* End-to-end call with HOST buffers (pinned or pageable): copies `ctrl` (nworld*nu floats, row
  * stride nu) to the device, runs `nsubstep` steps, copies qpos (nworld*nq) and qvel (nworld*nv)

@@ -379,6 +379,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int w = blockIdx.x * B2_WARPS_PER_CTA + warp;
   if (w >= dd.nworld) return;
+  if (dd.world_mask != nullptr && dd.world_mask[w] == 0) return;
   const Layout& L = m.lay;
 #ifdef B2_PHASE_TIMING
   long long tphase_ = clock64();

@@ -529,6 +529,14 @@ int b2_forward(b2_sim* s, void* stream) {
   DeviceGuard guard(s->device);
   return launch(s, false, (cudaStream_t)stream);
 }
+int b2_forward_masked(b2_sim* s, const unsigned char* world_mask_dev, void* stream) {
+  if (!s) return fail("b2_forward_masked: null sim");
+  DeviceGuard guard(s->device);
+  s->hd.world_mask = world_mask_dev;
+  int rc = launch(s, false, (cudaStream_t)stream);
+  s->hd.world_mask = nullptr;
+  return rc;
+}
 int b2_step_n(b2_sim* s, int n, void* stream) {
   if (!s) return fail("b2_step_n: null sim");
   DeviceGuard guard(s->device);

@@ -173,7 +173,7 @@ class VelocityFlatEnv:
     done = terminated | truncated
     # partial reset + forward (manager_based_rl_env.py:128-132), mask-based: no host sync
     self._reset_where(done)
-    self.sim.forward()
+    self.sim.forward(env_mask=done)  # only the reset envs need new derived quantities here
     # interval event: push_by_setting_velocity (events.py:127-143)
     self.push_time_left -= self.step_dt
     push = self.push_time_left <= 0

@@ -103,6 +103,7 @@ def load_library() -> ctypes.CDLL:
   L.b2_step.argtypes = [vp, vp]
   L.b2_forward.argtypes = [vp, vp]
   L.b2_step_n.argtypes = [vp, ci, vp]
+  L.b2_forward_masked.argtypes = [vp, vp, vp]
   L.b2_step_host.argtypes = [vp, vp, ci, vp, vp, vp]
   L.b2_stats.argtypes = [vp, vp, ctypes.POINTER(B2Stats)]
   L.b2_launch_count.argtypes = [vp]

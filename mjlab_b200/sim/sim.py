@@ -189,7 +189,15 @@ class Simulation:
   def reset(self) -> None:
     pass
 
-  def forward(self) -> None:
+  def forward(self, env_mask: torch.Tensor | None = None) -> None:
+    """``mjwarp.forward`` for all worlds, or only those selected by a bool ``env_mask`` (extension)."""
+    if env_mask is not None:
+      if env_mask.dtype != torch.bool or env_mask.numel() != self.num_envs or not env_mask.is_contiguous():
+        raise ValueError("env_mask must be a contiguous bool tensor with one entry per env")
+      native.check(
+        self._lib.b2_forward_masked(self._h, ctypes.c_void_p(env_mask.data_ptr()), self._stream())
+      )
+      return
     if self.use_cuda_graph and self._graph_dirty:
       self.create_graph()
     if self.use_cuda_graph and self.forward_graph is not None:

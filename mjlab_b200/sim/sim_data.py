@@ -74,7 +74,11 @@ class TorchArray:
       return NotImplemented
 
     def unwrap(x: Any) -> Any:
-      return x._tensor if isinstance(x, cls) else x
+      if isinstance(x, cls):
+        return x._tensor
+      if isinstance(x, (list, tuple)):
+        return type(x)(unwrap(y) for y in x)
+      return x
 
     return func(*tuple(unwrap(a) for a in args), **{k: unwrap(v) for k, v in kwargs.items()})
 

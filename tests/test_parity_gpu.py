@@ -219,3 +219,50 @@ def test_domain_randomization_fields(g1_model):
   assert np.abs(qv[0] - qv[1]).max() == 0.0
   assert np.abs(qv[0] - qv[2]).max() > 0.0
   sim.close()
+
+
+@pytest.mark.parametrize("name", ["g1_flat_seed101", "go1_flat_seed102", "g1_tracking_flat_seed103"])
+def test_cuda_matches_committed_golden(name):
+  """Same comparison against the committed fixtures (tests/golden, made by tools/make_golden.py)."""
+  from pathlib import Path
+
+  from mjlab_b200.asset_zoo import load_compiled
+  from mjlab_b200.sim import Simulation, SimulationCfg
+
+  z = np.load(Path(__file__).parent / "golden" / f"{name}.npz")
+  m = load_compiled(name.rsplit("_seed", 1)[0])
+  n = int(z["n"])
+  sim = Simulation(n, SimulationCfg(), m, "cuda:0")
+  st = {k[3:]: z[k] for k in z.files if k.startswith("in_")}
+  load_sim(sim, st)
+  sim.forward()
+  torch.cuda.synchronize()
+  assert (T(sim.data.ncon).ravel() == z["fwd_ncon"].ravel()).all()
+  assert relerr(T(sim.data.qacc), z["fwd_qacc"]).max() < 1e-3
+  assert relerr(T(sim.data.cvel).reshape(n, -1), z["fwd_cvel"]).max() < 1e-5
+  assert np.abs(T(sim.data.sensordata) - z["fwd_sensordata"]).max() < 1e-3
+  load_sim(sim, st)
+  for _ in range(3):
+    sim.step()
+  torch.cuda.synchronize()
+  assert relerr(T(sim.data.qpos), z["step3_qpos"]).max() < 1e-4
+  assert relerr(T(sim.data.qvel), z["step3_qvel"]).max() < 5e-3
+  sim.close()
+
+
+def test_masked_forward_only_touches_selected_worlds(g1_model):
+  from mjlab_b200.sim import Simulation, SimulationCfg
+
+  sim = Simulation(8, SimulationCfg(), g1_model, "cuda:0")
+  before = sim.data.xpos[:].clone()
+  sim.data.qpos[:, 2] += 1.0
+  mask = torch.zeros(8, dtype=torch.bool, device="cuda:0")
+  mask[[1, 5]] = True
+  sim.forward(env_mask=mask)
+  torch.cuda.synchronize()
+  after = sim.data.xpos[:]
+  assert (after[~mask] == before[~mask]).all()
+  assert torch.allclose(after[mask][:, 2, 2], before[mask][:, 2, 2] + 1.0)
+  with pytest.raises(ValueError):
+    sim.forward(env_mask=torch.zeros(3, dtype=torch.bool, device="cuda:0"))
+  sim.close()
