@@ -22,6 +22,9 @@
 #define MINIMP 0.0001f
 #define MAXIMP 0.9999f
 #define MINMU 1e-5f
+// shared-memory record strides chosen odd so lane-per-record accesses are bank-conflict free
+#define SD 7   // 6-float records: cdof, cdofdot, cvel, cacc / wrenches
+#define SI 11  // 10-float records: cinert, crb
 
 namespace b2 {
 
@@ -167,62 +170,65 @@ __device__ unsigned long long g_phase_cycles[32];
 #define PHASE_MARK(id)
 #endif
 
-// ---- dense packed Cholesky (lower, row-major packed) in shared memory ---------------------------
-// Balanced schedule: the trailing-triangle update of step k runs over a precomputed list of (i,j)
-// pairs ordered by descending j, so every lane gets the same number of pairs.  Each table word packs
-// the row bases of i and j and the column j: rb_i | rb_j << 11 | j << 22.
-__device__ __noinline__ void chol_factor(float* A, float* invdiag, int n,
-                                         const unsigned* __restrict__ coldesc, int lane) {
-  #pragma unroll 1
+// ---- dense packed LDL^T (lower, row-major packed) in shared memory --------------------------------
+// In place: after the call A[k,k] = d_k and A[i,k] = L_ik d_k (i > k); invdiag[k] = 1/d_k.  One warp
+// barrier per pivot.  Balanced schedule: the trailing-triangle update of step k runs over a list of
+// (i,j) pairs ordered by descending j (a prefix of the list per k), one table word per pair packing the
+// row bases: rb_i | rb_j << 11 | j << 22.  `coldesc` lives in shared memory (per CTA).
+__device__ __noinline__ void chol_factor(float* A, float* invdiag, int n, const unsigned* coldesc,
+                                         int lane) {
+#pragma unroll 1
   for (int k = 0; k < n; k++) {
     int rk = k * (k + 1) >> 1;
-    float akk = A[rk + k];
-    float inv = rsqrtf(fmaxf(akk, MINVAL));
-    #pragma unroll 1
-    for (int i = k + 1 + lane; i < n; i += 32) A[(i * (i + 1) >> 1) + k] *= inv;
-    if (lane == 0) { A[rk + k] = akk * inv; invdiag[k] = inv; }
-    __syncwarp();
+    float dinv = __frcp_rn(fmaxf(A[rk + k], MINVAL));
+    if (lane == 0) invdiag[k] = dinv;
     int mtr = n - k - 1;
     int np = mtr * (mtr + 1) >> 1;
     int p = lane;
-    for (; p + 32 < np; p += 64) {
-      unsigned e0 = coldesc[p], e1 = coldesc[p + 32];
+#pragma unroll 1
+    for (; p + 96 < np; p += 128) {  // 4 independent pair updates in flight per lane
+      unsigned e0 = coldesc[p], e1 = coldesc[p + 32], e2 = coldesc[p + 64], e3 = coldesc[p + 96];
       int ri0 = e0 & 0x7ff, rj0 = (e0 >> 11) & 0x7ff, j0 = e0 >> 22;
       int ri1 = e1 & 0x7ff, rj1 = (e1 >> 11) & 0x7ff, j1 = e1 >> 22;
+      int ri2 = e2 & 0x7ff, rj2 = (e2 >> 11) & 0x7ff, j2 = e2 >> 22;
+      int ri3 = e3 & 0x7ff, rj3 = (e3 >> 11) & 0x7ff, j3 = e3 >> 22;
       float a0 = A[ri0 + k], b0 = A[rj0 + k], a1 = A[ri1 + k], b1 = A[rj1 + k];
-      float c0 = A[ri0 + j0], c1 = A[ri1 + j1];
-      A[ri0 + j0] = c0 - a0 * b0;
-      A[ri1 + j1] = c1 - a1 * b1;
+      float a2 = A[ri2 + k], b2 = A[rj2 + k], a3 = A[ri3 + k], b3 = A[rj3 + k];
+      float c0 = A[ri0 + j0], c1 = A[ri1 + j1], c2 = A[ri2 + j2], c3 = A[ri3 + j3];
+      A[ri0 + j0] = c0 - a0 * (b0 * dinv);
+      A[ri1 + j1] = c1 - a1 * (b1 * dinv);
+      A[ri2 + j2] = c2 - a2 * (b2 * dinv);
+      A[ri3 + j3] = c3 - a3 * (b3 * dinv);
     }
-    if (p < np) {
+#pragma unroll 1
+    for (; p < np; p += 32) {
       unsigned e0 = coldesc[p];
       int ri0 = e0 & 0x7ff, rj0 = (e0 >> 11) & 0x7ff, j0 = e0 >> 22;
-      A[ri0 + j0] -= A[ri0 + k] * A[rj0 + k];
+      A[ri0 + j0] -= A[ri0 + k] * (A[rj0 + k] * dinv);
     }
     __syncwarp();
   }
 }
-// x <- (L L^T)^-1 x, x in shared memory (n <= 64). Values are held in registers during the sweeps.
+// x <- (L D L^T)^-1 x, x in shared memory (n <= 64); values stay in registers during the sweeps.
 __device__ __noinline__ void chol_solve(const float* L, const float* invdiag, float* x, int n,
                                         int lane) {
   float x0 = lane < n ? x[lane] : 0.f;
   float x1 = lane + 32 < n ? x[lane + 32] : 0.f;
+  const float d0 = lane < n ? invdiag[lane] : 0.f, d1 = lane + 32 < n ? invdiag[lane + 32] : 0.f;
   const int r0 = lane * (lane + 1) >> 1, r1 = (lane + 32) * (lane + 33) >> 1;
-  #pragma unroll 1
-  for (int k = 0; k < n; k++) {
+#pragma unroll 1
+  for (int k = 0; k < n; k++) {  // L y = b
     float xk = __shfl_sync(FULL, k < 32 ? x0 : x1, k & 31) * invdiag[k];
-    if (lane == k) x0 = xk;
-    if (lane + 32 == k) x1 = xk;
     if (lane > k && lane < n) x0 -= L[r0 + k] * xk;
     if (lane + 32 > k && lane + 32 < n) x1 -= L[r1 + k] * xk;
   }
-  for (int k = n - 1; k >= 0; k--) {
-    float xk = __shfl_sync(FULL, k < 32 ? x0 : x1, k & 31) * invdiag[k];
+  x0 *= d0; x1 *= d1;  // D z = y
+#pragma unroll 1
+  for (int k = n - 1; k >= 0; k--) {  // L^T x = z
+    float xk = __shfl_sync(FULL, k < 32 ? x0 : x1, k & 31);
     int rk = k * (k + 1) >> 1;
-    if (lane == k) x0 = xk;
-    if (lane + 32 == k) x1 = xk;
-    if (lane < k) x0 -= L[rk + lane] * xk;
-    if (lane + 32 < k) x1 -= L[rk + lane + 32] * xk;
+    if (lane < k) x0 -= L[rk + lane] * d0 * xk;
+    if (lane + 32 < k) x1 -= L[rk + lane + 32] * d1 * xk;
   }
   if (lane < n) x[lane] = x0;
   if (lane + 32 < n) x[lane + 32] = x1;
@@ -304,7 +310,7 @@ __device__ __noinline__ void mulJ(const float* x, int dstc, int dstl, bool accum
       while (mk) {
         int d = __ffsll((long long)mk) - 1;
         mk &= mk - 1;
-        float v = cdof[6 * d + comp] * x[d];
+        float v = cdof[SD * d + comp] * x[d];
         acc += (m2 >> d & 1ull) ? v : -v;
       }
       gV[6 * g + comp] = acc;
@@ -377,7 +383,13 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   extern __shared__ __align__(16) float smem_all[];
   __shared__ __align__(8) unsigned long long bars[B2_WARPS_PER_CTA];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int w = blockIdx.x * B2_WARPS_PER_CTA + warp;
+  const int slot = blockIdx.x * B2_WARPS_PER_CTA + warp;
+  const int w = (dd.world_order != nullptr && slot < dd.nworld) ? dd.world_order[slot] : slot;
+  // per-CTA copy of the factorisation pair schedule (shared by the CTA's warps)
+  unsigned* s_coldesc = (unsigned*)(smem_all + (size_t)B2_WARPS_PER_CTA * m.lay.total);
+#pragma unroll 1
+  for (int i = threadIdx.x; i < m.ntri; i += 32 * B2_WARPS_PER_CTA) s_coldesc[i] = m.tri_coldesc[i];
+  __syncthreads();  // the only block barrier; nothing below synchronises across warps
   if (w >= dd.nworld) return;
   if (dd.world_mask != nullptr && dd.world_mask[w] == 0) return;
   const Layout& L = m.lay;
@@ -584,7 +596,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         for (int j = 0; j < 3; j++)
           t[3 * i + j] = mat[3 * i] * in[0] * mat[3 * j] + mat[3 * i + 1] * in[1] * mat[3 * j + 1] +
                          mat[3 * i + 2] * in[2] * mat[3 * j + 2];
-      float* ci = cinert + 10 * b;
+      float* ci = cinert + SI * b;
       if (b == 0) {
 #pragma unroll
         for (int k = 0; k < 10; k++) ci[k] = 0.f;
@@ -606,19 +618,19 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         float mat[9];
         quat2mat(mat, xquat + 4 * b);
         for (int k = 0; k < 3; k++) {
-          float* c = cdof + 6 * (da + k);
+          float* c = cdof + SD * (da + k);
           c[0] = c[1] = c[2] = 0.f; c[3] = c[4] = c[5] = 0.f; c[3 + k] = 1.f;
           float ax[3] = {mat[k], mat[3 + k], mat[6 + k]};
-          float* r = cdof + 6 * (da + 3 + k);
+          float* r = cdof + SD * (da + 3 + k);
           r[0] = ax[0]; r[1] = ax[1]; r[2] = ax[2];
           cross3(r + 3, ax, off);
         }
       } else if (ty == JNT_SLIDE) {
-        float* c = cdof + 6 * da;
+        float* c = cdof + SD * da;
         c[0] = c[1] = c[2] = 0.f;
         c[3] = xaxis[3 * j]; c[4] = xaxis[3 * j + 1]; c[5] = xaxis[3 * j + 2];
       } else {
-        float* c = cdof + 6 * da;
+        float* c = cdof + SD * da;
         c[0] = xaxis[3 * j]; c[1] = xaxis[3 * j + 1]; c[2] = xaxis[3 * j + 2];
         cross3(c + 3, xaxis + 3 * j, off);
       }
@@ -637,11 +649,11 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     for (int d = 1; d < nb; d++) {
       if (m.body_ancmask[d] >> b & 1ull) {
 #pragma unroll
-        for (int k = 0; k < 10; k++) acc[k] += cinert[10 * d + k];
+        for (int k = 0; k < 10; k++) acc[k] += cinert[SI * d + k];
       }
     }
 #pragma unroll
-    for (int k = 0; k < 10; k++) crb[10 * b + k] = acc[k];
+    for (int k = 0; k < 10; k++) crb[SI * b + k] = acc[k];
   }
   #pragma unroll 1
   for (int i = lane; i < m.ntri; i += 32) Mq[i] = 0.f;
@@ -651,8 +663,8 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     #pragma unroll 1
     for (int i = lane; i < nv; i += 32) {
       float buf[6];
-      mul_inert_vec(buf, crb + 10 * m.dof_bodyid[i], cdof + 6 * i);
-      for (int j = i; j >= 0; j = m.dof_parentid[j]) Mq[tri(i, j)] = dot6(cdof + 6 * j, buf);
+      mul_inert_vec(buf, crb + SI * m.dof_bodyid[i], cdof + SD * i);
+      for (int j = i; j >= 0; j = m.dof_parentid[j]) Mq[tri(i, j)] = dot6(cdof + SD * j, buf);
       Mq[tri(i, i)] += arm[i];
     }
   }
@@ -668,11 +680,11 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     while (mask) {
       int d = __ffsll((long long)mask) - 1;
       mask &= mask - 1;
-      const float* c = cdof + 6 * d;
+      const float* c = cdof + SD * d;
       if (own0 >= 0 && d >= own0) {
         int j = m.dof_jntid[d];
         int off = d - m.jnt_dofadr[j];
-        float* cd = cdofdot + 6 * d;
+        float* cd = cdofdot + SD * d;
         if (m.jnt_type[j] == JNT_FREE) {
           if (off < 3) { cd[0] = cd[1] = cd[2] = cd[3] = cd[4] = cd[5] = 0.f; }
           else {
@@ -686,7 +698,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       for (int k = 0; k < 6; k++) v[k] += c[k] * qd;
     }
 #pragma unroll
-    for (int k = 0; k < 6; k++) cvel[6 * b + k] = v[k];
+    for (int k = 0; k < 6; k++) cvel[SD * b + k] = v[k];
     // output cvel in MuJoCo's convention: linear part at subtree_com[root]
     int r = m.body_rootid[b];
     float dr[3] = {scom[3 * r] - c0[0], scom[3 * r + 1] - c0[1], scom[3 * r + 2] - c0[2]}, t[3];
@@ -705,18 +717,18 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       mask &= mask - 1;
       float qd = qvel[d];
 #pragma unroll
-      for (int k = 0; k < 6; k++) a[k] += cdofdot[6 * d + k] * qd;
+      for (int k = 0; k < 6; k++) a[k] += cdofdot[SD * d + k] * qd;
     }
     float t[6], t1[6], t2[6];
-    mul_inert_vec(t, cinert + 10 * b, cvel + 6 * b);
-    cross_force(t1, cvel + 6 * b, t);
-    mul_inert_vec(t2, cinert + 10 * b, a);
+    mul_inert_vec(t, cinert + SI * b, cvel + SD * b);
+    cross_force(t1, cvel + SD * b, t);
+    mul_inert_vec(t2, cinert + SI * b, a);
     // net external wrench on the body about c0: xfrc_applied (force at xipos) minus bias wrench
     const float* xf = xfrc + 6 * b;
     float arm[3] = {xipos[3 * b] - c0[0], xipos[3 * b + 1] - c0[1], xipos[3 * b + 2] - c0[2]}, tq[3];
     cross3(tq, arm, xf);
-    float* cf = cacc + 6 * b;  // region reused: [bias wrench]
-    float* cx = crb + 6 * b;   // region reused: [applied wrench]
+    float* cf = cacc + SD * b;  // region reused: [bias wrench]
+    float* cx = crb + SD * b;   // region reused: [applied wrench]
     if (b == 0) {
 #pragma unroll
       for (int k = 0; k < 6; k++) { cf[k] = 0.f; cx[k] = 0.f; }
@@ -760,15 +772,15 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       for (int b = 1; b < nb; b++) {
         if (m.body_dofmask[b] >> i & 1ull) {
 #pragma unroll
-          for (int k = 0; k < 6; k++) { sb[k] += cacc[6 * b + k]; sx[k] += crb[6 * b + k]; }
+          for (int k = 0; k < 6; k++) { sb[k] += cacc[SD * b + k]; sx[k] += crb[SD * b + k]; }
         }
       }
-      float bias = dot6(cdof + 6 * i, sb);
+      float bias = dot6(cdof + SD * i, sb);
       float passive = -damp[i] * qvel[i];
       int j = m.dof_jntid[i];
       if (m.jnt_type[j] != JNT_FREE && stiff[j] != 0.f)
         passive -= stiff[j] * (qpos[m.jnt_qposadr[j]] - qpos0[m.jnt_qposadr[j]]);
-      float fs = passive - bias + qfrc_applied[i] + tmpv[i] + dot6(cdof + 6 * i, sx);
+      float fs = passive - bias + qfrc_applied[i] + tmpv[i] + dot6(cdof + SD * i, sx);
       qfrc_smooth[i] = fs;
       qacc_smooth[i] = fs;
       if (m.debug) {
@@ -1116,7 +1128,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   #pragma unroll 1
   for (int i = lane; i < m.ntri; i += 32) H[i] = Mq[i];
   __syncwarp();
-  chol_factor(H, invdiag, nv, m.tri_coldesc, lane);
+  chol_factor(H, invdiag, nv, s_coldesc, lane);
   chol_solve(H, invdiag, qacc_smooth, nv, lane);
   if (m.debug)
     #pragma unroll 1
@@ -1232,7 +1244,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
           unsigned long long m2 = m.body_dofmask[key >> 8];
           unsigned long long mk = m.body_dofmask[key & 0xff] ^ m2;
           if (mk >> i & 1ull) {
-            float v = dot6(cdof + 6 * i, gV + 6 * g);
+            float v = dot6(cdof + SD * i, gV + 6 * g);
             acc += (m2 >> i & 1ull) ? v : -v;
           }
         }
@@ -1310,7 +1322,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         for (int a = lane; a < ns; a += 32) {
           int d = glist[a];
           float sg = (m2 >> d & 1ull) ? 1.f : -1.f;
-          const float* c = cdof + 6 * d;
+          const float* c = cdof + SD * d;
 #pragma unroll
           for (int k = 0; k < 6; k++) {
             float t = 0.f;
@@ -1320,19 +1332,26 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
           }
         }
         __syncwarp();
-        int np = ns * (ns + 1) >> 1;
-        #pragma unroll 1
-        for (int p = lane; p < np; p += 32) {
-          unsigned short e = m.tri_rowmajor[p];
-          int a = e & 0xff, b = e >> 8;  // a >= b
-          int da = glist[a], db = glist[b];
-          float v = dot6(gu + 6 * a, cdof + 6 * db);
-          H[(da * (da + 1) >> 1) + db] += (m2 >> db & 1ull) ? v : -v;
+        // lane = column b of the group's dof list; rows a >= b visited in lock step (u_a broadcast)
+#pragma unroll 1
+        for (int b0 = 0; b0 < ns; b0 += 32) {
+          int b = b0 + lane;
+          int db = b < ns ? glist[b] : 0;
+          float sgb = (m2 >> db & 1ull) ? 1.f : -1.f;
+          float cb[6];
+#pragma unroll
+          for (int k = 0; k < 6; k++) cb[k] = sgb * cdof[SD * db + k];
+#pragma unroll 1
+          for (int a = b0; a < ns; a++) {
+            const float* u = gu + 6 * a;
+            float v = u[0] * cb[0] + u[1] * cb[1] + u[2] * cb[2] + u[3] * cb[3] + u[4] * cb[4] + u[5] * cb[5];
+            int da = glist[a];
+            if (b <= a && b < ns) H[(da * (da + 1) >> 1) + db] += v;
+          }
         }
         __syncwarp();
       }
-      PHASE_MARK(13);
-      chol_factor(H, invdiag, nv, m.tri_coldesc, lane);
+      chol_factor(H, invdiag, nv, s_coldesc, lane);
       #pragma unroll 1
       for (int i = lane; i < nv; i += 32) search[i] = -grad[i];
       __syncwarp();
@@ -1563,7 +1582,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       #pragma unroll 1
       for (int i = lane; i < nv; i += 32) tmpv[i] = qfrc_smooth[i] + qfrc_c[i];
       __syncwarp();
-      chol_factor(H, invdiag, nv, m.tri_coldesc, lane);
+      chol_factor(H, invdiag, nv, s_coldesc, lane);
       chol_solve(H, invdiag, tmpv, nv, lane);
     } else {
       #pragma unroll 1

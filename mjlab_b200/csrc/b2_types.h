@@ -98,5 +98,6 @@ struct DevData {
   DArr qfrc_bias, qfrc_smooth, qacc_smooth, qfrc_constraint, qM;
   DArr contact_dist, contact_pos, contact_frame, contact_force, solver_cost;
   IArr ncon, nefc, solver_niter, contact_geom, overflow;
+  const int* world_order;           // optional: launch slot -> world (heavy-first dispatch)
   const unsigned char* world_mask;  // optional: worlds with mask 0 are skipped (masked forward)
 };

@@ -55,6 +55,8 @@ struct b2_sim {
   std::vector<Field> data_fields, model_fields;
   std::vector<void*> allocs;
   int64_t launches = 0;
+  int* order = nullptr;       // heavy-first dispatch order (device)
+  int sorted_dispatch = 1;
   size_t smem_bytes = 0;
   std::map<std::string, std::vector<double>> mf;  // host copy of float model arrays
   std::map<std::string, std::vector<int>> mi;
@@ -82,6 +84,30 @@ __global__ void b2_init_rows_kernel(float* dst, int stride, const float* __restr
                                     int nworld) {
   long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid < (long long)nworld * n) dst[(tid / n) * stride + (tid % n)] = src[tid % n];
+}
+
+// Heavy-first dispatch: order worlds by the previous step's (Newton iterations, contacts),
+// descending, with a one-CTA counting sort (128 buckets).  Only scheduling changes, not results.
+__global__ void b2_order_kernel(const int* __restrict__ niter, int niter_stride, const int* __restrict__ ncon,
+                                int ncon_stride, int nworld, int* __restrict__ order) {
+  __shared__ int hist[128];
+  __shared__ int base[128];
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  for (int w = threadIdx.x; w < nworld; w += blockDim.x) {
+    int key = min(niter[(size_t)w * niter_stride], 15) * 8 + min(ncon[(size_t)w * ncon_stride] >> 3, 7);
+    atomicAdd(&hist[127 - key], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int i = 0; i < 128; i++) { base[i] = acc; acc += hist[i]; }
+  }
+  __syncthreads();
+  for (int w = threadIdx.x; w < nworld; w += blockDim.x) {
+    int key = min(niter[(size_t)w * niter_stride], 15) * 8 + min(ncon[(size_t)w * ncon_stride] >> 3, 7);
+    order[atomicAdd(&base[127 - key], 1)] = w;
+  }
 }
 
 // inner shapes of model float fields: dims after the (broadcast) world dimension
@@ -155,6 +181,14 @@ static int add_idata(b2_sim* s, const char* name, IArr* arr, int n, int second =
 
 static int launch(b2_sim* s, bool step, cudaStream_t st) {
   int grid = (s->nworld + B2_WARPS_PER_CTA - 1) / B2_WARPS_PER_CTA;
+  if (step && s->sorted_dispatch && s->order && s->nworld >= 512 && s->hd.world_mask == nullptr) {
+    b2_order_kernel<<<1, 1024, 0, st>>>(s->hd.solver_niter.p, s->hd.solver_niter.stride, s->hd.ncon.p,
+                                        s->hd.ncon.stride, s->nworld, s->order);
+    s->launches++;
+    s->hd.world_order = s->order;
+  } else {
+    s->hd.world_order = nullptr;
+  }
   if (step)
     b2_step_kernel<true><<<grid, 32 * B2_WARPS_PER_CTA, s->smem_bytes, st>>>(s->hm, s->hd);
   else
@@ -380,7 +414,7 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
   L.maxpair = 128;
   L.qpos = alloc(d.qpos.stride); L.qvel = alloc(d.qvel.stride); L.ctrl = alloc(d.ctrl.stride);
   L.qacc_ws = alloc(d.qacc_warmstart.stride); L.qfrc_applied = alloc(d.qfrc_applied.stride);
-  L.cdof = alloc(6 * nv); L.M = alloc(m.ntri);
+  L.cdof = alloc(7 * nv); L.M = alloc(m.ntri);
   int hsize = std::max(m.ntri, 12 * m.ncg + L.maxpair);
   L.H = alloc(hsize); L.gpose = L.H; L.pairlist = L.H + 12 * m.ncg;
   L.invdiag = alloc(nv);
@@ -392,8 +426,8 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
   L.xfrc = alloc(d.xfrc_applied.stride);
   L.xpos = alloc(3 * nb); L.xquat = alloc(4 * nb); L.xipos = alloc(3 * nb); L.scom = alloc(3 * nb);
   L.xanchor = alloc(3 * m.njnt); L.xaxis = alloc(3 * m.njnt);
-  L.cinert = alloc(10 * nb); L.crb = alloc(10 * nb); L.cdofdot = alloc(6 * nv); L.cvel = alloc(6 * nb);
-  L.cacc = alloc(6 * nb);
+  L.cinert = alloc(11 * nb); L.crb = alloc(11 * nb); L.cdofdot = alloc(7 * nv); L.cvel = alloc(7 * nb);
+  L.cacc = alloc(7 * nb);
   int endA = off;
   off = ubase;
   // union B: constraint / solver regions
@@ -401,7 +435,7 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
   L.gV = alloc(6 * mc); L.glist = alloc(64); L.gA = alloc(36); L.gu = alloc(6 * nv); L.sens = off;
   int endB = off;
   L.total = pad4(std::max(endA, endB));
-  s->smem_bytes = sizeof(float) * (size_t)L.total * B2_WARPS_PER_CTA;
+  s->smem_bytes = sizeof(float) * ((size_t)L.total * B2_WARPS_PER_CTA + pad4(m.ntri));
   if (s->smem_bytes > 227 * 1024) {
     b2_destroy(s);
     return fail("b2_create: model too large for the per-environment shared-memory block");
@@ -413,6 +447,12 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
       b2_destroy(s);
       return fail(std::string("cudaFuncSetAttribute(max dynamic smem): ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
     }
+  }
+  {
+    void* p = nullptr;
+    if (cudaMalloc(&p, sizeof(int) * (size_t)nworld) != cudaSuccess) { b2_destroy(s); return fail("cudaMalloc(order)"); }
+    s->allocs.push_back(p);
+    s->order = (int*)p;
   }
   // qpos <- qpos0 in every world, then one forward pass so all derived fields are valid
   {
@@ -499,6 +539,7 @@ int b2_set_option(b2_sim* s, const char* key, double v) {
   else if (k == "integrator") m.integrator = (int)v;
   else if (k == "debug_outputs") m.debug = (int)v;
   else if (k == "ls_parallel") { /* accepted for API parity; the line search here is exact */ }
+  else if (k == "sorted_dispatch") s->sorted_dispatch = (int)v;
   else return fail("b2_set_option: unknown option '" + k + "'");
   return 0;
 }
