@@ -177,34 +177,91 @@ __device__ unsigned long long g_phase_cycles[32];
 // row bases: rb_i | rb_j << 11 | j << 22.  `coldesc` lives in shared memory (per CTA).
 __device__ __noinline__ void chol_factor(float* A, float* invdiag, int n, const unsigned* coldesc,
                                          int lane) {
+  // Blocked right-looking LDL^T, 4 pivots per block step: a register-resident panel factorisation
+  // (lane = row) followed by one rank-4 trailing update over the balanced pair list.
 #pragma unroll 1
-  for (int k = 0; k < n; k++) {
-    int rk = k * (k + 1) >> 1;
-    float dinv = __frcp_rn(fmaxf(A[rk + k], MINVAL));
-    if (lane == 0) invdiag[k] = dinv;
-    int mtr = n - k - 1;
-    int np = mtr * (mtr + 1) >> 1;
-    int p = lane;
+  for (int k = 0; k < n; k += 4) {
+    const int nb = min(4, n - k);
+    float dv[4] = {0.f, 0.f, 0.f, 0.f};      // 1/d of the block's pivots (warp-uniform)
+    float Lb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // L10, L20, L21, L30, L31, L32 (warp-uniform)
+    // ---- panel: rows k.., columns k..k+nb-1 -------------------------------------------------
 #pragma unroll 1
-    for (; p + 96 < np; p += 128) {  // 4 independent pair updates in flight per lane
-      unsigned e0 = coldesc[p], e1 = coldesc[p + 32], e2 = coldesc[p + 64], e3 = coldesc[p + 96];
-      int ri0 = e0 & 0x7ff, rj0 = (e0 >> 11) & 0x7ff, j0 = e0 >> 22;
-      int ri1 = e1 & 0x7ff, rj1 = (e1 >> 11) & 0x7ff, j1 = e1 >> 22;
-      int ri2 = e2 & 0x7ff, rj2 = (e2 >> 11) & 0x7ff, j2 = e2 >> 22;
-      int ri3 = e3 & 0x7ff, rj3 = (e3 >> 11) & 0x7ff, j3 = e3 >> 22;
-      float a0 = A[ri0 + k], b0 = A[rj0 + k], a1 = A[ri1 + k], b1 = A[rj1 + k];
-      float a2 = A[ri2 + k], b2 = A[rj2 + k], a3 = A[ri3 + k], b3 = A[rj3 + k];
-      float c0 = A[ri0 + j0], c1 = A[ri1 + j1], c2 = A[ri2 + j2], c3 = A[ri3 + j3];
-      A[ri0 + j0] = c0 - a0 * (b0 * dinv);
-      A[ri1 + j1] = c1 - a1 * (b1 * dinv);
-      A[ri2 + j2] = c2 - a2 * (b2 * dinv);
-      A[ri3 + j3] = c3 - a3 * (b3 * dinv);
+    for (int base = k; base < n; base += 32) {
+      int i = base + lane;
+      bool ok = i < n;
+      int ri = ok ? (i * (i + 1) >> 1) : 0;
+      float r[4];
+#pragma unroll
+      for (int t = 0; t < 4; t++) r[t] = (ok && t < nb && k + t <= i) ? A[ri + k + t] : 0.f;
+      if (base == k) {
+        // block rows are lanes 0..nb-1 of the first pass: factor the 4x4 diagonal block by shuffles
+        float d0 = __shfl_sync(FULL, r[0], 0);
+        dv[0] = __frcp_rn(fmaxf(d0, MINVAL));
+        if (nb > 1) {
+          Lb[0] = __shfl_sync(FULL, r[0], 1) * dv[0];
+          if (i > k) r[1] -= r[0] * Lb[0];
+          dv[1] = __frcp_rn(fmaxf(__shfl_sync(FULL, r[1], 1), MINVAL));
+        }
+        if (nb > 2) {
+          Lb[1] = __shfl_sync(FULL, r[0], 2) * dv[0];
+          Lb[2] = __shfl_sync(FULL, r[1], 2) * dv[1];
+          if (i > k + 1) r[2] -= r[0] * Lb[1] + r[1] * Lb[2];
+          dv[2] = __frcp_rn(fmaxf(__shfl_sync(FULL, r[2], 2), MINVAL));
+        }
+        if (nb > 3) {
+          Lb[3] = __shfl_sync(FULL, r[0], 3) * dv[0];
+          Lb[4] = __shfl_sync(FULL, r[1], 3) * dv[1];
+          Lb[5] = __shfl_sync(FULL, r[2], 3) * dv[2];
+          if (i > k + 2) r[3] -= r[0] * Lb[3] + r[1] * Lb[4] + r[2] * Lb[5];
+          dv[3] = __frcp_rn(fmaxf(__shfl_sync(FULL, r[3], 3), MINVAL));
+        }
+        if (lane < nb) invdiag[k + lane] = lane == 0 ? dv[0] : (lane == 1 ? dv[1] : (lane == 2 ? dv[2] : dv[3]));
+      } else {
+        r[1] -= r[0] * Lb[0];
+        r[2] -= r[0] * Lb[1] + r[1] * Lb[2];
+        r[3] -= r[0] * Lb[3] + r[1] * Lb[4] + r[2] * Lb[5];
+      }
+      if (ok) {
+#pragma unroll
+        for (int t = 1; t < 4; t++)
+          if (t < nb && k + t <= i) A[ri + k + t] = r[t];
+      }
     }
+    __syncwarp();
+    // ---- trailing update: A[i,j] -= sum_t c_i,k+t * c_j,k+t / d_t for j >= k+nb ---------------
+    int mtr = n - k - nb;
+    if (mtr <= 0) break;
+    int np = mtr * (mtr + 1) >> 1;
+    if (nb == 4) {
+      int p = lane;
 #pragma unroll 1
-    for (; p < np; p += 32) {
-      unsigned e0 = coldesc[p];
-      int ri0 = e0 & 0x7ff, rj0 = (e0 >> 11) & 0x7ff, j0 = e0 >> 22;
-      A[ri0 + j0] -= A[ri0 + k] * (A[rj0 + k] * dinv);
+      for (; p + 32 < np; p += 64) {
+        unsigned e0 = coldesc[p], e1 = coldesc[p + 32];
+        int ri0 = (e0 & 0x7ff) + k, rj0 = ((e0 >> 11) & 0x7ff) + k, t0 = (e0 & 0x7ff) + (e0 >> 22);
+        int ri1 = (e1 & 0x7ff) + k, rj1 = ((e1 >> 11) & 0x7ff) + k, t1 = (e1 & 0x7ff) + (e1 >> 22);
+        float acc0 = A[ri0] * (A[rj0] * dv[0]) + A[ri0 + 1] * (A[rj0 + 1] * dv[1]) +
+                     A[ri0 + 2] * (A[rj0 + 2] * dv[2]) + A[ri0 + 3] * (A[rj0 + 3] * dv[3]);
+        float acc1 = A[ri1] * (A[rj1] * dv[0]) + A[ri1 + 1] * (A[rj1 + 1] * dv[1]) +
+                     A[ri1 + 2] * (A[rj1 + 2] * dv[2]) + A[ri1 + 3] * (A[rj1 + 3] * dv[3]);
+        A[t0] -= acc0;
+        A[t1] -= acc1;
+      }
+#pragma unroll 1
+      for (; p < np; p += 32) {
+        unsigned e0 = coldesc[p];
+        int ri0 = (e0 & 0x7ff) + k, rj0 = ((e0 >> 11) & 0x7ff) + k, t0 = (e0 & 0x7ff) + (e0 >> 22);
+        A[t0] -= A[ri0] * (A[rj0] * dv[0]) + A[ri0 + 1] * (A[rj0 + 1] * dv[1]) +
+                 A[ri0 + 2] * (A[rj0 + 2] * dv[2]) + A[ri0 + 3] * (A[rj0 + 3] * dv[3]);
+      }
+    } else {
+#pragma unroll 1
+      for (int p = lane; p < np; p += 32) {
+        unsigned e0 = coldesc[p];
+        int ri0 = (e0 & 0x7ff) + k, rj0 = ((e0 >> 11) & 0x7ff) + k, t0 = (e0 & 0x7ff) + (e0 >> 22);
+        float acc = 0.f;
+        for (int t = 0; t < nb; t++) acc += A[ri0 + t] * (A[rj0 + t] * dv[t]);
+        A[t0] -= acc;
+      }
     }
     __syncwarp();
   }
@@ -442,6 +499,61 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     for (int b = lane; b < nb; b += 32) {
       float pos[3] = {0.f, 0.f, 0.f}, quat[4] = {1.f, 0.f, 0.f, 0.f};
       int depth = m.body_depth[b];
+      if (m.fastkin) {
+        // one dependent load level per chain step: chain id -> 64-byte record (prefetched one ahead)
+        const int* chain = m.body_chain + b * m.maxdepth;
+        int c = depth > 0 ? chain[0] : 0;
+        #pragma unroll 1
+        for (int k = 0; k < depth; k++) {
+          int cn = k + 1 < depth ? chain[k + 1] : 0;
+          float4 r0 = m.kinrec[4 * c], r1 = m.kinrec[4 * c + 1], r2 = m.kinrec[4 * c + 2], r3 = m.kinrec[4 * c + 3];
+          int tj = __float_as_int(r2.w), qa = __float_as_int(r3.w);
+          int type = tj & 0xff, ja = tj >> 8;
+          bool last = (k == depth - 1);
+          if (type == JNT_FREE) {
+            pos[0] = qpos[qa]; pos[1] = qpos[qa + 1]; pos[2] = qpos[qa + 2];
+            quat[0] = qpos[qa + 3]; quat[1] = qpos[qa + 4]; quat[2] = qpos[qa + 5]; quat[3] = qpos[qa + 6];
+            normalize4(quat);
+            if (last) {
+              xanchor[3 * ja] = pos[0]; xanchor[3 * ja + 1] = pos[1]; xanchor[3 * ja + 2] = pos[2];
+              float ax0[3] = {r3.x, r3.y, r3.z}, ax[3];
+              rotq(ax, quat, ax0);
+              xaxis[3 * ja] = ax[0]; xaxis[3 * ja + 1] = ax[1]; xaxis[3 * ja + 2] = ax[2];
+            }
+          } else {
+            float bp[3] = {r0.x, r0.y, r0.z}, bq[4] = {r1.x, r1.y, r1.z, r1.w}, t[3], q2[4];
+            rotq(t, quat, bp);
+            pos[0] += t[0]; pos[1] += t[1]; pos[2] += t[2];
+            mulquat(q2, quat, bq);
+            quat[0] = q2[0]; quat[1] = q2[1]; quat[2] = q2[2]; quat[3] = q2[3];
+            if (type != 0xff) {
+              float jp[3] = {r2.x, r2.y, r2.z}, jax[3] = {r3.x, r3.y, r3.z}, anchor[3], axis[3];
+              rotq(anchor, quat, jp);
+              anchor[0] += pos[0]; anchor[1] += pos[1]; anchor[2] += pos[2];
+              rotq(axis, quat, jax);
+              if (last) {
+                xanchor[3 * ja] = anchor[0]; xanchor[3 * ja + 1] = anchor[1]; xanchor[3 * ja + 2] = anchor[2];
+                xaxis[3 * ja] = axis[0]; xaxis[3 * ja + 1] = axis[1]; xaxis[3 * ja + 2] = axis[2];
+              }
+              float dq = qpos[qa] - r0.w;
+              if (type == JNT_SLIDE) {
+                pos[0] += axis[0] * dq; pos[1] += axis[1] * dq; pos[2] += axis[2] * dq;
+              } else {
+                float sn, cs;
+                sincosf(0.5f * dq, &sn, &cs);
+                float ql[4] = {cs, jax[0] * sn, jax[1] * sn, jax[2] * sn};
+                mulquat(q2, quat, ql);
+                quat[0] = q2[0]; quat[1] = q2[1]; quat[2] = q2[2]; quat[3] = q2[3];
+                rotq(t, quat, jp);
+                pos[0] = anchor[0] - t[0]; pos[1] = anchor[1] - t[1]; pos[2] = anchor[2] - t[2];
+              }
+            }
+          }
+          normalize4(quat);
+          c = cn;
+        }
+        depth = 0;  // generic walk below is skipped
+      }
       #pragma unroll 1
       for (int k = 0; k < depth; k++) {
         int c = m.body_chain[b * m.maxdepth + k];
@@ -551,12 +663,12 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     #pragma unroll 1
     for (int b = lane; b < nb; b += 32) {
       float acc[3] = {0.f, 0.f, 0.f};
-      #pragma unroll 1
-      for (int d = 0; d < nb; d++) {
-        if (m.body_ancmask[d] >> b & 1ull) {
-          float md = mass[d];
-          acc[0] += md * xipos[3 * d]; acc[1] += md * xipos[3 * d + 1]; acc[2] += md * xipos[3 * d + 2];
-        }
+      unsigned long long desc = m.body_submask[b];
+      while (desc) {
+        int d = __ffsll((long long)desc) - 1;
+        desc &= desc - 1;
+        float md = mass[d];
+        acc[0] += md * xipos[3 * d]; acc[1] += md * xipos[3 * d + 1]; acc[2] += md * xipos[3 * d + 2];
       }
       if (sub[b] < MINVAL) { acc[0] = xipos[3 * b]; acc[1] = xipos[3 * b + 1]; acc[2] = xipos[3 * b + 2]; }
       else { float inv = 1.f / sub[b]; acc[0] *= inv; acc[1] *= inv; acc[2] *= inv; }
@@ -645,12 +757,12 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     float acc[10];
 #pragma unroll
     for (int k = 0; k < 10; k++) acc[k] = 0.f;
-    #pragma unroll 1
-    for (int d = 1; d < nb; d++) {
-      if (m.body_ancmask[d] >> b & 1ull) {
+    unsigned long long sub = m.body_submask[b] & ~1ull;
+    while (sub) {
+      int d = __ffsll((long long)sub) - 1;
+      sub &= sub - 1;
 #pragma unroll
-        for (int k = 0; k < 10; k++) acc[k] += cinert[SI * d + k];
-      }
+      for (int k = 0; k < 10; k++) acc[k] += cinert[SI * d + k];
     }
 #pragma unroll
     for (int k = 0; k < 10; k++) crb[SI * b + k] = acc[k];
@@ -768,12 +880,12 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     #pragma unroll 1
     for (int i = lane; i < nv; i += 32) {
       float sb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, sx[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      #pragma unroll 1
-      for (int b = 1; b < nb; b++) {
-        if (m.body_dofmask[b] >> i & 1ull) {
+      unsigned long long sub = m.dof_bodymask[i];
+      while (sub) {
+        int b = __ffsll((long long)sub) - 1;
+        sub &= sub - 1;
 #pragma unroll
-          for (int k = 0; k < 6; k++) { sb[k] += cacc[SD * b + k]; sx[k] += crb[SD * b + k]; }
-        }
+        for (int k = 0; k < 6; k++) { sb[k] += cacc[SD * b + k]; sx[k] += crb[SD * b + k]; }
       }
       float bias = dot6(cdof + SD * i, sb);
       float passive = -damp[i] * qvel[i];

@@ -70,6 +70,9 @@ struct DevModel {
   const int *body_parentid, *body_rootid, *body_jntadr, *body_jntnum, *body_dofadr, *body_dofnum;
   const int *body_chain, *body_depth;
   const unsigned long long *body_dofmask, *body_ancmask;
+  const unsigned long long *body_submask, *dof_bodymask;  // descendants of a body / bodies moved by a dof
+  const float4* kinrec;  // 4 x float4 per body: compact kinematic record (valid when fastkin)
+  int fastkin;
   const int *jnt_type, *jnt_qposadr, *jnt_dofadr, *jnt_bodyid, *jnt_limited;
   const int *dof_bodyid, *dof_jntid, *dof_parentid;
   const int *geom_type, *geom_bodyid, *geom_condim, *geom_priority, *geom_cslot, *cgeom;

@@ -290,6 +290,38 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
     for (int k = depth[b] - 1; k >= 0; k--) { chain[(size_t)b * maxdepth + k] = c; c = parent[c]; }
   }
   m.maxdepth = maxdepth;
+  std::vector<unsigned long long> submask(nb, 0ull), dofbody(std::max(m.nv, 1), 0ull);
+  for (int d = 0; d < nb; d++)
+    for (int a = 0; a < nb; a++)
+      if (ancmask[d] >> a & 1ull) submask[a] |= 1ull << d;
+  for (int b = 1; b < nb; b++)
+    for (int i = 0; i < m.nv; i++)
+      if (dofmask[b] >> i & 1ull) dofbody[i] |= 1ull << b;
+  // compact kinematic records (fast path: every body has at most one joint)
+  std::vector<float> kinrec((size_t)nb * 16, 0.f);
+  int fastkin = 1;
+  {
+    const std::vector<int>& jn = s->mi["body_jntnum"]; const std::vector<int>& ja = s->mi["body_jntadr"];
+    const std::vector<double>& bp = s->mf["body_pos"]; const std::vector<double>& bq = s->mf["body_quat"];
+    const std::vector<double>& jp = s->mf["jnt_pos"]; const std::vector<double>& jax = s->mf["jnt_axis"];
+    const std::vector<double>& q0 = s->mf["qpos0"];
+    for (int b = 0; b < nb; b++) {
+      if (jn[b] > 1) { fastkin = 0; break; }
+      float* r = kinrec.data() + 16 * b;
+      for (int k = 0; k < 3; k++) r[k] = (float)bp[3 * b + k];
+      for (int k = 0; k < 4; k++) r[4 + k] = (float)bq[4 * b + k];
+      int type = 0xff, j = 0, qa = 0;
+      if (jn[b] == 1) {
+        j = ja[b]; type = s->mi["jnt_type"][j]; qa = s->mi["jnt_qposadr"][j];
+        for (int k = 0; k < 3; k++) { r[8 + k] = (float)jp[3 * j + k]; r[12 + k] = (float)jax[3 * j + k]; }
+        r[3] = (float)q0[qa];
+      }
+      int tj = type | (j << 8);
+      memcpy(&r[11], &tj, 4);
+      memcpy(&r[15], &qa, 4);
+    }
+  }
+  m.fastkin = fastkin;
   std::vector<int> cslot(m.ngeom, -1), cgeom;
   for (int p = 0; p < m.npair; p++) {
     for (int g : {s->mi["pair_geom1"][p], s->mi["pair_geom2"][p]})
@@ -325,6 +357,13 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
   rc |= dev_upload<int>(s, chain, &m.body_chain);
   rc |= dev_upload<unsigned long long>(s, dofmask, &m.body_dofmask);
   rc |= dev_upload<unsigned long long>(s, ancmask, &m.body_ancmask);
+  rc |= dev_upload<unsigned long long>(s, submask, &m.body_submask);
+  rc |= dev_upload<unsigned long long>(s, dofbody, &m.dof_bodymask);
+  {
+    const float* kr = nullptr;
+    rc |= dev_upload<float>(s, kinrec, &kr);
+    m.kinrec = (const float4*)kr;
+  }
   rc |= dev_upload<int>(s, cslot, &m.geom_cslot);
   rc |= dev_upload<int>(s, cgeom, &m.cgeom);
   rc |= dev_upload<unsigned short>(s, trow, &m.tri_rowmajor);
@@ -521,6 +560,11 @@ int b2_expand_model_field(b2_sim* s, const char* name, void* stream, B2Tensor* o
     s->launches++;
     CUDA_OK(cudaGetLastError());
     f->farr->p = (const float*)p; f->farr->stride = n;
+    {
+      std::string nm = name;
+      if (nm == "body_pos" || nm == "body_quat" || nm == "jnt_pos" || nm == "jnt_axis" || nm == "qpos0")
+        s->hm.fastkin = 0;  // the compact kinematic records mirror the shared arrays only
+    }
     f->ptr = p; f->stride[0] = n;
   }
   if (out) fill_tensor(s, *f, out);
