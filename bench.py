@@ -169,6 +169,7 @@ def main():
   ap.add_argument("--envs", type=int, default=4096)
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-flush", action="store_true")
+  ap.add_argument("--preroll", type=int, default=100, help="untimed env steps before warm-up")
   args = ap.parse_args()
   if args.impl == "reference":
     return run_reference(args)
@@ -257,6 +258,9 @@ def main():
     b.record()
     phys_events.append((a, b, k))
 
+  # Pre-roll to the steady-state mix of standing / falling / freshly reset robots (all envs start
+  # standing at t=0, so without it the timed window would measure a transient), then W warm-up steps.
+  run("device", args.preroll, False)
   run("device", W, False)  # warm-up (untimed)
   env.sim.step_n = timed_step_n
   sampler = ClockSampler(local)
@@ -303,6 +307,7 @@ def main():
         "workload": WORKLOAD.format(envs=n), "envs_per_gpu": n, "decimation": 4,
         "parallelism": f"dp{world} (envs sharded, no physics coupling; one all-gather of reward/done)",
         "l2": "flushed between timed steps (256 MiB memset, untimed)" if flush_buf is not None else "not flushed",
+        "preroll_env_steps": args.preroll,
         "mean_ncon": st.ncon_mean, "mean_nefc": st.nefc_mean, "mean_newton_iters": st.niter_mean,
         "overflow_worlds": st.overflow_worlds,
       },

@@ -489,6 +489,11 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   float* search = s + L.search; float* Mv = s + L.Mv; float* qfrc_c = s + L.qfrc_c;
   float* tmpv = s + L.tmpv; float* actf = s + L.actf;
 
+  // The decimation loop (manager_based_rl_env.py:109-114: ctrl held, `decimation` x sim.step) runs inside
+  // the launch: state vectors stay in shared memory between sub-steps.
+#pragma unroll 1
+  for (int sub = 0;; sub++) {
+  const bool lastsub = !STEP || sub + 1 >= dd.nsub;
   // ---------------- phase 1: kinematics (lane per body, private walk down its ancestor chain) ----
   {
     const float* body_pos = MP(body_pos); const float* body_quat = MP(body_quat);
@@ -1463,6 +1468,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         }
         __syncwarp();
       }
+      PHASE_MARK(13);
       chol_factor(H, invdiag, nv, s_coldesc, lane);
       #pragma unroll 1
       for (int i = lane; i < nv; i += 32) search[i] = -grad[i];
@@ -1726,9 +1732,11 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     }
     __syncwarp();
     if (lane == 0) dd.time.p[(size_t)w * dd.time.stride] += h;
-    float* gws = dd.qacc_warmstart.p + (size_t)w * dd.qacc_warmstart.stride;
-    #pragma unroll 1
-    for (int i = lane; i < nv; i += 32) gws[i] = qacc[i];
+    if (lastsub) {
+      float* gws = dd.qacc_warmstart.p + (size_t)w * dd.qacc_warmstart.stride;
+      #pragma unroll 1
+      for (int i = lane; i < nv; i += 32) gws[i] = qacc[i];
+    }
   }
   // outputs that live contiguously in shared memory leave through bulk (TMA) stores
   {
@@ -1742,11 +1750,9 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     }
     fence_async_smem();
     __syncwarp();
-    if (lane == 0) {
-      if (STEP) {
-        bulk_s2g(gq, qpos, 4u * dd.qpos.stride);
-        bulk_s2g(gv, qvel, 4u * dd.qvel.stride);
-      }
+    if (lane == 0 && STEP && lastsub) {
+      bulk_s2g(gq, qpos, 4u * dd.qpos.stride);
+      bulk_s2g(gv, qvel, 4u * dd.qvel.stride);
       bulk_commit_wait();
     }
     PHASE_MARK(11);
@@ -1758,4 +1764,16 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       dd.solver_cost.p[(size_t)w * dd.solver_cost.stride] = cost;
     }
   }
+  if (lastsub) break;
+  // next sub-step: qpos/qvel/ctrl/qfrc_applied are still in shared memory; warm start from this
+  // sub-step's solution; the applied-wrench rows were overlaid by solver scratch, reload them
+  #pragma unroll 1
+  for (int i = lane; i < nv; i += 32) qacc_ws[i] = qacc[i];
+  {
+    const float* gx = dd.xfrc_applied.p + (size_t)w * dd.xfrc_applied.stride;
+    #pragma unroll 1
+    for (int i = lane; i < 6 * nb; i += 32) xfrc[i] = gx[i];
+  }
+  __syncwarp();
+  }  // sub-step loop
 }

@@ -57,6 +57,7 @@ struct b2_sim {
   int64_t launches = 0;
   int* order = nullptr;       // heavy-first dispatch order (device)
   int sorted_dispatch = 1;
+  int fused_decimation = 0;  // measured slower (r01: 979 vs 733 us/sub-step): off by default
   size_t smem_bytes = 0;
   std::map<std::string, std::vector<double>> mf;  // host copy of float model arrays
   std::map<std::string, std::vector<int>> mi;
@@ -179,7 +180,8 @@ static int add_idata(b2_sim* s, const char* name, IArr* arr, int n, int second =
   return 0;
 }
 
-static int launch(b2_sim* s, bool step, cudaStream_t st) {
+static int launch(b2_sim* s, bool step, cudaStream_t st, int nsub = 1) {
+  s->hd.nsub = nsub;
   int grid = (s->nworld + B2_WARPS_PER_CTA - 1) / B2_WARPS_PER_CTA;
   if (step && s->sorted_dispatch && s->order && s->nworld >= 512 && s->hd.world_mask == nullptr) {
     b2_order_kernel<<<1, 1024, 0, st>>>(s->hd.solver_niter.p, s->hd.solver_niter.stride, s->hd.ncon.p,
@@ -584,6 +586,7 @@ int b2_set_option(b2_sim* s, const char* key, double v) {
   else if (k == "debug_outputs") m.debug = (int)v;
   else if (k == "ls_parallel") { /* accepted for API parity; the line search here is exact */ }
   else if (k == "sorted_dispatch") s->sorted_dispatch = (int)v;
+  else if (k == "fused_decimation") s->fused_decimation = (int)v;
   else return fail("b2_set_option: unknown option '" + k + "'");
   return 0;
 }
@@ -625,6 +628,8 @@ int b2_forward_masked(b2_sim* s, const unsigned char* world_mask_dev, void* stre
 int b2_step_n(b2_sim* s, int n, void* stream) {
   if (!s) return fail("b2_step_n: null sim");
   DeviceGuard guard(s->device);
+  if (n <= 0) return 0;
+  if (s->fused_decimation) return launch(s, true, (cudaStream_t)stream, n);
   for (int i = 0; i < n; i++)
     if (launch(s, true, (cudaStream_t)stream)) return 1;
   return 0;
@@ -639,8 +644,7 @@ int b2_step_host(b2_sim* s, const float* ctrl_host, int nsubstep, float* qpos_ho
   if (ctrl_host && m.nu > 0)
     CUDA_OK(cudaMemcpy2DAsync(d.ctrl.p, sizeof(float) * d.ctrl.stride, ctrl_host, sizeof(float) * m.nu,
                               sizeof(float) * m.nu, s->nworld, cudaMemcpyHostToDevice, st));
-  for (int i = 0; i < nsubstep; i++)
-    if (launch(s, true, st)) return 1;
+  if (nsubstep > 0 && b2_step_n(s, nsubstep, stream)) return 1;
   if (qpos_host)
     CUDA_OK(cudaMemcpy2DAsync(qpos_host, sizeof(float) * m.nq, d.qpos.p, sizeof(float) * d.qpos.stride,
                               sizeof(float) * m.nq, s->nworld, cudaMemcpyDeviceToHost, st));

@@ -10,7 +10,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 mode = sys.argv[2] if len(sys.argv) > 2 else "time"
 env = VelocityFlatEnv(VelocityEnvCfg(num_envs=n), device="cuda:0")
 g = torch.Generator(device="cuda:0"); g.manual_seed(0)
-for _ in range(60):
+for _ in range(int(sys.argv[3]) if len(sys.argv) > 3 else 60):
   env.step(torch.rand((n, 29), generator=g, device="cuda:0") * 2 - 1)
 torch.cuda.synchronize()
 sim = env.sim
@@ -23,8 +23,17 @@ def timeit(label, k=20):
   st = sim.stats()
   print(f"{label:40s} {a.elapsed_time(b)/k*1e3:9.1f} us/step  ncon {st.ncon_mean:.1f} nefc {st.nefc_mean:.1f} iters {st.niter_mean:.2f} max {st.niter_max}")
   sim.data.qpos[:] = state[0]; sim.data.qvel[:] = state[1]; sim.data.qacc_warmstart[:] = state[2]
+def timeit4(label, k=10):
+  a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  state = (sim.data.qpos[:].clone(), sim.data.qvel[:].clone(), sim.data.qacc_warmstart[:].clone())
+  a.record()
+  for _ in range(k): sim.step_n(4)
+  b.record(); torch.cuda.synchronize()
+  print(f"{label:40s} {a.elapsed_time(b)/k/4*1e3:9.1f} us/sub-step")
+  sim.data.qpos[:] = state[0]; sim.data.qvel[:] = state[1]; sim.data.qacc_warmstart[:] = state[2]
 if mode == "time":
   timeit("steady state (random actions)")
+  timeit4("fused decimation step_n(4)")
   sim.set_option("iterations", 1); timeit("iterations=1")
   sim.set_option("iterations", 0); timeit("iterations=0")
   sim.set_option("iterations", 10)
