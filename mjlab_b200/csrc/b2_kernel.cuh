@@ -1293,7 +1293,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       __syncwarp();
     }
     const float scale = 1.f / (m.meaninertia * (float)max(1, nv));
-    float* gA = s + L.gA; float* gu = s + L.gu; int* glist = (int*)(s + L.glist);
+    float* gA = s + L.gA; float* gu = s + L.gu; int* glist = (int*)(s + L.glist); float* gW = s + L.gW;
     float oldcost = 0.f;
     bool first = true;
     while (true) {
@@ -1320,6 +1320,14 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         if (dim == 1) { F0 = f[0]; F1 = 0.f; F2 = 0.f; }
         else { F0 = f[0] + f[1] + f[2] + f[3]; F1 = mu * (f[0] - f[1]); F2 = mu * (f[2] - f[3]); }
         con[(CJV0 + 0) * MC + c] = F0; con[(CJV0 + 1) * MC + c] = F1; con[(CJV0 + 2) * MC + c] = F2;
+        // weights of this contact's 3x3 block W = B^T D_active B for the Hessian assembly
+        float w0 = (act & 1) ? D : 0.f, w1 = (act & 2) ? D : 0.f, w2 = (act & 4) ? D : 0.f, w3 = (act & 8) ? D : 0.f;
+        bool pyr = dim > 1;  // frictionless (condim 1) contacts contribute the normal row only
+        gW[0 * MC + c] = pyr ? w0 + w1 + w2 + w3 : w0;
+        gW[1 * MC + c] = pyr ? mu * (w0 - w1) : 0.f;
+        gW[2 * MC + c] = pyr ? mu * (w2 - w3) : 0.f;
+        gW[3 * MC + c] = pyr ? mu * mu * (w0 + w1) : 0.f;
+        gW[4 * MC + c] = pyr ? mu * mu * (w2 + w3) : 0.f;
       }
       #pragma unroll 1
       for (int i = lane; i < nv; i += 32) qfrc_c[i] = 0.f;
@@ -1409,17 +1417,10 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
           int b = a + e;
           float acc = 0.f;
           for (int c = gstart[g]; c < gstart[g + 1]; c++) {
-            float D = con[CD * MC + c], mu = con[CMU * MC + c];
-            int info = ((int*)con)[CINFO * MC + c];
-            int dim = info >> 16 & 0xf, act = info >> 20 & 0xf;
-            float w0 = (act & 1) ? D : 0.f;
+            float W00 = gW[c], W01 = gW[MC + c], W02 = gW[2 * MC + c], W11 = gW[3 * MC + c], W22 = gW[4 * MC + c];
             float sa0 = con[(CS0 + a) * MC + c], sb0 = con[(CS0 + b) * MC + c];
-            if (dim == 1) { acc += w0 * sa0 * sb0; continue; }
-            float w1 = (act & 2) ? D : 0.f, w2 = (act & 4) ? D : 0.f, w3 = (act & 8) ? D : 0.f;
             float sa1 = con[(CS0 + 6 + a) * MC + c], sb1 = con[(CS0 + 6 + b) * MC + c];
             float sa2 = con[(CS0 + 12 + a) * MC + c], sb2 = con[(CS0 + 12 + b) * MC + c];
-            float W00 = w0 + w1 + w2 + w3, W01 = mu * (w0 - w1), W02 = mu * (w2 - w3);
-            float W11 = mu * mu * (w0 + w1), W22 = mu * mu * (w2 + w3);
             acc += W00 * sa0 * sb0 + W01 * (sa0 * sb1 + sa1 * sb0) + W02 * (sa0 * sb2 + sa2 * sb0) +
                    W11 * sa1 * sb1 + W22 * sa2 * sb2;
           }

@@ -54,7 +54,7 @@ struct Layout {
   int M, H, invdiag;
   int qfrc_smooth, qacc_smooth, qacc, Ma, grad, search, Mv, qfrc_c, tmpv, actf;
   // collision / constraints (overlaid on smooth-only regions)
-  int gpose, pairlist, contacts, limits, gstart, gV, glist, gA, gu;
+  int gpose, pairlist, contacts, limits, gstart, gV, glist, gA, gu, gW;
   int sens;
   int maxcon, nlimcap, maxpair;
 };

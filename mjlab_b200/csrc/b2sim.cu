@@ -473,7 +473,8 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
   off = ubase;
   // union B: constraint / solver regions
   L.contacts = alloc(C_NFIELD * mc); L.limits = alloc(L_NFIELD * L.nlimcap); L.gstart = alloc(mc + 1);
-  L.gV = alloc(6 * mc); L.glist = alloc(64); L.gA = alloc(36); L.gu = alloc(6 * nv); L.sens = off;
+  L.gV = alloc(6 * mc); L.glist = alloc(64); L.gA = alloc(36); L.gu = alloc(6 * nv);
+  L.gW = alloc(5 * mc); L.sens = off;
   int endB = off;
   L.total = pad4(std::max(endA, endB));
   s->smem_bytes = sizeof(float) * ((size_t)L.total * B2_WARPS_PER_CTA + pad4(m.ntri));
