@@ -112,7 +112,8 @@ class VelocityFlatEnv:
 
   def _sample_timers(self, mask):
     lo, hi = self.cfg.push_interval_s
-    self.push_time_left = torch.where(mask, self._rand(self.num_envs) * (hi - lo) + lo, self.push_time_left)
+    # in-place updates everywhere: the step may be replayed from a CUDA graph (fixed addresses)
+    self.push_time_left.copy_(torch.where(mask, self._rand(self.num_envs) * (hi - lo) + lo, self.push_time_left))
 
   def _reset_where(self, mask: torch.Tensor) -> None:
     """reset_root_state_uniform + reset_joints_by_scale (envs/mdp/events.py:43-124) for masked envs."""
@@ -128,11 +129,11 @@ class VelocityFlatEnv:
     d.qpos[:] = torch.where(mk, qpos, d.qpos[:])
     d.qvel[:] = torch.where(mk, torch.zeros_like(d.qvel[:]), d.qvel[:])
     d.ctrl[:] = torch.where(mk, self.default_joint_pos.expand(n, -1), d.ctrl[:])
-    self.episode_length_buf = torch.where(mask, torch.zeros_like(self.episode_length_buf), self.episode_length_buf)
-    self.last_action = torch.where(mk, torch.zeros_like(self.last_action), self.last_action)
+    self.episode_length_buf.copy_(torch.where(mask, torch.zeros_like(self.episode_length_buf), self.episode_length_buf))
+    self.last_action.copy_(torch.where(mk, torch.zeros_like(self.last_action), self.last_action))
     # command resample (UniformVelocityCommand, velocity_env_cfg.py:66-83)
     cmd = torch.stack([self._rand(n) * 2 - 1, self._rand(n) - 0.5, self._rand(n) * 2 - 1], dim=1)
-    self.command = torch.where(mk, cmd, self.command)
+    self.command.copy_(torch.where(mk, cmd, self.command))
 
   def observations(self) -> torch.Tensor:
     d = self.sim.data
@@ -149,7 +150,33 @@ class VelocityFlatEnv:
     self.sim.forward()
     return self.observations()
 
+  def enable_cuda_graph(self) -> None:
+    """Capture one whole env step (ctrl write, 4 sub-steps, MDP glue, masked reset + forward) in a
+    CUDA graph.  The step has no host synchronisation, so replay is a single launch; inputs and
+    outputs live in static buffers (``step`` copies the action in and returns the static outputs)."""
+    dev = torch.device(self.device)
+    self._action_buf = torch.zeros(self.num_envs, self.nu, device=dev)
+    self._done_buf = torch.zeros(self.num_envs, dtype=torch.bool, device=dev)
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+      for _ in range(2):  # warm-up on the side stream (allocator, lazy inits)
+        self._step_impl(self._action_buf)
+      g = torch.cuda.CUDAGraph()
+      g.register_generator_state(self.gen)  # torch.rand(generator=self.gen) inside the capture
+      with torch.cuda.graph(g, stream=side):
+        self._graph_out = self._step_impl(self._action_buf)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    self._graph = g
+
   def step(self, action: torch.Tensor):
+    if getattr(self, "_graph", None) is not None:
+      self._action_buf.copy_(action, non_blocking=True)
+      self._graph.replay()
+      return self._graph_out
+    return self._step_impl(action)
+
+  def _step_impl(self, action: torch.Tensor):
     cfg, d = self.cfg, self.sim.data
     # JointPositionAction: target = default + scale * action (joint_actions.py:85-103)
     d.ctrl[:] = self.default_joint_pos + self.action_scale * action
@@ -169,11 +196,15 @@ class VelocityFlatEnv:
     r_lim = -((self.soft_lo - jp).clamp(min=0) + (jp - self.soft_hi).clamp(min=0)).sum(1)
     r_rate = -0.1 * ((action - self.last_action) ** 2).sum(1)
     reward = (r_lin + r_ang + r_pose + r_lim + r_rate) * self.step_dt
-    self.last_action = action
+    self.last_action.copy_(action)
     done = terminated | truncated
     # partial reset + forward (manager_based_rl_env.py:128-132), mask-based: no host sync
     self._reset_where(done)
-    self.sim.forward(env_mask=done)  # only the reset envs need new derived quantities here
+    if getattr(self, "_done_buf", None) is not None:
+      self._done_buf.copy_(done)  # fixed address for graph capture
+      self.sim.forward(env_mask=self._done_buf)
+    else:
+      self.sim.forward(env_mask=done)  # only the reset envs need new derived quantities here
     # interval event: push_by_setting_velocity (events.py:127-143)
     self.push_time_left -= self.step_dt
     push = self.push_time_left <= 0

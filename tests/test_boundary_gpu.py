@@ -184,3 +184,26 @@ def test_velocity_env_runs_and_resets():
   assert total_done > 0  # random actions make G1 fall within ~1 s; those envs were reset
   assert (env.sim.data.qpos[:, 2] > 0.2).all()
   env.close()
+
+
+def test_velocity_env_cuda_graph_matches_eager():
+  from mjlab_b200.envs import VelocityEnvCfg, VelocityFlatEnv
+
+  a = VelocityFlatEnv(VelocityEnvCfg(num_envs=32, push_interval_s=(1e9, 2e9)), device="cuda:0")
+  b = VelocityFlatEnv(VelocityEnvCfg(num_envs=32, push_interval_s=(1e9, 2e9)), device="cuda:0")
+  b.enable_cuda_graph()
+  # graph warm-up advanced b by two (zero-action) steps: bring both to the same state again
+  for f in ("qpos", "qvel", "qacc_warmstart", "ctrl"):
+    getattr(b.sim.data, f)[:] = getattr(a.sim.data, f)[:]
+  b.episode_length_buf[:] = a.episode_length_buf
+  b.last_action[:] = a.last_action
+  b.command[:] = a.command
+  g = torch.Generator(device="cuda:0")
+  g.manual_seed(5)
+  for _ in range(5):  # short horizon: nobody falls, so no (differently seeded) resets happen
+    act = (torch.rand((32, 29), generator=g, device="cuda:0") * 2 - 1) * 0.2
+    oa = a.step(act)
+    ob = b.step(act)
+    assert torch.allclose(oa[0], ob[0], atol=1e-5) and torch.allclose(oa[1], ob[1], atol=1e-6)
+  a.close()
+  b.close()
