@@ -103,6 +103,7 @@ class VelocityFlatEnv:
     self.command = torch.zeros(n, 3, **f32)
     self.command_time_left = torch.zeros(n, **f32)
     self.push_time_left = torch.zeros(n, **f32)
+    self._down = torch.tensor([0.0, 0.0, -1.0], **f32).expand(n, 3)  # gravity direction (world)
     self._sample_timers(torch.ones(n, dtype=torch.bool, device=dev))
     self.reset()
 
@@ -139,9 +140,8 @@ class VelocityFlatEnv:
     d = self.sim.data
     q = d.qpos[:, 3:7]
     lin_b = quat_rotate_inverse(q, d.qvel[:, 0:3])
-    grav = torch.tensor([0.0, 0.0, -1.0], device=self.device).expand(self.num_envs, 3)
     return torch.cat(
-      [lin_b, d.qvel[:, 3:6], quat_rotate_inverse(q, grav), d.qpos[:, 7:] - self.default_joint_pos,
+      [lin_b, d.qvel[:, 3:6], quat_rotate_inverse(q, self._down), d.qpos[:, 7:] - self.default_joint_pos,
        d.qvel[:, 6:], self.last_action, self.command], dim=1)
 
   # -- API ---------------------------------------------------------------------------------------
@@ -183,8 +183,7 @@ class VelocityFlatEnv:
     self.sim.step_n(cfg.decimation)
     self.episode_length_buf += 1
     q = d.qpos[:, 3:7]
-    grav_b = quat_rotate_inverse(
-      q, torch.tensor([0.0, 0.0, -1.0], device=self.device).expand(self.num_envs, 3))
+    grav_b = quat_rotate_inverse(q, self._down)
     terminated = torch.acos((-grav_b[:, 2]).clamp(-1.0, 1.0)) > cfg.fall_angle  # bad_orientation
     truncated = self.episode_length_buf >= self.max_episode_length              # time_out
     # rewards (velocity_env_cfg.py:183-214): tracking, posture, limits, action rate
