@@ -441,7 +441,9 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   __shared__ __align__(8) unsigned long long bars[B2_WARPS_PER_CTA];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = blockIdx.x * B2_WARPS_PER_CTA + warp;
-  const int w = (dd.world_order != nullptr && slot < dd.nworld) ? dd.world_order[slot] : slot;
+  const int w = slot < dd.world_count
+                    ? (dd.world_order != nullptr ? dd.world_order[dd.world_base + slot] : dd.world_base + slot)
+                    : dd.nworld;
   // per-CTA copy of the factorisation pair schedule (shared by the CTA's warps)
   unsigned* s_coldesc = (unsigned*)(smem_all + (size_t)B2_WARPS_PER_CTA * m.lay.total);
 #pragma unroll 1

@@ -95,6 +95,7 @@ struct DevModel {
 
 struct DevData {
   int nworld;
+  int world_base, world_count;  // this launch covers launch slots [0, world_count) -> worlds from world_base
   int nsub;  // sub-steps executed by one launch of the step kernel (decimation fused in-kernel)
   DArr qpos, qvel, ctrl, qacc_warmstart, qfrc_applied, xfrc_applied, act;
   DArr qacc, xpos, xquat, xmat, xipos, subtree_com, cvel, geom_xpos, geom_xmat, site_xpos,

@@ -57,7 +57,10 @@ struct b2_sim {
   int64_t launches = 0;
   int* order = nullptr;       // heavy-first dispatch order (device)
   int sorted_dispatch = 1;
-  int fused_decimation = 0;  // measured slower (r01: 979 vs 733 us/sub-step): off by default
+  int fused_decimation = 0;
+  int split_streams = 2;       // b2_step_n runs this many env partitions on internal streams
+  cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};  // measured slower (r01: 979 vs 733 us/sub-step): off by default
   size_t smem_bytes = 0;
   std::map<std::string, std::vector<double>> mf;  // host copy of float model arrays
   std::map<std::string, std::vector<int>> mi;
@@ -90,12 +93,13 @@ __global__ void b2_init_rows_kernel(float* dst, int stride, const float* __restr
 // Heavy-first dispatch: order worlds by the previous step's (Newton iterations, contacts),
 // descending, with a one-CTA counting sort (128 buckets).  Only scheduling changes, not results.
 __global__ void b2_order_kernel(const int* __restrict__ niter, int niter_stride, const int* __restrict__ ncon,
-                                int ncon_stride, int nworld, int* __restrict__ order) {
+                                int ncon_stride, int base_world, int count, int* __restrict__ order) {
   __shared__ int hist[128];
   __shared__ int base[128];
   for (int i = threadIdx.x; i < 128; i += blockDim.x) hist[i] = 0;
   __syncthreads();
-  for (int w = threadIdx.x; w < nworld; w += blockDim.x) {
+  for (int k = threadIdx.x; k < count; k += blockDim.x) {
+    int w = base_world + k;
     int key = min(niter[(size_t)w * niter_stride], 15) * 8 + min(ncon[(size_t)w * ncon_stride] >> 3, 7);
     atomicAdd(&hist[127 - key], 1);
   }
@@ -105,9 +109,10 @@ __global__ void b2_order_kernel(const int* __restrict__ niter, int niter_stride,
     for (int i = 0; i < 128; i++) { base[i] = acc; acc += hist[i]; }
   }
   __syncthreads();
-  for (int w = threadIdx.x; w < nworld; w += blockDim.x) {
+  for (int k = threadIdx.x; k < count; k += blockDim.x) {
+    int w = base_world + k;
     int key = min(niter[(size_t)w * niter_stride], 15) * 8 + min(ncon[(size_t)w * ncon_stride] >> 3, 7);
-    order[atomicAdd(&base[127 - key], 1)] = w;
+    order[base_world + atomicAdd(&base[127 - key], 1)] = w;
   }
 }
 
@@ -180,12 +185,15 @@ static int add_idata(b2_sim* s, const char* name, IArr* arr, int n, int second =
   return 0;
 }
 
-static int launch(b2_sim* s, bool step, cudaStream_t st, int nsub = 1) {
+static int launch(b2_sim* s, bool step, cudaStream_t st, int nsub = 1, int base = 0, int count = -1) {
+  if (count < 0) count = s->nworld;
   s->hd.nsub = nsub;
-  int grid = (s->nworld + B2_WARPS_PER_CTA - 1) / B2_WARPS_PER_CTA;
-  if (step && s->sorted_dispatch && s->order && s->nworld >= 512 && s->hd.world_mask == nullptr) {
+  s->hd.world_base = base;
+  s->hd.world_count = count;
+  int grid = (count + B2_WARPS_PER_CTA - 1) / B2_WARPS_PER_CTA;
+  if (step && s->sorted_dispatch && s->order && count >= 512 && s->hd.world_mask == nullptr) {
     b2_order_kernel<<<1, 1024, 0, st>>>(s->hd.solver_niter.p, s->hd.solver_niter.stride, s->hd.ncon.p,
-                                        s->hd.ncon.stride, s->nworld, s->order);
+                                        s->hd.ncon.stride, base, count, s->order);
     s->launches++;
     s->hd.world_order = s->order;
   } else {
@@ -495,6 +503,14 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
     if (cudaMalloc(&p, sizeof(int) * (size_t)nworld) != cudaSuccess) { b2_destroy(s); return fail("cudaMalloc(order)"); }
     s->allocs.push_back(p);
     s->order = (int*)p;
+    for (int h = 0; h < 4; h++) {
+      if (cudaStreamCreateWithFlags(&s->side[h], cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&s->ev_join[h], cudaEventDisableTiming) != cudaSuccess) {
+        b2_destroy(s);
+        return fail("b2_create: stream/event creation failed");
+      }
+    }
+    if (cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess) { b2_destroy(s); return fail("event"); }
   }
   // qpos <- qpos0 in every world, then one forward pass so all derived fields are valid
   {
@@ -517,6 +533,11 @@ int b2_destroy(b2_sim* s) {
   if (!s) return 0;
   DeviceGuard guard(s->device);
   for (void* p : s->allocs) cudaFree(p);
+  for (int h = 0; h < 4; h++) {
+    if (s->side[h]) cudaStreamDestroy(s->side[h]);
+    if (s->ev_join[h]) cudaEventDestroy(s->ev_join[h]);
+  }
+  if (s->ev_fork) cudaEventDestroy(s->ev_fork);
   delete s;
   return 0;
 }
@@ -588,6 +609,7 @@ int b2_set_option(b2_sim* s, const char* key, double v) {
   else if (k == "ls_parallel") { /* accepted for API parity; the line search here is exact */ }
   else if (k == "sorted_dispatch") s->sorted_dispatch = (int)v;
   else if (k == "fused_decimation") s->fused_decimation = (int)v;
+  else if (k == "split_streams") s->split_streams = (int)v;
   else return fail("b2_set_option: unknown option '" + k + "'");
   return 0;
 }
@@ -630,9 +652,29 @@ int b2_step_n(b2_sim* s, int n, void* stream) {
   if (!s) return fail("b2_step_n: null sim");
   DeviceGuard guard(s->device);
   if (n <= 0) return 0;
-  if (s->fused_decimation) return launch(s, true, (cudaStream_t)stream, n);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (s->fused_decimation) return launch(s, true, st, n);
+  int np = std::min(std::max(s->split_streams, 1), 4);
+  if (np > 1 && n > 1 && s->nworld >= 1024 * np) {
+    // Environments are independent, so the sub-steps of one partition need not wait for the others:
+    // fork the partitions onto internal streams (event fork/join, CUDA-graph capturable). Each
+    // partition keeps per-sub-step launches (phase-aligned warps, fresh heavy-first order) while
+    // its launch tails overlap the other partitions' work.
+    int per = (((s->nworld + np - 1) / np + B2_WARPS_PER_CTA - 1) / B2_WARPS_PER_CTA) * B2_WARPS_PER_CTA;
+    CUDA_OK(cudaEventRecord(s->ev_fork, st));
+    for (int h = 0; h < np; h++) {
+      int base = h * per, count = std::min(per, s->nworld - base);
+      if (count <= 0) break;
+      CUDA_OK(cudaStreamWaitEvent(s->side[h], s->ev_fork, 0));
+      for (int i = 0; i < n; i++)
+        if (launch(s, true, s->side[h], 1, base, count)) return 1;
+      CUDA_OK(cudaEventRecord(s->ev_join[h], s->side[h]));
+      CUDA_OK(cudaStreamWaitEvent(st, s->ev_join[h], 0));
+    }
+    return 0;
+  }
   for (int i = 0; i < n; i++)
-    if (launch(s, true, (cudaStream_t)stream)) return 1;
+    if (launch(s, true, st)) return 1;
   return 0;
 }
 

@@ -33,7 +33,9 @@ def timeit4(label, k=10):
   sim.data.qpos[:] = state[0]; sim.data.qvel[:] = state[1]; sim.data.qacc_warmstart[:] = state[2]
 if mode == "time":
   timeit("steady state (random actions)")
-  timeit4("fused decimation step_n(4)")
+  for k in (2, 3, 4, 1):
+    sim.set_option("split_streams", k); timeit4(f"step_n(4), {k} partition(s)/stream(s)")
+  sim.set_option("split_streams", 2)
   sim.set_option("iterations", 1); timeit("iterations=1")
   sim.set_option("iterations", 0); timeit("iterations=0")
   sim.set_option("iterations", 10)
