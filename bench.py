@@ -91,68 +91,83 @@ class ClockSampler:
             "samples": len(sm)}
 
 
-def cpu_reference_throughput(nthreads: int | None, budget_env_steps: int = 4, envs_per_thread: int = 24):
-  """env-steps/s of the CPU port (oracle, fp32, OpenMP over envs) on a bounded sample of the same
-  workload: keyframe + reset noise states, random actions, 4 sub-steps per env step."""
-  import numpy as np
+class CpuPort:
+  """The CPU port of the hot path (oracle, fp32, OpenMP static over envs) on a bounded sample of the
+  same workload: keyframe + reset noise, settled onto the ground, random actions, 4 sub-steps per
+  env step.  Test infrastructure used here only as the *measured baseline*, never by the product."""
 
-  from mjlab_b200.asset_zoo import g1, load_compiled
-  from oracle.oracle import Oracle
+  def __init__(self, envs_per_thread: int = 32, nthreads: int | None = None):
+    import re
 
-  m = load_compiled("g1_flat")
-  probe = Oracle(m, nworld=1, precision="f32")
-  cores = nthreads or probe.max_threads()
-  n = max(cores * envs_per_thread, 8)
-  o = Oracle(m, nworld=n, maxcon=48, precision="f32")
-  rng = np.random.default_rng(42)
-  key = m.keys["robot/init_state"]
-  qpos = np.tile(key["qpos"], (n, 1))
-  qpos[:, 0:2] += rng.uniform(-0.5, 0.5, (n, 2))
-  yaw = rng.uniform(-3.14, 3.14, n)
-  qpos[:, 3], qpos[:, 6] = np.cos(yaw / 2), np.sin(yaw / 2)
-  o.qpos[:] = qpos
-  names = [x.split("/")[-1] for x in m.names["joint"][1:]]
-  import re
-  scale = np.array([next((v for p, v in g1.ACTION_SCALE.items() if re.match(p, nm)), 0.5) for nm in names])
-  # settle onto the ground first (untimed) so the sample has the contact load of the real workload
-  o.ctrl[:] = key["ctrl"]
-  for _ in range(40):
-    o.step(cores)
-  t0 = time.perf_counter()
-  for _ in range(budget_env_steps):
-    o.ctrl[:] = key["ctrl"] + scale * rng.uniform(-1, 1, (n, len(names)))
+    import numpy as np
+
+    from mjlab_b200.asset_zoo import g1, load_compiled
+    from oracle.oracle import Oracle
+
+    self.np = np
+    m = load_compiled("g1_flat")
+    probe = Oracle(m, nworld=1, precision="f32")
+    self.cores = nthreads or probe.max_threads()
+    self.n = max(self.cores * envs_per_thread, 8)
+    self.o = Oracle(m, nworld=self.n, maxcon=48, precision="f32")
+    self.rng = np.random.default_rng(42)
+    self.key = m.keys["robot/init_state"]
+    qpos = np.tile(self.key["qpos"], (self.n, 1))
+    qpos[:, 0:2] += self.rng.uniform(-0.5, 0.5, (self.n, 2))
+    yaw = self.rng.uniform(-3.14, 3.14, self.n)
+    qpos[:, 3], qpos[:, 6] = np.cos(yaw / 2), np.sin(yaw / 2)
+    self.o.qpos[:] = qpos
+    names = [x.split("/")[-1] for x in m.names["joint"][1:]]
+    self.scale = np.array(
+      [next((v for p, v in g1.ACTION_SCALE.items() if re.match(p, nm)), 0.5) for nm in names])
+    self.o.ctrl[:] = self.key["ctrl"]
+    for _ in range(40):  # settle onto the ground (untimed) so the sample carries the contact load
+      self.o.step(self.cores)
+
+  def env_step(self) -> float:
+    t0 = time.perf_counter()
+    self.o.ctrl[:] = self.key["ctrl"] + self.scale * self.rng.uniform(-1, 1, (self.n, len(self.scale)))
     for _ in range(4):
-      o.step(cores)
-  dt = time.perf_counter() - t0
-  return {
-    "value": n * budget_env_steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
-    "sample": f"{n} envs x {budget_env_steps} env-steps (x4 sub-steps), fp32 restated CPU oracle "
-              f"(not C-MuJoCo, not mujoco_warp-CPU), OpenMP static over envs, {dt:.1f} s",
-  }
+      self.o.step(self.cores)
+    return time.perf_counter() - t0
+
+  def describe(self, env_steps: int, seconds: float) -> dict:
+    return {
+      "value": self.n * env_steps / seconds, "unit": UNIT, "cores": self.cores, "kind": "port",
+      "sample": f"{self.n} envs x {env_steps} env-steps (x4 sub-steps), fp32 restated CPU oracle "
+                f"(not C-MuJoCo, not mujoco_warp-CPU), OpenMP static over envs, {seconds:.1f} s",
+    }
+
+
+def cpu_reference_throughput(env_steps: int = 12):
+  port = CpuPort()
+  port.env_step()  # warm caches / thread pool
+  dt = sum(port.env_step() for _ in range(env_steps))
+  return port.describe(env_steps, dt)
 
 
 def run_reference(args):
   """--impl reference: the reference's physics cannot be installed here (mujoco / mujoco_warp /
-  warp wheels absent, no network; DESIGN.md), so this arm times the CPU port of the same path on
-  all host cores.  Rank 0 only."""
+  warp wheels absent, no network; DESIGN.md §7), so this arm times the CPU port of the same path on
+  all host cores; each step is one env step of a bounded sample of the workload.  Rank 0 only."""
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return
   t0 = time.perf_counter()
-  vals = []
-  for _ in range(args.warmup + args.steps):
-    vals.append(cpu_reference_throughput(None, budget_env_steps=1, envs_per_thread=8))
-  timed = vals[args.warmup:]
-  v = sum(x["value"] for x in timed) / len(timed)
-  cb = dict(timed[-1])
-  cb["value"] = v
-  n_envs = int(cb["sample"].split()[0])
+  port = CpuPort()
+  for _ in range(max(args.warmup, 1)):
+    port.env_step()
+  K = min(args.steps, 40)  # bounded: the whole arm must finish within a few minutes
+  dt = sum(port.env_step() for _ in range(K))
+  cb = port.describe(K, dt)
+  v = cb["value"]
   line = {
     "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-    "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_envs / v,
+    "steps": K, "warmup": args.warmup, "ms_per_step": 1e3 * dt / K,
     "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
     "data": "synthetic", "config": {"workload": WORKLOAD.format(envs=args.envs),
-                                     "note": "CPU port on host cores; each step a bounded sample"},
+                                     "note": "CPU port on host cores; each step = one env step of a "
+                                             f"bounded sample ({port.n} envs)"},
     "cpu_baseline": cb,
     "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     "wall_s": time.perf_counter() - t0,
@@ -339,7 +354,7 @@ def main():
     }
     if not args.no_cpu_baseline and world == 1:
       try:
-        line["cpu_baseline"] = cpu_reference_throughput(None)
+        line["cpu_baseline"] = cpu_reference_throughput()
       except Exception as e:  # the oracle is test infrastructure; never fail the bench on it
         line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
                                 "sample": f"failed: {e}"}

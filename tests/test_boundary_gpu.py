@@ -207,3 +207,24 @@ def test_velocity_env_cuda_graph_matches_eager():
     assert torch.allclose(oa[0], ob[0], atol=1e-5) and torch.allclose(oa[1], ob[1], atol=1e-6)
   a.close()
   b.close()
+
+
+def test_long_rollout_stays_finite_and_within_capacity():
+  """Soak: 300 env steps (1200 physics steps) of the benchmark workload at 1024 envs."""
+  from mjlab_b200.envs import VelocityEnvCfg, VelocityFlatEnv
+
+  env = VelocityFlatEnv(VelocityEnvCfg(num_envs=1024), device="cuda:0")
+  env.enable_cuda_graph()
+  g = torch.Generator(device="cuda:0")
+  g.manual_seed(9)
+  resets = 0
+  for k in range(300):
+    obs, r, term, trunc, _ = env.step(torch.rand((1024, 29), generator=g, device="cuda:0") * 2 - 1)
+    resets += int(term.sum())
+  d = env.sim.data
+  assert torch.isfinite(d.qpos[:]).all() and torch.isfinite(d.qvel[:]).all() and torch.isfinite(obs).all()
+  assert (d.qvel[:].abs() < 200).all()  # nothing exploded
+  st = env.sim.stats()
+  assert st.overflow_worlds == 0 and st.ncon_max <= st.ncon_cap
+  assert resets > 1024  # every env fell and was reset at least once on average
+  env.close()
