@@ -434,7 +434,7 @@ __device__ __noinline__ float rows_cost(int fc, int fl, const float* con, const 
 // The kernel
 // ==================================================================================================
 template <bool STEP>
-__global__ void __launch_bounds__(32 * B2_WARPS_PER_CTA, 6)
+__global__ void __launch_bounds__(32 * B2_WARPS_PER_CTA, B2_MIN_CTAS)
 b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevData dd) {
   using namespace b2;
   extern __shared__ __align__(16) float smem_all[];

@@ -3,7 +3,10 @@
 #include <stdint.h>
 
 #ifndef B2_WARPS_PER_CTA
-#define B2_WARPS_PER_CTA 2
+#define B2_WARPS_PER_CTA 4
+#endif
+#ifndef B2_MIN_CTAS
+#define B2_MIN_CTAS (12 / B2_WARPS_PER_CTA)  // 12 warps per SM
 #endif
 #define B2_MAX_FIELDS 96
 
