@@ -176,3 +176,41 @@ def test_fp32_oracle_tracks_fp64(g1_model):
   b.step()
   assert (a.ncon == b.ncon).all()
   assert np.abs(a.qvel - b.qvel).max() < 2e-3 * max(1.0, np.abs(a.qvel).max())
+
+
+INCLINE = """
+<mujoco><option timestep="0.002"/>
+  <worldbody><geom name="floor" type="plane" size="0 0 1" friction="{mu} 0.005 0.0001"/>
+    <body name="box" pos="0 0 0.0195"><freejoint/>
+      <geom type="box" size="0.2 0.2 0.02" mass="1" friction="{mu} 0.005 0.0001"/></body>
+  </worldbody></mujoco>
+"""
+
+
+@pytest.mark.parametrize("mu,theta_deg,slides", [(0.3, 30.0, True), (0.8, 20.0, False)])
+def test_coulomb_friction_on_incline(mu, theta_deg, slides):
+  """Known-answer check of the pyramidal friction model: a box on a plane tilted by theta (gravity is
+  tilted instead of the plane) slides with a = g (sin(theta) - mu cos(theta)) along a pyramid axis when
+  mu < tan(theta) and sticks otherwise."""
+  from mjlab_b200.compiler import Spec
+
+  sp = Spec.from_string(INCLINE.format(mu=mu))
+  th = np.radians(theta_deg)
+  sp.option.gravity = (9.81 * np.sin(th), 0.0, -9.81 * np.cos(th))
+  m = sp.compile()
+  o = Oracle(m)
+  for _ in range(300):  # 0.6 s: let the normal direction settle
+    o.step()
+  v0, t0 = o.qvel[0, 0], o.time[0, 0]
+  fn = []
+  for _ in range(500):
+    o.step()
+    nc = int(o.ncon[0, 0])
+    fn.append(o.contact_force[0, 0 : 3 * nc : 3].sum())
+  a = (o.qvel[0, 0] - v0) / (o.time[0, 0] - t0)
+  if slides:
+    assert a == pytest.approx(9.81 * (np.sin(th) - mu * np.cos(th)), rel=0.03)
+  else:
+    assert abs(o.qvel[0, 0]) < 0.02 and abs(a) < 0.02  # held by friction (soft-constraint creep only)
+  # time-averaged normal force carries the weight component perpendicular to the plane
+  assert np.mean(fn) == pytest.approx(9.81 * np.cos(th), rel=0.03)
