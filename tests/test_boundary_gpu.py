@@ -228,3 +228,33 @@ def test_long_rollout_stays_finite_and_within_capacity():
   assert st.overflow_worlds == 0 and st.ncon_max <= st.ncon_cap
   assert resets > 1024  # every env fell and was reset at least once on average
   env.close()
+
+
+def test_entity_data_over_engine_views(g1_model):
+  """EntityData (S7) on the real strided engine tensors: int32 index tensors, (N,1) env ids."""
+  from mjlab_b200.entity_data import EntityData, EntityIndexing
+  from mjlab_b200.sim import Simulation, SimulationCfg
+  from util import load_sim, make_states
+
+  n = 16
+  sim = Simulation(n, SimulationCfg(), g1_model, "cuda:0")
+  st = make_states(g1_model, n, seed=2, vel=1.0)
+  load_sim(sim, st)
+  sim.forward()
+  ed = EntityData(EntityIndexing.from_model(g1_model, "robot", "cuda:0"), sim.data, sim.model, "cuda:0", n)
+  qvel = torch.tensor(st["qvel"], dtype=torch.float32, device="cuda:0")
+  assert torch.allclose(ed.root_link_lin_vel_w, qvel[:, 0:3], atol=1e-4)   # csv_to_npz.py:279-284
+  assert torch.allclose(ed.root_link_ang_vel_b, qvel[:, 3:6], atol=1e-4)
+  assert ed.body_link_vel_w.shape == (n, 30, 6) and ed.geom_pose_w.shape == (n, 68, 7)
+  env_ids = torch.tensor([3, 7], device="cuda:0")
+  state = torch.arange(26, dtype=torch.float32, device="cuda:0").reshape(2, 13)
+  ed.write_root_state(state, env_ids)
+  assert torch.equal(sim.data.qpos[env_ids][:, :7], state[:, :7])
+  ed.write_joint_position(torch.full((2, 2), 0.1, device="cuda:0"), joint_ids=torch.tensor([1, 4], device="cuda:0"), env_ids=env_ids)
+  assert torch.allclose(sim.data.qpos[env_ids][:, [8, 11]], torch.full((2, 2), 0.1, device="cuda:0"))
+  ed.write_external_wrench(torch.ones(n, 30, 3, device="cuda:0"), None)
+  sim.step()
+  assert torch.isfinite(sim.data.qpos[:]).all()
+  ed.clear_state()
+  assert (sim.data.xfrc_applied[:] == 0).all()
+  sim.close()
