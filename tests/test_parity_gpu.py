@@ -292,3 +292,99 @@ def test_fused_decimation_matches_separate_steps(g1_model):
   assert b.launch_count() < a.launch_count()
   a.close()
   b.close()
+
+
+ARM_XML = """
+<mujoco><option timestep="0.002"/>
+  <worldbody>
+    <geom name="floor" type="plane" size="0 0 1"/>
+    <body name="base" pos="0 0 0.4">
+      <joint name="slide_z" type="slide" axis="0 0 1" range="-0.3 0.3" damping="2.0"/>
+      <geom type="sphere" size="0.05" mass="1"/>
+      <body name="link1" pos="0 0 0">
+        <joint name="h1" axis="0 1 0" range="-1.2 1.2" stiffness="3.0" armature="0.01"/>
+        <geom type="capsule" size="0.03" fromto="0 0 0 0.3 0 0" mass="0.5"/>
+        <body name="link2" pos="0.3 0 0">
+          <joint name="h2" axis="0 1 0" range="-2 2" damping="0.1"/>
+          <geom name="tip" type="capsule" size="0.03" fromto="0 0 0 0.3 0 0" mass="0.3" condim="3" friction="0.8 0.005 0.0001"/>
+        </body>
+      </body>
+    </body>
+  </worldbody>
+  <actuator><position name="a1" joint="h1" kp="20" kv="1"/><motor name="a2" joint="h2" ctrlrange="-2 2" ctrllimited="true"/></actuator>
+</mujoco>
+"""
+
+
+def test_fixed_base_slide_hinge_model_parity():
+  """Edge model: no free joint, slide + hinge joints, joint springs/damping, limits, motor + position
+  actuators, capsule tip hitting the floor; nv = 3 (tiny factorisations), nbody = 4."""
+  from mjlab_b200.compiler import Spec
+  from mjlab_b200.sim import Simulation, SimulationCfg
+  from oracle.oracle import Oracle
+
+  m = Spec.from_string(ARM_XML).compile()
+  n = 40
+  sim = Simulation(n, SimulationCfg(), m, "cuda:0")
+  sim.set_option("debug_outputs", 1)
+  o = Oracle(m, nworld=n, maxcon=int(sim.get_option("maxcon")))
+  rng = np.random.default_rng(3)
+  qpos = np.stack([rng.uniform(-0.35, 0.35, n), rng.uniform(-1.3, 1.3, n), rng.uniform(-2.1, 2.1, n)], 1)
+  qvel = rng.uniform(-2, 2, (n, 3))
+  ctrl = rng.uniform(-3, 3, (n, 2))
+  for k, v in (("qpos", qpos), ("qvel", qvel), ("ctrl", ctrl)):
+    o.field(k)[:] = v
+    getattr(sim.data, k)[:] = torch.tensor(v, dtype=torch.float32, device="cuda:0")
+  o.forward()
+  sim.forward()
+  torch.cuda.synchronize()
+  assert (T(sim.data.nefc).ravel() == o.nefc.ravel()).all() and int(o.nefc.max()) >= 2
+  assert relerr(T(sim.data.qfrc_smooth), o.qfrc_smooth).max() < 1e-5
+  assert relerr(T(sim.data.actuator_force), o.actuator_force).max() < 1e-5
+  assert relerr(T(sim.data.qacc), o.qacc).max() < 1e-3
+  for _ in range(50):
+    o.step()
+    sim.step()
+  torch.cuda.synchronize()
+  assert relerr(T(sim.data.qpos), o.qpos).max() < 2e-3
+  sim.close()
+
+
+def test_contact_capacity_overflow_is_flagged_and_deterministic(g1_model):
+  """More contacts than the per-world capacity: truncated in pair order, flagged, same set as the oracle."""
+  from mjlab_b200.sim import Simulation, SimulationCfg
+  from oracle.oracle import Oracle
+
+  n = 8
+  sim = Simulation(n, SimulationCfg(nconmax=16 * n), g1_model, "cuda:0")  # 16 contacts per world
+  cap = int(sim.get_option("maxcon"))
+  assert cap == 16
+  o = Oracle(g1_model, nworld=n, maxcon=cap)
+  st = make_states(g1_model, n, seed=13, z_range=(-0.05, -0.04), tilt=0.02)  # both feet well in the ground
+  load_oracle(o, st)
+  load_sim(sim, st)
+  o.forward()
+  sim.forward()
+  torch.cuda.synchronize()
+  assert (T(sim.data.ncon).ravel() == cap).all() and (o.ncon.ravel() == cap).all()
+  assert (T(sim.data.overflow).ravel() == 1).all() and sim.stats().overflow_worlds == n
+  assert (T(sim.data.contact_geom).reshape(n, -1) == o.contact_geom).all()
+  assert relerr(T(sim.data.qacc), o.qacc).max() < 1e-3
+  sim.close()
+
+
+@pytest.mark.parametrize("n", [1, 3, 5, 130])
+def test_world_counts_not_multiple_of_cta(g1_model, n):
+  from mjlab_b200.sim import Simulation, SimulationCfg
+  from oracle.oracle import Oracle
+
+  sim = Simulation(n, SimulationCfg(), g1_model, "cuda:0")
+  o = Oracle(g1_model, nworld=n, maxcon=int(sim.get_option("maxcon")))
+  st = make_states(g1_model, n, seed=40 + n)
+  load_oracle(o, st)
+  load_sim(sim, st)
+  o.step()
+  sim.step_n(1)
+  torch.cuda.synchronize()
+  assert relerr(T(sim.data.qvel), o.qvel).max() < 1e-3
+  sim.close()
