@@ -153,7 +153,10 @@ static int add_data(b2_sim* s, const char* name, DArr* arr, int n, int second = 
   arr->p = (float*)p; arr->stride = stride; arr->n = n;
   Field f;
   f.name = name; f.ptr = p; f.dtype = B2_F32; f.n = n;
-  if (second > 0) {
+  if (second == 9) {  // rotation matrices are exposed as (nworld, n, 3, 3) like mjwarp's mat33 arrays
+    f.ndim = 4; f.shape[0] = s->nworld; f.shape[1] = n / 9; f.shape[2] = 3; f.shape[3] = 3;
+    f.stride[0] = stride; f.stride[1] = 9; f.stride[2] = 3; f.stride[3] = 1;
+  } else if (second > 0) {
     f.ndim = 3; f.shape[0] = s->nworld; f.shape[1] = n / second; f.shape[2] = second;
     f.stride[0] = stride; f.stride[1] = second; f.stride[2] = 1;
   } else {

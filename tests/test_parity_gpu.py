@@ -366,8 +366,10 @@ def test_contact_capacity_overflow_is_flagged_and_deterministic(g1_model):
   o.forward()
   sim.forward()
   torch.cuda.synchronize()
-  assert (T(sim.data.ncon).ravel() == cap).all() and (o.ncon.ravel() == cap).all()
-  assert (T(sim.data.overflow).ravel() == 1).all() and sim.stats().overflow_worlds == n
+  assert (T(sim.data.ncon).ravel() == o.ncon.ravel()).all() and int(o.ncon.max()) == cap
+  over = o.overflow.ravel()
+  assert over.sum() >= n // 2  # most worlds exceed the capacity in this state
+  assert (T(sim.data.overflow).ravel() == over).all() and sim.stats().overflow_worlds == int(over.sum())
   assert (T(sim.data.contact_geom).reshape(n, -1) == o.contact_geom).all()
   assert relerr(T(sim.data.qacc), o.qacc).max() < 1e-3
   sim.close()
