@@ -102,6 +102,34 @@ int b2_forward_masked(b2_sim* sim, const unsigned char* world_mask_dev, void* cu
 int b2_step_host(b2_sim* sim, const float* ctrl_host, int nsubstep, float* qpos_host,
                  float* qvel_host, void* cuda_stream);
 
+/* Fused MDP glue of the velocity-tracking task around the step: what
+ * ManagerBasedRlEnv.step (manager_based_rl_env.py:106-147) does before and after the decimation loop for
+ * tasks/velocity/velocity_env_cfg.py, as two launches. All pointers are device pointers. */
+typedef struct B2VelEnvArgs {
+  const float* action;            /* [n][nu] */
+  const float* U;                 /* [n][10] uniforms in [0,1): reset xy, yaw, command(3), push(2), timer, spare */
+  const float* default_qpos;      /* [nq] */
+  const float* default_joint_pos; /* [nu] */
+  const float* action_scale;      /* [nu] */
+  const float* soft_lo;           /* [nu] */
+  const float* soft_hi;           /* [nu] */
+  const float* env_origins;       /* [n][3] */
+  int32_t* episode_length;        /* [n] in/out */
+  float* last_action;             /* [n][nu] in/out */
+  float* command;                 /* [n][3] in/out */
+  float* push_time_left;          /* [n] in/out */
+  float* obs;                     /* [n][9 + 3 nu + 3] out */
+  float* reward;                  /* [n] out */
+  unsigned char* terminated;      /* [n] out */
+  unsigned char* truncated;       /* [n] out */
+  unsigned char* done;            /* [n] out: mask for b2_forward_masked */
+  float step_dt, fall_angle, push_vel, push_lo, push_hi;
+  int32_t max_episode_length;
+} B2VelEnvArgs;
+int b2_velenv_pre(b2_sim* sim, const float* action, const float* default_joint_pos,
+                  const float* action_scale, void* cuda_stream);
+int b2_velenv_post(b2_sim* sim, const B2VelEnvArgs* args, void* cuda_stream);
+
 /* Diagnostics (synchronises `cuda_stream`). */
 int b2_stats(b2_sim* sim, void* cuda_stream, B2Stats* out);
 /* Number of kernels this library has launched for `sim` since creation. */

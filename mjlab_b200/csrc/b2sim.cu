@@ -10,6 +10,7 @@
 
 #include "../../include/b2sim.h"
 #include "b2_kernel.cuh"
+#include "b2_env.cuh"
 
 static thread_local std::string g_err;
 static int fail(const std::string& msg) {
@@ -678,6 +679,30 @@ int b2_step_n(b2_sim* s, int n, void* stream) {
   }
   for (int i = 0; i < n; i++)
     if (launch(s, true, st)) return 1;
+  return 0;
+}
+
+int b2_velenv_pre(b2_sim* s, const float* action, const float* default_joint_pos,
+                  const float* action_scale, void* stream) {
+  if (!s || !action) return fail("b2_velenv_pre: bad arguments");
+  DeviceGuard guard(s->device);
+  long long total = (long long)s->nworld * s->hm.nu;
+  if (total == 0) return 0;
+  b2_velenv_pre_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      s->hd, s->hm.nu, action, default_joint_pos, action_scale);
+  s->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int b2_velenv_post(b2_sim* s, const B2VelEnvArgs* args, void* stream) {
+  if (!s || !args) return fail("b2_velenv_post: bad arguments");
+  if (s->hm.nq != s->hm.nu + 7 || s->hm.nv != s->hm.nu + 6)
+    return fail("b2_velenv_post: expects one floating base plus nu actuated hinge joints");
+  DeviceGuard guard(s->device);
+  b2_velenv_post_kernel<<<(s->nworld + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      s->hd, s->hm.nq, s->hm.nv, s->hm.nu, *args);
+  s->launches++;
+  CUDA_OK(cudaGetLastError());
   return 0;
 }
 

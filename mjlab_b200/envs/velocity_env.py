@@ -60,7 +60,7 @@ def quat_rotate_inverse(q: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
 
 
 class VelocityFlatEnv:
-  def __init__(self, cfg: VelocityEnvCfg, device: str = "cuda:0", model=None):
+  def __init__(self, cfg: VelocityEnvCfg, device: str = "cuda:0", model=None, native_mdp: bool = True):
     self.cfg = cfg
     self.device = device
     zoo = g1 if cfg.robot == "g1" else go1
@@ -98,42 +98,75 @@ class VelocityFlatEnv:
     lo, hi = cfg.friction_range
     mu = torch.rand((n, len(foot_ids)), generator=self.gen, device=dev) * (hi - lo) + lo
     self.sim.model.geom_friction[:, foot_ids, 0] = mu
-    self.episode_length_buf = torch.zeros(n, dtype=torch.long, device=dev)
+    self.episode_length_buf = torch.zeros(n, dtype=torch.int32, device=dev)
     self.last_action = torch.zeros(n, self.nu, **f32)
     self.command = torch.zeros(n, 3, **f32)
-    self.command_time_left = torch.zeros(n, **f32)
     self.push_time_left = torch.zeros(n, **f32)
     self._down = torch.tensor([0.0, 0.0, -1.0], **f32).expand(n, 3)  # gravity direction (world)
-    self._sample_timers(torch.ones(n, dtype=torch.bool, device=dev))
+    self.native_mdp = bool(native_mdp)
+    self._graph = None
+    self._done_buf = torch.zeros(n, dtype=torch.bool, device=dev)  # fixed address (graph capture / native)
+    lo_t, hi_t = cfg.push_interval_s
+    self.push_time_left.copy_(self._rand(n) * (hi_t - lo_t) + lo_t)
+    if self.native_mdp:
+      self._init_native()
     self.reset()
 
   # -- helpers -----------------------------------------------------------------------------------
   def _rand(self, *shape):
     return torch.rand(shape, generator=self.gen, device=self.device)
 
-  def _sample_timers(self, mask):
-    lo, hi = self.cfg.push_interval_s
-    # in-place updates everywhere: the step may be replayed from a CUDA graph (fixed addresses)
-    self.push_time_left.copy_(torch.where(mask, self._rand(self.num_envs) * (hi - lo) + lo, self.push_time_left))
+  def _draw(self) -> torch.Tensor:
+    """The step's uniform numbers, one launch: columns 0-1 reset xy, 2 yaw, 3-5 command, 6-7 push, 8 timer."""
+    return self._rand(self.num_envs, 10)
 
-  def _reset_where(self, mask: torch.Tensor) -> None:
+  def _init_native(self) -> None:
+    from mjlab_b200.sim import native
+
+    n, dev = self.num_envs, self.device
+    self.nobs = 9 + 3 * self.nu + 3
+    self._obs = torch.zeros(n, self.nobs, device=dev)
+    self._reward = torch.zeros(n, device=dev)
+    self._term = torch.zeros(n, dtype=torch.bool, device=dev)
+    self._trunc = torch.zeros(n, dtype=torch.bool, device=dev)
+    self._U = torch.zeros(n, 10, device=dev)
+    self._action_in = torch.zeros(n, self.nu, device=dev)
+    self._origins = self.env_origins.contiguous()
+    a = native.B2VelEnvArgs()
+    for name, t in (
+      ("action", self._action_in), ("U", self._U), ("default_qpos", self.default_qpos),
+      ("default_joint_pos", self.default_joint_pos), ("action_scale", self.action_scale),
+      ("soft_lo", self.soft_lo), ("soft_hi", self.soft_hi), ("env_origins", self._origins),
+      ("episode_length", self.episode_length_buf), ("last_action", self.last_action),
+      ("command", self.command), ("push_time_left", self.push_time_left), ("obs", self._obs),
+      ("reward", self._reward), ("terminated", self._term), ("truncated", self._trunc), ("done", self._done_buf),
+    ):
+      assert t.is_contiguous()
+      setattr(a, name, t.data_ptr())
+    a.step_dt, a.fall_angle, a.push_vel = self.step_dt, self.cfg.fall_angle, self.cfg.push_vel
+    a.push_lo, a.push_hi = self.cfg.push_interval_s
+    a.max_episode_length = self.max_episode_length
+    self._native_args = a
+
+  def _reset_where(self, mask: torch.Tensor, U: torch.Tensor) -> None:
     """reset_root_state_uniform + reset_joints_by_scale (envs/mdp/events.py:43-124) for masked envs."""
     d = self.sim.data
     n = self.num_envs
     qpos = self.default_qpos.expand(n, -1).clone()
-    qpos[:, 0:2] += (self._rand(n, 2) - 0.5) + self.env_origins[:, 0:2]
-    yaw = (self._rand(n) * 2 - 1) * 3.14
+    qpos[:, 0:2] += (U[:, 0:2] - 0.5) + self.env_origins[:, 0:2]
+    yaw = (U[:, 2] * 2 - 1) * 3.14
     qpos[:, 3] = torch.cos(0.5 * yaw)
     qpos[:, 6] = torch.sin(0.5 * yaw)
     qpos[:, 7:] = torch.minimum(torch.maximum(qpos[:, 7:], self.soft_lo), self.soft_hi)
     mk = mask.unsqueeze(1)
+    # in-place updates everywhere: the step may be replayed from a CUDA graph (fixed addresses)
     d.qpos[:] = torch.where(mk, qpos, d.qpos[:])
     d.qvel[:] = torch.where(mk, torch.zeros_like(d.qvel[:]), d.qvel[:])
     d.ctrl[:] = torch.where(mk, self.default_joint_pos.expand(n, -1), d.ctrl[:])
     self.episode_length_buf.copy_(torch.where(mask, torch.zeros_like(self.episode_length_buf), self.episode_length_buf))
     self.last_action.copy_(torch.where(mk, torch.zeros_like(self.last_action), self.last_action))
     # command resample (UniformVelocityCommand, velocity_env_cfg.py:66-83)
-    cmd = torch.stack([self._rand(n) * 2 - 1, self._rand(n) - 0.5, self._rand(n) * 2 - 1], dim=1)
+    cmd = torch.stack([U[:, 3] * 2 - 1, U[:, 4] - 0.5, U[:, 5] * 2 - 1], dim=1)
     self.command.copy_(torch.where(mk, cmd, self.command))
 
   def observations(self) -> torch.Tensor:
@@ -146,7 +179,7 @@ class VelocityFlatEnv:
 
   # -- API ---------------------------------------------------------------------------------------
   def reset(self):
-    self._reset_where(torch.ones(self.num_envs, dtype=torch.bool, device=self.device))
+    self._reset_where(torch.ones(self.num_envs, dtype=torch.bool, device=self.device), self._draw())
     self.sim.forward()
     return self.observations()
 
@@ -156,7 +189,6 @@ class VelocityFlatEnv:
     outputs live in static buffers (``step`` copies the action in and returns the static outputs)."""
     dev = torch.device(self.device)
     self._action_buf = torch.zeros(self.num_envs, self.nu, device=dev)
-    self._done_buf = torch.zeros(self.num_envs, dtype=torch.bool, device=dev)
     side = torch.cuda.Stream(dev)
     side.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(side):
@@ -170,14 +202,37 @@ class VelocityFlatEnv:
     self._graph = g
 
   def step(self, action: torch.Tensor):
-    if getattr(self, "_graph", None) is not None:
+    if self._graph is not None:
       self._action_buf.copy_(action, non_blocking=True)
       self._graph.replay()
       return self._graph_out
     return self._step_impl(action)
 
   def _step_impl(self, action: torch.Tensor):
+    return self._step_native(action) if self.native_mdp else self._step_torch(action)
+
+  def _step_native(self, action: torch.Tensor):
+    """Two fused kernels (b2_velenv_pre / b2_velenv_post) instead of ~90 torch launches."""
+    import ctypes
+
+    from mjlab_b200.sim import native
+
+    sim = self.sim
+    self._action_in.copy_(action)
+    self._U.copy_(self._draw())
+    st = sim._stream()
+    native.check(sim._lib.b2_velenv_pre(
+      sim._h, ctypes.c_void_p(self._action_in.data_ptr()), ctypes.c_void_p(self.default_joint_pos.data_ptr()),
+      ctypes.c_void_p(self.action_scale.data_ptr()), st))
+    sim.step_n(self.cfg.decimation)
+    native.check(sim._lib.b2_velenv_post(sim._h, ctypes.byref(self._native_args), st))
+    sim.forward(env_mask=self._done_buf)
+    return self._obs, self._reward, self._term, self._trunc, {}
+
+  def _step_torch(self, action: torch.Tensor):
+    """Reference implementation of the same step in torch ops (also the oracle of the fused kernels)."""
     cfg, d = self.cfg, self.sim.data
+    U = self._draw()
     # JointPositionAction: target = default + scale * action (joint_actions.py:85-103)
     d.ctrl[:] = self.default_joint_pos + self.action_scale * action
     self.sim.step_n(cfg.decimation)
@@ -198,18 +253,16 @@ class VelocityFlatEnv:
     self.last_action.copy_(action)
     done = terminated | truncated
     # partial reset + forward (manager_based_rl_env.py:128-132), mask-based: no host sync
-    self._reset_where(done)
-    if getattr(self, "_done_buf", None) is not None:
-      self._done_buf.copy_(done)  # fixed address for graph capture
-      self.sim.forward(env_mask=self._done_buf)
-    else:
-      self.sim.forward(env_mask=done)  # only the reset envs need new derived quantities here
+    self._reset_where(done, U)
+    self._done_buf.copy_(done)
+    self.sim.forward(env_mask=self._done_buf)  # only the reset envs need new derived quantities here
     # interval event: push_by_setting_velocity (events.py:127-143)
     self.push_time_left -= self.step_dt
     push = self.push_time_left <= 0
-    pv = (self._rand(self.num_envs, 2) * 2 - 1) * cfg.push_vel
+    pv = (U[:, 6:8] * 2 - 1) * cfg.push_vel
     d.qvel[:, 0:2] = torch.where(push.unsqueeze(1), pv, d.qvel[:, 0:2])
-    self._sample_timers(push)
+    lo_t, hi_t = cfg.push_interval_s
+    self.push_time_left.copy_(torch.where(push, U[:, 8] * (hi_t - lo_t) + lo_t, self.push_time_left))
     return self.observations(), reward, terminated, truncated, {}
 
   def close(self):

@@ -44,6 +44,17 @@ class B2Stats(ctypes.Structure):
   ]
 
 
+class B2VelEnvArgs(ctypes.Structure):
+  _fields_ = (
+    [(n, ctypes.c_void_p) for n in (
+      "action", "U", "default_qpos", "default_joint_pos", "action_scale", "soft_lo", "soft_hi",
+      "env_origins", "episode_length", "last_action", "command", "push_time_left", "obs", "reward",
+      "terminated", "truncated", "done")]
+    + [(n, ctypes.c_float) for n in ("step_dt", "fall_angle", "push_vel", "push_lo", "push_hi")]
+    + [("max_episode_length", ctypes.c_int32)]
+  )
+
+
 def make_model_desc(model):
   """Pack a compiled Model into a B2ModelDesc. Returns (desc, keepalive)."""
   keep = []
@@ -104,6 +115,8 @@ def load_library() -> ctypes.CDLL:
   L.b2_forward.argtypes = [vp, vp]
   L.b2_step_n.argtypes = [vp, ci, vp]
   L.b2_forward_masked.argtypes = [vp, vp, vp]
+  L.b2_velenv_pre.argtypes = [vp, vp, vp, vp, vp]
+  L.b2_velenv_post.argtypes = [vp, ctypes.POINTER(B2VelEnvArgs), vp]
   L.b2_step_host.argtypes = [vp, vp, ci, vp, vp, vp]
   L.b2_stats.argtypes = [vp, vp, ctypes.POINTER(B2Stats)]
   L.b2_launch_count.argtypes = [vp]
