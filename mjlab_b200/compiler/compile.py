@@ -451,6 +451,14 @@ def compile_spec(spec: S.Spec) -> Model:
   A["pair_geom1"] = [p[0] for p in pairs]
   A["pair_geom2"] = [p[1] for p in pairs]
 
+  # features the engine does not implement must fail here, not silently change the physics
+  used = {g for p in pairs for g in p}
+  for g in used:
+    if A["geom_condim"][g] not in (1, 3):
+      raise NotImplementedError(
+        f"geom '{names['geom'][g]}': condim {A['geom_condim'][g]} (torsional/rolling friction) is not implemented")
+  if any(f != 0 for f in A["dof_frictionloss"]):
+    raise NotImplementedError("joint frictionloss (dry-friction constraint rows) is not implemented")
   A["qpos0"] = qpos0
   m = Model()
   shapes = {

@@ -629,7 +629,12 @@ def _parse_body(node: ET.Element, parent: Body, dfl: _Defaults, childclass, scal
       if "group" in a:
         s.group = int(a["group"])
       parent.sites.append(s)
-    # light / camera / frame-less extras: ignored (visual only)
+    elif ch.tag in ("light", "camera"):
+      pass  # visual only
+    else:
+      raise NotImplementedError(
+        f"<{ch.tag}> inside <body> is outside the MJCF subset of the hot path "
+        "(supported: body, inertial, joint, freejoint, geom, site, light, camera)")
 
 
 def _parse_mjcf(xml: str) -> Spec:
@@ -667,12 +672,19 @@ def _parse_mjcf(xml: str) -> Spec:
       o.cone = {"pyramidal": CONE_PYRAMIDAL, "elliptic": CONE_ELLIPTIC}[opt.get("cone")]
     if opt.get("solver") is not None:
       o.solver = {"PGS": SOL_PGS, "CG": SOL_CG, "Newton": SOL_NEWTON}[opt.get("solver")]
+  for ch in root:
+    if ch.tag not in ("compiler", "default", "option", "asset", "worldbody", "contact", "actuator",
+                      "keyframe", "visual", "statistic", "size"):
+      raise NotImplementedError(
+        f"<{ch.tag}> is outside the MJCF subset of the hot path (no tendons, equalities, MJCF sensors, ...)")
   wb = root.find("worldbody")
   if wb is not None:
     _parse_body(wb, spec.worldbody, dfl, None, scale)
   con = root.find("contact")
   if con is not None:
-    for ex in con.findall("exclude"):
+    for ex in con:
+      if ex.tag != "exclude":
+        raise NotImplementedError(f"<contact><{ex.tag}> (explicit contact pairs) is not supported")
       spec.excludes.append((ex.get("body1"), ex.get("body2")))
   act = root.find("actuator")
   if act is not None:

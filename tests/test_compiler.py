@@ -155,3 +155,23 @@ def test_attach_prefix_and_sensor_references(g1_model):
   assert m.names["body"][int(m.sensor_objid[i])] == "robot/left_ankle_roll_link"
   assert m.names["body"][int(m.sensor_refid[i])] == "terrain"  # un-prefixed global reference
   assert int(m.sensor_dim[i]) == 1
+
+
+def test_unsupported_features_fail_loudly():
+  base = '<mujoco><worldbody><geom name="f" type="plane" size="0 0 1"/><body name="b" pos="0 0 1"><freejoint/>{geom}{extra}</body></worldbody>{top}</mujoco>'
+  ok = base.format(geom='<geom name="g" type="sphere" size="0.1"/>', extra="", top="")
+  Spec.from_string(ok).compile()
+  with pytest.raises(NotImplementedError, match="tendon"):
+    Spec.from_string(base.format(geom='<geom type="sphere" size="0.1"/>', extra="", top="<tendon/>"))
+  with pytest.raises(NotImplementedError, match="composite"):
+    Spec.from_string(base.format(geom='<geom type="sphere" size="0.1"/>', extra="<composite/>", top=""))
+  with pytest.raises(NotImplementedError, match="condim 4"):
+    Spec.from_string(base.format(geom='<geom name="g" type="sphere" size="0.1" condim="4"/>', extra="", top="")).compile()
+  with pytest.raises(NotImplementedError, match="primitive set"):
+    Spec.from_string(base.format(geom='<geom name="g" type="cylinder" size="0.1 0.1"/>', extra="", top="")).compile()
+  with pytest.raises(NotImplementedError, match="ball"):
+    Spec.from_string('<mujoco><worldbody><body name="b"><joint type="ball"/><geom type="sphere" size="0.1"/></body></worldbody></mujoco>').compile()
+  sp = Spec.from_string(ok)
+  sp.worldbody.children[0].add_joint(name="h", type="hinge", frictionloss=0.1)
+  with pytest.raises(NotImplementedError, match="frictionloss"):
+    sp.compile()
