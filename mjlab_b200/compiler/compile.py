@@ -47,13 +47,16 @@ MODEL_ARRAYS = [
   ("actuator_gainprm", "f"), ("actuator_biasprm", "f"), ("actuator_ctrlrange", "f"),
   ("actuator_forcerange", "f"), ("actuator_gear", "f"),
   ("pair_geom1", "i"), ("pair_geom2", "i"),
+  # static (world-welded, non-plane) collision geoms found through a uniform xy grid instead of the pair table
+  ("static_geom", "i"), ("static_cell0", "i"), ("dyn_cgeom", "i"), ("grid_start", "i"), ("grid_items", "i"),
+  ("grid_params", "f"),
   ("sensor_type", "i"), ("sensor_objtype", "i"), ("sensor_objid", "i"),
   ("sensor_reftype", "i"), ("sensor_refid", "i"), ("sensor_intprm", "i"),
   ("sensor_adr", "i"), ("sensor_dim", "i"),
   ("qpos0", "f"),
 ]
 MODEL_SCALARS_I = [
-  "nq", "nv", "nu", "nbody", "njnt", "ngeom", "nsite", "nsensor", "nsensordata", "npair",
+  "nq", "nv", "nu", "nbody", "njnt", "ngeom", "nsite", "nsensor", "nsensordata", "npair", "nstatic",
   "opt_integrator", "opt_cone", "opt_solver", "opt_iterations", "opt_ls_iterations",
 ]
 MODEL_SCALARS_F = [
@@ -236,7 +239,74 @@ _SUPPORTED_PAIRS = {
   (S.GEOM_PLANE, S.GEOM_SPHERE), (S.GEOM_PLANE, S.GEOM_CAPSULE), (S.GEOM_PLANE, S.GEOM_BOX),
   (S.GEOM_SPHERE, S.GEOM_SPHERE), (S.GEOM_SPHERE, S.GEOM_CAPSULE),
   (S.GEOM_CAPSULE, S.GEOM_CAPSULE),
+  (S.GEOM_SPHERE, S.GEOM_BOX), (S.GEOM_CAPSULE, S.GEOM_BOX), (S.GEOM_BOX, S.GEOM_BOX),
 }
+STATIC_GRID_THRESHOLD = 16  # more static box/sphere/capsule geoms than this -> grid broadphase
+
+
+def _build_static_grid(A, static, weld, gbody, gtype, ngeom, cell: float = 1.0) -> None:
+  """Uniform xy grid over the static geoms' world AABBs (their bodies never move, so world pose = the
+  composition of the welded chain; only world-body children are supported, which is what the terrain is).
+  grid_params = [x0, y0, cell, nx, ny]; cell (ix, iy) -> index ix*ny + iy; grid_items lists positions in
+  ``static_geom``; static_cell0 holds each static geom's minimal cell (ix0, iy0) for duplicate rejection."""
+  A["static_geom"] = list(static)
+  A["dyn_cgeom"] = []
+  A["static_cell0"], A["grid_start"], A["grid_items"] = [], [0], []
+  A["grid_params"] = [0.0, 0.0, cell, 0.0, 0.0]
+  if not static:
+    return
+  lo, hi = [], []
+  for g in static:
+    b = gbody[g]
+    if A["body_parentid"][b] != 0:
+      raise NotImplementedError("static collision geoms must sit on a direct child of the world body")
+    Rb = quat_to_mat(np.array(A["body_quat"][b]))
+    pb = np.array(A["body_pos"][b])
+    R = Rb @ quat_to_mat(np.array(A["geom_quat"][g]))
+    c = pb + Rb @ np.array(A["geom_pos"][g])
+    sz = np.array(A["geom_size"][g], dtype=float)
+    if gtype[g] == S.GEOM_BOX:
+      ext = np.abs(R) @ sz
+    elif gtype[g] == S.GEOM_SPHERE:
+      ext = np.full(3, sz[0])
+    elif gtype[g] == S.GEOM_CAPSULE:
+      ext = np.abs(R[:, 2]) * sz[1] + sz[0]
+    else:
+      raise NotImplementedError("static grid supports box / sphere / capsule geoms")
+    lo.append(c - ext)
+    hi.append(c + ext)
+  lo, hi = np.array(lo), np.array(hi)
+  x0, y0 = lo[:, 0].min(), lo[:, 1].min()
+  # big outer borders would blow up the cell count: cap at 256 x 256 cells by growing the cell size
+  span = max(hi[:, 0].max() - x0, hi[:, 1].max() - y0)
+  cell = max(cell, span / 256.0)
+  nx = int(np.floor((hi[:, 0].max() - x0) / cell)) + 1
+  ny = int(np.floor((hi[:, 1].max() - y0) / cell)) + 1
+  cells = [[] for _ in range(nx * ny)]
+  for k in range(len(static)):
+    ix0, ix1 = int((lo[k, 0] - x0) // cell), int((hi[k, 0] - x0) // cell)
+    iy0, iy1 = int((lo[k, 1] - y0) // cell), int((hi[k, 1] - y0) // cell)
+    A["static_cell0"].append([ix0, iy0])
+    for ix in range(ix0, min(ix1, nx - 1) + 1):
+      for iy in range(iy0, min(iy1, ny - 1) + 1):
+        cells[ix * ny + iy].append(k)
+  for c in cells:
+    A["grid_items"].extend(c)
+    A["grid_start"].append(len(A["grid_items"]))
+  A["grid_params"] = [float(x0), float(y0), float(cell), float(nx), float(ny)]
+  inset = set(static)
+  # dynamic collision geoms that can touch the static set (bit masks are re-checked per candidate)
+  smask_t = 0
+  smask_a = 0
+  for g in static:
+    smask_t |= A["geom_contype"][g]
+    smask_a |= A["geom_conaffinity"][g]
+  A["dyn_cgeom"] = [g for g in range(ngeom)
+                    if g not in inset and weld[gbody[g]] != 0 and gtype[g] != S.GEOM_MESH
+                    and ((A["geom_contype"][g] & smask_a) or (A["geom_conaffinity"][g] & smask_t))]
+  for g in A["dyn_cgeom"]:
+    if gtype[g] not in (S.GEOM_SPHERE, S.GEOM_CAPSULE, S.GEOM_BOX):
+      raise NotImplementedError("only sphere / capsule / box geoms can collide with grid-static geoms")
 
 
 def compile_spec(spec: S.Spec) -> Model:
@@ -420,9 +490,19 @@ def compile_spec(spec: S.Spec) -> Model:
     excl.add((min(i1, i2), max(i1, i2)))
   gtype = A["geom_type"]
   gbody = A["geom_bodyid"]
+  # static collision geoms: on a body welded to the world, not a plane, with any collision bit
+  static = [g for g in range(ngeom)
+            if weld[gbody[g]] == 0 and gtype[g] not in (S.GEOM_PLANE, S.GEOM_MESH)
+            and (A["geom_contype"][g] or A["geom_conaffinity"][g])]
+  use_grid = len(static) > STATIC_GRID_THRESHOLD
+  in_grid = set(static) if use_grid else set()
   pairs = []
   for g1 in range(ngeom):
+    if g1 in in_grid:
+      continue
     for g2 in range(g1 + 1, ngeom):
+      if g2 in in_grid:
+        continue
       ct1, ca1 = A["geom_contype"][g1], A["geom_conaffinity"][g1]
       ct2, ca2 = A["geom_contype"][g2], A["geom_conaffinity"][g2]
       if not ((ct1 & ca2) or (ct2 & ca1)):
@@ -450,6 +530,7 @@ def compile_spec(spec: S.Spec) -> Model:
   pairs.sort(key=lambda p: (min(gbody[p[0]], gbody[p[1]]), max(gbody[p[0]], gbody[p[1]]), p))
   A["pair_geom1"] = [p[0] for p in pairs]
   A["pair_geom2"] = [p[1] for p in pairs]
+  _build_static_grid(A, static if use_grid else [], weld, gbody, gtype, ngeom)
 
   # features the engine does not implement must fail here, not silently change the physics
   used = {g for p in pairs for g in p}
@@ -467,7 +548,7 @@ def compile_spec(spec: S.Spec) -> Model:
     "geom_size": 3, "geom_pos": 3, "geom_quat": 4, "geom_friction": 3, "geom_solref": 2,
     "geom_solimp": 5, "geom_rgba": 4, "site_pos": 3, "site_quat": 4,
     "actuator_gainprm": 10, "actuator_biasprm": 10, "actuator_ctrlrange": 2,
-    "actuator_forcerange": 2, "sensor_intprm": 3, "body_invweight0": 2,
+    "actuator_forcerange": 2, "sensor_intprm": 3, "body_invweight0": 2, "static_cell0": 2,
   }
   for k, dt in MODEL_ARRAYS:
     if k in ("body_subtreemass", "body_invweight0", "dof_invweight0"):
@@ -480,7 +561,7 @@ def compile_spec(spec: S.Spec) -> Model:
   m.opt_gravity = np.array(o.gravity, dtype=float)
   scal = dict(
     nq=nq, nv=nv, nu=nu, nbody=nbody, njnt=njnt, ngeom=ngeom, nsite=nsite,
-    nsensor=len(spec.sensors), nsensordata=nsensordata, npair=len(pairs),
+    nsensor=len(spec.sensors), nsensordata=nsensordata, npair=len(pairs), nstatic=len(A["static_geom"]),
     opt_integrator=o.integrator, opt_cone=o.cone, opt_solver=o.solver,
     opt_iterations=o.iterations, opt_ls_iterations=o.ls_iterations,
     opt_timestep=o.timestep, opt_tolerance=o.tolerance, opt_ls_tolerance=o.ls_tolerance,

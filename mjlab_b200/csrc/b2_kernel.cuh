@@ -337,6 +337,139 @@ __device__ __forceinline__ int plane_sphere(RawCon& c, float margin, const float
   }
   return 1;
 }
+// ---- box primitives (own definitions, identical to oracle/b2_oracle.c: sphere_box, capsule_box, box_box) ----
+// poses are 12 floats: pos[3], row-major mat[9]
+__device__ __forceinline__ float point_box_dist2(const float* pt, const float* bx, const float* h) {
+  float d[3] = {pt[0] - bx[0], pt[1] - bx[1], pt[2] - bx[2]}, sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    float l = bx[3 + k] * d[0] + bx[6 + k] * d[1] + bx[9 + k] * d[2];
+    float e = l > h[k] ? l - h[k] : (l < -h[k] ? l + h[k] : 0.f);
+    sum += e * e;
+  }
+  return sum;
+}
+__device__ __noinline__ int sphere_box(RawCon& c, float margin, const float* sp, float r, const float* bx,
+                                       const float* h) {
+  float d[3] = {sp[0] - bx[0], sp[1] - bx[1], sp[2] - bx[2]}, l[3], cl[3], nl[3];
+  bool inside = true;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    l[k] = bx[3 + k] * d[0] + bx[6 + k] * d[1] + bx[9 + k] * d[2];
+    cl[k] = fminf(fmaxf(l[k], -h[k]), h[k]);
+    if (cl[k] != l[k]) inside = false;
+  }
+  float dist;
+  if (!inside) {
+    float e[3] = {l[0] - cl[0], l[1] - cl[1], l[2] - cl[2]};
+    float dc = sqrtf(dot3(e, e));
+    if (dc > r + margin) return 0;
+    dist = dc - r;
+    float inv = 1.f / dc;
+    nl[0] = -e[0] * inv; nl[1] = -e[1] * inv; nl[2] = -e[2] * inv;
+  } else {
+    int best = 0; float depth = h[0] - fabsf(l[0]);
+#pragma unroll
+    for (int k = 1; k < 3; k++) { float t = h[k] - fabsf(l[k]); if (t < depth) { depth = t; best = k; } }
+    nl[0] = nl[1] = nl[2] = 0.f;
+    float sg = l[best] >= 0.f ? -1.f : 1.f;
+    if (best == 0) nl[0] = sg; else if (best == 1) nl[1] = sg; else nl[2] = sg;
+    dist = -(depth + r);
+  }
+  c.dist = dist;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    float nk = bx[3 + 3 * k] * nl[0] + bx[4 + 3 * k] * nl[1] + bx[5 + 3 * k] * nl[2];
+    c.n[k] = nk; c.pos[k] = sp[k] + nk * (r + 0.5f * dist); c.yh[k] = 0.f;
+  }
+  return 1;
+}
+__device__ __forceinline__ float axis_box_dist(const float* cp, const float* ax, float t, const float* bx,
+                                               const float* h) {
+  float p[3] = {cp[0] + ax[0] * t, cp[1] + ax[1] * t, cp[2] + ax[2] * t};
+  return sqrtf(point_box_dist2(p, bx, h));
+}
+__device__ __noinline__ int capsule_box(RawCon* c, float margin, const float* cp, const float* cs, const float* bx,
+                                        const float* h) {
+  float ax[3] = {cp[3 + 2], cp[3 + 5], cp[3 + 8]}, len = cs[1], r = cs[0];
+  float lo = -len, hi = len;
+  const float gr = 0.6180339887498949f;
+  float x1 = hi - gr * (hi - lo), x2 = lo + gr * (hi - lo);
+  float f1 = axis_box_dist(cp, ax, x1, bx, h), f2 = axis_box_dist(cp, ax, x2, bx, h);
+  #pragma unroll 1
+  for (int it = 0; it < 24; it++) {
+    if (f1 <= f2) { hi = x2; x2 = x1; f2 = f1; x1 = hi - gr * (hi - lo); f1 = axis_box_dist(cp, ax, x1, bx, h); }
+    else { lo = x1; x1 = x2; f1 = f2; x2 = lo + gr * (hi - lo); f2 = axis_box_dist(cp, ax, x2, bx, h); }
+  }
+  float ts = 0.5f * (lo + hi);
+  float dmin = axis_box_dist(cp, ax, ts, bx, h);
+  if (dmin > r + margin) return 0;
+  float level = dmin + 1e-3f * r;
+  float tend[2] = {-len, len};
+  #pragma unroll 1
+  for (int e = 0; e < 2; e++) {
+    if (axis_box_dist(cp, ax, tend[e], bx, h) > level) {
+      float a = tend[e], b = ts;   // d(a) > level >= d(b)
+      #pragma unroll 1
+      for (int it = 0; it < 16; it++) {
+        float mid = 0.5f * (a + b);
+        if (axis_box_dist(cp, ax, mid, bx, h) > level) a = mid; else b = mid;
+      }
+      tend[e] = b;
+    }
+  }
+  int n = 0;
+  float p[3];
+  if (tend[1] - tend[0] < 0.02f * len) {
+    float tm = 0.5f * (tend[0] + tend[1]);
+    p[0] = cp[0] + ax[0] * tm; p[1] = cp[1] + ax[1] * tm; p[2] = cp[2] + ax[2] * tm;
+    n += sphere_box(c[n], margin, p, r, bx, h);
+  } else {
+    #pragma unroll 1
+    for (int e = 0; e < 2; e++) {
+      p[0] = cp[0] + ax[0] * tend[e]; p[1] = cp[1] + ax[1] * tend[e]; p[2] = cp[2] + ax[2] * tend[e];
+      n += sphere_box(c[n], margin, p, r, bx, h);
+    }
+  }
+  return n;
+}
+__device__ __noinline__ int box_box(RawCon* c, const float* x1, const float* h1, const float* x2, const float* h2) {
+  int n = 0;
+  #pragma unroll 1
+  for (int pass = 0; pass < 2 && n < 8; pass++) {
+    const float* xa = pass ? x2 : x1; const float* ha = pass ? h2 : h1;  // vertices of this box
+    const float* xb = pass ? x1 : x2; const float* hb = pass ? h1 : h2;  // tested against this box
+    #pragma unroll 1
+    for (int i = 0; i < 8 && n < 8; i++) {
+      float v[3] = {(i & 1) ? ha[0] : -ha[0], (i & 2) ? ha[1] : -ha[1], (i & 4) ? ha[2] : -ha[2]}, w[3], l[3];
+      bool in = true;
+#pragma unroll
+      for (int k = 0; k < 3; k++) w[k] = xa[k] + xa[3 + 3 * k] * v[0] + xa[4 + 3 * k] * v[1] + xa[5 + 3 * k] * v[2];
+      float d[3] = {w[0] - xb[0], w[1] - xb[1], w[2] - xb[2]};
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        l[k] = xb[3 + k] * d[0] + xb[6 + k] * d[1] + xb[9 + k] * d[2];
+        if (fabsf(l[k]) > hb[k]) in = false;
+      }
+      if (!in) continue;
+      int best = 0; float depth = hb[0] - fabsf(l[0]);
+#pragma unroll
+      for (int k = 1; k < 3; k++) { float t = hb[k] - fabsf(l[k]); if (t < depth) { depth = t; best = k; } }
+      float sg = (best == 0 ? l[0] : (best == 1 ? l[1] : l[2])) >= 0.f ? 1.f : -1.f;
+      float sgn = pass ? 1.f : -1.f;
+      c[n].dist = -depth;
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        float nw = sg * xb[3 + 3 * k + best];
+        c[n].n[k] = sgn * nw;
+        c[n].pos[k] = w[k] + nw * (0.5f * depth);
+        c[n].yh[k] = 0.f;
+      }
+      n++;
+    }
+  }
+  return n;
+}
 __device__ __forceinline__ void make_frame(float* f /*9: n, yhint -> n,t1,t2*/) {
   normalize3(f);
   if (sqrtf(dot3(f + 3, f + 3)) < 0.5f) {
@@ -629,7 +762,8 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     float* gxp = dd.geom_xpos.p + (size_t)w * dd.geom_xpos.stride;
     float* gxm = dd.geom_xmat.p + (size_t)w * dd.geom_xmat.stride;
     #pragma unroll 1
-    for (int g = lane; g < m.ngeom; g += 32) {
+    for (int gi = lane; gi < m.nposegeom; gi += 32) {
+      int g = m.posegeom[gi];
       int b = m.geom_bodyid[g];
       float p[3], q[4], mat[9];
       rotq(p, xquat + 4 * b, geom_pos + 3 * g);
@@ -953,9 +1087,70 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       }
       ncand += __popc(bal);
     }
+    const float* gsize = MP(geom_size);
+    if (m.nstatic > 0) {
+      // grid-static candidates: lane = dynamic geom, visiting the cells under its bounding sphere.  Two passes
+      // (count, then write at the scanned offset) keep the list in (geom, ix, iy, item) order, as the oracle's.
+      #pragma unroll 1
+      for (int q0 = 0; q0 < m.ndyn; q0 += 32) {
+        int q = q0 + lane;
+        int cnt = 0, wr = 0, tot = 0;
+        #pragma unroll 1
+        for (int pass = 0; pass < 2; pass++) {
+          if (q < m.ndyn) {
+            int g = m.dyn_cgeom[q];
+            const float* c = gpose + 12 * m.geom_cslot[g];
+            float r = rb[g], mg = gmar[g];
+            int ct = m.geom_contype[g], ca = m.geom_conaffinity[g];
+            int ix0 = max((int)floorf((c[0] - r - m.grid_x0) / m.grid_cell), 0);
+            int ix1 = min((int)floorf((c[0] + r - m.grid_x0) / m.grid_cell), m.grid_nx - 1);
+            int iy0 = max((int)floorf((c[1] - r - m.grid_y0) / m.grid_cell), 0);
+            int iy1 = min((int)floorf((c[1] + r - m.grid_y0) / m.grid_cell), m.grid_ny - 1);
+            #pragma unroll 1
+            for (int ix = ix0; ix <= ix1; ix++) {
+              #pragma unroll 1
+              for (int iy = iy0; iy <= iy1; iy++) {
+                int cell = ix * m.grid_ny + iy;
+                int it1 = m.grid_start[cell + 1];
+                #pragma unroll 1
+                for (int it = m.grid_start[cell]; it < it1; it++) {
+                  int k = m.grid_items[it];
+                  if (ix != max(m.static_cell0[2 * k], ix0) || iy != max(m.static_cell0[2 * k + 1], iy0)) continue;
+                  int sg = m.static_geom[k];
+                  if (!((ct & m.geom_conaffinity[sg]) || (m.geom_contype[sg] & ca))) continue;
+                  // conservative reach test (never rejects a pair the narrowphase would accept)
+                  const float* sp = m.static_pose + 16 * (size_t)k;
+                  float reach = r + fmaxf(mg, gmar[sg]);
+                  float d2;
+                  if (m.geom_type[sg] == G_BOX) d2 = point_box_dist2(c, sp, gsize + 3 * sg);
+                  else {
+                    float dif[3] = {c[0] - sp[0], c[1] - sp[1], c[2] - sp[2]};
+                    d2 = dot3(dif, dif); reach += sp[12];
+                  }
+                  if (d2 > reach * reach * 1.0001f + 1e-12f) continue;
+                  if (pass == 0) cnt++;
+                  else { if (wr < L.maxpair) pairlist[wr] = (int)(0x80000000u | ((unsigned)q << 20) | (unsigned)k); wr++; }
+                }
+              }
+            }
+          }
+          if (pass == 0) {
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              int t = __shfl_up_sync(FULL, incl, o);
+              if (lane >= o) incl += t;
+            }
+            wr = ncand + incl - cnt;
+            tot = __shfl_sync(FULL, incl, 31);
+          }
+        }
+        ncand += tot;
+      }
+    }
     if (ncand > L.maxpair) { ncand = L.maxpair; overflow = 1; }
     __syncwarp();
-    const float* gsize = MP(geom_size); const float* ggap = MP(geom_gap);
+    const float* ggap = MP(geom_gap);
     const float* gfri = MP(geom_friction); const float* gsolref = MP(geom_solref);
     const float* gsolimp = MP(geom_solimp); const float* gsolmix = MP(geom_solmix);
     const float* inv = MP(body_invweight0);
@@ -966,15 +1161,28 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     #pragma unroll 1
     for (int q0 = 0; q0 < ncand; q0 += 32) {
       int qi = q0 + lane;
-      RawCon rc[4];
+      RawCon rc[8];
       int n = 0, g1 = 0, g2 = 0;
       float margin = 0.f;
       if (qi < ncand) {
         int p = pairlist[qi];
-        g1 = m.pair_geom1[p]; g2 = m.pair_geom2[p];
+        const float *a, *b;
+        if (p >= 0) {
+          g1 = m.pair_geom1[p]; g2 = m.pair_geom2[p];
+          a = gpose + 12 * m.geom_cslot[g1];
+          b = gpose + 12 * m.geom_cslot[g2];
+        } else {  // grid-static candidate: (dynamic geom, static geom), ordered by (type, id)
+          int k = p & 0xfffff;
+          g1 = m.dyn_cgeom[(p >> 20) & 0x7ff]; g2 = m.static_geom[k];
+          a = gpose + 12 * m.geom_cslot[g1];
+          b = m.static_pose + 16 * (size_t)k;
+          int ta = m.geom_type[g1], tb = m.geom_type[g2];
+          if (ta > tb || (ta == tb && g1 > g2)) {
+            int tg = g1; g1 = g2; g2 = tg;
+            const float* tp = a; a = b; b = tp;
+          }
+        }
         int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
-        const float* a = gpose + 12 * m.geom_cslot[g1];
-        const float* b = gpose + 12 * m.geom_cslot[g2];
         margin = fmaxf(gmar[g1], gmar[g2]);
         const float* s1 = gsize + 3 * g1; const float* s2 = gsize + 3 * g2;
         if (t1 == G_PLANE) {
@@ -1011,6 +1219,10 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
           float x = fminf(fmaxf(dot3(ax, vec), -s2[1]), s2[1]);
           float pt[3] = {b[0] + ax[0] * x, b[1] + ax[1] * x, b[2] + ax[2] * x};
           n = sphere_sphere(rc[0], margin, a, s1[0], pt, s2[0]);
+        } else if (t2 == G_BOX) {
+          if (t1 == G_SPHERE) n = sphere_box(rc[0], margin, a, s1[0], b, s2);
+          else if (t1 == G_CAPSULE) n = capsule_box(rc, margin, a, s1, b, s2);
+          else if (t1 == G_BOX) n = box_box(rc, a, s1, b, s2);
         } else if (t1 == G_CAPSULE && t2 == G_CAPSULE) {
           float a1[3] = {a[3 + 2], a[3 + 5], a[3 + 8]}, a2[3] = {b[3 + 2], b[3 + 5], b[3 + 8]};
           float dif[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};

@@ -82,6 +82,14 @@ struct DevModel {
   const int *site_bodyid;
   const int *actuator_trnid, *actuator_ctrllimited, *actuator_forcelimited;
   const int *pair_geom1, *pair_geom2;
+  // grid-static collision set (terrain): geoms welded to the world, found through a uniform xy grid
+  int nstatic, ndyn, nposegeom, grid_nx, grid_ny;
+  float grid_x0, grid_y0, grid_cell;
+  const int *geom_contype, *geom_conaffinity;
+  const int *posegeom;     // geoms whose world pose is recomputed every step (all but the grid-static ones)
+  const int *dyn_cgeom;    // dynamic collision geoms that visit the grid
+  const int *static_geom, *static_cell0, *grid_start, *grid_items;
+  const float* static_pose;  // 16 floats per static geom: pos[3], mat[9], rbound, pad[3] (world 0's model values)
   const int *sensor_objtype, *sensor_objid, *sensor_reftype, *sensor_refid, *sensor_intprm;
   const int *sensor_adr, *sensor_dim;
   const unsigned short* tri_rowmajor;

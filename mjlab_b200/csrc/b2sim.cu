@@ -91,6 +91,19 @@ __global__ void b2_init_rows_kernel(float* dst, int stride, const float* __restr
   if (tid < (long long)nworld * n) dst[(tid / n) * stride + (tid % n)] = src[tid % n];
 }
 
+// World poses of the grid-static geoms are constant: written into every world's geom_xpos / geom_xmat once.
+__global__ void b2_static_rows_kernel(float* xpos, int xpos_stride, float* xmat, int xmat_stride,
+                                      const float* __restrict__ pose, const int* __restrict__ static_geom,
+                                      int nstatic, int nworld) {
+  long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= (long long)nworld * nstatic) return;
+  int k = (int)(tid % nstatic), g = static_geom[k];
+  size_t w = (size_t)(tid / nstatic);
+  const float* p = pose + 16 * (size_t)k;
+  for (int i = 0; i < 3; i++) xpos[w * xpos_stride + 3 * g + i] = p[i];
+  for (int i = 0; i < 9; i++) xmat[w * xmat_stride + 9 * g + i] = p[3 + i];
+}
+
 // Heavy-first dispatch: order worlds by the previous step's (Newton iterations, contacts),
 // descending, with a one-CTA counting sort (128 buckets).  Only scheduling changes, not results.
 __global__ void b2_order_kernel(const int* __restrict__ niter, int niter_stride, const int* __restrict__ ncon,
@@ -341,7 +354,79 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
     for (int g : {s->mi["pair_geom1"][p], s->mi["pair_geom2"][p]})
       if (cslot[g] < 0) { cslot[g] = (int)cgeom.size(); cgeom.push_back(g); }
   }
+  // grid-static collision set: static geoms never move, so their world poses are computed here once (in
+  // double, from world 0's model values) and shared by all worlds; only the other geoms are posed per step
+  m.nstatic = geti("nstatic");
+  m.ndyn = (int)s->mi["dyn_cgeom"].size();
+  std::vector<int> posegeom;
+  std::vector<float> static_pose((size_t)std::max(m.nstatic, 1) * 16, 0.f);
+  {
+    std::vector<char> is_static(m.ngeom, 0);
+    const std::vector<int>& sg = s->mi["static_geom"];
+    if ((int)sg.size() != m.nstatic) { delete s; return fail("b2_create: static_geom / nstatic mismatch"); }
+    if (m.nstatic >= (1 << 20) || m.ndyn >= (1 << 11)) { delete s; return fail("b2_create: static grid too large"); }
+    const std::vector<double>& bp = s->mf["body_pos"]; const std::vector<double>& bq = s->mf["body_quat"];
+    const std::vector<double>& gp = s->mf["geom_pos"]; const std::vector<double>& gq = s->mf["geom_quat"];
+    const std::vector<double>& rb = s->mf["geom_rbound"];
+    auto qmul = [](const double* a, const double* b, double* r) {
+      r[0] = a[0]*b[0] - a[1]*b[1] - a[2]*b[2] - a[3]*b[3];
+      r[1] = a[0]*b[1] + a[1]*b[0] + a[2]*b[3] - a[3]*b[2];
+      r[2] = a[0]*b[2] - a[1]*b[3] + a[2]*b[0] + a[3]*b[1];
+      r[3] = a[0]*b[3] + a[1]*b[2] - a[2]*b[1] + a[3]*b[0];
+    };
+    auto q2m = [](const double* q, double* R) {
+      R[0] = q[0]*q[0] + q[1]*q[1] - q[2]*q[2] - q[3]*q[3]; R[1] = 2*(q[1]*q[2] - q[0]*q[3]); R[2] = 2*(q[1]*q[3] + q[0]*q[2]);
+      R[3] = 2*(q[1]*q[2] + q[0]*q[3]); R[4] = q[0]*q[0] - q[1]*q[1] + q[2]*q[2] - q[3]*q[3]; R[5] = 2*(q[2]*q[3] - q[0]*q[1]);
+      R[6] = 2*(q[1]*q[3] - q[0]*q[2]); R[7] = 2*(q[2]*q[3] + q[0]*q[1]); R[8] = q[0]*q[0] - q[1]*q[1] - q[2]*q[2] + q[3]*q[3];
+    };
+    for (int k = 0; k < m.nstatic; k++) {
+      int g = sg[k], b = s->mi["geom_bodyid"][g];
+      if (g < 0 || g >= m.ngeom || parent[b] != 0 || dofnum[b] != 0) {
+        delete s;
+        return fail("b2_create: grid-static geoms must sit on a jointless child of the world body");
+      }
+      is_static[g] = 1;
+      double Rb[9], q[4], R[9];
+      q2m(&bq[4 * b], Rb);
+      qmul(&bq[4 * b], &gq[4 * g], q);
+      double nq = std::sqrt(q[0]*q[0] + q[1]*q[1] + q[2]*q[2] + q[3]*q[3]);
+      for (double& x : q) x /= nq;
+      q2m(q, R);
+      float* o = static_pose.data() + 16 * (size_t)k;
+      for (int i = 0; i < 3; i++)
+        o[i] = (float)(bp[3 * b + i] + Rb[3 * i] * gp[3 * g] + Rb[3 * i + 1] * gp[3 * g + 1] + Rb[3 * i + 2] * gp[3 * g + 2]);
+      for (int i = 0; i < 9; i++) o[3 + i] = (float)R[i];
+      o[12] = (float)rb[g];
+    }
+    for (int g = 0; g < m.ngeom; g++) if (!is_static[g]) posegeom.push_back(g);
+    m.nposegeom = (int)posegeom.size();
+    for (int g : s->mi["dyn_cgeom"]) {
+      if (g < 0 || g >= m.ngeom || is_static[g]) { delete s; return fail("b2_create: bad dyn_cgeom entry"); }
+      if (cslot[g] < 0) { cslot[g] = (int)cgeom.size(); cgeom.push_back(g); }
+    }
+    if (m.nstatic > 0) {
+      const std::vector<double>& gpar = s->mf["grid_params"];
+      if (gpar.size() != 5) { delete s; return fail("b2_create: grid_params must hold [x0, y0, cell, nx, ny]"); }
+      m.grid_x0 = (float)gpar[0]; m.grid_y0 = (float)gpar[1]; m.grid_cell = (float)gpar[2];
+      m.grid_nx = (int)gpar[3]; m.grid_ny = (int)gpar[4];
+      if ((int)s->mi["grid_start"].size() != m.grid_nx * m.grid_ny + 1 || (int)s->mi["static_cell0"].size() != 2 * m.nstatic) {
+        delete s;
+        return fail("b2_create: static grid tables have inconsistent sizes");
+      }
+    }
+  }
   m.ncg = (int)cgeom.size();
+  {  // every collision pair must have a narrowphase routine (plane/sphere/capsule/box primitives only)
+    const std::vector<int>& gt = s->mi["geom_type"];
+    auto prim = [](int t) { return t == G_SPHERE || t == G_CAPSULE || t == G_BOX; };
+    for (int p = 0; p < m.npair; p++) {
+      int t1 = gt[s->mi["pair_geom1"][p]], t2 = gt[s->mi["pair_geom2"][p]];
+      bool ok = (t1 == G_PLANE && prim(t2)) || (prim(t1) && prim(t2) && t1 <= t2);
+      if (!ok) { delete s; return fail("b2_create: collision pair with an unsupported geom type combination"); }
+    }
+    for (int g : s->mi["dyn_cgeom"]) if (!prim(gt[g])) { delete s; return fail("b2_create: unsupported dynamic geom type for the static grid"); }
+    for (int g : s->mi["static_geom"]) if (!prim(gt[g])) { delete s; return fail("b2_create: unsupported grid-static geom type"); }
+  }
   std::vector<unsigned short> trow(std::max(m.ntri, 1));
   std::vector<unsigned> tcol(std::max(m.ntri, 1));
   {
@@ -363,6 +448,9 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
   UPI(site_bodyid, "site_bodyid"); UPI(actuator_trnid, "actuator_trnid");
   UPI(actuator_ctrllimited, "actuator_ctrllimited"); UPI(actuator_forcelimited, "actuator_forcelimited");
   UPI(pair_geom1, "pair_geom1"); UPI(pair_geom2, "pair_geom2"); UPI(sensor_objtype, "sensor_objtype");
+  UPI(geom_contype, "geom_contype"); UPI(geom_conaffinity, "geom_conaffinity"); UPI(dyn_cgeom, "dyn_cgeom");
+  UPI(static_geom, "static_geom"); UPI(static_cell0, "static_cell0"); UPI(grid_start, "grid_start");
+  UPI(grid_items, "grid_items");
   UPI(sensor_objid, "sensor_objid"); UPI(sensor_reftype, "sensor_reftype");
   UPI(sensor_refid, "sensor_refid"); UPI(sensor_intprm, "sensor_intprm"); UPI(sensor_adr, "sensor_adr");
   UPI(sensor_dim, "sensor_dim");
@@ -378,6 +466,8 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
     rc |= dev_upload<float>(s, kinrec, &kr);
     m.kinrec = (const float4*)kr;
   }
+  rc |= dev_upload<int>(s, posegeom, &m.posegeom);
+  rc |= dev_upload<float>(s, static_pose, &m.static_pose);
   rc |= dev_upload<int>(s, cslot, &m.geom_cslot);
   rc |= dev_upload<int>(s, cgeom, &m.cgeom);
   rc |= dev_upload<unsigned short>(s, trow, &m.tri_rowmajor);
@@ -464,7 +554,7 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
   auto alloc = [&](int n) { int o = off; off += pad4(std::max(n, 1)); return o; };
   L.maxcon = mc;
   L.nlimcap = pad4(std::max(m.njnt, 1));
-  L.maxpair = 128;
+  L.maxpair = m.nstatic > 0 ? 256 : 128;
   L.qpos = alloc(d.qpos.stride); L.qvel = alloc(d.qvel.stride); L.ctrl = alloc(d.ctrl.stride);
   L.qacc_ws = alloc(d.qacc_warmstart.stride); L.qfrc_applied = alloc(d.qfrc_applied.stride);
   L.cdof = alloc(7 * nv); L.M = alloc(m.ntri);
@@ -521,6 +611,13 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
     long long total = (long long)nworld * nq;
     b2_init_rows_kernel<<<(unsigned)((total + 255) / 256), 256>>>(d.qpos.p, d.qpos.stride, m.qpos0.p, nq, nworld);
     s->launches++;
+    if (m.nstatic > 0) {
+      long long tot = (long long)nworld * m.nstatic;
+      b2_static_rows_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(d.geom_xpos.p, d.geom_xpos.stride, d.geom_xmat.p,
+                                                                     d.geom_xmat.stride, m.static_pose, m.static_geom,
+                                                                     m.nstatic, nworld);
+      s->launches++;
+    }
     if (launch(s, false, 0)) { b2_destroy(s); return 1; }
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {

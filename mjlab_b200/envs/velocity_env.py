@@ -230,7 +230,7 @@ class VelocityFlatEnv:
     return self._obs, self._reward, self._term, self._trunc, {}
 
   def _step_torch(self, action: torch.Tensor):
-    """Reference implementation of the same step in torch ops (also the oracle of the fused kernels)."""
+    """Reference implementation of the same step in torch ops (also the checker of the fused kernels)."""
     cfg, d = self.cfg, self.sim.data
     U = self._draw()
     # JointPositionAction: target = default + scale * action (joint_actions.py:85-103)

@@ -51,7 +51,8 @@ enum { EFC_LIMIT = 3, EFC_FRICTIONLESS = 4, EFC_PYRAMIDAL = 5 };
   X(dof_bodyid) X(dof_jntid) X(dof_parentid) X(geom_type) X(geom_bodyid) X(geom_condim)         \
   X(geom_priority) X(site_bodyid) X(actuator_trnid) X(actuator_ctrllimited)                     \
   X(actuator_forcelimited) X(pair_geom1) X(pair_geom2) X(sensor_type) X(sensor_objtype)         \
-  X(sensor_objid) X(sensor_reftype) X(sensor_refid) X(sensor_intprm) X(sensor_adr) X(sensor_dim)
+  X(sensor_objid) X(sensor_reftype) X(sensor_refid) X(sensor_intprm) X(sensor_adr) X(sensor_dim)          \
+  X(geom_contype) X(geom_conaffinity) X(static_geom) X(static_cell0) X(dyn_cgeom) X(grid_start) X(grid_items)
 
 /* float model arrays: (name, row length per element group) — all expandable per world */
 #define MODEL_REAL(X)                                                                           \
@@ -68,6 +69,7 @@ typedef struct { real* p; int n; int stride; } MF; /* stride 0 = shared by all w
 typedef struct B2Oracle {
   int nq, nv, nu, nbody, njnt, ngeom, nsite, nsensor, nsensordata, npair;
   int nworld, maxcon, njmax;
+  int nstatic, ndyn, grid_nx, grid_ny; real grid_x0, grid_y0, grid_cell;
   int integrator, cone, solver, iterations, ls_iterations;
   real timestep, tolerance, ls_tolerance, impratio, meaninertia, gravity[3];
 #define X(n) int* n;
@@ -551,6 +553,133 @@ static int capsule_capsule(RawCon* c, real margin, const real* p1, const real* m
   }
   return n;
 }
+/* sphere - box (sphere is geom1): closest point of the box to the sphere centre; a centre inside the box
+ * leaves through the nearest face.  Own restatement of the textbook test (MuJoCo's mjc_SphereBox follows the
+ * same idea; its source is not available here). */
+static int sphere_box(RawCon* c, real margin, const real* sp, real r, const real* bp, const real* bm,
+                      const real* h) {
+  real d[3] = { sp[0]-bp[0], sp[1]-bp[1], sp[2]-bp[2] }, l[3], cl[3], nl[3];
+  for (int k = 0; k < 3; k++) l[k] = bm[k]*d[0] + bm[3+k]*d[1] + bm[6+k]*d[2];   /* R^T d */
+  int inside = 1;
+  for (int k = 0; k < 3; k++) {
+    cl[k] = l[k] > h[k] ? h[k] : (l[k] < -h[k] ? -h[k] : l[k]);
+    if (cl[k] != l[k]) inside = 0;
+  }
+  real dist;
+  if (!inside) {
+    real e[3] = { l[0]-cl[0], l[1]-cl[1], l[2]-cl[2] };
+    real dc = norm3(e);
+    if (dc > r + margin) return 0;
+    dist = dc - r;
+    for (int k = 0; k < 3; k++) nl[k] = -e[k]/dc;
+  } else {
+    int best = 0; real depth = h[0] - fabs(l[0]);
+    for (int k = 1; k < 3; k++) { real t = h[k] - fabs(l[k]); if (t < depth) { depth = t; best = k; } }
+    nl[0] = nl[1] = nl[2] = 0;
+    nl[best] = l[best] >= 0 ? (real)-1 : (real)1;
+    dist = -(depth + r);
+  }
+  real n[3];
+  mulmatvec3(n, bm, nl);
+  c->dist = dist;
+  for (int k = 0; k < 3; k++) { c->frame[k] = n[k]; c->pos[k] = sp[k] + n[k]*(r + (real)0.5*dist); }
+  for (int k = 3; k < 9; k++) c->frame[k] = 0;
+  return 1;
+}
+static real point_box_dist2(const real* pt, const real* bp, const real* bm, const real* h) {
+  real d[3] = { pt[0]-bp[0], pt[1]-bp[1], pt[2]-bp[2] }, s = 0;
+  for (int k = 0; k < 3; k++) {
+    real l = bm[k]*d[0] + bm[3+k]*d[1] + bm[6+k]*d[2];
+    real e = l > h[k] ? l - h[k] : (l < -h[k] ? l + h[k] : 0);
+    s += e*e;
+  }
+  return s;
+}
+/* capsule - box (capsule is geom1).  The distance d(t) from the axis point c + t*a to the box is convex in
+ * t: golden-section search (24 steps) gives d_min; the contact set is the sub-segment [ta, tb] on which
+ * d(t) <= d_min + 1e-3*radius (its ends found by 16 bisection steps each, well conditioned because d crosses
+ * that level transversally).  A short sub-segment gives one sphere-box contact at its middle, a long one (the
+ * capsule lies along a face or across an edge) gives one at each end - chosen this way, rather than "closest
+ * point + an end cap", so that the result does not depend on which of many equidistant points a search lands
+ * on.  Own definition (MuJoCo's mjc_CapsuleBox source is not available here). */
+static real axis_box_dist(const real* cp, const real* ax, real t, const real* bp, const real* bm, const real* h) {
+  real p[3] = { cp[0] + ax[0]*t, cp[1] + ax[1]*t, cp[2] + ax[2]*t };
+  return sqrt(point_box_dist2(p, bp, bm, h));
+}
+static int capsule_box(RawCon* c, real margin, const real* cp, const real* cm, const real* cs,
+                       const real* bp, const real* bm, const real* h) {
+  real ax[3] = { cm[2], cm[5], cm[8] }, len = cs[1], r = cs[0];
+  real lo = -len, hi = len;
+  const real gr = (real)0.6180339887498949;
+  real x1 = hi - gr*(hi-lo), x2 = lo + gr*(hi-lo);
+  real f1 = axis_box_dist(cp, ax, x1, bp, bm, h), f2 = axis_box_dist(cp, ax, x2, bp, bm, h);
+  for (int it = 0; it < 24; it++) {
+    if (f1 <= f2) { hi = x2; x2 = x1; f2 = f1; x1 = hi - gr*(hi-lo); f1 = axis_box_dist(cp, ax, x1, bp, bm, h); }
+    else { lo = x1; x1 = x2; f1 = f2; x2 = lo + gr*(hi-lo); f2 = axis_box_dist(cp, ax, x2, bp, bm, h); }
+  }
+  real ts = (real)0.5*(lo+hi);
+  real dmin = axis_box_dist(cp, ax, ts, bp, bm, h);
+  if (dmin > r + margin) return 0;
+  real level = dmin + (real)1e-3*r;
+  real ta = -len, tb = len;
+  if (axis_box_dist(cp, ax, -len, bp, bm, h) > level) {
+    real a = -len, b = ts;
+    for (int it = 0; it < 16; it++) { real mid = (real)0.5*(a+b); if (axis_box_dist(cp, ax, mid, bp, bm, h) > level) a = mid; else b = mid; }
+    ta = b;
+  }
+  if (axis_box_dist(cp, ax, len, bp, bm, h) > level) {
+    real a = ts, b = len;
+    for (int it = 0; it < 16; it++) { real mid = (real)0.5*(a+b); if (axis_box_dist(cp, ax, mid, bp, bm, h) > level) b = mid; else a = mid; }
+    tb = a;
+  }
+  int n = 0; real p[3];
+  if (tb - ta < (real)0.02*len) {
+    real tm = (real)0.5*(ta+tb);
+    for (int k = 0; k < 3; k++) p[k] = cp[k] + ax[k]*tm;
+    n += sphere_box(c + n, margin, p, r, bp, bm, h);
+  } else {
+    for (int k = 0; k < 3; k++) p[k] = cp[k] + ax[k]*ta;
+    n += sphere_box(c + n, margin, p, r, bp, bm, h);
+    for (int k = 0; k < 3; k++) p[k] = cp[k] + ax[k]*tb;
+    n += sphere_box(c + n, margin, p, r, bp, bm, h);
+  }
+  return n;
+}
+/* box - box, vertex-face contacts only (no edge-edge): vertices of A inside B, then vertices of B inside A,
+ * each leaving through the nearest face of the other box; at most 8 contacts in that order. */
+static int box_box(RawCon* c, real margin, const real* p1, const real* m1, const real* h1,
+                   const real* p2, const real* m2, const real* h2) {
+  int n = 0; (void)margin;
+  for (int pass = 0; pass < 2 && n < 8; pass++) {
+    const real *pa = pass ? p2 : p1, *ma = pass ? m2 : m1, *ha = pass ? h2 : h1;   /* vertices of this box */
+    const real *pb = pass ? p1 : p2, *mb = pass ? m1 : m2, *hb = pass ? h1 : h2;   /* tested against this box */
+    for (int i = 0; i < 8 && n < 8; i++) {
+      real v[3] = { (i&1 ? ha[0] : -ha[0]), (i&2 ? ha[1] : -ha[1]), (i&4 ? ha[2] : -ha[2]) }, w[3], l[3];
+      mulmatvec3(w, ma, v);
+      for (int k = 0; k < 3; k++) w[k] += pa[k];
+      real d[3] = { w[0]-pb[0], w[1]-pb[1], w[2]-pb[2] };
+      int in = 1;
+      for (int k = 0; k < 3; k++) { l[k] = mb[k]*d[0] + mb[3+k]*d[1] + mb[6+k]*d[2]; if (fabs(l[k]) > hb[k]) in = 0; }
+      if (!in) continue;
+      int best = 0; real depth = hb[0] - fabs(l[0]);
+      for (int k = 1; k < 3; k++) { real t = hb[k] - fabs(l[k]); if (t < depth) { depth = t; best = k; } }
+      real nl[3] = {0,0,0}, nw[3];
+      nl[best] = l[best] >= 0 ? (real)1 : (real)-1;      /* outward face normal of the containing box */
+      mulmatvec3(nw, mb, nl);
+      /* normal must point from geom1 (A) to geom2 (B): a vertex of A leaves B along +nw -> n = -nw;
+         a vertex of B leaves A along +nw -> n = +nw */
+      real sgn = pass ? (real)1 : (real)-1;
+      c[n].dist = -depth;
+      for (int k = 0; k < 3; k++) {
+        c[n].frame[k] = sgn*nw[k];
+        c[n].pos[k] = w[k] + nw[k]*((real)0.5*depth);
+      }
+      for (int k = 3; k < 9; k++) c[n].frame[k] = 0;
+      n++;
+    }
+  }
+  return n;
+}
 /* mju_makeFrame */
 static void make_frame(real* f) {
   normalize3(f);
@@ -564,21 +693,86 @@ static void make_frame(real* f) {
   cross3(f+6, f, f+3);
 }
 
+/* contact parameters (mj_contactParam) + append to the contact list; returns the new count */
+static int emit_contacts(W* d, int ncon, int g1, int g2, RawCon* rc, int n, real margin) {
+  const B2Oracle* o = d->o; int w = d->w;
+  const real* ggap = M_(o, geom_gap, w);
+  const real* gfri = M_(o, geom_friction, w); const real* gsolref = M_(o, geom_solref, w);
+  const real* gsolimp = M_(o, geom_solimp, w); const real* gsolmix = M_(o, geom_solmix, w);
+  int condim; real fri[3], solref[2], solimp[5];
+  int pr1 = o->geom_priority[g1], pr2 = o->geom_priority[g2];
+  if (pr1 != pr2) {
+    int g = pr1 > pr2 ? g1 : g2;
+    condim = o->geom_condim[g];
+    for (int k = 0; k < 3; k++) fri[k] = gfri[3*g+k];
+    for (int k = 0; k < 2; k++) solref[k] = gsolref[2*g+k];
+    for (int k = 0; k < 5; k++) solimp[k] = gsolimp[5*g+k];
+  } else {
+    condim = o->geom_condim[g1] > o->geom_condim[g2] ? o->geom_condim[g1] : o->geom_condim[g2];
+    for (int k = 0; k < 3; k++) fri[k] = gfri[3*g1+k] > gfri[3*g2+k] ? gfri[3*g1+k] : gfri[3*g2+k];
+    real mix, s1 = gsolmix[g1], s2 = gsolmix[g2];
+    if (s1 >= MINVAL && s2 >= MINVAL) mix = s1/(s1+s2);
+    else if (s1 < MINVAL && s2 < MINVAL) mix = (real)0.5;
+    else mix = s1 < MINVAL ? 0 : 1;
+    if (gsolref[2*g1] > 0 && gsolref[2*g2] > 0)
+      for (int k = 0; k < 2; k++) solref[k] = mix*gsolref[2*g1+k] + (1-mix)*gsolref[2*g2+k];
+    else
+      for (int k = 0; k < 2; k++) solref[k] = gsolref[2*g1+k] < gsolref[2*g2+k] ? gsolref[2*g1+k] : gsolref[2*g2+k];
+    for (int k = 0; k < 5; k++) solimp[k] = mix*gsolimp[5*g1+k] + (1-mix)*gsolimp[5*g2+k];
+  }
+  real gap = ggap[g1] > ggap[g2] ? ggap[g1] : ggap[g2];
+  for (int i = 0; i < n; i++) {
+    if (ncon >= o->maxcon) { *d->overflow = 1; break; }
+    make_frame(rc[i].frame);
+    d->contact_dist[ncon] = rc[i].dist;
+    memcpy(d->contact_pos + 3*ncon, rc[i].pos, sizeof(real)*3);
+    memcpy(d->contact_frame + 9*ncon, rc[i].frame, sizeof(real)*9);
+    real* f5 = d->contact_friction + 5*ncon;
+    f5[0] = f5[1] = fri[0]; f5[2] = fri[1]; f5[3] = f5[4] = fri[2];
+    for (int k = 0; k < 5; k++) if (f5[k] < MINMU) f5[k] = MINMU;
+    memcpy(d->contact_solref + 2*ncon, solref, sizeof(real)*2);
+    memcpy(d->contact_solimp + 5*ncon, solimp, sizeof(real)*5);
+    d->contact_includemargin[ncon] = margin - gap;
+    d->contact_dim[ncon] = condim;
+    d->contact_geom[2*ncon] = g1; d->contact_geom[2*ncon+1] = g2;
+    d->contact_efc[ncon] = -1;
+    ncon++;
+  }
+  return ncon;
+}
+
+/* narrowphase dispatch; geoms are ordered so that type(g1) <= type(g2) */
+static int narrowphase(const W* d, RawCon* rc, int g1, int g2, real margin) {
+  const B2Oracle* o = d->o; int w = d->w;
+  const real* gsize = M_(o, geom_size, w);
+  int t1 = o->geom_type[g1], t2 = o->geom_type[g2];
+  const real *p1 = d->geom_xpos + 3*g1, *p2 = d->geom_xpos + 3*g2;
+  const real *m1 = d->geom_xmat + 9*g1, *m2 = d->geom_xmat + 9*g2;
+  const real *s1 = gsize + 3*g1, *s2 = gsize + 3*g2;
+  if (t1 == G_PLANE && t2 == G_SPHERE) return plane_sphere(rc, margin, p1, m1, p2, s2[0]);
+  if (t1 == G_PLANE && t2 == G_CAPSULE) return plane_capsule(rc, margin, p1, m1, p2, m2, s2);
+  if (t1 == G_PLANE && t2 == G_BOX) return plane_box(rc, margin, p1, m1, p2, m2, s2);
+  if (t1 == G_SPHERE && t2 == G_SPHERE) return sphere_sphere(rc, margin, p1, s1[0], p2, s2[0]);
+  if (t1 == G_SPHERE && t2 == G_CAPSULE) return sphere_capsule(rc, margin, p1, s1[0], p2, m2, s2);
+  if (t1 == G_CAPSULE && t2 == G_CAPSULE) return capsule_capsule(rc, margin, p1, m1, s1, p2, m2, s2);
+  if (t1 == G_SPHERE && t2 == G_BOX) return sphere_box(rc, margin, p1, s1[0], p2, m2, s2);
+  if (t1 == G_CAPSULE && t2 == G_BOX) return capsule_box(rc, margin, p1, m1, s1, p2, m2, s2);
+  if (t1 == G_BOX && t2 == G_BOX) return box_box(rc, margin, p1, m1, s1, p2, m2, s2);
+  return 0;
+}
+
 static void collision(W* d) {
   const B2Oracle* o = d->o; int w = d->w;
   int ncon = 0; *d->overflow = 0;
-  const real* rb = M_(o, geom_rbound, w); const real* gsize = M_(o, geom_size, w);
-  const real* gmargin = M_(o, geom_margin, w); const real* ggap = M_(o, geom_gap, w);
-  const real* gfri = M_(o, geom_friction, w); const real* gsolref = M_(o, geom_solref, w);
-  const real* gsolimp = M_(o, geom_solimp, w); const real* gsolmix = M_(o, geom_solmix, w);
+  const real* rb = M_(o, geom_rbound, w);
+  const real* gmargin = M_(o, geom_margin, w);
+  /* (1) static pair table with a bounding-sphere filter (mj_collideSphere / plane variant) */
   for (int p = 0; p < o->npair; p++) {
     int g1 = o->pair_geom1[p], g2 = o->pair_geom2[p];
-    int t1 = o->geom_type[g1], t2 = o->geom_type[g2];
     real margin = gmargin[g1] > gmargin[g2] ? gmargin[g1] : gmargin[g2];
     const real *p1 = d->geom_xpos + 3*g1, *p2 = d->geom_xpos + 3*g2;
-    const real *m1 = d->geom_xmat + 9*g1, *m2 = d->geom_xmat + 9*g2;
-    /* bounding-sphere filter (mj_collideSphere / plane variant) */
-    if (t1 == G_PLANE) {
+    const real *m1 = d->geom_xmat + 9*g1;
+    if (o->geom_type[g1] == G_PLANE) {
       real n[3] = { m1[2], m1[5], m1[8] }, dif[3] = { p2[0]-p1[0], p2[1]-p1[1], p2[2]-p1[2] };
       if (dot3(dif, n) > margin + rb[g2]) continue;
     } else {
@@ -586,54 +780,36 @@ static void collision(W* d) {
       real bound = margin + rb[g1] + rb[g2];
       if (dot3(dif, dif) > bound*bound) continue;
     }
-    RawCon rc[4]; int n = 0;
-    if (t1 == G_PLANE && t2 == G_SPHERE) n = plane_sphere(rc, margin, p1, m1, p2, gsize[3*g2]);
-    else if (t1 == G_PLANE && t2 == G_CAPSULE) n = plane_capsule(rc, margin, p1, m1, p2, m2, gsize + 3*g2);
-    else if (t1 == G_PLANE && t2 == G_BOX) n = plane_box(rc, margin, p1, m1, p2, m2, gsize + 3*g2);
-    else if (t1 == G_SPHERE && t2 == G_SPHERE) n = sphere_sphere(rc, margin, p1, gsize[3*g1], p2, gsize[3*g2]);
-    else if (t1 == G_SPHERE && t2 == G_CAPSULE) n = sphere_capsule(rc, margin, p1, gsize[3*g1], p2, m2, gsize + 3*g2);
-    else if (t1 == G_CAPSULE && t2 == G_CAPSULE) n = capsule_capsule(rc, margin, p1, m1, gsize + 3*g1, p2, m2, gsize + 3*g2);
-    if (!n) continue;
-    /* mj_contactParam */
-    int condim; real fri[3], solref[2], solimp[5];
-    int pr1 = o->geom_priority[g1], pr2 = o->geom_priority[g2];
-    if (pr1 != pr2) {
-      int g = pr1 > pr2 ? g1 : g2;
-      condim = o->geom_condim[g];
-      for (int k = 0; k < 3; k++) fri[k] = gfri[3*g+k];
-      for (int k = 0; k < 2; k++) solref[k] = gsolref[2*g+k];
-      for (int k = 0; k < 5; k++) solimp[k] = gsolimp[5*g+k];
-    } else {
-      condim = o->geom_condim[g1] > o->geom_condim[g2] ? o->geom_condim[g1] : o->geom_condim[g2];
-      for (int k = 0; k < 3; k++) fri[k] = gfri[3*g1+k] > gfri[3*g2+k] ? gfri[3*g1+k] : gfri[3*g2+k];
-      real mix, s1 = gsolmix[g1], s2 = gsolmix[g2];
-      if (s1 >= MINVAL && s2 >= MINVAL) mix = s1/(s1+s2);
-      else if (s1 < MINVAL && s2 < MINVAL) mix = (real)0.5;
-      else mix = s1 < MINVAL ? 0 : 1;
-      if (gsolref[2*g1] > 0 && gsolref[2*g2] > 0)
-        for (int k = 0; k < 2; k++) solref[k] = mix*gsolref[2*g1+k] + (1-mix)*gsolref[2*g2+k];
-      else
-        for (int k = 0; k < 2; k++) solref[k] = gsolref[2*g1+k] < gsolref[2*g2+k] ? gsolref[2*g1+k] : gsolref[2*g2+k];
-      for (int k = 0; k < 5; k++) solimp[k] = mix*gsolimp[5*g1+k] + (1-mix)*gsolimp[5*g2+k];
-    }
-    real gap = ggap[g1] > ggap[g2] ? ggap[g1] : ggap[g2];
-    for (int i = 0; i < n; i++) {
-      if (ncon >= o->maxcon) { *d->overflow = 1; break; }
-      make_frame(rc[i].frame);
-      d->contact_dist[ncon] = rc[i].dist;
-      memcpy(d->contact_pos + 3*ncon, rc[i].pos, sizeof(real)*3);
-      memcpy(d->contact_frame + 9*ncon, rc[i].frame, sizeof(real)*9);
-      real* f5 = d->contact_friction + 5*ncon;
-      f5[0] = f5[1] = fri[0]; f5[2] = fri[1]; f5[3] = f5[4] = fri[2];
-      for (int k = 0; k < 5; k++) if (f5[k] < MINMU) f5[k] = MINMU;
-      memcpy(d->contact_solref + 2*ncon, solref, sizeof(real)*2);
-      memcpy(d->contact_solimp + 5*ncon, solimp, sizeof(real)*5);
-      d->contact_includemargin[ncon] = margin - gap;
-      d->contact_dim[ncon] = condim;
-      d->contact_geom[2*ncon] = g1; d->contact_geom[2*ncon+1] = g2;
-      d->contact_efc[ncon] = -1;
-      ncon++;
-    }
+    RawCon rc[8];
+    int n = narrowphase(d, rc, g1, g2, margin);
+    if (n) ncon = emit_contacts(d, ncon, g1, g2, rc, n, margin);
+  }
+  /* (2) grid-static geoms: every dynamic collision geom (id order) visits the cells under its bounding
+   * sphere (ix outer, iy inner); a static geom spanning several cells is taken only in the first common cell */
+  for (int q = 0; q < o->ndyn; q++) {
+    int g = o->dyn_cgeom[q];
+    const real* c = d->geom_xpos + 3*g;
+    int ix0 = (int)floor((c[0] - rb[g] - o->grid_x0) / o->grid_cell), ix1 = (int)floor((c[0] + rb[g] - o->grid_x0) / o->grid_cell);
+    int iy0 = (int)floor((c[1] - rb[g] - o->grid_y0) / o->grid_cell), iy1 = (int)floor((c[1] + rb[g] - o->grid_y0) / o->grid_cell);
+    if (ix0 < 0) ix0 = 0; if (iy0 < 0) iy0 = 0;
+    if (ix1 >= o->grid_nx) ix1 = o->grid_nx - 1; if (iy1 >= o->grid_ny) iy1 = o->grid_ny - 1;
+    for (int ix = ix0; ix <= ix1; ix++)
+      for (int iy = iy0; iy <= iy1; iy++) {
+        int cell = ix*o->grid_ny + iy;
+        for (int it = o->grid_start[cell]; it < o->grid_start[cell+1]; it++) {
+          int k = o->grid_items[it], sg = o->static_geom[k];
+          int fx = o->static_cell0[2*k] > ix0 ? o->static_cell0[2*k] : ix0;
+          int fy = o->static_cell0[2*k+1] > iy0 ? o->static_cell0[2*k+1] : iy0;
+          if (ix != fx || iy != fy) continue;   /* duplicate: handled in an earlier cell */
+          if (!((o->geom_contype[g] & o->geom_conaffinity[sg]) || (o->geom_contype[sg] & o->geom_conaffinity[g]))) continue;
+          real margin = gmargin[g] > gmargin[sg] ? gmargin[g] : gmargin[sg];
+          int g1 = g, g2 = sg;
+          if (o->geom_type[g1] > o->geom_type[g2] || (o->geom_type[g1] == o->geom_type[g2] && g1 > g2)) { g1 = sg; g2 = g; }
+          RawCon rc[8];
+          int n = narrowphase(d, rc, g1, g2, margin);
+          if (n) ncon = emit_contacts(d, ncon, g1, g2, rc, n, margin);
+        }
+      }
   }
   *d->ncon = ncon;
 }
@@ -1182,6 +1358,12 @@ B2Oracle* b2o_create(const B2ModelDesc* desc, int nworld, int maxcon, int njmax)
   o->meaninertia = (real)get_f(desc, "stat_meaninertia");
   for (int k = 0; k < 3; k++) o->gravity[k] = (real)desc->gravity[k];
   o->nworld = nworld; o->maxcon = maxcon > 0 ? maxcon : 64; o->njmax = njmax > 0 ? njmax : 300;
+  o->nstatic = get_i(desc, "nstatic"); o->ndyn = (int)find_arr(desc, "dyn_cgeom")->n;
+  {
+    const B2Array* gp = find_arr(desc, "grid_params");
+    const double* v = (const double*)gp->data;
+    o->grid_x0 = (real)v[0]; o->grid_y0 = (real)v[1]; o->grid_cell = (real)v[2]; o->grid_nx = (int)v[3]; o->grid_ny = (int)v[4];
+  }
 #define X(n) o->n = dup_i(desc, #n);
   MODEL_INT(X)
 #undef X

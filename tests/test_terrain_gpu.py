@@ -1,0 +1,196 @@
+"""Box primitives + grid-static broadphase: CUDA path vs CPU oracle (BASELINE config E groundwork).
+
+Tolerances: as test_parity_gpu.py near the origin; the full rough terrain spans +-100 m, where fp32 world
+coordinates resolve 8e-6 m, so contact distances are compared to 5e-5 m and accelerations to 5e-3 there."""
+
+import numpy as np
+import pytest
+import torch
+
+from util import load_oracle, load_sim, make_states, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def T(x):
+  return x[:].detach().cpu().numpy()
+
+
+def _contacts(ncon, geom, dist, w):
+  k = int(ncon[w])
+  return sorted(zip(map(tuple, np.asarray(geom[w]).reshape(-1, 2)[:k].tolist()), np.asarray(dist[w])[:k].tolist()))
+
+
+def _check_contacts(sim, o, n, dist_tol):
+  d = sim.data
+  nc = o.ncon.ravel()
+  assert (T(d.ncon).ravel() == nc).all()
+  assert (T(d.overflow).ravel() == o.overflow.ravel()).all()
+  cg, og = T(d.contact_geom), o.contact_geom.reshape(n, -1, 2)
+  cd = T(d.contact_dist)
+  same_order = 0
+  for w in range(n):
+    a, b = _contacts(nc, cg, cd, w), _contacts(nc, og, o.contact_dist, w)
+    assert [x[0] for x in a] == [x[0] for x in b]
+    if nc[w]:
+      assert np.abs(np.array([x[1] for x in a]) - np.array([x[1] for x in b])).max() < dist_tol
+    same_order += int((cg[w, : nc[w]] == og[w, : nc[w]]).all())
+  return same_order
+
+
+ON_BOX = """
+<mujoco><option timestep="0.002"/>
+  <worldbody>
+    <body name="table" pos="0 0 0.25"><geom name="top" type="box" size="0.5 0.5 0.25"/></body>
+    <body name="obj" pos="0 0 {z}" quat="{quat}"><freejoint/>{geom}</body>
+  </worldbody></mujoco>
+"""
+
+
+@pytest.mark.parametrize("geom,z,quat", [
+  ('<geom type="sphere" size="0.1" mass="2"/>', 0.599, "1 0 0 0"),
+  ('<geom type="capsule" size="0.05 0.2" mass="2"/>', 0.549, "0.7071068 0 0.7071068 0"),
+  ('<geom type="capsule" size="0.05 0.2" mass="2"/>', 0.70, "0.9238795 0 0.3826834 0"),
+  ('<geom type="box" size="0.1 0.15 0.05" mass="2"/>', 0.549, "1 0 0 0"),
+  ('<geom type="box" size="0.1 0.15 0.05" mass="2"/>', 0.62, "0.9238795 0.3826834 0 0"),
+])
+def test_box_primitives_step_parity(geom, z, quat):
+  from mjlab_b200.compiler import Spec
+  from mjlab_b200.sim import Simulation, SimulationCfg
+  from oracle.oracle import Oracle
+
+  m = Spec.from_string(ON_BOX.format(geom=geom, z=z, quat=quat)).compile()
+  n = 8
+  pos_tol = 2e-3 if "capsule" in geom else 1e-4
+  sim = Simulation(n, SimulationCfg(), m, "cuda:0")
+  sim.set_option("debug_outputs", 1)
+  o = Oracle(m, nworld=n, maxcon=int(sim.get_option("maxcon")))
+  rng = np.random.default_rng(2)
+  qpos = np.tile(m.qpos0, (n, 1))
+  qpos[:, 0:2] += rng.uniform(-0.45, 0.45, (n, 2))  # some objects hang over the table edge
+  qpos[:, 2] += rng.uniform(-0.01, 0.005, n)
+  st = dict(qpos=qpos, qvel=rng.uniform(-0.2, 0.2, (n, 6)))
+  load_oracle(o, st)
+  load_sim(sim, st)
+  for it in range(40):
+    o.forward()
+    sim.forward()
+    torch.cuda.synchronize()
+    _check_contacts(sim, o, n, 1e-5)
+    e = relerr(T(sim.data.qacc), o.qacc, floor=10.0)
+    assert e.max() < 2e-3, (it, e.max())
+    k = o.ncon.ravel()
+    for w in range(n):
+      if k[w]:
+        # the ends of a capsule-box contact segment are level-set crossings (d_min + 1e-3 r) of a nearly flat
+        # distance profile: their position along the axis is only defined to ~1e-3 m in fp32
+        assert np.abs(T(sim.data.contact_pos)[w, : k[w]].ravel() - o.contact_pos[w, : 3 * k[w]]).max() < pos_tol
+        assert np.abs(T(sim.data.contact_frame)[w, : k[w]].ravel() - o.contact_frame[w, : 9 * k[w]]).max() < 1e-4
+    o.step()
+    sim.step()
+    # resynchronise so that the comparison stays a one-step comparison
+    sim.data.qpos[:] = torch.as_tensor(o.qpos, dtype=torch.float32, device="cuda:0")
+    sim.data.qvel[:] = torch.as_tensor(o.qvel, dtype=torch.float32, device="cuda:0")
+    sim.data.qacc_warmstart[:] = torch.as_tensor(o.qacc_warmstart, dtype=torch.float32, device="cuda:0")
+  assert int(o.ncon.max()) >= 1
+  sim.close()
+
+
+def _terrain_states(m, n, seed, spread):
+  rng = np.random.default_rng(seed)
+  st = make_states(m, n, seed=seed, z_range=(-0.05, 0.04))
+  org = np.asarray(m.arrays["terrain_origins"]).reshape(-1, 3)
+  spot = org[rng.integers(0, len(org), n)]
+  st["qpos"][:, 0:2] = spot[:, 0:2] + rng.uniform(-spread, spread, (n, 2))
+  st["qpos"][:, 2] += spot[:, 2]
+  return st
+
+
+@pytest.mark.parametrize("name,n,spread,dist_tol,acc_tol", [
+  ("go1_stairs_small", 128, 1.4, 1e-5, 2e-3),
+  ("go1_rough", 192, 2.2, 5e-5, 5e-3),
+])
+def test_go1_terrain_forward_parity(name, n, spread, dist_tol, acc_tol):
+  from mjlab_b200.asset_zoo import load_compiled
+  from mjlab_b200.sim import Simulation, SimulationCfg
+  from oracle.oracle import Oracle
+
+  m = load_compiled(name)
+  sim = Simulation(n, SimulationCfg(), m, "cuda:0")
+  sim.set_option("debug_outputs", 1)
+  o = Oracle(m, nworld=n, maxcon=int(sim.get_option("maxcon")))
+  st = _terrain_states(m, n, 21, spread)
+  load_oracle(o, st)
+  load_sim(sim, st)
+  o.forward()
+  sim.forward()
+  torch.cuda.synchronize()
+  d = sim.data
+  same = _check_contacts(sim, o, n, dist_tol)
+  assert same >= n - 2, same  # order can differ only when a bounding sphere touches a cell border in fp32
+  nc = o.ncon.ravel()
+  assert nc.max() >= 8 and (nc > 0).mean() > 0.5
+  for f in ["xpos", "xmat", "geom_xpos", "geom_xmat", "site_xpos", "subtree_com", "qfrc_bias", "qM"]:
+    e = relerr(T(getattr(d, f)).reshape(n, -1), o.field(f).reshape(n, -1)).max()
+    assert e < 1e-5, (f, e)
+  e = relerr(T(d.qacc), o.qacc, floor=10.0)
+  assert e.max() < acc_tol and np.median(e) < acc_tol / 10, (e.max(), np.median(e))
+  assert np.abs(T(d.sensordata) - o.sensordata).max() < 1e-3  # foot contact counts
+  sim.close()
+
+
+def test_go1_stairs_rollout_matches_oracle():
+  """40 control-free steps from rest on the stairs: state drift stays at fp32 level."""
+  from mjlab_b200.asset_zoo import load_compiled
+  from mjlab_b200.sim import Simulation, SimulationCfg
+  from oracle.oracle import Oracle
+
+  m = load_compiled("go1_stairs_small")
+  n = 32
+  sim = Simulation(n, SimulationCfg(), m, "cuda:0")
+  o = Oracle(m, nworld=n, maxcon=int(sim.get_option("maxcon")))
+  st = _terrain_states(m, n, 4, 1.0)
+  st["qvel"] *= 0.1
+  st["qpos"][:, 2] += 0.03
+  load_oracle(o, st)
+  load_sim(sim, st)
+  for _ in range(40):
+    o.step()
+  sim.step_n(40)
+  torch.cuda.synchronize()
+  q, qo = T(sim.data.qpos), o.qpos
+  assert np.isfinite(q).all()
+  err = np.abs(q - qo).max(axis=1)
+  assert np.median(err) < 2e-3 and (err < 2e-2).mean() > 0.85, (np.median(err), err.max())
+  sim.close()
+
+
+def test_go1_rough_full_size_properties():
+  """BASELINE config E shape (4096 envs on the 10 x 20 terrain): spawn on the curriculum origins, stand under
+  PD control; nothing explodes, the robots stay on their patches, feet report contact."""
+  from mjlab_b200.asset_zoo import load_compiled
+  from mjlab_b200.sim import Simulation, SimulationCfg
+  from mjlab_b200.terrains import env_origins_curriculum
+
+  m = load_compiled("go1_rough")
+  n = 4096
+  sim = Simulation(n, SimulationCfg(), m, "cuda:0")
+  org, level, kind = env_origins_curriculum(n, np.asarray(m.arrays["terrain_origins"]), max_init_level=9)
+  key = m.keys["robot/init_state"]
+  qpos = np.tile(key["qpos"], (n, 1))
+  qpos[:, 0:3] += org
+  qpos[:, 2] += 0.02
+  sim.data.qpos[:] = torch.as_tensor(qpos, dtype=torch.float32, device="cuda:0")
+  sim.data.qvel[:] = 0
+  sim.data.ctrl[:] = torch.as_tensor(np.tile(key["ctrl"], (n, 1)), dtype=torch.float32, device="cuda:0")
+  sim.step_n(200)
+  torch.cuda.synchronize()
+  q = T(sim.data.qpos)
+  assert np.isfinite(q).all()
+  h = q[:, 2] - org[:, 2]
+  assert (np.abs(q[:, 0:2] - org[:, 0:2]).max(axis=1) < 0.5).mean() > 0.99
+  assert ((h > 0.15) & (h < 0.40)).mean() > 0.99, (h.min(), h.max())
+  assert (T(sim.data.sensordata) > 0).mean() > 0.95
+  assert int(T(sim.data.overflow).sum()) == 0
+  assert np.abs(T(sim.data.qvel)).max() < 1.0
+  sim.close()

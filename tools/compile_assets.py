@@ -13,8 +13,13 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from mjlab_b200.asset_zoo import COMPILED_DIR, g1, go1, reference_xml  # noqa: E402
 from mjlab_b200.asset_zoo.scene import compile_scene  # noqa: E402
 from mjlab_b200.sim.sim import MujocoCfg  # noqa: E402
+from mjlab_b200.terrains import RoughTerrainCfg  # noqa: E402
 
 TASK = MujocoCfg(timestep=0.005, iterations=10, ls_iterations=20)
+_STAIRS = dict(step_height_range=(0.05, 0.15), step_width=0.3, platform_width=2.0, border_width=0.5)
+# small stairs scene for parity tests (2 x 4 patches) and the full BASELINE config E terrain (10 x 20)
+SMALL_STAIRS = RoughTerrainCfg(num_rows=2, num_cols=4, border_width=2.0, seed=3, sub_terrains=(
+  ("flat", 0.25, {}), ("pyramid_stairs", 0.5, _STAIRS), ("pyramid_stairs_inv", 0.25, _STAIRS)))
 
 
 def main():
@@ -24,13 +29,15 @@ def main():
     "g1_flat": compile_scene(g1.robot_cfg(g1_xml, g1.velocity_sensors()), TASK),
     "g1_tracking_flat": compile_scene(g1.robot_cfg(g1_xml, g1.tracking_sensors()), TASK),
     "go1_flat": compile_scene(go1.robot_cfg(go1_xml, go1.velocity_sensors()), TASK),
+    "go1_stairs_small": compile_scene(go1.robot_cfg(go1_xml, go1.velocity_sensors()), TASK, SMALL_STAIRS),
+    "go1_rough": compile_scene(go1.robot_cfg(go1_xml, go1.velocity_sensors()), TASK, RoughTerrainCfg()),
   }
   for name, m in out.items():
     m.save(COMPILED_DIR / f"{name}.npz")
     print(
       f"{name}: nq={int(m.nq)} nv={int(m.nv)} nu={int(m.nu)} nbody={int(m.nbody)} "
       f"njnt={int(m.njnt)} ngeom={int(m.ngeom)} nsite={int(m.nsite)} npair={int(m.npair)} "
-      f"nsensordata={int(m.nsensordata)} meaninertia={float(m.stat_meaninertia):.5f}"
+      f"nstatic={int(m.nstatic)} nsensordata={int(m.nsensordata)} meaninertia={float(m.stat_meaninertia):.5f}"
     )
 
 
