@@ -69,6 +69,7 @@ __global__ void b2_velenv_post_kernel(DevData dd, int nq, int nv, int nu, B2VelE
     for (int i = 0; i < nq; i++) qpos[i] = A.default_qpos[i];
     qpos[0] += (U[0] - 0.5f) + A.env_origins[3 * (size_t)w];
     qpos[1] += (U[1] - 0.5f) + A.env_origins[3 * (size_t)w + 1];
+    qpos[2] += A.env_origins[3 * (size_t)w + 2];  // terrain spawn height (0 on the flat scene)
     float yaw = (U[2] * 2.f - 1.f) * 3.14f;
     qpos[3] = cosf(0.5f * yaw); qpos[4] = A.default_qpos[4]; qpos[5] = A.default_qpos[5]; qpos[6] = sinf(0.5f * yaw);
     for (int a = 0; a < nu; a++) {

@@ -384,52 +384,69 @@ __device__ __noinline__ int sphere_box(RawCon& c, float margin, const float* sp,
   }
   return 1;
 }
-__device__ __forceinline__ float axis_box_dist(const float* cp, const float* ax, float t, const float* bx,
-                                               const float* h) {
-  float p[3] = {cp[0] + ax[0] * t, cp[1] + ax[1] * t, cp[2] + ax[2] * t};
-  return sqrtf(point_box_dist2(p, bx, h));
+// distance from the axis point l0 + t*al (box frame) to the box
+__device__ __forceinline__ float axis_box_dist(const float* l0, const float* al, float t, const float* h) {
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    float l = l0[k] + al[k] * t;
+    float e = l > h[k] ? l - h[k] : (l < -h[k] ? l + h[k] : 0.f);
+    sum += e * e;
+  }
+  return sqrtf(sum);
 }
 __device__ __noinline__ int capsule_box(RawCon* c, float margin, const float* cp, const float* cs, const float* bx,
                                         const float* h) {
   float ax[3] = {cp[3 + 2], cp[3 + 5], cp[3 + 8]}, len = cs[1], r = cs[0];
+  float d0[3] = {cp[0] - bx[0], cp[1] - bx[1], cp[2] - bx[2]}, l0[3], al[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    l0[k] = bx[3 + k] * d0[0] + bx[6 + k] * d0[1] + bx[9 + k] * d0[2];
+    al[k] = bx[3 + k] * ax[0] + bx[6 + k] * ax[1] + bx[9 + k] * ax[2];
+  }
   float lo = -len, hi = len;
   const float gr = 0.6180339887498949f;
   float x1 = hi - gr * (hi - lo), x2 = lo + gr * (hi - lo);
-  float f1 = axis_box_dist(cp, ax, x1, bx, h), f2 = axis_box_dist(cp, ax, x2, bx, h);
+  float f1 = axis_box_dist(l0, al, x1, h), f2 = axis_box_dist(l0, al, x2, h);
   #pragma unroll 1
   for (int it = 0; it < 24; it++) {
-    if (f1 <= f2) { hi = x2; x2 = x1; f2 = f1; x1 = hi - gr * (hi - lo); f1 = axis_box_dist(cp, ax, x1, bx, h); }
-    else { lo = x1; x1 = x2; f1 = f2; x2 = lo + gr * (hi - lo); f2 = axis_box_dist(cp, ax, x2, bx, h); }
+    if (f1 <= f2) { hi = x2; x2 = x1; f2 = f1; x1 = hi - gr * (hi - lo); f1 = axis_box_dist(l0, al, x1, h); }
+    else { lo = x1; x1 = x2; f1 = f2; x2 = lo + gr * (hi - lo); f2 = axis_box_dist(l0, al, x2, h); }
   }
   float ts = 0.5f * (lo + hi);
-  float dmin = axis_box_dist(cp, ax, ts, bx, h);
+  float dmin = axis_box_dist(l0, al, ts, h);
   if (dmin > r + margin) return 0;
   float level = dmin + 1e-3f * r;
-  float tend[2] = {-len, len};
-  #pragma unroll 1
-  for (int e = 0; e < 2; e++) {
-    if (axis_box_dist(cp, ax, tend[e], bx, h) > level) {
-      float a = tend[e], b = ts;   // d(a) > level >= d(b)
-      #pragma unroll 1
-      for (int it = 0; it < 16; it++) {
-        float mid = 0.5f * (a + b);
-        if (axis_box_dist(cp, ax, mid, bx, h) > level) a = mid; else b = mid;
-      }
-      tend[e] = b;
+  float ta = -len, tb = len;
+  if (axis_box_dist(l0, al, -len, h) > level) {
+    float a = -len, b = ts;   // d(a) > level >= d(b)
+    #pragma unroll 1
+    for (int it = 0; it < 16; it++) {
+      float mid = 0.5f * (a + b);
+      if (axis_box_dist(l0, al, mid, h) > level) a = mid; else b = mid;
     }
+    ta = b;
+  }
+  if (axis_box_dist(l0, al, len, h) > level) {
+    float a = ts, b = len;    // d(a) <= level < d(b)
+    #pragma unroll 1
+    for (int it = 0; it < 16; it++) {
+      float mid = 0.5f * (a + b);
+      if (axis_box_dist(l0, al, mid, h) > level) b = mid; else a = mid;
+    }
+    tb = a;
   }
   int n = 0;
   float p[3];
-  if (tend[1] - tend[0] < 0.02f * len) {
-    float tm = 0.5f * (tend[0] + tend[1]);
+  if (tb - ta < 0.02f * len) {
+    float tm = 0.5f * (ta + tb);
     p[0] = cp[0] + ax[0] * tm; p[1] = cp[1] + ax[1] * tm; p[2] = cp[2] + ax[2] * tm;
     n += sphere_box(c[n], margin, p, r, bx, h);
   } else {
-    #pragma unroll 1
-    for (int e = 0; e < 2; e++) {
-      p[0] = cp[0] + ax[0] * tend[e]; p[1] = cp[1] + ax[1] * tend[e]; p[2] = cp[2] + ax[2] * tend[e];
-      n += sphere_box(c[n], margin, p, r, bx, h);
-    }
+    p[0] = cp[0] + ax[0] * ta; p[1] = cp[1] + ax[1] * ta; p[2] = cp[2] + ax[2] * ta;
+    n += sphere_box(c[n], margin, p, r, bx, h);
+    p[0] = cp[0] + ax[0] * tb; p[1] = cp[1] + ax[1] * tb; p[2] = cp[2] + ax[2] * tb;
+    n += sphere_box(c[n], margin, p, r, bx, h);
   }
   return n;
 }
@@ -817,10 +834,24 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     }
   }
   __syncwarp();
-  // Internal reference point c0 = com of the whole world (subtree_com[0]); all cdof / cinert / cvel
-  // are expressed about c0 (MuJoCo uses subtree_com[root]; results are identical, cvel is converted
-  // on output).
-  const float c0[3] = {scom[0], scom[1], scom[2]};
+  // Internal reference point c0 = com of the moving bodies (those with a dof in their chain; static terrain
+  // mass would drag the point far from the robot and cost fp32 digits); all cdof / cinert / cvel are expressed
+  // about c0 (MuJoCo uses subtree_com[root]; results are identical, cvel is converted on output).
+  float c0[3];
+  {
+    const float* mass = MP(body_mass);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, am = 0.f;
+    #pragma unroll 1
+    for (int b = lane; b < nb; b += 32) {
+      if (m.body_dofmask[b] != 0ull) {
+        float mb = mass[b];
+        a0 += mb * xipos[3 * b]; a1 += mb * xipos[3 * b + 1]; a2 += mb * xipos[3 * b + 2]; am += mb;
+      }
+    }
+    a0 = wsum(a0); a1 = wsum(a1); a2 = wsum(a2); am = wsum(am);
+    if (am < MINVAL) { c0[0] = scom[0]; c0[1] = scom[1]; c0[2] = scom[2]; }
+    else { float inv = 1.f / am; c0[0] = a0 * inv; c0[1] = a1 * inv; c0[2] = a2 * inv; }
+  }
   {  // body poses / coms leave now (coalesced); their shared-memory home is recycled after phase 4
     float* g0 = dd.xpos.p + (size_t)w * dd.xpos.stride;
     float* g1 = dd.xquat.p + (size_t)w * dd.xquat.stride;

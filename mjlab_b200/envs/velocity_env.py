@@ -32,6 +32,8 @@ class VelocityEnvCfg:
   push_vel: float = 0.5                    # flat_env_cfg.py:20-24
   friction_range: tuple = (0.3, 1.2)       # :162-172
   env_spacing: float = 2.5
+  terrain: str = "flat"                    # "flat" (plane) | "rough" (box terrain, velocity_env_cfg.py:274-278)
+  max_init_terrain_level: int = 5          # terrain_importer.py:203-223
   seed: int = 42
   sim: SimulationCfg = field(
     default_factory=lambda: SimulationCfg(
@@ -64,7 +66,7 @@ class VelocityFlatEnv:
     self.cfg = cfg
     self.device = device
     zoo = g1 if cfg.robot == "g1" else go1
-    self.model = model if model is not None else load_compiled(f"{cfg.robot}_flat")
+    self.model = model if model is not None else load_compiled(f"{cfg.robot}_{cfg.terrain}")
     m = self.model
     self.num_envs = cfg.num_envs
     self.sim = Simulation(cfg.num_envs, cfg.sim, m, device)
@@ -90,6 +92,14 @@ class VelocityFlatEnv:
     self.env_origins = torch.stack(
       [(idx // cols - (cols - 1) / 2) * cfg.env_spacing, (idx % cols - (cols - 1) / 2) * cfg.env_spacing,
        torch.zeros(n, device=dev)], dim=1).float()
+    if "terrain_origins" in m.arrays:
+      # box terrain: spawn on the sub-terrain origins, level <= max_init_terrain_level, types round-robin
+      # (terrain_importer.py:203-223); the curriculum's level updates are host-side MDP and not restated
+      from mjlab_b200.terrains import env_origins_curriculum
+
+      org, self.terrain_levels, self.terrain_types = env_origins_curriculum(
+        n, m.arrays["terrain_origins"], cfg.max_init_terrain_level, cfg.seed)
+      self.env_origins = torch.tensor(org, dtype=torch.float32, device=dev)
     # startup domain randomisation: foot friction (events.py:212-265 'abs' on geom_friction[:, feet, 0])
     self.sim.expand_model_fields(["geom_friction"])
     foot_ids = torch.tensor(
@@ -154,6 +164,7 @@ class VelocityFlatEnv:
     n = self.num_envs
     qpos = self.default_qpos.expand(n, -1).clone()
     qpos[:, 0:2] += (U[:, 0:2] - 0.5) + self.env_origins[:, 0:2]
+    qpos[:, 2] += self.env_origins[:, 2]
     yaw = (U[:, 2] * 2 - 1) * 3.14
     qpos[:, 3] = torch.cos(0.5 * yaw)
     qpos[:, 6] = torch.sin(0.5 * yaw)

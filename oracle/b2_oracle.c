@@ -602,34 +602,46 @@ static real point_box_dist2(const real* pt, const real* bp, const real* bm, cons
  * capsule lies along a face or across an edge) gives one at each end - chosen this way, rather than "closest
  * point + an end cap", so that the result does not depend on which of many equidistant points a search lands
  * on.  Own definition (MuJoCo's mjc_CapsuleBox source is not available here). */
-static real axis_box_dist(const real* cp, const real* ax, real t, const real* bp, const real* bm, const real* h) {
-  real p[3] = { cp[0] + ax[0]*t, cp[1] + ax[1]*t, cp[2] + ax[2]*t };
-  return sqrt(point_box_dist2(p, bp, bm, h));
+/* distance from the axis point l0 + t*al (box frame) to the box; working in the box frame keeps the
+ * profile's shape free of the rounding of large world coordinates */
+static real axis_box_dist(const real* l0, const real* al, real t, const real* h) {
+  real s = 0;
+  for (int k = 0; k < 3; k++) {
+    real l = l0[k] + al[k]*t;
+    real e = l > h[k] ? l - h[k] : (l < -h[k] ? l + h[k] : 0);
+    s += e*e;
+  }
+  return sqrt(s);
 }
 static int capsule_box(RawCon* c, real margin, const real* cp, const real* cm, const real* cs,
                        const real* bp, const real* bm, const real* h) {
   real ax[3] = { cm[2], cm[5], cm[8] }, len = cs[1], r = cs[0];
+  real d0[3] = { cp[0]-bp[0], cp[1]-bp[1], cp[2]-bp[2] }, l0[3], al[3];
+  for (int k = 0; k < 3; k++) {
+    l0[k] = bm[k]*d0[0] + bm[3+k]*d0[1] + bm[6+k]*d0[2];
+    al[k] = bm[k]*ax[0] + bm[3+k]*ax[1] + bm[6+k]*ax[2];
+  }
   real lo = -len, hi = len;
   const real gr = (real)0.6180339887498949;
   real x1 = hi - gr*(hi-lo), x2 = lo + gr*(hi-lo);
-  real f1 = axis_box_dist(cp, ax, x1, bp, bm, h), f2 = axis_box_dist(cp, ax, x2, bp, bm, h);
+  real f1 = axis_box_dist(l0, al, x1, h), f2 = axis_box_dist(l0, al, x2, h);
   for (int it = 0; it < 24; it++) {
-    if (f1 <= f2) { hi = x2; x2 = x1; f2 = f1; x1 = hi - gr*(hi-lo); f1 = axis_box_dist(cp, ax, x1, bp, bm, h); }
-    else { lo = x1; x1 = x2; f1 = f2; x2 = lo + gr*(hi-lo); f2 = axis_box_dist(cp, ax, x2, bp, bm, h); }
+    if (f1 <= f2) { hi = x2; x2 = x1; f2 = f1; x1 = hi - gr*(hi-lo); f1 = axis_box_dist(l0, al, x1, h); }
+    else { lo = x1; x1 = x2; f1 = f2; x2 = lo + gr*(hi-lo); f2 = axis_box_dist(l0, al, x2, h); }
   }
   real ts = (real)0.5*(lo+hi);
-  real dmin = axis_box_dist(cp, ax, ts, bp, bm, h);
+  real dmin = axis_box_dist(l0, al, ts, h);
   if (dmin > r + margin) return 0;
   real level = dmin + (real)1e-3*r;
   real ta = -len, tb = len;
-  if (axis_box_dist(cp, ax, -len, bp, bm, h) > level) {
+  if (axis_box_dist(l0, al, -len, h) > level) {
     real a = -len, b = ts;
-    for (int it = 0; it < 16; it++) { real mid = (real)0.5*(a+b); if (axis_box_dist(cp, ax, mid, bp, bm, h) > level) a = mid; else b = mid; }
+    for (int it = 0; it < 16; it++) { real mid = (real)0.5*(a+b); if (axis_box_dist(l0, al, mid, h) > level) a = mid; else b = mid; }
     ta = b;
   }
-  if (axis_box_dist(cp, ax, len, bp, bm, h) > level) {
+  if (axis_box_dist(l0, al, len, h) > level) {
     real a = ts, b = len;
-    for (int it = 0; it < 16; it++) { real mid = (real)0.5*(a+b); if (axis_box_dist(cp, ax, mid, bp, bm, h) > level) b = mid; else a = mid; }
+    for (int it = 0; it < 16; it++) { real mid = (real)0.5*(a+b); if (axis_box_dist(l0, al, mid, h) > level) b = mid; else a = mid; }
     tb = a;
   }
   int n = 0; real p[3];

@@ -61,7 +61,8 @@ def test_box_primitives_step_parity(geom, z, quat):
 
   m = Spec.from_string(ON_BOX.format(geom=geom, z=z, quat=quat)).compile()
   n = 8
-  pos_tol = 2e-3 if "capsule" in geom else 1e-4
+  # capsule-box contact ends are defined to ~1e-3 m (see below): torques, hence accelerations, follow
+  pos_tol, acc_tol = (2e-3, 1e-2) if "capsule" in geom else (1e-4, 2e-3)
   sim = Simulation(n, SimulationCfg(), m, "cuda:0")
   sim.set_option("debug_outputs", 1)
   o = Oracle(m, nworld=n, maxcon=int(sim.get_option("maxcon")))
@@ -78,7 +79,7 @@ def test_box_primitives_step_parity(geom, z, quat):
     torch.cuda.synchronize()
     _check_contacts(sim, o, n, 1e-5)
     e = relerr(T(sim.data.qacc), o.qacc, floor=10.0)
-    assert e.max() < 2e-3, (it, e.max())
+    assert e.max() < acc_tol, (it, e.max())
     k = o.ncon.ravel()
     for w in range(n):
       if k[w]:
@@ -194,3 +195,39 @@ def test_go1_rough_full_size_properties():
   assert int(T(sim.data.overflow).sum()) == 0
   assert np.abs(T(sim.data.qvel)).max() < 1.0
   sim.close()
+
+
+def test_go1_rough_velocity_env_random_agent():
+  """BASELINE config E at env level: Go1 on the rough terrain, random actions, resets on the spawn origins;
+  native MDP kernels and the torch implementation agree on the first steps."""
+  from mjlab_b200.envs import VelocityEnvCfg, VelocityFlatEnv
+
+  cfg = dict(robot="go1", terrain="rough", num_envs=512, episode_length_s=0.3)
+  a = VelocityFlatEnv(VelocityEnvCfg(**cfg), device="cuda:0", native_mdp=False)
+  b = VelocityFlatEnv(VelocityEnvCfg(**cfg), device="cuda:0", native_mdp=True)
+  assert torch.equal(a.sim.data.qpos[:], b.sim.data.qpos[:])
+  z0 = a.sim.data.qpos[:, 2] - a.env_origins[:, 2]
+  assert torch.allclose(z0, torch.full_like(z0, float(a.default_qpos[2])), atol=1e-5)
+  assert a.env_origins[:, 2].abs().max() > 0.2  # stairs platforms are above / below the flat patches
+  g = torch.Generator(device="cuda:0")
+  g.manual_seed(5)
+  n_trunc = 0
+  for k in range(24):
+    act = torch.rand((512, 12), generator=g, device="cuda:0") * 2 - 1
+    oa, ra, ta, ua, _ = a.step(act)
+    ob, rb, tb, ub, _ = b.step(act)
+    assert torch.isfinite(oa).all() and torch.isfinite(ra).all()
+    ok = (ta == tb) & (ua == ub) & ((ra - rb).abs() < 1e-4) & ((oa - ob).abs().amax(dim=1) < 2e-3)
+    assert ok.float().mean() >= 0.97, (k, float(ok.float().mean()))
+    for f in ("qpos", "qvel", "qacc_warmstart", "ctrl"):
+      getattr(b.sim.data, f)[:] = getattr(a.sim.data, f)[:]
+    b.episode_length_buf.copy_(a.episode_length_buf)
+    b.last_action.copy_(a.last_action)
+    b.command.copy_(a.command)
+    n_trunc += int(ua.sum())
+  assert n_trunc >= 512  # every env went through a reset onto its terrain origin
+  h = a.sim.data.qpos[:, 2] - a.env_origins[:, 2]
+  assert (h > 0.05).float().mean() > 0.95 and (h < 0.6).all()  # nobody fell through the terrain
+  assert int(a.sim.data.overflow[:].sum()) == 0
+  a.close()
+  b.close()
