@@ -22,6 +22,7 @@ import os
 import subprocess
 import sys
 import tempfile
+import threading
 import time
 from pathlib import Path
 
@@ -42,7 +43,10 @@ def _peaks():
 
 
 class ClockSampler:
-  """nvidia-smi clock/throttle sampling during the timed region (B200_PROFILING.md recipe)."""
+  """SM clock / throttle-reason sampling during the timed region (B200_PROFILING.md clocks line).
+
+  NVML is polled from a thread every 5 ms (the timed region of the default run is ~150 ms, shorter than the
+  start-up time of an `nvidia-smi -lms` child process, which remains the fallback)."""
 
   Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
        "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -52,8 +56,44 @@ class ClockSampler:
     self.index = index
     self.proc = None
     self.path = None
+    self.thread = None
+    self.samples = []      # (sm_mhz, reasons bit mask)
+    self.smax = None
+    self._stop = False
+
+  def _nvml_handle(self):
+    import pynvml
+    import torch
+
+    pynvml.nvmlInit()
+    try:
+      uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+      if not uuid.startswith("GPU-"):
+        uuid = "GPU-" + uuid
+      return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+    except Exception:
+      return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
 
   def start(self):
+    try:
+      nv, h = self._nvml_handle()
+      self.smax = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+      nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+      get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+
+      def loop():
+        while not self._stop:
+          try:
+            self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(get_reasons(h))))
+          except Exception:
+            pass
+          time.sleep(0.005)
+
+      self.thread = threading.Thread(target=loop, daemon=True)
+      self.thread.start()
+      return
+    except Exception:
+      self.thread = None
     try:
       self.path = tempfile.mktemp(suffix=".csv")
       self.proc = subprocess.Popen(
@@ -63,6 +103,19 @@ class ClockSampler:
       self.proc = None
 
   def stop(self):
+    if self.thread is not None:
+      self._stop = True
+      self.thread.join(timeout=2)
+      if not self.samples:
+        return {"sm_mhz": None, "sm_max_mhz": self.smax, "reasons": ["no samples"]}
+      sm = sorted(x[0] for x in self.samples)
+      bits = 0
+      for _, r in self.samples:
+        bits |= r
+      # nvml.h: SwPowerCap 0x4, HwSlowdown 0x8, SwThermalSlowdown 0x20, HwThermalSlowdown 0x40
+      names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+      return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.smax,
+              "reasons": sorted(v for k, v in names.items() if bits & k), "samples": len(sm), "source": "nvml"}
     if self.proc is None:
       return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
     self.proc.terminate()
@@ -88,7 +141,7 @@ class ClockSampler:
       return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
     sm.sort()
     return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "reasons": sorted(reasons),
-            "samples": len(sm)}
+            "samples": len(sm), "source": "nvidia-smi"}
 
 
 class CpuPort:

@@ -171,3 +171,70 @@ def test_capsule_box_contact_set():
   o.forward()
   assert int(o.ncon[0, 0]) == 1
   assert o.contact_frame[0, :3] == pytest.approx([0, 0, -1], abs=1e-6)
+
+
+def obstacle_course_xml(seed=0, nobst=24, nobj=9):
+  """A plane, `nobst` static boxes / spheres / capsules (some rotated) and `nobj` free spheres / capsules /
+  boxes dropped among them: exercises the pair table and the static grid in one scene."""
+  rng = np.random.default_rng(seed)
+  obst, objs = [], []
+  for i in range(nobst):
+    x, y = rng.uniform(-2, 2, 2)
+    kind = ("box", "box", "box", "sphere", "capsule")[i % 5]
+    yaw = rng.uniform(-1.5, 1.5)
+    quat = f"{np.cos(yaw / 2):.6f} 0 0 {np.sin(yaw / 2):.6f}"
+    if kind == "box":
+      sx, sy, sz = rng.uniform(0.2, 0.6), rng.uniform(0.1, 0.5), rng.uniform(0.05, 0.2)
+      obst.append(f'<geom name="ob{i}" type="box" size="{sx:.3f} {sy:.3f} {sz:.3f}" pos="{x:.3f} {y:.3f} {sz:.3f}" quat="{quat}"/>')
+    elif kind == "sphere":
+      obst.append(f'<geom name="ob{i}" type="sphere" size="0.2" pos="{x:.3f} {y:.3f} 0.1"/>')
+    else:
+      obst.append(f'<geom name="ob{i}" type="capsule" size="0.1 0.4" pos="{x:.3f} {y:.3f} 0.1" quat="0.7071068 0.7071068 0 0"/>')
+  for i in range(nobj):
+    kind = ("sphere", "capsule", "box")[i % 3]
+    g = {"sphere": '<geom type="sphere" size="0.12" mass="1"/>',
+         "capsule": '<geom type="capsule" size="0.06 0.2" mass="1"/>',
+         "box": '<geom type="box" size="0.15 0.1 0.08" mass="1"/>'}[kind]
+    x, y = rng.uniform(-1.8, 1.8, 2)
+    objs.append(f'<body name="obj{i}" pos="{x:.3f} {y:.3f} 0.6"><freejoint/>{g}</body>')
+  return f"""<mujoco><option timestep="0.004"/>
+  <worldbody>
+    <geom name="floor" type="plane" size="0 0 0.01"/>
+    <body name="course">{''.join(obst)}</body>
+    {''.join(objs)}
+  </worldbody></mujoco>"""
+
+
+def test_mixed_pair_table_and_grid_scene():
+  xml = obstacle_course_xml()
+  mg = Spec.from_string(xml).compile()
+  old = C.STATIC_GRID_THRESHOLD
+  C.STATIC_GRID_THRESHOLD = 10**9
+  try:
+    mp = Spec.from_string(xml).compile()
+  finally:
+    C.STATIC_GRID_THRESHOLD = old
+  assert int(mg.nstatic) == 24 and int(mg.npair) > 0 and int(mp.nstatic) == 0
+  n = 6
+  rng = np.random.default_rng(1)
+  a, b = Oracle(mg, nworld=n, maxcon=96), Oracle(mp, nworld=n, maxcon=96)
+  q = np.tile(mg.qpos0, (n, 1))
+  q += rng.uniform(-0.05, 0.05, q.shape) * (np.arange(q.shape[1]) % 7 < 3)  # jitter positions only
+  for o in (a, b):
+    o.qpos[:] = q
+  seen = 0
+  for it in range(150):
+    for o in (a, b):
+      o.step()
+    assert (a.ncon == b.ncon).all()
+    for w in range(n):
+      k = int(a.ncon[w, 0])
+      sa = sorted(zip(map(tuple, a.contact_geom[w].reshape(-1, 2)[:k]), np.round(a.contact_dist[w][:k], 8)))
+      sb = sorted(zip(map(tuple, b.contact_geom[w].reshape(-1, 2)[:k]), np.round(b.contact_dist[w][:k], 8)))
+      assert sa == sb
+    seen = max(seen, int(a.ncon.max()))
+    # different contact order -> different summation order only
+    assert np.abs(a.qpos - b.qpos).max() < 1e-6
+    b.qpos[:], b.qvel[:], b.qacc_warmstart[:] = a.qpos, a.qvel, a.qacc_warmstart
+  assert seen >= 8 and np.isfinite(a.qpos).all()
+  assert a.qpos[:, 2::7].min() > 0.0  # nothing fell through the floor

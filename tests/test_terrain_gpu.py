@@ -231,3 +231,42 @@ def test_go1_rough_velocity_env_random_agent():
   assert int(a.sim.data.overflow[:].sum()) == 0
   a.close()
   b.close()
+
+
+def test_obstacle_course_step_parity():
+  """Plane + 24 static boxes / spheres / capsules (grid) + 9 free primitives (pair table, all six primitive
+  pair types): contact sets identical, accelerations within fp32 tolerance, step by step with resync."""
+  from test_boxes_terrain import obstacle_course_xml
+
+  from mjlab_b200.compiler import Spec
+  from mjlab_b200.sim import Simulation, SimulationCfg
+  from oracle.oracle import Oracle
+
+  m = Spec.from_string(obstacle_course_xml()).compile()
+  assert int(m.nstatic) == 24 and int(m.npair) > 0
+  n = 16
+  sim = Simulation(n, SimulationCfg(nconmax=96 * n), m, "cuda:0")
+  sim.set_option("debug_outputs", 1)
+  o = Oracle(m, nworld=n, maxcon=int(sim.get_option("maxcon")))
+  rng = np.random.default_rng(1)
+  q = np.tile(m.qpos0, (n, 1))
+  q += rng.uniform(-0.08, 0.08, q.shape) * (np.arange(q.shape[1]) % 7 < 3)
+  st = dict(qpos=q, qvel=rng.uniform(-0.3, 0.3, (n, int(m.nv))))
+  load_oracle(o, st)
+  load_sim(sim, st)
+  seen, worst = 0, 0.0
+  for it in range(120):
+    o.forward()
+    sim.forward()
+    torch.cuda.synchronize()
+    _check_contacts(sim, o, n, 2e-5)
+    e = relerr(T(sim.data.qacc), o.qacc, floor=10.0)
+    worst = max(worst, float(e.max()))
+    seen = max(seen, int(o.ncon.max()))
+    o.step()
+    sim.step()
+    for f in ("qpos", "qvel", "qacc_warmstart"):
+      getattr(sim.data, f)[:] = torch.as_tensor(getattr(o, f), dtype=torch.float32, device="cuda:0")
+  assert seen >= 8
+  assert worst < 1e-2, worst  # capsule-box contact ends, see test_box_primitives_step_parity
+  sim.close()
