@@ -26,6 +26,13 @@
 #define SD 7   // 6-float records: cdof, cdofdot, cvel, cacc / wrenches
 #define SI 11  // 10-float records: cinert, crb
 
+#ifndef B2_UNR_HPROJ
+#define B2_UNR_HPROJ 1
+#endif
+#define B2_STR(x) #x
+#define B2_PRAGMA(x) _Pragma(B2_STR(x))
+#define B2_UNROLL(n) B2_PRAGMA(unroll n)
+
 namespace b2 {
 
 __device__ __forceinline__ float wsum(float v) {
@@ -185,6 +192,50 @@ __device__ __noinline__ void chol_factor(float* A, float* invdiag, int n, const 
     float dv[4] = {0.f, 0.f, 0.f, 0.f};      // 1/d of the block's pivots (warp-uniform)
     float Lb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // L10, L20, L21, L30, L31, L32 (warp-uniform)
     // ---- panel: rows k.., columns k..k+nb-1 -------------------------------------------------
+#ifndef B2_PANEL_SHUFFLE
+    {
+      // the 4x4 diagonal block is factorised redundantly by every lane from ten broadcast loads (no
+      // shuffle chain); then every row of the panel, block rows included, gets the same three updates
+      const int q0 = k * (k + 1) >> 1, q1 = q0 + k + 1, q2 = q1 + k + 2, q3 = q2 + k + 3;
+      float a10 = 0.f, a11 = 1.f, a20 = 0.f, a21 = 0.f, a22 = 1.f, a30 = 0.f, a31 = 0.f, a32 = 0.f, a33 = 1.f;
+      float a00 = A[q0 + k];
+      if (nb > 1) { a10 = A[q1 + k]; a11 = A[q1 + k + 1]; }
+      if (nb > 2) { a20 = A[q2 + k]; a21 = A[q2 + k + 1]; a22 = A[q2 + k + 2]; }
+      if (nb > 3) { a30 = A[q3 + k]; a31 = A[q3 + k + 1]; a32 = A[q3 + k + 2]; a33 = A[q3 + k + 3]; }
+      __syncwarp();  // every lane holds the block before any panel store touches it
+      dv[0] = __frcp_rn(fmaxf(a00, MINVAL));
+      Lb[0] = a10 * dv[0];
+      dv[1] = __frcp_rn(fmaxf(a11 - a10 * Lb[0], MINVAL));
+      Lb[1] = a20 * dv[0];
+      float t21 = a21 - a20 * Lb[0];
+      Lb[2] = t21 * dv[1];
+      dv[2] = __frcp_rn(fmaxf(a22 - a20 * Lb[1] - t21 * Lb[2], MINVAL));
+      Lb[3] = a30 * dv[0];
+      float t31 = a31 - a30 * Lb[0];
+      Lb[4] = t31 * dv[1];
+      float t32 = a32 - a30 * Lb[1] - t31 * Lb[2];
+      Lb[5] = t32 * dv[2];
+      dv[3] = __frcp_rn(fmaxf(a33 - a30 * Lb[3] - t31 * Lb[4] - t32 * Lb[5], MINVAL));
+      if (lane < nb) invdiag[k + lane] = lane == 0 ? dv[0] : (lane == 1 ? dv[1] : (lane == 2 ? dv[2] : dv[3]));
+    }
+#pragma unroll 1
+    for (int base = k; base < n; base += 32) {
+      int i = base + lane;
+      bool ok = i < n;
+      int ri = ok ? (i * (i + 1) >> 1) : 0;
+      float r[4];
+#pragma unroll
+      for (int t = 0; t < 4; t++) r[t] = (ok && t < nb && k + t <= i) ? A[ri + k + t] : 0.f;
+      r[1] -= r[0] * Lb[0];
+      r[2] -= r[0] * Lb[1] + r[1] * Lb[2];
+      r[3] -= r[0] * Lb[3] + r[1] * Lb[4] + r[2] * Lb[5];
+      if (ok) {
+#pragma unroll
+        for (int t = 1; t < 4; t++)
+          if (t < nb && k + t <= i) A[ri + k + t] = r[t];
+      }
+    }
+#else
 #pragma unroll 1
     for (int base = k; base < n; base += 32) {
       int i = base + lane;
@@ -227,6 +278,7 @@ __device__ __noinline__ void chol_factor(float* A, float* invdiag, int n, const 
           if (t < nb && k + t <= i) A[ri + k + t] = r[t];
       }
     }
+#endif
     __syncwarp();
     // ---- trailing update: A[i,j] -= sum_t c_i,k+t * c_j,k+t / d_t for j >= k+nb ---------------
     int mtr = n - k - nb;
@@ -267,6 +319,8 @@ __device__ __noinline__ void chol_factor(float* A, float* invdiag, int n, const 
   }
 }
 // x <- (L D L^T)^-1 x, x in shared memory (n <= 64); values stay in registers during the sweeps.
+// (A 4-pivot blocked variant - redundant 4x4 block solve + rank-4 row update, 2*ceil(n/4) dependent steps -
+// measured 10 % slower end to end: the guards cost more issue slots than the shorter chain saves.)
 __device__ __noinline__ void chol_solve(const float* L, const float* invdiag, float* x, int n,
                                         int lane) {
   float x0 = lane < n ? x[lane] : 0.f;
@@ -291,7 +345,35 @@ __device__ __noinline__ void chol_solve(const float* L, const float* invdiag, fl
   if (lane + 32 < n) x[lane + 32] = x1;
   __syncwarp();
 }
-// y = M x for packed symmetric M (both in shared memory)
+// y = M x for packed symmetric M (both in shared memory).  One column loop for all lanes (entry (i,j) lives
+// at tri(max)+min), four independent accumulators so the loads of four columns are in flight together.
+#ifndef B2_SYMV_SIMPLE
+__device__ __noinline__ void symv(const float* M, const float* x, float* y, int n, int lane) {
+  #pragma unroll 1
+  for (int i = lane; i < n; i += 32) {
+    const int ri = i * (i + 1) >> 1;
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+    int j = 0, tj = 0;  // tj = tri(j, 0)
+    #pragma unroll 1
+    for (; j + 4 <= n; j += 4) {
+      int a0 = j <= i ? ri + j : tj + i;
+      int u1 = tj + j + 1, u2 = u1 + j + 2, u3 = u2 + j + 3;
+      int a1 = j + 1 <= i ? ri + j + 1 : u1 + i;
+      int a2 = j + 2 <= i ? ri + j + 2 : u2 + i;
+      int a3 = j + 3 <= i ? ri + j + 3 : u3 + i;
+      t0 += M[a0] * x[j]; t1 += M[a1] * x[j + 1]; t2 += M[a2] * x[j + 2]; t3 += M[a3] * x[j + 3];
+      tj = u3 + j + 4;
+    }
+    #pragma unroll 1
+    for (; j < n; j++) {
+      t0 += M[j <= i ? ri + j : tj + i] * x[j];
+      tj += j + 1;
+    }
+    y[i] = (t0 + t1) + (t2 + t3);
+  }
+  __syncwarp();
+}
+#else
 __device__ __noinline__ void symv(const float* M, const float* x, float* y, int n, int lane) {
   #pragma unroll 1
   for (int i = lane; i < n; i += 32) {
@@ -305,6 +387,7 @@ __device__ __noinline__ void symv(const float* M, const float* x, float* y, int 
   }
   __syncwarp();
 }
+#endif
 
 // ---- narrowphase primitives (engine_collision_primitive.c semantics) ----
 struct RawCon {
@@ -1488,7 +1571,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   PHASE_MARK(7);
   // ---------------- phase 7: unconstrained acceleration -------------------------------------------
   #pragma unroll 1
-  for (int i = lane; i < m.ntri; i += 32) H[i] = Mq[i];
+  for (int i = lane; i < (m.ntri + 3) >> 2; i += 32) ((float4*)H)[i] = ((const float4*)Mq)[i];  // both regions are 16 B aligned and padded
   __syncwarp();
   chol_factor(H, invdiag, nv, s_coldesc, lane);
   chol_solve(H, invdiag, qacc_smooth, nv, lane);
@@ -1644,7 +1727,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       PHASE_MARK(12);
       // ---- Hessian H = M + J^T D_active J via per-body-pair 6x6 blocks -------------------------
       #pragma unroll 1
-      for (int i = lane; i < m.ntri; i += 32) H[i] = Mq[i];
+      for (int i = lane; i < (m.ntri + 3) >> 2; i += 32) ((float4*)H)[i] = ((const float4*)Mq)[i];  // both regions are 16 B aligned and padded
       __syncwarp();
       #pragma unroll 1
       for (int r = lane; r < nlim; r += 32) {
@@ -1681,6 +1764,35 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         if (lo >> lane & 1u) glist[__popc(lo & ((1u << lane) - 1u))] = lane;
         if (hi >> lane & 1u) glist[nlo + __popc(hi & ((1u << lane) - 1u))] = 32 + lane;
         __syncwarp();
+#ifndef B2_HPROJ_ROWS
+        // u_a = sign_a * A * cdof_a: one (dof, component) per lane
+        #pragma unroll 1
+        for (int t = lane; t < 6 * ns; t += 32) {
+          int a = t / 6, k = t - 6 * a;
+          int d = glist[a];
+          const float* c = cdof + SD * d;
+          const float* ga = gA + 6 * k;
+          float v = ga[0] * c[0] + ga[1] * c[1] + ga[2] * c[2] + ga[3] * c[3] + ga[4] * c[4] + ga[5] * c[5];
+          gu[t] = (m2 >> d & 1ull) ? v : -v;
+        }
+        __syncwarp();
+        // H[da, db] += u_a . (sign_b cdof_b) for the pairs a >= b of the group's dof list, one pair per lane
+        const int npr = ns * (ns + 1) >> 1;
+        #pragma unroll 1
+        for (int p = lane; p < npr; p += 32) {
+          int a = (int)((sqrtf(8.f * (float)p + 1.f) - 1.f) * 0.5f);
+          if ((a * (a + 1) >> 1) > p) a--;
+          if (((a + 1) * (a + 2) >> 1) <= p) a++;
+          int b = p - (a * (a + 1) >> 1);
+          int da = glist[a], db = glist[b];
+          const float* u = gu + 6 * a;
+          const float* c = cdof + SD * db;
+          float v = u[0] * c[0] + u[1] * c[1] + u[2] * c[2] + u[3] * c[3] + u[4] * c[4] + u[5] * c[5];
+          H[(da * (da + 1) >> 1) + db] += (m2 >> db & 1ull) ? v : -v;
+        }
+        __syncwarp();
+      }
+#else
         #pragma unroll 1
         for (int a = lane; a < ns; a += 32) {
           int d = glist[a];
@@ -1704,7 +1816,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
           float cb[6];
 #pragma unroll
           for (int k = 0; k < 6; k++) cb[k] = sgb * cdof[SD * db + k];
-#pragma unroll 1
+B2_UNROLL(B2_UNR_HPROJ)
           for (int a = b0; a < ns; a++) {
             const float* u = gu + 6 * a;
             float v = u[0] * cb[0] + u[1] * cb[1] + u[2] * cb[2] + u[3] * cb[3] + u[4] * cb[4] + u[5] * cb[5];
@@ -1714,6 +1826,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         }
         __syncwarp();
       }
+#endif
       PHASE_MARK(13);
       chol_factor(H, invdiag, nv, s_coldesc, lane);
       #pragma unroll 1
@@ -1920,7 +2033,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     const float* damp = MP(dof_damping); const float* bp = MP(actuator_biasprm);
     const float* fr = MP(actuator_forcerange); const float* gear = MP(actuator_gear);
     #pragma unroll 1
-    for (int i = lane; i < m.ntri; i += 32) H[i] = Mq[i];
+    for (int i = lane; i < (m.ntri + 3) >> 2; i += 32) ((float4*)H)[i] = ((const float4*)Mq)[i];  // both regions are 16 B aligned and padded
     __syncwarp();
     #pragma unroll 1
     for (int i = lane; i < nv; i += 32) H[tri(i, i)] += h * damp[i];

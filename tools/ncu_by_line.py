@@ -5,7 +5,7 @@ usage: python tools/ncu_by_line.py <report.ncu-rep> <kernel-mangled-substring> [
 import csv, re, subprocess, sys, tempfile, os, collections
 rep, kname = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-so = os.path.join(os.path.dirname(__file__), "..", "mjlab_b200", "csrc", "libb2sim.so")
+so = os.environ.get("B2SIM_LIB") or os.path.join(os.path.dirname(__file__), "..", "mjlab_b200", "csrc", "libb2sim.so")  # must be the build the report was captured with
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, capture_output=True)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
