@@ -321,6 +321,52 @@ __device__ __noinline__ void chol_factor(float* A, float* invdiag, int n, const 
 // x <- (L D L^T)^-1 x, x in shared memory (n <= 64); values stay in registers during the sweeps.
 // (A 4-pivot blocked variant - redundant 4x4 block solve + rank-4 row update, 2*ceil(n/4) dependent steps -
 // measured 10 % slower end to end: the guards cost more issue slots than the shorter chain saves.)
+#ifndef B2_SOLVE_SIMPLE
+// Rows >= 32 (three of them for the 35-dof G1) are kept out of the two 32-row sweeps: their couplings are
+// applied by warp reductions (forward) and broadcasts (backward), so the long loops carry one row per lane.
+__device__ __noinline__ void chol_solve(const float* L, const float* invdiag, float* x, int n,
+                                        int lane) {
+  const int n0 = min(n, 32), nh = n - n0;
+  float x0 = lane < n0 ? x[lane] : 0.f;
+  float x1 = lane < nh ? x[lane + 32] : 0.f;
+  const float d0 = lane < n0 ? invdiag[lane] : 0.f, d1 = lane < nh ? invdiag[lane + 32] : 0.f;
+  const int r0 = lane * (lane + 1) >> 1;
+#pragma unroll 1
+  for (int k = 0; k < n0; k++) {  // L y = b, rows < 32
+    float xk = __shfl_sync(FULL, x0, k) * invdiag[k];
+    if (lane > k && lane < n0) x0 -= L[r0 + k] * xk;
+  }
+  if (nh > 0) {
+    const float w0 = x0 * d0;
+#pragma unroll 1
+    for (int r = 0; r < nh; r++) {  // y_hi[r] = b_hi[r] - sum_j L[32+r, j] y_j
+      const int rr = (32 + r) * (33 + r) >> 1;
+      float part = L[rr + lane] * w0;
+      if (lane < r) part += L[rr + 32 + lane] * (x1 * d1);
+      part = wsum(part);
+      if (lane == r) x1 -= part;
+    }
+  }
+  x0 *= d0; x1 *= d1;  // D z = y
+  if (nh > 0) {
+#pragma unroll 1
+    for (int j = nh - 1; j >= 0; j--) {  // L^T x = z: rows >= 32 first, then their effect on rows < 32
+      const int rj = (32 + j) * (33 + j) >> 1;
+      float xj = __shfl_sync(FULL, x1, j);
+      if (lane < j) x1 -= L[rj + 32 + lane] * d1 * xj;
+      x0 -= L[rj + lane] * d0 * xj;
+    }
+  }
+#pragma unroll 1
+  for (int k = n0 - 1; k >= 0; k--) {
+    float xk = __shfl_sync(FULL, x0, k);
+    if (lane < k) x0 -= L[(k * (k + 1) >> 1) + lane] * d0 * xk;
+  }
+  if (lane < n0) x[lane] = x0;
+  if (lane < nh) x[lane + 32] = x1;
+  __syncwarp();
+}
+#else
 __device__ __noinline__ void chol_solve(const float* L, const float* invdiag, float* x, int n,
                                         int lane) {
   float x0 = lane < n ? x[lane] : 0.f;
@@ -345,6 +391,7 @@ __device__ __noinline__ void chol_solve(const float* L, const float* invdiag, fl
   if (lane + 32 < n) x[lane + 32] = x1;
   __syncwarp();
 }
+#endif
 // y = M x for packed symmetric M (both in shared memory).  One column loop for all lanes (entry (i,j) lives
 // at tri(max)+min), four independent accumulators so the loads of four columns are in flight together.
 #ifndef B2_SYMV_SIMPLE
@@ -859,6 +906,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   float* gpose = s + L.gpose;
   {
     const float* geom_pos = MP(geom_pos); const float* geom_quat = MP(geom_quat);
+    const float* geom_rb = MP(geom_rbound); const float* geom_mar = MP(geom_margin);
     float* gxp = dd.geom_xpos.p + (size_t)w * dd.geom_xpos.stride;
     float* gxm = dd.geom_xmat.p + (size_t)w * dd.geom_xmat.stride;
     #pragma unroll 1
@@ -875,10 +923,11 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       for (int k = 0; k < 9; k++) gxm[9 * g + k] = mat[k];
       int cs = m.geom_cslot[g];
       if (cs >= 0) {
-        float* gp = gpose + 12 * cs;
+        float* gp = gpose + GP * cs;
         gp[0] = p[0]; gp[1] = p[1]; gp[2] = p[2];
 #pragma unroll
         for (int k = 0; k < 9; k++) gp[3 + k] = mat[k];
+        gp[12] = geom_rb[g]; gp[13] = geom_mar[g];  // per-world values: the broadphase reads nothing else
       }
     }
     const float* site_pos = MP(site_pos); const float* site_quat = MP(site_quat);
@@ -1174,23 +1223,23 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   int ncon = 0, overflow = 0;
   {
     int* pairlist = (int*)(s + L.pairlist);
-    const float* rb = MP(geom_rbound); const float* gmar = MP(geom_margin);
+    const float* gmar = MP(geom_margin);
     int ncand = 0;
     #pragma unroll 1
     for (int p0 = 0; p0 < m.npair; p0 += 32) {
       int p = p0 + lane;
       bool hit = false;
       if (p < m.npair) {
-        int g1 = m.pair_geom1[p], g2 = m.pair_geom2[p];
-        const float* a = gpose + 12 * m.geom_cslot[g1];
-        const float* b = gpose + 12 * m.geom_cslot[g2];
-        float margin = fmaxf(gmar[g1], gmar[g2]);
+        unsigned pw = m.pair_word[p];  // slot1 | slot2 << 12 | (geom1 is a plane) << 31
+        const float* a = gpose + GP * (pw & 0xfffu);
+        const float* b = gpose + GP * ((pw >> 12) & 0xfffu);
+        float margin = fmaxf(a[13], b[13]);
         float dif[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
-        if (m.geom_type[g1] == G_PLANE) {
+        if (pw >> 31) {
           float n[3] = {a[3 + 2], a[3 + 5], a[3 + 8]};
-          hit = dot3(dif, n) <= margin + rb[g2];
+          hit = dot3(dif, n) <= margin + b[12];
         } else {
-          float bound = margin + rb[g1] + rb[g2];
+          float bound = margin + a[12] + b[12];
           hit = dot3(dif, dif) <= bound * bound;
         }
       }
@@ -1213,8 +1262,8 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         for (int pass = 0; pass < 2; pass++) {
           if (q < m.ndyn) {
             int g = m.dyn_cgeom[q];
-            const float* c = gpose + 12 * m.geom_cslot[g];
-            float r = rb[g], mg = gmar[g];
+            const float* c = gpose + GP * m.geom_cslot[g];
+            float r = c[12], mg = c[13];
             int ct = m.geom_contype[g], ca = m.geom_conaffinity[g];
             int ix0 = max((int)floorf((c[0] - r - m.grid_x0) / m.grid_cell), 0);
             int ix1 = min((int)floorf((c[0] + r - m.grid_x0) / m.grid_cell), m.grid_nx - 1);
@@ -1283,12 +1332,12 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         const float *a, *b;
         if (p >= 0) {
           g1 = m.pair_geom1[p]; g2 = m.pair_geom2[p];
-          a = gpose + 12 * m.geom_cslot[g1];
-          b = gpose + 12 * m.geom_cslot[g2];
+          a = gpose + GP * m.geom_cslot[g1];
+          b = gpose + GP * m.geom_cslot[g2];
         } else {  // grid-static candidate: (dynamic geom, static geom), ordered by (type, id)
           int k = p & 0xfffff;
           g1 = m.dyn_cgeom[(p >> 20) & 0x7ff]; g2 = m.static_geom[k];
-          a = gpose + 12 * m.geom_cslot[g1];
+          a = gpose + GP * m.geom_cslot[g1];
           b = m.static_pose + 16 * (size_t)k;
           int ta = m.geom_type[g1], tb = m.geom_type[g2];
           if (ta > tb || (ta == tb && g1 > g2)) {

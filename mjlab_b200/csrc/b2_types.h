@@ -11,6 +11,7 @@
 #define B2_MAX_FIELDS 96
 
 enum { JNT_FREE = 0, JNT_BALL = 1, JNT_SLIDE = 2, JNT_HINGE = 3 };
+#define GP 15  // shared-memory collision pose records: pos[3], mat[9], rbound, margin (+1 pad: odd stride)
 enum { G_PLANE = 0, G_SPHERE = 2, G_CAPSULE = 3, G_BOX = 6, G_MESH = 7 };
 enum { OBJ_BODY = 1, OBJ_XBODY = 2, OBJ_GEOM = 5 };
 enum { INT_EULER = 0, INT_IMPLICITFAST = 3 };
@@ -82,6 +83,7 @@ struct DevModel {
   const int *site_bodyid;
   const int *actuator_trnid, *actuator_ctrllimited, *actuator_forcelimited;
   const int *pair_geom1, *pair_geom2;
+  const unsigned* pair_word;  // broadphase record per pair: slot1 | slot2 << 12 | (geom1 is a plane) << 31
   // grid-static collision set (terrain): geoms welded to the world, found through a uniform xy grid
   int nstatic, ndyn, nposegeom, grid_nx, grid_ny;
   float grid_x0, grid_y0, grid_cell;

@@ -468,6 +468,15 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
   }
   rc |= dev_upload<int>(s, posegeom, &m.posegeom);
   rc |= dev_upload<float>(s, static_pose, &m.static_pose);
+  {
+    if (m.ncg >= 4096) { b2_destroy(s); return fail("b2_create: too many collision geoms"); }
+    std::vector<unsigned> pw(std::max(m.npair, 1), 0u);
+    for (int p = 0; p < m.npair; p++) {
+      int g1 = s->mi["pair_geom1"][p], g2 = s->mi["pair_geom2"][p];
+      pw[p] = (unsigned)cslot[g1] | ((unsigned)cslot[g2] << 12) | (s->mi["geom_type"][g1] == G_PLANE ? 0x80000000u : 0u);
+    }
+    rc |= dev_upload<unsigned>(s, pw, &m.pair_word);
+  }
   rc |= dev_upload<int>(s, cslot, &m.geom_cslot);
   rc |= dev_upload<int>(s, cgeom, &m.cgeom);
   rc |= dev_upload<unsigned short>(s, trow, &m.tri_rowmajor);
@@ -558,8 +567,8 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
   L.qpos = alloc(d.qpos.stride); L.qvel = alloc(d.qvel.stride); L.ctrl = alloc(d.ctrl.stride);
   L.qacc_ws = alloc(d.qacc_warmstart.stride); L.qfrc_applied = alloc(d.qfrc_applied.stride);
   L.cdof = alloc(7 * nv); L.M = alloc(m.ntri);
-  int hsize = std::max(m.ntri, 12 * m.ncg + L.maxpair);
-  L.H = alloc(hsize); L.gpose = L.H; L.pairlist = L.H + 12 * m.ncg;
+  int hsize = std::max(m.ntri, pad4(GP * m.ncg) + L.maxpair);
+  L.H = alloc(hsize); L.gpose = L.H; L.pairlist = L.H + pad4(GP * m.ncg);
   L.invdiag = alloc(nv);
   L.qfrc_smooth = alloc(nv); L.qacc_smooth = alloc(nv); L.qacc = alloc(nv); L.Ma = alloc(nv);
   L.grad = alloc(nv); L.search = alloc(nv); L.Mv = alloc(nv); L.qfrc_c = alloc(nv); L.tmpv = alloc(nv);
