@@ -177,6 +177,12 @@ __device__ unsigned long long g_phase_cycles[32];
 #define PHASE_MARK(id)
 #endif
 
+// approximate reciprocal (MUFU.RCP): the IEEE-rounded __frcp_rn costs ~13 instructions per call
+__device__ __forceinline__ float b2_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 // ---- dense packed LDL^T (lower, row-major packed) in shared memory --------------------------------
 // In place: after the call A[k,k] = d_k and A[i,k] = L_ik d_k (i > k); invdiag[k] = 1/d_k.  One warp
 // barrier per pivot.  Balanced schedule: the trailing-triangle update of step k runs over a list of
@@ -203,20 +209,24 @@ __device__ __noinline__ void chol_factor(float* A, float* invdiag, int n, const 
       if (nb > 2) { a20 = A[q2 + k]; a21 = A[q2 + k + 1]; a22 = A[q2 + k + 2]; }
       if (nb > 3) { a30 = A[q3 + k]; a31 = A[q3 + k + 1]; a32 = A[q3 + k + 2]; a33 = A[q3 + k + 3]; }
       __syncwarp();  // every lane holds the block before any panel store touches it
-      dv[0] = __frcp_rn(fmaxf(a00, MINVAL));
+      dv[0] = b2_rcp(fmaxf(a00, MINVAL));
       Lb[0] = a10 * dv[0];
-      dv[1] = __frcp_rn(fmaxf(a11 - a10 * Lb[0], MINVAL));
+      dv[1] = b2_rcp(fmaxf(a11 - a10 * Lb[0], MINVAL));
       Lb[1] = a20 * dv[0];
       float t21 = a21 - a20 * Lb[0];
       Lb[2] = t21 * dv[1];
-      dv[2] = __frcp_rn(fmaxf(a22 - a20 * Lb[1] - t21 * Lb[2], MINVAL));
+      dv[2] = b2_rcp(fmaxf(a22 - a20 * Lb[1] - t21 * Lb[2], MINVAL));
       Lb[3] = a30 * dv[0];
       float t31 = a31 - a30 * Lb[0];
       Lb[4] = t31 * dv[1];
       float t32 = a32 - a30 * Lb[1] - t31 * Lb[2];
       Lb[5] = t32 * dv[2];
-      dv[3] = __frcp_rn(fmaxf(a33 - a30 * Lb[3] - t31 * Lb[4] - t32 * Lb[5], MINVAL));
-      if (lane < nb) invdiag[k + lane] = lane == 0 ? dv[0] : (lane == 1 ? dv[1] : (lane == 2 ? dv[2] : dv[3]));
+      dv[3] = b2_rcp(fmaxf(a33 - a30 * Lb[3] - t31 * Lb[4] - t32 * Lb[5], MINVAL));
+      // every lane holds the same four values: plain same-address stores, no select chain
+      invdiag[k] = dv[0];
+      if (nb > 1) invdiag[k + 1] = dv[1];
+      if (nb > 2) invdiag[k + 2] = dv[2];
+      if (nb > 3) invdiag[k + 3] = dv[3];
     }
 #pragma unroll 1
     for (int base = k; base < n; base += 32) {
@@ -332,9 +342,9 @@ __device__ __noinline__ void chol_solve(const float* L, const float* invdiag, fl
   const float d0 = lane < n0 ? invdiag[lane] : 0.f, d1 = lane < nh ? invdiag[lane + 32] : 0.f;
   const int r0 = lane * (lane + 1) >> 1;
 #pragma unroll 1
-  for (int k = 0; k < n0; k++) {  // L y = b, rows < 32
-    float xk = __shfl_sync(FULL, x0, k) * invdiag[k];
-    if (lane > k && lane < n0) x0 -= L[r0 + k] * xk;
+  for (int k = 0; k < n0; k++) {  // L y = b, rows < 32 (the scaled entry is ready before x_k arrives)
+    float t = (lane > k && lane < n0) ? L[r0 + k] * invdiag[k] : 0.f;
+    x0 = fmaf(-t, __shfl_sync(FULL, x0, k), x0);
   }
   if (nh > 0) {
     const float w0 = x0 * d0;
@@ -357,10 +367,12 @@ __device__ __noinline__ void chol_solve(const float* L, const float* invdiag, fl
       x0 -= L[rj + lane] * d0 * xj;
     }
   }
+  int rk = n0 * (n0 - 1) >> 1;  // tri(n0 - 1, 0)
 #pragma unroll 1
   for (int k = n0 - 1; k >= 0; k--) {
-    float xk = __shfl_sync(FULL, x0, k);
-    if (lane < k) x0 -= L[(k * (k + 1) >> 1) + lane] * d0 * xk;
+    float t = lane < k ? L[rk + lane] * d0 : 0.f;
+    x0 = fmaf(-t, __shfl_sync(FULL, x0, k), x0);
+    rk -= k;
   }
   if (lane < n0) x[lane] = x0;
   if (lane < nh) x[lane + 32] = x1;
@@ -790,10 +802,14 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         // one dependent load level per chain step: chain id -> 64-byte record (prefetched one ahead)
         const int* chain = m.body_chain + b * m.maxdepth;
         int c = depth > 0 ? chain[0] : 0;
+        int cn = depth > 1 ? chain[1] : 0;
+        float4 p0 = m.kinrec[4 * c], p1 = m.kinrec[4 * c + 1], p2 = m.kinrec[4 * c + 2], p3 = m.kinrec[4 * c + 3];
         #pragma unroll 1
         for (int k = 0; k < depth; k++) {
-          int cn = k + 1 < depth ? chain[k + 1] : 0;
-          float4 r0 = m.kinrec[4 * c], r1 = m.kinrec[4 * c + 1], r2 = m.kinrec[4 * c + 2], r3 = m.kinrec[4 * c + 3];
+          const float4 r0 = p0, r1 = p1, r2 = p2, r3 = p3;
+          c = cn;  // the next step's record and the id after it are in flight while this step computes
+          cn = k + 2 < depth ? chain[k + 2] : 0;
+          p0 = m.kinrec[4 * c]; p1 = m.kinrec[4 * c + 1]; p2 = m.kinrec[4 * c + 2]; p3 = m.kinrec[4 * c + 3];
           int tj = __float_as_int(r2.w), qa = __float_as_int(r3.w);
           int type = tj & 0xff, ja = tj >> 8;
           bool last = (k == depth - 1);
@@ -837,7 +853,6 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
             }
           }
           normalize4(quat);
-          c = cn;
         }
         depth = 0;  // generic walk below is skipped
       }
@@ -1225,12 +1240,14 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     int* pairlist = (int*)(s + L.pairlist);
     const float* gmar = MP(geom_margin);
     int ncand = 0;
+    unsigned pw_next = lane < m.npair ? m.pair_word[lane] : 0u;
     #pragma unroll 1
     for (int p0 = 0; p0 < m.npair; p0 += 32) {
       int p = p0 + lane;
       bool hit = false;
+      const unsigned pw = pw_next;  // slot1 | slot2 << 12 | (geom1 is a plane) << 31
+      if (p + 32 < m.npair) pw_next = m.pair_word[p + 32];  // next batch's word is in flight during this one
       if (p < m.npair) {
-        unsigned pw = m.pair_word[p];  // slot1 | slot2 << 12 | (geom1 is a plane) << 31
         const float* a = gpose + GP * (pw & 0xfffu);
         const float* b = gpose + GP * ((pw >> 12) & 0xfffu);
         float margin = fmaxf(a[13], b[13]);
