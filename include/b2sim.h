@@ -83,7 +83,8 @@ const char* b2_field_name(b2_sim* sim, int which, int index);
 int b2_expand_model_field(b2_sim* sim, const char* name, void* cuda_stream, B2Tensor* out);
 
 /* Options: "iterations", "ls_iterations", "tolerance", "ls_tolerance", "ls_parallel",
- * "timestep", "integrator", "debug_outputs", "sorted_dispatch" (heavy-first launch order, default on), "fused_decimation" (b2_step_n as one launch; default off). */
+ * "timestep", "integrator", "debug_outputs", "sorted_dispatch" (heavy-first launch order, default on), "fused_decimation" (b2_step_n as one launch; default off),
+ * "dense_factor" (testing: always take the dense factorisation schedule instead of the dof-tree one). */
 int b2_set_option(b2_sim* sim, const char* key, double value);
 int b2_get_option(b2_sim* sim, const char* key, double* value);
 

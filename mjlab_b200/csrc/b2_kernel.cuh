@@ -404,6 +404,132 @@ __device__ __noinline__ void chol_solve(const float* L, const float* invdiag, fl
   __syncwarp();
 }
 #endif
+// ---- bottom-up blocked L^T D L (leaves first) -----------------------------------------------------------
+// Pivots are eliminated from the last dof to the first, four per block step, so the dof tree's zero pattern
+// survives (no fill between branches) and the trailing update visits only the entries the tree can make
+// non-zero (G1: 437 instead of 1560 pair-visits per factorisation).  In place: A[k,k] = d_k,
+// A[k,j] = L_kj d_k (j < k), invdiag[k] = 1/d_k, M = L^T D L with L unit lower.  `list`/`start`: per-block
+// schedules (words p | i << 12 | j << 18); with sparse == false (a contact couples two branches) the block
+// with m leading rows takes the first tri(m) words of the dense list instead.
+__device__ __noinline__ void ldl_factor(float* A, float* invdiag, int n, const unsigned* slist, const int* start,
+                                        const unsigned* __restrict__ dense, bool sparse, int lane) {
+  int blk = 0;
+#pragma unroll 1
+  for (int kt = n - 1; kt >= 0; kt -= 4, blk++) {
+    const int nb = min(4, kt + 1), lead = kt - nb + 1;
+    const int rb0 = kt * (kt + 1) >> 1, rb1 = rb0 - kt, rb2 = rb1 - (kt - 1), rb3 = rb2 - (kt - 2);
+    float dv[4], Lb[6];
+    {
+      // 4x4 diagonal block (pivot order kt, kt-1, kt-2, kt-3), factorised redundantly by every lane
+      float a10 = 0.f, a11 = 1.f, a20 = 0.f, a21 = 0.f, a22 = 1.f, a30 = 0.f, a31 = 0.f, a32 = 0.f, a33 = 1.f;
+      float a00 = A[rb0 + kt];
+      if (nb > 1) { a10 = A[rb0 + kt - 1]; a11 = A[rb1 + kt - 1]; }
+      if (nb > 2) { a20 = A[rb0 + kt - 2]; a21 = A[rb1 + kt - 2]; a22 = A[rb2 + kt - 2]; }
+      if (nb > 3) { a30 = A[rb0 + kt - 3]; a31 = A[rb1 + kt - 3]; a32 = A[rb2 + kt - 3]; a33 = A[rb3 + kt - 3]; }
+      __syncwarp();  // every lane holds the block before any panel store touches it
+      dv[0] = b2_rcp(fmaxf(a00, MINVAL));
+      Lb[0] = a10 * dv[0];
+      dv[1] = b2_rcp(fmaxf(a11 - a10 * Lb[0], MINVAL));
+      Lb[1] = a20 * dv[0];
+      float t21 = a21 - a20 * Lb[0];
+      Lb[2] = t21 * dv[1];
+      dv[2] = b2_rcp(fmaxf(a22 - a20 * Lb[1] - t21 * Lb[2], MINVAL));
+      Lb[3] = a30 * dv[0];
+      float t31 = a31 - a30 * Lb[0];
+      Lb[4] = t31 * dv[1];
+      float t32 = a32 - a30 * Lb[1] - t31 * Lb[2];
+      Lb[5] = t32 * dv[2];
+      dv[3] = b2_rcp(fmaxf(a33 - a30 * Lb[3] - t31 * Lb[4] - t32 * Lb[5], MINVAL));
+      invdiag[kt] = dv[0];
+      if (nb > 1) invdiag[kt - 1] = dv[1];
+      if (nb > 2) invdiag[kt - 2] = dv[2];
+      if (nb > 3) invdiag[kt - 3] = dv[3];
+    }
+    // panel: the pivot rows kt-t at every column q < kt (lane = column); entry (kt-t, q) exists for q <= kt-t
+#pragma unroll 1
+    for (int base = 0; base < kt; base += 32) {
+      const int q = base + lane;
+      const bool ok = q < kt;
+      float r0 = ok ? A[rb0 + q] : 0.f;
+      float r1 = (ok && nb > 1 && q <= kt - 1) ? A[rb1 + q] : 0.f;
+      float r2 = (ok && nb > 2 && q <= kt - 2) ? A[rb2 + q] : 0.f;
+      float r3 = (ok && nb > 3 && q <= kt - 3) ? A[rb3 + q] : 0.f;
+      r1 -= r0 * Lb[0];
+      r2 -= r0 * Lb[1] + r1 * Lb[2];
+      r3 -= r0 * Lb[3] + r1 * Lb[4] + r2 * Lb[5];
+      if (ok && nb > 1 && q <= kt - 1) A[rb1 + q] = r1;
+      if (ok && nb > 2 && q <= kt - 2) A[rb2 + q] = r2;
+      if (ok && nb > 3 && q <= kt - 3) A[rb3 + q] = r3;
+    }
+    __syncwarp();
+    if (lead <= 0) break;  // (only the last block can be partial, and it has nothing left to update)
+    // trailing update: A[i,j] -= sum_t c_t,i c_t,j / d_t over the scheduled entries, c_t,q = A[kt-t, q]
+    const unsigned* lst = sparse ? slist + start[blk] : dense;
+    const int np = sparse ? start[blk + 1] - start[blk] : (lead * (lead + 1) >> 1);
+    int p = lane;
+#pragma unroll 1
+    for (; p + 32 < np; p += 64) {
+      unsigned e0 = lst[p], e1 = lst[p + 32];
+      int i0 = (e0 >> 12) & 63, j0 = e0 >> 18, i1 = (e1 >> 12) & 63, j1 = e1 >> 18;
+      float acc0 = A[rb0 + i0] * (A[rb0 + j0] * dv[0]) + A[rb1 + i0] * (A[rb1 + j0] * dv[1]) +
+                   A[rb2 + i0] * (A[rb2 + j0] * dv[2]) + A[rb3 + i0] * (A[rb3 + j0] * dv[3]);
+      float acc1 = A[rb0 + i1] * (A[rb0 + j1] * dv[0]) + A[rb1 + i1] * (A[rb1 + j1] * dv[1]) +
+                   A[rb2 + i1] * (A[rb2 + j1] * dv[2]) + A[rb3 + i1] * (A[rb3 + j1] * dv[3]);
+      A[e0 & 0xfff] -= acc0;
+      A[e1 & 0xfff] -= acc1;
+    }
+#pragma unroll 1
+    for (; p < np; p += 32) {
+      unsigned e0 = lst[p];
+      int i0 = (e0 >> 12) & 63, j0 = e0 >> 18;
+      A[e0 & 0xfff] -= A[rb0 + i0] * (A[rb0 + j0] * dv[0]) + A[rb1 + i0] * (A[rb1 + j0] * dv[1]) +
+                       A[rb2 + i0] * (A[rb2 + j0] * dv[2]) + A[rb3 + i0] * (A[rb3 + j0] * dv[3]);
+    }
+    __syncwarp();
+  }
+}
+// x <- (L^T D L)^-1 x for the factor above.  Rows >= 32 are kept out of the two 32-row sweeps (broadcasts in
+// the first sweep, warp reductions in the second).
+__device__ __noinline__ void ldl_solve(const float* L, const float* invdiag, float* x, int n, int lane) {
+  const int n0 = min(n, 32), nh = n - n0;
+  float x0 = lane < n0 ? x[lane] : 0.f;
+  float x1 = lane < nh ? x[lane + 32] : 0.f;
+  const float d0 = lane < n0 ? invdiag[lane] : 0.f, d1 = lane < nh ? invdiag[lane + 32] : 0.f;
+  const int r0 = lane * (lane + 1) >> 1;
+  // L^T y = b: pivots from the last row up; row k is contiguous (lane = column)
+#pragma unroll 1
+  for (int j = nh - 1; j >= 0; j--) {
+    const int rk = (32 + j) * (33 + j) >> 1;
+    float yk = __shfl_sync(FULL, x1, j) * invdiag[32 + j];
+    if (lane < j) x1 -= L[rk + 32 + lane] * yk;
+    x0 -= L[rk + lane] * yk;
+  }
+  int rk = n0 * (n0 - 1) >> 1;  // tri(n0 - 1, 0)
+#pragma unroll 1
+  for (int k = n0 - 1; k >= 0; k--) {
+    float t = lane < k ? L[rk + lane] * invdiag[k] : 0.f;
+    x0 = fmaf(-t, __shfl_sync(FULL, x0, k), x0);
+    rk -= k;
+  }
+  x0 *= d0; x1 *= d1;  // D z = y
+  // L x = z: x_k = z_k - (1/d_k) sum_{j<k} A[k,j] x_j, columns in ascending order (lane = row)
+#pragma unroll 1
+  for (int j = 0; j < n0; j++) {
+    float t = (lane > j && lane < n0) ? L[r0 + j] * d0 : 0.f;
+    x0 = fmaf(-t, __shfl_sync(FULL, x0, j), x0);
+  }
+#pragma unroll 1
+  for (int r = 0; r < nh; r++) {
+    const int rr = (32 + r) * (33 + r) >> 1;
+    float part = L[rr + lane] * x0;  // nh > 0 implies n0 == 32: every lane owns a row < 32
+    if (lane < r) part += L[rr + 32 + lane] * x1;
+    part = wsum(part);
+    if (lane == r) x1 -= d1 * part;
+  }
+  if (lane < n0) x[lane] = x0;
+  if (lane < nh) x[lane + 32] = x1;
+  __syncwarp();
+}
 // y = M x for packed symmetric M (both in shared memory).  One column loop for all lanes (entry (i,j) lives
 // at tri(max)+min), four independent accumulators so the loads of four columns are in flight together.
 #ifndef B2_SYMV_SIMPLE
@@ -738,8 +864,19 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
                     : dd.nworld;
   // per-CTA copy of the factorisation pair schedule (shared by the CTA's warps)
   unsigned* s_coldesc = (unsigned*)(smem_all + (size_t)B2_WARPS_PER_CTA * m.lay.total);
+#ifdef B2_DENSE_LDL
+#define FACTOR(sp) chol_factor(H, invdiag, nv, s_coldesc, lane)
+#define SOLVE(v) chol_solve(H, invdiag, v, nv, lane)
+#else
+#define FACTOR(sp) ldl_factor(H, invdiag, nv, s_coldesc, m.ldl_start, m.ldl_dense, sp, lane)
+#define SOLVE(v) ldl_solve(H, invdiag, v, nv, lane)
+#endif
 #pragma unroll 1
+#ifdef B2_DENSE_LDL
   for (int i = threadIdx.x; i < m.ntri; i += 32 * B2_WARPS_PER_CTA) s_coldesc[i] = m.tri_coldesc[i];
+#else
+  for (int i = threadIdx.x; i < m.ldl_nsparse; i += 32 * B2_WARPS_PER_CTA) s_coldesc[i] = m.ldl_sparse[i];
+#endif
   __syncthreads();  // the only block barrier; nothing below synchronises across warps
   if (w >= dd.nworld) return;
   if (dd.world_mask != nullptr && dd.world_mask[w] == 0) return;
@@ -1214,14 +1351,14 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       float fs = passive - bias + qfrc_applied[i] + tmpv[i] + dot6(cdof + SD * i, sx);
       qfrc_smooth[i] = fs;
       qacc_smooth[i] = fs;
-      if (m.debug) {
+      if (m.debug & 1) {
         dd.qfrc_bias.p[(size_t)w * dd.qfrc_bias.stride + i] = bias;
         dd.qfrc_smooth.p[(size_t)w * dd.qfrc_smooth.stride + i] = fs;
       }
     }
   }
   __syncwarp();
-  if (m.debug) {
+  if (m.debug & 1) {
     float* gM = dd.qM.p + (size_t)w * dd.qM.stride;
     #pragma unroll 1
     for (int p = lane; p < nv * nv; p += 32) {
@@ -1604,6 +1741,20 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   }
   if (lane == 0) gstart[ngroup] = ncon;
   __syncwarp();
+  // The Hessian keeps the dof tree's zero pattern unless a contact couples two branches (both bodies move and
+  // neither chain contains the other): only then the factorisation takes the dense schedule.
+  bool treeok = !(m.debug & 2);
+  #pragma unroll 1
+  for (int g0 = 0; g0 < ngroup; g0 += 32) {
+    bool bad = false;
+    if (g0 + lane < ngroup) {
+      int key = ((int*)con)[CINFO * MC + gstart[g0 + lane]] & 0xffff;
+      unsigned long long m1 = m.body_dofmask[key & 0xff], m2 = m.body_dofmask[key >> 8];
+      unsigned long long c = m1 & m2;
+      bad = c != m1 && c != m2;
+    }
+    if (__any_sync(FULL, bad)) treeok = false;
+  }
   int nefc = nlim;
   {
     int cnt = 0;
@@ -1639,9 +1790,9 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   #pragma unroll 1
   for (int i = lane; i < (m.ntri + 3) >> 2; i += 32) ((float4*)H)[i] = ((const float4*)Mq)[i];  // both regions are 16 B aligned and padded
   __syncwarp();
-  chol_factor(H, invdiag, nv, s_coldesc, lane);
-  chol_solve(H, invdiag, qacc_smooth, nv, lane);
-  if (m.debug)
+  FACTOR(true);
+  SOLVE(qacc_smooth);
+  if (m.debug & 1)
     #pragma unroll 1
     for (int i = lane; i < nv; i += 32) dd.qacc_smooth.p[(size_t)w * dd.qacc_smooth.stride + i] = qacc_smooth[i];
 
@@ -1806,9 +1957,8 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       for (int g = 0; g < ngroup; g++) {
         // A (6x6 symmetric, 21 entries), lane e owns entry (a,b)
         if (lane < 21) {
-          int a = 0, e = lane;
-          while (e >= 6 - a) { e -= 6 - a; a++; }
-          int b = a + e;
+          // (a, b), a <= b, of the lane's entry: 3-bit fields of two packed constants
+          const int a = (int)(0x591b692449240000ull >> (3 * lane)) & 7, b = (int)(0x5b2c76356346c688ull >> (3 * lane)) & 7;
           float acc = 0.f;
           for (int c = gstart[g]; c < gstart[g + 1]; c++) {
             float W00 = gW[c], W01 = gW[MC + c], W02 = gW[2 * MC + c], W11 = gW[3 * MC + c], W22 = gW[4 * MC + c];
@@ -1894,11 +2044,11 @@ B2_UNROLL(B2_UNR_HPROJ)
       }
 #endif
       PHASE_MARK(13);
-      chol_factor(H, invdiag, nv, s_coldesc, lane);
+      FACTOR(treeok);
       #pragma unroll 1
       for (int i = lane; i < nv; i += 32) search[i] = -grad[i];
       __syncwarp();
-      chol_solve(H, invdiag, search, nv, lane);
+      SOLVE(search);
       PHASE_MARK(14);
       // ---- exact line search along `search` --------------------------------------------------
       symv(Mq, search, Mv, nv, lane);
@@ -2125,8 +2275,8 @@ B2_UNROLL(B2_UNR_HPROJ)
       #pragma unroll 1
       for (int i = lane; i < nv; i += 32) tmpv[i] = qfrc_smooth[i] + qfrc_c[i];
       __syncwarp();
-      chol_factor(H, invdiag, nv, s_coldesc, lane);
-      chol_solve(H, invdiag, tmpv, nv, lane);
+      FACTOR(true);
+      SOLVE(tmpv);
     } else {
       #pragma unroll 1
       for (int i = lane; i < nv; i += 32) tmpv[i] = qacc[i];
@@ -2168,7 +2318,7 @@ B2_UNROLL(B2_UNR_HPROJ)
     float* gqa = dd.qacc.p + (size_t)w * dd.qacc.stride;
     #pragma unroll 1
     for (int i = lane; i < nv; i += 32) gqa[i] = qacc[i];
-    if (m.debug) {
+    if (m.debug & 1) {
       float* gfc = dd.qfrc_constraint.p + (size_t)w * dd.qfrc_constraint.stride;
       #pragma unroll 1
       for (int i = lane; i < nv; i += 32) gfc[i] = qfrc_c[i];

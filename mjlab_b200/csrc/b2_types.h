@@ -96,6 +96,12 @@ struct DevModel {
   const int *sensor_adr, *sensor_dim;
   const unsigned short* tri_rowmajor;
   const unsigned* tri_coldesc;
+  // bottom-up (leaves first) blocked L^T D L: trailing-update schedules, one word per target entry
+  // p | i << 12 | j << 18.  ldl_dense: every packed index in order (a block with m leading rows uses the
+  // first tri(m)); ldl_sparse: per block only the entries the dof tree can make non-zero.
+  const unsigned *ldl_dense, *ldl_sparse;
+  int ldl_start[18];
+  int ldl_nsparse;
   // float arrays (expandable per world)
   FArr body_pos, body_quat, body_ipos, body_iquat, body_mass, body_subtreemass, body_inertia,
       body_invweight0, jnt_pos, jnt_axis, jnt_range, jnt_solref, jnt_solimp, jnt_margin,

@@ -479,6 +479,34 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
   }
   rc |= dev_upload<int>(s, cslot, &m.geom_cslot);
   rc |= dev_upload<int>(s, cgeom, &m.cgeom);
+  {
+    // schedules of the bottom-up blocked factorisation (b2_kernel.cuh: ldl_factor)
+    const std::vector<int>& dpar = s->mi["dof_parentid"];
+    std::vector<unsigned long long> danc(m.nv, 0ull);  // strict dof ancestors
+    for (int k = 0; k < m.nv; k++)
+      for (int a = dpar[k]; a >= 0; a = dpar[a]) danc[k] |= 1ull << a;
+    std::vector<unsigned> dense, sparse;
+    for (int i = 0; i < m.nv; i++)
+      for (int j = 0; j <= i; j++) dense.push_back((unsigned)(i * (i + 1) / 2 + j) | ((unsigned)i << 12) | ((unsigned)j << 18));
+    int blk = 0;
+    for (int kt = m.nv - 1; kt >= 0; kt -= 4, blk++) {
+      int nbk = std::min(4, kt + 1), lead = kt - nbk + 1;
+      m.ldl_start[blk] = (int)sparse.size();
+      for (int i = 0; i < lead; i++)
+        for (int j = 0; j <= i; j++) {
+          bool hit = false;
+          for (int t = 0; t < nbk; t++) {
+            unsigned long long a = danc[kt - t];
+            if ((a >> i & 1ull) && (a >> j & 1ull)) hit = true;
+          }
+          if (hit) sparse.push_back((unsigned)(i * (i + 1) / 2 + j) | ((unsigned)i << 12) | ((unsigned)j << 18));
+        }
+    }
+    for (int b = blk; b < 18; b++) m.ldl_start[b] = (int)sparse.size();
+    m.ldl_nsparse = (int)sparse.size();
+    rc |= dev_upload<unsigned>(s, dense, &m.ldl_dense);
+    rc |= dev_upload<unsigned>(s, sparse, &m.ldl_sparse);
+  }
   rc |= dev_upload<unsigned short>(s, trow, &m.tri_rowmajor);
   rc |= dev_upload<unsigned>(s, tcol, &m.tri_coldesc);
   if (rc) { b2_destroy(s); return 1; }
@@ -588,7 +616,11 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
   L.gW = alloc(5 * mc); L.sens = off;
   int endB = off;
   L.total = pad4(std::max(endA, endB));
+#ifdef B2_DENSE_LDL
   s->smem_bytes = sizeof(float) * ((size_t)L.total * B2_WARPS_PER_CTA + pad4(m.ntri));
+#else
+  s->smem_bytes = sizeof(float) * ((size_t)L.total * B2_WARPS_PER_CTA + pad4(std::max(m.ldl_nsparse, 1)));
+#endif
   if (s->smem_bytes > 227 * 1024) {
     b2_destroy(s);
     return fail("b2_create: model too large for the per-environment shared-memory block");
@@ -715,7 +747,8 @@ int b2_set_option(b2_sim* s, const char* key, double v) {
   else if (k == "ls_tolerance") m.ls_tolerance = (float)v;
   else if (k == "timestep") m.timestep = (float)v;
   else if (k == "integrator") m.integrator = (int)v;
-  else if (k == "debug_outputs") m.debug = (int)v;
+  else if (k == "debug_outputs") m.debug = (m.debug & ~1) | ((int)v & 1);
+  else if (k == "dense_factor") m.debug = (m.debug & ~2) | ((int)v ? 2 : 0);  // force the dense LDL schedule (tests)
   else if (k == "ls_parallel") { /* accepted for API parity; the line search here is exact */ }
   else if (k == "sorted_dispatch") s->sorted_dispatch = (int)v;
   else if (k == "fused_decimation") s->fused_decimation = (int)v;
@@ -733,7 +766,8 @@ int b2_get_option(b2_sim* s, const char* key, double* v) {
   else if (k == "ls_tolerance") *v = m.ls_tolerance;
   else if (k == "timestep") *v = m.timestep;
   else if (k == "integrator") *v = m.integrator;
-  else if (k == "debug_outputs") *v = m.debug;
+  else if (k == "debug_outputs") *v = m.debug & 1;
+  else if (k == "dense_factor") *v = (m.debug >> 1) & 1;
   else if (k == "smem_bytes_per_env") *v = 4.0 * m.lay.total;
   else if (k == "maxcon") *v = m.maxcon;
   else return fail("b2_get_option: unknown option '" + k + "'");

@@ -393,3 +393,34 @@ def test_world_counts_not_multiple_of_cta(g1_model, n):
   e = relerr(T(sim.data.qvel), o.qvel)
   assert e.max() < 2e-3 and np.median(e) < 1e-4, (e.max(), np.median(e))
   sim.close()
+
+
+def test_tree_and_dense_factor_schedules_agree(g1_model):
+  """The bottom-up L^T D L takes the dof-tree schedule unless a contact couples two branches; forcing the
+  dense schedule everywhere must give the same step (both paths are exercised: self-contacts occur in this batch)."""
+  from mjlab_b200.sim import Simulation, SimulationCfg
+  from oracle.oracle import Oracle
+
+  n = 192
+  a = Simulation(n, SimulationCfg(), g1_model, "cuda:0")
+  b = Simulation(n, SimulationCfg(), g1_model, "cuda:0")
+  b.set_option("dense_factor", 1)
+  assert b.get_option("dense_factor") == 1 and a.get_option("dense_factor") == 0
+  st = make_states(g1_model, n, seed=77, joint_noise=0.6)
+  load_sim(a, st)
+  load_sim(b, st)
+  a.step_n(1)
+  b.step_n(1)
+  torch.cuda.synchronize()
+  o = Oracle(g1_model, nworld=n, maxcon=int(a.get_option("maxcon")))
+  load_oracle(o, st)
+  o.step()
+  body = o.field("contact_geom").reshape(n, -1, 2)
+  gb = np.asarray(g1_model.geom_bodyid)
+  self_contact = sum(int(((gb[body[w, : o.ncon[w, 0], 0]] > 1) & (gb[body[w, : o.ncon[w, 0], 1]] > 1)).any()) for w in range(n))
+  assert self_contact >= 5, self_contact  # robot-robot contacts present -> the dense schedule is taken by the default path too
+  ea, eb = relerr(T(a.data.qvel), o.qvel), relerr(T(b.data.qvel), o.qvel)
+  assert np.median(ea) < 1e-4 and np.median(eb) < 1e-4 and ea.max() < 3e-3 and eb.max() < 3e-3, (ea.max(), eb.max())
+  assert relerr(T(a.data.qvel), T(b.data.qvel)).max() < 3e-3
+  a.close()
+  b.close()
