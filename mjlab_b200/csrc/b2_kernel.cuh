@@ -29,6 +29,9 @@
 #ifndef B2_UNR_HPROJ
 #define B2_UNR_HPROJ 1
 #endif
+#ifndef B2_UNR_SOLVE
+#define B2_UNR_SOLVE 1
+#endif
 #define B2_STR(x) #x
 #define B2_PRAGMA(x) _Pragma(B2_STR(x))
 #define B2_UNROLL(n) B2_PRAGMA(unroll n)
@@ -505,7 +508,8 @@ __device__ __noinline__ void ldl_solve(const float* L, const float* invdiag, flo
     x0 -= L[rk + lane] * yk;
   }
   int rk = n0 * (n0 - 1) >> 1;  // tri(n0 - 1, 0)
-#pragma unroll 1
+  // (unrolled so that the loads of four steps are in flight while the shuffle/FMA chain advances)
+B2_UNROLL(B2_UNR_SOLVE)
   for (int k = n0 - 1; k >= 0; k--) {
     float t = lane < k ? L[rk + lane] * invdiag[k] : 0.f;
     x0 = fmaf(-t, __shfl_sync(FULL, x0, k), x0);
@@ -513,7 +517,7 @@ __device__ __noinline__ void ldl_solve(const float* L, const float* invdiag, flo
   }
   x0 *= d0; x1 *= d1;  // D z = y
   // L x = z: x_k = z_k - (1/d_k) sum_{j<k} A[k,j] x_j, columns in ascending order (lane = row)
-#pragma unroll 1
+B2_UNROLL(B2_UNR_SOLVE)
   for (int j = 0; j < n0; j++) {
     float t = (lane > j && lane < n0) ? L[r0 + j] * d0 : 0.f;
     x0 = fmaf(-t, __shfl_sync(FULL, x0, j), x0);
@@ -868,7 +872,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
 #define FACTOR(sp) chol_factor(H, invdiag, nv, s_coldesc, lane)
 #define SOLVE(v) chol_solve(H, invdiag, v, nv, lane)
 #else
-#define FACTOR(sp) ldl_factor(H, invdiag, nv, s_coldesc, m.ldl_start, m.ldl_dense, sp, lane)
+#define FACTOR(sp) ldl_factor(H, invdiag, nv, s_coldesc, (const int*)s_coldesc + m.ldl_nsparse, m.ldl_dense, sp, lane)
 #define SOLVE(v) ldl_solve(H, invdiag, v, nv, lane)
 #endif
 #pragma unroll 1
@@ -876,6 +880,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   for (int i = threadIdx.x; i < m.ntri; i += 32 * B2_WARPS_PER_CTA) s_coldesc[i] = m.tri_coldesc[i];
 #else
   for (int i = threadIdx.x; i < m.ldl_nsparse; i += 32 * B2_WARPS_PER_CTA) s_coldesc[i] = m.ldl_sparse[i];
+  if (threadIdx.x < 18) s_coldesc[m.ldl_nsparse + threadIdx.x] = (unsigned)m.ldl_start[threadIdx.x];
 #endif
   __syncthreads();  // the only block barrier; nothing below synchronises across warps
   if (w >= dd.nworld) return;

@@ -619,7 +619,7 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
 #ifdef B2_DENSE_LDL
   s->smem_bytes = sizeof(float) * ((size_t)L.total * B2_WARPS_PER_CTA + pad4(m.ntri));
 #else
-  s->smem_bytes = sizeof(float) * ((size_t)L.total * B2_WARPS_PER_CTA + pad4(std::max(m.ldl_nsparse, 1)));
+  s->smem_bytes = sizeof(float) * ((size_t)L.total * B2_WARPS_PER_CTA + pad4(m.ldl_nsparse + 18));
 #endif
   if (s->smem_bytes > 227 * 1024) {
     b2_destroy(s);
