@@ -159,8 +159,13 @@ class CpuPort:
 
     self.np = np
     m = load_compiled("g1_flat")
-    probe = Oracle(m, nworld=1, precision="f32")
-    self.cores = nthreads or probe.max_threads()
+    # all host cores this process may use; torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+    # otherwise shrink the CPU arm to one thread when the driver launches it under torchrun (N > 1)
+    try:
+      avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+      avail = os.cpu_count() or 1
+    self.cores = nthreads or avail
     self.n = max(self.cores * envs_per_thread, 8)
     self.o = Oracle(m, nworld=self.n, maxcon=48, precision="f32")
     self.rng = np.random.default_rng(42)
