@@ -305,8 +305,13 @@ def main():
       else:
         e1.record()
       ev.append((e0, e1))
+    # the log gather runs on a side stream; its tail after the last step belongs to the timed region
+    j0, j1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    j0.record()
+    gather_logs.join()
+    j1.record()
     torch.cuda.synchronize()
-    total = sum(a.elapsed_time(b) for a, b in ev)
+    total = sum(a.elapsed_time(b) for a, b in ev) + j0.elapsed_time(j1)
     return total, (n * nu * 4, n * 4 + n * 2 + (obs.numel() * 4)) if kind == "host" else None
 
   def barrier():

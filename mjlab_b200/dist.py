@@ -35,23 +35,57 @@ def shard_range(num_envs_total: int, rank: int, world: int) -> tuple[int, int]:
 
 
 class EnvLogGather:
-  """Preallocated all-gather of (reward f32, terminated, truncated) -> ``[world, n, 3]`` float32."""
+  """Preallocated all-gather of (reward f32, terminated, truncated) -> ``[world, n, 3]`` float32.
+
+  On CUDA the collective runs on a side stream: the env step never waits for the other
+  ranks, the gather of step k overlaps the physics of step k+1, and two packing buffers keep a step from
+  overwriting what the previous gather is still reading.  ``join()`` makes the current stream wait for the
+  outstanding gather (call it before reading ``out`` or ending a timed region)."""
 
   def __init__(self, num_envs: int, device, group=None):
     self.world = dist.get_world_size(group) if dist.is_initialized() else 1
     self.group = group
     self.n = num_envs
-    self.packed = torch.empty((num_envs, 3), dtype=torch.float32, device=device)
-    self.out = torch.empty((self.world, num_envs, 3), dtype=torch.float32, device=device)
+    dev = torch.device(device)
+    self.cuda = dev.type == "cuda"
+    self.packed = [torch.empty((num_envs, 3), dtype=torch.float32, device=dev) for _ in range(2)]
+    self.out = torch.empty((self.world, num_envs, 3), dtype=torch.float32, device=dev)
+    self.k = 0
+    if self.cuda:
+      self.side = torch.cuda.Stream(device=dev)
+      self.ready = torch.cuda.Event()
+      self.done = [torch.cuda.Event(), torch.cuda.Event()]
+      self.pending = [False, False]
 
   def __call__(self, reward: torch.Tensor, terminated: torch.Tensor, truncated: torch.Tensor):
-    self.packed[:, 0] = reward
-    self.packed[:, 1] = terminated.to(torch.float32)
-    self.packed[:, 2] = truncated.to(torch.float32)
-    if self.world == 1:
-      self.out[0] = self.packed
-    else:
-      dist.all_gather_into_tensor(self.out.view(self.world * self.n, 3), self.packed, group=self.group)
+    i = self.k & 1
+    self.k += 1
+    buf = self.packed[i]
+    if self.cuda and self.pending[i]:
+      torch.cuda.current_stream().wait_event(self.done[i])  # the gather that read this buffer two steps ago
+    buf[:, 0] = reward
+    buf[:, 1] = terminated.to(torch.float32)
+    buf[:, 2] = truncated.to(torch.float32)
+    if not self.cuda:
+      if self.world == 1:
+        self.out[0] = buf
+      else:
+        dist.all_gather_into_tensor(self.out.view(self.world * self.n, 3), buf, group=self.group)
+      return self.out
+    self.ready.record()
+    with torch.cuda.stream(self.side):
+      self.side.wait_event(self.ready)
+      if self.world == 1:
+        self.out[0] = buf
+      else:
+        dist.all_gather_into_tensor(self.out.view(self.world * self.n, 3), buf, group=self.group)
+      self.done[i].record()
+    self.pending[i] = True
+    return self.out
+
+  def join(self):
+    if self.cuda:
+      torch.cuda.current_stream().wait_stream(self.side)
     return self.out
 
   @staticmethod
