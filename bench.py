@@ -271,13 +271,15 @@ def main():
   from mjlab_b200.dist import EnvLogGather
 
   # the one collective of the data-parallel path: per-env (reward, done) to rank 0 for logging
-  gather_logs = EnvLogGather(n, dev)
+  gathers = {"device": EnvLogGather(n, dev), "host": EnvLogGather(n, dev, overlap=True)}
 
   def run(kind: str, steps: int, timed: bool):
     """kind: 'device' (actions resident) or 'host' (pinned host actions, results read back)."""
     ev = []
     phys_ms = 0.0
     host_actions = None
+    # stream-ordered when steps are enqueued back to back, side stream when the host syncs every step
+    gather_logs = gathers[kind]
     if kind == "host":
       host_actions = [(torch.rand((n, nu)) * 2 - 1).pin_memory() for _ in range(steps)]
       out_r = torch.empty(n, pin_memory=True)
