@@ -26,15 +26,6 @@
 #define SD 7   // 6-float records: cdof, cdofdot, cvel, cacc / wrenches
 #define SI 11  // 10-float records: cinert, crb
 
-#ifndef B2_UNR_HPROJ
-#define B2_UNR_HPROJ 1
-#endif
-#ifndef B2_UNR_SOLVE
-#define B2_UNR_SOLVE 1
-#endif
-#define B2_STR(x) #x
-#define B2_PRAGMA(x) _Pragma(B2_STR(x))
-#define B2_UNROLL(n) B2_PRAGMA(unroll n)
 
 namespace b2 {
 
@@ -186,227 +177,6 @@ __device__ __forceinline__ float b2_rcp(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-// ---- dense packed LDL^T (lower, row-major packed) in shared memory --------------------------------
-// In place: after the call A[k,k] = d_k and A[i,k] = L_ik d_k (i > k); invdiag[k] = 1/d_k.  One warp
-// barrier per pivot.  Balanced schedule: the trailing-triangle update of step k runs over a list of
-// (i,j) pairs ordered by descending j (a prefix of the list per k), one table word per pair packing the
-// row bases: rb_i | rb_j << 11 | j << 22.  `coldesc` lives in shared memory (per CTA).
-__device__ __noinline__ void chol_factor(float* A, float* invdiag, int n, const unsigned* coldesc,
-                                         int lane) {
-  // Blocked right-looking LDL^T, 4 pivots per block step: a register-resident panel factorisation
-  // (lane = row) followed by one rank-4 trailing update over the balanced pair list.
-#pragma unroll 1
-  for (int k = 0; k < n; k += 4) {
-    const int nb = min(4, n - k);
-    float dv[4] = {0.f, 0.f, 0.f, 0.f};      // 1/d of the block's pivots (warp-uniform)
-    float Lb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // L10, L20, L21, L30, L31, L32 (warp-uniform)
-    // ---- panel: rows k.., columns k..k+nb-1 -------------------------------------------------
-#ifndef B2_PANEL_SHUFFLE
-    {
-      // the 4x4 diagonal block is factorised redundantly by every lane from ten broadcast loads (no
-      // shuffle chain); then every row of the panel, block rows included, gets the same three updates
-      const int q0 = k * (k + 1) >> 1, q1 = q0 + k + 1, q2 = q1 + k + 2, q3 = q2 + k + 3;
-      float a10 = 0.f, a11 = 1.f, a20 = 0.f, a21 = 0.f, a22 = 1.f, a30 = 0.f, a31 = 0.f, a32 = 0.f, a33 = 1.f;
-      float a00 = A[q0 + k];
-      if (nb > 1) { a10 = A[q1 + k]; a11 = A[q1 + k + 1]; }
-      if (nb > 2) { a20 = A[q2 + k]; a21 = A[q2 + k + 1]; a22 = A[q2 + k + 2]; }
-      if (nb > 3) { a30 = A[q3 + k]; a31 = A[q3 + k + 1]; a32 = A[q3 + k + 2]; a33 = A[q3 + k + 3]; }
-      __syncwarp();  // every lane holds the block before any panel store touches it
-      dv[0] = b2_rcp(fmaxf(a00, MINVAL));
-      Lb[0] = a10 * dv[0];
-      dv[1] = b2_rcp(fmaxf(a11 - a10 * Lb[0], MINVAL));
-      Lb[1] = a20 * dv[0];
-      float t21 = a21 - a20 * Lb[0];
-      Lb[2] = t21 * dv[1];
-      dv[2] = b2_rcp(fmaxf(a22 - a20 * Lb[1] - t21 * Lb[2], MINVAL));
-      Lb[3] = a30 * dv[0];
-      float t31 = a31 - a30 * Lb[0];
-      Lb[4] = t31 * dv[1];
-      float t32 = a32 - a30 * Lb[1] - t31 * Lb[2];
-      Lb[5] = t32 * dv[2];
-      dv[3] = b2_rcp(fmaxf(a33 - a30 * Lb[3] - t31 * Lb[4] - t32 * Lb[5], MINVAL));
-      // every lane holds the same four values: plain same-address stores, no select chain
-      invdiag[k] = dv[0];
-      if (nb > 1) invdiag[k + 1] = dv[1];
-      if (nb > 2) invdiag[k + 2] = dv[2];
-      if (nb > 3) invdiag[k + 3] = dv[3];
-    }
-#pragma unroll 1
-    for (int base = k; base < n; base += 32) {
-      int i = base + lane;
-      bool ok = i < n;
-      int ri = ok ? (i * (i + 1) >> 1) : 0;
-      float r[4];
-#pragma unroll
-      for (int t = 0; t < 4; t++) r[t] = (ok && t < nb && k + t <= i) ? A[ri + k + t] : 0.f;
-      r[1] -= r[0] * Lb[0];
-      r[2] -= r[0] * Lb[1] + r[1] * Lb[2];
-      r[3] -= r[0] * Lb[3] + r[1] * Lb[4] + r[2] * Lb[5];
-      if (ok) {
-#pragma unroll
-        for (int t = 1; t < 4; t++)
-          if (t < nb && k + t <= i) A[ri + k + t] = r[t];
-      }
-    }
-#else
-#pragma unroll 1
-    for (int base = k; base < n; base += 32) {
-      int i = base + lane;
-      bool ok = i < n;
-      int ri = ok ? (i * (i + 1) >> 1) : 0;
-      float r[4];
-#pragma unroll
-      for (int t = 0; t < 4; t++) r[t] = (ok && t < nb && k + t <= i) ? A[ri + k + t] : 0.f;
-      if (base == k) {
-        // block rows are lanes 0..nb-1 of the first pass: factor the 4x4 diagonal block by shuffles
-        float d0 = __shfl_sync(FULL, r[0], 0);
-        dv[0] = __frcp_rn(fmaxf(d0, MINVAL));
-        if (nb > 1) {
-          Lb[0] = __shfl_sync(FULL, r[0], 1) * dv[0];
-          if (i > k) r[1] -= r[0] * Lb[0];
-          dv[1] = __frcp_rn(fmaxf(__shfl_sync(FULL, r[1], 1), MINVAL));
-        }
-        if (nb > 2) {
-          Lb[1] = __shfl_sync(FULL, r[0], 2) * dv[0];
-          Lb[2] = __shfl_sync(FULL, r[1], 2) * dv[1];
-          if (i > k + 1) r[2] -= r[0] * Lb[1] + r[1] * Lb[2];
-          dv[2] = __frcp_rn(fmaxf(__shfl_sync(FULL, r[2], 2), MINVAL));
-        }
-        if (nb > 3) {
-          Lb[3] = __shfl_sync(FULL, r[0], 3) * dv[0];
-          Lb[4] = __shfl_sync(FULL, r[1], 3) * dv[1];
-          Lb[5] = __shfl_sync(FULL, r[2], 3) * dv[2];
-          if (i > k + 2) r[3] -= r[0] * Lb[3] + r[1] * Lb[4] + r[2] * Lb[5];
-          dv[3] = __frcp_rn(fmaxf(__shfl_sync(FULL, r[3], 3), MINVAL));
-        }
-        if (lane < nb) invdiag[k + lane] = lane == 0 ? dv[0] : (lane == 1 ? dv[1] : (lane == 2 ? dv[2] : dv[3]));
-      } else {
-        r[1] -= r[0] * Lb[0];
-        r[2] -= r[0] * Lb[1] + r[1] * Lb[2];
-        r[3] -= r[0] * Lb[3] + r[1] * Lb[4] + r[2] * Lb[5];
-      }
-      if (ok) {
-#pragma unroll
-        for (int t = 1; t < 4; t++)
-          if (t < nb && k + t <= i) A[ri + k + t] = r[t];
-      }
-    }
-#endif
-    __syncwarp();
-    // ---- trailing update: A[i,j] -= sum_t c_i,k+t * c_j,k+t / d_t for j >= k+nb ---------------
-    int mtr = n - k - nb;
-    if (mtr <= 0) break;
-    int np = mtr * (mtr + 1) >> 1;
-    if (nb == 4) {
-      int p = lane;
-#pragma unroll 1
-      for (; p + 32 < np; p += 64) {
-        unsigned e0 = coldesc[p], e1 = coldesc[p + 32];
-        int ri0 = (e0 & 0x7ff) + k, rj0 = ((e0 >> 11) & 0x7ff) + k, t0 = (e0 & 0x7ff) + (e0 >> 22);
-        int ri1 = (e1 & 0x7ff) + k, rj1 = ((e1 >> 11) & 0x7ff) + k, t1 = (e1 & 0x7ff) + (e1 >> 22);
-        float acc0 = A[ri0] * (A[rj0] * dv[0]) + A[ri0 + 1] * (A[rj0 + 1] * dv[1]) +
-                     A[ri0 + 2] * (A[rj0 + 2] * dv[2]) + A[ri0 + 3] * (A[rj0 + 3] * dv[3]);
-        float acc1 = A[ri1] * (A[rj1] * dv[0]) + A[ri1 + 1] * (A[rj1 + 1] * dv[1]) +
-                     A[ri1 + 2] * (A[rj1 + 2] * dv[2]) + A[ri1 + 3] * (A[rj1 + 3] * dv[3]);
-        A[t0] -= acc0;
-        A[t1] -= acc1;
-      }
-#pragma unroll 1
-      for (; p < np; p += 32) {
-        unsigned e0 = coldesc[p];
-        int ri0 = (e0 & 0x7ff) + k, rj0 = ((e0 >> 11) & 0x7ff) + k, t0 = (e0 & 0x7ff) + (e0 >> 22);
-        A[t0] -= A[ri0] * (A[rj0] * dv[0]) + A[ri0 + 1] * (A[rj0 + 1] * dv[1]) +
-                 A[ri0 + 2] * (A[rj0 + 2] * dv[2]) + A[ri0 + 3] * (A[rj0 + 3] * dv[3]);
-      }
-    } else {
-#pragma unroll 1
-      for (int p = lane; p < np; p += 32) {
-        unsigned e0 = coldesc[p];
-        int ri0 = (e0 & 0x7ff) + k, rj0 = ((e0 >> 11) & 0x7ff) + k, t0 = (e0 & 0x7ff) + (e0 >> 22);
-        float acc = 0.f;
-        for (int t = 0; t < nb; t++) acc += A[ri0 + t] * (A[rj0 + t] * dv[t]);
-        A[t0] -= acc;
-      }
-    }
-    __syncwarp();
-  }
-}
-// x <- (L D L^T)^-1 x, x in shared memory (n <= 64); values stay in registers during the sweeps.
-// (A 4-pivot blocked variant - redundant 4x4 block solve + rank-4 row update, 2*ceil(n/4) dependent steps -
-// measured 10 % slower end to end: the guards cost more issue slots than the shorter chain saves.)
-#ifndef B2_SOLVE_SIMPLE
-// Rows >= 32 (three of them for the 35-dof G1) are kept out of the two 32-row sweeps: their couplings are
-// applied by warp reductions (forward) and broadcasts (backward), so the long loops carry one row per lane.
-__device__ __noinline__ void chol_solve(const float* L, const float* invdiag, float* x, int n,
-                                        int lane) {
-  const int n0 = min(n, 32), nh = n - n0;
-  float x0 = lane < n0 ? x[lane] : 0.f;
-  float x1 = lane < nh ? x[lane + 32] : 0.f;
-  const float d0 = lane < n0 ? invdiag[lane] : 0.f, d1 = lane < nh ? invdiag[lane + 32] : 0.f;
-  const int r0 = lane * (lane + 1) >> 1;
-#pragma unroll 1
-  for (int k = 0; k < n0; k++) {  // L y = b, rows < 32 (the scaled entry is ready before x_k arrives)
-    float t = (lane > k && lane < n0) ? L[r0 + k] * invdiag[k] : 0.f;
-    x0 = fmaf(-t, __shfl_sync(FULL, x0, k), x0);
-  }
-  if (nh > 0) {
-    const float w0 = x0 * d0;
-#pragma unroll 1
-    for (int r = 0; r < nh; r++) {  // y_hi[r] = b_hi[r] - sum_j L[32+r, j] y_j
-      const int rr = (32 + r) * (33 + r) >> 1;
-      float part = L[rr + lane] * w0;
-      if (lane < r) part += L[rr + 32 + lane] * (x1 * d1);
-      part = wsum(part);
-      if (lane == r) x1 -= part;
-    }
-  }
-  x0 *= d0; x1 *= d1;  // D z = y
-  if (nh > 0) {
-#pragma unroll 1
-    for (int j = nh - 1; j >= 0; j--) {  // L^T x = z: rows >= 32 first, then their effect on rows < 32
-      const int rj = (32 + j) * (33 + j) >> 1;
-      float xj = __shfl_sync(FULL, x1, j);
-      if (lane < j) x1 -= L[rj + 32 + lane] * d1 * xj;
-      x0 -= L[rj + lane] * d0 * xj;
-    }
-  }
-  int rk = n0 * (n0 - 1) >> 1;  // tri(n0 - 1, 0)
-#pragma unroll 1
-  for (int k = n0 - 1; k >= 0; k--) {
-    float t = lane < k ? L[rk + lane] * d0 : 0.f;
-    x0 = fmaf(-t, __shfl_sync(FULL, x0, k), x0);
-    rk -= k;
-  }
-  if (lane < n0) x[lane] = x0;
-  if (lane < nh) x[lane + 32] = x1;
-  __syncwarp();
-}
-#else
-__device__ __noinline__ void chol_solve(const float* L, const float* invdiag, float* x, int n,
-                                        int lane) {
-  float x0 = lane < n ? x[lane] : 0.f;
-  float x1 = lane + 32 < n ? x[lane + 32] : 0.f;
-  const float d0 = lane < n ? invdiag[lane] : 0.f, d1 = lane + 32 < n ? invdiag[lane + 32] : 0.f;
-  const int r0 = lane * (lane + 1) >> 1, r1 = (lane + 32) * (lane + 33) >> 1;
-#pragma unroll 1
-  for (int k = 0; k < n; k++) {  // L y = b
-    float xk = __shfl_sync(FULL, k < 32 ? x0 : x1, k & 31) * invdiag[k];
-    if (lane > k && lane < n) x0 -= L[r0 + k] * xk;
-    if (lane + 32 > k && lane + 32 < n) x1 -= L[r1 + k] * xk;
-  }
-  x0 *= d0; x1 *= d1;  // D z = y
-#pragma unroll 1
-  for (int k = n - 1; k >= 0; k--) {  // L^T x = z
-    float xk = __shfl_sync(FULL, k < 32 ? x0 : x1, k & 31);
-    int rk = k * (k + 1) >> 1;
-    if (lane < k) x0 -= L[rk + lane] * d0 * xk;
-    if (lane + 32 < k) x1 -= L[rk + lane + 32] * d1 * xk;
-  }
-  if (lane < n) x[lane] = x0;
-  if (lane + 32 < n) x[lane + 32] = x1;
-  __syncwarp();
-}
-#endif
 // ---- bottom-up blocked L^T D L (leaves first) -----------------------------------------------------------
 // Pivots are eliminated from the last dof to the first, four per block step, so the dof tree's zero pattern
 // survives (no fill between branches) and the trailing update visits only the entries the tree can make
@@ -509,7 +279,7 @@ __device__ __noinline__ void ldl_solve(const float* L, const float* invdiag, flo
   }
   int rk = n0 * (n0 - 1) >> 1;  // tri(n0 - 1, 0)
   // (unrolled so that the loads of four steps are in flight while the shuffle/FMA chain advances)
-B2_UNROLL(B2_UNR_SOLVE)
+#pragma unroll 1
   for (int k = n0 - 1; k >= 0; k--) {
     float t = lane < k ? L[rk + lane] * invdiag[k] : 0.f;
     x0 = fmaf(-t, __shfl_sync(FULL, x0, k), x0);
@@ -517,7 +287,7 @@ B2_UNROLL(B2_UNR_SOLVE)
   }
   x0 *= d0; x1 *= d1;  // D z = y
   // L x = z: x_k = z_k - (1/d_k) sum_{j<k} A[k,j] x_j, columns in ascending order (lane = row)
-B2_UNROLL(B2_UNR_SOLVE)
+#pragma unroll 1
   for (int j = 0; j < n0; j++) {
     float t = (lane > j && lane < n0) ? L[r0 + j] * d0 : 0.f;
     x0 = fmaf(-t, __shfl_sync(FULL, x0, j), x0);
@@ -536,7 +306,6 @@ B2_UNROLL(B2_UNR_SOLVE)
 }
 // y = M x for packed symmetric M (both in shared memory).  One column loop for all lanes (entry (i,j) lives
 // at tri(max)+min), four independent accumulators so the loads of four columns are in flight together.
-#ifndef B2_SYMV_SIMPLE
 __device__ __noinline__ void symv(const float* M, const float* x, float* y, int n, int lane) {
   #pragma unroll 1
   for (int i = lane; i < n; i += 32) {
@@ -562,21 +331,6 @@ __device__ __noinline__ void symv(const float* M, const float* x, float* y, int 
   }
   __syncwarp();
 }
-#else
-__device__ __noinline__ void symv(const float* M, const float* x, float* y, int n, int lane) {
-  #pragma unroll 1
-  for (int i = lane; i < n; i += 32) {
-    float t = 0.f;
-    int ri = i * (i + 1) >> 1;
-    #pragma unroll 1
-    for (int j = 0; j <= i; j++) t += M[ri + j] * x[j];
-    int idx = ri + i + i + 1;  // tri(i+1, i)
-    for (int j = i + 1; j < n; j++) { t += M[idx] * x[j]; idx += j + 1; }
-    y[i] = t;
-  }
-  __syncwarp();
-}
-#endif
 
 // ---- narrowphase primitives (engine_collision_primitive.c semantics) ----
 struct RawCon {
@@ -867,21 +621,12 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
                     ? (dd.world_order != nullptr ? dd.world_order[dd.world_base + slot] : dd.world_base + slot)
                     : dd.nworld;
   // per-CTA copy of the factorisation pair schedule (shared by the CTA's warps)
-  unsigned* s_coldesc = (unsigned*)(smem_all + (size_t)B2_WARPS_PER_CTA * m.lay.total);
-#ifdef B2_DENSE_LDL
-#define FACTOR(sp) chol_factor(H, invdiag, nv, s_coldesc, lane)
-#define SOLVE(v) chol_solve(H, invdiag, v, nv, lane)
-#else
-#define FACTOR(sp) ldl_factor(H, invdiag, nv, s_coldesc, (const int*)s_coldesc + m.ldl_nsparse, m.ldl_dense, sp, lane)
+  unsigned* s_sched = (unsigned*)(smem_all + (size_t)B2_WARPS_PER_CTA * m.lay.total);
+#define FACTOR(sp) ldl_factor(H, invdiag, nv, s_sched, (const int*)s_sched + m.ldl_nsparse, m.ldl_dense, sp, lane)
 #define SOLVE(v) ldl_solve(H, invdiag, v, nv, lane)
-#endif
 #pragma unroll 1
-#ifdef B2_DENSE_LDL
-  for (int i = threadIdx.x; i < m.ntri; i += 32 * B2_WARPS_PER_CTA) s_coldesc[i] = m.tri_coldesc[i];
-#else
-  for (int i = threadIdx.x; i < m.ldl_nsparse; i += 32 * B2_WARPS_PER_CTA) s_coldesc[i] = m.ldl_sparse[i];
-  if (threadIdx.x < 18) s_coldesc[m.ldl_nsparse + threadIdx.x] = (unsigned)m.ldl_start[threadIdx.x];
-#endif
+  for (int i = threadIdx.x; i < m.ldl_nsparse; i += 32 * B2_WARPS_PER_CTA) s_sched[i] = m.ldl_sparse[i];
+  if (threadIdx.x < 18) s_sched[m.ldl_nsparse + threadIdx.x] = (unsigned)m.ldl_start[threadIdx.x];
   __syncthreads();  // the only block barrier; nothing below synchronises across warps
   if (w >= dd.nworld) return;
   if (dd.world_mask != nullptr && dd.world_mask[w] == 0) return;
@@ -1985,7 +1730,6 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         if (lo >> lane & 1u) glist[__popc(lo & ((1u << lane) - 1u))] = lane;
         if (hi >> lane & 1u) glist[nlo + __popc(hi & ((1u << lane) - 1u))] = 32 + lane;
         __syncwarp();
-#ifndef B2_HPROJ_ROWS
         // u_a = sign_a * A * cdof_a: one (dof, component) per lane
         #pragma unroll 1
         for (int t = lane; t < 6 * ns; t += 32) {
@@ -2013,41 +1757,6 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         }
         __syncwarp();
       }
-#else
-        #pragma unroll 1
-        for (int a = lane; a < ns; a += 32) {
-          int d = glist[a];
-          float sg = (m2 >> d & 1ull) ? 1.f : -1.f;
-          const float* c = cdof + SD * d;
-#pragma unroll
-          for (int k = 0; k < 6; k++) {
-            float t = 0.f;
-#pragma unroll
-            for (int l = 0; l < 6; l++) t += gA[k * 6 + l] * c[l];
-            gu[6 * a + k] = sg * t;
-          }
-        }
-        __syncwarp();
-        // lane = column b of the group's dof list; rows a >= b visited in lock step (u_a broadcast)
-#pragma unroll 1
-        for (int b0 = 0; b0 < ns; b0 += 32) {
-          int b = b0 + lane;
-          int db = b < ns ? glist[b] : 0;
-          float sgb = (m2 >> db & 1ull) ? 1.f : -1.f;
-          float cb[6];
-#pragma unroll
-          for (int k = 0; k < 6; k++) cb[k] = sgb * cdof[SD * db + k];
-B2_UNROLL(B2_UNR_HPROJ)
-          for (int a = b0; a < ns; a++) {
-            const float* u = gu + 6 * a;
-            float v = u[0] * cb[0] + u[1] * cb[1] + u[2] * cb[2] + u[3] * cb[3] + u[4] * cb[4] + u[5] * cb[5];
-            int da = glist[a];
-            if (b <= a && b < ns) H[(da * (da + 1) >> 1) + db] += v;
-          }
-        }
-        __syncwarp();
-      }
-#endif
       PHASE_MARK(13);
       FACTOR(treeok);
       #pragma unroll 1

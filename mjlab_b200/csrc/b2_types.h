@@ -94,8 +94,6 @@ struct DevModel {
   const float* static_pose;  // 16 floats per static geom: pos[3], mat[9], rbound, pad[3] (world 0's model values)
   const int *sensor_objtype, *sensor_objid, *sensor_reftype, *sensor_refid, *sensor_intprm;
   const int *sensor_adr, *sensor_dim;
-  const unsigned short* tri_rowmajor;
-  const unsigned* tri_coldesc;
   // bottom-up (leaves first) blocked L^T D L: trailing-update schedules, one word per target entry
   // p | i << 12 | j << 18.  ldl_dense: every packed index in order (a block with m leading rows uses the
   // first tri(m)); ldl_sparse: per block only the entries the dof tree can make non-zero.

@@ -427,16 +427,6 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
     for (int g : s->mi["dyn_cgeom"]) if (!prim(gt[g])) { delete s; return fail("b2_create: unsupported dynamic geom type for the static grid"); }
     for (int g : s->mi["static_geom"]) if (!prim(gt[g])) { delete s; return fail("b2_create: unsupported grid-static geom type"); }
   }
-  std::vector<unsigned short> trow(std::max(m.ntri, 1));
-  std::vector<unsigned> tcol(std::max(m.ntri, 1));
-  {
-    int p = 0;
-    for (int i = 0; i < m.nv; i++) for (int j = 0; j <= i; j++) trow[p++] = (unsigned short)(i | (j << 8));
-    p = 0;
-    for (int j = m.nv - 1; j >= 0; j--)
-      for (int i = j; i < m.nv; i++)
-        tcol[p++] = (unsigned)(i * (i + 1) / 2) | ((unsigned)(j * (j + 1) / 2) << 11) | ((unsigned)j << 22);
-  }
   int rc = 0;
 #define UPI(field, key) rc |= dev_upload<int>(s, s->mi[key], &m.field)
   UPI(body_parentid, "body_parentid"); UPI(body_rootid, "body_rootid"); UPI(body_jntadr, "body_jntadr");
@@ -507,8 +497,6 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
     rc |= dev_upload<unsigned>(s, dense, &m.ldl_dense);
     rc |= dev_upload<unsigned>(s, sparse, &m.ldl_sparse);
   }
-  rc |= dev_upload<unsigned short>(s, trow, &m.tri_rowmajor);
-  rc |= dev_upload<unsigned>(s, tcol, &m.tri_coldesc);
   if (rc) { b2_destroy(s); return 1; }
   // supported sensor set: contact sensors with data in {found,force,dist,pos,normal}, reduce none/netforce
   for (int i = 0; i < m.nsensor; i++) {
@@ -616,11 +604,7 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
   L.gW = alloc(5 * mc); L.sens = off;
   int endB = off;
   L.total = pad4(std::max(endA, endB));
-#ifdef B2_DENSE_LDL
-  s->smem_bytes = sizeof(float) * ((size_t)L.total * B2_WARPS_PER_CTA + pad4(m.ntri));
-#else
   s->smem_bytes = sizeof(float) * ((size_t)L.total * B2_WARPS_PER_CTA + pad4(m.ldl_nsparse + 18));
-#endif
   if (s->smem_bytes > 227 * 1024) {
     b2_destroy(s);
     return fail("b2_create: model too large for the per-environment shared-memory block");
