@@ -214,3 +214,98 @@ def test_coulomb_friction_on_incline(mu, theta_deg, slides):
     assert abs(o.qvel[0, 0]) < 0.02 and abs(a) < 0.02  # held by friction (soft-constraint creep only)
   # time-averaged normal force carries the weight component perpendicular to the plane
   assert np.mean(fn) == pytest.approx(9.81 * np.cos(th), rel=0.03)
+
+
+ARM = """
+<mujoco><compiler angle="radian"/><option timestep="0.002" integrator="{integ}"/>
+  <worldbody><body name="arm" pos="0 0 1"><joint name="h" axis="0 1 0" range="-0.5 0.5" limited="{limited}" damping="{damping}"/>
+    <geom type="capsule" fromto="0 0 0 0.5 0 0" size="0.02" mass="1"/></body></worldbody>
+  {actuator}
+</mujoco>
+"""
+
+
+def test_position_actuator_steady_state_and_clamps():
+  """Affine-bias position actuator (force = kp (ctrl - q) - kd qdot): a horizontal 1 kg arm (com at 0.25 m)
+  settles where kp (target - q) balances gravity; a force range clamps the actuator output."""
+  act = '<actuator><position joint="h" kp="{kp}" kv="2" {fr}/></actuator>'
+  m = Spec.from_string(ARM.format(integ="implicitfast", limited="false", damping="0", actuator=act.format(kp=200, fr=""))).compile()
+  o = Oracle(m)
+  o.ctrl[:] = 0.1
+  for _ in range(4000):
+    o.step()
+  q = o.qpos[0, 0]
+  # axis +y: positive q lowers the tip; gravity torque about y for the com at 0.25 cos(q) ahead of the hinge
+  tau_g = 1.0 * 9.81 * 0.25 * np.cos(q)
+  assert abs(o.qvel[0, 0]) < 1e-6
+  assert 200 * (0.1 - q) == pytest.approx(-tau_g, rel=1e-4)
+  assert o.actuator_force[0, 0] == pytest.approx(-tau_g, rel=1e-4)
+  # forcerange +-1 N m cannot hold the arm: the output sits on the clamp while the arm falls
+  m = Spec.from_string(ARM.format(integ="implicitfast", limited="false", damping="0",
+                                  actuator=act.format(kp=200, fr='forcerange="-1 1" forcelimited="true"'))).compile()
+  o = Oracle(m)
+  o.ctrl[:] = 0.0
+  for _ in range(100):
+    o.step()
+  assert o.actuator_force[0, 0] == pytest.approx(-1.0) and o.qpos[0, 0] > 0.05
+
+
+def test_joint_limit_holds_against_gravity():
+  """The arm falls onto its upper limit (0.5 rad) and rests there: limit force = gravity torque, penetration
+  follows the soft-constraint law f = (1/R) k imp (-r) with R = (1 - imp)/imp * dof_invweight0."""
+  m = Spec.from_string(ARM.format(integ="implicitfast", limited="true", damping="0.05", actuator="")).compile()
+  o = Oracle(m)
+  for _ in range(6000):
+    o.step()
+  q = o.qpos[0, 0]
+  assert abs(o.qvel[0, 0]) < 1e-5 and int(o.nefc[0, 0]) == 1
+  r = 0.5 - q
+  assert -2e-3 < r < 0.0  # slightly beyond the limit
+  tau_g = 9.81 * 0.25 * np.cos(q)
+  # default solref (0.02, 1), solimp (0.9, 0.95, 0.001, 0.5, 2): stiffness k = 1/(dmax^2 tc^2 dr^2)
+  k = 1.0 / (0.95**2 * 0.02**2 * 1.0)
+  x = abs(r) / 0.001
+  y = x**2 / 0.5 if x <= 0.5 else 1 - (1 - x) ** 2 / 0.5
+  imp = 0.95 if x >= 1 else 0.9 + y * 0.05
+  R = (1 - imp) / imp * float(m.dof_invweight0[0])
+  assert tau_g == pytest.approx(k * imp * (-r) / R, rel=2e-3)
+  assert o.qfrc_constraint[0, 0] == pytest.approx(-tau_g, rel=1e-4)
+
+
+@pytest.mark.parametrize("integ", ["Euler", "implicitfast"])
+def test_joint_damping_decay_rate(integ):
+  """Zero-gravity spin with viscous joint damping b: omega decays as exp(-b t / I); both integrators treat
+  damping implicitly (MuJoCo's Euler does so for joint damping), so the discrete rate is 1 / (1 + h b / I)."""
+  sp = Spec.from_string(ARM.format(integ=integ, limited="false", damping="0.3", actuator=""))
+  sp.option.gravity = (0.0, 0.0, 0.0)
+  m = sp.compile()
+  o = Oracle(m)
+  o.qvel[:] = 2.0
+  o.forward()
+  inertia = float(o.qM[0, 0])
+  for _ in range(500):
+    o.step()
+  expect = 2.0 * (1.0 / (1.0 + 0.002 * 0.3 / inertia)) ** 500
+  assert o.qvel[0, 0] == pytest.approx(expect, rel=1e-6)
+  assert expect == pytest.approx(2.0 * np.exp(-0.3 * 1.0 / inertia), rel=2e-2)  # backward-Euler discretisation error
+
+
+def test_resting_contact_penetration_follows_soft_constraint_law():
+  """Ball on a plane at rest: depth r solves m g = (1/R) k imp(r) (-r), R = (1-imp)/imp (invweight_ball + 0);
+  checks impedance, reference acceleration and regulariser together (MuJoCo 'Computation' chapter)."""
+  m = Spec.from_string(BALL_ON_PLANE).compile()
+  o = Oracle(m)
+  for _ in range(3000):
+    o.step()
+  assert abs(o.qvel[0]).max() < 1e-6 and int(o.ncon[0, 0]) == 1
+  r = float(o.contact_dist[0, 0])
+  assert -1e-3 < r < 0
+  k = 1.0 / (0.95**2 * 0.02**2)
+  x = abs(r) / 0.001
+  y = x**2 / 0.5 if x <= 0.5 else 1 - (1 - x) ** 2 / 0.5
+  imp = 0.95 if x >= 1 else 0.9 + y * 0.05
+  ball = [i for i, n in enumerate(m.names["body"]) if n == "ball"][0]
+  # the four pyramid rows share D: the normal force is the sum of four equal row forces, each (1/R_row) k imp (-r)
+  mu = float(o.contact_friction[0, 0])
+  Rrow = 2 * mu * mu * (1 - imp) / imp * float(m.body_invweight0[ball, 0]) * (1 + mu * mu)
+  assert 2 * 9.81 == pytest.approx(4 * k * imp * (-r) / Rrow, rel=2e-3)
