@@ -244,9 +244,98 @@ int b2_phase_cycles(unsigned long long* out32) {
 #endif
 }
 
+// Sizes and index ranges of the model table (mjModel field names).  Returns "" when consistent.
+static std::string validate_desc(const B2ModelDesc* desc) {
+  std::map<std::string, const B2Array*> by;
+  for (int i = 0; i < desc->narray; i++) {
+    const B2Array& a = desc->arrays[i];
+    if (!a.name || a.n < 0 || (a.n > 0 && !a.data)) return "array without name or data";
+    if (a.dtype != B2_I32 && a.dtype != B2_F64) return std::string("array '") + a.name + "': dtype must be int32 or float64";
+    by[a.name] = &a;
+  }
+  auto scalar = [&](const char* k, long long* out) -> bool {
+    auto it = by.find(k);
+    if (it == by.end() || it->second->n < 1) return false;
+    *out = it->second->dtype == B2_I32 ? ((const int32_t*)it->second->data)[0] : (long long)((const double*)it->second->data)[0];
+    return true;
+  };
+  long long nq, nv, nu, nbody, njnt, ngeom, nsite, nsensor, npair, nstatic = 0;
+  if (!scalar("nq", &nq) || !scalar("nv", &nv) || !scalar("nu", &nu) || !scalar("nbody", &nbody) || !scalar("njnt", &njnt) ||
+      !scalar("ngeom", &ngeom) || !scalar("nsite", &nsite) || !scalar("nsensor", &nsensor) || !scalar("npair", &npair))
+    return "missing size scalar (nq nv nu nbody njnt ngeom nsite nsensor npair)";
+  scalar("nstatic", &nstatic);
+  if (nq < 1 || nv < 1 || nbody < 1 || nu < 0 || njnt < 0 || ngeom < 0 || nsite < 0 || nsensor < 0 || npair < 0 || nstatic < 0)
+    return "negative or zero model size";
+  struct Req { const char* name; int dtype; long long n; long long lo, hi; };  // index range checked for lo <= v < hi
+  const long long NO = -(1ll << 40);
+  std::vector<Req> req = {
+    {"body_parentid", B2_I32, nbody, 0, nbody}, {"body_rootid", B2_I32, nbody, 0, nbody}, {"body_jntadr", B2_I32, nbody, -1, njnt},
+    {"body_jntnum", B2_I32, nbody, 0, njnt + 1}, {"body_dofadr", B2_I32, nbody, -1, nv}, {"body_dofnum", B2_I32, nbody, 0, nv + 1},
+    {"jnt_type", B2_I32, njnt, 0, 4}, {"jnt_qposadr", B2_I32, njnt, 0, nq}, {"jnt_dofadr", B2_I32, njnt, 0, nv},
+    {"jnt_bodyid", B2_I32, njnt, 0, nbody}, {"jnt_limited", B2_I32, njnt, 0, 2}, {"dof_bodyid", B2_I32, nv, 0, nbody},
+    {"dof_jntid", B2_I32, nv, 0, njnt}, {"dof_parentid", B2_I32, nv, -1, nv}, {"geom_type", B2_I32, ngeom, 0, 9},
+    {"geom_bodyid", B2_I32, ngeom, 0, nbody}, {"geom_condim", B2_I32, ngeom, 1, 7}, {"geom_priority", B2_I32, ngeom, NO, -NO},
+    {"site_bodyid", B2_I32, nsite, 0, nbody}, {"actuator_trnid", B2_I32, nu, 0, njnt},
+    {"actuator_ctrllimited", B2_I32, nu, 0, 2}, {"actuator_forcelimited", B2_I32, nu, 0, 2},
+    {"pair_geom1", B2_I32, npair, 0, ngeom}, {"pair_geom2", B2_I32, npair, 0, ngeom},
+    {"sensor_objtype", B2_I32, nsensor, NO, -NO}, {"sensor_objid", B2_I32, nsensor, NO, -NO}, {"sensor_reftype", B2_I32, nsensor, NO, -NO},
+    {"sensor_refid", B2_I32, nsensor, NO, -NO}, {"sensor_intprm", B2_I32, 3 * nsensor, NO, -NO}, {"sensor_adr", B2_I32, nsensor, 0, 1 << 20},
+    {"sensor_dim", B2_I32, nsensor, 0, 1 << 20},
+    {"body_pos", B2_F64, 3 * nbody}, {"body_quat", B2_F64, 4 * nbody}, {"body_ipos", B2_F64, 3 * nbody}, {"body_iquat", B2_F64, 4 * nbody},
+    {"body_mass", B2_F64, nbody}, {"body_subtreemass", B2_F64, nbody}, {"body_inertia", B2_F64, 3 * nbody}, {"body_invweight0", B2_F64, 2 * nbody},
+    {"jnt_pos", B2_F64, 3 * njnt}, {"jnt_axis", B2_F64, 3 * njnt}, {"jnt_range", B2_F64, 2 * njnt}, {"jnt_solref", B2_F64, 2 * njnt},
+    {"jnt_solimp", B2_F64, 5 * njnt}, {"jnt_margin", B2_F64, njnt}, {"jnt_stiffness", B2_F64, njnt}, {"dof_armature", B2_F64, nv},
+    {"dof_damping", B2_F64, nv}, {"dof_frictionloss", B2_F64, nv}, {"dof_invweight0", B2_F64, nv}, {"geom_size", B2_F64, 3 * ngeom},
+    {"geom_pos", B2_F64, 3 * ngeom}, {"geom_quat", B2_F64, 4 * ngeom}, {"geom_friction", B2_F64, 3 * ngeom}, {"geom_solref", B2_F64, 2 * ngeom},
+    {"geom_solimp", B2_F64, 5 * ngeom}, {"geom_solmix", B2_F64, ngeom}, {"geom_margin", B2_F64, ngeom}, {"geom_gap", B2_F64, ngeom},
+    {"geom_rbound", B2_F64, ngeom}, {"geom_rgba", B2_F64, 4 * ngeom}, {"site_pos", B2_F64, 3 * nsite}, {"site_quat", B2_F64, 4 * nsite},
+    {"actuator_gainprm", B2_F64, 10 * nu}, {"actuator_biasprm", B2_F64, 10 * nu}, {"actuator_ctrlrange", B2_F64, 2 * nu},
+    {"actuator_forcerange", B2_F64, 2 * nu}, {"actuator_gear", B2_F64, nu}, {"qpos0", B2_F64, nq},
+  };
+  if (nstatic > 0) {
+    req.push_back({"geom_contype", B2_I32, ngeom, NO, -NO});
+    req.push_back({"geom_conaffinity", B2_I32, ngeom, NO, -NO});
+    req.push_back({"static_geom", B2_I32, nstatic, 0, ngeom});
+    req.push_back({"static_cell0", B2_I32, 2 * nstatic, 0, 1 << 20});
+    req.push_back({"grid_params", B2_F64, 5});
+  }
+  for (const Req& r : req) {
+    auto it = by.find(r.name);
+    long long have = it == by.end() ? 0 : it->second->n;
+    if (have != r.n) return std::string("array '") + r.name + "' has " + std::to_string(have) + " elements, expected " + std::to_string(r.n);
+    if (r.n == 0) continue;
+    if (it->second->dtype != r.dtype) return std::string("array '") + r.name + "' has the wrong dtype";
+    if (r.dtype == B2_I32 && r.lo != NO) {
+      const int32_t* v = (const int32_t*)it->second->data;
+      for (long long i = 0; i < r.n; i++)
+        if (v[i] < r.lo || v[i] >= r.hi) return std::string("array '") + r.name + "' holds an index out of range";
+    }
+  }
+  for (const char* k : {"dyn_cgeom", "grid_items"}) {
+    auto it = by.find(k);
+    if (it == by.end()) continue;
+    if (it->second->dtype != B2_I32) return std::string("array '") + k + "' has the wrong dtype";
+    long long hi = std::string(k) == "dyn_cgeom" ? ngeom : nstatic;
+    const int32_t* v = (const int32_t*)it->second->data;
+    for (long long i = 0; i < it->second->n; i++)
+      if (v[i] < 0 || v[i] >= hi) return std::string("array '") + k + "' holds an index out of range";
+  }
+  {  // parents precede children (the kinematic walks and the factorisation schedule rely on it)
+    const int32_t* bp = (const int32_t*)by["body_parentid"]->data;
+    for (long long b = 1; b < nbody; b++) if (bp[b] >= b) return "body_parentid: parents must precede children";
+    const int32_t* dp = (const int32_t*)by["dof_parentid"]->data;
+    for (long long d = 0; d < nv; d++) if (dp[d] >= d) return "dof_parentid: parents must precede children";
+  }
+  return "";
+}
+
 int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax, int cuda_device,
               b2_sim** out) {
   if (!desc || !out || nworld <= 0) return fail("b2_create: bad arguments");
+  {
+    std::string why = validate_desc(desc);  // host-only: a malformed table must not reach the index loops
+    if (!why.empty()) return fail("b2_create: " + why);
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail("b2_create: no CUDA device available (this library has no CPU path)");

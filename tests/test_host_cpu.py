@@ -137,3 +137,40 @@ def test_shard_range():
   assert shard_range(32768, 3, 8) == (12288, 16384)
   with pytest.raises(ValueError):
     shard_range(10, 0, 3)
+
+
+def test_b2_create_rejects_malformed_model_tables(g1_model):
+  """The descriptor is validated on the host before any device work: wrong sizes and out-of-range indices are
+  refused with a message (no compute happens here; on a CPU box a valid table ends at 'no CUDA device')."""
+  import copy
+  import ctypes
+
+  import numpy as np
+
+  from mjlab_b200.sim import native
+
+  lib = native.load_library()
+  lib.b2_last_error.restype = ctypes.c_char_p
+
+  def create(model):
+    desc, keep = native.make_model_desc(model)
+    h = ctypes.c_void_p()
+    rc = lib.b2_create(ctypes.byref(desc), 2, 0, 0, 0, ctypes.byref(h))
+    msg = lib.b2_last_error(None).decode() if rc else ""
+    if rc == 0:
+      lib.b2_destroy(h)
+    return rc, msg
+
+  rc, msg = create(g1_model)
+  assert rc == 0 or "no CUDA device" in msg  # the unmodified table passes validation
+  cases = [
+    ("dof_parentid", lambda a: a[:-1], "has 34 elements, expected 35"),
+    ("pair_geom1", lambda a: np.where(np.arange(len(a)) == 3, 999, a).astype(np.int32), "index out of range"),
+    ("geom_size", lambda a: a[:-1], "'geom_size' has"),
+    ("body_parentid", lambda a: np.where(np.arange(len(a)) == 2, 5, a).astype(np.int32), "parents must precede children"),
+  ]
+  for field, mod, expect in cases:
+    m2 = copy.deepcopy(g1_model)
+    m2.arrays[field] = np.ascontiguousarray(mod(np.asarray(g1_model.arrays[field])))
+    rc, msg = create(m2)
+    assert rc != 0 and expect in msg, (field, msg)
