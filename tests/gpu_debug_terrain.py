@@ -13,7 +13,8 @@ from mjlab_b200.asset_zoo import load_compiled  # noqa: E402
 from mjlab_b200.compiler import Spec  # noqa: E402
 from mjlab_b200.sim import Simulation, SimulationCfg  # noqa: E402
 from oracle.oracle import Oracle  # noqa: E402
-from test_terrain_gpu import ON_BOX, _terrain_states  # noqa: E402
+from test_terrain_gpu import ON_BOX  # noqa: E402
+from util import terrain_states as _terrain_states  # noqa: E402
 
 
 def T(x):

@@ -10,7 +10,7 @@ import pytest
 
 from mjlab_b200.compiler import Spec
 from oracle.oracle import Oracle
-from util import load_oracle, make_states
+from util import load_oracle, make_states, terrain_states
 
 GOLDEN = Path(__file__).parent / "golden"
 
@@ -143,14 +143,16 @@ def test_pyramid_rows_share_regulariser(g1_model):
     assert len(rows) == 4 and np.ptp(R[rows]) == 0.0  # R = 2 mu^2 R_first on all four edges
 
 
-@pytest.mark.parametrize("name", ["g1_flat_seed101", "go1_flat_seed102", "g1_tracking_flat_seed103"])
+@pytest.mark.parametrize("name", ["g1_flat_seed101", "go1_flat_seed102", "g1_tracking_flat_seed103",
+                                  "go1_stairs_small_seed104"])
 def test_oracle_reproduces_golden(name):
   from mjlab_b200.asset_zoo import load_compiled
 
   z = np.load(GOLDEN / f"{name}.npz")
   m = load_compiled(name.rsplit("_seed", 1)[0])
   n = int(z["n"])
-  st = make_states(m, n, seed=int(z["seed"]))
+  seed = int(z["seed"])
+  st = terrain_states(m, n, seed, 1.4) if "terrain_origins" in m.arrays else make_states(m, n, seed=seed)
   for k, v in st.items():
     assert v == pytest.approx(z[f"in_{k}"], abs=0)  # the seeded inputs themselves are reproducible
   o = Oracle(m, nworld=n, maxcon=48)

@@ -8,6 +8,7 @@ import pytest
 import torch
 
 from util import load_oracle, load_sim, make_states, relerr
+from util import terrain_states as _terrain_states
 
 pytestmark = pytest.mark.gpu
 
@@ -95,16 +96,6 @@ def test_box_primitives_step_parity(geom, z, quat):
     sim.data.qacc_warmstart[:] = torch.as_tensor(o.qacc_warmstart, dtype=torch.float32, device="cuda:0")
   assert int(o.ncon.max()) >= 1
   sim.close()
-
-
-def _terrain_states(m, n, seed, spread):
-  rng = np.random.default_rng(seed)
-  st = make_states(m, n, seed=seed, z_range=(-0.05, 0.04))
-  org = np.asarray(m.arrays["terrain_origins"]).reshape(-1, 3)
-  spot = org[rng.integers(0, len(org), n)]
-  st["qpos"][:, 0:2] = spot[:, 0:2] + rng.uniform(-spread, spread, (n, 2))
-  st["qpos"][:, 2] += spot[:, 2]
-  return st
 
 
 @pytest.mark.parametrize("name,n,spread,dist_tol,acc_tol", [

@@ -39,6 +39,17 @@ def make_states(model, n: int, seed: int = 0, key: str = "robot/init_state", z_r
   return dict(qpos=qpos, qvel=qvel, ctrl=ctrl, qacc_warmstart=warm)
 
 
+def terrain_states(model, n: int, seed: int, spread: float):
+  """make_states() moved onto random sub-terrain origins of a box-terrain scene (xy spread around them)."""
+  rng = np.random.default_rng(seed)
+  st = make_states(model, n, seed=seed, z_range=(-0.05, 0.04))
+  org = np.asarray(model.arrays["terrain_origins"]).reshape(-1, 3)
+  spot = org[rng.integers(0, len(org), n)]
+  st["qpos"][:, 0:2] = spot[:, 0:2] + rng.uniform(-spread, spread, (n, 2))
+  st["qpos"][:, 2] += spot[:, 2]
+  return st
+
+
 def load_oracle(o, st):
   for k, v in st.items():
     o.field(k)[:] = v

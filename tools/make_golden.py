@@ -16,7 +16,7 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 from mjlab_b200.asset_zoo import load_compiled  # noqa: E402
 from oracle.oracle import Oracle  # noqa: E402
-from util import load_oracle, make_states  # noqa: E402
+from util import load_oracle, make_states, terrain_states  # noqa: E402
 
 OUT = ROOT / "tests" / "golden"
 FIELDS = ["qpos", "qvel", "qacc", "qacc_smooth", "qfrc_smooth", "qfrc_constraint", "xpos", "xquat",
@@ -25,10 +25,11 @@ FIELDS = ["qpos", "qvel", "qacc", "qacc_smooth", "qfrc_smooth", "qfrc_constraint
 
 def main():
   OUT.mkdir(exist_ok=True)
-  for name, seed in (("g1_flat", 101), ("go1_flat", 102), ("g1_tracking_flat", 103)):
+  for name, seed in (("g1_flat", 101), ("go1_flat", 102), ("g1_tracking_flat", 103), ("go1_stairs_small", 104)):
     m = load_compiled(name)
     n = 8
-    st = make_states(m, n, seed=seed)
+    # box-terrain scenes: robots dropped around random sub-terrain origins (grid-static broadphase + box primitives)
+    st = terrain_states(m, n, seed, 1.4) if "terrain_origins" in m.arrays else make_states(m, n, seed=seed)
     o = Oracle(m, nworld=n, maxcon=48)
     load_oracle(o, st)
     o.forward()
