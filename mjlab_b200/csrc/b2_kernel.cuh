@@ -9,9 +9,15 @@
 //   * the constraint Jacobian is never materialised: contacts of one body pair share a 6x6 block
 //     A_g = sum_c S_c W_c S_c^T that is projected through the motion vectors (cdof) of the dofs
 //     between the two bodies, so H = M + J^T D J, J v and J^T f cost O(ndof_chain^2) per body pair;
-//   * Newton with exact 1-D line search, dense packed Cholesky with a balanced (i,j)-pair schedule.
+//   * Newton with exact 1-D line search; packed blocked L^T D L, eliminated bottom-up with dof-tree schedules.
+// With -DB2_HOST_EMULATION the warp-level helpers (everything above the kernel) compile as plain C++ against
+// tests/emul/warp_emul.h (32 host threads in lock step), so they are unit-tested without a GPU.
 #pragma once
+#ifdef B2_HOST_EMULATION
+#include "warp_emul.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <math.h>
 #include <stdint.h>
 
@@ -109,6 +115,7 @@ __device__ __forceinline__ float dot6(const float* a, const float* b) {
 }
 __device__ __forceinline__ int tri(int i, int j) { return (i * (i + 1) >> 1) + j; }  // j <= i
 
+#ifndef B2_HOST_EMULATION
 // ---- TMA 1-D bulk copy + mbarrier (PTX) -------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -155,6 +162,7 @@ __device__ __forceinline__ void bulk_commit_wait() {
 __device__ __forceinline__ void fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+#endif  // !B2_HOST_EMULATION
 
 #define MP(arr) (m.arr.p + (size_t)w * m.arr.stride)
 
@@ -173,9 +181,13 @@ __device__ unsigned long long g_phase_cycles[32];
 
 // approximate reciprocal (MUFU.RCP): the IEEE-rounded __frcp_rn costs ~13 instructions per call
 __device__ __forceinline__ float b2_rcp(float x) {
+#ifdef B2_HOST_EMULATION
+  return 1.f / x;
+#else
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
+#endif
 }
 // ---- bottom-up blocked L^T D L (leaves first) -----------------------------------------------------------
 // Pivots are eliminated from the last dof to the first, four per block step, so the dof tree's zero pattern
@@ -606,6 +618,7 @@ __device__ __noinline__ float rows_cost(int fc, int fl, const float* con, const 
 
 }  // namespace b2
 
+#ifndef B2_HOST_EMULATION
 // ==================================================================================================
 // The kernel
 // ==================================================================================================
@@ -2066,3 +2079,4 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   __syncwarp();
   }  // sub-step loop
 }
+#endif  // !B2_HOST_EMULATION

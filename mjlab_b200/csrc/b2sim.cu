@@ -10,6 +10,7 @@
 
 #include "../../include/b2sim.h"
 #include "b2_kernel.cuh"
+#include "b2_tables.h"
 #include "b2_env.cuh"
 
 static thread_local std::string g_err;
@@ -560,28 +561,8 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
   rc |= dev_upload<int>(s, cgeom, &m.cgeom);
   {
     // schedules of the bottom-up blocked factorisation (b2_kernel.cuh: ldl_factor)
-    const std::vector<int>& dpar = s->mi["dof_parentid"];
-    std::vector<unsigned long long> danc(m.nv, 0ull);  // strict dof ancestors
-    for (int k = 0; k < m.nv; k++)
-      for (int a = dpar[k]; a >= 0; a = dpar[a]) danc[k] |= 1ull << a;
     std::vector<unsigned> dense, sparse;
-    for (int i = 0; i < m.nv; i++)
-      for (int j = 0; j <= i; j++) dense.push_back((unsigned)(i * (i + 1) / 2 + j) | ((unsigned)i << 12) | ((unsigned)j << 18));
-    int blk = 0;
-    for (int kt = m.nv - 1; kt >= 0; kt -= 4, blk++) {
-      int nbk = std::min(4, kt + 1), lead = kt - nbk + 1;
-      m.ldl_start[blk] = (int)sparse.size();
-      for (int i = 0; i < lead; i++)
-        for (int j = 0; j <= i; j++) {
-          bool hit = false;
-          for (int t = 0; t < nbk; t++) {
-            unsigned long long a = danc[kt - t];
-            if ((a >> i & 1ull) && (a >> j & 1ull)) hit = true;
-          }
-          if (hit) sparse.push_back((unsigned)(i * (i + 1) / 2 + j) | ((unsigned)i << 12) | ((unsigned)j << 18));
-        }
-    }
-    for (int b = blk; b < 18; b++) m.ldl_start[b] = (int)sparse.size();
+    b2_build_ldl_schedules(m.nv, s->mi["dof_parentid"].data(), dense, sparse, m.ldl_start);
     m.ldl_nsparse = (int)sparse.size();
     rc |= dev_upload<unsigned>(s, dense, &m.ldl_dense);
     rc |= dev_upload<unsigned>(s, sparse, &m.ldl_sparse);

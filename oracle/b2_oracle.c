@@ -1475,3 +1475,29 @@ int b2o_max_threads(void) {
   return 1;
 #endif
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * primitive-level entry points (tests/test_warp_emul.py compares the CUDA device routines, compiled
+ * for the host, against these).  out: 7 reals per contact = dist, pos[3], normal[3].
+ * ------------------------------------------------------------------------------------------- */
+static int prim_out(const RawCon* c, int n, real* out) {
+  for (int i = 0; i < n; i++) {
+    out[7*i] = c[i].dist;
+    for (int k = 0; k < 3; k++) { out[7*i+1+k] = c[i].pos[k]; out[7*i+4+k] = c[i].frame[k]; }
+  }
+  return n;
+}
+int b2o_prim_sphere_box(const real* sp, real r, const real* bp, const real* bm, const real* h, real margin, real* out) {
+  RawCon c[1];
+  return prim_out(c, sphere_box(c, margin, sp, r, bp, bm, h), out);
+}
+int b2o_prim_capsule_box(const real* cp, const real* cm, const real* cs, const real* bp, const real* bm, const real* h,
+                         real margin, real* out) {
+  RawCon c[2];
+  return prim_out(c, capsule_box(c, margin, cp, cm, cs, bp, bm, h), out);
+}
+int b2o_prim_box_box(const real* p1, const real* m1, const real* h1, const real* p2, const real* m2, const real* h2,
+                     real margin, real* out) {
+  RawCon c[8];
+  return prim_out(c, box_box(c, margin, p1, m1, h1, p2, m2, h2), out);
+}

@@ -1,0 +1,79 @@
+// emul.cpp — C entry points that run warp-level device helpers of b2_kernel.cuh on 32 host threads.
+#define B2_HOST_EMULATION
+#include "warp_emul.h"
+
+#include <functional>
+#include <vector>
+
+#include "../../mjlab_b200/csrc/b2_kernel.cuh"
+#include "../../mjlab_b200/csrc/b2_tables.h"
+
+namespace {
+struct Job { std::function<void(int)>* fn; int lane; };
+void* trampoline(void* p) {
+  Job* j = (Job*)p;
+  warp_emul::lane() = j->lane;
+  (*j->fn)(j->lane);
+  return nullptr;
+}
+void run_warp(std::function<void(int)> fn) {
+  pthread_barrier_init(&warp_emul::ctx().bar, nullptr, 32);
+  pthread_t th[32];
+  Job jobs[32];
+  for (int l = 0; l < 32; l++) { jobs[l] = {&fn, l}; pthread_create(&th[l], nullptr, trampoline, &jobs[l]); }
+  for (int l = 0; l < 32; l++) pthread_join(th[l], nullptr);
+  pthread_barrier_destroy(&warp_emul::ctx().bar);
+}
+}  // namespace
+
+extern "C" {
+// schedules exactly as b2_create builds them; returns the number of sparse words
+int emul_schedules(int nv, const int* dof_parentid, unsigned* dense, unsigned* sparse, int* start) {
+  std::vector<unsigned> d, s;
+  b2_build_ldl_schedules(nv, dof_parentid, d, s, start);
+  if (dense) memcpy(dense, d.data(), d.size() * 4);
+  if (sparse) memcpy(sparse, s.data(), s.size() * 4);
+  return (int)s.size();
+}
+// factor the packed matrix A in place (device routine ldl_factor) and solve for x (ldl_solve)
+void emul_ldl(int n, const int* dof_parentid, float* A, float* invdiag, float* x, int use_sparse) {
+  std::vector<unsigned> d, s;
+  int start[18];
+  b2_build_ldl_schedules(n, dof_parentid, d, s, start);
+  s.push_back(0);  // never empty
+  run_warp([&](int lane) {
+    b2::ldl_factor(A, invdiag, n, s.data(), start, d.data(), use_sparse != 0, lane);
+    b2::ldl_solve(A, invdiag, x, n, lane);
+  });
+}
+void emul_symv(int n, const float* M, const float* x, float* y) {
+  run_warp([&](int lane) { b2::symv(M, x, y, n, lane); });
+}
+// narrowphase primitives (no warp intrinsics inside: called on the calling thread).  Poses are 12 floats
+// (pos[3], row-major mat[9]); out: 7 floats per contact = dist, pos[3], normal[3].
+static int prim_out(const b2::RawCon* c, int n, float* out) {
+  for (int i = 0; i < n; i++) {
+    out[7 * i] = c[i].dist;
+    for (int k = 0; k < 3; k++) { out[7 * i + 1 + k] = c[i].pos[k]; out[7 * i + 4 + k] = c[i].n[k]; }
+  }
+  return n;
+}
+int emul_sphere_box(const float* sp, float r, const float* box, const float* h, float margin, float* out) {
+  b2::RawCon c[1];
+  return prim_out(c, b2::sphere_box(c[0], margin, sp, r, box, h), out);
+}
+int emul_capsule_box(const float* cap, const float* size, const float* box, const float* h, float margin, float* out) {
+  b2::RawCon c[2];
+  return prim_out(c, b2::capsule_box(c, margin, cap, size, box, h), out);
+}
+int emul_box_box(const float* b1, const float* h1, const float* b2_, const float* h2, float* out) {
+  b2::RawCon c[8];
+  return prim_out(c, b2::box_box(c, b1, h1, b2_, h2), out);
+}
+float emul_wsum(const float* v) {
+  float out[32];
+  run_warp([&](int lane) { out[lane] = b2::wsum(v[lane]); });
+  for (int l = 1; l < 32; l++) if (out[l] != out[0]) return NAN;  // every lane must hold the same bits
+  return out[0];
+}
+}
