@@ -70,6 +70,19 @@ int emul_box_box(const float* b1, const float* h1, const float* b2_, const float
   b2::RawCon c[8];
   return prim_out(c, b2::box_box(c, b1, h1, b2_, h2), out);
 }
+// J x for contact rows (4 pyramid rows per contact, written to CJV0..3) and limit rows (LJV): device mulJ on
+// caller-built SoA blocks.  layout[] returns the enum values the caller needs to fill them.
+void emul_layout(int* out) {
+  int v[] = {CS0, CMU, CINFO, CGRP, CJV0, C_NFIELD, LINFO, LJV, L_NFIELD, SD};
+  memcpy(out, v, sizeof(v));
+}
+void emul_mulJ(const float* x, float* con, float* lim, const int* gstart, const float* cdof,
+               const unsigned long long* dofmask, int ncon, int nlim, int ngroup, int MC, int NLC) {
+  std::vector<float> gV(6 * (size_t)MC + 6, 0.f);
+  run_warp([&](int lane) {
+    b2::mulJ(x, CJV0, LJV, false, con, lim, gstart, gV.data(), cdof, dofmask, ncon, nlim, ngroup, MC, NLC, lane);
+  });
+}
 float emul_wsum(const float* v) {
   float out[32];
   run_warp([&](int lane) { out[lane] = b2::wsum(v[lane]); });

@@ -239,3 +239,65 @@ def test_box_primitives_device_code_matches_oracle(lib):
       assert np.abs(o32[: 7 * n64] - o64[: 7 * n64]).max() < 10 * tol, (trial, n64)
       counts["box"] += 1
   assert counts["sphere"] > 150 and counts["capsule"] > 50 and counts["capsule2"] > 3 and counts["box"] > 100, counts
+
+
+def test_matrix_free_jacobian_product(lib):
+  """mulJ (J x without ever forming J: per body-pair group a relative spatial velocity from the chain dofs,
+  then S_m . V per contact direction, pyramid rows a0 +- mu a_t) against an explicit Jacobian built in numpy."""
+  lay = np.zeros(10, dtype=np.int32)
+  lib.emul_layout(ptr(lay, ctypes.c_int))
+  CS0, CMU, CINFO, CGRP, CJV0, CN, LINFO, LJV, LN, SD = lay.tolist()
+  rng = np.random.default_rng(8)
+  nv, nbody, MC, NLC = 35, 12, 24, 8
+  # bodies 1..11 with random chain dof sets (nested along a random tree)
+  bpar = [0] + [int(rng.integers(0, b)) for b in range(1, nbody)]
+  masks = [0] * nbody
+  nxt = 0
+  for b in range(1, nbody):
+    k = int(rng.integers(1, 4))
+    own = sum(1 << d for d in range(nxt, min(nxt + k, nv)))
+    nxt = min(nxt + k, nv)
+    masks[b] = masks[bpar[b]] | own
+  dofmask = np.array(masks, dtype=np.uint64)
+  cdof = np.zeros((nv, SD), dtype=np.float32)
+  cdof[:, :6] = rng.normal(size=(nv, 6))
+  # contacts grouped by body pair (contiguous groups), mixed condim 1 / 3 and one excluded contact (dim 0)
+  pairs = [(0, 3), (2, 7), (5, 9), (4, 4 if False else 11)]
+  con = np.zeros((CN, MC), dtype=np.float32)
+  coni = con.view(np.int32)
+  gstart, c = [], 0
+  dims = []
+  for g, (b1, b2) in enumerate(pairs):
+    gstart.append(c)
+    for _ in range(int(rng.integers(1, 5))):
+      dim = [3, 3, 1, 0][int(rng.integers(0, 4))]
+      con[CS0 : CS0 + 18, c] = rng.normal(size=18)
+      con[CMU, c] = rng.uniform(0.3, 1.2)
+      coni[CINFO, c] = b1 | (b2 << 8) | (dim << 16)
+      coni[CGRP, c] = g
+      dims.append(dim)
+      c += 1
+  ncon = c
+  gstart.append(ncon)
+  gstart = np.array(gstart, dtype=np.int32)
+  lim = np.zeros((LN, NLC), dtype=np.float32)
+  limi = lim.view(np.int32)
+  nlim = 5
+  ldof = rng.integers(0, nv, nlim)
+  lside = rng.integers(0, 2, nlim)
+  limi[LINFO, :nlim] = ldof | (lside << 16)
+  x = rng.normal(size=nv).astype(np.float32)
+  lib.emul_mulJ(ptr(x, ctypes.c_float), ptr(con, ctypes.c_float), ptr(lim, ctypes.c_float), ptr(gstart, ctypes.c_int),
+                ptr(cdof, ctypes.c_float), dofmask.ctypes.data_as(ctypes.POINTER(ctypes.c_ulonglong)), ncon, nlim, len(pairs), MC, NLC)
+  for ci in range(ncon):
+    b1, b2 = coni[CINFO, ci] & 0xff, (coni[CINFO, ci] >> 8) & 0xff
+    m1, m2 = int(dofmask[b1]), int(dofmask[b2])
+    V = np.zeros(6)
+    for d in range(nv):
+      if (m1 ^ m2) >> d & 1:
+        V += (1.0 if m2 >> d & 1 else -1.0) * cdof[d, :6] * x[d]
+    a = [con[CS0 + 6 * mm : CS0 + 6 * mm + 6, ci] @ V for mm in range(3)]
+    mu = con[CMU, ci]
+    want = {3: [a[0] + mu * a[1], a[0] - mu * a[1], a[0] + mu * a[2], a[0] - mu * a[2]], 1: [a[0], 0, 0, 0], 0: [0, 0, 0, 0]}[dims[ci]]
+    assert con[CJV0 : CJV0 + 4, ci] == pytest.approx(want, rel=1e-4, abs=1e-4), (ci, dims[ci])
+  assert lim[LJV, :nlim] == pytest.approx(np.where(lside == 1, -1.0, 1.0) * x[ldof], rel=1e-6)
