@@ -316,6 +316,66 @@ __device__ __noinline__ void ldl_solve(const float* L, const float* invdiag, flo
   if (lane < nh) x[lane + 32] = x1;
   __syncwarp();
 }
+// Level-scheduled variant of ldl_solve for factors that kept the dof tree's pattern (candidate, not yet wired
+// into the kernel: DESIGN.md 9.1).  Pivots of one tree level are independent, so up to four of them are
+// broadcast together before their updates are applied: the dependent chain is one step per level (16 for G1)
+// instead of one per dof (35), at the same number of loads and FMAs.  `order` / `lstart`: b2_build_dof_levels.
+__device__ __noinline__ void ldl_solve_levels(const float* L, const float* invdiag, float* x, int n,
+                                              const unsigned char* order, const unsigned char* lstart, int nlevel,
+                                              int lane) {
+  float x0 = lane < n ? x[lane] : 0.f;
+  float x1 = lane + 32 < n ? x[lane + 32] : 0.f;
+  const float d0 = lane < n ? invdiag[lane] : 0.f, d1 = lane + 32 < n ? invdiag[lane + 32] : 0.f;
+  const int r0 = lane * (lane + 1) >> 1, r1 = (lane + 32) * (lane + 33) >> 1;
+  // L^T y = b: deepest level first; x_j -= A[k,j] / d_k * y_k for the ancestors j of pivot k (row k, lane = column)
+#pragma unroll 1
+  for (int lv = nlevel - 1; lv >= 0; lv--) {
+    const int e = lstart[lv + 1];
+#pragma unroll 1
+    for (int i = lstart[lv]; i < e; i += 4) {
+      const int c = min(4, e - i);
+      int k[4];
+      float y[4];
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        k[t] = t < c ? order[i + t] : 0;
+        float v = __shfl_sync(FULL, k[t] < 32 ? x0 : x1, k[t] & 31);
+        y[t] = t < c ? v * invdiag[k[t]] : 0.f;
+      }
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const int rk = k[t] * (k[t] + 1) >> 1;
+        if (t < c && lane < k[t]) x0 -= L[rk + lane] * y[t];
+        if (t < c && lane + 32 < k[t]) x1 -= L[rk + lane + 32] * y[t];
+      }
+    }
+  }
+  x0 *= d0; x1 *= d1;  // D z = y
+  // L x = z: root level first; x_k -= A[k,j] / d_k * x_j for the descendants k of pivot j (column j, lane = row)
+#pragma unroll 1
+  for (int lv = 0; lv < nlevel; lv++) {
+    const int e = lstart[lv + 1];
+#pragma unroll 1
+    for (int i = lstart[lv]; i < e; i += 4) {
+      const int c = min(4, e - i);
+      int j[4];
+      float v[4];
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        j[t] = t < c ? order[i + t] : 0;
+        v[t] = __shfl_sync(FULL, j[t] < 32 ? x0 : x1, j[t] & 31);
+      }
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        if (t < c && lane > j[t] && lane < n) x0 -= L[r0 + j[t]] * d0 * v[t];
+        if (t < c && lane + 32 > j[t] && lane + 32 < n) x1 -= L[r1 + j[t]] * d1 * v[t];
+      }
+    }
+  }
+  if (lane < n) x[lane] = x0;
+  if (lane + 32 < n) x[lane + 32] = x1;
+  __syncwarp();
+}
 // y = M x for packed symmetric M (both in shared memory).  One column loop for all lanes (entry (i,j) lives
 // at tri(max)+min), four independent accumulators so the loads of four columns are in flight together.
 __device__ __noinline__ void symv(const float* M, const float* x, float* y, int n, int lane) {
