@@ -14,7 +14,7 @@
 // tests/emul/warp_emul.h (32 host threads in lock step), so they are unit-tested without a GPU.
 #pragma once
 #ifdef B2_HOST_EMULATION
-#include "warp_emul.h"
+#include "cuda_emul.h"
 #else
 #include <cuda_runtime.h>
 #endif
@@ -162,7 +162,17 @@ __device__ __forceinline__ void bulk_commit_wait() {
 __device__ __forceinline__ void fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-#endif  // !B2_HOST_EMULATION
+#else
+// host emulation: the bulk copies are plain memcpy by the issuing lane; the warp barrier that precedes
+// mbar_wait in the kernel orders them
+inline void mbar_init(unsigned long long*, int) {}
+inline void mbar_expect(unsigned long long*, uint32_t) {}
+inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long*) { memcpy(dst, src, bytes); }
+inline void mbar_wait(unsigned long long*, uint32_t) {}
+inline void bulk_s2g(void* dst, const void* src, uint32_t bytes) { memcpy(dst, src, bytes); }
+inline void bulk_commit_wait() {}
+inline void fence_async_smem() {}
+#endif  // B2_HOST_EMULATION
 
 #define MP(arr) (m.arr.p + (size_t)w * m.arr.stride)
 
@@ -678,7 +688,6 @@ __device__ __noinline__ float rows_cost(int fc, int fl, const float* con, const 
 
 }  // namespace b2
 
-#ifndef B2_HOST_EMULATION
 // ==================================================================================================
 // The kernel
 // ==================================================================================================
@@ -686,7 +695,11 @@ template <bool STEP>
 __global__ void __launch_bounds__(32 * B2_WARPS_PER_CTA, B2_MIN_CTAS)
 b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevData dd) {
   using namespace b2;
+#ifdef B2_HOST_EMULATION
+  float* smem_all = (float*)warp_emul::ctx().dyn_smem;
+#else
   extern __shared__ __align__(16) float smem_all[];
+#endif
   __shared__ __align__(8) unsigned long long bars[B2_WARPS_PER_CTA];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = blockIdx.x * B2_WARPS_PER_CTA + warp;
@@ -2139,4 +2152,3 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   __syncwarp();
   }  // sub-step loop
 }
-#endif  // !B2_HOST_EMULATION

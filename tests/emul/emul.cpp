@@ -12,17 +12,18 @@ namespace {
 struct Job { std::function<void(int)>* fn; int lane; };
 void* trampoline(void* p) {
   Job* j = (Job*)p;
-  warp_emul::lane() = j->lane;
+  warp_emul::tl().lane = j->lane;
+  warp_emul::tl().warp = 0;
   (*j->fn)(j->lane);
   return nullptr;
 }
 void run_warp(std::function<void(int)> fn) {
-  pthread_barrier_init(&warp_emul::ctx().bar, nullptr, 32);
+  pthread_barrier_init(&warp_emul::ctx().w[0].bar, nullptr, 32);
   pthread_t th[32];
   Job jobs[32];
   for (int l = 0; l < 32; l++) { jobs[l] = {&fn, l}; pthread_create(&th[l], nullptr, trampoline, &jobs[l]); }
   for (int l = 0; l < 32; l++) pthread_join(th[l], nullptr);
-  pthread_barrier_destroy(&warp_emul::ctx().bar);
+  pthread_barrier_destroy(&warp_emul::ctx().w[0].bar);
 }
 }  // namespace
 

@@ -1,0 +1,202 @@
+"""The whole product library (b2sim.cu + the fused step kernel) compiled for the host (tests/emul/build.py:
+g++ against cuda_emul.h, one warp per CTA on 32 lock-step threads) and driven through its C ABI — the same
+parity checks as tests/test_parity_gpu.py, without a GPU.  Slow (every shuffle is a pthread barrier), so the
+batches are tiny; tolerances are the GPU tests' (fp32 engine vs fp64 oracle)."""
+
+import ctypes
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from mjlab_b200.sim import native
+from oracle.oracle import Oracle
+from util import load_oracle, make_states, relerr, terrain_states
+
+sys.path.insert(0, str(Path(__file__).parent / "emul"))
+
+
+@pytest.fixture(scope="module")
+def lib():
+  from build import build
+
+  L = ctypes.CDLL(str(build()))
+  L.b2_last_error.restype = ctypes.c_char_p
+  vp, ci = ctypes.c_void_p, ctypes.c_int
+  L.b2_create.argtypes = [ctypes.POINTER(native.B2ModelDesc), ci, ci, ci, ci, ctypes.POINTER(vp)]
+  L.b2_destroy.argtypes = [vp]
+  L.b2_get_field.argtypes = [vp, ci, ctypes.c_char_p, ctypes.POINTER(native.B2Tensor)]
+  L.b2_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_double]
+  L.b2_get_option.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]
+  L.b2_step.argtypes = [vp, vp]
+  L.b2_forward.argtypes = [vp, vp]
+  L.b2_step_n.argtypes = [vp, ci, vp]
+  L.b2_forward_masked.argtypes = [vp, vp, vp]
+  return L
+
+
+class EmulSim:
+  """ctypes + numpy views over the emulated library ("device" memory is host memory)."""
+
+  def __init__(self, lib, model, nworld, ncon=0):
+    self.lib, self.n = lib, nworld
+    self.desc, self._keep = native.make_model_desc(model)
+    self.h = ctypes.c_void_p()
+    rc = lib.b2_create(ctypes.byref(self.desc), nworld, ncon, 0, 0, ctypes.byref(self.h))
+    assert rc == 0, lib.b2_last_error(None).decode()
+    lib.b2_set_option(self.h, b"debug_outputs", 1.0)
+    lib.b2_set_option(self.h, b"sorted_dispatch", 0.0)  # (the 1024-thread sort kernel works but is slow to emulate)
+
+  def field(self, name, which=0):
+    t = native.B2Tensor()
+    rc = self.lib.b2_get_field(self.h, which, name.encode(), ctypes.byref(t))
+    assert rc == 0, name
+    dt = {0: np.float32, 1: np.int32}[t.dtype] if t.dtype in (0, 1) else np.float32
+    shape = tuple(t.shape[i] for i in range(t.ndim))
+    strides = tuple(t.stride[i] * 4 for i in range(t.ndim))
+    total = 1 + sum((s - 1) * st for s, st in zip(shape, (t.stride[i] for i in range(t.ndim))))
+    buf = (ctypes.c_byte * (total * 4)).from_address(t.ptr)
+    return np.ndarray(shape, dtype=dt, buffer=buf, strides=strides)
+
+  def load(self, st):
+    for k, v in st.items():
+      self.field(k)[...] = v
+
+  def option(self, key):
+    v = ctypes.c_double()
+    self.lib.b2_get_option(self.h, key.encode(), ctypes.byref(v))
+    return v.value
+
+  def forward(self):
+    assert self.lib.b2_forward(self.h, None) == 0
+
+  def step(self, n=1):
+    assert self.lib.b2_step_n(self.h, n, None) == 0
+
+  def close(self):
+    self.lib.b2_destroy(self.h)
+
+
+def _check_forward(sim, o, n, acc_tol=1e-3):
+  nc = o.ncon.ravel()
+  assert (sim.field("ncon").ravel() == nc).all() and (sim.field("nefc").ravel() == o.nefc.ravel()).all()
+  cg, og = sim.field("contact_geom"), o.contact_geom.reshape(n, -1, 2)
+  for w in range(n):
+    assert (cg[w, : nc[w]] == og[w, : nc[w]]).all()
+    if nc[w]:
+      assert np.abs(sim.field("contact_dist")[w, : nc[w]] - o.contact_dist[w, : nc[w]]).max() < 1e-5
+  for f in ["xpos", "xquat", "xmat", "xipos", "subtree_com", "cvel", "geom_xpos", "geom_xmat", "site_xpos",
+            "actuator_force", "qfrc_bias", "qfrc_smooth", "qM"]:
+    e = relerr(np.asarray(sim.field(f)).reshape(n, -1), o.field(f).reshape(n, -1)).max()
+    assert e < 1e-5, (f, e)
+  assert relerr(sim.field("qacc_smooth"), o.qacc_smooth).max() < 1e-4
+  e = relerr(sim.field("qacc"), o.qacc, floor=10.0)
+  assert e.max() < acc_tol, e
+  assert np.abs(sim.field("sensordata") - o.sensordata).max() < 1e-3
+
+
+@pytest.mark.parametrize("name,n", [("go1_flat", 4), ("g1_flat", 3)])
+def test_emulated_kernel_forward_and_step_parity(lib, name, n):
+  from mjlab_b200.asset_zoo import load_compiled
+
+  m = load_compiled(name)
+  sim = EmulSim(lib, m, n)
+  # derived fields are valid right after construction (b2_create ran one forward at qpos0)
+  assert np.isfinite(sim.field("xpos")).all() and (sim.field("time") == 0).all()
+  o = Oracle(m, nworld=n, maxcon=int(sim.option("maxcon")))
+  st = make_states(m, n, seed=5)
+  load_oracle(o, st)
+  sim.load(st)
+  o.forward()
+  sim.forward()
+  _check_forward(sim, o, n)
+  for _ in range(2):
+    o.step()
+  sim.step(2)
+  assert relerr(sim.field("qpos"), o.qpos).max() < 1e-4
+  assert relerr(sim.field("qvel"), o.qvel).max() < 5e-3
+  assert sim.field("time").ravel() == pytest.approx(2 * float(m.opt_timestep))
+  sim.close()
+
+
+def test_emulated_kernel_on_stairs_and_masked_forward(lib):
+  from mjlab_b200.asset_zoo import load_compiled
+
+  m = load_compiled("go1_stairs_small")
+  n = 4
+  sim = EmulSim(lib, m, n)
+  o = Oracle(m, nworld=n, maxcon=int(sim.option("maxcon")))
+  st = terrain_states(m, n, 104, 1.4)
+  load_oracle(o, st)
+  sim.load(st)
+  o.forward()
+  sim.forward()
+  _check_forward(sim, o, n, acc_tol=2e-3)
+  assert int(o.ncon.max()) >= 5  # box terrain contacts through the grid broadphase
+  # masked forward: only the selected worlds are recomputed
+  before = sim.field("xpos").copy()
+  sim.field("qpos")[:, 2] += 1.0
+  mask = np.array([0, 1, 0, 1], dtype=np.uint8)
+  assert lib.b2_forward_masked(sim.h, mask.ctypes.data_as(ctypes.c_void_p), None) == 0
+  after = sim.field("xpos")
+  assert (after[0] == before[0]).all() and (after[2] == before[2]).all()
+  assert np.abs(after[1, 2:, 2] - before[1, 2:, 2] - 1.0).max() < 1e-5  # (body 1 is the static terrain)
+  sim.close()
+
+
+def test_emulated_kernel_dense_and_tree_schedules_agree(lib):
+  from mjlab_b200.asset_zoo import load_compiled
+
+  m = load_compiled("go1_flat")
+  n = 3
+  a, b = EmulSim(lib, m, n), EmulSim(lib, m, n)
+  lib.b2_set_option(b.h, b"dense_factor", 1.0)
+  st = make_states(m, n, seed=9)
+  a.load(st)
+  b.load(st)
+  a.step(1)
+  b.step(1)
+  assert relerr(a.field("qvel"), b.field("qvel")).max() < 1e-4
+  a.close()
+  b.close()
+
+
+def test_emulated_kernel_obstacle_course(lib):
+  """Pair table + static grid + all six primitive pair types inside the emulated kernel, a few resynchronised steps."""
+  from test_boxes_terrain import obstacle_course_xml
+
+  from mjlab_b200.compiler import Spec
+
+  m = Spec.from_string(obstacle_course_xml()).compile()
+  n = 2
+  sim = EmulSim(lib, m, n, ncon=96)
+  o = Oracle(m, nworld=n, maxcon=int(sim.option("maxcon")))
+  rng = np.random.default_rng(1)
+  q = np.tile(m.qpos0, (n, 1))
+  q += rng.uniform(-0.08, 0.08, q.shape) * (np.arange(q.shape[1]) % 7 < 3)
+  q[:, 2::7] -= 0.42  # start near the ground so that contacts exist from the first step
+  st = dict(qpos=q, qvel=rng.uniform(-0.3, 0.3, (n, int(m.nv))))
+  load_oracle(o, st)
+  sim.load(st)
+  seen = 0
+  for it in range(6):
+    o.forward()
+    sim.forward()
+    nc = o.ncon.ravel()
+    assert (sim.field("ncon").ravel() == nc).all()
+    cg, og = sim.field("contact_geom"), o.contact_geom.reshape(n, -1, 2)
+    for w in range(n):
+      a = sorted(zip(map(tuple, cg[w, : nc[w]].tolist()), sim.field("contact_dist")[w, : nc[w]].tolist()))
+      b = sorted(zip(map(tuple, og[w, : nc[w]].tolist()), o.contact_dist[w, : nc[w]].tolist()))
+      assert [x[0] for x in a] == [x[0] for x in b]
+      if nc[w]:
+        assert np.abs(np.array([x[1] for x in a]) - np.array([x[1] for x in b])).max() < 2e-5
+    assert relerr(sim.field("qacc"), o.qacc, floor=10.0).max() < 1e-2
+    seen = max(seen, int(nc.max()))
+    o.step()
+    sim.step(1)
+    for f in ("qpos", "qvel", "qacc_warmstart"):
+      sim.field(f)[...] = getattr(o, f)
+  assert seen >= 6
+  sim.close()
