@@ -326,8 +326,8 @@ __device__ __noinline__ void ldl_solve(const float* L, const float* invdiag, flo
   if (lane < nh) x[lane + 32] = x1;
   __syncwarp();
 }
-// Level-scheduled variant of ldl_solve for factors that kept the dof tree's pattern (candidate, not yet wired
-// into the kernel: DESIGN.md 9.1).  Pivots of one tree level are independent, so up to four of them are
+// Level-scheduled variant of ldl_solve for factors that kept the dof tree's pattern (experiment, compiled into
+// the kernel only with -DB2_LEVEL_SOLVE: DESIGN.md 9.1).  Pivots of one tree level are independent, so up to four of them are
 // broadcast together before their updates are applied: the dependent chain is one step per level (16 for G1)
 // instead of one per dof (35), at the same number of loads and FMAs.  `order` / `lstart`: b2_build_dof_levels.
 __device__ __noinline__ void ldl_solve_levels(const float* L, const float* invdiag, float* x, int n,
@@ -709,10 +709,23 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   // per-CTA copy of the factorisation pair schedule (shared by the CTA's warps)
   unsigned* s_sched = (unsigned*)(smem_all + (size_t)B2_WARPS_PER_CTA * m.lay.total);
 #define FACTOR(sp) ldl_factor(H, invdiag, nv, s_sched, (const int*)s_sched + m.ldl_nsparse, m.ldl_dense, sp, lane)
-#define SOLVE(v) ldl_solve(H, invdiag, v, nv, lane)
+#ifdef B2_LEVEL_SOLVE
+  // experiment: level-scheduled sweeps whenever the factor kept the dof tree's pattern
+  const unsigned char* s_lvl = (const unsigned char*)(s_sched + m.ldl_nsparse + 18);
+#define SOLVE(v, tree)                                                                       \
+  do {                                                                                       \
+    if (tree) ldl_solve_levels(H, invdiag, v, nv, s_lvl, s_lvl + 64, m.ldl_nlevel, lane);    \
+    else ldl_solve(H, invdiag, v, nv, lane);                                                 \
+  } while (0)
+#else
+#define SOLVE(v, tree) ldl_solve(H, invdiag, v, nv, lane)
+#endif
 #pragma unroll 1
   for (int i = threadIdx.x; i < m.ldl_nsparse; i += 32 * B2_WARPS_PER_CTA) s_sched[i] = m.ldl_sparse[i];
   if (threadIdx.x < 18) s_sched[m.ldl_nsparse + threadIdx.x] = (unsigned)m.ldl_start[threadIdx.x];
+#ifdef B2_LEVEL_SOLVE
+  for (int i = threadIdx.x; i < 34; i += 32 * B2_WARPS_PER_CTA) s_sched[m.ldl_nsparse + 18 + i] = m.ldl_levels[i];
+#endif
   __syncthreads();  // the only block barrier; nothing below synchronises across warps
   if (w >= dd.nworld) return;
   if (dd.world_mask != nullptr && dd.world_mask[w] == 0) return;
@@ -1627,7 +1640,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   for (int i = lane; i < (m.ntri + 3) >> 2; i += 32) ((float4*)H)[i] = ((const float4*)Mq)[i];  // both regions are 16 B aligned and padded
   __syncwarp();
   FACTOR(true);
-  SOLVE(qacc_smooth);
+  SOLVE(qacc_smooth, true);
   if (m.debug & 1)
     #pragma unroll 1
     for (int i = lane; i < nv; i += 32) dd.qacc_smooth.p[(size_t)w * dd.qacc_smooth.stride + i] = qacc_smooth[i];
@@ -1848,7 +1861,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       #pragma unroll 1
       for (int i = lane; i < nv; i += 32) search[i] = -grad[i];
       __syncwarp();
-      SOLVE(search);
+      SOLVE(search, treeok);
       PHASE_MARK(14);
       // ---- exact line search along `search` --------------------------------------------------
       symv(Mq, search, Mv, nv, lane);
@@ -2076,7 +2089,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       for (int i = lane; i < nv; i += 32) tmpv[i] = qfrc_smooth[i] + qfrc_c[i];
       __syncwarp();
       FACTOR(true);
-      SOLVE(tmpv);
+      SOLVE(tmpv, true);
     } else {
       #pragma unroll 1
       for (int i = lane; i < nv; i += 32) tmpv[i] = qacc[i];

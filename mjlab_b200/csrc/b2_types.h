@@ -100,6 +100,11 @@ struct DevModel {
   const unsigned *ldl_dense, *ldl_sparse;
   int ldl_start[18];
   int ldl_nsparse;
+#ifdef B2_LEVEL_SOLVE
+  // experiment: dof tree levels for ldl_solve_levels; 34 words staged after the block starts
+  unsigned ldl_levels[34];  // bytes: order[64], lstart[66] (padded), b2_build_dof_levels
+  int ldl_nlevel;
+#endif
   // float arrays (expandable per world)
   FArr body_pos, body_quat, body_ipos, body_iquat, body_mass, body_subtreemass, body_inertia,
       body_invweight0, jnt_pos, jnt_axis, jnt_range, jnt_solref, jnt_solimp, jnt_margin,

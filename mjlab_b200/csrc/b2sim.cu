@@ -11,6 +11,11 @@
 #include "../../include/b2sim.h"
 #include "b2_kernel.cuh"
 #include "b2_tables.h"
+#ifdef B2_LEVEL_SOLVE
+#define B2_LEVEL_WORDS 34
+#else
+#define B2_LEVEL_WORDS 0
+#endif
 #include "b2_env.cuh"
 
 static thread_local std::string g_err;
@@ -564,6 +569,13 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
     std::vector<unsigned> dense, sparse;
     b2_build_ldl_schedules(m.nv, s->mi["dof_parentid"].data(), dense, sparse, m.ldl_start);
     m.ldl_nsparse = (int)sparse.size();
+#ifdef B2_LEVEL_SOLVE
+    {
+      unsigned char* lv = (unsigned char*)m.ldl_levels;
+      memset(lv, 0, sizeof(m.ldl_levels));
+      m.ldl_nlevel = b2_build_dof_levels(m.nv, s->mi["dof_parentid"].data(), lv, lv + 64);
+    }
+#endif
     rc |= dev_upload<unsigned>(s, dense, &m.ldl_dense);
     rc |= dev_upload<unsigned>(s, sparse, &m.ldl_sparse);
   }
@@ -674,7 +686,7 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
   L.gW = alloc(5 * mc); L.sens = off;
   int endB = off;
   L.total = pad4(std::max(endA, endB));
-  s->smem_bytes = sizeof(float) * ((size_t)L.total * B2_WARPS_PER_CTA + pad4(m.ldl_nsparse + 18));
+  s->smem_bytes = sizeof(float) * ((size_t)L.total * B2_WARPS_PER_CTA + pad4(m.ldl_nsparse + 18 + B2_LEVEL_WORDS));
   if (s->smem_bytes > 227 * 1024) {
     b2_destroy(s);
     return fail("b2_create: model too large for the per-environment shared-memory block");

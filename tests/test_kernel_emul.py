@@ -17,11 +17,10 @@ from util import load_oracle, make_states, relerr, terrain_states
 sys.path.insert(0, str(Path(__file__).parent / "emul"))
 
 
-@pytest.fixture(scope="module")
-def lib():
+def _load(defines=()):
   from build import build
 
-  L = ctypes.CDLL(str(build()))
+  L = ctypes.CDLL(str(build(defines=defines)))
   L.b2_last_error.restype = ctypes.c_char_p
   vp, ci = ctypes.c_void_p, ctypes.c_int
   L.b2_create.argtypes = [ctypes.POINTER(native.B2ModelDesc), ci, ci, ci, ci, ctypes.POINTER(vp)]
@@ -34,6 +33,11 @@ def lib():
   L.b2_step_n.argtypes = [vp, ci, vp]
   L.b2_forward_masked.argtypes = [vp, vp, vp]
   return L
+
+
+@pytest.fixture(scope="module")
+def lib():
+  return _load()
 
 
 class EmulSim:
@@ -199,4 +203,25 @@ def test_emulated_kernel_obstacle_course(lib):
     for f in ("qpos", "qvel", "qacc_warmstart"):
       sim.field(f)[...] = getattr(o, f)
   assert seen >= 6
+  sim.close()
+
+
+def test_emulated_level_scheduled_solve_experiment():
+  """-DB2_LEVEL_SOLVE (off by default): same forward / step parity with the level-scheduled sweeps."""
+  from mjlab_b200.asset_zoo import load_compiled
+
+  L = _load(("B2_LEVEL_SOLVE",))
+  m = load_compiled("go1_flat")
+  n = 3
+  sim = EmulSim(L, m, n)
+  o = Oracle(m, nworld=n, maxcon=int(sim.option("maxcon")))
+  st = make_states(m, n, seed=5)
+  load_oracle(o, st)
+  sim.load(st)
+  o.forward()
+  sim.forward()
+  _check_forward(sim, o, n)
+  o.step()
+  sim.step(1)
+  assert relerr(sim.field("qvel"), o.qvel).max() < 5e-3
   sim.close()
