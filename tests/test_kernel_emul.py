@@ -225,3 +225,48 @@ def test_emulated_level_scheduled_solve_experiment():
   sim.step(1)
   assert relerr(sim.field("qvel"), o.qvel).max() < 5e-3
   sim.close()
+
+
+def test_emulated_host_entry_fused_decimation_and_field_expansion(lib):
+  """Three host paths no CPU test could reach before: b2_step_host (host buffers in/out) equals b2_step_n, the
+  in-kernel decimation loop (`fused_decimation`) equals separate launches, and an expanded per-world model field
+  (geom_friction) is what the kernel reads."""
+  from mjlab_b200.asset_zoo import load_compiled
+
+  lib.b2_step_host.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+  lib.b2_expand_model_field.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.POINTER(native.B2Tensor)]
+  m = load_compiled("go1_flat")
+  n, nq, nv, nu = 3, int(m.nq), int(m.nv), int(m.nu)
+  st = make_states(m, n, seed=21)
+  ref, host, fused = EmulSim(lib, m, n), EmulSim(lib, m, n), EmulSim(lib, m, n)
+  for s in (ref, host, fused):
+    s.load(st)
+  ref.step(2)
+  # host-buffer entry: ctrl from a dense host array, qpos/qvel back into dense host arrays
+  ctrl = np.ascontiguousarray(st["ctrl"], dtype=np.float32)
+  qpos_out, qvel_out = np.zeros((n, nq), dtype=np.float32), np.zeros((n, nv), dtype=np.float32)
+  assert lib.b2_step_host(host.h, ctrl.ctypes.data, 2, qpos_out.ctypes.data, qvel_out.ctypes.data, None) == 0
+  assert (qpos_out == ref.field("qpos")).all() and (qvel_out == ref.field("qvel")).all()
+  # decimation fused into one launch
+  lib.b2_set_option(fused.h, b"fused_decimation", 1.0)
+  fused.step(2)
+  assert np.abs(fused.field("qpos") - ref.field("qpos")).max() < 1e-6
+  assert np.abs(fused.field("qvel") - ref.field("qvel")).max() < 1e-5
+  # per-world friction: world 0 keeps the model's value, world 1 gets ice under its feet
+  t = native.B2Tensor()
+  assert lib.b2_expand_model_field(ref.h, b"geom_friction", None, ctypes.byref(t)) == 0
+  fr = ref.field("geom_friction", which=1)
+  assert fr.shape[0] == n and fr.strides[0] > 0  # a real leading world dimension now
+  fr[1, :, 0] = 1e-3
+  st2 = make_states(m, n, seed=22, vel=1.5)
+  ref.load(st2)
+  ref.forward()
+  qa = ref.field("qacc").copy()
+  fr[1, :, 0] = np.asarray(m.geom_friction)[:, 0]
+  ref.forward()
+  qb = ref.field("qacc")
+  assert np.abs(qa[0] - qb[0]).max() == 0.0 and np.abs(qa[2] - qb[2]).max() == 0.0  # untouched worlds: identical
+  if int(ref.field("ncon").ravel()[1]) > 0:
+    assert np.abs(qa[1] - qb[1]).max() > 1e-3  # friction matters for the sliding world
+  for s in (ref, host, fused):
+    s.close()
