@@ -252,21 +252,20 @@ def test_emulated_host_entry_fused_decimation_and_field_expansion(lib):
   fused.step(2)
   assert np.abs(fused.field("qpos") - ref.field("qpos")).max() < 1e-6
   assert np.abs(fused.field("qvel") - ref.field("qvel")).max() < 1e-5
-  # per-world friction: world 0 keeps the model's value, world 1 gets ice under its feet
+  # per-world friction: world 0 keeps the model's value, the others get ice under their feet
   t = native.B2Tensor()
   assert lib.b2_expand_model_field(ref.h, b"geom_friction", None, ctypes.byref(t)) == 0
   fr = ref.field("geom_friction", which=1)
   assert fr.shape[0] == n and fr.strides[0] > 0  # a real leading world dimension now
-  fr[1, :, 0] = 1e-3
   st2 = make_states(m, n, seed=22, vel=1.5)
   ref.load(st2)
   ref.forward()
   qa = ref.field("qacc").copy()
-  fr[1, :, 0] = np.asarray(m.geom_friction)[:, 0]
+  fr[1:, :, 0] = 1e-3
   ref.forward()
   qb = ref.field("qacc")
-  assert np.abs(qa[0] - qb[0]).max() == 0.0 and np.abs(qa[2] - qb[2]).max() == 0.0  # untouched worlds: identical
-  if int(ref.field("ncon").ravel()[1]) > 0:
-    assert np.abs(qa[1] - qb[1]).max() > 1e-3  # friction matters for the sliding world
+  assert np.abs(qa[0] - qb[0]).max() == 0.0  # the untouched world: bit-identical
+  # (only the feet have condim 3; a world whose contacts are all frictionless would not notice)
+  assert max(np.abs(qa[w] - qb[w]).max() for w in range(1, n)) > 1e-3
   for s in (ref, host, fused):
     s.close()
