@@ -350,3 +350,50 @@ def test_emulated_env_native_mdp_kernels_match_torch_reference(monkeypatch):
   assert resets >= 3  # time-outs (every 2 steps) exercised the masked reset path
   a.close()
   b.close()
+
+
+def _limb(name, n, pos, axes):
+  s, close = "", ""
+  for k in range(n):
+    p = pos if k == 0 else "0 0 -0.12"
+    s += (f'<body name="{name}{k}" pos="{p}"><joint name="{name}j{k}" axis="{axes[k % len(axes)]}" range="-1.2 1.2" '
+          f'limited="true" damping="0.2" armature="0.01"/><geom type="capsule" fromto="0 0 0 0 0 -0.12" size="0.03" mass="0.4"/>')
+    close += "</body>"
+  return s + close
+
+
+def test_emulated_kernel_synthetic_45dof_robot(lib):
+  """Sizes no GPU test reaches: a 45-dof, 41-body floating base with five 7-8 joint limbs, 781 collision pairs,
+  self-collisions (dense factorisation schedule), ~40 contacts / ~160 constraint rows per world."""
+  from mjlab_b200.compiler import Spec
+
+  xml = f"""<mujoco><compiler angle="radian"/><option timestep="0.004" integrator="implicitfast"/>
+  <worldbody><geom name="floor" type="plane" size="0 0 1"/>
+  <body name="base" pos="0 0 0.55"><freejoint/><geom type="box" size="0.2 0.15 0.06" mass="4"/>
+  {_limb("a", 8, "0.18 0.12 -0.06", ["1 0 0", "0 1 0"])}{_limb("b", 8, "0.18 -0.12 -0.06", ["0 1 0", "1 0 0"])}
+  {_limb("c", 8, "-0.18 0.12 -0.06", ["1 0 0", "0 1 0", "0 0 1"])}{_limb("d", 8, "-0.18 -0.12 -0.06", ["0 1 0", "0 0 1"])}
+  {_limb("e", 7, "0 0 0.06", ["0 1 0", "1 0 0"])}
+  </body></worldbody></mujoco>"""
+  m = Spec.from_string(xml).compile()
+  assert int(m.nv) == 45 and int(m.nbody) == 41 and int(m.npair) > 500
+  n = 2
+  sim = EmulSim(lib, m, n, ncon=64)
+  o = Oracle(m, nworld=n, maxcon=int(sim.option("maxcon")))
+  rng = np.random.default_rng(0)
+  q = np.tile(m.qpos0, (n, 1))
+  q[:, 2] += rng.uniform(-0.25, 0.0, n)
+  q[:, 7:] += rng.uniform(-0.9, 0.9, (n, int(m.nq) - 7))
+  st = dict(qpos=q, qvel=rng.uniform(-1, 1, (n, 45)), qacc_warmstart=rng.uniform(-1, 1, (n, 45)))
+  load_oracle(o, st)
+  sim.load(st)
+  o.forward()
+  sim.forward()
+  assert (sim.field("ncon").ravel() == o.ncon.ravel()).all() and int(o.ncon.min()) >= 20
+  assert (sim.field("nefc").ravel() == o.nefc.ravel()).all()
+  for f in ["xpos", "cvel", "qfrc_bias", "qM"]:
+    assert relerr(np.asarray(sim.field(f)).reshape(n, -1), o.field(f).reshape(n, -1)).max() < 1e-5, f
+  assert relerr(sim.field("qacc"), o.qacc, floor=10.0).max() < 1e-3
+  o.step()
+  sim.step(1)
+  assert relerr(sim.field("qvel"), o.qvel).max() < 1e-3
+  sim.close()
