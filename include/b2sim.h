@@ -66,7 +66,9 @@ typedef struct b2_sim b2_sim;
 /* Create a simulation: uploads the model, allocates Data for `nworld` worlds on `cuda_device`,
  * initialises qpos=qpos0 and runs one forward pass so every derived field is valid
  * (reference sim.py:106-107 relies on a forwarded MjData).
- *   ncon_per_world <= 0 : default capacity; njmax <= 0 : default.  */
+ *   ncon_per_world <= 0 : default capacity; njmax <= 0 : default.
+ *   njmax is recorded (B2Stats.nefc_cap) but never truncates: the solver is matrix-free, so constraint rows
+ *   need no storage and every contact within the contact capacity gets its rows (upstream drops rows past njmax). */
 int b2_create(const B2ModelDesc* model, int nworld, int ncon_per_world, int njmax,
               int cuda_device, b2_sim** out);
 int b2_destroy(b2_sim* sim);

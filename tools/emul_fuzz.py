@@ -60,7 +60,7 @@ def main():
     m = Spec.from_string(robot_xml(rng, a.limbs, a.joints)).compile()
     n, nv = a.worlds, int(m.nv)
     sim = EmulSim(lib, m, n, ncon=96)
-    o = Oracle(m, nworld=n, maxcon=int(sim.option("maxcon")))
+    o = Oracle(m, nworld=n, maxcon=int(sim.option("maxcon")), njmax=2000)  # (the engine never truncates at njmax)
     q = np.tile(m.qpos0, (n, 1))
     q[:, 2] += rng.uniform(-0.3, 0.3, n)
     q[:, 7:] += rng.uniform(-1.0, 1.0, (n, int(m.nq) - 7))
