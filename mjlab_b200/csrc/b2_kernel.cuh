@@ -1396,7 +1396,9 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
           float u = -dot3(a1, dif), v = dot3(a2, dif);
           float det = ma * mc - mb * mb;
           float len1 = s1[1], len2 = s2[1];
-          if (fabsf(det) >= MINVAL) {
+          // parallel axes: MuJoCo tests |det| < 1e-15 in double; in fp32 det = sin^2(angle) of exactly parallel
+          // unit axes evaluates to ~1e-7, so the test is made at 1e-6 (angles below 0.06 degrees)
+          if (fabsf(det) >= 1e-6f) {
             float x1 = (mc * u - mb * v) / det, x2 = (ma * v - mb * u) / det;
             if (x1 > len1) { x1 = len1; x2 = (v - mb * len1) / mc; }
             else if (x1 < -len1) { x1 = -len1; x2 = (v + mb * len1) / mc; }

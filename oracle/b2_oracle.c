@@ -530,7 +530,8 @@ static int capsule_capsule(RawCon* c, real margin, const real* p1, const real* m
   real u = -dot3(a1, dif), v = dot3(a2, dif);
   real det = ma*mc - mb*mb;
   real len1 = s1[1], len2 = s2[1];
-  if (fabs(det) >= MINVAL) { /* general configuration */
+  /* parallel test at fp64 resolution (mjMINVAL) or, in the fp32 build, at what fp32 can resolve (det ~ 1e-7 noise) */
+  if (fabs(det) >= (sizeof(real) == 4 ? (real)1e-6 : MINVAL)) { /* general configuration */
     real x1 = (mc*u - mb*v)/det, x2 = (ma*v - mb*u)/det;
     if (x1 > len1) { x1 = len1; x2 = (v - mb*len1)/mc; }
     else if (x1 < -len1) { x1 = -len1; x2 = (v + mb*len1)/mc; }
