@@ -174,3 +174,30 @@ def test_b2_create_rejects_malformed_model_tables(g1_model):
     m2.arrays[field] = np.ascontiguousarray(mod(np.asarray(g1_model.arrays[field])))
     rc, msg = create(m2)
     assert rc != 0 and expect in msg, (field, msg)
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+  """`bench.py --impl reference` (the CPU arm the driver launches, also under torchrun where OMP_NUM_THREADS=1):
+  one JSON line with the contract's keys, all available cores in use."""
+  import json
+  import os
+  import subprocess
+  import sys
+
+  root = Path(__file__).resolve().parents[1]
+  env = dict(os.environ, OMP_NUM_THREADS="1")
+  out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, env=env, timeout=600)
+  assert out.returncode == 0, out.stderr[-500:]
+  lines = [l for l in out.stdout.splitlines() if l.strip()]
+  assert len(lines) == 1
+  d = json.loads(lines[0])
+  assert d["impl"] == "reference" and d["metric"] == "env_steps_per_sec" and d["unit"] == "env-steps/s"
+  assert d["higher_is_better"] is True and d["value"] > 0 and d["e2e"]["value"] == d["value"]
+  assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+  assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+  # rank != 0 of a torchrun launch exits quietly
+  env["RANK"] = "1"
+  out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, env=env, timeout=120)
+  assert out.returncode == 0 and out.stdout.strip() == ""
