@@ -1,6 +1,7 @@
 """Fuzz the fused kernel on the host emulation (tests/emul) against the oracle with synthetic robots.
 
   python tools/emul_fuzz.py [--seeds 5] [--limbs 5] [--joints 8] [--worlds 2] [--steps 2]
+  python tools/emul_fuzz.py --scene obstacle [--seeds 6]      # free primitives among static boxes (grid + box routines)
 
 Each seed builds a floating base with `limbs` chains of up to `joints` hinge joints (random axes, limits, capsule
 links; nv <= 64, nbody <= 64), drops it on a plane in a random pose (self-collisions included), and compares one
@@ -67,8 +68,47 @@ def robot_xml(rng, limbs, joints):
   </worldbody><actuator>{acts}</actuator></mujoco>"""
 
 
+def obstacle_runs(lib, seeds, worlds, steps):
+  """Free spheres / capsules / boxes in random orientations among 20+ static boxes, spheres and capsules on a plane
+  (tests/test_boxes_terrain.py: obstacle_course_xml): pair table + static grid + every primitive pair type."""
+  from test_boxes_terrain import obstacle_course_xml
+
+  for seed in range(1, seeds + 1):
+    m = Spec.from_string(obstacle_course_xml(seed=seed, nobst=20 + seed, nobj=9)).compile()
+    n = worlds
+    sim = EmulSim(lib, m, n, ncon=96)
+    o = Oracle(m, nworld=n, maxcon=int(sim.option("maxcon")), njmax=2000)
+    rng = np.random.default_rng(seed)
+    q = np.tile(m.qpos0, (n, 1))
+    q += rng.uniform(-0.08, 0.08, q.shape) * (np.arange(q.shape[1]) % 7 < 3)
+    q[:, 2::7] -= rng.uniform(0.3, 0.45)
+    for b in range(q.shape[1] // 7):
+      v = rng.normal(size=(n, 4))
+      q[:, 7 * b + 3 : 7 * b + 7] = v / np.linalg.norm(v, axis=1, keepdims=True)
+    st = dict(qpos=q, qvel=rng.uniform(-0.5, 0.5, (n, int(m.nv))))
+    for k, v in st.items():
+      o.field(k)[:] = v
+    sim.load(st)
+    worst, seen = 0.0, 0
+    for _ in range(max(steps, 1) + 3):
+      o.forward()
+      sim.forward()
+      assert (sim.field("ncon").ravel() == o.ncon.ravel()).all(), (seed, sim.field("ncon").ravel(), o.ncon.ravel())
+      worst = max(worst, float(relerr(sim.field("qacc"), o.qacc, floor=10.0).max()))
+      seen = max(seen, int(o.ncon.max()))
+      o.step()
+      sim.step(1)
+      for f in ("qpos", "qvel", "qacc_warmstart"):
+        sim.field(f)[...] = getattr(o, f)
+    print(f"seed {seed}: nstatic={int(m.nstatic)} npair={int(m.npair)} max ncon {seen} worst qacc rel err {worst:.2e}")
+    assert worst < 1e-2, seed  # (capsule-box contact ends are defined to ~1e-3 m)
+    sim.close()
+  print("ok")
+
+
 def main():
   ap = argparse.ArgumentParser()
+  ap.add_argument("--scene", choices=["robot", "obstacle"], default="robot")
   ap.add_argument("--seeds", type=int, default=5)
   ap.add_argument("--limbs", type=int, default=5)
   ap.add_argument("--joints", type=int, default=8)
@@ -76,6 +116,8 @@ def main():
   ap.add_argument("--steps", type=int, default=2)
   a = ap.parse_args()
   lib = _load()
+  if a.scene == "obstacle":
+    return obstacle_runs(lib, a.seeds, a.worlds, a.steps)
   worst = 0.0
   for seed in range(a.seeds):
     rng = np.random.default_rng(seed)
