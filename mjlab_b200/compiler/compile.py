@@ -82,6 +82,8 @@ class Model:
     arrays = object.__getattribute__(self, "arrays")
     if name in arrays:
       return arrays[name]
+    if name in ("na", "nmocap", "ntendon", "neq"):
+      return 0  # mjModel sizes of features outside the compiled subset (read by NanGuard / viewers)
     raise AttributeError(name)
 
   # name -> id helpers (mirror model.body(name).id style accessors, Appendix D)
@@ -94,18 +96,20 @@ class Model:
   def body(self, name):
     return _Accessor(id=self.name2id("body", name), name=name)
 
+  # (scalar attributes come back as 1-element arrays, as the MuJoCo bindings return them: `jnt.dofadr[0]`)
   def joint(self, name):
-    i = self.name2id("joint", name)
+    i = name if isinstance(name, int) else self.name2id("joint", name)
     return _Accessor(
-      id=i, name=name, type=int(self.jnt_type[i]),
-      qposadr=int(self.jnt_qposadr[i]), dofadr=int(self.jnt_dofadr[i]),
+      id=i, name=self.names["joint"][i], type=np.array([int(self.jnt_type[i])]),
+      qposadr=np.array([int(self.jnt_qposadr[i])]), dofadr=np.array([int(self.jnt_dofadr[i])]),
+      range=np.asarray(self.jnt_range).reshape(-1, 2)[i],
     )
 
   def geom(self, key):
     i = key if isinstance(key, int) else self.name2id("geom", key)
     return _Accessor(
-      id=i, name=self.names["geom"][i], condim=int(self.geom_condim[i]),
-      priority=int(self.geom_priority[i]), friction=self.geom_friction[i],
+      id=i, name=self.names["geom"][i], condim=np.array([int(self.geom_condim[i])]),
+      priority=np.array([int(self.geom_priority[i])]), friction=self.geom_friction[i],
     )
 
   def actuator(self, key):
@@ -116,8 +120,9 @@ class Model:
     )
 
   def sensor(self, name):
-    i = self.name2id("sensor", name)
-    return _Accessor(id=i, adr=int(self.sensor_adr[i]), dim=int(self.sensor_dim[i]))
+    i = name if isinstance(name, int) else self.name2id("sensor", name)
+    return _Accessor(id=i, name=self.names["sensor"][i], adr=np.array([int(self.sensor_adr[i])]),
+                     dim=np.array([int(self.sensor_dim[i])]))
 
   def key(self, name):
     return _Accessor(**self.keys[name])

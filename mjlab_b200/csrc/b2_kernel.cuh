@@ -191,8 +191,8 @@ __device__ unsigned long long g_phase_cycles[32];
 
 // approximate reciprocal (MUFU.RCP): the IEEE-rounded __frcp_rn costs ~13 instructions per call
 __device__ __forceinline__ float b2_rcp(float x) {
-#ifdef B2_HOST_EMULATION
-  return 1.f / x;
+#if defined(B2_HOST_EMULATION) || defined(B2_PRECISE_RCP)
+  return __frcp_rn(x);
 #else
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -206,11 +206,20 @@ __device__ __forceinline__ float b2_rcp(float x) {
 // A[k,j] = L_kj d_k (j < k), invdiag[k] = 1/d_k, M = L^T D L with L unit lower.  `list`/`start`: per-block
 // schedules (words p | i << 12 | j << 18); with sparse == false (a contact couples two branches) the block
 // with m leading rows takes the first tri(m) words of the dense list instead.
+// `blk0`: index of the first block's schedule when only the leading n x n part of an nv x nv matrix is factorised
+// (n = nv - 4 * blk0).  `snap_n` / `snap`: when the elimination reaches the leading snap_n x snap_n block (all
+// pivots >= snap_n done) that block - the Schur complement onto the first snap_n dofs - is copied to `snap`.
 __device__ __noinline__ void ldl_factor(float* A, float* invdiag, int n, const unsigned* slist, const int* start,
-                                        const unsigned* __restrict__ dense, bool sparse, int lane) {
-  int blk = 0;
+                                        const unsigned* __restrict__ dense, bool sparse, int lane, int blk0 = 0,
+                                        int snap_n = 0, float* snap = nullptr) {
+  int blk = blk0;
 #pragma unroll 1
   for (int kt = n - 1; kt >= 0; kt -= 4, blk++) {
+    if (kt + 1 == snap_n) {
+#pragma unroll 1
+      for (int i = lane; i < (snap_n * (snap_n + 1) >> 1); i += 32) snap[i] = A[i];
+      __syncwarp();
+    }
     const int nb = min(4, kt + 1), lead = kt - nb + 1;
     const int rb0 = kt * (kt + 1) >> 1, rb1 = rb0 - kt, rb2 = rb1 - (kt - 1), rb3 = rb2 - (kt - 2);
     float dv[4], Lb[6];
@@ -324,66 +333,6 @@ __device__ __noinline__ void ldl_solve(const float* L, const float* invdiag, flo
   }
   if (lane < n0) x[lane] = x0;
   if (lane < nh) x[lane + 32] = x1;
-  __syncwarp();
-}
-// Level-scheduled variant of ldl_solve for factors that kept the dof tree's pattern (experiment, compiled into
-// the kernel only with -DB2_LEVEL_SOLVE: DESIGN.md 9.1).  Pivots of one tree level are independent, so up to four of them are
-// broadcast together before their updates are applied: the dependent chain is one step per level (16 for G1)
-// instead of one per dof (35), at the same number of loads and FMAs.  `order` / `lstart`: b2_build_dof_levels.
-__device__ __noinline__ void ldl_solve_levels(const float* L, const float* invdiag, float* x, int n,
-                                              const unsigned char* order, const unsigned char* lstart, int nlevel,
-                                              int lane) {
-  float x0 = lane < n ? x[lane] : 0.f;
-  float x1 = lane + 32 < n ? x[lane + 32] : 0.f;
-  const float d0 = lane < n ? invdiag[lane] : 0.f, d1 = lane + 32 < n ? invdiag[lane + 32] : 0.f;
-  const int r0 = lane * (lane + 1) >> 1, r1 = (lane + 32) * (lane + 33) >> 1;
-  // L^T y = b: deepest level first; x_j -= A[k,j] / d_k * y_k for the ancestors j of pivot k (row k, lane = column)
-#pragma unroll 1
-  for (int lv = nlevel - 1; lv >= 0; lv--) {
-    const int e = lstart[lv + 1];
-#pragma unroll 1
-    for (int i = lstart[lv]; i < e; i += 4) {
-      const int c = min(4, e - i);
-      int k[4];
-      float y[4];
-#pragma unroll
-      for (int t = 0; t < 4; t++) {
-        k[t] = t < c ? order[i + t] : 0;
-        float v = __shfl_sync(FULL, k[t] < 32 ? x0 : x1, k[t] & 31);
-        y[t] = t < c ? v * invdiag[k[t]] : 0.f;
-      }
-#pragma unroll
-      for (int t = 0; t < 4; t++) {
-        const int rk = k[t] * (k[t] + 1) >> 1;
-        if (t < c && lane < k[t]) x0 -= L[rk + lane] * y[t];
-        if (t < c && lane + 32 < k[t]) x1 -= L[rk + lane + 32] * y[t];
-      }
-    }
-  }
-  x0 *= d0; x1 *= d1;  // D z = y
-  // L x = z: root level first; x_k -= A[k,j] / d_k * x_j for the descendants k of pivot j (column j, lane = row)
-#pragma unroll 1
-  for (int lv = 0; lv < nlevel; lv++) {
-    const int e = lstart[lv + 1];
-#pragma unroll 1
-    for (int i = lstart[lv]; i < e; i += 4) {
-      const int c = min(4, e - i);
-      int j[4];
-      float v[4];
-#pragma unroll
-      for (int t = 0; t < 4; t++) {
-        j[t] = t < c ? order[i + t] : 0;
-        v[t] = __shfl_sync(FULL, j[t] < 32 ? x0 : x1, j[t] & 31);
-      }
-#pragma unroll
-      for (int t = 0; t < 4; t++) {
-        if (t < c && lane > j[t] && lane < n) x0 -= L[r0 + j[t]] * d0 * v[t];
-        if (t < c && lane + 32 > j[t] && lane + 32 < n) x1 -= L[r1 + j[t]] * d1 * v[t];
-      }
-    }
-  }
-  if (lane < n) x[lane] = x0;
-  if (lane + 32 < n) x[lane + 32] = x1;
   __syncwarp();
 }
 // y = M x for packed symmetric M (both in shared memory).  One column loop for all lanes (entry (i,j) lives
@@ -702,48 +651,50 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
 #endif
   __shared__ __align__(8) unsigned long long bars[B2_WARPS_PER_CTA];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int slot = blockIdx.x * B2_WARPS_PER_CTA + warp;
-  const int w = slot < dd.world_count
-                    ? (dd.world_order != nullptr ? dd.world_order[dd.world_base + slot] : dd.world_base + slot)
-                    : dd.nworld;
   // per-CTA copy of the factorisation pair schedule (shared by the CTA's warps)
   unsigned* s_sched = (unsigned*)(smem_all + (size_t)B2_WARPS_PER_CTA * m.lay.total);
-#define FACTOR(sp) ldl_factor(H, invdiag, nv, s_sched, (const int*)s_sched + m.ldl_nsparse, m.ldl_dense, sp, lane)
-#ifdef B2_LEVEL_SOLVE
-  // experiment: level-scheduled sweeps whenever the factor kept the dof tree's pattern
-  const unsigned char* s_lvl = (const unsigned char*)(s_sched + m.ldl_nsparse + 18);
-#define SOLVE(v, tree)                                                                       \
-  do {                                                                                       \
-    if (tree) ldl_solve_levels(H, invdiag, v, nv, s_lvl, s_lvl + 64, m.ldl_nlevel, lane);    \
-    else ldl_solve(H, invdiag, v, nv, lane);                                                 \
-  } while (0)
-#else
+#define SCHED s_sched, (const int*)s_sched + m.ldl_nsparse, m.ldl_dense
+#define FACTOR(sp) ldl_factor(H, invdiag, nv, SCHED, sp, lane)
 #define SOLVE(v, tree) ldl_solve(H, invdiag, v, nv, lane)
-#endif
 #pragma unroll 1
   for (int i = threadIdx.x; i < m.ldl_nsparse; i += 32 * B2_WARPS_PER_CTA) s_sched[i] = m.ldl_sparse[i];
   if (threadIdx.x < 18) s_sched[m.ldl_nsparse + threadIdx.x] = (unsigned)m.ldl_start[threadIdx.x];
-#ifdef B2_LEVEL_SOLVE
-  for (int i = threadIdx.x; i < 34; i += 32 * B2_WARPS_PER_CTA) s_sched[m.ldl_nsparse + 18 + i] = m.ldl_levels[i];
-#endif
+  if (lane == 0) mbar_init(&bars[warp], 1);
   __syncthreads();  // the only block barrier; nothing below synchronises across warps
-  if (w >= dd.nworld) return;
-  if (dd.world_mask != nullptr && dd.world_mask[w] == 0) return;
   const Layout& L = m.lay;
-#ifdef B2_PHASE_TIMING
-  long long tphase_ = clock64();
-#endif
   float* s = smem_all + (size_t)warp * L.total;
   const int nq = m.nq, nv = m.nv, nu = m.nu, nb = m.nbody, njnt = m.njnt;
   const int MC = L.maxcon, NLC = L.nlimcap;
+  uint32_t barphase = 0;
+  // Every warp is an independent worker.  With a ticket counter (dd.ticket) it pulls launch slots until the
+  // queue is empty - environments are handed out heavy-first (dd.world_order), so the warps of the whole grid
+  // finish together; without one it processes the single slot its position in the grid names.
+#pragma unroll 1
+  for (bool more = true; more;) {
+  int slot;
+  if (dd.ticket != nullptr) {
+    slot = 0;
+    if (lane == 0) slot = atomicAdd(dd.ticket, 1);
+    slot = __shfl_sync(FULL, slot, 0);
+  } else {
+    slot = blockIdx.x * B2_WARPS_PER_CTA + warp;
+    more = false;
+  }
+  if (slot >= dd.world_count) break;
+  const int w = dd.world_order != nullptr ? dd.world_order[dd.world_base + slot] : dd.world_base + slot;
+  if (dd.world_mask != nullptr && dd.world_mask[w] == 0) continue;
+#ifdef B2_PHASE_TIMING
+  long long tphase_ = clock64();
+#endif
 
   // ---------------- phase 0: TMA bulk load of this environment's state -------------------------
   float* qpos = s + L.qpos; float* qvel = s + L.qvel; float* ctrl = s + L.ctrl;
   float* qacc_ws = s + L.qacc_ws; float* qfrc_applied = s + L.qfrc_applied; float* xfrc = s + L.xfrc;
   {
     unsigned long long* bar = &bars[warp];
+    fence_async_smem();  // the previous environment's generic-proxy accesses precede this one's bulk writes
+    __syncwarp();
     if (lane == 0) {
-      mbar_init(bar, 1);
       uint32_t bytes = 4u * (dd.qpos.stride + dd.qvel.stride + dd.ctrl.stride +
                              dd.qacc_warmstart.stride + dd.qfrc_applied.stride + dd.xfrc_applied.stride);
       mbar_expect(bar, bytes);
@@ -755,7 +706,8 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       bulk_g2s(xfrc, dd.xfrc_applied.p + (size_t)w * dd.xfrc_applied.stride, 4u * dd.xfrc_applied.stride, bar);
     }
     __syncwarp();
-    mbar_wait(bar, 0);
+    mbar_wait(bar, barphase);
+    barphase ^= 1u;
   }
 
   PHASE_MARK(0);
@@ -1595,17 +1547,30 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   // The Hessian keeps the dof tree's zero pattern unless a contact couples two branches (both bodies move and
   // neither chain contains the other): only then the factorisation takes the dense schedule.
   bool treeok = !(m.debug & 2);
+  // kd: highest dof that any constraint row touches.  Dofs above it are unconstrained: eliminating them from
+  // M once (phase 7) leaves the Schur complement on the leading block, and the Newton iterations run on that
+  // block only (n x n instead of nv x nv; the other accelerations follow by back-substitution, phase 8).
+  int kd = -1;
   #pragma unroll 1
   for (int g0 = 0; g0 < ngroup; g0 += 32) {
     bool bad = false;
     if (g0 + lane < ngroup) {
       int key = ((int*)con)[CINFO * MC + gstart[g0 + lane]] & 0xffff;
       unsigned long long m1 = m.body_dofmask[key & 0xff], m2 = m.body_dofmask[key >> 8];
-      unsigned long long c = m1 & m2;
+      unsigned long long c = m1 & m2, x = m1 ^ m2;
       bad = c != m1 && c != m2;
+      if (x) kd = max(kd, 63 - __clzll((long long)x));
     }
     if (__any_sync(FULL, bad)) treeok = false;
   }
+  #pragma unroll 1
+  for (int r = lane; r < nlim; r += 32) kd = max(kd, ((int*)lim)[LINFO * NLC + r] & 0xffff);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) kd = max(kd, __shfl_xor_sync(FULL, kd, o));
+  // n: the leading block the solver works on; a multiple of four pivots is eliminated (block factorisation)
+  int n = nv - (((nv - (kd + 1)) >> 2) << 2);
+  if (n > L.ndcap || (m.debug & 4)) n = nv;
+  const bool reduced = n < nv;
   int nefc = nlim;
   {
     int cnt = 0;
@@ -1641,7 +1606,8 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   #pragma unroll 1
   for (int i = lane; i < (m.ntri + 3) >> 2; i += 32) ((float4*)H)[i] = ((const float4*)Mq)[i];  // both regions are 16 B aligned and padded
   __syncwarp();
-  FACTOR(true);
+  float* Mred = s + L.Mred;
+  ldl_factor(H, invdiag, nv, SCHED, true, lane, 0, (reduced && nefc > 0) ? n : 0, Mred);
   SOLVE(qacc_smooth, true);
   if (m.debug & 1)
     #pragma unroll 1
@@ -1656,8 +1622,17 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     for (int i = lane; i < nv; i += 32) { qacc[i] = qacc_smooth[i]; qfrc_c[i] = 0.f; }
     __syncwarp();
   } else {
+    // Reduced problem (n < nv): minimising the Gauss term over the unconstrained dofs in closed form leaves
+    // 1/2 (a-a_s)^T Mr (a-a_s) on the leading block, Mr = Schur complement of M (snapshot of phase 7); the
+    // code below is the full-size solver with (Mr, Mr a_s) in place of (M, qfrc_smooth).
+    const float* Mr = reduced ? Mred : Mq;
+    const float* qs = qfrc_smooth;
+    if (reduced) {
+      symv(Mr, qacc_smooth, tmpv, n, lane);
+      qs = tmpv;
+    }
     // warm start: qacc_warmstart unless qacc_smooth is cheaper (mj_fwdConstraint)
-    symv(Mq, qacc_ws, Ma, nv, lane);
+    symv(Mr, qacc_ws, Ma, n, lane);
     MULJ(qacc_smooth, CJV0, LJV, false);
     #pragma unroll 1
     for (int c = lane; c < ncon; c += 32)
@@ -1671,15 +1646,15 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     float cw = rows_cost(CJAR0, LJAR, con, lim, ncon, nlim, MC, NLC, lane);
     float gs = 0.f;
     #pragma unroll 1
-    for (int i = lane; i < nv; i += 32) gs += (Ma[i] - qfrc_smooth[i]) * (qacc_ws[i] - qacc_smooth[i]);
+    for (int i = lane; i < n; i += 32) gs += (Ma[i] - qs[i]) * (qacc_ws[i] - qacc_smooth[i]);
     cw += 0.5f * wsum(gs);
     bool use_smooth = cw > csm;
     #pragma unroll 1
-    for (int i = lane; i < nv; i += 32) qacc[i] = use_smooth ? qacc_smooth[i] : qacc_ws[i];
+    for (int i = lane; i < n; i += 32) qacc[i] = use_smooth ? qacc_smooth[i] : qacc_ws[i];
     __syncwarp();
     if (use_smooth) {
       #pragma unroll 1
-      for (int i = lane; i < nv; i += 32) Ma[i] = qfrc_smooth[i];  // M * qacc_smooth
+      for (int i = lane; i < n; i += 32) Ma[i] = qs[i];  // M * qacc_smooth
       #pragma unroll 1
       for (int c = lane; c < ncon; c += 32)
 #pragma unroll
@@ -1726,7 +1701,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         gW[4 * MC + c] = pyr ? mu * mu * (w2 + w3) : 0.f;
       }
       #pragma unroll 1
-      for (int i = lane; i < nv; i += 32) qfrc_c[i] = 0.f;
+      for (int i = lane; i < n; i += 32) qfrc_c[i] = 0.f;
       __syncwarp();
       #pragma unroll 1
       for (int r = lane; r < nlim; r += 32) {
@@ -1757,7 +1732,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       }
       __syncwarp();
       #pragma unroll 1
-      for (int i = lane; i < nv; i += 32) {
+      for (int i = lane; i < n; i += 32) {
         float acc = qfrc_c[i];
         #pragma unroll 1
         for (int g = 0; g < ngroup; g++) {
@@ -1774,11 +1749,11 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       __syncwarp();
       float gg = 0.f, gn = 0.f;
       #pragma unroll 1
-      for (int i = lane; i < nv; i += 32) {
-        float g = Ma[i] - qfrc_smooth[i] - qfrc_c[i];
+      for (int i = lane; i < n; i += 32) {
+        float g = Ma[i] - qs[i] - qfrc_c[i];
         grad[i] = g;
         gn += g * g;
-        gg += (Ma[i] - qfrc_smooth[i]) * (qacc[i] - qacc_smooth[i]);
+        gg += (Ma[i] - qs[i]) * (qacc[i] - qacc_smooth[i]);
       }
       cost = wsum(cst) + 0.5f * wsum(gg);
       gn = wsum(gn);
@@ -1794,8 +1769,12 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       first = false;
       PHASE_MARK(12);
       // ---- Hessian H = M + J^T D_active J via per-body-pair 6x6 blocks -------------------------
-      #pragma unroll 1
-      for (int i = lane; i < (m.ntri + 3) >> 2; i += 32) ((float4*)H)[i] = ((const float4*)Mq)[i];  // both regions are 16 B aligned and padded
+      {  // leading block only: the rows of the eliminated dofs keep the factor of M (needed after the loop)
+        const int nt = n * (n + 1) >> 1;
+        #pragma unroll 1
+        for (int i = lane; i < nt >> 2; i += 32) ((float4*)H)[i] = ((const float4*)Mr)[i];  // 16 B aligned regions
+        if (lane < (nt & 3)) H[(nt & ~3) + lane] = Mr[(nt & ~3) + lane];
+      }
       __syncwarp();
       #pragma unroll 1
       for (int r = lane; r < nlim; r += 32) {
@@ -1859,19 +1838,19 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         __syncwarp();
       }
       PHASE_MARK(13);
-      FACTOR(treeok);
+      ldl_factor(H, invdiag, n, SCHED, treeok, lane, (nv - n) >> 2);
       #pragma unroll 1
-      for (int i = lane; i < nv; i += 32) search[i] = -grad[i];
+      for (int i = lane; i < n; i += 32) search[i] = -grad[i];
       __syncwarp();
-      SOLVE(search, treeok);
+      ldl_solve(H, invdiag, search, n, lane);
       PHASE_MARK(14);
       // ---- exact line search along `search` --------------------------------------------------
-      symv(Mq, search, Mv, nv, lane);
+      symv(Mr, search, Mv, n, lane);
       MULJ(search, CJV0, LJV, false);
       float g1 = 0.f, g2 = 0.f, sn = 0.f;
       #pragma unroll 1
-      for (int i = lane; i < nv; i += 32) {
-        g1 += search[i] * (Ma[i] - qfrc_smooth[i]);
+      for (int i = lane; i < n; i += 32) {
+        g1 += search[i] * (Ma[i] - qs[i]);
         g2 += 0.5f * search[i] * Mv[i];
         sn += search[i] * search[i];
       }
@@ -1945,7 +1924,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       PHASE_MARK(16);
       if (alpha == 0.f) break;
       #pragma unroll 1
-      for (int i = lane; i < nv; i += 32) { qacc[i] += alpha * search[i]; Ma[i] += alpha * Mv[i]; }
+      for (int i = lane; i < n; i += 32) { qacc[i] += alpha * search[i]; Ma[i] += alpha * Mv[i]; }
       #pragma unroll 1
       for (int c = lane; c < ncon; c += 32)
 #pragma unroll
@@ -1955,6 +1934,25 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       __syncwarp();
       oldcost = cost;
       niter++;
+    }
+    if (reduced) {
+      // eliminated dofs: a_c = a_s,c - L_cc^-1 L_cd (a_d - a_s,d), i.e. rows k >= n of L x = 0 with x_d given
+      // (the factor of M from phase 7 is intact in those rows: x_k = -(1/d_k) sum_{j<k} A[k,j] x_j)
+      #pragma unroll 1
+      for (int i = lane; i < nv; i += 32) Mv[i] = i < n ? qacc[i] - qacc_smooth[i] : 0.f;
+      __syncwarp();
+      #pragma unroll 1
+      for (int k = n; k < nv; k++) {
+        const int rk = k * (k + 1) >> 1;
+        float part = lane < k ? H[rk + lane] * Mv[lane] : 0.f;
+        if (lane + 32 < k) part += H[rk + 32 + lane] * Mv[lane + 32];
+        part = wsum(part);
+        if (lane == 0) Mv[k] = -invdiag[k] * part;
+        __syncwarp();
+      }
+      #pragma unroll 1
+      for (int i = n + lane; i < nv; i += 32) { qacc[i] = qacc_smooth[i] + Mv[i]; qfrc_c[i] = 0.f; }
+      __syncwarp();
     }
   }
 
@@ -2166,4 +2164,5 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   }
   __syncwarp();
   }  // sub-step loop
+  }  // worker loop
 }

@@ -34,23 +34,3 @@ inline void b2_build_ldl_schedules(int nv, const int* dof_parentid, std::vector<
   }
   for (int b = blk; b < 18; b++) start[b] = (int)sparse.size();
 }
-
-// Tree levels of the dofs (depth 0 = roots) for level-scheduled triangular solves: order[] lists the dofs by
-// ascending depth, lstart[l] .. lstart[l+1] delimits level l.  Dofs of one level are never ancestors of each
-// other, so their pivots are independent in both sweeps.  Returns the number of levels.
-inline int b2_build_dof_levels(int nv, const int* dof_parentid, unsigned char* order, unsigned char* lstart) {
-  std::vector<int> depth(std::max(nv, 1), 0);
-  int nlevel = 0;
-  for (int k = 0; k < nv; k++) {
-    depth[k] = dof_parentid[k] < 0 ? 0 : depth[dof_parentid[k]] + 1;
-    nlevel = std::max(nlevel, depth[k] + 1);
-  }
-  int w = 0;
-  for (int l = 0; l < nlevel; l++) {
-    lstart[l] = (unsigned char)w;
-    for (int k = 0; k < nv; k++)
-      if (depth[k] == l) order[w++] = (unsigned char)k;
-  }
-  lstart[nlevel] = (unsigned char)w;
-  return nlevel;
-}

@@ -60,6 +60,8 @@ struct Layout {
   // collision / constraints (overlaid on smooth-only regions)
   int gpose, pairlist, contacts, limits, gstart, gV, glist, gA, gu, gW;
   int sens;
+  int Mred;   // Schur complement of M on the leading ndcap x ndcap block (reduced Newton problem)
+  int ndcap;  // largest leading block the reduced solver may use (nv - 4k, packed size <= the Mred region)
   int maxcon, nlimcap, maxpair;
 };
 
@@ -100,11 +102,6 @@ struct DevModel {
   const unsigned *ldl_dense, *ldl_sparse;
   int ldl_start[18];
   int ldl_nsparse;
-#ifdef B2_LEVEL_SOLVE
-  // experiment: dof tree levels for ldl_solve_levels; 34 words staged after the block starts
-  unsigned ldl_levels[34];  // bytes: order[64], lstart[66] (padded), b2_build_dof_levels
-  int ldl_nlevel;
-#endif
   // float arrays (expandable per world)
   FArr body_pos, body_quat, body_ipos, body_iquat, body_mass, body_subtreemass, body_inertia,
       body_invweight0, jnt_pos, jnt_axis, jnt_range, jnt_solref, jnt_solimp, jnt_margin,
@@ -125,6 +122,7 @@ struct DevData {
   DArr qfrc_bias, qfrc_smooth, qacc_smooth, qfrc_constraint, qM;
   DArr contact_dist, contact_pos, contact_frame, contact_force, solver_cost;
   IArr ncon, nefc, solver_niter, contact_geom, overflow;
+  int* ticket;                      // optional: work queue of launch slots (one atomic per environment)
   const int* world_order;           // optional: launch slot -> world (heavy-first dispatch)
   const unsigned char* world_mask;  // optional: worlds with mask 0 are skipped (masked forward)
 };

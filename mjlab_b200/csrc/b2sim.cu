@@ -11,11 +11,6 @@
 #include "../../include/b2sim.h"
 #include "b2_kernel.cuh"
 #include "b2_tables.h"
-#ifdef B2_LEVEL_SOLVE
-#define B2_LEVEL_WORDS 34
-#else
-#define B2_LEVEL_WORDS 0
-#endif
 #include "b2_env.cuh"
 
 static thread_local std::string g_err;
@@ -66,6 +61,9 @@ struct b2_sim {
   int sorted_dispatch = 1;
   int fused_decimation = 0;
   int split_streams = 2;       // b2_step_n runs this many env partitions on internal streams
+  int work_queue = 0;          // warps pull environments from a ticket counter (persistent grid)
+  int* tickets = nullptr;      // one counter per stream partition (device)
+  int resident_ctas = 0;       // co-resident CTAs of the step kernel on this device
   cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};  // measured slower (r01: 979 vs 733 us/sub-step): off by default
   size_t smem_bytes = 0;
@@ -113,8 +111,10 @@ __global__ void b2_static_rows_kernel(float* xpos, int xpos_stride, float* xmat,
 // Heavy-first dispatch: order worlds by the previous step's (Newton iterations, contacts),
 // descending, with a one-CTA counting sort (128 buckets).  Only scheduling changes, not results.
 __global__ void b2_order_kernel(const int* __restrict__ niter, int niter_stride, const int* __restrict__ ncon,
-                                int ncon_stride, int base_world, int count, int* __restrict__ order) {
+                                int ncon_stride, int base_world, int count, int* __restrict__ order,
+                                int* __restrict__ ticket) {
   __shared__ int hist[128];
+  if (ticket != nullptr && threadIdx.x == 0) *ticket = 0;  // the step kernel's work queue starts empty
   __shared__ int base[128];
   for (int i = threadIdx.x; i < 128; i += blockDim.x) hist[i] = 0;
   __syncthreads();
@@ -208,20 +208,25 @@ static int add_idata(b2_sim* s, const char* name, IArr* arr, int n, int second =
   return 0;
 }
 
-static int launch(b2_sim* s, bool step, cudaStream_t st, int nsub = 1, int base = 0, int count = -1) {
+static int launch(b2_sim* s, bool step, cudaStream_t st, int nsub = 1, int base = 0, int count = -1, int part = 0) {
   if (count < 0) count = s->nworld;
   s->hd.nsub = nsub;
   s->hd.world_base = base;
   s->hd.world_count = count;
   int grid = (count + B2_WARPS_PER_CTA - 1) / B2_WARPS_PER_CTA;
+  const bool queue = s->work_queue && s->tickets && s->resident_ctas > 0 && grid > s->resident_ctas;
+  int* ticket = queue ? s->tickets + part : nullptr;
   if (step && s->sorted_dispatch && s->order && count >= 512 && s->hd.world_mask == nullptr) {
     b2_order_kernel<<<1, 1024, 0, st>>>(s->hd.solver_niter.p, s->hd.solver_niter.stride, s->hd.ncon.p,
-                                        s->hd.ncon.stride, base, count, s->order);
+                                        s->hd.ncon.stride, base, count, s->order, ticket);
     s->launches++;
     s->hd.world_order = s->order;
   } else {
     s->hd.world_order = nullptr;
+    if (queue) CUDA_OK(cudaMemsetAsync(ticket, 0, sizeof(int), st));
   }
+  s->hd.ticket = ticket;
+  if (queue) grid = s->resident_ctas;
   if (step)
     b2_step_kernel<true><<<grid, 32 * B2_WARPS_PER_CTA, s->smem_bytes, st>>>(s->hm, s->hd);
   else
@@ -569,13 +574,6 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
     std::vector<unsigned> dense, sparse;
     b2_build_ldl_schedules(m.nv, s->mi["dof_parentid"].data(), dense, sparse, m.ldl_start);
     m.ldl_nsparse = (int)sparse.size();
-#ifdef B2_LEVEL_SOLVE
-    {
-      unsigned char* lv = (unsigned char*)m.ldl_levels;
-      memset(lv, 0, sizeof(m.ldl_levels));
-      m.ldl_nlevel = b2_build_dof_levels(m.nv, s->mi["dof_parentid"].data(), lv, lv + 64);
-    }
-#endif
     rc |= dev_upload<unsigned>(s, dense, &m.ldl_dense);
     rc |= dev_upload<unsigned>(s, sparse, &m.ldl_sparse);
   }
@@ -684,19 +682,34 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
   L.contacts = alloc(C_NFIELD * mc); L.limits = alloc(L_NFIELD * L.nlimcap); L.gstart = alloc(mc + 1);
   L.gV = alloc(6 * mc); L.glist = alloc(64); L.gA = alloc(36); L.gu = alloc(6 * nv);
   L.gW = alloc(5 * mc); L.sens = off;
+  // reduced Newton problem: room for the Schur complement on the largest leading block nv - 4k (k >= 1) whose
+  // packed size fits 300 floats (G1: 23 x 23 covers legs + waist; arm contacts fall back to the full problem)
+  L.ndcap = 0;
+  for (int k = 1; nv - 4 * k >= 6; k++) {
+    int cand = nv - 4 * k;
+    if (cand * (cand + 1) / 2 <= 300) { L.ndcap = cand; break; }
+  }
+  L.Mred = alloc(L.ndcap * (L.ndcap + 1) / 2);
   int endB = off;
   L.total = pad4(std::max(endA, endB));
-  s->smem_bytes = sizeof(float) * ((size_t)L.total * B2_WARPS_PER_CTA + pad4(m.ldl_nsparse + 18 + B2_LEVEL_WORDS));
+  if (L.ndcap == 0) L.Mred = L.M;  // never used
+  s->smem_bytes = sizeof(float) * ((size_t)L.total * B2_WARPS_PER_CTA + pad4(m.ldl_nsparse + 18));
   if (s->smem_bytes > 227 * 1024) {
     b2_destroy(s);
     return fail("b2_create: model too large for the per-environment shared-memory block");
   }
   {
-    cudaError_t e1 = cudaFuncSetAttribute(b2_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes);
-    cudaError_t e2 = cudaFuncSetAttribute(b2_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes);
-    if (e1 != cudaSuccess || e2 != cudaSuccess) {
-      b2_destroy(s);
-      return fail(std::string("cudaFuncSetAttribute(max dynamic smem): ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    // The attribute is per function and per device, not per sim: only ever raise it, so that an earlier,
+    // larger sim in the same process keeps launching after a smaller one is created.
+    static size_t dev_max[64] = {0};
+    if (s->smem_bytes > dev_max[cuda_device & 63]) {
+      cudaError_t e1 = cudaFuncSetAttribute(b2_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes);
+      cudaError_t e2 = cudaFuncSetAttribute(b2_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes);
+      if (e1 != cudaSuccess || e2 != cudaSuccess) {
+        b2_destroy(s);
+        return fail(std::string("cudaFuncSetAttribute(max dynamic smem): ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+      }
+      dev_max[cuda_device & 63] = s->smem_bytes;
     }
   }
   {
@@ -704,6 +717,14 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
     if (cudaMalloc(&p, sizeof(int) * (size_t)nworld) != cudaSuccess) { b2_destroy(s); return fail("cudaMalloc(order)"); }
     s->allocs.push_back(p);
     s->order = (int*)p;
+    if (cudaMalloc(&p, sizeof(int) * 4) != cudaSuccess) { b2_destroy(s); return fail("cudaMalloc(tickets)"); }
+    s->allocs.push_back(p);
+    s->tickets = (int*)p;
+    cudaMemset(p, 0, sizeof(int) * 4);
+    int per_sm = 0, sms = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b2_step_kernel<true>, 32 * B2_WARPS_PER_CTA, s->smem_bytes);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cuda_device);
+    s->resident_ctas = per_sm * sms;
     for (int h = 0; h < 4; h++) {
       if (cudaStreamCreateWithFlags(&s->side[h], cudaStreamNonBlocking) != cudaSuccess ||
           cudaEventCreateWithFlags(&s->ev_join[h], cudaEventDisableTiming) != cudaSuccess) {
@@ -819,6 +840,8 @@ int b2_set_option(b2_sim* s, const char* key, double v) {
   else if (k == "sorted_dispatch") s->sorted_dispatch = (int)v;
   else if (k == "fused_decimation") s->fused_decimation = (int)v;
   else if (k == "split_streams") s->split_streams = (int)v;
+  else if (k == "work_queue") s->work_queue = (int)v;
+  else if (k == "full_solver") m.debug = (m.debug & ~4) | ((int)v ? 4 : 0);  // Newton on all dofs even when a leading block suffices (tests, A/B)
   else return fail("b2_set_option: unknown option '" + k + "'");
   return 0;
 }
@@ -836,6 +859,10 @@ int b2_get_option(b2_sim* s, const char* key, double* v) {
   else if (k == "dense_factor") *v = (m.debug >> 1) & 1;
   else if (k == "smem_bytes_per_env") *v = 4.0 * m.lay.total;
   else if (k == "maxcon") *v = m.maxcon;
+  else if (k == "full_solver") *v = (m.debug >> 2) & 1;
+  else if (k == "work_queue") *v = s->work_queue;
+  else if (k == "resident_ctas") *v = s->resident_ctas;
+  else if (k == "reduced_block_cap") *v = m.lay.ndcap;
   else return fail("b2_get_option: unknown option '" + k + "'");
   return 0;
 }
@@ -877,7 +904,7 @@ int b2_step_n(b2_sim* s, int n, void* stream) {
       if (count <= 0) break;
       CUDA_OK(cudaStreamWaitEvent(s->side[h], s->ev_fork, 0));
       for (int i = 0; i < n; i++)
-        if (launch(s, true, s->side[h], 1, base, count)) return 1;
+        if (launch(s, true, s->side[h], 1, base, count, h)) return 1;
       CUDA_OK(cudaEventRecord(s->ev_join[h], s->side[h]));
       CUDA_OK(cudaStreamWaitEvent(st, s->ev_join[h], 0));
     }

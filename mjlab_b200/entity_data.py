@@ -176,9 +176,12 @@ class EntityData:
 
   # -- writers (data.py:69-178) ---------------------------------------------------------------------
   def _resolve_env_ids(self, env_ids):
-    if env_ids is None or isinstance(env_ids, slice):
+    # data.py:180-188: None -> all envs; tensor -> column for broadcasting; slices pass through unchanged
+    if env_ids is None:
       return slice(None)
-    return env_ids[:, None]
+    if isinstance(env_ids, torch.Tensor):
+      return env_ids[:, None]
+    return env_ids
 
   def write_root_state(self, root_state, env_ids=None) -> None:
     if self.is_fixed_base:

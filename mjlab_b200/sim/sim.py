@@ -217,6 +217,12 @@ class Simulation:
   def step_n(self, n: int) -> None:
     """``n`` sub-steps with ``ctrl`` held (the decimation loop of
     ``envs/manager_based_rl_env.py:109-114``) in one library call."""
+    if self.nan_guard.enabled and not torch.cuda.is_current_stream_capturing():
+      # the guard copies state to the host, so each sub-step is watched like a `step()` call
+      for _ in range(int(n)):
+        with self.nan_guard.watch(self.data):
+          native.check(self._lib.b2_step(self._h, self._stream()))
+      return
     native.check(self._lib.b2_step_n(self._h, int(n), self._stream()))
 
   def stats(self) -> native.B2Stats:
@@ -231,8 +237,11 @@ class Simulation:
     h = getattr(self, "_h", None)
     if h:
       torch.cuda.synchronize(self._dev_index)
-      self._wp_data._tensors.clear()
-      self._wp_model._tensors.clear()
+      # engine memory is about to be freed: drop every cached view and make later field access fail loudly
+      for st, br in ((self._wp_data, self._data_bridge), (self._wp_model, self._model_bridge)):
+        st._tensors.clear()
+        st._closed = True
+        object.__getattribute__(br, "_wrapped_cache").clear()
       self._lib.b2_destroy(h)
       self._h = None
 

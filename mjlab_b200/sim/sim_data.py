@@ -164,6 +164,8 @@ class EngineStruct:
       raise AttributeError(name)
     if name in self._extra:
       return self._extra[name]
+    if self.__dict__.get("_closed"):
+      raise RuntimeError(f"Simulation is closed: field '{name}' no longer exists (engine memory was freed)")
     if name in self._tensors:
       return self._tensors[name]
     if name not in self._names:

@@ -47,6 +47,10 @@ inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (vo
 inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return 0; }
 inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return 0; }
+enum { cudaDevAttrMultiProcessorCount = 16 };
+// a "device" with two SMs holding one CTA each: a batch of more than two environments exercises the work queue
+template <class F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 1; return 0; }
+inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 2; return 0; }
 
 namespace cuda_emul {
 struct Job { std::function<void()>* body; int tid; };

@@ -47,19 +47,6 @@ void emul_ldl(int n, const int* dof_parentid, float* A, float* invdiag, float* x
     b2::ldl_solve(A, invdiag, x, n, lane);
   });
 }
-// same as emul_ldl (tree schedule) but solving with the level-scheduled sweeps
-void emul_ldl_levels(int n, const int* dof_parentid, float* A, float* invdiag, float* x) {
-  std::vector<unsigned> d, s;
-  int start[18];
-  b2_build_ldl_schedules(n, dof_parentid, d, s, start);
-  s.push_back(0);
-  unsigned char order[64], lstart[66];
-  int nlevel = b2_build_dof_levels(n, dof_parentid, order, lstart);
-  run_warp([&](int lane) {
-    b2::ldl_factor(A, invdiag, n, s.data(), start, d.data(), true, lane);
-    b2::ldl_solve_levels(A, invdiag, x, n, order, lstart, nlevel, lane);
-  });
-}
 void emul_symv(int n, const float* M, const float* x, float* y) {
   run_warp([&](int lane) { b2::symv(M, x, y, n, lane); });
 }

@@ -138,3 +138,16 @@ def test_writers_land_exactly(g1_entity):
   ed.clear_state(env_ids)
   assert (ed.data.xfrc_applied[env_ids] == 0).all() and (ed.data.ctrl[env_ids] == 0).all()
   assert (ed.data.ctrl[0] == 1).all()
+
+
+def test_writers_with_partial_slice(g1_entity):
+  """env_ids given as a slice selects that range only (reference entity/data.py:180-188 passes slices through)."""
+  ed, o, st, n = g1_entity
+  before = ed.data.qpos.clone()
+  pose = torch.tensor([[1.0, 2.0, 3.0, 1.0, 0.0, 0.0, 0.0]]).repeat(2, 1)
+  ed.write_root_pose(pose, env_ids=slice(2, 4))
+  assert torch.equal(ed.data.qpos[2:4, :7], pose)
+  assert torch.equal(ed.data.qpos[:2], before[:2]) and torch.equal(ed.data.qpos[4:], before[4:])
+  ed.write_ctrl(torch.ones(n, 29))
+  ed.clear_state(env_ids=slice(0, 1))
+  assert (ed.data.ctrl[0] == 0).all() and (ed.data.ctrl[1:] == 1).all()

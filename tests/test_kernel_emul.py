@@ -206,27 +206,6 @@ def test_emulated_kernel_obstacle_course(lib):
   sim.close()
 
 
-def test_emulated_level_scheduled_solve_experiment():
-  """-DB2_LEVEL_SOLVE (off by default): same forward / step parity with the level-scheduled sweeps."""
-  from mjlab_b200.asset_zoo import load_compiled
-
-  L = _load(("B2_LEVEL_SOLVE",))
-  m = load_compiled("go1_flat")
-  n = 3
-  sim = EmulSim(L, m, n)
-  o = Oracle(m, nworld=n, maxcon=int(sim.option("maxcon")))
-  st = make_states(m, n, seed=5)
-  load_oracle(o, st)
-  sim.load(st)
-  o.forward()
-  sim.forward()
-  _check_forward(sim, o, n)
-  o.step()
-  sim.step(1)
-  assert relerr(sim.field("qvel"), o.qvel).max() < 5e-3
-  sim.close()
-
-
 def test_emulated_host_entry_fused_decimation_and_field_expansion(lib):
   """Three host paths no CPU test could reach before: b2_step_host (host buffers in/out) equals b2_step_n, the
   in-kernel decimation loop (`fused_decimation`) equals separate launches, and an expanded per-world model field
@@ -396,4 +375,41 @@ def test_emulated_kernel_synthetic_45dof_robot(lib):
   o.step()
   sim.step(1)
   assert relerr(sim.field("qvel"), o.qvel).max() < 1e-3
+  sim.close()
+
+
+def test_emulated_reduced_solver_and_work_queue(lib):
+  """The Newton solver on the constrained leading block (Schur complement of M onto the dofs any constraint
+  touches, the rest by back-substitution) gives the full-size solver's answer, and the ticket work queue
+  (persistent warps pulling environments) visits every environment exactly once."""
+  from mjlab_b200.asset_zoo import load_compiled
+
+  m = load_compiled("g1_flat")
+  n = 5  # more environments than the emulated device holds CTAs (2): the queue hands out several per warp
+  sim = EmulSim(lib, m, n)
+  assert sim.option("reduced_block_cap") == 23 and sim.option("resident_ctas") == 2
+  o = Oracle(m, nworld=n, maxcon=int(sim.option("maxcon")))
+  st = make_states(m, n, seed=5)
+  load_oracle(o, st)
+  o.forward()
+  res = {}
+  for mode, full, queue in (("reduced", 0, 0), ("full", 1, 0), ("queue", 0, 1)):
+    lib.b2_set_option(sim.h, b"full_solver", float(full))
+    lib.b2_set_option(sim.h, b"work_queue", float(queue))
+    sim.load(st)
+    sim.field("qacc")[...] = 0
+    sim.forward()
+    res[mode] = (np.array(sim.field("qacc")), np.array(sim.field("qfrc_constraint")))
+    assert relerr(res[mode][0], o.qacc).max() < 1e-4, mode
+    assert relerr(res[mode][1], o.qfrc_constraint).max() < 1e-4, mode
+  assert (o.nefc.ravel() > 0).sum() >= 3
+  assert np.array_equal(res["reduced"][0], res["queue"][0])  # same arithmetic, different dispatch
+  assert relerr(res["reduced"][0], res["full"][0]).max() < 1e-4
+  lib.b2_set_option(sim.h, b"work_queue", 1.0)
+  load_oracle(o, st)
+  sim.load(st)
+  o.step()
+  sim.step(1)
+  for f in ("qpos", "qvel", "qacc_warmstart"):
+    assert relerr(sim.field(f), o.field(f)).max() < 1e-4, f
   sim.close()

@@ -301,24 +301,3 @@ def test_matrix_free_jacobian_product(lib):
     want = {3: [a[0] + mu * a[1], a[0] - mu * a[1], a[0] + mu * a[2], a[0] - mu * a[2]], 1: [a[0], 0, 0, 0], 0: [0, 0, 0, 0]}[dims[ci]]
     assert con[CJV0 : CJV0 + 4, ci] == pytest.approx(want, rel=1e-4, abs=1e-4), (ci, dims[ci])
   assert lim[LJV, :nlim] == pytest.approx(np.where(lside == 1, -1.0, 1.0) * x[ldof], rel=1e-6)
-
-
-@pytest.mark.parametrize("case", ["g1_flat", "go1_flat", "tree33", "tree47", "tree64", "single"])
-def test_level_scheduled_solve_matches_sequential(lib, case):
-  """ldl_solve_levels (pivots of one tree level broadcast together) against numpy and against
-  the sequential sweeps, on tree-pattern matrices."""
-  rng = np.random.default_rng(13)
-  par = model_trees()[case] if case in ("g1_flat", "go1_flat") else {
-    "tree33": random_tree(33, rng), "tree47": random_tree(47, rng), "tree64": random_tree(64, rng, 0.5),
-    "single": np.array([-1], dtype=np.int32)}[case]
-  n = len(par)
-  M = tree_spd(par, rng)
-  b = rng.normal(size=n)
-  ref = np.linalg.solve(M, b)
-  A = pack(M)
-  inv = np.zeros(n, dtype=np.float32)
-  x = b.astype(np.float32).copy()
-  lib.emul_ldl_levels(n, ptr(par, ctypes.c_int), ptr(A, ctypes.c_float), ptr(inv, ctypes.c_float), ptr(x, ctypes.c_float))
-  assert np.abs(x - ref).max() < 2e-4 * max(1.0, np.abs(ref).max())
-  xs, _, _ = _solve(lib, par, M, b, True)
-  assert np.abs(x - xs).max() < 1e-4 * max(1.0, np.abs(ref).max())

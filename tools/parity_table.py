@@ -1,0 +1,105 @@
+"""Per-field error table of the CUDA path against the fp64 oracle.
+
+For each workload (B: g1_flat, C: g1_tracking_flat, E: go1_rough) and each build of libb2sim (default +
+mjlab_b200/csrc/variants/v_*.so) one forward and one step from identical seeded states on >= 1024 envs;
+the error of a field is the norm-wise relative error per env, max|a-b| / max|b| (no floor), reported as
+p50 / p99 / max over envs.  Writes gpurun_out/parity_table.json and a markdown table on stdout.
+
+  python tools/parity_table.py [n_envs]            # all builds, one subprocess per build
+  python tools/parity_table.py --one <tag> [n]     # (internal) one build in this process
+"""
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+WORKLOADS = [("B", "g1_flat", dict(seed=31)),
+             ("C", "g1_tracking_flat", dict(seed=32, tilt=0.5, joint_noise=0.6, vel=1.5)),
+             ("E", "go1_rough", dict(seed=33, spread=2.2))]
+FWD = ["qacc_smooth", "qacc", "qfrc_constraint", "contact_force", "cvel", "qM"]
+STEP = ["qpos", "qvel", "qacc_warmstart"]
+
+
+def rel(a, b):
+  import numpy as np
+  a = np.asarray(a, dtype=np.float64).reshape(len(a), -1)
+  b = np.asarray(b, dtype=np.float64).reshape(len(b), -1)
+  den = np.abs(b).max(axis=1)
+  ok = den > 1e-9
+  return (np.abs(a - b).max(axis=1)[ok] / den[ok])
+
+
+def one(tag: str, n: int):
+  import numpy as np
+  import torch
+  from util import load_oracle, load_sim, make_states, terrain_states
+  from mjlab_b200.asset_zoo import load_compiled
+  from mjlab_b200.sim import Simulation, SimulationCfg
+  from oracle.oracle import Oracle
+
+  rows = []
+  for cfg, name, kw in WORKLOADS:
+    m = load_compiled(name)
+    sim = Simulation(n, SimulationCfg(), m, "cuda:0")
+    sim.set_option("debug_outputs", 1)
+    o = Oracle(m, nworld=n, maxcon=int(sim.get_option("maxcon")))
+    kw = dict(kw)
+    if "spread" in kw:
+      st = terrain_states(m, n, kw["seed"], kw["spread"])
+    else:
+      st = make_states(m, n, **kw)
+    load_oracle(o, st)
+    load_sim(sim, st)
+    o.forward(); sim.forward(); torch.cuda.synchronize()
+    T = lambda x: x[:].detach().cpu().numpy()
+    d = sim.data
+    same = (T(d.ncon).ravel() == o.ncon.ravel())
+    stats = dict(mean_ncon=float(o.ncon.mean()), max_ncon=int(o.ncon.max()), same_ncon=int(same.sum()),
+                 mean_niter=float(T(d.solver_niter).mean()))
+    for f in FWD:
+      e = rel(T(getattr(d, f)).reshape(n, -1)[same], o.field(f).reshape(n, -1)[same])
+      rows.append(dict(build=tag, cfg=cfg, model=name, phase="forward", field=f, n=int(len(e)),
+                       p50=float(np.percentile(e, 50)), p99=float(np.percentile(e, 99)), max=float(e.max()), **stats))
+    load_oracle(o, st); load_sim(sim, st)
+    o.step(); sim.step(); torch.cuda.synchronize()
+    for f in STEP:
+      e = rel(T(getattr(d, f))[same], o.field(f)[same])
+      rows.append(dict(build=tag, cfg=cfg, model=name, phase="step", field=f, n=int(len(e)),
+                       p50=float(np.percentile(e, 50)), p99=float(np.percentile(e, 99)), max=float(e.max()), **stats))
+    sim.close()
+  print("ROWS " + json.dumps(rows))
+
+
+def main():
+  if len(sys.argv) > 2 and sys.argv[1] == "--one":
+    return one(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 1024)
+  n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+  vdir = ROOT / "mjlab_b200" / "csrc" / "variants"
+  builds = [("default", None)] + [(p.stem, p) for p in sorted(vdir.glob("v_*.so"))]
+  allrows = []
+  for tag, path in builds:
+    env = dict(os.environ)
+    if path:
+      env["B2SIM_LIB"] = str(path)
+    r = subprocess.run([sys.executable, __file__, "--one", tag, str(n)], capture_output=True, text=True, env=env)
+    got = [l for l in r.stdout.splitlines() if l.startswith("ROWS ")]
+    if not got:
+      print(f"build {tag} failed:\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
+      continue
+    allrows += json.loads(got[0][5:])
+  out = ROOT / "gpurun_out"
+  out.mkdir(exist_ok=True)
+  (out / "parity_table.json").write_text(json.dumps(allrows, indent=1))
+  print("| build | cfg | phase | field | envs | p50 | p99 | max |")
+  print("|---|---|---|---|---|---|---|---|")
+  for r in allrows:
+    print(f"| {r['build']} | {r['cfg']} | {r['phase']} | {r['field']} | {r['n']} | {r['p50']:.2e} | {r['p99']:.2e} | {r['max']:.2e} |")
+
+
+if __name__ == "__main__":
+  main()

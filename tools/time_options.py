@@ -1,0 +1,46 @@
+"""A/B timing of engine options on the bench workload (one process, same states for every variant):
+  python tools/time_options.py [n_envs] [preroll_env_steps]
+Each line: option set -> us per physics sub-step of step_n(4) (CUDA events, 12 env steps, state restored)."""
+import sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import torch
+from mjlab_b200.envs import VelocityEnvCfg, VelocityFlatEnv
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+pre = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+env = VelocityFlatEnv(VelocityEnvCfg(num_envs=n), device="cuda:0")
+g = torch.Generator(device="cuda:0"); g.manual_seed(0)
+for _ in range(pre):
+  env.step(torch.rand((n, 29), generator=g, device="cuda:0") * 2 - 1)
+torch.cuda.synchronize()
+sim = env.sim
+print("resident_ctas", sim.get_option("resident_ctas"), "smem/env", sim.get_option("smem_bytes_per_env"))
+state = {k: getattr(sim.data, k)[:].clone() for k in ("qpos", "qvel", "qacc_warmstart", "ctrl")}
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
+
+def run(label, opts, k=12):
+  for key, v in opts.items():
+    sim.set_option(key, v)
+  for key, v in state.items():
+    getattr(sim.data, key)[:] = v
+  sim.step_n(4)  # warm
+  for key, v in state.items():
+    getattr(sim.data, key)[:] = v
+  tot = 0.0
+  for _ in range(k):
+    flush.zero_()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); sim.step_n(4); b.record(); torch.cuda.synchronize()
+    tot += a.elapsed_time(b)
+  st = sim.stats()
+  print(f"{label:44s} {tot / k / 4 * 1e3:8.1f} us/sub-step   ncon {st.ncon_mean:.1f} iters {st.niter_mean:.2f}")
+
+base = dict(full_solver=0, work_queue=0, split_streams=2)
+run("r01 path: full solver, 2 streams", dict(base, full_solver=1))
+run("reduced solver, 2 streams", base)
+run("reduced solver, 1 stream", dict(base, split_streams=1))
+run("reduced + work queue, 1 stream", dict(base, work_queue=1, split_streams=1))
+run("reduced + work queue, 2 streams", dict(base, work_queue=1, split_streams=2))
+run("full + work queue, 1 stream", dict(base, full_solver=1, work_queue=1, split_streams=1))
+run("reduced + queue, unsorted dispatch", dict(base, work_queue=1, split_streams=1, sorted_dispatch=0))
