@@ -31,8 +31,31 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
-WORKLOAD = ("Unitree G1 velocity-tracking flat, {envs} envs/GPU, random-action agent, decimation 4, "
-            "dt 0.005, Newton<=10 it / ls<=20, implicitfast, pyramidal, foot-friction DR, resets+pushes")
+WORKLOADS = {
+  # BASELINE.json configs[1] (the headline), configs[2], configs[4] (per-GPU share): SURVEY.md §8d B / C / E
+  "B": dict(desc="Unitree G1 velocity-tracking flat, {envs} envs/GPU, random-action agent, decimation 4, "
+                 "dt 0.005, Newton<=10 it / ls<=20, implicitfast, pyramidal, foot-friction DR, resets+pushes",
+            model="g1_flat", robot="g1"),
+  "C": dict(desc="Unitree G1 motion-tracking flat (synthetic static clip, self-collision sensor num=10), {envs} envs/GPU, "
+                 "random-action agent, decimation 4, dt 0.005, Newton<=10 it / ls<=20, implicitfast, pyramidal, "
+                 "DR body_ipos/qpos0/foot friction, RSI resets + pushes, policy obs noise + critic group",
+            model="g1_tracking_flat", robot="g1"),
+  "E": dict(desc="Unitree Go1 velocity-tracking on the rough box terrain (3564 boxes, curriculum spawn levels <= 5), "
+                 "{envs} envs/GPU, random-action agent, decimation 4, dt 0.005, Newton<=10 it / ls<=20, implicitfast, "
+                 "pyramidal, foot-friction DR, resets+pushes",
+            model="go1_rough", robot="go1"),
+}
+WORKLOAD = WORKLOADS["B"]["desc"]
+
+
+def make_env(workload: str, envs: int, seed: int, dev: str):
+  from mjlab_b200.envs import TrackingEnvCfg, TrackingFlatEnv, VelocityEnvCfg, VelocityFlatEnv
+
+  if workload == "C":
+    return TrackingFlatEnv(TrackingEnvCfg(num_envs=envs, seed=seed), device=dev)
+  if workload == "E":
+    return VelocityFlatEnv(VelocityEnvCfg(robot="go1", terrain="rough", num_envs=envs, seed=seed), device=dev)
+  return VelocityFlatEnv(VelocityEnvCfg(num_envs=envs, seed=seed), device=dev)
 
 
 def _peaks():
@@ -149,16 +172,18 @@ class CpuPort:
   same workload: keyframe + reset noise, settled onto the ground, random actions, 4 sub-steps per
   env step.  Test infrastructure used here only as the *measured baseline*, never by the product."""
 
-  def __init__(self, envs_per_thread: int = 32, nthreads: int | None = None):
+  def __init__(self, envs_per_thread: int = 32, nthreads: int | None = None, workload: str = "B"):
     import re
 
     import numpy as np
 
-    from mjlab_b200.asset_zoo import g1, load_compiled
+    from mjlab_b200.asset_zoo import g1, go1, load_compiled
     from oracle.oracle import Oracle
 
     self.np = np
-    m = load_compiled("g1_flat")
+    wl = WORKLOADS[workload]
+    zoo = g1 if wl["robot"] == "g1" else go1
+    m = load_compiled(wl["model"])
     # all host cores this process may use; torchrun exports OMP_NUM_THREADS=1 to its workers, which would
     # otherwise shrink the CPU arm to one thread when the driver launches it under torchrun (N > 1)
     try:
@@ -172,12 +197,15 @@ class CpuPort:
     self.key = m.keys["robot/init_state"]
     qpos = np.tile(self.key["qpos"], (self.n, 1))
     qpos[:, 0:2] += self.rng.uniform(-0.5, 0.5, (self.n, 2))
+    if "terrain_origins" in m.arrays:  # rough terrain: spawn on sub-terrain origins of the lower levels
+      org = np.asarray(m.arrays["terrain_origins"])[:6].reshape(-1, 3)
+      qpos[:, 0:3] += org[self.rng.integers(0, len(org), self.n)]
     yaw = self.rng.uniform(-3.14, 3.14, self.n)
     qpos[:, 3], qpos[:, 6] = np.cos(yaw / 2), np.sin(yaw / 2)
     self.o.qpos[:] = qpos
     names = [x.split("/")[-1] for x in m.names["joint"][1:]]
     self.scale = np.array(
-      [next((v for p, v in g1.ACTION_SCALE.items() if re.match(p, nm)), 0.5) for nm in names])
+      [next((v for p, v in zoo.ACTION_SCALE.items() if re.match(p, nm)), 0.5) for nm in names])
     self.o.ctrl[:] = self.key["ctrl"]
     for _ in range(40):  # settle onto the ground (untimed) so the sample carries the contact load
       self.o.step(self.cores)
@@ -197,8 +225,8 @@ class CpuPort:
     }
 
 
-def cpu_reference_throughput(env_steps: int = 12):
-  port = CpuPort()
+def cpu_reference_throughput(env_steps: int = 12, workload: str = "B"):
+  port = CpuPort(workload=workload)
   port.env_step()  # warm caches / thread pool
   dt = sum(port.env_step() for _ in range(env_steps))
   return port.describe(env_steps, dt)
@@ -212,7 +240,7 @@ def run_reference(args):
   if rank != 0:
     return
   t0 = time.perf_counter()
-  port = CpuPort()
+  port = CpuPort(workload=args.workload)
   for _ in range(max(args.warmup, 1)):
     port.env_step()
   K = min(args.steps, 40)  # bounded: the whole arm must finish within a few minutes
@@ -223,7 +251,7 @@ def run_reference(args):
     "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
     "steps": K, "warmup": args.warmup, "ms_per_step": 1e3 * dt / K,
     "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-    "data": "synthetic", "config": {"workload": WORKLOAD.format(envs=args.envs),
+    "data": "synthetic", "config": {"workload": WORKLOADS[args.workload]["desc"].format(envs=args.envs),
                                      "note": "CPU port on host cores; each step = one env step of a "
                                              f"bounded sample ({port.n} envs)"},
     "cpu_baseline": cb,
@@ -240,6 +268,7 @@ def main():
   ap.add_argument("--warmup", type=int, default=10)
   ap.add_argument("--impl", default="b200")
   ap.add_argument("--envs", type=int, default=4096)
+  ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS), help="SURVEY.md §8d config: B (headline), C, E")
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-flush", action="store_true")
   ap.add_argument("--preroll", type=int, default=100, help="untimed env steps before warm-up")
@@ -251,8 +280,6 @@ def main():
   import torch
   import torch.distributed as dist
 
-  from mjlab_b200.envs import VelocityEnvCfg, VelocityFlatEnv
-
   world = int(os.environ.get("WORLD_SIZE", "1"))
   rank = int(os.environ.get("RANK", "0"))
   local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -263,7 +290,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device(dev))
   W = max(args.warmup, 3)
   K = args.steps
-  env = VelocityFlatEnv(VelocityEnvCfg(num_envs=args.envs, seed=42 + rank), device=dev)
+  env = make_env(args.workload, args.envs, 42 + rank, dev)
   n, nu = env.num_envs, env.nu
   gen = torch.Generator(device=dev)
   gen.manual_seed(1234 + rank)
@@ -271,7 +298,7 @@ def main():
   from mjlab_b200.dist import EnvLogGather
 
   # the one collective of the data-parallel path: per-env (reward, done) to rank 0 for logging
-  gathers = {"device": EnvLogGather(n, dev), "host": EnvLogGather(n, dev, overlap=True)}
+  gathers = {"device": EnvLogGather(n, dev, every=16), "host": EnvLogGather(n, dev, every=16)}
 
   def run(kind: str, steps: int, timed: bool):
     """kind: 'device' (actions resident) or 'host' (pinned host actions, results read back)."""
@@ -295,7 +322,7 @@ def main():
       else:
         action = torch.rand((n, nu), generator=gen, device=dev) * 2 - 1
       obs, reward, terminated, truncated, _ = env.step(action)
-      gather_logs(reward, terminated, truncated)
+      gather_logs(env.log_row)  # packed (reward, terminated, truncated), written by the env step itself
       if kind == "host":
         out_r.copy_(reward, non_blocking=True)
         out_d.copy_(torch.stack([terminated, truncated], dim=1), non_blocking=True)
@@ -393,8 +420,10 @@ def main():
       "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
       "dtype": "f32", "data": "synthetic",
       "config": {
-        "workload": WORKLOAD.format(envs=n), "envs_per_gpu": n, "decimation": 4,
-        "parallelism": f"dp{world} (envs sharded, no physics coupling; one all-gather of reward/done)",
+        "workload": WORKLOADS[args.workload]["desc"].format(envs=n), "config_id": args.workload,
+        "envs_per_gpu": n, "decimation": 4,
+        "parallelism": f"dp{world} (envs sharded, no physics coupling; (reward, done) rows all-gathered to every rank "
+                       "once per 16 env steps, same packing at 1 GPU)",
         "env_step": "one CUDA-graph replay per env step" if not args.no_graph else "eager",
         "l2": "flushed between timed steps (256 MiB memset, untimed)" if flush_buf is not None else "not flushed",
         "preroll_env_steps": args.preroll,
@@ -419,7 +448,7 @@ def main():
     }
     if not args.no_cpu_baseline and world == 1:
       try:
-        line["cpu_baseline"] = cpu_reference_throughput()
+        line["cpu_baseline"] = cpu_reference_throughput(workload=args.workload)
       except Exception as e:  # the oracle is test infrastructure; never fail the bench on it
         line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
                                 "sample": f"failed: {e}"}

@@ -108,9 +108,12 @@ int b2_step_host(b2_sim* sim, const float* ctrl_host, int nsubstep, float* qpos_
 /* Fused MDP glue of the velocity-tracking task around the step: what
  * ManagerBasedRlEnv.step (manager_based_rl_env.py:106-147) does before and after the decimation loop for
  * tasks/velocity/velocity_env_cfg.py, as two launches. All pointers are device pointers. */
+#define B2_VELENV_NU(nu) (16 + 9 + 2 * (nu))
 typedef struct B2VelEnvArgs {
   const float* action;            /* [n][nu] */
-  const float* U;                 /* [n][10] uniforms in [0,1): reset xy, yaw, command(3), push(2), timer, spare */
+  const float* U;                 /* [n][B2_VELENV_NU(nu)] uniforms in [0,1): 0-1 reset xy, 2 yaw, 3-5 command, 6 heading
+                                     target, 7 standing draw, 8 command timer, 9-10 push, 11 push timer, 12-15 spare,
+                                     16.. observation noise (9 + 2 nu) */
   const float* default_qpos;      /* [nq] */
   const float* default_joint_pos; /* [nu] */
   const float* action_scale;      /* [nu] */
@@ -126,6 +129,11 @@ typedef struct B2VelEnvArgs {
   unsigned char* terminated;      /* [n] out */
   unsigned char* truncated;       /* [n] out */
   unsigned char* done;            /* [n] out: mask for b2_forward_masked */
+  float* cmd_time_left;           /* [n] in/out: command resampling timer (velocity_env_cfg.py:69 3..8 s) */
+  float* heading_target;          /* [n] in/out: heading command (velocity_command.py:71-75) */
+  unsigned char* is_standing;     /* [n] in/out: standing envs get a zero command (rel_standing_envs = 0.1) */
+  float* critic;                  /* [n][9 + 3 nu + 3] out: the same terms without noise (PrivilegedCfg) */
+  float* log_row;                 /* [n][3] out: (reward, terminated, truncated) packed for the rank-0 log gather */
   float step_dt, fall_angle, push_vel, push_lo, push_hi;
   int32_t max_episode_length;
 } B2VelEnvArgs;

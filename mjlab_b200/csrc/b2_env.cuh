@@ -38,7 +38,8 @@ __global__ void b2_velenv_post_kernel(DevData dd, int nq, int nv, int nu, B2VelE
   float* qvel = dd.qvel.p + (size_t)w * dd.qvel.stride;
   float* ctrl = dd.ctrl.p + (size_t)w * dd.ctrl.stride;
   const float* act = A.action + (size_t)w * nu;
-  const float* U = A.U + (size_t)w * 10;
+  const int NUU = B2_VELENV_NU(nu);
+  const float* U = A.U + (size_t)w * NUU;
   float* last = A.last_action + (size_t)w * nu;
   float* cmd = A.command + 3 * (size_t)w;
   int ep = A.episode_length[w] + 1;
@@ -64,6 +65,8 @@ __global__ void b2_velenv_post_kernel(DevData dd, int nq, int nv, int nu, B2VelE
   A.reward[w] = (r_lin + r_ang + r_pose - lim - 0.1f * rate) * A.step_dt;
   bool done = term || trunc;
   A.terminated[w] = term; A.truncated[w] = trunc; A.done[w] = done;
+  A.log_row[3 * (size_t)w] = A.reward[w]; A.log_row[3 * (size_t)w + 1] = term ? 1.f : 0.f;
+  A.log_row[3 * (size_t)w + 2] = trunc ? 1.f : 0.f;
   // masked reset (reset_root_state_uniform + reset_joints_by_scale), command resample
   if (done) {
     for (int i = 0; i < nq; i++) qpos[i] = A.default_qpos[i];
@@ -78,32 +81,58 @@ __global__ void b2_velenv_post_kernel(DevData dd, int nq, int nv, int nu, B2VelE
       last[a] = 0.f;
     }
     for (int i = 0; i < nv; i++) qvel[i] = 0.f;
-    cmd[0] = U[3] * 2.f - 1.f; cmd[1] = U[4] - 0.5f; cmd[2] = U[5] * 2.f - 1.f;
     ep = 0;
   } else {
     for (int a = 0; a < nu; a++) last[a] = act[a];
   }
   A.episode_length[w] = ep;
+  // command term (CommandTerm.compute + UniformVelocityCommand, velocity_command.py:64-110): resample on
+  // reset and when the timer runs out, then heading control and standing envs every step
+  float ctl = A.cmd_time_left[w] - A.step_dt;
+  if (done || ctl <= 0.f) {
+    cmd[0] = U[3] * 2.f - 1.f; cmd[1] = U[4] - 0.5f; cmd[2] = U[5] * 2.f - 1.f;
+    A.heading_target[w] = (U[6] * 2.f - 1.f) * 3.14159265358979f;
+    A.is_standing[w] = U[7] <= 0.1f;
+    ctl = 3.f + 5.f * U[8];
+  }
+  A.cmd_time_left[w] = ctl;
+  {
+    // heading_w = atan2 of the body x axis in the world (entity/data.py:480-484), from the post-reset pose
+    float qw = qpos[3], qx = qpos[4], qy = qpos[5], qz = qpos[6];
+    float fx = 1.f - 2.f * (qy * qy + qz * qz), fy = 2.f * (qx * qy + qw * qz);
+    float err = A.heading_target[w] - atan2f(fy, fx);
+    err -= 6.28318530717959f * floorf((err + 3.14159265358979f) / 6.28318530717959f);  // wrap_to_pi
+    cmd[2] = fminf(fmaxf(0.5f * err, -1.f), 1.f);
+    if (A.is_standing[w]) { cmd[0] = 0.f; cmd[1] = 0.f; cmd[2] = 0.f; }
+  }
   // interval event: push_by_setting_velocity
   float tl = A.push_time_left[w] - A.step_dt;
   if (tl <= 0.f) {
-    qvel[0] = (U[6] * 2.f - 1.f) * A.push_vel;
-    qvel[1] = (U[7] * 2.f - 1.f) * A.push_vel;
-    tl = U[8] * (A.push_hi - A.push_lo) + A.push_lo;
+    qvel[0] = (U[9] * 2.f - 1.f) * A.push_vel;
+    qvel[1] = (U[10] * 2.f - 1.f) * A.push_vel;
+    tl = U[11] * (A.push_hi - A.push_lo) + A.push_lo;
   }
   A.push_time_left[w] = tl;
   // observations from the (possibly reset / pushed) state
+  // policy group with uniform noise (velocity_env_cfg.py:86-118), critic group without (:120-125)
   float* o = A.obs + (size_t)w * (9 + 3 * nu + 3);
+  float* cr = A.critic + (size_t)w * (9 + 3 * nu + 3);
+  const float* Z = U + 16;  // noise draws
   float q2[4] = {qpos[3], qpos[4], qpos[5], qpos[6]}, lin2[3] = {qvel[0], qvel[1], qvel[2]};
   b2e_rot_inv(q2, lin2, lb);
   b2e_rot_inv(q2, down, gb);
-  o[0] = lb[0]; o[1] = lb[1]; o[2] = lb[2];
-  o[3] = qvel[3]; o[4] = qvel[4]; o[5] = qvel[5];
-  o[6] = gb[0]; o[7] = gb[1]; o[8] = gb[2];
+  for (int k = 0; k < 3; k++) {
+    cr[k] = lb[k]; cr[3 + k] = qvel[3 + k]; cr[6 + k] = gb[k];
+    o[k] = lb[k] + (Z[k] * 2.f - 1.f) * 0.1f;
+    o[3 + k] = qvel[3 + k] + (Z[3 + k] * 2.f - 1.f) * 0.2f;
+    o[6 + k] = gb[k] + (Z[6 + k] * 2.f - 1.f) * 0.05f;
+  }
   for (int a = 0; a < nu; a++) {
-    o[9 + a] = qpos[7 + a] - A.default_joint_pos[a];
-    o[9 + nu + a] = qvel[6 + a];
+    float jp = qpos[7 + a] - A.default_joint_pos[a], jv = qvel[6 + a];
+    cr[9 + a] = jp; cr[9 + nu + a] = jv; cr[9 + 2 * nu + a] = last[a];
+    o[9 + a] = jp + (Z[9 + a] * 2.f - 1.f) * 0.01f;
+    o[9 + nu + a] = jv + (Z[9 + nu + a] * 2.f - 1.f) * 1.5f;
     o[9 + 2 * nu + a] = last[a];
   }
-  o[9 + 3 * nu] = cmd[0]; o[10 + 3 * nu] = cmd[1]; o[11 + 3 * nu] = cmd[2];
+  for (int k = 0; k < 3; k++) { o[9 + 3 * nu + k] = cmd[k]; cr[9 + 3 * nu + k] = cmd[k]; }
 }

@@ -656,6 +656,10 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
 #define SCHED s_sched, (const int*)s_sched + m.ldl_nsparse, m.ldl_dense
 #define FACTOR(sp) ldl_factor(H, invdiag, nv, SCHED, sp, lane)
 #define SOLVE(v, tree) ldl_solve(H, invdiag, v, nv, lane)
+  // Phase-synchronous execution (dd.phase_sync): the kernel's code is ~200 KB against a 32 KB instruction cache,
+  // so the CTA's warps are re-aligned at every phase boundary and they fetch the same code together.
+  const bool psync = dd.phase_sync != 0;
+#define PSYNC() do { if (psync) __syncthreads(); } while (0)
 #pragma unroll 1
   for (int i = threadIdx.x; i < m.ldl_nsparse; i += 32 * B2_WARPS_PER_CTA) s_sched[i] = m.ldl_sparse[i];
   if (threadIdx.x < 18) s_sched[m.ldl_nsparse + threadIdx.x] = (unsigned)m.ldl_start[threadIdx.x];
@@ -711,6 +715,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   }
 
   PHASE_MARK(0);
+  PSYNC();
   float* xpos = s + L.xpos; float* xquat = s + L.xquat; float* xipos = s + L.xipos;
   float* scom = s + L.scom; float* xanchor = s + L.xanchor; float* xaxis = s + L.xaxis;
   float* cinert = s + L.cinert; float* crb = s + L.crb; float* cdof = s + L.cdof;
@@ -855,6 +860,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   __syncwarp();
 
   PHASE_MARK(1);
+  PSYNC();
   // geom / site world poses -> global (and shared for collidable geoms)
   float* gpose = s + L.gpose;
   {
@@ -900,6 +906,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   }
 
   PHASE_MARK(2);
+  PSYNC();
   // ---------------- phase 2: subtree com, spatial inertias, motion vectors -----------------------
   {
     const float* mass = MP(body_mass); const float* sub = MP(body_subtreemass);
@@ -1008,6 +1015,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   __syncwarp();
 
   PHASE_MARK(3);
+  PSYNC();
   // ---------------- phase 3: composite inertias -> joint-space inertia M (packed lower) ----------
   #pragma unroll 1
   for (int b = lane; b < nb; b += 32) {
@@ -1040,6 +1048,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   __syncwarp();
 
   PHASE_MARK(4);
+  PSYNC();
   // ---------------- phase 4: velocities, bias forces, actuation, qfrc_smooth ----------------------
   #pragma unroll 1
   for (int b = lane; b < nb; b += 32) {
@@ -1169,6 +1178,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   }
 
   PHASE_MARK(5);
+  PSYNC();
   // ---------------- phase 5: collision (static pair table, bounding-sphere filter, primitives) ----
   float* con = s + L.contacts;   // overlays the smooth-only regions (cinert, crb, cdofdot, cacc, ...)
   float* lim = s + L.limits;
@@ -1469,6 +1479,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   __syncwarp();
 
   PHASE_MARK(6);
+  PSYNC();
   // ---------------- phase 6: joint-limit rows, body-pair groups ----------------------------------
   int nlim = 0;
   {
@@ -1602,6 +1613,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   }
 
   PHASE_MARK(7);
+  PSYNC();
   // ---------------- phase 7: unconstrained acceleration -------------------------------------------
   #pragma unroll 1
   for (int i = lane; i < (m.ntri + 3) >> 2; i += 32) ((float4*)H)[i] = ((const float4*)Mq)[i];  // both regions are 16 B aligned and padded
@@ -1614,9 +1626,17 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     for (int i = lane; i < nv; i += 32) dd.qacc_smooth.p[(size_t)w * dd.qacc_smooth.stride + i] = qacc_smooth[i];
 
   PHASE_MARK(8);
+  PSYNC();
   // ---------------- phase 8: Newton solver (primal, exact line search) ----------------------------
   int niter = 0;
   float cost = 0.f;
+  const float* Mr = reduced ? Mred : Mq;  // reduced problem: Schur complement of M on the leading block
+  const float* qs = qfrc_smooth;
+  const float scale = 1.f / (m.meaninertia * (float)max(1, nv));
+  float* gA = s + L.gA; float* gu = s + L.gu; int* glist = (int*)(s + L.glist); float* gW = s + L.gW;
+  float oldcost = 0.f;
+  bool first = true;
+  bool run = nefc > 0;  // this warp still iterates (under phase_sync finished warps keep voting at the loop top)
   if (nefc == 0) {
     #pragma unroll 1
     for (int i = lane; i < nv; i += 32) { qacc[i] = qacc_smooth[i]; qfrc_c[i] = 0.f; }
@@ -1625,8 +1645,6 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     // Reduced problem (n < nv): minimising the Gauss term over the unconstrained dofs in closed form leaves
     // 1/2 (a-a_s)^T Mr (a-a_s) on the leading block, Mr = Schur complement of M (snapshot of phase 7); the
     // code below is the full-size solver with (Mr, Mr a_s) in place of (M, qfrc_smooth).
-    const float* Mr = reduced ? Mred : Mq;
-    const float* qs = qfrc_smooth;
     if (reduced) {
       symv(Mr, qacc_smooth, tmpv, n, lane);
       qs = tmpv;
@@ -1663,11 +1681,11 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       for (int r = lane; r < nlim; r += 32) lim[LJAR * NLC + r] = lim[LJV * NLC + r];
       __syncwarp();
     }
-    const float scale = 1.f / (m.meaninertia * (float)max(1, nv));
-    float* gA = s + L.gA; float* gu = s + L.gu; int* glist = (int*)(s + L.glist); float* gW = s + L.gW;
-    float oldcost = 0.f;
-    bool first = true;
-    while (true) {
+  }
+  #pragma unroll 1
+  while (true) {
+    if (psync) { if (!__syncthreads_or(run ? 1 : 0)) break; } else if (!run) break;
+    if (run) do {
       // ---- constraint update: forces, cost, active set, qfrc_constraint = J^T f ---------------
       float cst = 0.f;
       bool changed = false;
@@ -1759,15 +1777,18 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       gn = wsum(gn);
       if (!first) {
         float improvement = scale * (oldcost - cost), gradient = scale * sqrtf(gn);
-        if (improvement < m.tolerance || gradient < m.tolerance) break;
+        if (improvement < m.tolerance || gradient < m.tolerance) { run = false; break; }
         // Exact termination: the cost is one quadratic per active set, and a Newton step with exact
         // line search lands on that quadratic's minimiser; if the active set did not change across
         // the move, the new point is the minimiser of the true (convex) cost.
-        if (!changed) break;
+        if (!changed) { run = false; break; }
       }
-      if (niter >= m.iterations) break;
+      if (niter >= m.iterations) { run = false; break; }
       first = false;
-      PHASE_MARK(12);
+    } while (0);
+    PHASE_MARK(12);
+    PSYNC();
+    if (run) {
       // ---- Hessian H = M + J^T D_active J via per-body-pair 6x6 blocks -------------------------
       {  // leading block only: the rows of the eliminated dofs keep the factor of M (needed after the loop)
         const int nt = n * (n + 1) >> 1;
@@ -1843,7 +1864,10 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       for (int i = lane; i < n; i += 32) search[i] = -grad[i];
       __syncwarp();
       ldl_solve(H, invdiag, search, n, lane);
-      PHASE_MARK(14);
+    }
+    PHASE_MARK(14);
+    PSYNC();
+    if (run) do {
       // ---- exact line search along `search` --------------------------------------------------
       symv(Mr, search, Mv, n, lane);
       MULJ(search, CJV0, LJV, false);
@@ -1855,7 +1879,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         sn += search[i] * search[i];
       }
       g1 = wsum(g1); g2 = wsum(g2); sn = sqrtf(wsum(sn));
-      if (sn < MINVAL) break;
+      if (sn < MINVAL) { run = false; break; }
       float gtol = m.tolerance * m.ls_tolerance * sn / scale;
       // each lane keeps its rows in registers for the whole search (<= 2 contacts + 1 limit per lane)
       float lsD[3], lsJ[9], lsV[9];
@@ -1922,7 +1946,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         }
       }
       PHASE_MARK(16);
-      if (alpha == 0.f) break;
+      if (alpha == 0.f) { run = false; break; }
       #pragma unroll 1
       for (int i = lane; i < n; i += 32) { qacc[i] += alpha * search[i]; Ma[i] += alpha * Mv[i]; }
       #pragma unroll 1
@@ -1934,7 +1958,9 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       __syncwarp();
       oldcost = cost;
       niter++;
-    }
+    } while (0);
+  }
+  if (nefc > 0) {
     if (reduced) {
       // eliminated dofs: a_c = a_s,c - L_cc^-1 L_cd (a_d - a_s,d), i.e. rows k >= n of L x = 0 with x_d given
       // (the factor of M from phase 7 is intact in those rows: x_k = -(1/d_k) sum_{j<k} A[k,j] x_j)
@@ -1957,6 +1983,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   }
 
   PHASE_MARK(9);
+  PSYNC();
   // ---------------- phase 9: contact forces, sensors -----------------------------------------------
   {
     float* g_force = dd.contact_force.p + (size_t)w * dd.contact_force.stride;
@@ -2054,6 +2081,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   }
 
   PHASE_MARK(10);
+  PSYNC();
   // ---------------- phase 10: integrate (implicitfast / Euler), write state ------------------------
   float* gq = dd.qpos.p + (size_t)w * dd.qpos.stride;
   float* gv = dd.qvel.p + (size_t)w * dd.qvel.stride;

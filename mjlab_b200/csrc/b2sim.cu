@@ -61,6 +61,7 @@ struct b2_sim {
   int sorted_dispatch = 1;
   int fused_decimation = 0;
   int split_streams = 2;       // b2_step_n runs this many env partitions on internal streams
+  int phase_sync = 0;          // CTA barriers at phase boundaries (instruction-cache locality)
   int work_queue = 0;          // warps pull environments from a ticket counter (persistent grid)
   int* tickets = nullptr;      // one counter per stream partition (device)
   int resident_ctas = 0;       // co-resident CTAs of the step kernel on this device
@@ -226,6 +227,8 @@ static int launch(b2_sim* s, bool step, cudaStream_t st, int nsub = 1, int base 
     if (queue) CUDA_OK(cudaMemsetAsync(ticket, 0, sizeof(int), st));
   }
   s->hd.ticket = ticket;
+  // phase-synchronous warps need every warp of every CTA to own an environment (no early exits, no mask)
+  s->hd.phase_sync = s->phase_sync && !queue && s->hd.world_mask == nullptr && count % B2_WARPS_PER_CTA == 0;
   if (queue) grid = s->resident_ctas;
   if (step)
     b2_step_kernel<true><<<grid, 32 * B2_WARPS_PER_CTA, s->smem_bytes, st>>>(s->hm, s->hd);
@@ -841,6 +844,7 @@ int b2_set_option(b2_sim* s, const char* key, double v) {
   else if (k == "fused_decimation") s->fused_decimation = (int)v;
   else if (k == "split_streams") s->split_streams = (int)v;
   else if (k == "work_queue") s->work_queue = (int)v;
+  else if (k == "phase_sync") s->phase_sync = (int)v;
   else if (k == "full_solver") m.debug = (m.debug & ~4) | ((int)v ? 4 : 0);  // Newton on all dofs even when a leading block suffices (tests, A/B)
   else return fail("b2_set_option: unknown option '" + k + "'");
   return 0;
@@ -861,6 +865,7 @@ int b2_get_option(b2_sim* s, const char* key, double* v) {
   else if (k == "maxcon") *v = m.maxcon;
   else if (k == "full_solver") *v = (m.debug >> 2) & 1;
   else if (k == "work_queue") *v = s->work_queue;
+  else if (k == "phase_sync") *v = s->phase_sync;
   else if (k == "resident_ctas") *v = s->resident_ctas;
   else if (k == "reduced_block_cap") *v = m.lay.ndcap;
   else return fail("b2_get_option: unknown option '" + k + "'");

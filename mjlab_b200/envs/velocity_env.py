@@ -111,6 +111,11 @@ class VelocityFlatEnv:
     self.episode_length_buf = torch.zeros(n, dtype=torch.int32, device=dev)
     self.last_action = torch.zeros(n, self.nu, **f32)
     self.command = torch.zeros(n, 3, **f32)
+    # UniformVelocityCommand state (velocity_env_cfg.py:66-83): resampling timer 3..8 s, heading control, 10 % standing
+    self.cmd_time_left = torch.zeros(n, **f32)
+    self.heading_target = torch.zeros(n, **f32)
+    self.is_standing = torch.zeros(n, dtype=torch.bool, device=dev)
+    self.log_row = torch.zeros(n, 3, **f32)  # (reward, terminated, truncated): the rank-0 log gather reads this
     self.push_time_left = torch.zeros(n, **f32)
     self._down = torch.tensor([0.0, 0.0, -1.0], **f32).expand(n, 3)  # gravity direction (world)
     self.native_mdp = bool(native_mdp)
@@ -127,8 +132,9 @@ class VelocityFlatEnv:
     return torch.rand(shape, generator=self.gen, device=self.device)
 
   def _draw(self) -> torch.Tensor:
-    """The step's uniform numbers, one launch: columns 0-1 reset xy, 2 yaw, 3-5 command, 6-7 push, 8 timer."""
-    return self._rand(self.num_envs, 10)
+    """The step's uniform numbers, one launch (layout: include/b2sim.h B2VelEnvArgs.U): 0-1 reset xy, 2 yaw,
+    3-5 command, 6 heading target, 7 standing draw, 8 command timer, 9-10 push, 11 push timer, 16.. obs noise."""
+    return self._rand(self.num_envs, 16 + 9 + 2 * self.nu)
 
   def _init_native(self) -> None:
     from mjlab_b200.sim import native
@@ -139,7 +145,8 @@ class VelocityFlatEnv:
     self._reward = torch.zeros(n, device=dev)
     self._term = torch.zeros(n, dtype=torch.bool, device=dev)
     self._trunc = torch.zeros(n, dtype=torch.bool, device=dev)
-    self._U = torch.zeros(n, 10, device=dev)
+    self._U = torch.zeros(n, 16 + 9 + 2 * self.nu, device=dev)
+    self._critic = torch.zeros(n, self.nobs, device=dev)
     self._action_in = torch.zeros(n, self.nu, device=dev)
     self._origins = self.env_origins.contiguous()
     a = native.B2VelEnvArgs()
@@ -150,6 +157,8 @@ class VelocityFlatEnv:
       ("episode_length", self.episode_length_buf), ("last_action", self.last_action),
       ("command", self.command), ("push_time_left", self.push_time_left), ("obs", self._obs),
       ("reward", self._reward), ("terminated", self._term), ("truncated", self._trunc), ("done", self._done_buf),
+      ("cmd_time_left", self.cmd_time_left), ("heading_target", self.heading_target),
+      ("is_standing", self.is_standing), ("critic", self._critic), ("log_row", self.log_row),
     ):
       assert t.is_contiguous()
       setattr(a, name, t.data_ptr())
@@ -176,22 +185,46 @@ class VelocityFlatEnv:
     d.ctrl[:] = torch.where(mk, self.default_joint_pos.expand(n, -1), d.ctrl[:])
     self.episode_length_buf.copy_(torch.where(mask, torch.zeros_like(self.episode_length_buf), self.episode_length_buf))
     self.last_action.copy_(torch.where(mk, torch.zeros_like(self.last_action), self.last_action))
-    # command resample (UniformVelocityCommand, velocity_env_cfg.py:66-83)
-    cmd = torch.stack([U[:, 3] * 2 - 1, U[:, 4] - 0.5, U[:, 5] * 2 - 1], dim=1)
-    self.command.copy_(torch.where(mk, cmd, self.command))
 
-  def observations(self) -> torch.Tensor:
+  def _update_command(self, done: torch.Tensor, U: torch.Tensor) -> None:
+    """CommandTerm.compute + UniformVelocityCommand (tasks/velocity/mdp/velocity_command.py:64-110): resample on
+    reset and on timer expiry (3..8 s), heading control on every env, standing envs (10 %) get a zero command."""
+    ctl = self.cmd_time_left - self.step_dt
+    rs = done | (ctl <= 0)
+    cmd = torch.stack([U[:, 3] * 2 - 1, U[:, 4] - 0.5, U[:, 5] * 2 - 1], dim=1)
+    self.command.copy_(torch.where(rs.unsqueeze(1), cmd, self.command))
+    self.heading_target.copy_(torch.where(rs, (U[:, 6] * 2 - 1) * math.pi, self.heading_target))
+    self.is_standing.copy_(torch.where(rs, U[:, 7] <= 0.1, self.is_standing))
+    self.cmd_time_left.copy_(torch.where(rs, 3.0 + 5.0 * U[:, 8], ctl))
+    q = self.sim.data.qpos[:, 3:7]
+    fx = 1 - 2 * (q[:, 2] ** 2 + q[:, 3] ** 2)
+    fy = 2 * (q[:, 1] * q[:, 2] + q[:, 0] * q[:, 3])
+    err = self.heading_target - torch.atan2(fy, fx)
+    err = err - 2 * math.pi * torch.floor((err + math.pi) / (2 * math.pi))
+    self.command[:, 2] = (0.5 * err).clamp(-1.0, 1.0)
+    self.command.copy_(torch.where(self.is_standing.unsqueeze(1), torch.zeros_like(self.command), self.command))
+
+  def observations(self, U: torch.Tensor | None = None):
+    """Policy group (uniform noise per term, velocity_env_cfg.py:86-118); ``critic`` is the noise-free copy."""
     d = self.sim.data
     q = d.qpos[:, 3:7]
     lin_b = quat_rotate_inverse(q, d.qvel[:, 0:3])
-    return torch.cat(
-      [lin_b, d.qvel[:, 3:6], quat_rotate_inverse(q, self._down), d.qpos[:, 7:] - self.default_joint_pos,
-       d.qvel[:, 6:], self.last_action, self.command], dim=1)
+    terms = [lin_b, d.qvel[:, 3:6], quat_rotate_inverse(q, self._down), d.qpos[:, 7:] - self.default_joint_pos,
+             d.qvel[:, 6:], self.last_action, self.command]
+    self.critic_obs = torch.cat(terms, dim=1)
+    if U is None:
+      return self.critic_obs
+    Z, nu = U[:, 16:] * 2 - 1, self.nu
+    noise = [Z[:, 0:3] * 0.1, Z[:, 3:6] * 0.2, Z[:, 6:9] * 0.05, Z[:, 9:9 + nu] * 0.01, Z[:, 9 + nu:9 + 2 * nu] * 1.5]
+    return torch.cat([t + z for t, z in zip(terms[:5], noise)] + terms[5:], dim=1)
 
   # -- API ---------------------------------------------------------------------------------------
   def reset(self):
-    self._reset_where(torch.ones(self.num_envs, dtype=torch.bool, device=self.device), self._draw())
+    all_ = torch.ones(self.num_envs, dtype=torch.bool, device=self.device)
+    U = self._draw()
+    self._reset_where(all_, U)
     self.sim.forward()
+    self._update_command(all_, U)
     return self.observations()
 
   def enable_cuda_graph(self) -> None:
@@ -238,7 +271,7 @@ class VelocityFlatEnv:
     sim.step_n(self.cfg.decimation)
     native.check(sim._lib.b2_velenv_post(sim._h, ctypes.byref(self._native_args), st))
     sim.forward(env_mask=self._done_buf)
-    return self._obs, self._reward, self._term, self._trunc, {}
+    return self._obs, self._reward, self._term, self._trunc, {"critic": self._critic}
 
   def _step_torch(self, action: torch.Tensor):
     """Reference implementation of the same step in torch ops (also the checker of the fused kernels)."""
@@ -267,14 +300,17 @@ class VelocityFlatEnv:
     self._reset_where(done, U)
     self._done_buf.copy_(done)
     self.sim.forward(env_mask=self._done_buf)  # only the reset envs need new derived quantities here
+    self._update_command(done, U)
+    self.log_row.copy_(torch.stack([reward, terminated.float(), truncated.float()], dim=1))
     # interval event: push_by_setting_velocity (events.py:127-143)
     self.push_time_left -= self.step_dt
     push = self.push_time_left <= 0
-    pv = (U[:, 6:8] * 2 - 1) * cfg.push_vel
+    pv = (U[:, 9:11] * 2 - 1) * cfg.push_vel
     d.qvel[:, 0:2] = torch.where(push.unsqueeze(1), pv, d.qvel[:, 0:2])
     lo_t, hi_t = cfg.push_interval_s
-    self.push_time_left.copy_(torch.where(push, U[:, 8] * (hi_t - lo_t) + lo_t, self.push_time_left))
-    return self.observations(), reward, terminated, truncated, {}
+    self.push_time_left.copy_(torch.where(push, U[:, 11] * (hi_t - lo_t) + lo_t, self.push_time_left))
+    obs = self.observations(U)
+    return obs, reward, terminated, truncated, {"critic": self.critic_obs}
 
   def close(self):
     self.sim.close()

@@ -49,7 +49,7 @@ class B2VelEnvArgs(ctypes.Structure):
     [(n, ctypes.c_void_p) for n in (
       "action", "U", "default_qpos", "default_joint_pos", "action_scale", "soft_lo", "soft_hi",
       "env_origins", "episode_length", "last_action", "command", "push_time_left", "obs", "reward",
-      "terminated", "truncated", "done")]
+      "terminated", "truncated", "done", "cmd_time_left", "heading_target", "is_standing", "critic", "log_row")]
     + [(n, ctypes.c_float) for n in ("step_dt", "fall_angle", "push_vel", "push_lo", "push_hi")]
     + [("max_episode_length", ctypes.c_int32)]
   )

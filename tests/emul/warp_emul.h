@@ -66,6 +66,16 @@ inline dim3& emul_gridDim() { static dim3 v; return v; }
 
 inline void __syncwarp(unsigned = 0xffffffffu) { warp_emul::sync(); }
 inline void __syncthreads() { pthread_barrier_wait(&warp_emul::ctx().cta); }
+inline int __syncthreads_or(int pred) {
+  static int vote = 0;
+  if (pred) __atomic_store_n(&vote, 1, __ATOMIC_RELAXED);
+  __syncthreads();
+  int r = __atomic_load_n(&vote, __ATOMIC_RELAXED);
+  __syncthreads();
+  __atomic_store_n(&vote, 0, __ATOMIC_RELAXED);
+  __syncthreads();
+  return r;
+}
 template <class T> inline T __shfl_sync(unsigned, T v, int src) { return warp_emul::exchange(v, src); }
 template <class T> inline T __shfl_xor_sync(unsigned, T v, int m) { return warp_emul::exchange(v, warp_emul::lane() ^ m); }
 template <class T> inline T __shfl_up_sync(unsigned, T v, int d) {

@@ -106,10 +106,21 @@ def _gloo_worker(rank, world, port, q):
   r, w = b2dist.init(backend="gloo")
   n = 16
   lo, hi = b2dist.shard_range(world * n, r, w)
-  g = b2dist.EnvLogGather(n, "cpu")
+  g = b2dist.EnvLogGather(n, "cpu", every=4)
   reward = torch.arange(lo, hi, dtype=torch.float32)
-  out = g(reward, reward % 2 == 0, reward % 3 == 0)
-  q.put((r, out[..., 0].flatten().tolist(), b2dist.EnvLogGather.summarize(out)))
+  # six env steps: one gather after the 4th row (ring full), join() flushes the 2 rows of the next round
+  for k in range(4):
+    out = g(reward + 100.0 * k, reward % 2 == 0, reward % 3 == 0)
+  assert g.flushes == 1
+  first = out.clone()
+  packed = torch.stack([reward + 400.0, (reward % 2 == 0).float(), (reward % 3 == 0).float()], dim=1)
+  g(packed)  # a row the env packed itself (b2_velenv_post writes env.log_row)
+  g(packed + 0.0)
+  assert g.flushes == 1
+  out = g.join()
+  assert g.flushes == 2 and g.join() is out and g.flushes == 2
+  q.put((r, first[:, 0, :, 0].flatten().tolist(), first[:, 3, :, 0].flatten().tolist(), out[:, 0, :, 0].flatten().tolist(),
+         b2dist.EnvLogGather.summarize(first[:, 0])))
   dist.destroy_process_group()
 
 
@@ -126,8 +137,9 @@ def test_env_log_gather_world_size_2_gloo():
   for p in procs:
     p.join(timeout=60)
     assert p.exitcode == 0
-  for _, rewards, summ in res:
-    assert rewards == [float(i) for i in range(32)]  # every rank sees the whole job, rank order
+  for _, row0, row3, row4, summ in res:
+    assert row0 == [float(i) for i in range(32)]  # every rank sees the whole job, rank order, step order
+    assert row3 == [float(i) + 300.0 for i in range(32)] and row4 == [float(i) + 400.0 for i in range(32)]
     assert summ["terminated"] == 16 and summ["truncated"] == 11
 
 

@@ -1,0 +1,91 @@
+"""Config C (BASELINE.json configs[2]): G1 motion tracking on flat ground — the env-level caller and one-step
+parity against the fp64 oracle at the contact-rich, self-colliding states the random-action agent produces
+(per-world domain randomisation of body_ipos / qpos0 / geom_friction included)."""
+
+import numpy as np
+import pytest
+import torch
+
+from util import relerr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def T(x):
+  return x[:].detach().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def env():
+  from mjlab_b200.envs import TrackingEnvCfg, TrackingFlatEnv
+
+  e = TrackingFlatEnv(TrackingEnvCfg(num_envs=256, seed=7), device=DEV)
+  yield e
+  e.close()
+
+
+def test_tracking_env_steps_and_resets(env):
+  n = env.num_envs
+  g = torch.Generator(device=DEV)
+  g.manual_seed(0)
+  pol, crit = env.observations()
+  assert pol.shape == (n, 58 + 3 + 6 + 3 + 3 + 29 + 29 + 29) and crit.shape == (n, pol.shape[1] + 14 * 3 + 14 * 6)
+  resets, selfcol, maxcon = 0, 0.0, 0
+  for _ in range(40):
+    obs, rew, term, trunc, extra = env.step(torch.rand((n, 29), generator=g, device=DEV) * 2 - 1)
+    assert torch.isfinite(obs).all() and torch.isfinite(rew).all() and torch.isfinite(extra["critic"]).all()
+    resets += int((term | trunc).sum())
+    selfcol = max(selfcol, float(env.sim.data.sensordata[:, env.self_collision_adr[0]].max()))
+    maxcon = max(maxcon, int(env.sim.data.ncon[:].max()))
+  assert resets > 0          # flailing robots leave the reference pose and are put back on the clip
+  assert selfcol >= 1.0      # the self-collision sensor (num=10 slots, slot 0 = count) sees contacts
+  assert maxcon >= 12
+  assert (env.time_steps >= 0).all() and (env.time_steps < env.cfg.clip_frames).all()
+  assert int(env.sim.stats().overflow_worlds) == 0
+  # per-world DR is in place: torso com offsets, joint zero offsets and foot friction differ between worlds
+  assert env.sim.model.body_ipos[:].std(dim=0).max() > 1e-3 and env.sim.model.qpos0[:].std(dim=0).max() > 1e-3
+
+
+def test_tracking_step_parity_at_self_collision_states(env):
+  """One physics step from the env's own mid-rollout states (many contacts, self-collisions, active limits)."""
+  from oracle.oracle import Oracle
+
+  sim, m, n = env.sim, env.model, env.num_envs
+  o = Oracle(m, nworld=n, maxcon=int(sim.get_option("maxcon")))
+  for f in ("body_ipos", "qpos0", "geom_friction"):
+    o.model_field(f)[:] = T(getattr(sim.model, f)).reshape(n, -1)
+  for f in ("qpos", "qvel", "ctrl", "qacc_warmstart"):
+    o.field(f)[:] = T(getattr(sim.data, f))
+  o.field("xfrc_applied")[:] = T(sim.data.xfrc_applied).reshape(n, -1)
+  o.step()
+  sim.step()
+  torch.cuda.synchronize()
+  d = sim.data
+  same = T(d.ncon).ravel() == o.ncon.ravel()
+  assert same.mean() > 0.97  # a contact at the detection threshold may appear on one side only
+  assert o.ncon.max() >= 12 and o.sensordata[:, 0].max() >= 1
+  assert (T(d.sensordata)[same] == o.sensordata[same]).all()  # self-collision counts are integers: exact
+  for f, p99, mx in (("qpos", 1e-5, 1e-4), ("qvel", 1e-4, 1e-3), ("qacc_warmstart", 1e-4, 1e-3)):
+    e = relerr(T(getattr(d, f))[same], o.field(f)[same], floor=1e-9)
+    assert np.percentile(e, 99) < p99 * 3 and e.max() < mx * 3, (f, np.percentile(e, 99), e.max())
+
+
+def test_tracking_env_step_is_graph_capturable():
+  """One whole env step (ctrl, 4 sub-steps, terminations, rewards, RSI resets + masked forwards, command update,
+  push, both observation groups) replays from a CUDA graph: no host synchronisation anywhere in the step."""
+  from mjlab_b200.envs import TrackingEnvCfg, TrackingFlatEnv
+
+  b = TrackingFlatEnv(TrackingEnvCfg(num_envs=64, seed=3), device=DEV)
+  b.enable_cuda_graph()
+  g = torch.Generator(device=DEV)
+  g.manual_seed(1)
+  q0 = b.sim.data.qpos[:].clone()
+  done = 0
+  for _ in range(30):
+    ob, rb, tb, ub, info = b.step(torch.rand((64, 29), generator=g, device=DEV) * 2 - 1)
+    assert torch.isfinite(ob).all() and torch.isfinite(rb).all() and torch.isfinite(info["critic"]).all()
+    done += int((tb | ub).sum())
+    assert torch.equal(b.log_row[:, 0], rb)
+  assert not torch.equal(b.sim.data.qpos[:], q0) and done > 0
+  b.close()

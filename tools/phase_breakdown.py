@@ -8,9 +8,12 @@ from mjlab_b200.envs import VelocityEnvCfg, VelocityFlatEnv
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 env = VelocityFlatEnv(VelocityEnvCfg(num_envs=n), device="cuda:0")
 g = torch.Generator(device="cuda:0"); g.manual_seed(0)
-for _ in range(60):
+for _ in range(int(sys.argv[2]) if len(sys.argv) > 2 else 100):
   env.step(torch.rand((n, 29), generator=g, device="cuda:0") * 2 - 1)
 sim = env.sim
+for kv in sys.argv[3:]:
+  k, v = kv.split("=")
+  sim.set_option(k, float(v))
 buf = (ctypes.c_ulonglong * 32)()
 sim._lib.b2_phase_cycles(buf)  # reset
 K = 20

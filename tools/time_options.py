@@ -36,11 +36,10 @@ def run(label, opts, k=12):
   st = sim.stats()
   print(f"{label:44s} {tot / k / 4 * 1e3:8.1f} us/sub-step   ncon {st.ncon_mean:.1f} iters {st.niter_mean:.2f}")
 
-base = dict(full_solver=0, work_queue=0, split_streams=2)
-run("r01 path: full solver, 2 streams", dict(base, full_solver=1))
+base = dict(full_solver=0, work_queue=0, split_streams=2, phase_sync=0)
 run("reduced solver, 2 streams", base)
-run("reduced solver, 1 stream", dict(base, split_streams=1))
-run("reduced + work queue, 1 stream", dict(base, work_queue=1, split_streams=1))
-run("reduced + work queue, 2 streams", dict(base, work_queue=1, split_streams=2))
-run("full + work queue, 1 stream", dict(base, full_solver=1, work_queue=1, split_streams=1))
-run("reduced + queue, unsorted dispatch", dict(base, work_queue=1, split_streams=1, sorted_dispatch=0))
+run("reduced, 2 streams, phase_sync", dict(base, phase_sync=1))
+run("reduced, 1 stream, phase_sync", dict(base, phase_sync=1, split_streams=1))
+run("reduced, 1 stream", dict(base, split_streams=1))
+run("full solver, 2 streams, phase_sync", dict(base, full_solver=1, phase_sync=1))
+run("reduced, 3 streams, phase_sync", dict(base, phase_sync=1, split_streams=3))
