@@ -65,6 +65,23 @@ def _peaks():
   return 6650.0, "fallback"
 
 
+def _issue_roofline(kern_ms: float, envs: int, clocks) -> dict:
+  """The roofline that actually binds this kernel: warp-instruction issue slots (4 schedulers per SM, one warp
+  instruction per cycle each).  Instructions per environment come from the committed ncu capture of the same
+  kernel and workload (profiles/step_kernel_traffic.json: smsp__inst_executed.sum / envs); time is this run's."""
+  tp = ROOT / "profiles" / "step_kernel_traffic.json"
+  try:
+    t = json.loads(tp.read_text())
+    ipe, sms = float(t["warp_inst_per_env"]), int(t.get("sms", 148))
+  except Exception:
+    return {"bound": "issue", "frac": None, "note": "no warp_inst_per_env in profiles/step_kernel_traffic.json"}
+  mhz = (clocks or {}).get("sm_mhz") or 1965.0
+  achieved = ipe * envs / (kern_ms * 1e-3)
+  peak = sms * 4 * mhz * 1e6
+  return {"bound": "issue", "achieved": achieved, "peak": peak, "unit": "warp-inst/s", "frac": achieved / peak,
+          "warp_inst_per_env": ipe, "source": t.get("source", "profiles/")}
+
+
 class ClockSampler:
   """SM clock / throttle-reason sampling during the timed region (B200_PROFILING.md clocks line).
 
@@ -167,12 +184,42 @@ class ClockSampler:
             "samples": len(sm), "source": "nvidia-smi"}
 
 
+def physical_cores() -> list[int]:
+  """One logical CPU per physical core among those this process may run on (hyper-thread siblings dropped)."""
+  try:
+    allowed = sorted(os.sched_getaffinity(0))
+  except AttributeError:
+    allowed = list(range(os.cpu_count() or 1))
+  seen, out = set(), []
+  for c in allowed:
+    try:
+      sib = Path(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list").read_text().strip()
+    except OSError:
+      sib = str(c)
+    if sib not in seen:
+      seen.add(sib)
+      out.append(c)
+  return out
+
+
+def _pinned_env(ncores: int) -> dict:
+  """Environment of the CPU arm's process: one OpenMP thread per physical core, pinned (torchrun exports
+  OMP_NUM_THREADS=1 to its workers and torch's own OpenMP runtime is already initialised in this process, so the
+  arm runs in a child whose runtime starts with these settings)."""
+  env = dict(os.environ)
+  # (the core count travels with it: once the runtime has bound the main thread to its place, the child's own
+  # affinity mask no longer shows the other cores)
+  env.update(OMP_NUM_THREADS=str(ncores), OMP_PROC_BIND="close", OMP_PLACES="cores", OMP_DYNAMIC="false",
+             B2_CPU_ARM_PINNED="1", B2_CPU_ARM_CORES=str(ncores))
+  return env
+
+
 class CpuPort:
   """The CPU port of the hot path (oracle, fp32, OpenMP static over envs) on a bounded sample of the
   same workload: keyframe + reset noise, settled onto the ground, random actions, 4 sub-steps per
   env step.  Test infrastructure used here only as the *measured baseline*, never by the product."""
 
-  def __init__(self, envs_per_thread: int = 32, nthreads: int | None = None, workload: str = "B"):
+  def __init__(self, envs_per_thread: int = 128, nthreads: int | None = None, workload: str = "B"):
     import re
 
     import numpy as np
@@ -184,13 +231,8 @@ class CpuPort:
     wl = WORKLOADS[workload]
     zoo = g1 if wl["robot"] == "g1" else go1
     m = load_compiled(wl["model"])
-    # all host cores this process may use; torchrun exports OMP_NUM_THREADS=1 to its workers, which would
-    # otherwise shrink the CPU arm to one thread when the driver launches it under torchrun (N > 1)
-    try:
-      avail = len(os.sched_getaffinity(0))
-    except AttributeError:
-      avail = os.cpu_count() or 1
-    self.cores = nthreads or avail
+    self.cores = nthreads or int(os.environ.get("B2_CPU_ARM_CORES", 0)) or len(physical_cores())
+    self.pinned = os.environ.get("B2_CPU_ARM_PINNED") == "1"
     self.n = max(self.cores * envs_per_thread, 8)
     self.o = Oracle(m, nworld=self.n, maxcon=48, precision="f32")
     self.rng = np.random.default_rng(42)
@@ -217,43 +259,69 @@ class CpuPort:
       self.o.step(self.cores)
     return time.perf_counter() - t0
 
-  def describe(self, env_steps: int, seconds: float) -> dict:
+  def measure(self, env_steps: int, repeats: int = 3, min_seconds: float = 4.0) -> dict:
+    """`repeats` timed blocks of at least `env_steps` env steps and `min_seconds` each (10-30 s of CPU work in
+    all): value = median block, spread = (max - min) / median."""
+    self.env_step()  # warm caches / thread pool
+    vals, secs, total_steps = [], 0.0, 0
+    for _ in range(repeats):
+      dt, k = 0.0, 0
+      while k < env_steps or dt < min_seconds:
+        dt += self.env_step()
+        k += 1
+      secs += dt
+      total_steps += k
+      vals.append(self.n * k / dt)
+    vals.sort()
+    v = vals[len(vals) // 2]
     return {
-      "value": self.n * env_steps / seconds, "unit": UNIT, "cores": self.cores, "kind": "port",
-      "sample": f"{self.n} envs x {env_steps} env-steps (x4 sub-steps), fp32 restated CPU oracle "
-                f"(not C-MuJoCo, not mujoco_warp-CPU), OpenMP static over envs, {seconds:.1f} s",
+      "value": v, "unit": UNIT, "cores": self.cores, "kind": "port",
+      "per_core": v / self.cores, "repeats": vals, "spread": (vals[-1] - vals[0]) / v,
+      "threads": f"{self.cores} OpenMP threads, one per physical core, " +
+                 ("pinned (OMP_PROC_BIND=close, OMP_PLACES=cores)" if self.pinned else "NOT pinned"),
+      "sample": f"{self.n} envs ({self.n // self.cores} per thread) x {total_steps} env-steps in {repeats} blocks (x4 sub-steps), fp32 "
+                f"restated CPU oracle (not C-MuJoCo, not mujoco_warp-CPU), OpenMP static over envs, {secs:.1f} s",
     }
 
 
-def cpu_reference_throughput(env_steps: int = 12, workload: str = "B"):
-  port = CpuPort(workload=workload)
-  port.env_step()  # warm caches / thread pool
-  dt = sum(port.env_step() for _ in range(env_steps))
-  return port.describe(env_steps, dt)
+def cpu_reference_throughput(env_steps: int = 4, workload: str = "B"):
+  """The cpu_baseline leg: the pinned CPU arm in a child process (see _pinned_env); returns its description."""
+  cores = len(physical_cores())
+  r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--workload", workload,
+                      "--steps", str(3 * env_steps), "--warmup", "1"],
+                     capture_output=True, text=True, env={**_pinned_env(cores), "RANK": "0", "WORLD_SIZE": "1"}, timeout=900)
+  for line in reversed(r.stdout.splitlines()):
+    if line.startswith("{"):
+      return json.loads(line)["cpu_baseline"]
+  raise RuntimeError(f"cpu arm produced no line: {r.stderr[-300:]}")
 
 
 def run_reference(args):
   """--impl reference: the reference's physics cannot be installed here (mujoco / mujoco_warp /
   warp wheels absent, no network), so this arm times the CPU port of the same path on
-  all host cores; each step is one env step of a bounded sample of the workload.  Rank 0 only."""
+  all physical host cores (pinned); each step is one env step of a bounded sample of the workload.  Rank 0 only."""
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return
+  if os.environ.get("B2_CPU_ARM_PINNED") != "1":
+    # re-run in a child whose OpenMP runtime starts pinned with one thread per physical core
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py")] + sys.argv[1:], env=_pinned_env(len(physical_cores())))
+    sys.exit(r.returncode)
   t0 = time.perf_counter()
   port = CpuPort(workload=args.workload)
-  for _ in range(max(args.warmup, 1)):
-    port.env_step()
-  K = min(args.steps, 40)  # bounded: the whole arm must finish within a few minutes
-  dt = sum(port.env_step() for _ in range(K))
-  cb = port.describe(K, dt)
+  K = max(1, min(args.steps, 36) // 3)  # three timed blocks; bounded so the whole arm ends within a few minutes
+  cb = port.measure(K, repeats=3)
   v = cb["value"]
   line = {
     "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-    "steps": K, "warmup": args.warmup, "ms_per_step": 1e3 * dt / K,
+    "steps": 3 * K, "warmup": args.warmup, "ms_per_step": 1e3 * port.n / v,
     "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
     "data": "synthetic", "config": {"workload": WORKLOADS[args.workload]["desc"].format(envs=args.envs),
-                                     "note": "CPU port on host cores; each step = one env step of a "
+                                     "config_id": args.workload,
+                                     "note": "CPU port of the hot path on host cores (the reference's mujoco_warp / C-MuJoCo "
+                                             "cannot be installed in this image); each step = one env step of a "
                                              f"bounded sample ({port.n} envs)"},
+    "reference_runnable": False, "impl_detail": "cpu_port (restated oracle, fp32, OpenMP)", "gpus_used": 0,
     "cpu_baseline": cb,
     "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     "wall_s": time.perf_counter() - t0,
@@ -276,6 +344,8 @@ def main():
   args = ap.parse_args()
   if args.impl == "reference":
     return run_reference(args)
+
+  import ctypes
 
   import torch
   import torch.distributed as dist
@@ -360,26 +430,33 @@ def main():
   run("device", 1, False)
   launches_per_step = env.sim.launch_count() - l0
 
-  # ---- physics-kernel timing hook: events around the 4 sub-step launches ---------------------------
-  phys_events = []
-  orig_step_n = env.sim.step_n
-
-  def timed_step_n(k):
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    orig_step_n(k)
-    b.record()
-    phys_events.append((a, b, k))
-
   # Pre-roll to the steady-state mix of standing / falling / freshly reset robots (all envs start
   # standing at t=0, so without it the timed window would measure a transient), then W warm-up steps.
   run("device", args.preroll, False)
-  # kernel-only timing pass (eager, events around the sub-step launches): feeds the roofline
-  env.sim.step_n = timed_step_n
-  run("device", max(W, 5), False)
-  env.sim.step_n = orig_step_n
-  kern_ms = sum(a.elapsed_time(b) for a, b, _ in phys_events) / max(sum(k for _, _, k in phys_events), 1)
-  kern_ms = maxr(kern_ms)
+  # ---- kernel-only timing: the decimation's sub-step launches replayed from their own CUDA graph (no launch
+  # gaps, like inside the env-step graph), one replay after every env step of a short pass so that the states
+  # keep the workload's distribution.  Feeds the roofline; 4 x kernel_ms <= ms_per_step by construction.
+  dec = env.cfg.decimation
+  side = torch.cuda.Stream(dev)
+  side.wait_stream(torch.cuda.current_stream())
+  with torch.cuda.stream(side):
+    env.sim.step_n(dec)
+    g_phys = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g_phys, stream=side):
+      env.sim.step_n(dec)
+  torch.cuda.current_stream().wait_stream(side)
+  phys_ms, reps = 0.0, max(W, 8)
+  for _ in range(reps):
+    env.step(torch.rand((n, nu), generator=gen, device=dev) * 2 - 1)
+    if flush_buf is not None:
+      flush_buf.zero_()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    g_phys.replay()
+    b.record()
+    torch.cuda.synchronize()
+    phys_ms += a.elapsed_time(b)
+  kern_ms = maxr(phys_ms / (reps * dec))
   if not args.no_graph:
     env.enable_cuda_graph()
   run("device", W, False)  # warm-up (untimed)
@@ -405,6 +482,30 @@ def main():
   e2e_ms, (h2d, d2h) = run("host", K, True)
   barrier()
   e2e_ms = maxr(e2e_ms)
+
+  # ---- the plugin call itself: b2_step_host (C ABI, HOST buffers in and out, copies inside the call) -------
+  import numpy as np
+
+  ctrl_h = torch.empty((n, nu), pin_memory=True)
+  qpos_h = torch.empty((n, env.nq), pin_memory=True)
+  qvel_h = torch.empty((n, env.nv), pin_memory=True)
+  base_ctrl = env.sim.data.ctrl[:].cpu()
+  cabi_ev = []
+  for k in range(W + K):
+    ctrl_h.copy_(base_ctrl + 0.1 * (torch.rand((n, nu)) * 2 - 1))
+    if flush_buf is not None:
+      flush_buf.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = env.sim._lib.b2_step_host(env.sim._h, ctypes.c_void_p(ctrl_h.data_ptr()), dec, ctypes.c_void_p(qpos_h.data_ptr()),
+                                   ctypes.c_void_p(qvel_h.data_ptr()), env.sim._stream())
+    assert rc == 0
+    e1.record()
+    e1.synchronize()
+    if k >= W:
+      cabi_ev.append(e0.elapsed_time(e1))
+  cabi_ms = maxr(sum(cabi_ev))
+  assert np.isfinite(qpos_h.numpy()).all()
 
   if rank == 0:
     peak, which = _peaks()
@@ -432,7 +533,11 @@ def main():
       },
       "clocks": clocks,
       "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-              "ms_per_step": e2e_ms / K},
+              "ms_per_step": e2e_ms / K,
+              "path": "env.step through the public Python API: pinned host actions in, reward/done/obs out every step"},
+      "e2e_cabi": {"value": world * n * K / (cabi_ms * 1e-3), "unit": UNIT, "ms_per_step": cabi_ms / K,
+                   "h2d_bytes_per_step": n * nu * 4, "d2h_bytes_per_step": n * (env.nq + env.nv) * 4,
+                   "path": "b2_step_host (include/b2sim.h): host ctrl in, 4 sub-steps, host qpos/qvel out; physics only, no MDP terms"},
       "gpu_launches": int(launches),
       "roofline": {
         "kernel": "b2_step_kernel<true> (fused physics sub-step)", "bound": "hbm",
@@ -443,6 +548,7 @@ def main():
                 "latency/ALU bound, the constraint Jacobian never exists in HBM",
         "solver_formula_gbs": sb.value / (kern_ms * 1e-3) / 1e9,
       },
+      "roofline_issue": _issue_roofline(kern_ms, n, clocks),
       "physics_only_env_steps_per_sec": world * n / (4 * kern_ms * 1e-3),
       "wall_s": wall,
     }

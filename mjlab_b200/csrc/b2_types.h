@@ -121,7 +121,7 @@ struct DevData {
       site_xmat, sensordata, actuator_force, time;
   DArr qfrc_bias, qfrc_smooth, qacc_smooth, qfrc_constraint, qM;
   DArr contact_dist, contact_pos, contact_frame, contact_force, solver_cost;
-  IArr ncon, nefc, solver_niter, contact_geom, overflow;
+  IArr ncon, nefc, solver_niter, contact_geom, overflow, solver_nd;
   int phase_sync;                   // CTA barriers at phase boundaries (every warp of the launch owns an environment)
   int* ticket;                      // optional: work queue of launch slots (one atomic per environment)
   const int* world_order;           // optional: launch slot -> world (heavy-first dispatch)

@@ -57,6 +57,7 @@ class EnvLogGather:
     self.out = torch.zeros((self.world, self.every, num_envs, 3), dtype=torch.float32, device=dev)
     self.k = 0
     self.flushes = 0
+    self._pending = 0  # rows appended since the last gather
 
   def __call__(self, reward: torch.Tensor, terminated: torch.Tensor | None = None, truncated: torch.Tensor | None = None):
     slot = self.ring[self.k % self.every]
@@ -67,6 +68,7 @@ class EnvLogGather:
       slot[:, 1] = terminated.to(torch.float32)
       slot[:, 2] = truncated.to(torch.float32)
     self.k += 1
+    self._pending += 1
     if self.k % self.every == 0:
       self.flush()
     return self.out
@@ -77,11 +79,12 @@ class EnvLogGather:
     else:
       dist.all_gather_into_tensor(self.out.view(-1), self.ring.view(-1), group=self.group)
     self.flushes += 1
+    self._pending = 0
     return self.out
 
   def join(self):
     """Flush rows appended since the last gather (no-op when the ring was just gathered)."""
-    if self.k % self.every != 0:
+    if self._pending:
       self.flush()
     return self.out
 

@@ -48,6 +48,10 @@ def one(tag: str, n: int):
     sim = Simulation(n, SimulationCfg(), m, "cuda:0")
     sim.set_option("debug_outputs", 1)
     o = Oracle(m, nworld=n, maxcon=int(sim.get_option("maxcon")))
+    # the oracle is run to convergence: with MuJoCo's cap of 10 Newton iterations a few stiff environments stop
+    # early in fp64 and their (path-dependent) answer is further from the minimiser than the fp32 engine's
+    o.set_option("iterations", 50)
+    sim.set_option("iterations", 50)  # (both sides: a capped, unconverged answer depends on the path taken)
     kw = dict(kw)
     if "spread" in kw:
       st = terrain_states(m, n, kw["seed"], kw["spread"])
@@ -59,8 +63,17 @@ def one(tag: str, n: int):
     T = lambda x: x[:].detach().cpu().numpy()
     d = sim.data
     same = (T(d.ncon).ravel() == o.ncon.ravel())
+    # contact sets must be the same contacts: a sphere centre on the mid-plane of a thin box (or a capsule
+    # exactly parallel to a face) is pushed out through either face depending on the last bit - such ties are
+    # geometry degeneracies of the random test states, not solver error, and are counted separately
+    mc = T(d.contact_frame).shape[1]
+    fr_o = o.contact_frame.reshape(n, -1, 9)[:, :mc, :3]
+    fr_g = T(d.contact_frame).reshape(n, mc, 9)[:, :, :3]
+    live = np.arange(mc)[None, :] < o.ncon.reshape(n, 1)
+    tie = ((np.abs(fr_g - fr_o).max(-1) > 1e-3) & live).any(1)
+    same &= ~tie
     stats = dict(mean_ncon=float(o.ncon.mean()), max_ncon=int(o.ncon.max()), same_ncon=int(same.sum()),
-                 mean_niter=float(T(d.solver_niter).mean()))
+                 geometry_ties=int(tie.sum()), mean_niter=float(T(d.solver_niter).mean()))
     for f in FWD:
       e = rel(T(getattr(d, f)).reshape(n, -1)[same], o.field(f).reshape(n, -1)[same])
       rows.append(dict(build=tag, cfg=cfg, model=name, phase="forward", field=f, n=int(len(e)),

@@ -47,5 +47,5 @@ if mode == "time":
   sim.data.qpos[:, 2] += 5.0  # lift everyone: no contacts
   timeit("airborne (no contacts)")
 else:
-  for _ in range(6): sim.step()
+  for _ in range(6): sim.step_n(1) if hasattr(sim, "step_n") else sim.step()
   torch.cuda.synchronize()
