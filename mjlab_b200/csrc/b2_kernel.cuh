@@ -734,6 +734,9 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
 #pragma unroll 1
   for (int sub = 0;; sub++) {
   const bool lastsub = !STEP || sub + 1 >= dd.nsub;
+  // Consumer-visible kinematics (poses, cvel, derived velocities) are observable only after the last sub-step
+  // of a decimation loop: the launches before it skip those stores (and the poses of non-colliding geoms).
+  const bool emit = dd.emit != 0 && lastsub;
   // ---------------- phase 1: kinematics (lane per body, private walk down its ancestor chain) ----
   {
     const float* body_pos = MP(body_pos); const float* body_quat = MP(body_quat);
@@ -854,10 +857,12 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       float t[3], mat[9];
       rotq(t, quat, body_ipos + 3 * b);
       xipos[3 * b] = pos[0] + t[0]; xipos[3 * b + 1] = pos[1] + t[1]; xipos[3 * b + 2] = pos[2] + t[2];
-      quat2mat(mat, quat);
-      float* gx = dd.xmat.p + (size_t)w * dd.xmat.stride + 9 * b;
+      if (emit) {
+        quat2mat(mat, quat);
+        float* gx = dd.xmat.p + (size_t)w * dd.xmat.stride + 9 * b;
 #pragma unroll
-      for (int k = 0; k < 9; k++) gx[k] = mat[k];
+        for (int k = 0; k < 9; k++) gx[k] = mat[k];
+      }
     }
   }
   __syncwarp();
@@ -874,16 +879,19 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     #pragma unroll 1
     for (int gi = lane; gi < m.nposegeom; gi += 32) {
       int g = m.posegeom[gi];
+      int cs = m.geom_cslot[g];
+      if (!emit && cs < 0) continue;  // a geom that cannot collide is posed for its consumers only
       int b = m.geom_bodyid[g];
       float p[3], q[4], mat[9];
       rotq(p, xquat + 4 * b, geom_pos + 3 * g);
       p[0] += xpos[3 * b]; p[1] += xpos[3 * b + 1]; p[2] += xpos[3 * b + 2];
       mulquat(q, xquat + 4 * b, geom_quat + 4 * g);
       quat2mat(mat, q);
-      gxp[3 * g] = p[0]; gxp[3 * g + 1] = p[1]; gxp[3 * g + 2] = p[2];
+      if (emit) {
+        gxp[3 * g] = p[0]; gxp[3 * g + 1] = p[1]; gxp[3 * g + 2] = p[2];
 #pragma unroll
-      for (int k = 0; k < 9; k++) gxm[9 * g + k] = mat[k];
-      int cs = m.geom_cslot[g];
+        for (int k = 0; k < 9; k++) gxm[9 * g + k] = mat[k];
+      }
       if (cs >= 0) {
         float* gp = gpose + GP * cs;
         gp[0] = p[0]; gp[1] = p[1]; gp[2] = p[2];
@@ -896,7 +904,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     float* sxp = dd.site_xpos.p + (size_t)w * dd.site_xpos.stride;
     float* sxm = dd.site_xmat.p + (size_t)w * dd.site_xmat.stride;
     #pragma unroll 1
-    for (int g = lane; g < m.nsite; g += 32) {
+    for (int g = emit ? lane : m.nsite; g < m.nsite; g += 32) {
       int b = m.site_bodyid[g];
       float p[3], q[4], mat[9];
       rotq(p, xquat + 4 * b, site_pos + 3 * g);
@@ -947,7 +955,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     if (am < MINVAL) { c0[0] = scom[0]; c0[1] = scom[1]; c0[2] = scom[2]; }
     else { float inv = 1.f / am; c0[0] = a0 * inv; c0[1] = a1 * inv; c0[2] = a2 * inv; }
   }
-  {  // body poses / coms leave now (coalesced); their shared-memory home is recycled after phase 4
+  if (emit) {  // body poses / coms leave now (coalesced); their shared-memory home is recycled after phase 4
     float* g0 = dd.xpos.p + (size_t)w * dd.xpos.stride;
     float* g1 = dd.xquat.p + (size_t)w * dd.xquat.stride;
     float* g2 = dd.xipos.p + (size_t)w * dd.xipos.stride;
@@ -1080,13 +1088,39 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     }
 #pragma unroll
     for (int k = 0; k < 6; k++) cvel[SD * b + k] = v[k];
-    // output cvel in MuJoCo's convention: linear part at subtree_com[root]
-    int r = m.body_rootid[b];
-    float dr[3] = {scom[3 * r] - c0[0], scom[3 * r + 1] - c0[1], scom[3 * r + 2] - c0[2]}, t[3];
-    cross3(t, v, dr);
-    float* gc = dd.cvel.p + (size_t)w * dd.cvel.stride + 6 * b;
-    gc[0] = v[0]; gc[1] = v[1]; gc[2] = v[2];
-    gc[3] = v[3] + t[0]; gc[4] = v[4] + t[1]; gc[5] = v[5] + t[2];
+    if (emit) {
+      // output cvel in MuJoCo's convention: linear part at subtree_com[root]
+      int r = m.body_rootid[b];
+      float dr[3] = {scom[3 * r] - c0[0], scom[3 * r + 1] - c0[1], scom[3 * r + 2] - c0[2]}, t[3];
+      cross3(t, v, dr);
+      float* gc = dd.cvel.p + (size_t)w * dd.cvel.stride + 6 * b;
+      gc[0] = v[0]; gc[1] = v[1]; gc[2] = v[2];
+      gc[3] = v[3] + t[0]; gc[4] = v[4] + t[1]; gc[5] = v[5] + t[2];
+      // The quantities mjlab's EntityData derives from (xpos, subtree_com, cvel, xquat) with gathers and quaternion
+      // kernels (entity/data.py:190-516), written here once per body: world velocity of the link origin and of
+      // the body com, and in the link frame the linear / angular velocity, projected gravity and the heading.
+      float dl[3] = {xpos[3 * b] - c0[0], xpos[3 * b + 1] - c0[1], xpos[3 * b + 2] - c0[2]}, tl[3];
+      float dc[3] = {xipos[3 * b] - c0[0], xipos[3 * b + 1] - c0[1], xipos[3 * b + 2] - c0[2]}, tc[3];
+      cross3(tl, v, dl);
+      cross3(tc, v, dc);
+      float lin[3] = {v[3] + tl[0], v[4] + tl[1], v[5] + tl[2]};
+      float* lw = dd.link_vel_w.p + (size_t)w * dd.link_vel_w.stride + 6 * b;
+      float* cw = dd.com_vel_w.p + (size_t)w * dd.com_vel_w.stride + 6 * b;
+      float* lb = dd.link_state_b.p + (size_t)w * dd.link_state_b.stride + 10 * b;
+      const float* q = xquat + 4 * b;
+      float qi[4] = {q[0], -q[1], -q[2], -q[3]}, lbv[3], abv[3], gbv[3];
+      const float down[3] = {0.f, 0.f, -1.f};
+      rotq(lbv, qi, lin);
+      rotq(abv, qi, v);
+      rotq(gbv, qi, down);
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        lw[k] = lin[k]; lw[3 + k] = v[k];
+        cw[k] = v[3 + k] + tc[k]; cw[3 + k] = v[k];
+        lb[k] = lbv[k]; lb[3 + k] = abv[k]; lb[6 + k] = gbv[k];
+      }
+      lb[9] = atan2f(2.f * (q[1] * q[2] + q[0] * q[3]), 1.f - 2.f * (q[2] * q[2] + q[3] * q[3]));
+    }
   }
   __syncwarp();
   PSYNC_L(3);

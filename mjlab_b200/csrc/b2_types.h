@@ -119,9 +119,11 @@ struct DevData {
   DArr qpos, qvel, ctrl, qacc_warmstart, qfrc_applied, xfrc_applied, act;
   DArr qacc, xpos, xquat, xmat, xipos, subtree_com, cvel, geom_xpos, geom_xmat, site_xpos,
       site_xmat, sensordata, actuator_force, time;
+  DArr link_vel_w, com_vel_w, link_state_b;  // per body: EntityData's derived velocities / body-frame state
   DArr qfrc_bias, qfrc_smooth, qacc_smooth, qfrc_constraint, qM;
   DArr contact_dist, contact_pos, contact_frame, contact_force, solver_cost;
   IArr ncon, nefc, solver_niter, contact_geom, overflow, solver_nd;
+  int emit;                         // write consumer-visible kinematics (0 for all but the last sub-step of a decimation loop)
   int phase_sync;                   // CTA barriers at phase boundaries (every warp of the launch owns an environment)
   int* ticket;                      // optional: work queue of launch slots (one atomic per environment)
   const int* world_order;           // optional: launch slot -> world (heavy-first dispatch)

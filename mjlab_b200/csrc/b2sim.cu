@@ -61,6 +61,7 @@ struct b2_sim {
   int sorted_dispatch = 1;
   int fused_decimation = 0;
   int split_streams = 2;       // b2_step_n runs this many env partitions on internal streams
+  int reorder_every_substep = 1;  // heavy-first order recomputed before every sub-step (measured 447 vs 462 us: fresh Newton counts keep phase-synchronous CTAs balanced)
   int phase_sync = 2;          // CTA barriers at phase boundaries, level 0..3 (instruction-cache locality; -14 % measured)
   int work_queue = 0;          // warps pull environments from a ticket counter (persistent grid)
   int* tickets = nullptr;      // one counter per stream partition (device)
@@ -214,19 +215,24 @@ static int add_idata(b2_sim* s, const char* name, IArr* arr, int n, int second =
   return 0;
 }
 
-static int launch(b2_sim* s, bool step, cudaStream_t st, int nsub = 1, int base = 0, int count = -1, int part = 0) {
+static int launch(b2_sim* s, bool step, cudaStream_t st, int nsub = 1, int base = 0, int count = -1, int part = 0,
+                  int emit = 1, bool reorder = true) {
   if (count < 0) count = s->nworld;
   s->hd.nsub = nsub;
+  s->hd.emit = emit;
   s->hd.world_base = base;
   s->hd.world_count = count;
   int grid = (count + B2_WARPS_PER_CTA - 1) / B2_WARPS_PER_CTA;
   const bool queue = s->work_queue && s->tickets && s->resident_ctas > 0 && grid > s->resident_ctas;
   int* ticket = queue ? s->tickets + part : nullptr;
   if (step && s->sorted_dispatch && s->order && count >= 512 && s->hd.world_mask == nullptr) {
-    b2_order_kernel<<<1, 1024, 0, st>>>(s->hd.solver_niter.p, s->hd.solver_niter.stride, s->hd.ncon.p,
-                                        s->hd.ncon.stride, s->hd.solver_nd.p, s->hd.solver_nd.stride,
-                                        s->hm.lay.ndcap, base, count, s->order, ticket);
-    s->launches++;
+    // (the order of the first sub-step of a decimation loop serves the whole loop: costs change little within it)
+    if (reorder || queue) {
+      b2_order_kernel<<<1, 1024, 0, st>>>(s->hd.solver_niter.p, s->hd.solver_niter.stride, s->hd.ncon.p,
+                                          s->hd.ncon.stride, s->hd.solver_nd.p, s->hd.solver_nd.stride,
+                                          s->hm.lay.ndcap, base, count, s->order, ticket);
+      s->launches++;
+    }
     s->hd.world_order = s->order;
   } else {
     s->hd.world_order = nullptr;
@@ -643,6 +649,8 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
   rc |= add_data(s, "cvel", &d.cvel, 6 * nb, 6); rc |= add_data(s, "geom_xpos", &d.geom_xpos, 3 * ng, 3);
   rc |= add_data(s, "geom_xmat", &d.geom_xmat, 9 * ng, 9); rc |= add_data(s, "site_xpos", &d.site_xpos, 3 * ns, 3);
   rc |= add_data(s, "site_xmat", &d.site_xmat, 9 * ns, 9);
+  rc |= add_data(s, "link_vel_w", &d.link_vel_w, 6 * nb, 6); rc |= add_data(s, "com_vel_w", &d.com_vel_w, 6 * nb, 6);
+  rc |= add_data(s, "link_state_b", &d.link_state_b, 10 * nb, 10);
   rc |= add_data(s, "sensordata", &d.sensordata, m.nsensordata);
   rc |= add_data(s, "actuator_force", &d.actuator_force, nu); rc |= add_data(s, "time", &d.time, 1);
   rc |= add_data(s, "qfrc_bias", &d.qfrc_bias, nv); rc |= add_data(s, "qfrc_smooth", &d.qfrc_smooth, nv);
@@ -852,6 +860,7 @@ int b2_set_option(b2_sim* s, const char* key, double v) {
   else if (k == "split_streams") s->split_streams = (int)v;
   else if (k == "work_queue") s->work_queue = (int)v;
   else if (k == "phase_sync") s->phase_sync = (int)v;
+  else if (k == "reorder_every_substep") s->reorder_every_substep = (int)v;
   else if (k == "full_solver") m.debug = (m.debug & ~4) | ((int)v ? 4 : 0);  // Newton on all dofs even when a leading block suffices (tests, A/B)
   else return fail("b2_set_option: unknown option '" + k + "'");
   return 0;
@@ -916,14 +925,14 @@ int b2_step_n(b2_sim* s, int n, void* stream) {
       if (count <= 0) break;
       CUDA_OK(cudaStreamWaitEvent(s->side[h], s->ev_fork, 0));
       for (int i = 0; i < n; i++)
-        if (launch(s, true, s->side[h], 1, base, count, h)) return 1;
+        if (launch(s, true, s->side[h], 1, base, count, h, i == n - 1, i == 0 || s->reorder_every_substep)) return 1;
       CUDA_OK(cudaEventRecord(s->ev_join[h], s->side[h]));
       CUDA_OK(cudaStreamWaitEvent(st, s->ev_join[h], 0));
     }
     return 0;
   }
   for (int i = 0; i < n; i++)
-    if (launch(s, true, st)) return 1;
+    if (launch(s, true, st, 1, 0, -1, 0, i == n - 1, i == 0 || s->reorder_every_substep)) return 1;
   return 0;
 }
 

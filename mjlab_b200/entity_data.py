@@ -151,8 +151,9 @@ class EntityData:
   def __init__(self, indexing: EntityIndexing, data, model, device: str, num_envs: int,
                default_root_state: torch.Tensor | None = None,
                default_joint_pos: torch.Tensor | None = None,
-               soft_joint_pos_limit_factor: float = 1.0):
+               soft_joint_pos_limit_factor: float = 1.0, native: bool = True):
     self.indexing, self.data, self.model, self.device = indexing, data, model, device
+    self.native = native
     ix = indexing
     self.is_fixed_base = ix.free_joint_q_adr.numel() == 0
     self.is_articulated = ix.joint_q_adr.numel() > 0
@@ -252,8 +253,18 @@ class EntityData:
   def root_link_pose_w(self):
     return torch.cat([self.data.xpos[:, self._rb], self.data.xquat[:, self._rb]], dim=-1)
 
+  # Velocities and body-frame quantities: when the data struct carries the engine's per-body outputs
+  # (``link_vel_w`` / ``com_vel_w`` / ``link_state_b``, written by the kinematics phase of the step kernel,
+  # SURVEY.md §8f-2) the properties are plain gathers; otherwise (``native=False``, or a data struct from another
+  # engine) they are computed from ``cvel`` as the reference does (``data.py:20-31,472-516``).
+  @property
+  def _native(self) -> bool:
+    return self.native and hasattr(self.data, "link_state_b")
+
   @property
   def root_link_vel_w(self):
+    if self._native:
+      return self.data.link_vel_w[:, self._rb]
     return compute_velocity_from_cvel(self.data.xpos[:, self._rb], self.data.subtree_com[:, self._rb],
                                       self.data.cvel[:, self._rb])
 
@@ -264,6 +275,8 @@ class EntityData:
 
   @property
   def root_com_vel_w(self):
+    if self._native:
+      return self.data.com_vel_w[:, self._rb]
     return compute_velocity_from_cvel(self.data.xipos[:, self._rb], self.data.subtree_com[:, self._rb],
                                       self.data.cvel[:, self._rb])
 
@@ -276,6 +289,8 @@ class EntityData:
   @property
   def body_link_vel_w(self):
     b = self.indexing.body_ids
+    if self._native:
+      return self.data.link_vel_w[:, b]
     return compute_velocity_from_cvel(self.data.xpos[:, b], self.data.subtree_com[:, self._rb].unsqueeze(1),
                                       self.data.cvel[:, b])
 
@@ -287,6 +302,8 @@ class EntityData:
   @property
   def body_com_vel_w(self):
     b = self.indexing.body_ids
+    if self._native:
+      return self.data.com_vel_w[:, b]
     return compute_velocity_from_cvel(self.data.xipos[:, b], self.data.subtree_com[:, self._rb].unsqueeze(1),
                                       self.data.cvel[:, b])
 
@@ -374,19 +391,27 @@ class EntityData:
   # -- derived (data.py:472-516) ---------------------------------------------------------------------------
   @property
   def projected_gravity_b(self):
+    if self._native:
+      return self.data.link_state_b[:, self._rb, 6:9]
     return quat_apply_inverse(self.root_link_quat_w, self.gravity_vec_w)
 
   @property
   def heading_w(self):
+    if self._native:
+      return self.data.link_state_b[:, self._rb, 9]
     fwd = quat_apply(self.root_link_quat_w, self.forward_vec_b)
     return torch.atan2(fwd[:, 1], fwd[:, 0])
 
   @property
   def root_link_lin_vel_b(self):
+    if self._native:
+      return self.data.link_state_b[:, self._rb, 0:3]
     return quat_apply_inverse(self.root_link_quat_w, self.root_link_lin_vel_w)
 
   @property
   def root_link_ang_vel_b(self):
+    if self._native:
+      return self.data.link_state_b[:, self._rb, 3:6]
     return quat_apply_inverse(self.root_link_quat_w, self.root_link_ang_vel_w)
 
   @property

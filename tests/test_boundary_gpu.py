@@ -304,3 +304,39 @@ def test_native_mdp_kernels_match_torch_reference():
   assert n_term > 20 and n_trunc > 20  # both reset paths were exercised
   a.close()
   b.close()
+
+
+def test_engine_side_entity_quantities_match_torch_derivation(g1_model):
+  """link / com velocities, body-frame velocities, projected gravity and heading written by the
+  step kernel equal what EntityData derives from (xpos, xquat, subtree_com, cvel) with torch ops; in a decimation
+  loop only the last sub-step writes the consumer-visible kinematics, with the same final values."""
+  from mjlab_b200.entity_data import EntityData, EntityIndexing
+  from mjlab_b200.sim import Simulation, SimulationCfg
+  from util import load_sim, make_states
+
+  n = 64
+  st = make_states(g1_model, n, seed=41, vel=2.0, tilt=0.8)
+  sim = Simulation(n, SimulationCfg(), g1_model, "cuda:0")
+  load_sim(sim, st)
+  sim.forward()
+  ix = EntityIndexing.from_model(g1_model, "robot", "cuda:0")
+  a = EntityData(ix, sim.data, sim.model, "cuda:0", n, native=True)
+  b = EntityData(ix, sim.data, sim.model, "cuda:0", n, native=False)
+  assert a._native and not b._native
+  for name in ("root_link_vel_w", "root_com_vel_w", "body_link_vel_w", "body_com_vel_w", "projected_gravity_b",
+               "heading_w", "root_link_lin_vel_b", "root_link_ang_vel_b", "root_com_lin_vel_b", "root_com_ang_vel_b"):
+    x, y = getattr(a, name), getattr(b, name)
+    assert x.shape == y.shape and torch.allclose(x, y, atol=2e-5, rtol=1e-5), (name, float((x - y).abs().max()))
+  # step_n(4) == 4 x step(): state and the (last sub-step's) kinematics outputs
+  sim2 = Simulation(n, SimulationCfg(), g1_model, "cuda:0")
+  load_sim(sim, st)
+  load_sim(sim2, st)
+  sim.step_n(4)
+  for _ in range(4):
+    sim2.step()
+  torch.cuda.synchronize()
+  for f in ("qpos", "qvel", "xpos", "xquat", "xmat", "geom_xpos", "geom_xmat", "site_xpos", "cvel", "subtree_com",
+            "link_vel_w", "com_vel_w", "link_state_b"):
+    assert torch.equal(getattr(sim.data, f)[:], getattr(sim2.data, f)[:]), f
+  sim.close()
+  sim2.close()

@@ -62,8 +62,8 @@ def load_sim(sim, st):
     getattr(sim.data, k)[:] = torch.as_tensor(v, dtype=torch.float32, device=sim.device)
 
 
-def relerr(a, b, floor=1.0):
-  """Norm-wise relative error per env: max|a-b| / max(max|b|, floor)."""
+def relerr(a, b, floor=1e-9):
+  """True norm-wise relative error per env: max|a-b| / max|b| (``floor`` only guards an all-zero reference)."""
   a = np.asarray(a, dtype=np.float64).reshape(len(a), -1)
   b = np.asarray(b, dtype=np.float64).reshape(len(b), -1)
   return np.abs(a - b).max(axis=1) / np.maximum(np.abs(b).max(axis=1), floor)

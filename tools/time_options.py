@@ -36,13 +36,8 @@ def run(label, opts, k=12):
   st = sim.stats()
   print(f"{label:44s} {tot / k / 4 * 1e3:8.1f} us/sub-step   ncon {st.ncon_mean:.1f} iters {st.niter_mean:.2f}")
 
-base = dict(full_solver=0, work_queue=0, split_streams=2, phase_sync=2)
-run("psync level 2 (default), 2 streams", base)
-run("psync level 1", dict(base, phase_sync=1))
-run("psync level 3", dict(base, phase_sync=3))
-run("psync off", dict(base, phase_sync=0))
-run("psync 2, unsorted dispatch", dict(base, sorted_dispatch=0))
-sim.set_option("sorted_dispatch", 1)
-run("psync 2, 3 streams", dict(base, split_streams=3))
-run("psync 2, 4 streams", dict(base, split_streams=4))
-run("psync 2, full solver", dict(base, full_solver=1))
+base = dict(full_solver=0, work_queue=0, split_streams=2, phase_sync=2, reorder_every_substep=0)
+run("default (order once per step_n, emit last)", base)
+run("reorder every sub-step", dict(base, reorder_every_substep=1))
+run("default again", base)
+run("3 streams", dict(base, split_streams=3))
