@@ -114,6 +114,7 @@ __device__ __forceinline__ float dot6(const float* a, const float* b) {
   return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
 }
 __device__ __forceinline__ int tri(int i, int j) { return (i * (i + 1) >> 1) + j; }  // j <= i
+__device__ __forceinline__ int pad4i(int n) { return (n + 3) & ~3; }
 
 #ifndef B2_HOST_EMULATION
 // ---- TMA 1-D bulk copy + mbarrier (PTX) -------------------------------------------------------
@@ -583,7 +584,7 @@ __device__ __noinline__ void mulJ(const float* x, int dstc, int dstl, bool accum
   __syncwarp();
   #pragma unroll 1
   for (int c = lane; c < ncon; c += 32) {
-    const float* V = gV + 6 * ((int*)con)[CGRP * MC + c];
+    const float* V = gV + 6 * (((int*)con)[CINFO * MC + c] >> 24 & 0xff);
     float a3[3];
 #pragma unroll
     for (int mm = 0; mm < 3; mm++) {
@@ -695,22 +696,21 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
 #endif
 
   // ---------------- phase 0: TMA bulk load of this environment's state -------------------------
-  float* qpos = s + L.qpos; float* qvel = s + L.qvel; float* ctrl = s + L.ctrl;
-  float* qacc_ws = s + L.qacc_ws; float* qfrc_applied = s + L.qfrc_applied; float* xfrc = s + L.xfrc;
+  float* qpos = s + L.qpos; float* qvel = s + L.qvel; float* qacc_ws = s + L.qacc_ws;
+  // inputs with a single use (phase 4) are read from global memory in place
+  const float* ctrl = dd.ctrl.p + (size_t)w * dd.ctrl.stride;
+  const float* qfrc_applied = dd.qfrc_applied.p + (size_t)w * dd.qfrc_applied.stride;
+  const float* xfrc = dd.xfrc_applied.p + (size_t)w * dd.xfrc_applied.stride;
   {
     unsigned long long* bar = &bars[warp];
     fence_async_smem();  // the previous environment's generic-proxy accesses precede this one's bulk writes
     __syncwarp();
     if (lane == 0) {
-      uint32_t bytes = 4u * (dd.qpos.stride + dd.qvel.stride + dd.ctrl.stride +
-                             dd.qacc_warmstart.stride + dd.qfrc_applied.stride + dd.xfrc_applied.stride);
+      uint32_t bytes = 4u * (dd.qpos.stride + dd.qvel.stride + dd.qacc_warmstart.stride);
       mbar_expect(bar, bytes);
       bulk_g2s(qpos, dd.qpos.p + (size_t)w * dd.qpos.stride, 4u * dd.qpos.stride, bar);
       bulk_g2s(qvel, dd.qvel.p + (size_t)w * dd.qvel.stride, 4u * dd.qvel.stride, bar);
-      if (dd.ctrl.stride) bulk_g2s(ctrl, dd.ctrl.p + (size_t)w * dd.ctrl.stride, 4u * dd.ctrl.stride, bar);
       bulk_g2s(qacc_ws, dd.qacc_warmstart.p + (size_t)w * dd.qacc_warmstart.stride, 4u * dd.qacc_warmstart.stride, bar);
-      bulk_g2s(qfrc_applied, dd.qfrc_applied.p + (size_t)w * dd.qfrc_applied.stride, 4u * dd.qfrc_applied.stride, bar);
-      bulk_g2s(xfrc, dd.xfrc_applied.p + (size_t)w * dd.xfrc_applied.stride, 4u * dd.xfrc_applied.stride, bar);
     }
     __syncwarp();
     mbar_wait(bar, barphase);
@@ -723,10 +723,13 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   float* scom = s + L.scom; float* xanchor = s + L.xanchor; float* xaxis = s + L.xaxis;
   float* cinert = s + L.cinert; float* crb = s + L.crb; float* cdof = s + L.cdof;
   float* cdofdot = s + L.cdofdot; float* cvel = s + L.cvel; float* cacc = s + L.cacc;
-  float* Mq = s + L.M; float* H = s + L.H; float* invdiag = s + L.invdiag;
+  float* H = s + L.H; float* invdiag = s + L.invdiag;
+  // the joint-space inertia lives in global memory (2.5 KB per env, L2-resident): it is written once, copied
+  // into H before each factorisation and read by symv only when the solver runs on all dofs
+  float* Mq = dd.qM_packed.p + (size_t)w * dd.qM_packed.stride;
   float* qfrc_smooth = s + L.qfrc_smooth; float* qacc_smooth = s + L.qacc_smooth;
   float* qacc = s + L.qacc; float* Ma = s + L.Ma; float* grad = s + L.grad;
-  float* search = s + L.search; float* Mv = s + L.Mv; float* qfrc_c = s + L.qfrc_c;
+  float* Mv = s + L.Mv; float* qfrc_c = s + L.qfrc_c;
   float* tmpv = s + L.tmpv; float* actf = s + L.actf;
 
   // The decimation loop (manager_based_rl_env.py:109-114: ctrl held, `decimation` x sim.step) runs inside
@@ -1052,8 +1055,8 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     for (int i = lane; i < nv; i += 32) {
       float buf[6];
       mul_inert_vec(buf, crb + SI * m.dof_bodyid[i], cdof + SD * i);
-      for (int j = i; j >= 0; j = m.dof_parentid[j]) Mq[tri(i, j)] = dot6(cdof + SD * j, buf);
-      Mq[tri(i, i)] += arm[i];
+      Mq[tri(i, i)] = dot6(cdof + SD * i, buf) + arm[i];
+      for (int j = m.dof_parentid[i]; j >= 0; j = m.dof_parentid[j]) Mq[tri(i, j)] = dot6(cdof + SD * j, buf);
     }
   }
   __syncwarp();
@@ -1567,7 +1570,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
           float vel = Jd * qvel[dof];
           ((int*)lim)[LINFO * NLC + r] = dof | ((side > 0 ? 1 : 0) << 16);
           lim[LD * NLC + r] = 1.f / R;
-          lim[LAREF * NLC + r] = -B * vel - K * imp * (dist - jmar[j]);
+          lim[LJAR * NLC + r] = B * vel + K * imp * (dist - jmar[j]);  // -aref (J a is added by the solver)
         }
       }
       nlim += __popc(bal);
@@ -1589,7 +1592,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     int before = ngroup + __popc(bal & ((1u << lane) - 1u));
     if (c < ncon) {
       int g = start ? before : before - 1;
-      ((int*)con)[CGRP * MC + c] = g;
+      ((int*)con)[CINFO * MC + c] = (((int*)con)[CINFO * MC + c] & 0xffffff) | (g << 24);
       if (start) gstart[g] = c;
     }
     ngroup += __popc(bal);
@@ -1648,8 +1651,6 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
 #pragma unroll
       for (int r = 0; r < 4; r++) con[(CJAR0 + r) * MC + c] = r < nr ? B * con[(CJV0 + r) * MC + c] + ki : 0.f;
     }
-    #pragma unroll 1
-    for (int r = lane; r < nlim; r += 32) lim[LJAR * NLC + r] = -lim[LAREF * NLC + r];
     __syncwarp();
   }
 
@@ -1657,7 +1658,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   PSYNC();
   // ---------------- phase 7: unconstrained acceleration -------------------------------------------
   #pragma unroll 1
-  for (int i = lane; i < (m.ntri + 3) >> 2; i += 32) ((float4*)H)[i] = ((const float4*)Mq)[i];  // both regions are 16 B aligned and padded
+  for (int i = lane; i < (m.ntri + 3) >> 2; i += 32) ((float4*)H)[i] = ((const float4*)Mq)[i];  // both rows are 16 B aligned and padded
   __syncwarp();
   float* Mred = s + L.Mred;
   ldl_factor(H, invdiag, nv, SCHED, true, lane, 0, (reduced && nefc > 0) ? n : 0, Mred);
@@ -1677,6 +1678,13 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   float* gA = s + L.gA; float* gu = s + L.gu; int* glist = (int*)(s + L.glist); float* gW = s + L.gW;
   float oldcost = 0.f;
   bool first = true;
+  // Conjugate gradient variant (opt.solver = CG; mujoco_warp's second solver): same cost, same update pass and
+  // line search, search direction -M^-1 grad + beta * previous (Polak-Ribiere, preconditioned by M whose factor
+  // phase 7 left in H - on a reduced problem its leading block is the factor of the Schur complement).  The
+  // Hessian scratch is unused, so its weight region holds the direction and the previous (grad, M^-1 grad).
+  const bool cg = m.solver == SOL_CG_;
+  float* search = cg ? gW : s + L.search;  // Newton: search = -grad in place
+  float* cgM = gW + pad4i(nv); float* cgG0 = gW + 2 * pad4i(nv); float* cgM0 = gW + 3 * pad4i(nv);
   bool refine = false;  // active set unchanged: the Hessian factor of the previous iteration is still valid
   int stall = 0;
   bool run = nefc > 0;  // this warp still iterates (under phase_sync finished warps keep voting at the loop top)
@@ -1747,7 +1755,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
           if (on) { cst += 0.5f * D * v * v; act |= 1 << r; }
         }
         changed |= act != (info >> 20 & 0xf);
-        ((int*)con)[CINFO * MC + c] = (info & 0xfffff) | (act << 20);
+        ((int*)con)[CINFO * MC + c] = (info & (int)0xff0fffff) | (act << 20);
         float F0, F1, F2;
         if (dim == 1) { F0 = f[0]; F1 = 0.f; F2 = 0.f; }
         else { F0 = f[0] + f[1] + f[2] + f[3]; F1 = mu * (f[0] - f[1]); F2 = mu * (f[2] - f[3]); }
@@ -1755,11 +1763,13 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         // weights of this contact's 3x3 block W = B^T D_active B for the Hessian assembly
         float w0 = (act & 1) ? D : 0.f, w1 = (act & 2) ? D : 0.f, w2 = (act & 4) ? D : 0.f, w3 = (act & 8) ? D : 0.f;
         bool pyr = dim > 1;  // frictionless (condim 1) contacts contribute the normal row only
-        gW[0 * MC + c] = pyr ? w0 + w1 + w2 + w3 : w0;
-        gW[1 * MC + c] = pyr ? mu * (w0 - w1) : 0.f;
-        gW[2 * MC + c] = pyr ? mu * (w2 - w3) : 0.f;
-        gW[3 * MC + c] = pyr ? mu * mu * (w0 + w1) : 0.f;
-        gW[4 * MC + c] = pyr ? mu * mu * (w2 + w3) : 0.f;
+        if (!cg) {
+          gW[0 * MC + c] = pyr ? w0 + w1 + w2 + w3 : w0;
+          gW[1 * MC + c] = pyr ? mu * (w0 - w1) : 0.f;
+          gW[2 * MC + c] = pyr ? mu * (w2 - w3) : 0.f;
+          gW[3 * MC + c] = pyr ? mu * mu * (w0 + w1) : 0.f;
+          gW[4 * MC + c] = pyr ? mu * mu * (w2 + w3) : 0.f;
+        }
       }
       #pragma unroll 1
       for (int i = lane; i < n; i += 32) qfrc_c[i] = 0.f;
@@ -1834,17 +1844,17 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         // new point is the minimiser of the true (convex) cost - up to the error of the fp32 solve, hence the
         // same gradient condition.  When the set is unchanged but the residual is not yet small, the next
         // iteration is one step of iterative refinement: same Hessian, its factor is reused.
-        if (small && (improvement < m.tolerance || !changed)) { run = false; break; }
+        if (small && (improvement < m.tolerance || (!changed && !cg))) { run = false; break; }
         stall = improvement <= 0.f ? stall + 1 : 0;
         if (stall >= 2) { run = false; break; }  // two moves without any measurable decrease: fp32 floor reached
-        refine = !changed;
+        refine = !changed && !cg;
       }
       if (niter >= m.iterations) { run = false; break; }
       first = false;
     } while (0);
     PHASE_MARK(12);
     PSYNC_L(2);
-    if (run && !refine) {
+    if (run && !refine && !cg) {
       // ---- Hessian H = M + J^T D_active J via per-body-pair 6x6 blocks -------------------------
       {  // leading block only: the rows of the eliminated dofs keep the factor of M (needed after the loop)
         const int nt = n * (n + 1) >> 1;
@@ -1917,12 +1927,29 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     }
     PHASE_MARK(13);
     PSYNC_L(2);
-    if (run) {
+    if (run && !cg) {
       if (!refine) ldl_factor(H, invdiag, n, SCHED, treeok, lane, (nv - n) >> 2);
       #pragma unroll 1
-      for (int i = lane; i < n; i += 32) search[i] = -grad[i];
+      for (int i = lane; i < n; i += 32) search[i] = -grad[i];  // (grad and search share one vector)
       __syncwarp();
       ldl_solve(H, invdiag, search, n, lane);
+    }
+    if (run && cg) {
+      #pragma unroll 1
+      for (int i = lane; i < n; i += 32) cgM[i] = grad[i];
+      __syncwarp();
+      ldl_solve(H, invdiag, cgM, n, lane);  // M^-1 grad (factor of M, phase 7)
+      float num = 0.f, den = 0.f;
+      #pragma unroll 1
+      for (int i = lane; i < n; i += 32) { num += grad[i] * (cgM[i] - cgM0[i]); den += cgG0[i] * cgM0[i]; }
+      num = wsum(num); den = wsum(den);
+      const float beta = niter == 0 ? 0.f : fmaxf(0.f, num / fmaxf(den, MINVAL));
+      #pragma unroll 1
+      for (int i = lane; i < n; i += 32) {
+        search[i] = -cgM[i] + (niter == 0 ? 0.f : beta * search[i]);
+        cgG0[i] = grad[i]; cgM0[i] = cgM[i];
+      }
+      __syncwarp();
     }
     PHASE_MARK(14);
     PSYNC_L(2);
@@ -2149,7 +2176,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     const float* damp = MP(dof_damping); const float* bp = MP(actuator_biasprm);
     const float* fr = MP(actuator_forcerange); const float* gear = MP(actuator_gear);
     #pragma unroll 1
-    for (int i = lane; i < (m.ntri + 3) >> 2; i += 32) ((float4*)H)[i] = ((const float4*)Mq)[i];  // both regions are 16 B aligned and padded
+    for (int i = lane; i < (m.ntri + 3) >> 2; i += 32) ((float4*)H)[i] = ((const float4*)Mq)[i];  // both rows are 16 B aligned and padded
     __syncwarp();
     #pragma unroll 1
     for (int i = lane; i < nv; i += 32) H[tri(i, i)] += h * damp[i];
@@ -2241,15 +2268,9 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     }
   }
   if (lastsub) break;
-  // next sub-step: qpos/qvel/ctrl/qfrc_applied are still in shared memory; warm start from this
-  // sub-step's solution; the applied-wrench rows were overlaid by solver scratch, reload them
+  // next sub-step: qpos/qvel/ctrl/qfrc_applied are still in shared memory; warm start from this sub-step's solution
   #pragma unroll 1
   for (int i = lane; i < nv; i += 32) qacc_ws[i] = qacc[i];
-  {
-    const float* gx = dd.xfrc_applied.p + (size_t)w * dd.xfrc_applied.stride;
-    #pragma unroll 1
-    for (int i = lane; i < 6 * nb; i += 32) xfrc[i] = gx[i];
-  }
   __syncwarp();
   }  // sub-step loop
   }  // worker loop

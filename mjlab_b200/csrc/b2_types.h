@@ -6,7 +6,9 @@
 #define B2_WARPS_PER_CTA 4
 #endif
 #ifndef B2_MIN_CTAS
-#define B2_MIN_CTAS (12 / B2_WARPS_PER_CTA)  // 12 warps per SM
+// 16 warps per SM: the kernel fits 128 registers without spills (ptxas only takes more when allowed to), and the
+// per-environment shared-memory block of the G1 scene (13.1 KB at 35 contacts) lets four 4-warp CTAs share an SM
+#define B2_MIN_CTAS (16 / B2_WARPS_PER_CTA)
 #endif
 #define B2_MAX_FIELDS 96
 
@@ -15,6 +17,7 @@ enum { JNT_FREE = 0, JNT_BALL = 1, JNT_SLIDE = 2, JNT_HINGE = 3 };
 enum { G_PLANE = 0, G_SPHERE = 2, G_CAPSULE = 3, G_BOX = 6, G_MESH = 7 };
 enum { OBJ_BODY = 1, OBJ_XBODY = 2, OBJ_GEOM = 5 };
 enum { INT_EULER = 0, INT_IMPLICITFAST = 3 };
+enum { SOL_PGS_ = 0, SOL_CG_ = 1, SOL_NEWTON_ = 2 };
 
 // A float model array; `stride` is the per-world stride in floats (0 = shared by all worlds).
 struct FArr {
@@ -38,24 +41,25 @@ struct IArr {
 // Per-contact SoA fields inside the per-env shared-memory block (index f*maxcon + c).
 enum {
   CS0 = 0,        // 18 floats: S_m[a] at CS0 + m*6 + a; S_m = [r x e_m ; e_m], e_0 = normal
-  CDIST = 18, CMU, CD, CKI, CB, CINFO, CGRP,
+  CDIST = 18, CMU, CD, CKI, CB,
+  CINFO,  // int: body1 | body2 << 8 | condim << 16 | active rows << 20 | body-pair group << 24
   CJAR0, CJAR1, CJAR2, CJAR3,
   CJV0, CJV1, CJV2, CJV3,
-  C_NFIELD  // 33
+  C_NFIELD  // 32
 };
 // Per-limit-row SoA fields (index f*nlimcap + r).
-enum { LINFO = 0, LD, LAREF, LJAR, LJV, L_NFIELD };
+enum { LINFO = 0, LD, LJAR, LJV, L_NFIELD };
 
 // Offsets (in floats) of every region of one environment's shared-memory block.
 struct Layout {
   int total;  // floats per env (multiple of 4)
   // bulk-loaded inputs (16 B aligned)
-  int qpos, qvel, ctrl, qacc_ws, qfrc_applied, xfrc;
+  int qpos, qvel, qacc_ws;  // (ctrl, qfrc_applied and xfrc_applied have one use each and are read from global memory)
   // kinematics
   int xpos, xquat, xipos, scom, xanchor, xaxis;
   // smooth dynamics
   int cinert, crb, cdof, cdofdot, cvel, cacc;
-  int M, H, invdiag;
+  int H, invdiag;  // (the joint-space inertia M itself lives in global memory: Data field qM_packed)
   int qfrc_smooth, qacc_smooth, qacc, Ma, grad, search, Mv, qfrc_c, tmpv, actf;
   // collision / constraints (overlaid on smooth-only regions)
   int gpose, pairlist, contacts, limits, gstart, gV, glist, gA, gu, gW;
@@ -69,7 +73,7 @@ struct DevModel {
   int nq, nv, nu, nbody, njnt, ngeom, nsite, nsensor, nsensordata, npair, ncg, maxdepth;
   int ntri;  // nv*(nv+1)/2
   int maxcon, njmax;
-  int integrator, iterations, ls_iterations, debug;
+  int integrator, iterations, ls_iterations, debug, solver;
   float timestep, tolerance, ls_tolerance, impratio, meaninertia;
   float gravity[3];
   // integer tables
@@ -119,6 +123,7 @@ struct DevData {
   DArr qpos, qvel, ctrl, qacc_warmstart, qfrc_applied, xfrc_applied, act;
   DArr qacc, xpos, xquat, xmat, xipos, subtree_com, cvel, geom_xpos, geom_xmat, site_xpos,
       site_xmat, sensordata, actuator_force, time;
+  DArr qM_packed;  // joint-space inertia, packed lower triangle (engine scratch between phases; L2-resident)
   DArr link_vel_w, com_vel_w, link_state_b;  // per body: EntityData's derived velocities / body-frame state
   DArr qfrc_bias, qfrc_smooth, qacc_smooth, qfrc_constraint, qM;
   DArr contact_dist, contact_pos, contact_frame, contact_force, solver_cost;

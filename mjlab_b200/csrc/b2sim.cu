@@ -406,7 +406,11 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
   m.meaninertia = (float)getf("stat_meaninertia");
   for (int k = 0; k < 3; k++) m.gravity[k] = (float)desc->gravity[k];
   if (geti("opt_cone") != 0) { delete s; return fail("b2_create: only pyramidal cones are supported"); }
-  if (geti("opt_solver") != 2) { delete s; return fail("b2_create: only the Newton solver is implemented"); }
+  m.solver = geti("opt_solver");
+  if (m.solver != SOL_NEWTON_ && m.solver != SOL_CG_) {
+    delete s;
+    return fail("b2_create: solver must be Newton or CG (PGS works on the dual problem and is not implemented)");
+  }
   m.maxcon = ncon_per_world > 0 ? std::min(ncon_per_world, 255) : 48;
   m.njmax = njmax > 0 ? njmax : 300;
 
@@ -657,6 +661,7 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
   rc |= add_data(s, "qacc_smooth", &d.qacc_smooth, nv);
   rc |= add_data(s, "qfrc_constraint", &d.qfrc_constraint, nv);
   rc |= add_data(s, "qM", &d.qM, nv * nv, nv);
+  rc |= add_data(s, "qM_packed", &d.qM_packed, m.ntri);
   rc |= add_data(s, "contact_dist", &d.contact_dist, mc); rc |= add_data(s, "contact_pos", &d.contact_pos, 3 * mc, 3);
   rc |= add_data(s, "contact_frame", &d.contact_frame, 9 * mc, 9);
   rc |= add_data(s, "contact_force", &d.contact_force, 3 * mc, 3);
@@ -678,39 +683,42 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
   L.maxcon = mc;
   L.nlimcap = pad4(std::max(m.njnt, 1));
   L.maxpair = m.nstatic > 0 ? 256 : 128;
-  L.qpos = alloc(d.qpos.stride); L.qvel = alloc(d.qvel.stride); L.ctrl = alloc(d.ctrl.stride);
-  L.qacc_ws = alloc(d.qacc_warmstart.stride); L.qfrc_applied = alloc(d.qfrc_applied.stride);
-  L.cdof = alloc(7 * nv); L.M = alloc(m.ntri);
+  L.qpos = alloc(d.qpos.stride); L.qvel = alloc(d.qvel.stride); L.qacc_ws = alloc(d.qacc_warmstart.stride);
+  L.cdof = alloc(7 * nv);
   int hsize = std::max(m.ntri, pad4(GP * m.ncg) + L.maxpair);
   L.H = alloc(hsize); L.gpose = L.H; L.pairlist = L.H + pad4(GP * m.ncg);
   L.invdiag = alloc(nv);
   L.qfrc_smooth = alloc(nv); L.qacc_smooth = alloc(nv); L.qacc = alloc(nv); L.Ma = alloc(nv);
-  L.grad = alloc(nv); L.search = alloc(nv); L.Mv = alloc(nv); L.qfrc_c = alloc(nv); L.tmpv = alloc(nv);
+  L.grad = alloc(nv); L.search = L.grad;  // search = -grad is formed in place
+  L.Mv = alloc(nv); L.qfrc_c = alloc(nv); L.tmpv = alloc(nv);
   L.actf = alloc(nu);
   int ubase = off;
   // union A: regions that are dead once the smooth dynamics (phases 1-4) are done
-  L.xfrc = alloc(d.xfrc_applied.stride);
   L.xpos = alloc(3 * nb); L.xquat = alloc(4 * nb); L.xipos = alloc(3 * nb); L.scom = alloc(3 * nb);
-  L.xanchor = alloc(3 * m.njnt); L.xaxis = alloc(3 * m.njnt);
-  L.cinert = alloc(11 * nb); L.crb = alloc(11 * nb); L.cdofdot = alloc(7 * nv); L.cvel = alloc(7 * nb);
+  L.cinert = alloc(11 * nb); L.crb = alloc(11 * nb);
+  // joint anchors / axes are dead once the motion vectors exist (phase 2); cdofdot is first written in phase 4
+  L.cdofdot = alloc(std::max(7 * nv, 2 * pad4(3 * m.njnt))); L.xanchor = L.cdofdot; L.xaxis = L.cdofdot + pad4(3 * m.njnt);
+  L.cvel = alloc(7 * nb);
   L.cacc = alloc(7 * nb);
   int endA = off;
   off = ubase;
   // union B: constraint / solver regions
   L.contacts = alloc(C_NFIELD * mc); L.limits = alloc(L_NFIELD * L.nlimcap); L.gstart = alloc(mc + 1);
-  L.gV = alloc(6 * mc); L.glist = alloc(64); L.gA = alloc(36); L.gu = alloc(6 * nv);
-  L.gW = alloc(5 * mc); L.sens = off;
+  // gV (group velocities / wrenches: J x, J^T f) and gu (Hessian projection) are never live together
+  L.gV = alloc(std::max(6 * mc, 6 * nv)); L.gu = L.gV; L.glist = alloc(nv + 1); L.gA = alloc(36);
+  L.gW = alloc(std::max(5 * mc, 4 * pad4(nv))); L.sens = off;  // (the CG variant keeps its four vectors here)
   // reduced Newton problem: room for the Schur complement on the largest leading block nv - 4k (k >= 1) whose
-  // packed size fits 300 floats (G1: 23 x 23 covers legs + waist; arm contacts fall back to the full problem)
+  // packed size fits 200 floats (G1: 19 x 19 = both legs + the first waist dof, 82 % of the bench workload's
+  // environments; torso / arm contacts fall back to the full problem)
   L.ndcap = 0;
   for (int k = 1; nv - 4 * k >= 6; k++) {
     int cand = nv - 4 * k;
-    if (cand * (cand + 1) / 2 <= 300) { L.ndcap = cand; break; }
+    if (cand * (cand + 1) / 2 <= 200) { L.ndcap = cand; break; }
   }
   L.Mred = alloc(L.ndcap * (L.ndcap + 1) / 2);
   int endB = off;
   L.total = pad4(std::max(endA, endB));
-  if (L.ndcap == 0) L.Mred = L.M;  // never used
+  if (L.ndcap == 0) L.Mred = L.H;  // never used
   s->smem_bytes = sizeof(float) * ((size_t)L.total * B2_WARPS_PER_CTA + pad4(m.ldl_nsparse + 18));
   if (s->smem_bytes > 227 * 1024) {
     b2_destroy(s);
@@ -852,6 +860,10 @@ int b2_set_option(b2_sim* s, const char* key, double v) {
   else if (k == "ls_tolerance") m.ls_tolerance = (float)v;
   else if (k == "timestep") m.timestep = (float)v;
   else if (k == "integrator") m.integrator = (int)v;
+  else if (k == "solver") {
+    if ((int)v != SOL_NEWTON_ && (int)v != SOL_CG_) return fail("b2_set_option: solver must be 1 (CG) or 2 (Newton)");
+    m.solver = (int)v;
+  }
   else if (k == "debug_outputs") m.debug = (m.debug & ~1) | ((int)v & 1);
   else if (k == "dense_factor") m.debug = (m.debug & ~2) | ((int)v ? 2 : 0);  // force the dense LDL schedule (tests)
   else if (k == "ls_parallel") { /* accepted for API parity; the line search here is exact */ }
@@ -875,6 +887,7 @@ int b2_get_option(b2_sim* s, const char* key, double* v) {
   else if (k == "ls_tolerance") *v = m.ls_tolerance;
   else if (k == "timestep") *v = m.timestep;
   else if (k == "integrator") *v = m.integrator;
+  else if (k == "solver") *v = m.solver;
   else if (k == "debug_outputs") *v = m.debug & 1;
   else if (k == "dense_factor") *v = (m.debug >> 1) & 1;
   else if (k == "smem_bytes_per_env") *v = 4.0 * m.lay.total;

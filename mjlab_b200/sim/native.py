@@ -11,7 +11,7 @@ from mjlab_b200.compiler.compile import MODEL_ARRAYS, MODEL_SCALARS_F, MODEL_SCA
 
 import os
 
-LIB_PATH = Path(os.environ.get("B2SIM_LIB", Path(__file__).resolve().parents[1] / "csrc" / "libb2sim.so"))
+LIB_PATH = Path(os.environ.get("B2SIM_LIB") or Path(__file__).resolve().parents[1] / "csrc" / "libb2sim.so")
 
 
 class B2Array(ctypes.Structure):

@@ -74,7 +74,7 @@ int emul_box_box(const float* b1, const float* h1, const float* b2_, const float
 // J x for contact rows (4 pyramid rows per contact, written to CJV0..3) and limit rows (LJV): device mulJ on
 // caller-built SoA blocks.  layout[] returns the enum values the caller needs to fill them.
 void emul_layout(int* out) {
-  int v[] = {CS0, CMU, CINFO, CGRP, CJV0, C_NFIELD, LINFO, LJV, L_NFIELD, SD};
+  int v[] = {CS0, CMU, CINFO, CJV0, C_NFIELD, LINFO, LJV, L_NFIELD, SD};
   memcpy(out, v, sizeof(v));
 }
 void emul_mulJ(const float* x, float* con, float* lim, const int* gstart, const float* cdof,

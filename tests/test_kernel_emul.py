@@ -387,7 +387,7 @@ def test_emulated_reduced_solver_and_work_queue(lib):
   m = load_compiled("g1_flat")
   n = 5  # more environments than the emulated device holds CTAs (2): the queue hands out several per warp
   sim = EmulSim(lib, m, n)
-  assert sim.option("reduced_block_cap") == 23 and sim.option("resident_ctas") == 2
+  assert sim.option("reduced_block_cap") == 19 and sim.option("resident_ctas") == 2
   o = Oracle(m, nworld=n, maxcon=int(sim.option("maxcon")))
   st = make_states(m, n, seed=5)
   load_oracle(o, st)
@@ -412,4 +412,30 @@ def test_emulated_reduced_solver_and_work_queue(lib):
   sim.step(1)
   for f in ("qpos", "qvel", "qacc_warmstart"):
     assert relerr(sim.field(f), o.field(f)).max() < 1e-4, f
+  sim.close()
+
+
+def test_emulated_cg_solver_reaches_the_newton_minimiser(lib):
+  """opt.solver = CG (mujoco_warp's second solver, `MujocoCfg.solver="cg"`): Polak-Ribiere directions
+  preconditioned by the factor of M, same cost / update pass / exact line search - same minimiser as the fp64
+  Newton oracle once it is given enough iterations (CG needs tens where Newton needs a handful)."""
+  from mjlab_b200.asset_zoo import load_compiled
+
+  m = load_compiled("go1_flat")
+  n = 3
+  sim = EmulSim(lib, m, n)
+  o = Oracle(m, nworld=n, maxcon=int(sim.option("maxcon")))
+  o.set_option("iterations", 50)
+  st = make_states(m, n, seed=5)
+  load_oracle(o, st)
+  o.forward()
+  lib.b2_set_option(sim.h, b"solver", 1.0)
+  lib.b2_set_option(sim.h, b"iterations", 200.0)
+  assert sim.option("solver") == 1
+  sim.load(st)
+  sim.forward()
+  assert relerr(sim.field("qacc"), o.qacc).max() < 2e-3 and relerr(sim.field("qfrc_constraint"), o.qfrc_constraint).max() < 2e-3
+  it = sim.field("solver_niter").ravel()
+  assert it.max() > 10 and it.max() < 200  # converged by its own criterion, not by the cap
+  assert lib.b2_set_option(sim.h, b"solver", 0.0) != 0  # PGS is refused
   sim.close()

@@ -466,3 +466,30 @@ def test_tree_and_dense_factor_schedules_agree(g1_model):
   assert relerr(T(a.data.qvel), T(b.data.qvel)).max() < 3e-3
   a.close()
   b.close()
+
+
+def test_cg_solver_option(g1_model):
+  """`MujocoCfg(solver="cg")` is accepted (reference `sim/sim.py:56`): the CG variant converges to the same
+  minimiser as Newton; PGS is refused at construction."""
+  from mjlab_b200.sim import Simulation, SimulationCfg
+
+  n = 128
+  sim, o, st = _pair(g1_model, n, seed=17)
+  o.set_option("iterations", 50)
+  o.forward()
+  sim.set_option("solver", 1)
+  sim.set_option("iterations", 300)
+  sim.forward()
+  torch.cuda.synchronize()
+  e = relerr(T(sim.data.qacc), o.qacc)
+  assert np.percentile(e, 90) < 1e-3 and e.max() < 2e-2, (np.percentile(e, 90), e.max())
+  it = T(sim.data.solver_niter).ravel()
+  assert it.max() > 10
+  sim.close()
+  import copy
+
+  bad = copy.deepcopy(g1_model)
+  bad.arrays = dict(bad.arrays)
+  bad.arrays["opt_solver"] = np.array([0], dtype=np.int32)
+  with pytest.raises(RuntimeError, match="PGS"):
+    Simulation(2, SimulationCfg(), bad, "cuda:0")

@@ -244,9 +244,9 @@ def test_box_primitives_device_code_matches_oracle(lib):
 def test_matrix_free_jacobian_product(lib):
   """mulJ (J x without ever forming J: per body-pair group a relative spatial velocity from the chain dofs,
   then S_m . V per contact direction, pyramid rows a0 +- mu a_t) against an explicit Jacobian built in numpy."""
-  lay = np.zeros(10, dtype=np.int32)
+  lay = np.zeros(9, dtype=np.int32)
   lib.emul_layout(ptr(lay, ctypes.c_int))
-  CS0, CMU, CINFO, CGRP, CJV0, CN, LINFO, LJV, LN, SD = lay.tolist()
+  CS0, CMU, CINFO, CJV0, CN, LINFO, LJV, LN, SD = lay.tolist()
   rng = np.random.default_rng(8)
   nv, nbody, MC, NLC = 35, 12, 24, 8
   # bodies 1..11 with random chain dof sets (nested along a random tree)
@@ -273,8 +273,7 @@ def test_matrix_free_jacobian_product(lib):
       dim = [3, 3, 1, 0][int(rng.integers(0, 4))]
       con[CS0 : CS0 + 18, c] = rng.normal(size=18)
       con[CMU, c] = rng.uniform(0.3, 1.2)
-      coni[CINFO, c] = b1 | (b2 << 8) | (dim << 16)
-      coni[CGRP, c] = g
+      coni[CINFO, c] = b1 | (b2 << 8) | (dim << 16) | (g << 24)  # body pair, condim, body-pair group
       dims.append(dim)
       c += 1
   ncon = c

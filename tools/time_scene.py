@@ -22,10 +22,11 @@ def main():
   ap.add_argument("scenes", nargs="+")
   ap.add_argument("--n", type=int, default=4096)
   ap.add_argument("--iters", type=int, default=50)
+  ap.add_argument("--ncon", type=int, default=0, help="contact capacity per world (0: engine default)")
   a = ap.parse_args()
   for name in a.scenes:
     m = load_compiled(name)
-    sim = Simulation(a.n, SimulationCfg(), m, "cuda:0")
+    sim = Simulation(a.n, SimulationCfg(nconmax=a.ncon * a.n if a.ncon else None), m, "cuda:0")
     key = m.keys["robot/init_state"]
     qpos = np.tile(key["qpos"], (a.n, 1))
     if "terrain_origins" in m.arrays:
@@ -51,7 +52,7 @@ def main():
     ni = sim.data.solver_niter[:].float().mean().item()
     ov = int(sim.data.overflow[:].sum().item())
     print(f"{name}: n={a.n} {us:.1f} us/sub-step  {a.n / us:.2f} M env-substeps/s  ncon={nc:.1f} niter={ni:.2f} overflow={ov} "
-          f"smem/env={int(sim.get_option('smem_bytes_per_env'))}")
+          f"smem/env={int(sim.get_option('smem_bytes_per_env'))} resident_ctas={int(sim.get_option('resident_ctas'))}")
     sim.close()
 
 
