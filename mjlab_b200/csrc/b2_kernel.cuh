@@ -508,42 +508,113 @@ __device__ __noinline__ int capsule_box(RawCon* c, float margin, const float* cp
   }
   return n;
 }
-__device__ __noinline__ int box_box(RawCon* c, const float* x1, const float* h1, const float* x2, const float* h2) {
-  int n = 0;
-  #pragma unroll 1
-  for (int pass = 0; pass < 2 && n < 8; pass++) {
-    const float* xa = pass ? x2 : x1; const float* ha = pass ? h2 : h1;  // vertices of this box
-    const float* xb = pass ? x1 : x2; const float* hb = pass ? h1 : h2;  // tested against this box
-    #pragma unroll 1
-    for (int i = 0; i < 8 && n < 8; i++) {
-      float v[3] = {(i & 1) ? ha[0] : -ha[0], (i & 2) ? ha[1] : -ha[1], (i & 4) ? ha[2] : -ha[2]}, w[3], l[3];
-      bool in = true;
+// box - box: separating-axis test (15 axes), then either the incident face clipped against the reference face
+// (<= 8 contacts) or one edge-edge contact; the same statement as oracle/b2_oracle.c: box_box (see there).
+__device__ __noinline__ int box_box(RawCon* c, float margin, const float* x1, const float* h1, const float* x2,
+                                    const float* h2) {
+  const float *p1 = x1, *m1 = x1 + 3, *p2 = x2, *m2 = x2 + 3;
+  float A[3][3], B[3][3], R[3][3], Q[3][3], t[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]}, tA[3], tB[3];
 #pragma unroll
-      for (int k = 0; k < 3; k++) w[k] = xa[k] + xa[3 + 3 * k] * v[0] + xa[4 + 3 * k] * v[1] + xa[5 + 3 * k] * v[2];
-      float d[3] = {w[0] - xb[0], w[1] - xb[1], w[2] - xb[2]};
+  for (int i = 0; i < 3; i++)
 #pragma unroll
-      for (int k = 0; k < 3; k++) {
-        l[k] = xb[3 + k] * d[0] + xb[6 + k] * d[1] + xb[9 + k] * d[2];
-        if (fabsf(l[k]) > hb[k]) in = false;
-      }
-      if (!in) continue;
-      int best = 0; float depth = hb[0] - fabsf(l[0]);
+    for (int k = 0; k < 3; k++) { A[i][k] = m1[3 * k + i]; B[i][k] = m2[3 * k + i]; }  // axes = columns
 #pragma unroll
-      for (int k = 1; k < 3; k++) { float t = hb[k] - fabsf(l[k]); if (t < depth) { depth = t; best = k; } }
-      float sg = (best == 0 ? l[0] : (best == 1 ? l[1] : l[2])) >= 0.f ? 1.f : -1.f;
-      float sgn = pass ? 1.f : -1.f;
-      c[n].dist = -depth;
+  for (int i = 0; i < 3; i++) {
+    tA[i] = dot3(t, A[i]); tB[i] = dot3(t, B[i]);
 #pragma unroll
-      for (int k = 0; k < 3; k++) {
-        float nw = sg * xb[3 + 3 * k + best];
-        c[n].n[k] = sgn * nw;
-        c[n].pos[k] = w[k] + nw * (0.5f * depth);
-        c[n].yh[k] = 0.f;
-      }
-      n++;
-    }
+    for (int j = 0; j < 3; j++) { R[i][j] = dot3(A[i], B[j]); Q[i][j] = fabsf(R[i][j]) + 1e-6f; }
   }
-  return n;
+  int best = -1; float bdepth = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {  // face axes of box 1
+    float depth = h1[i] + h2[0] * Q[i][0] + h2[1] * Q[i][1] + h2[2] * Q[i][2] - fabsf(tA[i]);
+    if (depth < -margin) return 0;
+    if (best < 0 || depth < bdepth - 1e-5f * (1.f + fabsf(bdepth))) { best = i; bdepth = depth; }
+  }
+#pragma unroll
+  for (int j = 0; j < 3; j++) {  // face axes of box 2
+    float depth = h2[j] + h1[0] * Q[0][j] + h1[1] * Q[1][j] + h1[2] * Q[2][j] - fabsf(tB[j]);
+    if (depth < -margin) return 0;
+    if (depth < bdepth - 1e-5f * (1.f + fabsf(bdepth))) { best = 3 + j; bdepth = depth; }
+  }
+  #pragma unroll 1
+  for (int e = 0; e < 9; e++) {  // edge axes a_i x b_j
+    const int i = e / 3, j = e - 3 * i;
+    float l2 = 1.f - R[i][j] * R[i][j];
+    if (l2 < 1e-6f) continue;  // (nearly) parallel edges: covered by the face axes
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+    float il = 1.f / sqrtf(l2);
+    float depth = (h1[i1] * Q[i2][j] + h1[i2] * Q[i1][j] + h2[j1] * Q[i][j2] + h2[j2] * Q[i][j1] -
+                   fabsf(tA[i2] * R[i1][j] - tA[i1] * R[i2][j])) * il;
+    if (depth < -margin) return 0;
+    if (depth + 0.05f * fabsf(depth) + 1e-6f < bdepth) { best = 6 + e; bdepth = depth; }
+  }
+  if (best >= 6) {
+    const int i = (best - 6) / 3, j = (best - 6) % 3;
+    float L[3];
+    cross3(L, A[i], B[j]);
+    normalize3(L);
+    if (dot3(L, t) < 0.f) { L[0] = -L[0]; L[1] = -L[1]; L[2] = -L[2]; }
+    float pa[3] = {p1[0], p1[1], p1[2]}, pb[3] = {p2[0], p2[1], p2[2]};
+    for (int k = 0; k < 3; k++) {
+      if (k != i) { float sg = dot3(A[k], L) >= 0.f ? h1[k] : -h1[k]; for (int x = 0; x < 3; x++) pa[x] += sg * A[k][x]; }
+      if (k != j) { float sg = dot3(B[k], L) >= 0.f ? -h2[k] : h2[k]; for (int x = 0; x < 3; x++) pb[x] += sg * B[k][x]; }
+    }
+    float d[3] = {pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]}, r = R[i][j], da = dot3(d, A[i]), db = dot3(d, B[j]);
+    float den = 1.f - r * r;
+    float sA = (da - r * db) / den, sB = (r * da - db) / den;
+    sA = fminf(fmaxf(sA, -h1[i]), h1[i]);
+    sB = fminf(fmaxf(sB, -h2[j]), h2[j]);
+    c[0].dist = -bdepth;
+    for (int x = 0; x < 3; x++) {
+      c[0].pos[x] = 0.5f * (pa[x] + sA * A[i][x] + pb[x] + sB * B[j][x]);
+      c[0].n[x] = L[x]; c[0].yh[x] = 0.f;
+    }
+    return 1;
+  }
+  const int ref = best >= 3, ax = ref ? best - 3 : best;
+  float (*Ar)[3] = ref ? B : A; float (*Ai)[3] = ref ? A : B;
+  const float *pr = ref ? p2 : p1, *pi = ref ? p1 : p2, *hr = ref ? h2 : h1, *hi = ref ? h1 : h2;
+  float sgn = (ref ? -tB[ax] : tA[ax]) >= 0.f ? 1.f : -1.f;
+  float n[3] = {sgn * Ar[ax][0], sgn * Ar[ax][1], sgn * Ar[ax][2]};
+  int inc = 0; float bd = fabsf(dot3(n, Ai[0]));
+  for (int k = 1; k < 3; k++) { float v = fabsf(dot3(n, Ai[k])); if (v > bd + 1e-6f) { bd = v; inc = k; } }
+  float si = dot3(n, Ai[inc]) > 0.f ? -1.f : 1.f;
+  const int k1 = (inc + 1) % 3, k2 = (inc + 2) % 3, u1 = (ax + 1) % 3, u2 = (ax + 2) % 3;
+  float poly[16][3], tmp[16][3]; int np_ = 4;
+  for (int v = 0; v < 4; v++) {
+    float s1 = (v == 0 || v == 3) ? hi[k1] : -hi[k1], s2 = (v < 2) ? hi[k2] : -hi[k2];
+    for (int x = 0; x < 3; x++) poly[v][x] = pi[x] + si * hi[inc] * Ai[inc][x] + s1 * Ai[k1][x] + s2 * Ai[k2][x];
+  }
+  #pragma unroll 1
+  for (int pl = 0; pl < 4 && np_ > 0; pl++) {  // the four side planes of the reference face
+    const float* u = Ar[pl < 2 ? u1 : u2]; float lim = hr[pl < 2 ? u1 : u2] + 1e-6f, sg = (pl & 1) ? -1.f : 1.f;
+    int nt = 0;
+    #pragma unroll 1
+    for (int v = 0; v < np_; v++) {
+      const float *P = poly[v], *Qv = poly[(v + 1) % np_];
+      float dP = sg * ((P[0] - pr[0]) * u[0] + (P[1] - pr[1]) * u[1] + (P[2] - pr[2]) * u[2]) - lim;
+      float dQ = sg * ((Qv[0] - pr[0]) * u[0] + (Qv[1] - pr[1]) * u[1] + (Qv[2] - pr[2]) * u[2]) - lim;
+      if (dP <= 0.f) { for (int x = 0; x < 3; x++) tmp[nt][x] = P[x]; nt++; }
+      if ((dP <= 0.f) != (dQ <= 0.f)) { float f = dP / (dP - dQ); for (int x = 0; x < 3; x++) tmp[nt][x] = P[x] + f * (Qv[x] - P[x]); nt++; }
+    }
+    np_ = nt > 8 ? 8 : nt;
+    for (int v = 0; v < np_; v++) for (int x = 0; x < 3; x++) poly[v][x] = tmp[v][x];
+  }
+  int nc = 0;
+  #pragma unroll 1
+  for (int v = 0; v < np_ && nc < 8; v++) {
+    float depth = hr[ax] - ((poly[v][0] - pr[0]) * n[0] + (poly[v][1] - pr[1]) * n[1] + (poly[v][2] - pr[2]) * n[2]);
+    if (depth < -margin) continue;
+    c[nc].dist = -depth;
+    for (int x = 0; x < 3; x++) {
+      c[nc].pos[x] = poly[v][x] + 0.5f * depth * n[x];
+      c[nc].n[x] = ref ? -n[x] : n[x];  // from box 1 to box 2
+      c[nc].yh[x] = 0.f;
+    }
+    nc++;
+  }
+  return nc;
 }
 __device__ __forceinline__ void make_frame(float* f /*9: n, yhint -> n,t1,t2*/) {
   normalize3(f);
@@ -1273,10 +1344,13 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
             const float* c = gpose + GP * m.geom_cslot[g];
             float r = c[12], mg = c[13];
             int ct = m.geom_contype[g], ca = m.geom_conaffinity[g];
-            int ix0 = max((int)floorf((c[0] - r - m.grid_x0) / m.grid_cell), 0);
-            int ix1 = min((int)floorf((c[0] + r - m.grid_x0) / m.grid_cell), m.grid_nx - 1);
-            int iy0 = max((int)floorf((c[1] - r - m.grid_y0) / m.grid_cell), 0);
-            int iy1 = min((int)floorf((c[1] + r - m.grid_y0) / m.grid_cell), m.grid_ny - 1);
+            // (cell range widened by 1e-4 cell: never narrower than the exact range, whatever the rounding of the
+            // fast division; a cell visited in excess only adds candidates that the reach test below rejects)
+            const float icell = 1.f / m.grid_cell;
+            int ix0 = max((int)floorf((c[0] - r - m.grid_x0) * icell - 1e-4f), 0);
+            int ix1 = min((int)floorf((c[0] + r - m.grid_x0) * icell + 1e-4f), m.grid_nx - 1);
+            int iy0 = max((int)floorf((c[1] - r - m.grid_y0) * icell - 1e-4f), 0);
+            int iy1 = min((int)floorf((c[1] + r - m.grid_y0) * icell + 1e-4f), m.grid_ny - 1);
             #pragma unroll 1
             for (int ix = ix0; ix <= ix1; ix++) {
               #pragma unroll 1
@@ -1303,6 +1377,17 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
                   else { if (wr < L.maxpair) pairlist[wr] = (int)(0x80000000u | ((unsigned)q << 20) | (unsigned)k); wr++; }
                 }
               }
+            }
+          }
+          if (pass == 1 && cnt > 1) {
+            // the lane's candidates in ascending static index: the order no longer depends on the cell a
+            // candidate was found in (same rule in the oracle)
+            const int lo = wr - cnt, hi = min(wr, L.maxpair);
+            #pragma unroll 1
+            for (int a = lo + 1; a < hi; a++) {
+              int v = pairlist[a], b = a - 1;
+              while (b >= lo && (unsigned)pairlist[b] > (unsigned)v) { pairlist[b + 1] = pairlist[b]; b--; }
+              pairlist[b + 1] = v;
             }
           }
           if (pass == 0) {
@@ -1394,7 +1479,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         } else if (t2 == G_BOX) {
           if (t1 == G_SPHERE) n = sphere_box(rc[0], margin, a, s1[0], b, s2);
           else if (t1 == G_CAPSULE) n = capsule_box(rc, margin, a, s1, b, s2);
-          else if (t1 == G_BOX) n = box_box(rc, a, s1, b, s2);
+          else if (t1 == G_BOX) n = box_box(rc, margin, a, s1, b, s2);
         } else if (t1 == G_CAPSULE && t2 == G_CAPSULE) {
           float a1[3] = {a[3 + 2], a[3 + 5], a[3 + 8]}, a2[3] = {b[3 + 2], b[3 + 5], b[3 + 8]};
           float dif[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};

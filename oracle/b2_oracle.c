@@ -658,40 +658,114 @@ static int capsule_box(RawCon* c, real margin, const real* cp, const real* cm, c
   }
   return n;
 }
-/* box - box, vertex-face contacts only (no edge-edge): vertices of A inside B, then vertices of B inside A,
- * each leaving through the nearest face of the other box; at most 8 contacts in that order. */
+/* box - box: separating-axis test over the 15 candidate axes (3 + 3 face normals, 9 edge cross products), then
+ *   face case  - the incident face of the other box (the one most anti-parallel to the reference normal) is clipped
+ *                against the four side planes of the reference face (Sutherland-Hodgman); every clipped vertex
+ *                within `margin` of the reference face is a contact (<= 8), position = midpoint between the surfaces;
+ *   edge case  - one contact at the midpoint of the closest points of the two edges.
+ * The axis of least penetration wins; a later axis replaces an earlier one only when it is better by more than
+ * 1e-5 (relative), and an edge axis only when its depth is 5 % smaller than the best face axis (the usual bias
+ * towards face contacts) - so ties (stacked, aligned boxes) resolve the same way in fp32 and fp64.
+ * The normal points from box 1 to box 2.  (Own statement of the textbook algorithm: the source of MuJoCo's
+ * mjc_BoxBox is not available in this image; contact counts and positions for face and edge cases are pinned by
+ * statics in tests/test_boxes_terrain.py.) */
 static int box_box(RawCon* c, real margin, const real* p1, const real* m1, const real* h1,
                    const real* p2, const real* m2, const real* h2) {
-  int n = 0; (void)margin;
-  for (int pass = 0; pass < 2 && n < 8; pass++) {
-    const real *pa = pass ? p2 : p1, *ma = pass ? m2 : m1, *ha = pass ? h2 : h1;   /* vertices of this box */
-    const real *pb = pass ? p1 : p2, *mb = pass ? m1 : m2, *hb = pass ? h1 : h2;   /* tested against this box */
-    for (int i = 0; i < 8 && n < 8; i++) {
-      real v[3] = { (i&1 ? ha[0] : -ha[0]), (i&2 ? ha[1] : -ha[1]), (i&4 ? ha[2] : -ha[2]) }, w[3], l[3];
-      mulmatvec3(w, ma, v);
-      for (int k = 0; k < 3; k++) w[k] += pa[k];
-      real d[3] = { w[0]-pb[0], w[1]-pb[1], w[2]-pb[2] };
-      int in = 1;
-      for (int k = 0; k < 3; k++) { l[k] = mb[k]*d[0] + mb[3+k]*d[1] + mb[6+k]*d[2]; if (fabs(l[k]) > hb[k]) in = 0; }
-      if (!in) continue;
-      int best = 0; real depth = hb[0] - fabs(l[0]);
-      for (int k = 1; k < 3; k++) { real t = hb[k] - fabs(l[k]); if (t < depth) { depth = t; best = k; } }
-      real nl[3] = {0,0,0}, nw[3];
-      nl[best] = l[best] >= 0 ? (real)1 : (real)-1;      /* outward face normal of the containing box */
-      mulmatvec3(nw, mb, nl);
-      /* normal must point from geom1 (A) to geom2 (B): a vertex of A leaves B along +nw -> n = -nw;
-         a vertex of B leaves A along +nw -> n = +nw */
-      real sgn = pass ? (real)1 : (real)-1;
-      c[n].dist = -depth;
-      for (int k = 0; k < 3; k++) {
-        c[n].frame[k] = sgn*nw[k];
-        c[n].pos[k] = w[k] + nw[k]*((real)0.5*depth);
-      }
-      for (int k = 3; k < 9; k++) c[n].frame[k] = 0;
-      n++;
-    }
+  real A[3][3], B[3][3], R[3][3], Q[3][3], t[3] = { p2[0]-p1[0], p2[1]-p1[1], p2[2]-p1[2] }, tA[3], tB[3];
+  for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) { A[i][k] = m1[3*k+i]; B[i][k] = m2[3*k+i]; }  /* axes = columns */
+  for (int i = 0; i < 3; i++) {
+    tA[i] = dot3(t, A[i]); tB[i] = dot3(t, B[i]);
+    for (int j = 0; j < 3; j++) { R[i][j] = dot3(A[i], B[j]); Q[i][j] = fabs(R[i][j]) + (real)1e-6; }
   }
-  return n;
+  int best = -1; real bdepth = 0;
+  /* face axes of box 1 (codes 0-2) and box 2 (codes 3-5) */
+  for (int i = 0; i < 3; i++) {
+    real depth = h1[i] + h2[0]*Q[i][0] + h2[1]*Q[i][1] + h2[2]*Q[i][2] - fabs(tA[i]);
+    if (depth < -margin) return 0;
+    if (best < 0 || depth < bdepth - (real)1e-5*((real)1 + fabs(bdepth))) { best = i; bdepth = depth; }
+  }
+  for (int j = 0; j < 3; j++) {
+    real depth = h2[j] + h1[0]*Q[0][j] + h1[1]*Q[1][j] + h1[2]*Q[2][j] - fabs(tB[j]);
+    if (depth < -margin) return 0;
+    if (depth < bdepth - (real)1e-5*((real)1 + fabs(bdepth))) { best = 3 + j; bdepth = depth; }
+  }
+  /* edge axes a_i x b_j (codes 6 + 3 i + j) */
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+    real l2 = (real)1 - R[i][j]*R[i][j];
+    if (l2 < (real)1e-6) continue;  /* (nearly) parallel edges: covered by the face axes */
+    int i1 = (i+1)%3, i2 = (i+2)%3, j1 = (j+1)%3, j2 = (j+2)%3;
+    real il = (real)1 / sqrt(l2);
+    real depth = (h1[i1]*Q[i2][j] + h1[i2]*Q[i1][j] + h2[j1]*Q[i][j2] + h2[j2]*Q[i][j1]
+                  - fabs(tA[i2]*R[i1][j] - tA[i1]*R[i2][j])) * il;
+    if (depth < -margin) return 0;
+    if (depth + (real)0.05*fabs(depth) + (real)1e-6 < bdepth) { best = 6 + 3*i + j; bdepth = depth; }
+  }
+  if (best >= 6) {
+    int i = (best-6)/3, j = (best-6)%3;
+    real L[3]; cross3(L, A[i], B[j]); normalize3(L);
+    if (dot3(L, t) < 0) { L[0] = -L[0]; L[1] = -L[1]; L[2] = -L[2]; }
+    real pa[3] = { p1[0], p1[1], p1[2] }, pb[3] = { p2[0], p2[1], p2[2] };
+    for (int k = 0; k < 3; k++) {
+      if (k != i) { real sg = dot3(A[k], L) >= 0 ? h1[k] : -h1[k]; for (int x = 0; x < 3; x++) pa[x] += sg*A[k][x]; }
+      if (k != j) { real sg = dot3(B[k], L) >= 0 ? -h2[k] : h2[k]; for (int x = 0; x < 3; x++) pb[x] += sg*B[k][x]; }
+    }
+    /* closest points of the lines pa + s a_i and pb + u b_j, clamped to the edges */
+    real d[3] = { pb[0]-pa[0], pb[1]-pa[1], pb[2]-pa[2] }, r = R[i][j], da = dot3(d, A[i]), db = dot3(d, B[j]);
+    real den = (real)1 - r*r;
+    real sA = (da - r*db) / den, sB = (r*da - db) / den;
+    sA = sA > h1[i] ? h1[i] : (sA < -h1[i] ? -h1[i] : sA);
+    sB = sB > h2[j] ? h2[j] : (sB < -h2[j] ? -h2[j] : sB);
+    c[0].dist = -bdepth;
+    for (int x = 0; x < 3; x++) {
+      c[0].pos[x] = (real)0.5*(pa[x] + sA*A[i][x] + pb[x] + sB*B[j][x]);
+      c[0].frame[x] = L[x];
+    }
+    for (int k = 3; k < 9; k++) c[0].frame[k] = 0;
+    return 1;
+  }
+  /* face case: reference box `ref` (0: box 1, 1: box 2), reference axis `ax`, n = outward normal towards the other box */
+  int ref = best >= 3, ax = ref ? best-3 : best;
+  real (*Ar)[3] = ref ? B : A; real (*Ai)[3] = ref ? A : B;
+  const real *pr = ref ? p2 : p1, *pi = ref ? p1 : p2, *hr = ref ? h2 : h1, *hi = ref ? h1 : h2;
+  real sgn = (ref ? -tB[ax] : tA[ax]) >= 0 ? (real)1 : (real)-1;
+  real n[3] = { sgn*Ar[ax][0], sgn*Ar[ax][1], sgn*Ar[ax][2] };
+  /* incident face: the face of the other box whose outward normal is most anti-parallel to n */
+  int inc = 0; real bd = fabs(dot3(n, Ai[0]));
+  for (int k = 1; k < 3; k++) { real v = fabs(dot3(n, Ai[k])); if (v > bd + (real)1e-6) { bd = v; inc = k; } }
+  real si = dot3(n, Ai[inc]) > 0 ? (real)-1 : (real)1;
+  int k1 = (inc+1)%3, k2 = (inc+2)%3, u1 = (ax+1)%3, u2 = (ax+2)%3;
+  real poly[16][3], tmp[16][3]; int np_ = 4;
+  for (int v = 0; v < 4; v++) {
+    real s1 = (v == 0 || v == 3) ? hi[k1] : -hi[k1], s2 = (v < 2) ? hi[k2] : -hi[k2];
+    for (int x = 0; x < 3; x++) poly[v][x] = pi[x] + si*hi[inc]*Ai[inc][x] + s1*Ai[k1][x] + s2*Ai[k2][x];
+  }
+  /* clip against the four side planes of the reference face: +-u1, +-u2 */
+  for (int pl = 0; pl < 4 && np_ > 0; pl++) {
+    const real* u = Ar[pl < 2 ? u1 : u2]; real lim = hr[pl < 2 ? u1 : u2] + (real)1e-6, sg = (pl & 1) ? (real)-1 : (real)1;
+    int nt = 0;
+    for (int v = 0; v < np_; v++) {
+      const real *P = poly[v], *Qv = poly[(v+1)%np_];
+      real dP = sg*((P[0]-pr[0])*u[0] + (P[1]-pr[1])*u[1] + (P[2]-pr[2])*u[2]) - lim;
+      real dQ = sg*((Qv[0]-pr[0])*u[0] + (Qv[1]-pr[1])*u[1] + (Qv[2]-pr[2])*u[2]) - lim;
+      if (dP <= 0) { for (int x = 0; x < 3; x++) tmp[nt][x] = P[x]; nt++; }
+      if ((dP <= 0) != (dQ <= 0)) { real f = dP / (dP - dQ); for (int x = 0; x < 3; x++) tmp[nt][x] = P[x] + f*(Qv[x]-P[x]); nt++; }
+    }
+    np_ = nt > 8 ? 8 : nt;
+    for (int v = 0; v < np_; v++) for (int x = 0; x < 3; x++) poly[v][x] = tmp[v][x];
+  }
+  int nc = 0;
+  for (int v = 0; v < np_ && nc < 8; v++) {
+    real depth = hr[ax] - ((poly[v][0]-pr[0])*n[0] + (poly[v][1]-pr[1])*n[1] + (poly[v][2]-pr[2])*n[2]);
+    if (depth < -margin) continue;
+    c[nc].dist = -depth;
+    for (int x = 0; x < 3; x++) {
+      c[nc].pos[x] = poly[v][x] + (real)0.5*depth*n[x];
+      c[nc].frame[x] = ref ? -n[x] : n[x];  /* from box 1 to box 2 */
+    }
+    for (int k = 3; k < 9; k++) c[nc].frame[k] = 0;
+    nc++;
+  }
+  return nc;
 }
 /* mju_makeFrame */
 static void make_frame(real* f) {
@@ -798,7 +872,9 @@ static void collision(W* d) {
     if (n) ncon = emit_contacts(d, ncon, g1, g2, rc, n, margin);
   }
   /* (2) grid-static geoms: every dynamic collision geom (id order) visits the cells under its bounding
-   * sphere (ix outer, iy inner); a static geom spanning several cells is taken only in the first common cell */
+   * sphere; a static geom spanning several cells is taken only in the first common cell.  The candidates of one
+   * dynamic geom are processed in ascending static index, so the contact order does not depend on which cell a
+   * candidate was found in (a bounding sphere touching a cell border lands in either cell in fp32). */
   for (int q = 0; q < o->ndyn; q++) {
     int g = o->dyn_cgeom[q];
     const real* c = d->geom_xpos + 3*g;
@@ -806,6 +882,7 @@ static void collision(W* d) {
     int iy0 = (int)floor((c[1] - rb[g] - o->grid_y0) / o->grid_cell), iy1 = (int)floor((c[1] + rb[g] - o->grid_y0) / o->grid_cell);
     if (ix0 < 0) ix0 = 0; if (iy0 < 0) iy0 = 0;
     if (ix1 >= o->grid_nx) ix1 = o->grid_nx - 1; if (iy1 >= o->grid_ny) iy1 = o->grid_ny - 1;
+    int cand[1024], ncand = 0;
     for (int ix = ix0; ix <= ix1; ix++)
       for (int iy = iy0; iy <= iy1; iy++) {
         int cell = ix*o->grid_ny + iy;
@@ -815,14 +892,23 @@ static void collision(W* d) {
           int fy = o->static_cell0[2*k+1] > iy0 ? o->static_cell0[2*k+1] : iy0;
           if (ix != fx || iy != fy) continue;   /* duplicate: handled in an earlier cell */
           if (!((o->geom_contype[g] & o->geom_conaffinity[sg]) || (o->geom_contype[sg] & o->geom_conaffinity[g]))) continue;
-          real margin = gmargin[g] > gmargin[sg] ? gmargin[g] : gmargin[sg];
-          int g1 = g, g2 = sg;
-          if (o->geom_type[g1] > o->geom_type[g2] || (o->geom_type[g1] == o->geom_type[g2] && g1 > g2)) { g1 = sg; g2 = g; }
-          RawCon rc[8];
-          int n = narrowphase(d, rc, g1, g2, margin);
-          if (n) ncon = emit_contacts(d, ncon, g1, g2, rc, n, margin);
+          if (ncand < 1024) cand[ncand++] = k;
         }
       }
+    for (int a = 1; a < ncand; a++) {  /* insertion sort by static index */
+      int v = cand[a], b = a - 1;
+      while (b >= 0 && cand[b] > v) { cand[b+1] = cand[b]; b--; }
+      cand[b+1] = v;
+    }
+    for (int a = 0; a < ncand; a++) {
+      int sg = o->static_geom[cand[a]];
+      real margin = gmargin[g] > gmargin[sg] ? gmargin[g] : gmargin[sg];
+      int g1 = g, g2 = sg;
+      if (o->geom_type[g1] > o->geom_type[g2] || (o->geom_type[g1] == o->geom_type[g2] && g1 > g2)) { g1 = sg; g2 = g; }
+      RawCon rc[8];
+      int n = narrowphase(d, rc, g1, g2, margin);
+      if (n) ncon = emit_contacts(d, ncon, g1, g2, rc, n, margin);
+    }
   }
   *d->ncon = ncon;
 }

@@ -69,7 +69,7 @@ int emul_capsule_box(const float* cap, const float* size, const float* box, cons
 }
 int emul_box_box(const float* b1, const float* h1, const float* b2_, const float* h2, float* out) {
   b2::RawCon c[8];
-  return prim_out(c, b2::box_box(c, b1, h1, b2_, h2), out);
+  return prim_out(c, b2::box_box(c, 0.f, b1, h1, b2_, h2), out);
 }
 // J x for contact rows (4 pyramid rows per contact, written to CJV0..3) and limit rows (LJV): device mulJ on
 // caller-built SoA blocks.  layout[] returns the enum values the caller needs to fill them.

@@ -1,8 +1,8 @@
 """Box primitives and grid-static broadphase in the oracle + terrain generator (BASELINE config E groundwork).
 
 The box routines are own restatements (MuJoCo's sources for mjc_SphereBox / mjc_CapsuleBox / mjc_BoxBox are not
-available here; box-box is vertex-face only), so they are pinned by statics and by cross-checking the grid
-broadphase against the exhaustive pair table."""
+available here; box-box is the textbook separating-axis test + face clipping / edge-edge contact), so they are
+pinned by statics and by cross-checking the grid broadphase against the exhaustive pair table."""
 
 import sys
 from pathlib import Path
@@ -45,6 +45,68 @@ def test_objects_rest_on_a_box(geom, z, quat, ncon):
   g1 = int(o.contact_geom[0, 0])
   assert fr[0] == pytest.approx([0, 0, 1.0 if g1 == 0 else -1.0], abs=1e-6)
   assert o.qpos[0, 2] == pytest.approx(z, abs=2e-3)
+
+
+def _prim_box_box(p1, R1, h1, p2, R2, h2, margin=0.0):
+  import ctypes
+
+  from oracle.oracle import build
+  build()
+  L = ctypes.CDLL(str(Path(__file__).parents[1] / "oracle" / "libb2oracle64.so"))
+  dp = ctypes.POINTER(ctypes.c_double)
+  L.b2o_prim_box_box.argtypes = [dp] * 6 + [ctypes.c_double, dp]
+  out = np.zeros(56)
+  P = lambda a: np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(dp)
+  arrs = [np.ascontiguousarray(np.asarray(a, dtype=np.float64).ravel()) for a in (p1, R1, h1, p2, R2, h2)]
+  n = L.b2o_prim_box_box(*[a.ctypes.data_as(dp) for a in arrs], margin, out.ctypes.data_as(dp))
+  return n, out[: 7 * n].reshape(n, 7)
+
+
+def test_box_box_face_clipping_and_edge_edge_cases():
+  """box-box = SAT + clipping: a cube on a slab (4 contacts at its bottom corners), the same cube overhanging the
+  slab's edge (the incident face is clipped at the slab's side plane), rotated 45 deg (4), two crossed beams
+  turned edge-up / edge-down (one edge-edge contact at the crossing, depth = overlap of the edges), separation
+  beyond the margin (none), and symmetry under swapping the two boxes (normal flips)."""
+  I = np.eye(3)
+  n, c = _prim_box_box([0, 0, 0], I, [2, 2, .5], [0.3, 0.2, 0.999], I, [.5, .5, .5])
+  assert n == 4 and c[:, 0] == pytest.approx(-0.001) and np.allclose(c[:, 4:7], [0, 0, 1])
+  assert sorted(map(tuple, np.round(c[:, 1:3], 6))) == [(-0.2, -0.3), (-0.2, 0.7), (0.8, -0.3), (0.8, 0.7)]
+  assert c[:, 3] == pytest.approx(0.4995)  # midway between the two surfaces
+  n, c = _prim_box_box([0, 0, 0], I, [2, 2, .5], [1.8, 0, 0.999], I, [.5, .5, .5])  # overhang: x in [1.3, 2.3] clipped at 2
+  assert n == 4 and c[:, 1].max() == pytest.approx(2.0, abs=1e-5) and c[:, 1].min() == pytest.approx(1.3)
+  a = np.pi / 4
+  Rz = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+  n, c = _prim_box_box([0, 0, 0], I, [2, 2, .5], [0, 0, 0.99], Rz, [.5, .5, .5])
+  assert n == 4 and c[:, 0] == pytest.approx(-0.01) and np.hypot(c[:, 1], c[:, 2]) == pytest.approx(np.sqrt(0.5))
+  Rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+  Ry = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+  n, c = _prim_box_box([0, 0, 0], Rx, [1, .1, .1], [0, 0, 0.27], Ry, [.1, 1, .1])
+  assert n == 1 and c[0, 0] == pytest.approx(0.27 - 2 * 0.1 * np.sqrt(2), abs=2e-6) and np.allclose(c[0, 4:7], [0, 0, 1])
+  assert np.allclose(c[0, 1:4], [0, 0, 0.135], atol=1e-9)
+  assert _prim_box_box([0, 0, 0], I, [1, 1, 1], [0, 0, 2.05], I, [1, 1, 1])[0] == 0
+  assert _prim_box_box([0, 0, 0], I, [1, 1, 1], [0, 0, 2.05], I, [1, 1, 1], margin=0.1)[0] == 4  # within the margin
+  n1, c1 = _prim_box_box([0, 0, 0], Rx, [1, .1, .1], [0, 0, 0.27], Ry, [.1, 1, .1])
+  n2, c2 = _prim_box_box([0, 0, 0.27], Ry, [.1, 1, .1], [0, 0, 0], Rx, [1, .1, .1])
+  assert n1 == n2 == 1 and np.allclose(c1[0, :4], c2[0, :4]) and np.allclose(c1[0, 4:7], -c2[0, 4:7])
+
+
+def test_box_resting_on_an_edge_of_a_box():
+  """A flat box lying across the table's edge (half of it overhangs): it rests on the clipped contact patch, the
+  contact forces carry its weight and the net moment about its centre vanishes (it does not tip: com is over the table)."""
+  xml = ON_BOX.format(geom='<geom type="box" size="0.2 0.1 0.02" mass="3"/>', z=0.5199, quat="").replace('pos="0 0 0.5199"', 'pos="0.4 0 0.5199"')
+  m = Spec.from_string(xml).compile()
+  o = Oracle(m)
+  fz = []
+  for i in range(3000):
+    o.step()
+    if i >= 2000:
+      fz.append(o.contact_force[0, 0 : 3 * int(o.ncon[0, 0]) : 3].sum())
+  n = int(o.ncon[0, 0])
+  assert n == 4 and abs(o.qvel[0]).max() < 0.05  # (a lightly damped rocking mode of the soft contacts remains)
+  assert np.mean(fz) == pytest.approx(3 * 9.81, rel=5e-3)
+  assert abs(o.qpos[0, 2] - 0.5199) < 2e-3 and abs(o.qpos[0, 0] - 0.4) < 5e-3  # it neither sinks, tips nor slides
+  pos = o.contact_pos[0, : 3 * n].reshape(n, 3)
+  assert pos[:, 0].max() == pytest.approx(0.5, abs=1e-4) and pos[:, 0].min() == pytest.approx(0.2, abs=1e-3)  # patch ends at the table's edge
 
 
 def test_sphere_inside_box_is_pushed_out_through_the_nearest_face():

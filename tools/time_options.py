@@ -36,8 +36,10 @@ def run(label, opts, k=12):
   st = sim.stats()
   print(f"{label:44s} {tot / k / 4 * 1e3:8.1f} us/sub-step   ncon {st.ncon_mean:.1f} iters {st.niter_mean:.2f}")
 
-base = dict(full_solver=0, work_queue=0, split_streams=2, phase_sync=2, reorder_every_substep=0)
-run("default (order once per step_n, emit last)", base)
-run("reorder every sub-step", dict(base, reorder_every_substep=1))
-run("default again", base)
+base = dict(full_solver=0, work_queue=0, split_streams=2, phase_sync=2, reorder_every_substep=1)
+run("default: 2 streams", base)
+run("1 stream", dict(base, split_streams=1))
 run("3 streams", dict(base, split_streams=3))
+run("4 streams", dict(base, split_streams=4))
+run("2 streams, psync off", dict(base, phase_sync=0))
+run("2 streams, full solver", dict(base, full_solver=1))
