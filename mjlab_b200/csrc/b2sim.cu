@@ -1030,7 +1030,7 @@ int b2_algorithmic_bytes(b2_sim* s, void* stream, double* solver_bytes, double* 
   // whole step: state in/out + consumer-visible kinematics (what this kernel actually moves)
   double in = m.nq + m.nv + m.nu + m.nv + m.nv + 6.0 * m.nbody;
   double outb = m.nq + 3.0 * m.nv + m.nu + m.nsensordata + (3 + 4 + 9 + 3 + 3 + 6) * (double)m.nbody +
-                12.0 * m.ngeom + 12.0 * m.nsite;
+                12.0 * m.nposegeom + 12.0 * m.nsite;  // geoms welded to the world are posed once at create, not per step
   if (solver_bytes) *solver_bytes = solver * s->nworld;
   if (step_bytes) *step_bytes = 4.0 * (in + outb) * s->nworld;
   return 0;
