@@ -44,6 +44,12 @@ WORKLOADS = {
                  "{envs} envs/GPU, random-action agent, decimation 4, dt 0.005, Newton<=10 it / ls<=20, implicitfast, "
                  "pyramidal, foot-friction DR, resets+pushes",
             model="go1_rough", robot="go1"),
+  # not a BASELINE config: config E's terrain with the four height-field sub-terrains the reference keeps commented
+  # out of ROUGH_TERRAINS_CFG (terrains/config.py:28-55) switched on — exercises csrc/b2_convex.h
+  "F": dict(desc="Unitree Go1 velocity-tracking on the rough terrain with height fields (2374 boxes + 70 hfields of 80x80 "
+                 "samples: pyramid slopes, random rough, waves), {envs} envs/GPU, random-action agent, decimation 4, "
+                 "dt 0.005, Newton<=10 it / ls<=20, implicitfast, pyramidal, foot-friction DR, resets+pushes",
+            model="go1_rough_hf", robot="go1"),
 }
 WORKLOAD = WORKLOADS["B"]["desc"]
 
@@ -53,8 +59,9 @@ def make_env(workload: str, envs: int, seed: int, dev: str):
 
   if workload == "C":
     return TrackingFlatEnv(TrackingEnvCfg(num_envs=envs, seed=seed), device=dev)
-  if workload == "E":
-    return VelocityFlatEnv(VelocityEnvCfg(robot="go1", terrain="rough", num_envs=envs, seed=seed), device=dev)
+  if workload in ("E", "F"):
+    return VelocityFlatEnv(VelocityEnvCfg(robot="go1", terrain="rough" if workload == "E" else "rough_hf",
+                                          num_envs=envs, seed=seed), device=dev)
   return VelocityFlatEnv(VelocityEnvCfg(num_envs=envs, seed=seed), device=dev)
 
 

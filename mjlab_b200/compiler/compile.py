@@ -50,6 +50,9 @@ MODEL_ARRAYS = [
   # static (world-welded, non-plane) collision geoms found through a uniform xy grid instead of the pair table
   ("static_geom", "i"), ("static_cell0", "i"), ("dyn_cgeom", "i"), ("grid_start", "i"), ("grid_items", "i"),
   ("grid_params", "f"),
+  # mesh / height-field assets (csrc/b2_convex.h): geom_dataid -> mesh id (mesh geoms) or hfield id (hfield geoms)
+  ("geom_dataid", "i"), ("mesh_vertadr", "i"), ("mesh_vertnum", "i"), ("mesh_vert", "f"),
+  ("hfield_adr", "i"), ("hfield_nrow", "i"), ("hfield_ncol", "i"), ("hfield_size", "f"), ("hfield_data", "f"),
   ("sensor_type", "i"), ("sensor_objtype", "i"), ("sensor_objid", "i"),
   ("sensor_reftype", "i"), ("sensor_refid", "i"), ("sensor_intprm", "i"),
   ("sensor_adr", "i"), ("sensor_dim", "i"),
@@ -147,6 +150,7 @@ class Model:
     meta = json.loads(str(z["__meta__"]))
     m = Model()
     m.arrays = {k: z[k] for k in z.files if k != "__meta__"}
+    fill_asset_defaults(m.arrays)
     m.names = meta["names"]
     m.keys = {
       k: {n: (None if v is None else np.array(v)) for n, v in d.items()}
@@ -156,9 +160,53 @@ class Model:
     return m
 
 
+def fill_asset_defaults(arrays: dict) -> None:
+  """Model tables written before mesh / height-field assets existed (compiled blobs, MjModel-like objects
+  without assets) get empty asset arrays and ``geom_dataid = -1``."""
+  if "geom_dataid" not in arrays:
+    arrays["geom_dataid"] = np.full(int(np.asarray(arrays["ngeom"]).reshape(-1)[0]), -1, dtype=np.int32)
+  for k, dt in (("mesh_vertadr", np.int32), ("mesh_vertnum", np.int32), ("mesh_vert", np.float64),
+                ("hfield_adr", np.int32), ("hfield_nrow", np.int32), ("hfield_ncol", np.int32),
+                ("hfield_size", np.float64), ("hfield_data", np.float64)):
+    if k not in arrays:
+      arrays[k] = np.zeros((0, 3) if k == "mesh_vert" else ((0, 4) if k == "hfield_size" else 0), dtype=dt)
+
+
 # ---------------------------------------------------------------------------------------
 # geometry-derived inertia (bodies without <inertial>)
 # ---------------------------------------------------------------------------------------
+
+
+def mesh_volume_inertia(vertex: np.ndarray, face: np.ndarray | None):
+  """(volume, centre of mass, 3x3 unit-density inertia about the com) of a closed triangle mesh (signed
+  tetrahedra against the origin); without faces the convex hull is used, which is also what collides."""
+  if face is None:
+    from scipy.spatial import ConvexHull
+
+    hull = ConvexHull(vertex)
+    face = hull.simplices.copy()
+    c = vertex[hull.vertices].mean(axis=0)
+    for k, f in enumerate(face):  # orient outwards
+      a, b, d = vertex[f]
+      if np.dot(np.cross(b - a, d - a), a - c) < 0:
+        face[k] = f[::-1]
+  a, b, c = vertex[face[:, 0]], vertex[face[:, 1]], vertex[face[:, 2]]
+  vol6 = np.einsum("ij,ij->i", a, np.cross(b, c))
+  V = vol6.sum() / 6.0
+  if abs(V) < 1e-18:
+    return 0.0, np.zeros(3), np.zeros((3, 3))
+  com = ((a + b + c) * vol6[:, None]).sum(axis=0) / (24.0 * V)
+  # second moments: integral of x x^T over a tetrahedron (0, a, b, c) = vol/20 * (sum_i p_i p_i^T + s s^T), s = a+b+c
+  ssum = a + b + c
+  C = (np.einsum("i,ij,ik->jk", vol6, a, a) + np.einsum("i,ij,ik->jk", vol6, b, b) + np.einsum("i,ij,ik->jk", vol6, c, c)
+       + np.einsum("i,ij,ik->jk", vol6, ssum, ssum)) / 120.0
+  if V < 0:
+    V, C = -V, -C
+  C = C - V * np.outer(com, com)
+  inertia = np.trace(C) * np.eye(3) - C
+  return float(V), com, inertia
+
+
 
 
 def _geom_volume_inertia(g: S.Geom):
@@ -195,10 +243,27 @@ def _geom_volume_inertia(g: S.Geom):
   return 0.0, np.zeros(3)  # plane / mesh / hfield carry no mass here
 
 
-def _body_inertial_from_geoms(b: S.Body):
+def _body_inertial_from_geoms(b: S.Body, meshes: dict | None = None):
   tot_m, com = 0.0, np.zeros(3)
   parts = []
   for g in b.geoms:
+    if g.type == S.GEOM_MESH and meshes and g.mesh in meshes and (g.mass is not None or g.density > 0):
+      mesh = meshes[g.mesh]
+      try:
+        vol, mc, mi = mesh_volume_inertia(mesh.load(), mesh.face)
+      except (OSError, ValueError):
+        continue  # asset not readable here: the geom carries no mass (bodies of the zoo robots have <inertial>)
+      if vol <= 0:
+        continue
+      m = g.mass if g.mass is not None else g.density * vol
+      if m <= 0:
+        continue
+      R = quat_to_mat(g.quat)
+      w, v = np.linalg.eigh(mi * (m / vol))
+      parts.append((m, g.pos + R @ mc, R @ v, w))
+      tot_m += m
+      com += m * (g.pos + R @ mc)
+      continue
     vol, inert = _geom_volume_inertia(g)
     if vol <= 0:
       continue
@@ -245,6 +310,11 @@ _SUPPORTED_PAIRS = {
   (S.GEOM_SPHERE, S.GEOM_SPHERE), (S.GEOM_SPHERE, S.GEOM_CAPSULE),
   (S.GEOM_CAPSULE, S.GEOM_CAPSULE),
   (S.GEOM_SPHERE, S.GEOM_BOX), (S.GEOM_CAPSULE, S.GEOM_BOX), (S.GEOM_BOX, S.GEOM_BOX),
+  # convex routines (csrc/b2_convex.h): meshes through their convex hull, height fields prism by prism
+  (S.GEOM_PLANE, S.GEOM_MESH), (S.GEOM_SPHERE, S.GEOM_MESH), (S.GEOM_CAPSULE, S.GEOM_MESH),
+  (S.GEOM_BOX, S.GEOM_MESH), (S.GEOM_MESH, S.GEOM_MESH),
+  (S.GEOM_HFIELD, S.GEOM_SPHERE), (S.GEOM_HFIELD, S.GEOM_CAPSULE), (S.GEOM_HFIELD, S.GEOM_BOX),
+  (S.GEOM_HFIELD, S.GEOM_MESH),
 }
 STATIC_GRID_THRESHOLD = 16  # more static box/sphere/capsule geoms than this -> grid broadphase
 
@@ -307,11 +377,11 @@ def _build_static_grid(A, static, weld, gbody, gtype, ngeom, cell: float = 1.0) 
     smask_t |= A["geom_contype"][g]
     smask_a |= A["geom_conaffinity"][g]
   A["dyn_cgeom"] = [g for g in range(ngeom)
-                    if g not in inset and weld[gbody[g]] != 0 and gtype[g] != S.GEOM_MESH
+                    if g not in inset and weld[gbody[g]] != 0
                     and ((A["geom_contype"][g] & smask_a) or (A["geom_conaffinity"][g] & smask_t))]
   for g in A["dyn_cgeom"]:
-    if gtype[g] not in (S.GEOM_SPHERE, S.GEOM_CAPSULE, S.GEOM_BOX):
-      raise NotImplementedError("only sphere / capsule / box geoms can collide with grid-static geoms")
+    if gtype[g] not in (S.GEOM_SPHERE, S.GEOM_CAPSULE, S.GEOM_BOX, S.GEOM_MESH):
+      raise NotImplementedError("only sphere / capsule / box / mesh geoms can collide with grid-static geoms")
 
 
 def compile_spec(spec: S.Spec) -> Model:
@@ -327,6 +397,8 @@ def compile_spec(spec: S.Spec) -> Model:
   jid = gid = sid = 0
   dof_last_of_body = {}
   qpos0 = []
+  mesh_ids: dict[str, int] = {}
+  hfield_ids: dict[str, int] = {}
   for b in bodies:
     names["body"].append(b.name)
     pid = b.parent.id if b.parent is not None else 0
@@ -336,7 +408,7 @@ def compile_spec(spec: S.Spec) -> Model:
     if b.mass is not None:
       ipos, iquat, mass, inertia = b.ipos, b.iquat, b.mass, b.inertia
     else:
-      ipos, iquat, mass, inertia = _body_inertial_from_geoms(b)
+      ipos, iquat, mass, inertia = _body_inertial_from_geoms(b, spec.meshes)
     A["body_ipos"].append(ipos)
     A["body_iquat"].append(iquat / np.linalg.norm(iquat))
     A["body_mass"].append(mass)
@@ -401,12 +473,46 @@ def compile_spec(spec: S.Spec) -> Model:
       names["geom"].append(g.name)
       A["geom_type"].append(g.type)
       A["geom_bodyid"].append(b.id)
-      colliding = g.type != S.GEOM_MESH
+      dataid, size, rbound = -1, g.size, _rbound(g.type, g.size)
+      colliding = True
+      if g.type == S.GEOM_MESH:
+        # A mesh collides (through its convex hull) when it has collision bits and vertex data; a mesh whose
+        # file cannot be read stays what it always was here: a visual.
+        colliding = False
+        mesh = spec.meshes.get(g.mesh) if g.mesh else None
+        if mesh is not None and (g.contype or g.conaffinity):
+          try:
+            v = mesh.load()
+          except OSError as e:
+            raise FileNotFoundError(f"geom '{g.name}': mesh '{g.mesh}' has collision bits but its file is unreadable ({e})") from None
+          if g.mesh not in mesh_ids:
+            mesh_ids[g.mesh] = len(mesh_ids)
+            A["mesh_vertadr"].append(sum(A["mesh_vertnum"]))
+            A["mesh_vertnum"].append(len(v))
+            A["mesh_vert"].extend(v.tolist())
+          dataid, colliding = mesh_ids[g.mesh], True
+          size = np.abs(v).max(axis=0)
+          rbound = float(np.linalg.norm(v, axis=1).max())
+      elif g.type == S.GEOM_HFIELD:
+        hf = spec.hfields.get(g.hfield) if g.hfield else None
+        if hf is None:
+          raise ValueError(f"geom '{g.name}': hfield asset '{g.hfield}' not found")
+        if g.hfield not in hfield_ids:
+          hfield_ids[g.hfield] = len(hfield_ids)
+          A["hfield_adr"].append(len(A["hfield_data"]))
+          A["hfield_nrow"].append(hf.nrow)
+          A["hfield_ncol"].append(hf.ncol)
+          A["hfield_size"].append(hf.size)
+          A["hfield_data"].extend(np.asarray(hf.userdata, dtype=float).reshape(-1).tolist())
+        dataid = hfield_ids[g.hfield]
+        size = np.array(hf.size[:3], dtype=float)
+        rbound = float(np.sqrt(hf.size[0] ** 2 + hf.size[1] ** 2 + max(hf.size[2], hf.size[3]) ** 2))
+      A["geom_dataid"].append(dataid)
       A["geom_contype"].append(g.contype if colliding else 0)
       A["geom_conaffinity"].append(g.conaffinity if colliding else 0)
       A["geom_condim"].append(g.condim)
       A["geom_priority"].append(g.priority)
-      A["geom_size"].append(g.size)
+      A["geom_size"].append(size)
       A["geom_pos"].append(g.pos)
       A["geom_quat"].append(g.quat / np.linalg.norm(g.quat))
       A["geom_friction"].append(g.friction)
@@ -415,7 +521,7 @@ def compile_spec(spec: S.Spec) -> Model:
       A["geom_solmix"].append(g.solmix)
       A["geom_margin"].append(g.margin)
       A["geom_gap"].append(g.gap)
-      A["geom_rbound"].append(_rbound(g.type, g.size))
+      A["geom_rbound"].append(rbound)
       A["geom_rgba"].append(g.rgba)
       gid += 1
     for s in b.sites:
@@ -497,7 +603,7 @@ def compile_spec(spec: S.Spec) -> Model:
   gbody = A["geom_bodyid"]
   # static collision geoms: on a body welded to the world, not a plane, with any collision bit
   static = [g for g in range(ngeom)
-            if weld[gbody[g]] == 0 and gtype[g] not in (S.GEOM_PLANE, S.GEOM_MESH)
+            if weld[gbody[g]] == 0 and gtype[g] not in (S.GEOM_PLANE, S.GEOM_MESH, S.GEOM_HFIELD)
             and (A["geom_contype"][g] or A["geom_conaffinity"][g])]
   use_grid = len(static) > STATIC_GRID_THRESHOLD
   in_grid = set(static) if use_grid else set()
@@ -523,7 +629,7 @@ def compile_spec(spec: S.Spec) -> Model:
         continue
       a, b = (g1, g2) if gtype[g1] <= gtype[g2] else (g2, g1)
       if (gtype[a], gtype[b]) not in _SUPPORTED_PAIRS:
-        if gtype[a] == S.GEOM_PLANE and gtype[b] == S.GEOM_PLANE:
+        if gtype[a] in (S.GEOM_PLANE, S.GEOM_HFIELD) and gtype[b] in (S.GEOM_PLANE, S.GEOM_HFIELD):
           continue
         raise NotImplementedError(
           f"collision pair {names['geom'][a]}({gtype[a]}) - {names['geom'][b]}({gtype[b]}) "
@@ -554,6 +660,7 @@ def compile_spec(spec: S.Spec) -> Model:
     "geom_solimp": 5, "geom_rgba": 4, "site_pos": 3, "site_quat": 4,
     "actuator_gainprm": 10, "actuator_biasprm": 10, "actuator_ctrlrange": 2,
     "actuator_forcerange": 2, "sensor_intprm": 3, "body_invweight0": 2, "static_cell0": 2,
+    "mesh_vert": 3, "hfield_size": 4,
   }
   for k, dt in MODEL_ARRAYS:
     if k in ("body_subtreemass", "body_invweight0", "dof_invweight0"):

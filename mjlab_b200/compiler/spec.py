@@ -157,6 +157,7 @@ class Geom:
   mass: float | None = None
   density: float = 1000.0
   mesh: str | None = None
+  hfield: str | None = None
   id: int = -1
 
 
@@ -224,6 +225,9 @@ class Body:
       s[: v.size] = v
       kw["size"] = s
     kw.pop("material", None)
+    for api, attr in (("hfieldname", "hfield"), ("meshname", "mesh")):  # MjsGeom attribute names
+      if api in kw:
+        kw[attr] = kw.pop(api)
     g = Geom(**kw)
     self.geoms.append(g)
     return g
@@ -255,6 +259,68 @@ def _np_kw(kw):
       v = np.array(v, dtype=float)
     out[k] = v
   return out
+
+
+@dataclass
+class Mesh:
+  """``<asset><mesh>``: vertices in the mesh frame (after ``scale``).  Collision uses the convex hull of the
+  vertex set (support mapping over all vertices, ``csrc/b2_convex.h``); faces are only needed to derive an
+  inertia for bodies without ``<inertial>``.  ``file`` (STL binary/ASCII or OBJ) is read lazily."""
+
+  name: str = ""
+  vertex: np.ndarray | None = None  # (n, 3)
+  face: np.ndarray | None = None    # (m, 3) int
+  file: str | None = None
+  scale: np.ndarray = field(default_factory=lambda: np.ones(3))
+
+  def load(self) -> np.ndarray:
+    if self.vertex is None:
+      if self.file is None:
+        raise ValueError(f"mesh '{self.name}' has neither vertex data nor a file")
+      v, f = read_mesh_file(self.file)
+      self.vertex, self.face = v * self.scale, f
+    return self.vertex
+
+
+@dataclass
+class HField:
+  """``<asset><hfield>`` / ``spec.add_hfield`` (``terrains/heightfield_terrains.py:213-225``): ``nrow x ncol``
+  samples in [0, 1] (row index along y), ``size = (radius_x, radius_y, elevation_z, base_z)``."""
+
+  name: str = ""
+  nrow: int = 0
+  ncol: int = 0
+  size: np.ndarray = field(default_factory=lambda: np.array([1.0, 1.0, 1.0, 0.1]))
+  userdata: np.ndarray | None = None
+
+
+def read_mesh_file(path) -> tuple[np.ndarray, np.ndarray | None]:
+  """Vertices (n, 3) and triangles (m, 3) of an STL (binary or ASCII) or OBJ file."""
+  path = Path(path)
+  raw = path.read_bytes()
+  if path.suffix.lower() == ".obj":
+    vs, fs = [], []
+    for ln in raw.decode(errors="replace").splitlines():
+      t = ln.split()
+      if not t:
+        continue
+      if t[0] == "v":
+        vs.append([float(x) for x in t[1:4]])
+      elif t[0] == "f":
+        idx = [int(x.split("/")[0]) for x in t[1:]]
+        idx = [i - 1 if i > 0 else len(vs) + i for i in idx]
+        fs.extend([idx[0], idx[k], idx[k + 1]] for k in range(1, len(idx) - 1))
+    return np.array(vs, dtype=float).reshape(-1, 3), (np.array(fs, dtype=np.int64) if fs else None)
+  if raw[:5].lower() == b"solid" and b"facet" in raw[:1000]:
+    pts = [[float(x) for x in ln.split()[1:4]] for ln in raw.decode(errors="replace").splitlines()
+           if ln.strip().startswith("vertex")]
+    tri = np.array(pts, dtype=float).reshape(-1, 3, 3)
+  else:
+    n = int(np.frombuffer(raw[80:84], dtype="<u4")[0])
+    rec = np.frombuffer(raw[84:84 + 50 * n], dtype=np.dtype([("n", "<f4", 3), ("v", "<f4", (3, 3)), ("a", "<u2")]))
+    tri = rec["v"].astype(float)
+  v, inv = np.unique(tri.reshape(-1, 3), axis=0, return_inverse=True)
+  return v, inv.reshape(-1, 3)
 
 
 @dataclass
@@ -323,6 +389,8 @@ class Spec:
     self.sensors: list[Sensor] = []
     self.keys: list[Key] = []
     self.excludes: list[tuple[str, str]] = []
+    self.meshes: dict[str, Mesh] = {}
+    self.hfields: dict[str, HField] = {}
     self.autolimits = True
     self.angle_scale = 1.0  # radians
 
@@ -394,6 +462,21 @@ class Spec:
     self.excludes.append((body1, body2))
 
   # -- composition ------------------------------------------------------------------------
+  def add_mesh(self, name: str, vertex=None, face=None, file=None, scale=(1.0, 1.0, 1.0)) -> Mesh:
+    m = Mesh(name=name, vertex=None if vertex is None else np.array(vertex, dtype=float).reshape(-1, 3),
+             face=None if face is None else np.array(face, dtype=np.int64).reshape(-1, 3), file=file,
+             scale=np.array(scale, dtype=float))
+    if m.vertex is not None:
+      m.vertex = m.vertex * m.scale
+    self.meshes[name] = m
+    return m
+
+  def add_hfield(self, name: str, size, nrow: int, ncol: int, userdata) -> HField:
+    h = HField(name=name, nrow=int(nrow), ncol=int(ncol), size=np.array(size, dtype=float).reshape(4),
+               userdata=np.array(userdata, dtype=float).reshape(int(nrow), int(ncol)))
+    self.hfields[name] = h
+    return h
+
   def attach(self, child: "Spec", prefix: str = "", parent: Body | None = None) -> None:
     """Graft a deep copy of ``child``'s world-body children under ``parent`` (default: the
     world body), prefixing every name.  Mirrors ``spec.attach(child, prefix=, frame=)`` as used by
@@ -407,11 +490,22 @@ class Spec:
       return prefix + n if n else n
 
     for b in child._walk():
+      for g in b.geoms:  # asset references follow the prefixed asset names
+        if g.mesh:
+          g.mesh = ren(g.mesh)
+        if g.hfield:
+          g.hfield = ren(g.hfield)
       if b is child.worldbody:
         continue
       b.name = ren(b.name)
       for e in (*b.joints, *b.geoms, *b.sites):
         e.name = ren(e.name)
+    for k, v in child.meshes.items():
+      v.name = ren(k)
+      self.meshes[v.name] = v
+    for k, v in child.hfields.items():
+      v.name = ren(k)
+      self.hfields[v.name] = v
     # world-level geoms / sites of the child land on the parent body
     for g in child.worldbody.geoms:
       g.name = ren(g.name)
@@ -440,11 +534,11 @@ class Spec:
   # -- io ---------------------------------------------------------------------------------
   @staticmethod
   def from_file(path: str | Path) -> "Spec":
-    return Spec.from_string(Path(path).read_text())
+    return _parse_mjcf(Path(path).read_text(), Path(path).parent)
 
   @staticmethod
-  def from_string(xml: str) -> "Spec":
-    return _parse_mjcf(xml)
+  def from_string(xml: str, asset_dir: str | Path | None = None) -> "Spec":
+    return _parse_mjcf(xml, None if asset_dir is None else Path(asset_dir))
 
   def compile(self):
     from mjlab_b200.compiler.compile import compile_spec
@@ -562,6 +656,7 @@ def _parse_geom(a: dict[str, str], scale: float) -> Geom:
   if "rgba" in a:
     g.rgba = _vec(a["rgba"], 4)
   g.mesh = a.get("mesh")
+  g.hfield = a.get("hfield")
   return g
 
 
@@ -637,7 +732,7 @@ def _parse_body(node: ET.Element, parent: Body, dfl: _Defaults, childclass, scal
         "(supported: body, inertial, joint, freejoint, geom, site, light, camera)")
 
 
-def _parse_mjcf(xml: str) -> Spec:
+def _parse_mjcf(xml: str, asset_dir: Path | None = None) -> Spec:
   root = ET.fromstring(xml)
   if root.tag != "mujoco":
     raise ValueError("root element must be <mujoco>")
@@ -677,6 +772,27 @@ def _parse_mjcf(xml: str) -> Spec:
                       "keyframe", "visual", "statistic", "size"):
       raise NotImplementedError(
         f"<{ch.tag}> is outside the MJCF subset of the hot path (no tendons, equalities, MJCF sensors, ...)")
+  meshdir = comp.get("meshdir", comp.get("assetdir", "")) if comp is not None else ""
+  for asset in root.findall("asset"):
+    for a in asset:
+      if a.tag == "mesh":
+        at = dfl.attrs("mesh", a.get("class"), a.attrib)
+        f = at.get("file")
+        name = at.get("name") or (Path(f).stem if f else "")
+        if f is not None:
+          f = str((asset_dir if asset_dir is not None else Path(".")) / meshdir / f)
+        spec.add_mesh(name, vertex=_vec(at["vertex"]) if "vertex" in at else None,
+                      face=_vec(at["face"]) if "face" in at else None, file=f, scale=_vec(at.get("scale"), 3, [1, 1, 1]))
+      elif a.tag == "hfield":
+        if a.get("file") is not None:
+          raise NotImplementedError("<hfield file=...> (PNG / custom binary) is not supported: give nrow, ncol and elevation")
+        nrow, ncol = int(a.get("nrow")), int(a.get("ncol"))
+        elev = _vec(a.get("elevation"), nrow * ncol) if a.get("elevation") is not None else np.zeros(nrow * ncol)
+        # MJCF lists the elevation rows top to bottom (image convention); mjModel.hfield_data stores row 0 at -y
+        elev = elev.reshape(nrow, ncol)[::-1]
+        lo, hi = float(elev.min()), float(elev.max())
+        elev = (elev - lo) / (hi - lo) if hi > lo else np.zeros_like(elev)
+        spec.add_hfield(a.get("name", ""), _vec(a.get("size"), 4), nrow, ncol, elev)
   wb = root.find("worldbody")
   if wb is not None:
     _parse_body(wb, spec.worldbody, dfl, None, scale)

@@ -616,6 +616,44 @@ __device__ __noinline__ int box_box(RawCon* c, float margin, const float* x1, co
   }
   return nc;
 }
+// ---- mesh / height-field pairs: convex routines of b2_convex.h (GJK / EPA, single source with the oracle) ----
+#define B2C_REAL float
+#define B2C_FN __device__ __noinline__
+#define B2C_INL __device__ __forceinline__
+#define B2C_SQRT sqrtf
+#include "b2_convex.h"
+// a, b: pose records (pos[3], mat[9], rbound, margin) of geoms g1, g2 with type(g1) <= type(g2)
+__device__ __noinline__ int convex_narrowphase(RawCon* rc, float margin, const DevModel& m, int g1, int g2,
+                                               const float* a, const float* b, const float* s1, const float* s2) {
+  const int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
+  B2CCon cc[B2C_MAXOUT];
+  B2CShape A, B;
+  const float* v2 = nullptr; int n2 = 0;
+  if (t2 == G_MESH) { int id = m.geom_dataid[g2]; v2 = m.mesh_vert + 3 * m.mesh_vertadr[id]; n2 = m.mesh_vertnum[id]; }
+  const float r2 = b2c_shape(&B, t2, b, b + 3, s2, v2, n2);
+  int n = 0;
+  if (t1 == G_PLANE) {
+    float pn[3] = {a[3 + 2], a[3 + 5], a[3 + 8]};
+    n = b2c_plane_mesh(cc, margin, a, pn, &B);
+  } else if (t1 == G_HFIELD) {
+    if (t2 != G_HFIELD) {
+      int id = m.geom_dataid[g1];
+      n = b2c_hfield(cc, margin, a, a + 3, m.hfield_size + 4 * id, m.hfield_nrow[id], m.hfield_ncol[id],
+                     m.hfield_data + m.hfield_adr[id], &B, r2, b, b[12]);
+    }
+  } else {
+    const float* v1 = nullptr; int n1 = 0;
+    if (t1 == G_MESH) { int id = m.geom_dataid[g1]; v1 = m.mesh_vert + 3 * m.mesh_vertadr[id]; n1 = m.mesh_vertnum[id]; }
+    const float r1 = b2c_shape(&A, t1, a, a + 3, s1, v1, n1);
+    n = b2c_pair(cc, margin, &A, r1, &B, r2, a, b, a[12] + b[12]);
+  }
+  for (int i = 0; i < n; i++) {
+    rc[i].dist = cc[i].dist;
+    for (int k = 0; k < 3; k++) { rc[i].pos[k] = cc[i].pos[k]; rc[i].n[k] = cc[i].n[k]; rc[i].yh[k] = 0.f; }
+  }
+  return n;
+}
+
 __device__ __forceinline__ void make_frame(float* f /*9: n, yhint -> n,t1,t2*/) {
   normalize3(f);
   if (sqrtf(dot3(f + 3, f + 3)) < 0.5f) {
@@ -1442,7 +1480,9 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
         margin = fmaxf(gmar[g1], gmar[g2]);
         const float* s1 = gsize + 3 * g1; const float* s2 = gsize + 3 * g2;
-        if (t1 == G_PLANE) {
+        if (t2 == G_MESH || t1 == G_HFIELD) {
+          n = convex_narrowphase(rc, margin, m, g1, g2, a, b, s1, s2);
+        } else if (t1 == G_PLANE) {
           float pn[3] = {a[3 + 2], a[3 + 5], a[3 + 8]};
           if (t2 == G_SPHERE) n = plane_sphere(rc[0], margin, a, pn, b, s2[0]);
           else if (t2 == G_CAPSULE) {

@@ -14,7 +14,7 @@
 
 enum { JNT_FREE = 0, JNT_BALL = 1, JNT_SLIDE = 2, JNT_HINGE = 3 };
 #define GP 15  // shared-memory collision pose records: pos[3], mat[9], rbound, margin (+1 pad: odd stride)
-enum { G_PLANE = 0, G_SPHERE = 2, G_CAPSULE = 3, G_BOX = 6, G_MESH = 7 };
+enum { G_PLANE = 0, G_HFIELD = 1, G_SPHERE = 2, G_CAPSULE = 3, G_BOX = 6, G_MESH = 7 };
 enum { OBJ_BODY = 1, OBJ_XBODY = 2, OBJ_GEOM = 5 };
 enum { INT_EULER = 0, INT_IMPLICITFAST = 3 };
 enum { SOL_PGS_ = 0, SOL_CG_ = 1, SOL_NEWTON_ = 2 };
@@ -98,6 +98,9 @@ struct DevModel {
   const int *dyn_cgeom;    // dynamic collision geoms that visit the grid
   const int *static_geom, *static_cell0, *grid_start, *grid_items;
   const float* static_pose;  // 16 floats per static geom: pos[3], mat[9], rbound, pad[3] (world 0's model values)
+  // mesh / height-field assets (b2_convex.h): geom_dataid -> mesh or hfield id; shared by all worlds
+  const int *geom_dataid, *mesh_vertadr, *mesh_vertnum, *hfield_adr, *hfield_nrow, *hfield_ncol;
+  const float *mesh_vert, *hfield_size, *hfield_data;
   const int *sensor_objtype, *sensor_objid, *sensor_reftype, *sensor_refid, *sensor_intprm;
   const int *sensor_adr, *sensor_dim;
   // bottom-up (leaves first) blocked L^T D L: trailing-update schedules, one word per target entry

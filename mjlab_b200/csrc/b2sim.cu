@@ -538,12 +538,29 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
   {  // every collision pair must have a narrowphase routine (plane/sphere/capsule/box primitives only)
     const std::vector<int>& gt = s->mi["geom_type"];
     auto prim = [](int t) { return t == G_SPHERE || t == G_CAPSULE || t == G_BOX; };
+    auto conv = [&](int t) { return prim(t) || t == G_MESH; };  // shapes the GJK/EPA routine takes (b2_convex.h)
+    const std::vector<int>& did = s->mi["geom_dataid"];
+    const int nmesh = (int)s->mi["mesh_vertnum"].size(), nhf = (int)s->mi["hfield_nrow"].size();
     for (int p = 0; p < m.npair; p++) {
-      int t1 = gt[s->mi["pair_geom1"][p]], t2 = gt[s->mi["pair_geom2"][p]];
-      bool ok = (t1 == G_PLANE && prim(t2)) || (prim(t1) && prim(t2) && t1 <= t2);
+      int g1 = s->mi["pair_geom1"][p], g2 = s->mi["pair_geom2"][p];
+      int t1 = gt[g1], t2 = gt[g2];
+      bool ok = (t1 == G_PLANE && conv(t2)) || (t1 == G_HFIELD && conv(t2)) || (conv(t1) && conv(t2) && t1 <= t2);
       if (!ok) { delete s; return fail("b2_create: collision pair with an unsupported geom type combination"); }
+      for (int g : {g1, g2}) {
+        int t = gt[g];
+        if (t != G_MESH && t != G_HFIELD) continue;
+        int id = g < (int)did.size() ? did[g] : -1;
+        if (id < 0 || id >= (t == G_MESH ? nmesh : nhf)) { delete s; return fail("b2_create: colliding mesh / hfield geom without asset data (geom_dataid)"); }
+        if (t == G_MESH && (s->mi["mesh_vertnum"][id] < 1 || (size_t)3 * (s->mi["mesh_vertadr"][id] + s->mi["mesh_vertnum"][id]) > s->mf["mesh_vert"].size())) {
+          delete s; return fail("b2_create: mesh vertex range outside mesh_vert");
+        }
+        if (t == G_HFIELD && (s->mi["hfield_nrow"][id] < 2 || s->mi["hfield_ncol"][id] < 2 || (size_t)4 * (id + 1) > s->mf["hfield_size"].size() ||
+                              (size_t)s->mi["hfield_adr"][id] + (size_t)s->mi["hfield_nrow"][id] * s->mi["hfield_ncol"][id] > s->mf["hfield_data"].size())) {
+          delete s; return fail("b2_create: hfield sample range outside hfield_data");
+        }
+      }
     }
-    for (int g : s->mi["dyn_cgeom"]) if (!prim(gt[g])) { delete s; return fail("b2_create: unsupported dynamic geom type for the static grid"); }
+    for (int g : s->mi["dyn_cgeom"]) if (!conv(gt[g])) { delete s; return fail("b2_create: unsupported dynamic geom type for the static grid"); }
     for (int g : s->mi["static_geom"]) if (!prim(gt[g])) { delete s; return fail("b2_create: unsupported grid-static geom type"); }
   }
   int rc = 0;
@@ -560,6 +577,8 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
   UPI(geom_contype, "geom_contype"); UPI(geom_conaffinity, "geom_conaffinity"); UPI(dyn_cgeom, "dyn_cgeom");
   UPI(static_geom, "static_geom"); UPI(static_cell0, "static_cell0"); UPI(grid_start, "grid_start");
   UPI(grid_items, "grid_items");
+  UPI(geom_dataid, "geom_dataid"); UPI(mesh_vertadr, "mesh_vertadr"); UPI(mesh_vertnum, "mesh_vertnum");
+  UPI(hfield_adr, "hfield_adr"); UPI(hfield_nrow, "hfield_nrow"); UPI(hfield_ncol, "hfield_ncol");
   UPI(sensor_objid, "sensor_objid"); UPI(sensor_reftype, "sensor_reftype");
   UPI(sensor_refid, "sensor_refid"); UPI(sensor_intprm, "sensor_intprm"); UPI(sensor_adr, "sensor_adr");
   UPI(sensor_dim, "sensor_dim");
@@ -574,6 +593,12 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
     const float* kr = nullptr;
     rc |= dev_upload<float>(s, kinrec, &kr);
     m.kinrec = (const float4*)kr;
+  }
+  for (auto kv : {std::make_pair("mesh_vert", &m.mesh_vert), std::make_pair("hfield_size", &m.hfield_size),
+                  std::make_pair("hfield_data", &m.hfield_data)}) {
+    const std::vector<double>& h = s->mf[kv.first];
+    std::vector<float> hf(h.begin(), h.end());
+    rc |= dev_upload<float>(s, hf, kv.second);
   }
   rc |= dev_upload<int>(s, posegeom, &m.posegeom);
   rc |= dev_upload<float>(s, static_pose, &m.static_pose);

@@ -7,7 +7,7 @@ from pathlib import Path
 
 import numpy as np
 
-from mjlab_b200.compiler.compile import MODEL_ARRAYS, MODEL_SCALARS_F, MODEL_SCALARS_I
+from mjlab_b200.compiler.compile import MODEL_ARRAYS, MODEL_SCALARS_F, MODEL_SCALARS_I, fill_asset_defaults
 
 import os
 
@@ -59,6 +59,7 @@ def make_model_desc(model):
   """Pack a compiled Model into a B2ModelDesc. Returns (desc, keepalive)."""
   keep = []
   names = [n for n, _ in MODEL_ARRAYS] + MODEL_SCALARS_I + MODEL_SCALARS_F
+  fill_asset_defaults(model.arrays)
   arrs = (B2Array * len(names))()
   for i, n in enumerate(names):
     a = np.asarray(model.arrays[n])

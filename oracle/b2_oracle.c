@@ -37,7 +37,7 @@ typedef double real;
 #define MAXIMP ((real)0.9999)
 #define MINMU ((real)1e-5)
 enum { JNT_FREE = 0, JNT_BALL = 1, JNT_SLIDE = 2, JNT_HINGE = 3 };
-enum { G_PLANE = 0, G_SPHERE = 2, G_CAPSULE = 3, G_BOX = 6 };
+enum { G_PLANE = 0, G_HFIELD = 1, G_SPHERE = 2, G_CAPSULE = 3, G_BOX = 6, G_MESH = 7 };
 enum { OBJ_BODY = 1, OBJ_XBODY = 2, OBJ_GEOM = 5 };
 enum { INT_EULER = 0, INT_IMPLICITFAST = 3 };
 enum { EFC_LIMIT = 3, EFC_FRICTIONLESS = 4, EFC_PYRAMIDAL = 5 };
@@ -52,7 +52,8 @@ enum { EFC_LIMIT = 3, EFC_FRICTIONLESS = 4, EFC_PYRAMIDAL = 5 };
   X(geom_priority) X(site_bodyid) X(actuator_trnid) X(actuator_ctrllimited)                     \
   X(actuator_forcelimited) X(pair_geom1) X(pair_geom2) X(sensor_type) X(sensor_objtype)         \
   X(sensor_objid) X(sensor_reftype) X(sensor_refid) X(sensor_intprm) X(sensor_adr) X(sensor_dim)          \
-  X(geom_contype) X(geom_conaffinity) X(static_geom) X(static_cell0) X(dyn_cgeom) X(grid_start) X(grid_items)
+  X(geom_contype) X(geom_conaffinity) X(static_geom) X(static_cell0) X(dyn_cgeom) X(grid_start) X(grid_items) \
+  X(geom_dataid) X(mesh_vertadr) X(mesh_vertnum) X(hfield_adr) X(hfield_nrow) X(hfield_ncol)
 
 /* float model arrays: (name, row length per element group) — all expandable per world */
 #define MODEL_REAL(X)                                                                           \
@@ -62,7 +63,8 @@ enum { EFC_LIMIT = 3, EFC_FRICTIONLESS = 4, EFC_PYRAMIDAL = 5 };
   X(dof_frictionloss) X(dof_invweight0) X(geom_size) X(geom_pos) X(geom_quat) X(geom_friction)  \
   X(geom_solref) X(geom_solimp) X(geom_solmix) X(geom_margin) X(geom_gap) X(geom_rbound)        \
   X(geom_rgba) X(site_pos) X(site_quat) X(actuator_gainprm) X(actuator_biasprm)                 \
-  X(actuator_ctrlrange) X(actuator_forcerange) X(actuator_gear) X(qpos0)
+  X(actuator_ctrlrange) X(actuator_forcerange) X(actuator_gear) X(qpos0)                        \
+  X(mesh_vert) X(hfield_size) X(hfield_data)
 
 typedef struct { real* p; int n; int stride; } MF; /* stride 0 = shared by all worlds */
 
@@ -460,6 +462,21 @@ static void jac_point(const W* d, real* jacp, real* jacr, const real* point, int
  * ------------------------------------------------------------------------------------------- */
 typedef struct { real dist, pos[3], frame[9]; } RawCon;
 
+/* mesh / height-field narrowphase: the product's single-source routines (mjlab_b200/csrc/b2_convex.h) compiled
+ * in this file's precision; pinned independently in tests/test_convex.py (see that header's note) */
+#define B2C_REAL real
+#define B2C_FN static
+#define B2C_INL static inline
+#define B2C_SQRT sqrt
+#include "../mjlab_b200/csrc/b2_convex.h"
+static int from_b2c(RawCon* rc, const B2CCon* c, int n) {
+  for (int i = 0; i < n; i++) {
+    rc[i].dist = c[i].dist;
+    for (int k = 0; k < 3; k++) { rc[i].pos[k] = c[i].pos[k]; rc[i].frame[k] = c[i].n[k]; rc[i].frame[3+k] = 0; }
+  }
+  return n;
+}
+
 static int sphere_sphere(RawCon* c, real margin, const real* p1, real r1, const real* p2, real r2) {
   real dif[3] = { p2[0]-p1[0], p2[1]-p1[1], p2[2]-p1[2] };
   real cd = norm3(dif);
@@ -845,6 +862,28 @@ static int narrowphase(const W* d, RawCon* rc, int g1, int g2, real margin) {
   if (t1 == G_SPHERE && t2 == G_BOX) return sphere_box(rc, margin, p1, s1[0], p2, m2, s2);
   if (t1 == G_CAPSULE && t2 == G_BOX) return capsule_box(rc, margin, p1, m1, s1, p2, m2, s2);
   if (t1 == G_BOX && t2 == G_BOX) return box_box(rc, margin, p1, m1, s1, p2, m2, s2);
+  if (t2 == G_MESH || t1 == G_HFIELD) {  /* convex routines (b2_convex.h) */
+    const real* rb = M_(o, geom_rbound, w);
+    B2CCon cc[B2C_MAXOUT];
+    B2CShape A, B;
+    const real* v2 = NULL; int n2 = 0;
+    if (t2 == G_MESH) { int id = o->geom_dataid[g2]; v2 = o->mesh_vert.p + 3*o->mesh_vertadr[id]; n2 = o->mesh_vertnum[id]; }
+    real r2 = b2c_shape(&B, t2, p2, m2, s2, v2, n2);
+    if (t1 == G_PLANE) {
+      real pn[3] = { m1[2], m1[5], m1[8] };
+      return from_b2c(rc, cc, b2c_plane_mesh(cc, margin, p1, pn, &B));
+    }
+    if (t1 == G_HFIELD) {
+      if (t2 == G_HFIELD) return 0;
+      int id = o->geom_dataid[g1];
+      return from_b2c(rc, cc, b2c_hfield(cc, margin, p1, m1, o->hfield_size.p + 4*id, o->hfield_nrow[id], o->hfield_ncol[id],
+                                         o->hfield_data.p + o->hfield_adr[id], &B, r2, p2, rb[g2]));
+    }
+    const real* v1 = NULL; int n1 = 0;
+    if (t1 == G_MESH) { int id = o->geom_dataid[g1]; v1 = o->mesh_vert.p + 3*o->mesh_vertadr[id]; n1 = o->mesh_vertnum[id]; }
+    real r1 = b2c_shape(&A, t1, p1, m1, s1, v1, n1);
+    return from_b2c(rc, cc, b2c_pair(cc, margin, &A, r1, &B, r2, p1, p2, rb[g1] + rb[g2]));
+  }
   return 0;
 }
 
@@ -1587,4 +1626,29 @@ int b2o_prim_box_box(const real* p1, const real* m1, const real* h1, const real*
                      real margin, real* out) {
   RawCon c[8];
   return prim_out(c, box_box(c, margin, p1, m1, h1, p2, m2, h2), out);
+}
+/* convex routines: shapes given as (MuJoCo geom type, pos, mat, size, verts, nvert) */
+int b2o_prim_convex(int t1, const real* p1, const real* m1, const real* s1, const real* v1, int n1,
+                    int t2, const real* p2, const real* m2, const real* s2, const real* v2, int n2,
+                    real margin, real scale, real* out) {
+  B2CShape A, B; B2CCon c[1];
+  real r1 = b2c_shape(&A, t1, p1, m1, s1, v1, n1), r2 = b2c_shape(&B, t2, p2, m2, s2, v2, n2);
+  int n = b2c_pair(c, margin, &A, r1, &B, r2, p1, p2, scale);
+  RawCon rc[1];
+  return prim_out(rc, from_b2c(rc, c, n), out);
+}
+int b2o_prim_plane_mesh(const real* pp, const real* pn, const real* p2, const real* m2, const real* v2, int n2,
+                        real margin, real* out) {
+  B2CShape B; B2CCon c[4]; real sz[3] = {0, 0, 0};
+  b2c_shape(&B, G_MESH, p2, m2, sz, v2, n2);
+  RawCon rc[4];
+  return prim_out(rc, from_b2c(rc, c, b2c_plane_mesh(c, margin, pp, pn, &B)), out);
+}
+int b2o_prim_hfield(const real* hp, const real* hm, const real* hsize, int nrow, int ncol, const real* hdata,
+                    int t2, const real* p2, const real* m2, const real* s2, const real* v2, int n2, real rbound,
+                    real margin, real* out) {
+  B2CShape B; B2CCon c[B2C_MAXOUT];
+  real r2 = b2c_shape(&B, t2, p2, m2, s2, v2, n2);
+  RawCon rc[B2C_MAXOUT];
+  return prim_out(rc, from_b2c(rc, c, b2c_hfield(c, margin, hp, hm, hsize, nrow, ncol, hdata, &B, r2, p2, rbound)), out);
 }
