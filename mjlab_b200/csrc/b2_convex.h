@@ -469,7 +469,8 @@ B2C_FN int b2c_hfield(B2CCon* out, b2c_real margin, const b2c_real* hp, const b2
   if (c[1] - reach + hsize[1] < 0) r0 = 0;
   if (c1 > ncol - 2) c1 = ncol - 2;
   if (r1 > nrow - 2) r1 = nrow - 2;
-  int n = 0;
+  int n = 0, seq = 0;
+  int order[B2C_MAXOUT];  // prism sequence number of each kept contact: the output is in grid order whatever was evicted
   B2CShape P;
   P.type = B2C_PRISM; P.nvert = 6; P.pos = hp; P.mat = hR; P.size = hsize; P.vert = hdata;
   const b2c_real scale = rbound + dx + dy;
@@ -494,15 +495,22 @@ B2C_FN int b2c_hfield(B2CCon* out, b2c_real margin, const b2c_real* hp, const b2
           }
         }
         B2CCon cn;
+        seq++;
         if (!b2c_pair(&cn, margin, &P, 0, G, rg, pc, gc, scale)) continue;
-        if (n < B2C_MAXOUT) out[n++] = cn;
+        if (n < B2C_MAXOUT) { order[n] = seq; out[n++] = cn; }
         else {
           int worst = 0;
           for (int i = 1; i < n; i++) if (out[i].dist > out[worst].dist) worst = i;
-          if (cn.dist < out[worst].dist) out[worst] = cn;
+          if (cn.dist < out[worst].dist) { out[worst] = cn; order[worst] = seq; }
         }
       }
     }
+  for (int a = 1; a < n; a++) {  // back to grid order (insertion sort, n <= 8)
+    B2CCon cv = out[a];
+    int ov = order[a], b = a - 1;
+    while (b >= 0 && order[b] > ov) { out[b + 1] = out[b]; order[b + 1] = order[b]; b--; }
+    out[b + 1] = cv; order[b + 1] = ov;
+  }
   return n;
 }
 

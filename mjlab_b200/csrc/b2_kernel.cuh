@@ -750,10 +750,14 @@ __device__ __noinline__ float rows_cost(int fc, int fl, const float* con, const 
 // ==================================================================================================
 // The kernel
 // ==================================================================================================
-template <bool STEP>
+// MODE bit 0: integrate (step) or not (forward); bit 1: the model has mesh / height-field collision pairs.  The
+// convex routines are ~120 KB of code: models without such pairs (BASELINE configs A-E) run the instantiation
+// that does not contain them (measured: their presence alone costs 2 % of the G1 step through code layout).
+template <int MODE>
 __global__ void __launch_bounds__(32 * B2_WARPS_PER_CTA, B2_MIN_CTAS)
 b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevData dd) {
   using namespace b2;
+  constexpr bool STEP = (MODE & 1) != 0, CVX = (MODE & 2) != 0;
 #ifdef B2_HOST_EMULATION
   float* smem_all = (float*)warp_emul::ctx().dyn_smem;
 #else
@@ -1480,7 +1484,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
         margin = fmaxf(gmar[g1], gmar[g2]);
         const float* s1 = gsize + 3 * g1; const float* s2 = gsize + 3 * g2;
-        if (t2 == G_MESH || t1 == G_HFIELD) {
+        if (CVX && (t2 == G_MESH || t1 == G_HFIELD)) {
           n = convex_narrowphase(rc, margin, m, g1, g2, a, b, s1, s2);
         } else if (t1 == G_PLANE) {
           float pn[3] = {a[3 + 2], a[3 + 5], a[3 + 8]};
@@ -1795,7 +1799,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   PHASE_MARK(8);
   PSYNC();
   // ---------------- phase 8: Newton solver (primal, exact line search) ----------------------------
-  int niter = 0;
+  int niter = 0, nls = 0;
   float cost = 0.f;
   const float* Mr = reduced ? Mred : Mq;  // reduced problem: Schur complement of M on the leading block
   const float* qs = qfrc_smooth;
@@ -1808,6 +1812,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   // phase 7 left in H - on a reduced problem its leading block is the factor of the Schur complement).  The
   // Hessian scratch is unused, so its weight region holds the direction and the previous (grad, M^-1 grad).
   const bool cg = m.solver == SOL_CG_;
+  const bool ls_relstep = (m.debug & 8) != 0;
   float* search = cg ? gW : s + L.search;  // Newton: search = -grad in place
   float* cgM = gW + pad4i(nv); float* cgG0 = gW + 2 * pad4i(nv); float* cgM0 = gW + 3 * pad4i(nv);
   bool refine = false;  // active set unchanged: the Hessian factor of the previous iteration is still valid
@@ -2138,6 +2143,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         }
         d0 = wsum(a0) + g1 + 2.f * al * g2;
         d1 = fmaxf(wsum(a1) + 2.f * g2, MINVAL);
+        nls++;
       };
       PHASE_MARK(15);
       float alpha = 0.f, d0, d1;
@@ -2153,6 +2159,10 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
           float nxt = alpha - d0 / d1;
           if (hi_a >= 0.f && !(nxt > lo_a && nxt < hi_a)) nxt = 0.5f * (lo_a + hi_a);
           if (nxt == alpha) break;
+          // The derivative is piecewise linear: a Newton step taken inside the root's piece lands on the root, and
+          // the next evaluation returns fp32 noise, never |d0| < gtol (gtol ~ 1e-8 |search|).  A step below a few
+          // ulp of alpha is that situation: take it and stop instead of dithering until the bracket collapses.
+          if (ls_relstep && fabsf(nxt - alpha) <= 4e-7f * fabsf(alpha)) { alpha = nxt; break; }
           alpha = nxt;
         }
       }
@@ -2388,6 +2398,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       dd.nefc.p[(size_t)w * dd.nefc.stride] = nefc;
       dd.solver_niter.p[(size_t)w * dd.solver_niter.stride] = niter;
       dd.solver_nd.p[(size_t)w * dd.solver_nd.stride] = nefc > 0 ? n : 0;  // size of the block the solver worked on
+      dd.solver_nls.p[(size_t)w * dd.solver_nls.stride] = nls;
       dd.overflow.p[(size_t)w * dd.overflow.stride] = overflow;
       dd.solver_cost.p[(size_t)w * dd.solver_cost.stride] = cost;
     }

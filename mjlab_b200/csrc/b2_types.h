@@ -130,7 +130,7 @@ struct DevData {
   DArr link_vel_w, com_vel_w, link_state_b;  // per body: EntityData's derived velocities / body-frame state
   DArr qfrc_bias, qfrc_smooth, qacc_smooth, qfrc_constraint, qM;
   DArr contact_dist, contact_pos, contact_frame, contact_force, solver_cost;
-  IArr ncon, nefc, solver_niter, contact_geom, overflow, solver_nd;
+  IArr ncon, nefc, solver_niter, contact_geom, overflow, solver_nd, solver_nls;
   int emit;                         // write consumer-visible kinematics (0 for all but the last sub-step of a decimation loop)
   int phase_sync;                   // CTA barriers at phase boundaries (every warp of the launch owns an environment)
   int* ticket;                      // optional: work queue of launch slots (one atomic per environment)

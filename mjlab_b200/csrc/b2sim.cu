@@ -63,6 +63,7 @@ struct b2_sim {
   int split_streams = 2;       // b2_step_n runs this many env partitions on internal streams
   int reorder_every_substep = 1;  // heavy-first order recomputed before every sub-step (measured 447 vs 462 us: fresh Newton counts keep phase-synchronous CTAs balanced)
   int phase_sync = 2;          // CTA barriers at phase boundaries, level 0..3 (instruction-cache locality; -14 % measured)
+  int has_convex = 0;          // the model has mesh / height-field collision pairs: kernels with the convex routines
   int work_queue = 0;          // warps pull environments from a ticket counter (persistent grid)
   int* tickets = nullptr;      // one counter per stream partition (device)
   int resident_ctas = 0;       // co-resident CTAs of the step kernel on this device
@@ -243,9 +244,11 @@ static int launch(b2_sim* s, bool step, cudaStream_t st, int nsub = 1, int base 
   s->hd.phase_sync = (!queue && s->hd.world_mask == nullptr && count % B2_WARPS_PER_CTA == 0) ? s->phase_sync : 0;
   if (queue) grid = s->resident_ctas;
   if (step)
-    b2_step_kernel<true><<<grid, 32 * B2_WARPS_PER_CTA, s->smem_bytes, st>>>(s->hm, s->hd);
+    if (s->has_convex) b2_step_kernel<3><<<grid, 32 * B2_WARPS_PER_CTA, s->smem_bytes, st>>>(s->hm, s->hd);
+    else b2_step_kernel<1><<<grid, 32 * B2_WARPS_PER_CTA, s->smem_bytes, st>>>(s->hm, s->hd);
   else
-    b2_step_kernel<false><<<grid, 32 * B2_WARPS_PER_CTA, s->smem_bytes, st>>>(s->hm, s->hd);
+    if (s->has_convex) b2_step_kernel<2><<<grid, 32 * B2_WARPS_PER_CTA, s->smem_bytes, st>>>(s->hm, s->hd);
+    else b2_step_kernel<0><<<grid, 32 * B2_WARPS_PER_CTA, s->smem_bytes, st>>>(s->hm, s->hd);
   s->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -545,6 +548,7 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
       int g1 = s->mi["pair_geom1"][p], g2 = s->mi["pair_geom2"][p];
       int t1 = gt[g1], t2 = gt[g2];
       bool ok = (t1 == G_PLANE && conv(t2)) || (t1 == G_HFIELD && conv(t2)) || (conv(t1) && conv(t2) && t1 <= t2);
+      if (t2 == G_MESH || t1 == G_HFIELD) s->has_convex = 1;
       if (!ok) { delete s; return fail("b2_create: collision pair with an unsupported geom type combination"); }
       for (int g : {g1, g2}) {
         int t = gt[g];
@@ -560,7 +564,10 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
         }
       }
     }
-    for (int g : s->mi["dyn_cgeom"]) if (!conv(gt[g])) { delete s; return fail("b2_create: unsupported dynamic geom type for the static grid"); }
+    for (int g : s->mi["dyn_cgeom"]) {
+      if (!conv(gt[g])) { delete s; return fail("b2_create: unsupported dynamic geom type for the static grid"); }
+      if (gt[g] == G_MESH) s->has_convex = 1;
+    }
     for (int g : s->mi["static_geom"]) if (!prim(gt[g])) { delete s; return fail("b2_create: unsupported grid-static geom type"); }
   }
   int rc = 0;
@@ -696,6 +703,7 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
   rc |= add_idata(s, "contact_geom", &d.contact_geom, 2 * mc, 2);
   rc |= add_idata(s, "overflow", &d.overflow, 1);
   rc |= add_idata(s, "solver_nd", &d.solver_nd, 1);
+  rc |= add_idata(s, "solver_nls", &d.solver_nls, 1);  // line-search derivative evaluations of the last step (diagnostic)
   if (rc) { b2_destroy(s); return 1; }
   // time is exposed as a 1-D (nworld,) tensor
   for (Field& f : s->data_fields)
@@ -754,8 +762,10 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
     // larger sim in the same process keeps launching after a smaller one is created.
     static size_t dev_max[64] = {0};
     if (s->smem_bytes > dev_max[cuda_device & 63]) {
-      cudaError_t e1 = cudaFuncSetAttribute(b2_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes);
-      cudaError_t e2 = cudaFuncSetAttribute(b2_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes);
+      cudaError_t e1 = cudaFuncSetAttribute(b2_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes);
+      cudaError_t e2 = cudaFuncSetAttribute(b2_step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes);
+      if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(b2_step_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes);
+      if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(b2_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes);
       if (e1 != cudaSuccess || e2 != cudaSuccess) {
         b2_destroy(s);
         return fail(std::string("cudaFuncSetAttribute(max dynamic smem): ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
@@ -773,7 +783,7 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
     s->tickets = (int*)p;
     cudaMemset(p, 0, sizeof(int) * 4);
     int per_sm = 0, sms = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b2_step_kernel<true>, 32 * B2_WARPS_PER_CTA, s->smem_bytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b2_step_kernel<1>, 32 * B2_WARPS_PER_CTA, s->smem_bytes);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cuda_device);
     s->resident_ctas = per_sm * sms;
     for (int h = 0; h < 4; h++) {
@@ -899,6 +909,7 @@ int b2_set_option(b2_sim* s, const char* key, double v) {
   else if (k == "phase_sync") s->phase_sync = (int)v;
   else if (k == "reorder_every_substep") s->reorder_every_substep = (int)v;
   else if (k == "full_solver") m.debug = (m.debug & ~4) | ((int)v ? 4 : 0);  // Newton on all dofs even when a leading block suffices (tests, A/B)
+  else if (k == "ls_relstep") m.debug = (m.debug & ~8) | ((int)v ? 8 : 0);  // line search stops on a relative step of a few ulp
   else return fail("b2_set_option: unknown option '" + k + "'");
   return 0;
 }

@@ -32,7 +32,7 @@ names = {"after mark 0": "1 kinematics", "after mark 1": "1b geom/site poses", "
          "after mark 9": "9 contact forces / sensors", "after mark 10": "10 integrate", "after mark 11": "11 stores"}
 marks.sort()
 out = subprocess.run([sys.executable, os.path.join(root, "tools", "ncu_by_line.py"), sys.argv[1],
-                      sys.argv[2] if len(sys.argv) > 2 else "b2_step_kernelILb1", "100000"],
+                      sys.argv[2] if len(sys.argv) > 2 else "b2_step_kernelILi1", "100000"],
                      capture_output=True, text=True).stdout
 tot = {}
 for line in out.splitlines():

@@ -34,7 +34,8 @@ def run(label, opts, k=12):
     a.record(); sim.step_n(4); b.record(); torch.cuda.synchronize()
     tot += a.elapsed_time(b)
   st = sim.stats()
-  print(f"{label:44s} {tot / k / 4 * 1e3:8.1f} us/sub-step   ncon {st.ncon_mean:.1f} iters {st.niter_mean:.2f}")
+  nls = sim.data.solver_nls[:].float().mean().item() if hasattr(sim.data, "solver_nls") else float("nan")
+  print(f"{label:44s} {tot / k / 4 * 1e3:8.1f} us/sub-step   ncon {st.ncon_mean:.1f} iters {st.niter_mean:.2f}  ls evals {nls:.2f}")
 
 base = dict(full_solver=0, work_queue=0, split_streams=2, phase_sync=2, reorder_every_substep=1)
 run("default: 2 streams", base)
@@ -43,3 +44,5 @@ run("3 streams", dict(base, split_streams=3))
 run("4 streams", dict(base, split_streams=4))
 run("2 streams, psync off", dict(base, phase_sync=0))
 run("2 streams, full solver", dict(base, full_solver=1))
+run("2 streams, ls_relstep", dict(base, ls_relstep=1))
+run("default again", dict(base, ls_relstep=0))
