@@ -473,7 +473,7 @@ B2C_FN int b2c_hfield(B2CCon* out, b2c_real margin, const b2c_real* hp, const b2
   int order[B2C_MAXOUT];  // prism sequence number of each kept contact: the output is in grid order whatever was evicted
   B2CShape P;
   P.type = B2C_PRISM; P.nvert = 6; P.pos = hp; P.mat = hR; P.size = hsize; P.vert = hdata;
-  const b2c_real scale = rbound + dx + dy;
+  const b2c_real scale = rbound + dx + dy, tie = (b2c_real)1e-5 * scale;
   for (int r = r0; r <= r1; r++)
     for (int cc = c0; cc <= c1; cc++) {
       const b2c_real z00 = hdata[r * ncol + cc] * hsize[2], z01 = hdata[r * ncol + cc + 1] * hsize[2];
@@ -499,9 +499,13 @@ B2C_FN int b2c_hfield(B2CCon* out, b2c_real margin, const b2c_real* hp, const b2
         if (!b2c_pair(&cn, margin, &P, 0, G, rg, pc, gc, scale)) continue;
         if (n < B2C_MAXOUT) { order[n] = seq; out[n++] = cn; }
         else {
-          int worst = 0;
-          for (int i = 1; i < n; i++) if (out[i].dist > out[worst].dist) worst = i;
-          if (cn.dist < out[worst].dist) { out[worst] = cn; order[worst] = seq; }
+          // evict the shallowest; neighbouring prisms often report the same contact, so depths within `tie` count
+          // as equal and the later prism goes (the choice must not hinge on the last bit of a depth)
+          b2c_real dmax = out[0].dist;
+          for (int i = 1; i < n; i++) if (out[i].dist > dmax) dmax = out[i].dist;
+          int worst = -1;
+          for (int i = 0; i < n; i++) if (out[i].dist >= dmax - tie && (worst < 0 || order[i] > order[worst])) worst = i;
+          if (cn.dist < dmax - tie) { out[worst] = cn; order[worst] = seq; }
         }
       }
     }

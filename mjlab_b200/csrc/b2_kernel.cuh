@@ -310,16 +310,19 @@ __device__ __noinline__ void ldl_solve(const float* L, const float* invdiag, flo
     x0 -= L[rk + lane] * yk;
   }
   int rk = n0 * (n0 - 1) >> 1;  // tri(n0 - 1, 0)
-  // (unrolled so that the loads of four steps are in flight while the shuffle/FMA chain advances)
-#pragma unroll 1
+  // Pivot k's contribution is A[k,lane] * (u_k / d_k): lane k holds 1/d_k in a register and its u_k is final once
+  // the pivots above it are done, so the product is formed there and shuffled (no load of invdiag[k] per step).
+  // Unrolled by four: the kernel is issue bound and the loop control was a third of the sweep's instructions.
+#pragma unroll 4
   for (int k = n0 - 1; k >= 0; k--) {
-    float t = lane < k ? L[rk + lane] * invdiag[k] : 0.f;
-    x0 = fmaf(-t, __shfl_sync(FULL, x0, k), x0);
+    const float yk = __shfl_sync(FULL, x0 * d0, k);
+    const float l = lane < k ? L[rk + lane] : 0.f;
+    x0 = fmaf(-l, yk, x0);
     rk -= k;
   }
   x0 *= d0; x1 *= d1;  // D z = y
   // L x = z: x_k = z_k - (1/d_k) sum_{j<k} A[k,j] x_j, columns in ascending order (lane = row)
-#pragma unroll 1
+#pragma unroll 4
   for (int j = 0; j < n0; j++) {
     float t = (lane > j && lane < n0) ? L[r0 + j] * d0 : 0.f;
     x0 = fmaf(-t, __shfl_sync(FULL, x0, j), x0);
@@ -681,11 +684,19 @@ __device__ __noinline__ void mulJ(const float* x, int dstc, int dstl, bool accum
       unsigned long long m2 = dofmask[key >> 8];
       unsigned long long mk = dofmask[key & 0xff] ^ m2;
       float acc = 0.f;
-      while (mk) {
-        int d = __ffsll((long long)mk) - 1;
-        mk &= mk - 1;
-        float v = cdof[SD * d + comp] * x[d];
-        acc += (m2 >> d & 1ull) ? v : -v;
+      // (the two 32-bit halves separately: 64-bit find-first-set / shifts cost twice the instructions)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        unsigned wd = h ? (unsigned)(mk >> 32) : (unsigned)mk;
+        const unsigned sg = h ? (unsigned)(m2 >> 32) : (unsigned)m2;
+        const float* cd = cdof + SD * 32 * h + comp;
+        const float* xx = x + 32 * h;
+        while (wd) {
+          int d = __ffs((int)wd) - 1;
+          wd &= wd - 1u;
+          float v = cd[SD * d] * xx[d];
+          acc += (sg >> d & 1u) ? v : -v;
+        }
       }
       gV[6 * g + comp] = acc;
     }
@@ -2098,31 +2109,31 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       if (sn < MINVAL) { run = false; break; }
       float gtol = m.tolerance * m.ls_tolerance * sn / scale;
       // each lane keeps its rows in registers for the whole search (<= 2 contacts + 1 limit per lane)
-      float lsD[3], lsJ[9], lsV[9];
+      float lsJ[9], lsV[9], lsDV[9];  // residual, its slope, and D * slope per row
 #pragma unroll
       for (int q = 0; q < 2; q++) {
         int c = lane + 32 * q;
         bool ok = c < ncon;
-        lsD[q] = ok ? con[CD * MC + c] : 0.f;
+        const float D = ok ? con[CD * MC + c] : 0.f;
 #pragma unroll
         for (int r = 0; r < 4; r++) {
           lsJ[4 * q + r] = ok ? con[(CJAR0 + r) * MC + c] : 0.f;
           lsV[4 * q + r] = ok ? con[(CJV0 + r) * MC + c] : 0.f;
+          lsDV[4 * q + r] = D * lsV[4 * q + r];
         }
       }
       {
         bool ok = lane < nlim;
-        lsD[2] = ok ? lim[LD * NLC + lane] : 0.f;
         lsJ[8] = ok ? lim[LJAR * NLC + lane] : 0.f;
         lsV[8] = ok ? lim[LJV * NLC + lane] : 0.f;
+        lsDV[8] = ok ? lim[LD * NLC + lane] * lsV[8] : 0.f;
       }
       auto ls_eval = [&](float al, float& d0, float& d1) {
         float a0 = 0.f, a1 = 0.f;
 #pragma unroll
         for (int q = 0; q < 9; q++) {
-          float D = lsD[q < 8 ? (q >> 2) : 2];
-          float x = lsJ[q] + al * lsV[q];
-          if (x < 0.f) { a0 += D * x * lsV[q]; a1 += D * lsV[q] * lsV[q]; }
+          float x = fmaf(al, lsV[q], lsJ[q]);
+          if (x < 0.f) { a0 = fmaf(lsDV[q], x, a0); a1 = fmaf(lsDV[q], lsV[q], a1); }
         }
         // rows beyond the register window (ncon > 64 or nlim > 32)
         #pragma unroll 1

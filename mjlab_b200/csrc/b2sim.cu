@@ -403,7 +403,7 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
   if (m.nv > 64 || m.nbody > 64) { delete s; return fail("b2_create: nv and nbody must be <= 64"); }
   if (m.nv < 1) { delete s; return fail("b2_create: model has no degrees of freedom"); }
   m.integrator = geti("opt_integrator"); m.iterations = geti("opt_iterations");
-  m.ls_iterations = geti("opt_ls_iterations"); m.debug = 0;
+  m.ls_iterations = geti("opt_ls_iterations"); m.debug = 8;  // bit 3: relative-step stop of the line search (on)
   m.timestep = (float)getf("opt_timestep"); m.tolerance = (float)getf("opt_tolerance");
   m.ls_tolerance = (float)getf("opt_ls_tolerance"); m.impratio = (float)getf("opt_impratio");
   m.meaninertia = (float)getf("stat_meaninertia");

@@ -111,9 +111,11 @@ def convex_scene():
   return m, anchors, hf
 
 
-def convex_states(model, anchors, hf, n: int, seed: int):
+def convex_states(model, anchors, hf, n: int, seed: int, drop: bool = False):
   """Generic (untied) poses: every body near its anchor with a random orientation; the bodies over the height field
-  sit at the local surface height minus a small random penetration."""
+  sit at the local surface height minus a small random penetration.  ``drop``: bodies at rest, spread apart and
+  lifted clear of every surface (a settling run; the interpenetrating parity states produce impacts that spin the
+  capsules up to hundreds of rad/s, where no fixed-step integrator of free bodies is stable)."""
   rng = np.random.default_rng(seed)
   nq, nv = int(model.nq), int(model.nv)
   qpos = np.zeros((n, nq))
@@ -124,13 +126,18 @@ def convex_states(model, anchors, hf, n: int, seed: int):
   for w in range(n):
     for k, name in enumerate(names):
       p = anchors[name] + rng.normal(size=3) * np.array([0.04, 0.04, 0.02])
+      if drop and not name.startswith("h"):
+        p[0:2] = anchors[name][0:2] * 3.0
+        p[2] += 0.25
       if name.startswith("h"):
         lx, ly = p[0] - hf["pos"][0] + hf["size"][0], p[1] - hf["pos"][1] + hf["size"][1]
         c, r = int(lx / dx), int(ly / dy)
-        p[2] = hf["data"][r:r + 2, c:c + 2].mean() * hf["size"][2] + rng.uniform(0.03, 0.1)
+        p[2] = hf["data"][r:r + 2, c:c + 2].mean() * hf["size"][2] + rng.uniform(0.03, 0.1) + (0.3 if drop else 0.0)
       q = rng.normal(size=4)
       qpos[w, 7 * k:7 * k + 3] = p
       qpos[w, 7 * k + 3:7 * k + 7] = q / np.linalg.norm(q)
+  if drop:
+    qvel[:] = 0.0
   return dict(qpos=qpos, qvel=qvel, ctrl=np.zeros((n, int(model.nu))), qacc_warmstart=np.zeros((n, nv)))
 
 
