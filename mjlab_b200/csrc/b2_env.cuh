@@ -31,8 +31,18 @@ __global__ void b2_velenv_pre_kernel(DevData dd, int nu, const float* __restrict
   dd.ctrl.p[(size_t)w * dd.ctrl.stride + a] = default_joint_pos[a] + action_scale[a] * action[tid];
 }
 
+__device__ __forceinline__ float b2e_wsum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One warp per environment (a thread per environment left 4096 threads = 128 warps on 148 SMs walking ~400
+// dependent loads each: 50 us of pure latency on the critical path of every env step).  Scalar terms are computed
+// redundantly by every lane from values read before any lane writes; per-joint terms are spread over the lanes.
 __global__ void b2_velenv_post_kernel(DevData dd, int nq, int nv, int nu, B2VelEnvArgs A) {
-  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int w = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (w >= dd.nworld) return;
   float* qpos = dd.qpos.p + (size_t)w * dd.qpos.stride;
   float* qvel = dd.qvel.p + (size_t)w * dd.qvel.stride;
@@ -45,94 +55,115 @@ __global__ void b2_velenv_post_kernel(DevData dd, int nq, int nv, int nu, B2VelE
   int ep = A.episode_length[w] + 1;
   const float down[3] = {0.f, 0.f, -1.f};
   float q[4] = {qpos[3], qpos[4], qpos[5], qpos[6]}, gb[3], lb[3];
+  float c0 = cmd[0], c1 = cmd[1], c2 = cmd[2];
+  float ctl = A.cmd_time_left[w] - A.step_dt, tl = A.push_time_left[w] - A.step_dt;
+  float htarget = A.heading_target[w];
+  bool standing = A.is_standing[w] != 0;
+  const float v0 = qvel[0], v1 = qvel[1], v2 = qvel[2], wz = qvel[5];
   b2e_rot_inv(q, down, gb);
   bool term = acosf(fminf(fmaxf(-gb[2], -1.f), 1.f)) > A.fall_angle;  // bad_orientation
   bool trunc = ep >= A.max_episode_length;                              // time_out
   // rewards (velocity_env_cfg.py:183-214)
-  float lin[3] = {qvel[0], qvel[1], qvel[2]};
+  float lin[3] = {v0, v1, v2};
   b2e_rot_inv(q, lin, lb);
-  float e0 = cmd[0] - lb[0], e1 = cmd[1] - lb[1], e2 = cmd[2] - qvel[5];
+  float e0 = c0 - lb[0], e1 = c1 - lb[1], e2 = c2 - wz;
   float r_lin = expf(-(e0 * e0 + e1 * e1) / 0.25f), r_ang = expf(-(e2 * e2) / 0.25f);
   float pose = 0.f, lim = 0.f, rate = 0.f;
-  for (int a = 0; a < nu; a++) {
+  for (int a = lane; a < nu; a += 32) {
     float jp = qpos[7 + a], dj = jp - A.default_joint_pos[a];
     pose += dj * dj;
     lim += fmaxf(A.soft_lo[a] - jp, 0.f) + fmaxf(jp - A.soft_hi[a], 0.f);
     float da = act[a] - last[a];
     rate += da * da;
   }
+  pose = b2e_wsum(pose); lim = b2e_wsum(lim); rate = b2e_wsum(rate);
+  __syncwarp();  // every lane holds the pre-reset state it needs; writes may start
   float r_pose = expf(-(pose / (float)nu) / 0.09f);
-  A.reward[w] = (r_lin + r_ang + r_pose - lim - 0.1f * rate) * A.step_dt;
+  const float reward = (r_lin + r_ang + r_pose - lim - 0.1f * rate) * A.step_dt;
   bool done = term || trunc;
-  A.terminated[w] = term; A.truncated[w] = trunc; A.done[w] = done;
-  A.log_row[3 * (size_t)w] = A.reward[w]; A.log_row[3 * (size_t)w + 1] = term ? 1.f : 0.f;
-  A.log_row[3 * (size_t)w + 2] = trunc ? 1.f : 0.f;
+  if (lane == 0) {
+    A.reward[w] = reward;
+    A.terminated[w] = term; A.truncated[w] = trunc; A.done[w] = done;
+    A.log_row[3 * (size_t)w] = reward; A.log_row[3 * (size_t)w + 1] = term ? 1.f : 0.f;
+    A.log_row[3 * (size_t)w + 2] = trunc ? 1.f : 0.f;
+  }
   // masked reset (reset_root_state_uniform + reset_joints_by_scale), command resample
   if (done) {
-    for (int i = 0; i < nq; i++) qpos[i] = A.default_qpos[i];
-    qpos[0] += (U[0] - 0.5f) + A.env_origins[3 * (size_t)w];
-    qpos[1] += (U[1] - 0.5f) + A.env_origins[3 * (size_t)w + 1];
-    qpos[2] += A.env_origins[3 * (size_t)w + 2];  // terrain spawn height (0 on the flat scene)
-    float yaw = (U[2] * 2.f - 1.f) * 3.14f;
-    qpos[3] = cosf(0.5f * yaw); qpos[4] = A.default_qpos[4]; qpos[5] = A.default_qpos[5]; qpos[6] = sinf(0.5f * yaw);
-    for (int a = 0; a < nu; a++) {
-      qpos[7 + a] = fminf(fmaxf(qpos[7 + a], A.soft_lo[a]), A.soft_hi[a]);
-      ctrl[a] = A.default_joint_pos[a];
-      last[a] = 0.f;
+    for (int i = lane; i < nq; i += 32) {
+      float v = A.default_qpos[i];
+      if (i == 0) v += (U[0] - 0.5f) + A.env_origins[3 * (size_t)w];
+      if (i == 1) v += (U[1] - 0.5f) + A.env_origins[3 * (size_t)w + 1];
+      if (i == 2) v += A.env_origins[3 * (size_t)w + 2];  // terrain spawn height (0 on the flat scene)
+      if (i == 3 || i == 6) {
+        float yaw = (U[2] * 2.f - 1.f) * 3.14f;
+        v = i == 3 ? cosf(0.5f * yaw) : sinf(0.5f * yaw);
+      }
+      if (i >= 7) v = fminf(fmaxf(v, A.soft_lo[i - 7]), A.soft_hi[i - 7]);
+      qpos[i] = v;
     }
-    for (int i = 0; i < nv; i++) qvel[i] = 0.f;
+    for (int a = lane; a < nu; a += 32) { ctrl[a] = A.default_joint_pos[a]; last[a] = 0.f; }
+    for (int i = lane; i < nv; i += 32) qvel[i] = 0.f;
     ep = 0;
   } else {
-    for (int a = 0; a < nu; a++) last[a] = act[a];
+    for (int a = lane; a < nu; a += 32) last[a] = act[a];
   }
-  A.episode_length[w] = ep;
   // command term (CommandTerm.compute + UniformVelocityCommand, velocity_command.py:64-110): resample on
   // reset and when the timer runs out, then heading control and standing envs every step
-  float ctl = A.cmd_time_left[w] - A.step_dt;
   if (done || ctl <= 0.f) {
-    cmd[0] = U[3] * 2.f - 1.f; cmd[1] = U[4] - 0.5f; cmd[2] = U[5] * 2.f - 1.f;
-    A.heading_target[w] = (U[6] * 2.f - 1.f) * 3.14159265358979f;
-    A.is_standing[w] = U[7] <= 0.1f;
+    c0 = U[3] * 2.f - 1.f; c1 = U[4] - 0.5f; c2 = U[5] * 2.f - 1.f;
+    htarget = (U[6] * 2.f - 1.f) * 3.14159265358979f;
+    standing = U[7] <= 0.1f;
     ctl = 3.f + 5.f * U[8];
   }
-  A.cmd_time_left[w] = ctl;
+  __syncwarp();  // the reset state is visible to every lane
   {
     // heading_w = atan2 of the body x axis in the world (entity/data.py:480-484), from the post-reset pose
     float qw = qpos[3], qx = qpos[4], qy = qpos[5], qz = qpos[6];
     float fx = 1.f - 2.f * (qy * qy + qz * qz), fy = 2.f * (qx * qy + qw * qz);
-    float err = A.heading_target[w] - atan2f(fy, fx);
+    float err = htarget - atan2f(fy, fx);
     err -= 6.28318530717959f * floorf((err + 3.14159265358979f) / 6.28318530717959f);  // wrap_to_pi
-    cmd[2] = fminf(fmaxf(0.5f * err, -1.f), 1.f);
-    if (A.is_standing[w]) { cmd[0] = 0.f; cmd[1] = 0.f; cmd[2] = 0.f; }
+    c2 = fminf(fmaxf(0.5f * err, -1.f), 1.f);
+    if (standing) { c0 = 0.f; c1 = 0.f; c2 = 0.f; }
   }
   // interval event: push_by_setting_velocity
-  float tl = A.push_time_left[w] - A.step_dt;
-  if (tl <= 0.f) {
-    qvel[0] = (U[9] * 2.f - 1.f) * A.push_vel;
-    qvel[1] = (U[10] * 2.f - 1.f) * A.push_vel;
+  float pv0 = qvel[0], pv1 = qvel[1];
+  const bool push = tl <= 0.f;
+  if (push) {
+    pv0 = (U[9] * 2.f - 1.f) * A.push_vel;
+    pv1 = (U[10] * 2.f - 1.f) * A.push_vel;
     tl = U[11] * (A.push_hi - A.push_lo) + A.push_lo;
   }
-  A.push_time_left[w] = tl;
+  __syncwarp();
+  if (lane == 0) {
+    A.episode_length[w] = ep;
+    cmd[0] = c0; cmd[1] = c1; cmd[2] = c2;
+    A.heading_target[w] = htarget; A.is_standing[w] = standing; A.cmd_time_left[w] = ctl;
+    A.push_time_left[w] = tl;
+    if (push) { qvel[0] = pv0; qvel[1] = pv1; }
+  }
   // observations from the (possibly reset / pushed) state
   // policy group with uniform noise (velocity_env_cfg.py:86-118), critic group without (:120-125)
   float* o = A.obs + (size_t)w * (9 + 3 * nu + 3);
   float* cr = A.critic + (size_t)w * (9 + 3 * nu + 3);
   const float* Z = U + 16;  // noise draws
-  float q2[4] = {qpos[3], qpos[4], qpos[5], qpos[6]}, lin2[3] = {qvel[0], qvel[1], qvel[2]};
+  float q2[4] = {qpos[3], qpos[4], qpos[5], qpos[6]}, lin2[3] = {pv0, pv1, qvel[2]};
   b2e_rot_inv(q2, lin2, lb);
   b2e_rot_inv(q2, down, gb);
-  for (int k = 0; k < 3; k++) {
-    cr[k] = lb[k]; cr[3 + k] = qvel[3 + k]; cr[6 + k] = gb[k];
+  if (lane < 3) {
+    const int k = lane;
+    const float av = qvel[3 + k];
+    cr[k] = lb[k]; cr[3 + k] = av; cr[6 + k] = gb[k];
     o[k] = lb[k] + (Z[k] * 2.f - 1.f) * 0.1f;
-    o[3 + k] = qvel[3 + k] + (Z[3 + k] * 2.f - 1.f) * 0.2f;
+    o[3 + k] = av + (Z[3 + k] * 2.f - 1.f) * 0.2f;
     o[6 + k] = gb[k] + (Z[6 + k] * 2.f - 1.f) * 0.05f;
+    const float ck = k == 0 ? c0 : (k == 1 ? c1 : c2);
+    o[9 + 3 * nu + k] = ck; cr[9 + 3 * nu + k] = ck;
   }
-  for (int a = 0; a < nu; a++) {
-    float jp = qpos[7 + a] - A.default_joint_pos[a], jv = qvel[6 + a];
-    cr[9 + a] = jp; cr[9 + nu + a] = jv; cr[9 + 2 * nu + a] = last[a];
+  for (int a = lane; a < nu; a += 32) {
+    float jp = qpos[7 + a] - A.default_joint_pos[a], jv = qvel[6 + a], la = last[a];
+    cr[9 + a] = jp; cr[9 + nu + a] = jv; cr[9 + 2 * nu + a] = la;
     o[9 + a] = jp + (Z[9 + a] * 2.f - 1.f) * 0.01f;
     o[9 + nu + a] = jv + (Z[9 + nu + a] * 2.f - 1.f) * 1.5f;
-    o[9 + 2 * nu + a] = last[a];
+    o[9 + 2 * nu + a] = la;
   }
-  for (int k = 0; k < 3; k++) { o[9 + 3 * nu + k] = cmd[k]; cr[9 + 3 * nu + k] = cmd[k]; }
 }

@@ -176,6 +176,13 @@ inline void fence_async_smem() {}
 #endif  // B2_HOST_EMULATION
 
 #define MP(arr) (m.arr.p + (size_t)w * m.arr.stride)
+// Visit the set bits of a 64-bit mask in ascending order, one 32-bit half at a time (64-bit find-first-set,
+// clear-lowest and shifts cost twice the instructions; the halves share one copy of the loop body).
+#define FOR_BITS64(mask64, d)                                                        \
+  _Pragma("unroll 1") for (int h_ = 0; h_ < 2; h_++)                                 \
+    for (unsigned w_ = h_ ? (unsigned)((mask64) >> 32) : (unsigned)(mask64), d_ = 0; \
+         w_ != 0u && ((d_ = 32u * h_ + (unsigned)__ffs((int)w_) - 1u), true); w_ &= w_ - 1u) \
+      for (int d = (int)d_, once_ = 1; once_; once_ = 0)
 
 #ifdef B2_PHASE_TIMING
 __device__ unsigned long long g_phase_cycles[32];
@@ -271,24 +278,32 @@ __device__ __noinline__ void ldl_factor(float* A, float* invdiag, int n, const u
     // trailing update: A[i,j] -= sum_t c_t,i c_t,j / d_t over the scheduled entries, c_t,q = A[kt-t, q]
     const unsigned* lst = sparse ? slist + start[blk] : dense;
     const int np = sparse ? start[blk + 1] - start[blk] : (lead * (lead + 1) >> 1);
+    // The pivot rows are addressed from row 3's base: rows 2, 1, 0 start kt-2, 2kt-3 and 3kt-3 floats further on,
+    // so one index register per operand serves all four loads (offsets folded into the block's row pointers).
+    const float* R3 = A + rb3; const float* R2 = A + rb2; const float* R1 = A + rb1; const float* R0 = A + rb0;
     int p = lane;
 #pragma unroll 1
     for (; p + 32 < np; p += 64) {
       unsigned e0 = lst[p], e1 = lst[p + 32];
       int i0 = (e0 >> 12) & 63, j0 = e0 >> 18, i1 = (e1 >> 12) & 63, j1 = e1 >> 18;
-      float acc0 = A[rb0 + i0] * (A[rb0 + j0] * dv[0]) + A[rb1 + i0] * (A[rb1 + j0] * dv[1]) +
-                   A[rb2 + i0] * (A[rb2 + j0] * dv[2]) + A[rb3 + i0] * (A[rb3 + j0] * dv[3]);
-      float acc1 = A[rb0 + i1] * (A[rb0 + j1] * dv[0]) + A[rb1 + i1] * (A[rb1 + j1] * dv[1]) +
-                   A[rb2 + i1] * (A[rb2 + j1] * dv[2]) + A[rb3 + i1] * (A[rb3 + j1] * dv[3]);
-      A[e0 & 0xfff] -= acc0;
-      A[e1 & 0xfff] -= acc1;
+      float acc0 = A[e0 & 0xfff], acc1 = A[e1 & 0xfff];
+      acc0 = fmaf(-R0[i0], R0[j0] * dv[0], acc0); acc1 = fmaf(-R0[i1], R0[j1] * dv[0], acc1);
+      acc0 = fmaf(-R1[i0], R1[j0] * dv[1], acc0); acc1 = fmaf(-R1[i1], R1[j1] * dv[1], acc1);
+      acc0 = fmaf(-R2[i0], R2[j0] * dv[2], acc0); acc1 = fmaf(-R2[i1], R2[j1] * dv[2], acc1);
+      acc0 = fmaf(-R3[i0], R3[j0] * dv[3], acc0); acc1 = fmaf(-R3[i1], R3[j1] * dv[3], acc1);
+      A[e0 & 0xfff] = acc0;
+      A[e1 & 0xfff] = acc1;
     }
 #pragma unroll 1
     for (; p < np; p += 32) {
       unsigned e0 = lst[p];
       int i0 = (e0 >> 12) & 63, j0 = e0 >> 18;
-      A[e0 & 0xfff] -= A[rb0 + i0] * (A[rb0 + j0] * dv[0]) + A[rb1 + i0] * (A[rb1 + j0] * dv[1]) +
-                       A[rb2 + i0] * (A[rb2 + j0] * dv[2]) + A[rb3 + i0] * (A[rb3 + j0] * dv[3]);
+      float acc0 = A[e0 & 0xfff];
+      acc0 = fmaf(-R0[i0], R0[j0] * dv[0], acc0);
+      acc0 = fmaf(-R1[i0], R1[j0] * dv[1], acc0);
+      acc0 = fmaf(-R2[i0], R2[j0] * dv[2], acc0);
+      acc0 = fmaf(-R3[i0], R3[j0] * dv[3], acc0);
+      A[e0 & 0xfff] = acc0;
     }
     __syncwarp();
   }
@@ -1051,10 +1066,8 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     #pragma unroll 1
     for (int b = lane; b < nb; b += 32) {
       float acc[3] = {0.f, 0.f, 0.f};
-      unsigned long long desc = m.body_submask[b];
-      while (desc) {
-        int d = __ffsll((long long)desc) - 1;
-        desc &= desc - 1;
+      const unsigned long long desc = m.body_submask[b];
+      FOR_BITS64(desc, d) {
         float md = mass[d];
         acc[0] += md * xipos[3 * d]; acc[1] += md * xipos[3 * d + 1]; acc[2] += md * xipos[3 * d + 2];
       }
@@ -1160,10 +1173,8 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     float acc[10];
 #pragma unroll
     for (int k = 0; k < 10; k++) acc[k] = 0.f;
-    unsigned long long sub = m.body_submask[b] & ~1ull;
-    while (sub) {
-      int d = __ffsll((long long)sub) - 1;
-      sub &= sub - 1;
+    const unsigned long long sub = m.body_submask[b] & ~1ull;
+    FOR_BITS64(sub, d) {
 #pragma unroll
       for (int k = 0; k < 10; k++) acc[k] += cinert[SI * d + k];
     }
@@ -1191,11 +1202,9 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   #pragma unroll 1
   for (int b = lane; b < nb; b += 32) {
     float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, snap[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    unsigned long long mask = m.body_dofmask[b];
+    const unsigned long long mask = m.body_dofmask[b];
     int own0 = m.body_dofadr[b];
-    while (mask) {
-      int d = __ffsll((long long)mask) - 1;
-      mask &= mask - 1;
+    FOR_BITS64(mask, d) {
       const float* c = cdof + SD * d;
       if (own0 >= 0 && d >= own0) {
         int j = m.dof_jntid[d];
@@ -1254,10 +1263,8 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
   #pragma unroll 1
   for (int b = lane; b < nb; b += 32) {
     float a[6] = {0.f, 0.f, 0.f, -m.gravity[0], -m.gravity[1], -m.gravity[2]};
-    unsigned long long mask = m.body_dofmask[b];
-    while (mask) {
-      int d = __ffsll((long long)mask) - 1;
-      mask &= mask - 1;
+    const unsigned long long mask = m.body_dofmask[b];
+    FOR_BITS64(mask, d) {
       float qd = qvel[d];
 #pragma unroll
       for (int k = 0; k < 6; k++) a[k] += cdofdot[SD * d + k] * qd;
@@ -1313,10 +1320,8 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     #pragma unroll 1
     for (int i = lane; i < nv; i += 32) {
       float sb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, sx[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      unsigned long long sub = m.dof_bodymask[i];
-      while (sub) {
-        int b = __ffsll((long long)sub) - 1;
-        sub &= sub - 1;
+      const unsigned long long sub = m.dof_bodymask[i];
+      FOR_BITS64(sub, b) {
 #pragma unroll
         for (int k = 0; k < 6; k++) { sb[k] += cacc[SD * b + k]; sx[k] += crb[SD * b + k]; }
       }

@@ -1002,7 +1002,7 @@ int b2_velenv_post(b2_sim* s, const B2VelEnvArgs* args, void* stream) {
   if (s->hm.nq != s->hm.nu + 7 || s->hm.nv != s->hm.nu + 6)
     return fail("b2_velenv_post: expects one floating base plus nu actuated hinge joints");
   DeviceGuard guard(s->device);
-  b2_velenv_post_kernel<<<(s->nworld + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+  b2_velenv_post_kernel<<<(s->nworld + 3) / 4, 128, 0, (cudaStream_t)stream>>>(  // one warp per environment
       s->hd, s->hm.nq, s->hm.nv, s->hm.nu, *args);
   s->launches++;
   CUDA_OK(cudaGetLastError());
