@@ -141,6 +141,49 @@ int b2_velenv_pre(b2_sim* sim, const float* action, const float* default_joint_p
                   const float* action_scale, void* cuda_stream);
 int b2_velenv_post(b2_sim* sim, const B2VelEnvArgs* args, void* cuda_stream);
 
+/* ---- fused MDP glue of the motion-tracking task (BASELINE config C; reference tasks/tracking/tracking_env_cfg.py,
+ * tasks/tracking/mdp/commands.py:283-388) ------------------------------------------------------------------------
+ * post1 runs after the sub-steps (terminations, rewards, RSI resets, clip time step) and leaves the mask for
+ * b2_forward_masked; post2 runs after that forward (anchor-relative targets, interval push, observations).
+ * Per-step uniforms U[n][B2_TRACKENV_NU(nu)]: with S = 13 + nu, [0, S) reset block (0 clip frame, 1-6 pose noise,
+ * 7-12 velocity noise, 13.. joint noise), [S, 2S) the same for envs that ran off the clip, [2S, 2S+7) push (6
+ * velocity + timer), then observation noise: anchor pos 3, anchor ori 6, base lin 3, base ang 3, joint pos nu, joint vel nu. */
+#define B2_TRACKENV_NU(nu) (48 + 4 * (nu))
+typedef struct B2TrackEnvArgs {
+  const float* action;            /* [n][nu] */
+  const float* U;                 /* [n][B2_TRACKENV_NU(nu)] */
+  const float* default_joint_pos; /* [nu] */
+  const float* soft_lo;           /* [nu] */
+  const float* soft_hi;           /* [nu] */
+  const float* env_origins;       /* [n][3] */
+  const float* m_joint_pos;       /* motion clip, T frames: [T][nu] */
+  const float* m_joint_vel;       /* [T][nu] */
+  const float* m_body_pos;        /* [T][nb][3] */
+  const float* m_body_quat;       /* [T][nb][4] */
+  const float* m_body_lin;        /* [T][nb][3] */
+  const float* m_body_ang;        /* [T][nb][3] */
+  const int32_t* body_idx;        /* [nb] engine body ids of the tracked bodies */
+  const int32_t* ee_idx;          /* [nee] end effectors, as indices into the tracked bodies */
+  int64_t* time_steps;            /* [n] in/out: clip frame */
+  int32_t* episode_length;        /* [n] in/out */
+  float* last_action;             /* [n][nu] in/out */
+  float* push_time_left;          /* [n] in/out */
+  float* body_pos_rel;            /* [n][nb][3] in/out: anchor-relative target positions */
+  float* body_quat_rel;           /* [n][nb][4] in/out */
+  float* reward;                  /* [n] out */
+  unsigned char* terminated;      /* [n] out */
+  unsigned char* truncated;       /* [n] out */
+  unsigned char* mask;            /* [n] out: envs whose state was rewritten (reset or clip restart) */
+  float* log_row;                 /* [n][3] out */
+  float* obs;                     /* [n][5 nu + 15] out */
+  float* critic;                  /* [n][5 nu + 15 + 9 nb] out */
+  float pose_range[12], vel_range[12]; /* (lo, hi) x 6 */
+  float step_dt, jp_lo, jp_hi, push_lo, push_hi;
+  int32_t nb, nee, anchor, T, self_collision_adr, root_body, max_episode_length;
+} B2TrackEnvArgs;
+int b2_trackenv_post1(b2_sim* sim, const B2TrackEnvArgs* args, void* cuda_stream);
+int b2_trackenv_post2(b2_sim* sim, const B2TrackEnvArgs* args, void* cuda_stream);
+
 /* Diagnostics (synchronises `cuda_stream`). */
 int b2_stats(b2_sim* sim, void* cuda_stream, B2Stats* out);
 /* Number of kernels this library has launched for `sim` since creation. */

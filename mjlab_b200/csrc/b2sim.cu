@@ -12,6 +12,7 @@
 #include "b2_kernel.cuh"
 #include "b2_tables.h"
 #include "b2_env.cuh"
+#include "b2_trackenv.cuh"
 
 static thread_local std::string g_err;
 static int fail(const std::string& msg) {
@@ -1004,6 +1005,33 @@ int b2_velenv_post(b2_sim* s, const B2VelEnvArgs* args, void* stream) {
   DeviceGuard guard(s->device);
   b2_velenv_post_kernel<<<(s->nworld + 3) / 4, 128, 0, (cudaStream_t)stream>>>(  // one warp per environment
       s->hd, s->hm.nq, s->hm.nv, s->hm.nu, *args);
+  s->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static int trackenv_check(b2_sim* s, const B2TrackEnvArgs* a) {
+  if (!s || !a) return fail("b2_trackenv: bad arguments");
+  if (s->hm.nq != s->hm.nu + 7 || s->hm.nv != s->hm.nu + 6)
+    return fail("b2_trackenv: expects one floating base plus nu actuated hinge joints");
+  if (a->nb < 1 || a->nb > 32 || a->anchor < 0 || a->anchor >= a->nb || a->T < 2 || a->nee < 0 ||
+      a->root_body < 0 || a->root_body >= s->hm.nbody || a->self_collision_adr < 0 ||
+      a->self_collision_adr >= s->hm.nsensordata)
+    return fail("b2_trackenv: bad sizes (1 <= nb <= 32 tracked bodies, anchor among them, T >= 2 clip frames)");
+  return 0;
+}
+int b2_trackenv_post1(b2_sim* s, const B2TrackEnvArgs* args, void* stream) {
+  if (trackenv_check(s, args)) return 1;
+  DeviceGuard guard(s->device);
+  b2_trackenv_post1_kernel<<<(s->nworld + 3) / 4, 128, 0, (cudaStream_t)stream>>>(s->hd, s->hm.nu, s->hm.nbody, *args);
+  s->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int b2_trackenv_post2(b2_sim* s, const B2TrackEnvArgs* args, void* stream) {
+  if (trackenv_check(s, args)) return 1;
+  DeviceGuard guard(s->device);
+  b2_trackenv_post2_kernel<<<(s->nworld + 3) / 4, 128, 0, (cudaStream_t)stream>>>(s->hd, s->hm.nu, s->hm.nbody, *args);
   s->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;

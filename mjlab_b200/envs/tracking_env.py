@@ -26,7 +26,7 @@ import torch
 from mjlab_b200.asset_zoo import g1, load_compiled
 from mjlab_b200.entity_data import EntityData, EntityIndexing, quat_apply, quat_apply_inverse, quat_mul
 from mjlab_b200.envs.velocity_env import _resolve
-from mjlab_b200.sim import MujocoCfg, Simulation, SimulationCfg
+from mjlab_b200.sim import MujocoCfg, Simulation, SimulationCfg, native
 
 VELOCITY_RANGE = ((-0.5, 0.5), (-0.5, 0.5), (-0.2, 0.2), (-0.52, 0.52), (-0.52, 0.52), (-0.78, 0.78))  # tracking_env_cfg.py:30-37
 POSE_RANGE = ((-0.05, 0.05), (-0.05, 0.05), (-0.01, 0.01), (-0.1, 0.1), (-0.1, 0.1), (-0.2, 0.2))       # :61-68
@@ -85,8 +85,9 @@ def rot6(q):
 
 
 class TrackingFlatEnv:
-  def __init__(self, cfg: TrackingEnvCfg, device: str = "cuda:0", model=None):
+  def __init__(self, cfg: TrackingEnvCfg, device: str = "cuda:0", model=None, native_mdp: bool = True):
     self.cfg, self.device = cfg, device
+    self.native_mdp = native_mdp  # fused CUDA kernels (csrc/b2_trackenv.cuh) or the torch reference below
     self.model = m = model if model is not None else load_compiled("g1_tracking_flat")
     n = self.num_envs = cfg.num_envs
     self.sim = Simulation(n, cfg.sim, m, device)
@@ -153,21 +154,21 @@ class TrackingFlatEnv:
   def _clip(self, name):
     return self.motion[name][self.time_steps]
 
-  def _resample(self, mask: torch.Tensor, restart_clip: torch.Tensor) -> None:
-    """``MotionCommand._resample_command`` for the masked envs: new clip frame, RSI noise, state write."""
+  def _resample(self, mask: torch.Tensor, restart_clip: torch.Tensor, Ub: torch.Tensor) -> None:
+    """``MotionCommand._resample_command`` for the masked envs: new clip frame, RSI noise, state write.  ``Ub``:
+    this call's uniforms ``[n, 13 + nu]`` (0 clip frame, 1-6 pose, 7-12 velocity, 13.. joints; include/b2sim.h)."""
     n, d = self.num_envs, self.sim.data
     T = self.cfg.clip_frames
-    ts = (self._rand(n) * (T - 1)).long()
+    ts = (Ub[:, 0] * (T - 1)).long()
     self.time_steps.copy_(torch.where(restart_clip, ts, self.time_steps))
-    U = self._rand(n, 12) * 1.0
-    pose_n = U[:, 0:6] * (self._pr[:, 1] - self._pr[:, 0]) + self._pr[:, 0]
-    vel_n = U[:, 6:12] * (self._vr[:, 1] - self._vr[:, 0]) + self._vr[:, 0]
+    pose_n = Ub[:, 1:7] * (self._pr[:, 1] - self._pr[:, 0]) + self._pr[:, 0]
+    vel_n = Ub[:, 7:13] * (self._vr[:, 1] - self._vr[:, 0]) + self._vr[:, 0]
     root_pos = self._clip("body_pos_w")[:, 0] + self.env_origins + pose_n[:, 0:3]
     root_ori = quat_mul(quat_from_euler_xyz(pose_n[:, 3], pose_n[:, 4], pose_n[:, 5]), self._clip("body_quat_w")[:, 0])
     lin = self._clip("body_lin_vel_w")[:, 0] + vel_n[:, 0:3]
     ang = self._clip("body_ang_vel_w")[:, 0] + vel_n[:, 3:6]
     lo, hi = self.cfg.joint_position_range
-    jp = self._clip("joint_pos") + self._rand(n, self.nu) * (hi - lo) + lo
+    jp = self._clip("joint_pos") + Ub[:, 13:13 + self.nu] * (hi - lo) + lo
     lim = self.robot.soft_joint_pos_limits
     jp = torch.minimum(torch.maximum(jp, lim[..., 0]), lim[..., 1])
     qpos = torch.cat([root_pos, root_ori, jp], dim=1)
@@ -193,12 +194,16 @@ class TrackingFlatEnv:
     r_quat = quat[:, self.anchor][:, None, :].expand(-1, nbk, -1)
     delta_pos = torch.cat([r_pos[..., 0:2], a_pos[..., 2:3]], dim=-1)
     delta_ori = yaw_quat(quat_mul(r_quat, quat_inv(a_quat)))
-    self.body_quat_relative_w = quat_mul(delta_ori, self._clip("body_quat_w"))
-    self.body_pos_relative_w = delta_pos + quat_apply(delta_ori, self._clip("body_pos_w") + self.env_origins[:, None, :] - a_pos)
+    # (in place: the fused kernels hold pointers to these two tensors)
+    self.body_quat_relative_w.copy_(quat_mul(delta_ori, self._clip("body_quat_w")))
+    self.body_pos_relative_w.copy_(delta_pos + quat_apply(delta_ori, self._clip("body_pos_w") + self.env_origins[:, None, :] - a_pos))
 
-  def observations(self):
-    """(policy, critic) groups of tracking_env_cfg.py:88-150; uniform noise on the policy group."""
+  def observations(self, Z: torch.Tensor | None = None):
+    """(policy, critic) groups of tracking_env_cfg.py:88-150; uniform noise on the policy group from the draws
+    ``Z[n, 15 + 2 nu]`` (anchor pos 3, anchor ori 6, base lin 3, base ang 3, joint pos, joint vel)."""
     d = self.sim.data
+    if Z is None:
+      Z = self._rand(self.num_envs, 15 + 2 * self.nu)
     pos, quat, _, _ = self._robot_bodies()
     a_pos = self._clip("body_pos_w")[:, self.anchor] + self.env_origins
     a_quat = self._clip("body_quat_w")[:, self.anchor]
@@ -210,7 +215,13 @@ class TrackingFlatEnv:
     jp, jv = d.qpos[:, 7:] - self.default_joint_pos, d.qvel[:, 6:]
     terms = [command, anchor_pos_b, anchor_ori_b, base_lin, base_ang, jp, jv, self.last_action]
     amp = (0.0, 0.25, 0.05, 0.5, 0.2, 0.01, 0.5, 0.0)
-    noisy = [t if a == 0.0 else t + (self._rand(*t.shape) * 2 - 1) * a for t, a in zip(terms, amp)]
+    noisy, k = [], 0
+    for t, a in zip(terms, amp):
+      if a == 0.0:
+        noisy.append(t)
+      else:
+        noisy.append(t + (Z[:, k:k + t.shape[1]] * 2 - 1) * a)
+        k += t.shape[1]
     rq = r_quat[:, None, :].expand(-1, len(BODY_NAMES), -1)
     body_pos_b = quat_apply_inverse(rq, pos - r_pos[:, None, :]).flatten(1)
     body_ori_b = rot6(quat_mul(quat_inv(rq), quat)).flatten(1)
@@ -220,7 +231,7 @@ class TrackingFlatEnv:
   # -- API -----------------------------------------------------------------------------------------
   def reset(self):
     all_ = torch.ones(self.num_envs, dtype=torch.bool, device=self.device)
-    self._resample(all_, all_)
+    self._resample(all_, all_, self._rand(self.num_envs, 13 + self.nu))
     self.sim.forward()
     self._update_command()
     return self.observations()
@@ -248,7 +259,78 @@ class TrackingFlatEnv:
     return self._step_impl(action)
 
   def _step_impl(self, action: torch.Tensor):
-    cfg, d, n = self.cfg, self.sim.data, self.num_envs
+    n = self.num_envs
+    U = self._rand(n, 48 + 4 * self.nu)  # B2_TRACKENV_NU: every random number of this env step (include/b2sim.h)
+    if self.native_mdp:
+      return self._step_native(action, U)
+    return self._step_torch(action, U)
+
+  def _native_setup(self) -> None:
+    """Argument block of the fused kernels: device pointers of the env's own tensors (all persistent)."""
+    n, nu, dev = self.num_envs, self.nu, torch.device(self.device)
+    f32 = dict(dtype=torch.float32, device=dev)
+    nb = len(BODY_NAMES)
+    self._U = torch.zeros(n, 48 + 4 * nu, **f32)
+    self._act = torch.zeros(n, nu, **f32)
+    self._reward = torch.zeros(n, **f32)
+    self._term = torch.zeros(n, dtype=torch.bool, device=dev)
+    self._trunc = torch.zeros(n, dtype=torch.bool, device=dev)
+    self._obs = torch.zeros(n, 5 * nu + 15, **f32)
+    self._critic = torch.zeros(n, 5 * nu + 15 + 9 * nb, **f32)
+    self._body_idx32 = self.robot.indexing.body_ids[self.body_idx].to(torch.int32).contiguous()
+    self._ee_idx32 = self.ee_idx.to(torch.int32).contiguous()
+    lim = self.robot.soft_joint_pos_limits
+    self._soft_lo, self._soft_hi = lim[0, :, 0].contiguous(), lim[0, :, 1].contiguous()
+    self.body_pos_relative_w = self.body_pos_relative_w.contiguous()
+    self.body_quat_relative_w = self.body_quat_relative_w.contiguous()
+    A = native.B2TrackEnvArgs()
+    ptr = dict(action=self._act, U=self._U, default_joint_pos=self.default_joint_pos, soft_lo=self._soft_lo,
+               soft_hi=self._soft_hi, env_origins=self.env_origins, m_joint_pos=self.motion["joint_pos"],
+               m_joint_vel=self.motion["joint_vel"], m_body_pos=self.motion["body_pos_w"],
+               m_body_quat=self.motion["body_quat_w"], m_body_lin=self.motion["body_lin_vel_w"],
+               m_body_ang=self.motion["body_ang_vel_w"], body_idx=self._body_idx32, ee_idx=self._ee_idx32,
+               time_steps=self.time_steps, episode_length=self.episode_length_buf, last_action=self.last_action,
+               push_time_left=self.push_time_left, body_pos_rel=self.body_pos_relative_w,
+               body_quat_rel=self.body_quat_relative_w, reward=self._reward, terminated=self._term,
+               truncated=self._trunc, mask=self._done_buf, log_row=self.log_row, obs=self._obs, critic=self._critic)
+    for k, t in ptr.items():
+      assert t.is_contiguous(), k
+      setattr(A, k, t.data_ptr())
+    for k in range(6):
+      A.pose_range[2 * k], A.pose_range[2 * k + 1] = POSE_RANGE[k]
+      A.vel_range[2 * k], A.vel_range[2 * k + 1] = VELOCITY_RANGE[k]
+    A.step_dt = self.step_dt
+    A.jp_lo, A.jp_hi = self.cfg.joint_position_range
+    A.push_lo, A.push_hi = self.cfg.push_interval_s
+    A.nb, A.nee, A.anchor, A.T = nb, len(EE_NAMES), self.anchor, self.cfg.clip_frames
+    A.self_collision_adr = self.self_collision_adr[0]
+    A.root_body = int(self.robot.indexing.root_body_id)
+    A.max_episode_length = self.max_episode_length
+    self._native_args = A
+    self._keep = ptr
+
+  def _step_native(self, action: torch.Tensor, U: torch.Tensor):
+    """Two fused kernels around the masked forward (csrc/b2_trackenv.cuh) instead of ~150 torch launches."""
+    import ctypes
+
+    if getattr(self, "_native_args", None) is None:
+      self._native_setup()
+    sim = self.sim
+    st = sim._stream()
+    self._U.copy_(U)
+    self._act.copy_(action)
+    native.check(sim._lib.b2_velenv_pre(sim._h, ctypes.c_void_p(self._act.data_ptr()),
+                                        ctypes.c_void_p(self.default_joint_pos.data_ptr()),
+                                        ctypes.c_void_p(self.action_scale.data_ptr()), st))
+    sim.step_n(self.cfg.decimation)
+    native.check(sim._lib.b2_trackenv_post1(sim._h, ctypes.byref(self._native_args), st))
+    sim.forward(env_mask=self._done_buf)
+    native.check(sim._lib.b2_trackenv_post2(sim._h, ctypes.byref(self._native_args), st))
+    return self._obs, self._reward, self._term, self._trunc, {"critic": self._critic}
+
+  def _step_torch(self, action: torch.Tensor, U: torch.Tensor):
+    cfg, d, n, nu = self.cfg, self.sim.data, self.num_envs, self.nu
+    S = 13 + nu
     d.ctrl[:] = self.default_joint_pos + self.action_scale * action  # JointPositionAction, use_default_offset
     self.sim.step_n(cfg.decimation)
     self.episode_length_buf += 1
@@ -278,29 +360,27 @@ class TrackingFlatEnv:
     self.last_action.copy_(action)
     done = terminated | truncated
     self.log_row.copy_(torch.stack([reward, terminated.float(), truncated.float()], dim=1))
-    # reset onto the clip (RSI) + forward for the reset envs only
-    self._resample(done, done)
+    # reset onto the clip (RSI); then the clip's time step: envs that ran off its end restart on it.  Both rewrite
+    # the whole state of their envs, so one forward over the union follows (the reference runs one per event)
+    self._resample(done, done, U[:, 0:S])
     self.episode_length_buf.copy_(torch.where(done, torch.zeros_like(self.episode_length_buf), self.episode_length_buf))
     self.last_action.copy_(torch.where(done.unsqueeze(1), torch.zeros_like(self.last_action), self.last_action))
-    self._done_buf.copy_(done)
-    self.sim.forward(env_mask=self._done_buf)
-    # command update: next clip frame; envs that ran off the end of the clip restart on it
     self.time_steps += 1
     ended = self.time_steps >= cfg.clip_frames
-    self._resample(ended, ended)
-    self._done_buf.copy_(ended)
+    self._resample(ended, ended, U[:, S:2 * S])
+    self._done_buf.copy_(done | ended)
     self.sim.forward(env_mask=self._done_buf)
     self._update_command()
     # interval push (push_by_setting_velocity with VELOCITY_RANGE, tracking_env_cfg.py:155-161)
     self.push_time_left -= self.step_dt
     push = self.push_time_left <= 0
-    U = self._rand(n, 7)
-    vel_w = self.robot.root_link_vel_w + U[:, 0:6] * (self._vr[:, 1] - self._vr[:, 0]) + self._vr[:, 0]
+    P = U[:, 2 * S:2 * S + 7]
+    vel_w = self.robot.root_link_vel_w + P[:, 0:6] * (self._vr[:, 1] - self._vr[:, 0]) + self._vr[:, 0]
     vel = torch.cat([vel_w[:, 0:3], quat_apply_inverse(self.robot.root_link_quat_w, vel_w[:, 3:6])], dim=1)
     d.qvel[:, 0:6] = torch.where(push.unsqueeze(1), vel, d.qvel[:, 0:6])
     lo_t, hi_t = cfg.push_interval_s
-    self.push_time_left.copy_(torch.where(push, U[:, 6] * (hi_t - lo_t) + lo_t, self.push_time_left))
-    policy, critic = self.observations()
+    self.push_time_left.copy_(torch.where(push, P[:, 6] * (hi_t - lo_t) + lo_t, self.push_time_left))
+    policy, critic = self.observations(U[:, 2 * S + 7:])
     return policy, reward, terminated, truncated, {"critic": critic}
 
   def close(self):

@@ -55,6 +55,19 @@ class B2VelEnvArgs(ctypes.Structure):
   )
 
 
+class B2TrackEnvArgs(ctypes.Structure):
+  _fields_ = (
+    [(n, ctypes.c_void_p) for n in (
+      "action", "U", "default_joint_pos", "soft_lo", "soft_hi", "env_origins", "m_joint_pos", "m_joint_vel",
+      "m_body_pos", "m_body_quat", "m_body_lin", "m_body_ang", "body_idx", "ee_idx", "time_steps",
+      "episode_length", "last_action", "push_time_left", "body_pos_rel", "body_quat_rel", "reward", "terminated",
+      "truncated", "mask", "log_row", "obs", "critic")]
+    + [("pose_range", ctypes.c_float * 12), ("vel_range", ctypes.c_float * 12)]
+    + [(n, ctypes.c_float) for n in ("step_dt", "jp_lo", "jp_hi", "push_lo", "push_hi")]
+    + [(n, ctypes.c_int32) for n in ("nb", "nee", "anchor", "T", "self_collision_adr", "root_body", "max_episode_length")]
+  )
+
+
 def make_model_desc(model):
   """Pack a compiled Model into a B2ModelDesc. Returns (desc, keepalive)."""
   keep = []
@@ -118,6 +131,8 @@ def load_library() -> ctypes.CDLL:
   L.b2_forward_masked.argtypes = [vp, vp, vp]
   L.b2_velenv_pre.argtypes = [vp, vp, vp, vp, vp]
   L.b2_velenv_post.argtypes = [vp, ctypes.POINTER(B2VelEnvArgs), vp]
+  L.b2_trackenv_post1.argtypes = [vp, ctypes.POINTER(B2TrackEnvArgs), vp]
+  L.b2_trackenv_post2.argtypes = [vp, ctypes.POINTER(B2TrackEnvArgs), vp]
   L.b2_step_host.argtypes = [vp, vp, ci, vp, vp, vp]
   L.b2_stats.argtypes = [vp, vp, ctypes.POINTER(B2Stats)]
   L.b2_launch_count.argtypes = [vp]

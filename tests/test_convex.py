@@ -298,3 +298,48 @@ def test_hfield_flat_box_rest_contacts():
   assert np.allclose(c[:, 0], -0.004, atol=1e-9)
   assert np.allclose(c[:, 4:7], [0, 0, 1], atol=1e-9)  # from the field up into the box
   assert np.allclose(c[:, 3], 0.2 - 0.002, atol=1e-9)
+
+
+@pytest.mark.parametrize("prec", [64, 32])
+def test_box_primitives_match_minkowski_hull(prec):
+  """The primitive box routines (oracle/b2_oracle.c box_box / sphere_box, restated in the kernel) are own definitions;
+  their DEEPEST contact must still carry the exact penetration depth of the two boxes — the origin's depth inside the
+  hull of the Minkowski difference — and, when separated within the margin, the exact distance."""
+  L, dt, ct = _lib(prec)
+  rng = np.random.default_rng(17)
+  tol = 1e-6 if prec == 64 else 2e-4
+  npen = nsep = exact = 0
+  out = np.zeros(7 * 8, dtype=dt)
+  for it in range(300):
+    h1, h2 = rng.uniform(0.08, 0.35, size=3), rng.uniform(0.08, 0.35, size=3)
+    R1, R2 = _rot(rng), _rot(rng)
+    p1 = rng.normal(size=3) * 0.05
+    p2 = p1 + rng.normal(size=3) * rng.choice([0.15, 0.3, 0.5])
+    A, _ = _shape_points(G_BOX, p1, R1, h1, None)
+    B, _ = _shape_points(G_BOX, p2, R2, h2, None)
+    core, nrm = _exact(A, B)
+    margin = 0.05
+    a = [np.ascontiguousarray(x, dtype=dt) for x in (p1, R1.reshape(-1), h1, p2, R2.reshape(-1), h2)]
+    n = L.b2o_prim_box_box(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), _p(a[5]), ct(margin), _p(out))
+    c = out[: 7 * n].reshape(n, 7).astype(float)
+    if core > margin + 1e-3:
+      assert n == 0, (it, core)
+      continue
+    if core > margin - 1e-3 or abs(core) < 1e-3:
+      continue
+    assert 1 <= n <= 8, (it, core, n)
+    if core < 0:
+      npen += 1
+      # exact depth, or a face axis within the routine's 5 % preference of faces over a marginally shallower edge axis
+      cmin = c[:, 0].min()
+      assert 1.05 * core - 1e-5 - tol <= cmin <= core + tol, (it, cmin, core)
+      exact += abs(cmin - core) <= tol
+      if nrm is not None and abs(cmin - core) <= tol:
+        k = int(np.argmin(c[:, 0]))
+        assert np.dot(c[k, 4:7], nrm) > 1 - 2e-3, (it, c[k, 4:7], nrm)
+    else:
+      nsep += 1
+      # separated boxes inside the margin: the routine reports the gap along its separating axis, a lower bound of
+      # the closest-point distance (equal to it for face-vertex and edge-edge configurations)
+      assert 0 < c[:, 0].min() <= core + tol, (it, c[:, 0].min(), core)
+  assert npen > 80 and nsep > 5 and exact > 0.6 * npen, (npen, nsep, exact)

@@ -263,6 +263,8 @@ class EmulSimulation:
     self._lib.b2_velenv_pre.argtypes = [vp, vp, vp, vp, vp]
     self._lib.b2_velenv_post.argtypes = [vp, ctypes.POINTER(native.B2VelEnvArgs), vp]
     self._lib.b2_expand_model_field.argtypes = [vp, ctypes.c_char_p, vp, ctypes.POINTER(native.B2Tensor)]
+    self._lib.b2_trackenv_post1.argtypes = [vp, ctypes.POINTER(native.B2TrackEnvArgs), vp]
+    self._lib.b2_trackenv_post2.argtypes = [vp, ctypes.POINTER(native.B2TrackEnvArgs), vp]
     self._e = EmulSim(self._lib, model, num_envs, ncon=max(16, min(96, -(-cfg.nconmax // num_envs))) if cfg.nconmax else 0)
     self._h = self._e.h
     self.device = device
@@ -273,7 +275,10 @@ class EmulSimulation:
         object.__setattr__(self, "_which", which)
 
       def __getattr__(self, name):
-        return outer._torch.from_numpy(outer._e.field(name, which=self._which))
+        try:
+          return outer._torch.from_numpy(outer._e.field(name, which=self._which))
+        except AssertionError:
+          raise AttributeError(name) from None
 
     self.data, self.model = _Fields(0), _Fields(1)
 
@@ -327,6 +332,54 @@ def test_emulated_env_native_mdp_kernels_match_torch_reference(monkeypatch):
       getattr(b.sim.data, f)[:] = getattr(a.sim.data, f)[:]
     resets += int((ta | ua).sum())
   assert resets >= 3  # time-outs (every 2 steps) exercised the masked reset path
+  a.close()
+  b.close()
+
+
+def test_emulated_tracking_env_native_mdp_kernels_match_torch_reference(monkeypatch):
+  """The tracking env (config C) on the emulated library: the fused MDP kernels (csrc/b2_trackenv.cuh) against the
+  torch implementation of the same step - terminations, rewards, RSI resets, clip restarts, anchor-relative targets,
+  pushes, policy and critic observations - on CPU, consuming the same uniforms."""
+  import torch
+
+  import mjlab_b200.envs.tracking_env as te
+
+  monkeypatch.setattr(te, "Simulation", EmulSimulation)
+  monkeypatch.setattr(native, "check", lambda rc: (_ for _ in ()).throw(RuntimeError("b2sim call failed")) if rc else None)
+  cfg = dict(num_envs=3, decimation=1, episode_length_s=0.015, clip_frames=4, push_interval_s=(0.004, 0.012))
+  a = te.TrackingFlatEnv(te.TrackingEnvCfg(**cfg), device="cpu", native_mdp=False)
+  b = te.TrackingFlatEnv(te.TrackingEnvCfg(**cfg), device="cpu", native_mdp=True)
+  assert torch.equal(a.sim.data.qpos[:], b.sim.data.qpos[:])
+  g = torch.Generator()
+  g.manual_seed(5)
+  events = dict(term=0, trunc=0, ended=0, push=0)
+  for k in range(6):
+    act = torch.rand((3, a.nu), generator=g) * 2 - 1
+    if k == 2:  # a fall: the anchor drops below the clip's by more than 0.25 m
+      for e in (a, b):
+        e.sim.data.qpos[1, 2] -= 0.4
+    ts0, ptl0 = a.time_steps.clone(), a.push_time_left.clone()
+    oa, ra, ta, ua, xa = a.step(act)
+    ob, rb, tb, ub, xb = b.step(act)
+    assert torch.equal(ta, tb) and torch.equal(ua, ub), (k, ta, tb, ua, ub)
+    assert torch.allclose(ra, rb, atol=2e-5), (k, ra, rb)
+    assert torch.equal(a.time_steps, b.time_steps) and torch.equal(a.episode_length_buf, b.episode_length_buf)
+    assert torch.allclose(a.push_time_left, b.push_time_left, atol=1e-6)
+    assert torch.allclose(a.last_action, b.last_action)
+    assert torch.equal(a._done_buf, b._done_buf)
+    assert torch.allclose(a.body_pos_relative_w, b.body_pos_relative_w, atol=1e-5)
+    assert torch.allclose(a.body_quat_relative_w, b.body_quat_relative_w, atol=1e-5)
+    assert torch.allclose(a.log_row, b.log_row, atol=2e-5)
+    for f in ("qpos", "qvel", "ctrl"):
+      assert torch.allclose(getattr(a.sim.data, f)[:], getattr(b.sim.data, f)[:], atol=1e-5), (k, f)
+    assert oa.shape == ob.shape == (3, 160) and xa["critic"].shape == xb["critic"].shape == (3, 286)
+    assert torch.allclose(oa, ob, atol=1e-4), (k, (oa - ob).abs().max())
+    assert torch.allclose(xa["critic"], xb["critic"], atol=1e-4), (k, (xa["critic"] - xb["critic"]).abs().max())
+    events["term"] += int(ta.sum()); events["trunc"] += int(ua.sum())
+    events["ended"] += int(((ts0 + 1 >= 4) & ~(ta | ua)).sum()); events["push"] += int((ptl0 - a.step_dt <= 0).sum())
+    for f in ("qpos", "qvel", "qacc_warmstart", "ctrl"):  # resynchronise: the MDP logic is what is under test
+      getattr(b.sim.data, f)[:] = getattr(a.sim.data, f)[:]
+  assert all(v > 0 for v in events.values()), events
   a.close()
   b.close()
 
