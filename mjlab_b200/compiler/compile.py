@@ -439,6 +439,10 @@ def compile_spec(spec: S.Spec) -> Model:
         limited = int(spec.autolimits and j.range[0] < j.range[1])
       if j.type == S.JNT_FREE:
         limited = 0
+      if limited and j.range[1] - j.range[0] < 2.0 * j.margin:
+        # both limit rows of the joint could be active at once; the engine keeps one row per joint
+        raise NotImplementedError(
+          f"joint '{j.name}': range narrower than twice its margin (both limits active at once) is not supported")
       A["jnt_limited"].append(limited)
       A["jnt_range"].append(j.range)
       A["jnt_solref"].append(j.solref_limit)

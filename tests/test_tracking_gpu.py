@@ -106,6 +106,9 @@ def test_tracking_native_mdp_kernels_match_torch_reference():
   term = trunc = 0
   for k in range(25):
     act = torch.rand((n, 29), generator=g, device=DEV) * 2 - 1
+    if k == 5:  # falls: the anchors of the first envs drop below the clip's by more than 0.25 m
+      for e in (a, b):
+        e.sim.data.qpos[:8, 2] -= 0.4
     oa, ra, ta, ua, xa = a.step(act)
     ob, rb, tb, ub, xb = b.step(act)
     # a termination threshold crossed within fp32 rounding may differ between two runs of the physics: compare the
