@@ -462,11 +462,22 @@ B2C_FN int b2c_hfield(B2CCon* out, b2c_real margin, const b2c_real* hp, const b2
   const b2c_real reach = rbound + margin;
   if (c[2] - reach > hsize[2] || c[2] + reach < -hsize[3]) return 0;
   if (c[0] - reach > hsize[0] || c[0] + reach < -hsize[0] || c[1] - reach > hsize[1] || c[1] + reach < -hsize[1]) return 0;
+  // extent of the inflated geom along the field's axes (six support points): only the cells under its footprint
+  // can touch it, and only prisms that rise to within `margin` of its lowest point
+  b2c_real lo[3], hi[3];
+  for (int k = 0; k < 3; k++) {
+    b2c_real ax[3] = {hR[k], hR[3 + k], hR[6 + k]}, nax[3] = {-ax[0], -ax[1], -ax[2]}, p[3];
+    b2c_support(G, ax, p);
+    hi[k] = (p[0] - hp[0]) * ax[0] + (p[1] - hp[1]) * ax[1] + (p[2] - hp[2]) * ax[2] + rg + margin;
+    b2c_support(G, nax, p);
+    lo[k] = (p[0] - hp[0]) * ax[0] + (p[1] - hp[1]) * ax[1] + (p[2] - hp[2]) * ax[2] - rg - margin;
+  }
+  if (lo[2] > hsize[2] || hi[2] < -hsize[3] || lo[0] > hsize[0] || hi[0] < -hsize[0] || lo[1] > hsize[1] || hi[1] < -hsize[1]) return 0;
   const b2c_real dx = 2 * hsize[0] / (b2c_real)(ncol - 1), dy = 2 * hsize[1] / (b2c_real)(nrow - 1);
-  int c0 = (int)((c[0] - reach + hsize[0]) / dx), c1 = (int)((c[0] + reach + hsize[0]) / dx);
-  int r0 = (int)((c[1] - reach + hsize[1]) / dy), r1 = (int)((c[1] + reach + hsize[1]) / dy);
-  if (c[0] - reach + hsize[0] < 0) c0 = 0;
-  if (c[1] - reach + hsize[1] < 0) r0 = 0;
+  int c0 = (int)((lo[0] + hsize[0]) / dx), c1 = (int)((hi[0] + hsize[0]) / dx);
+  int r0 = (int)((lo[1] + hsize[1]) / dy), r1 = (int)((hi[1] + hsize[1]) / dy);
+  if (lo[0] + hsize[0] < 0) c0 = 0;
+  if (lo[1] + hsize[1] < 0) r0 = 0;
   if (c1 > ncol - 2) c1 = ncol - 2;
   if (r1 > nrow - 2) r1 = nrow - 2;
   int n = 0, seq = 0;
@@ -485,7 +496,7 @@ B2C_FN int b2c_hfield(B2CCon* out, b2c_real margin, const b2c_real* hp, const b2
         b2c_real ly[3] = {y0, t ? y0 + dy : y0, y0 + dy};
         b2c_real lz[3] = {z00, t ? z11 : z01, t ? z10 : z11};
         b2c_real zmax = lz[0] > lz[1] ? (lz[0] > lz[2] ? lz[0] : lz[2]) : (lz[1] > lz[2] ? lz[1] : lz[2]);
-        if (c[2] - reach > zmax) continue;
+        if (lo[2] > zmax) continue;
         b2c_real pc[3] = {0, 0, 0};
         for (int i = 0; i < 6; i++) {
           b2c_real l[3] = {lx[i % 3], ly[i % 3], i < 3 ? lz[i] : -hsize[3]};

@@ -1365,7 +1365,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     for (int p0 = 0; p0 < m.npair; p0 += 32) {
       int p = p0 + lane;
       bool hit = false;
-      const unsigned pw = pw_next;  // slot1 | slot2 << 12 | (geom1 is a plane) << 31
+      const unsigned pw = pw_next;  // slot1 | slot2 << 12 | (geom1 is a height field) << 30 | (geom1 is a plane) << 31
       if (p + 32 < m.npair) pw_next = m.pair_word[p + 32];  // next batch's word is in flight during this one
       if (p < m.npair) {
         const float* a = gpose + GP * (pw & 0xfffu);
@@ -1375,6 +1375,14 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         if (pw >> 31) {
           float n[3] = {a[3 + 2], a[3 + 5], a[3 + 8]};
           hit = dot3(dif, n) <= margin + b[12];
+        } else if (CVX && (pw >> 30 & 1u)) {
+          // height field: the geom's bounding sphere against the field's box (a terrain is a grid of fields whose
+          // bounding spheres all contain the robot: the sphere test would pass every neighbour to the narrowphase)
+          const float* hs = m.hfield_size + 4 * m.geom_dataid[m.pair_geom1[p]];
+          const float reach = margin + b[12];
+          const float lx = a[3] * dif[0] + a[6] * dif[1] + a[9] * dif[2], ly = a[4] * dif[0] + a[7] * dif[1] + a[10] * dif[2];
+          const float lz = a[5] * dif[0] + a[8] * dif[1] + a[11] * dif[2];
+          hit = fabsf(lx) <= hs[0] + reach && fabsf(ly) <= hs[1] + reach && lz - reach <= hs[2] && lz + reach >= -hs[3];
         } else {
           float bound = margin + a[12] + b[12];
           hit = dot3(dif, dif) <= bound * bound;

@@ -89,7 +89,7 @@ struct DevModel {
   const int *site_bodyid;
   const int *actuator_trnid, *actuator_ctrllimited, *actuator_forcelimited;
   const int *pair_geom1, *pair_geom2;
-  const unsigned* pair_word;  // broadphase record per pair: slot1 | slot2 << 12 | (geom1 is a plane) << 31
+  const unsigned* pair_word;  // broadphase record per pair: slot1 | slot2 << 12 | (geom1 is a height field) << 30 | (geom1 is a plane) << 31
   // grid-static collision set (terrain): geoms welded to the world, found through a uniform xy grid
   int nstatic, ndyn, nposegeom, grid_nx, grid_ny;
   float grid_x0, grid_y0, grid_cell;

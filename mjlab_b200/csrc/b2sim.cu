@@ -615,7 +615,8 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
     std::vector<unsigned> pw(std::max(m.npair, 1), 0u);
     for (int p = 0; p < m.npair; p++) {
       int g1 = s->mi["pair_geom1"][p], g2 = s->mi["pair_geom2"][p];
-      pw[p] = (unsigned)cslot[g1] | ((unsigned)cslot[g2] << 12) | (s->mi["geom_type"][g1] == G_PLANE ? 0x80000000u : 0u);
+      pw[p] = (unsigned)cslot[g1] | ((unsigned)cslot[g2] << 12) | (s->mi["geom_type"][g1] == G_PLANE ? 0x80000000u : 0u) |
+              (s->mi["geom_type"][g1] == G_HFIELD ? 0x40000000u : 0u);
     }
     rc |= dev_upload<unsigned>(s, pw, &m.pair_word);
   }

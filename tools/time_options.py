@@ -45,6 +45,6 @@ run("4 streams", dict(base, split_streams=4))
 run("2 streams, psync off", dict(base, phase_sync=0))
 run("2 streams, full solver", dict(base, full_solver=1))
 run("2 streams, ls_relstep off", dict(base, ls_relstep=0))
-run("psync level 1", dict(base, ls_relstep=1, phase_sync=1))
+run("reorder once per step_n", dict(base, ls_relstep=1, reorder_every_substep=0))
 run("psync level 3", dict(base, ls_relstep=1, phase_sync=3))
 run("default again", dict(base, ls_relstep=1))
