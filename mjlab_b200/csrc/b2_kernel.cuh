@@ -235,9 +235,14 @@ __device__ __noinline__ void ldl_factor(float* A, float* invdiag, int n, const u
       // 4x4 diagonal block (pivot order kt, kt-1, kt-2, kt-3), factorised redundantly by every lane
       float a10 = 0.f, a11 = 1.f, a20 = 0.f, a21 = 0.f, a22 = 1.f, a30 = 0.f, a31 = 0.f, a32 = 0.f, a33 = 1.f;
       float a00 = A[rb0 + kt];
-      if (nb > 1) { a10 = A[rb0 + kt - 1]; a11 = A[rb1 + kt - 1]; }
-      if (nb > 2) { a20 = A[rb0 + kt - 2]; a21 = A[rb1 + kt - 2]; a22 = A[rb2 + kt - 2]; }
-      if (nb > 3) { a30 = A[rb0 + kt - 3]; a31 = A[rb1 + kt - 3]; a32 = A[rb2 + kt - 3]; a33 = A[rb3 + kt - 3]; }
+      if (nb == 4) {  // (every block but possibly the last: one uniform branch instead of three predicated groups)
+        a10 = A[rb0 + kt - 1]; a11 = A[rb1 + kt - 1];
+        a20 = A[rb0 + kt - 2]; a21 = A[rb1 + kt - 2]; a22 = A[rb2 + kt - 2];
+        a30 = A[rb0 + kt - 3]; a31 = A[rb1 + kt - 3]; a32 = A[rb2 + kt - 3]; a33 = A[rb3 + kt - 3];
+      } else {
+        if (nb > 1) { a10 = A[rb0 + kt - 1]; a11 = A[rb1 + kt - 1]; }
+        if (nb > 2) { a20 = A[rb0 + kt - 2]; a21 = A[rb1 + kt - 2]; a22 = A[rb2 + kt - 2]; }
+      }
       __syncwarp();  // every lane holds the block before any panel store touches it
       dv[0] = b2_rcp(fmaxf(a00, MINVAL));
       Lb[0] = a10 * dv[0];
@@ -2123,10 +2128,11 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       float gtol = m.tolerance * m.ls_tolerance * sn / scale;
       // each lane keeps its rows in registers for the whole search (<= 2 contacts + 1 limit per lane)
       float lsJ[9], lsV[9], lsDV[9];  // residual, its slope, and D * slope per row
+      const bool wide = ncon > 32, anylim = nlim > 0;  // second contact per lane / limit rows present (warp-uniform)
 #pragma unroll
       for (int q = 0; q < 2; q++) {
         int c = lane + 32 * q;
-        bool ok = c < ncon;
+        bool ok = c < ncon && (q == 0 || wide);
         const float D = ok ? con[CD * MC + c] : 0.f;
 #pragma unroll
         for (int r = 0; r < 4; r++) {
@@ -2144,9 +2150,20 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       auto ls_eval = [&](float al, float& d0, float& d1) {
         float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-        for (int q = 0; q < 9; q++) {
+        for (int q = 0; q < 4; q++) {
           float x = fmaf(al, lsV[q], lsJ[q]);
           if (x < 0.f) { a0 = fmaf(lsDV[q], x, a0); a1 = fmaf(lsDV[q], lsV[q], a1); }
+        }
+        if (wide) {  // (environments with at most 32 contacts - nearly all - skip the second contact's rows)
+#pragma unroll
+          for (int q = 4; q < 8; q++) {
+            float x = fmaf(al, lsV[q], lsJ[q]);
+            if (x < 0.f) { a0 = fmaf(lsDV[q], x, a0); a1 = fmaf(lsDV[q], lsV[q], a1); }
+          }
+        }
+        if (anylim) {
+          float x = fmaf(al, lsV[8], lsJ[8]);
+          if (x < 0.f) { a0 = fmaf(lsDV[8], x, a0); a1 = fmaf(lsDV[8], lsV[8], a1); }
         }
         // rows beyond the register window (ncon > 64 or nlim > 32)
         #pragma unroll 1
