@@ -497,6 +497,22 @@ B2C_FN int b2c_hfield(B2CCon* out, b2c_real margin, const b2c_real* hp, const b2
         b2c_real lz[3] = {z00, t ? z11 : z01, t ? z10 : z11};
         b2c_real zmax = lz[0] > lz[1] ? (lz[0] > lz[2] ? lz[0] : lz[2]) : (lz[1] > lz[2] ? lz[1] : lz[2]);
         if (lo[2] > zmax) continue;
+        {
+          // the prism lies below the plane of its top triangle: a geom whose lowest point along that plane's normal
+          // clears it by more than the margin cannot touch (rejects the prisms under a limb that hovers over a slope)
+          b2c_real e1[3] = {lx[1] - lx[0], ly[1] - ly[0], lz[1] - lz[0]}, e2[3] = {lx[2] - lx[0], ly[2] - ly[0], lz[2] - lz[0]}, nl[3];
+          b2c_cross(nl, e1, e2);
+          if (nl[2] < 0) { nl[0] = -nl[0]; nl[1] = -nl[1]; nl[2] = -nl[2]; }
+          b2c_real nw[3], dn[3], q[3];
+          for (int k = 0; k < 3; k++) nw[k] = hR[3 * k] * nl[0] + hR[3 * k + 1] * nl[1] + hR[3 * k + 2] * nl[2];
+          dn[0] = -nw[0]; dn[1] = -nw[1]; dn[2] = -nw[2];
+          b2c_support(G, dn, q);
+          b2c_real p0[3];
+          for (int k = 0; k < 3; k++) p0[k] = hp[k] + hR[3 * k] * lx[0] + hR[3 * k + 1] * ly[0] + hR[3 * k + 2] * lz[0];
+          const b2c_real nn = B2C_SQRT(b2c_dot(nw, nw));
+          const b2c_real h = (q[0] - p0[0]) * nw[0] + (q[1] - p0[1]) * nw[1] + (q[2] - p0[2]) * nw[2];
+          if (h > (rg + margin) * nn) { seq++; continue; }
+        }
         b2c_real pc[3] = {0, 0, 0};
         for (int i = 0; i < 6; i++) {
           b2c_real l[3] = {lx[i % 3], ly[i % 3], i < 3 ? lz[i] : -hsize[3]};

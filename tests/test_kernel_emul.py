@@ -184,7 +184,7 @@ def test_emulated_kernel_obstacle_course(lib):
   load_oracle(o, st)
   sim.load(st)
   seen = 0
-  for it in range(6):
+  for it in range(4):
     o.forward()
     sim.forward()
     nc = o.ncon.ravel()
