@@ -1366,12 +1366,17 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     const float* gmar = MP(geom_margin);
     int ncand = 0;
     unsigned pw_next = lane < m.npair ? m.pair_word[lane] : 0u;
+    float4 hb_next = (CVX && m.pair_hbox != nullptr && lane < m.npair) ? m.pair_hbox[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
     #pragma unroll 1
     for (int p0 = 0; p0 < m.npair; p0 += 32) {
       int p = p0 + lane;
       bool hit = false;
       const unsigned pw = pw_next;  // slot1 | slot2 << 12 | (geom1 is a height field) << 30 | (geom1 is a plane) << 31
-      if (p + 32 < m.npair) pw_next = m.pair_word[p + 32];  // next batch's word is in flight during this one
+      const float4 hb = hb_next;    // height-field pairs: the field's box (rx, ry, elevation, base)
+      if (p + 32 < m.npair) {       // next batch's records are in flight during this one
+        pw_next = m.pair_word[p + 32];
+        if (CVX && m.pair_hbox != nullptr) hb_next = m.pair_hbox[p + 32];
+      }
       if (p < m.npair) {
         const float* a = gpose + GP * (pw & 0xfffu);
         const float* b = gpose + GP * ((pw >> 12) & 0xfffu);
@@ -1383,7 +1388,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         } else if (CVX && (pw >> 30 & 1u)) {
           // height field: the geom's bounding sphere against the field's box (a terrain is a grid of fields whose
           // bounding spheres all contain the robot: the sphere test would pass every neighbour to the narrowphase)
-          const float* hs = m.hfield_size + 4 * m.geom_dataid[m.pair_geom1[p]];
+          const float hs[4] = {hb.x, hb.y, hb.z, hb.w};
           const float reach = margin + b[12];
           const float lx = a[3] * dif[0] + a[6] * dif[1] + a[9] * dif[2], ly = a[4] * dif[0] + a[7] * dif[1] + a[10] * dif[2];
           const float lz = a[5] * dif[0] + a[8] * dif[1] + a[11] * dif[2];

@@ -89,6 +89,7 @@ struct DevModel {
   const int *site_bodyid;
   const int *actuator_trnid, *actuator_ctrllimited, *actuator_forcelimited;
   const int *pair_geom1, *pair_geom2;
+  const float4* pair_hbox;    // per pair: the box (rx, ry, elevation, base) of geom 1 when it is a height field (else zeros); nullptr without fields
   const unsigned* pair_word;  // broadphase record per pair: slot1 | slot2 << 12 | (geom1 is a height field) << 30 | (geom1 is a plane) << 31
   // grid-static collision set (terrain): geoms welded to the world, found through a uniform xy grid
   int nstatic, ndyn, nposegeom, grid_nx, grid_ny;

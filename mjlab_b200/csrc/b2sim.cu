@@ -619,6 +619,21 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
               (s->mi["geom_type"][g1] == G_HFIELD ? 0x40000000u : 0u);
     }
     rc |= dev_upload<unsigned>(s, pw, &m.pair_word);
+    bool anyhf = false;
+    std::vector<float> hb((size_t)std::max(m.npair, 1) * 4, 0.f);
+    for (int p = 0; p < m.npair; p++) {
+      int g1 = s->mi["pair_geom1"][p];
+      if (s->mi["geom_type"][g1] != G_HFIELD) continue;
+      anyhf = true;
+      const int id = s->mi["geom_dataid"][g1];
+      for (int k = 0; k < 4; k++) hb[4 * (size_t)p + k] = (float)s->mf["hfield_size"][4 * (size_t)id + k];
+    }
+    m.pair_hbox = nullptr;
+    if (anyhf) {
+      const float* hp = nullptr;
+      rc |= dev_upload<float>(s, hb, &hp);
+      m.pair_hbox = (const float4*)hp;
+    }
   }
   rc |= dev_upload<int>(s, cslot, &m.geom_cslot);
   rc |= dev_upload<int>(s, cgeom, &m.cgeom);

@@ -21,6 +21,7 @@
 #define __align__(n) __attribute__((aligned(n)))
 
 struct float4 { float x, y, z, w; };
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 struct uint3 { unsigned x, y, z; };
 struct dim3 {
   unsigned x, y, z;

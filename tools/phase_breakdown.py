@@ -6,10 +6,14 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import torch
 from mjlab_b200.envs import VelocityEnvCfg, VelocityFlatEnv
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-env = VelocityFlatEnv(VelocityEnvCfg(num_envs=n), device="cuda:0")
+import os
+_wl = os.environ.get("B2_WORKLOAD", "B")  # B: G1 flat, E: Go1 rough boxes, F: Go1 rough boxes + height fields
+_kw = dict(B={}, E=dict(robot="go1", terrain="rough"), F=dict(robot="go1", terrain="rough_hf"))[_wl]
+env = VelocityFlatEnv(VelocityEnvCfg(num_envs=n, **_kw), device="cuda:0")
+_nu = env.nu if hasattr(env, "nu") else (29 if _wl == "B" else 12)
 g = torch.Generator(device="cuda:0"); g.manual_seed(0)
 for _ in range(int(sys.argv[2]) if len(sys.argv) > 2 else 100):
-  env.step(torch.rand((n, 29), generator=g, device="cuda:0") * 2 - 1)
+  env.step(torch.rand((n, _nu), generator=g, device="cuda:0") * 2 - 1)
 sim = env.sim
 for kv in sys.argv[3:]:
   k, v = kv.split("=")
