@@ -1,7 +1,7 @@
 // cuda_emul.h — host stand-ins for the CUDA runtime calls and the kernel-launch syntax used by
 // mjlab_b200/csrc/b2sim.cu (tests/emul/build.py rewrites `k<<<g, b, s, st>>>(args)` into EMUL_LAUNCH).
-// "Device" memory is host memory, streams and events do nothing, CTAs of a launch run one after the other on a
-// pool of blockDim.x host threads.  Test infrastructure only.
+// "Device" memory is host memory, streams and events do nothing, CTAs of a launch run one after the other, each on
+// blockDim.x fibers (warp_emul.h).  Test infrastructure only.
 #pragma once
 #include "warp_emul.h"
 
@@ -53,44 +53,22 @@ template <class F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiproces
 inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 2; return 0; }
 
 namespace cuda_emul {
-struct Job { std::function<void()>* body; int tid; };
-inline void* trampoline(void* p) {
-  Job* j = (Job*)p;
-  warp_emul::tl().lane = j->tid & 31;
-  warp_emul::tl().warp = j->tid >> 5;
-  emul_threadIdx() = {(unsigned)j->tid, 0, 0};
-  (*j->body)();
-  return nullptr;
-}
-// run `kernel(args...)` for every CTA of the grid, one CTA at a time, on block.x host threads
+// run `kernel(args...)` for every CTA of the grid, one CTA at a time, on block.x fibers
 template <class K, class... A>
 inline void launch(K kernel, dim3 grid, dim3 block, size_t smem, A... args) {
   warp_emul::Ctx& c = warp_emul::ctx();
   const int nt = (int)block.x, nw = (nt + 31) / 32;
   emul_blockDim() = block;
   emul_gridDim() = grid;
-  for (int w = 0; w < nw; w++) pthread_barrier_init(&c.w[w].bar, nullptr, (unsigned)((w + 1) * 32 <= nt ? 32 : nt - w * 32));
-  pthread_barrier_init(&c.cta, nullptr, (unsigned)nt);
+  for (int w = 0; w < nw; w++) c.w[w].bar = warp_emul::Bar{0, (w + 1) * 32 <= nt ? 32 : nt - w * 32, 0};
+  c.cta = warp_emul::Bar{0, nt, 0};
   c.dyn_smem = aligned_alloc(128, ((smem + 127) & ~(size_t)127) + 128);
-  std::function<void()> body = [&]() {
-    for (unsigned b = 0; b < grid.x; b++) {
-      emul_blockIdx() = {b, 0, 0};
-      kernel(args...);
-      pthread_barrier_wait(&c.cta);  // the next CTA reuses the shared-memory block
-    }
-  };
-  std::vector<pthread_t> th(nt);
-  std::vector<Job> jobs(nt);
-  pthread_attr_t attr;
-  pthread_attr_init(&attr);
-  pthread_attr_setstacksize(&attr, 1 << 20);
-  for (int t = 0; t < nt; t++) { jobs[t] = {&body, t}; pthread_create(&th[t], &attr, trampoline, &jobs[t]); }
-  for (int t = 0; t < nt; t++) pthread_join(th[t], nullptr);
-  pthread_attr_destroy(&attr);
+  for (unsigned b = 0; b < grid.x; b++) {
+    emul_blockIdx() = {b, 0, 0};
+    warp_emul::run_fibers(nt, [&]() { kernel(args...); });
+  }
   free(c.dyn_smem);
   c.dyn_smem = nullptr;
-  for (int w = 0; w < nw; w++) pthread_barrier_destroy(&c.w[w].bar);
-  pthread_barrier_destroy(&c.cta);
 }
 }  // namespace cuda_emul
 #define EMUL_LAUNCH(kernel, grid, block, smem, stream, ...) cuda_emul::launch(kernel, dim3(grid), dim3(block), (size_t)(smem), __VA_ARGS__)

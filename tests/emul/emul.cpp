@@ -1,4 +1,4 @@
-// emul.cpp — C entry points that run warp-level device helpers of b2_kernel.cuh on 32 host threads.
+// emul.cpp — C entry points that run warp-level device helpers of b2_kernel.cuh on one emulated warp (32 fibers).
 #define B2_HOST_EMULATION
 #include "warp_emul.h"
 
@@ -9,21 +9,9 @@
 #include "../../mjlab_b200/csrc/b2_tables.h"
 
 namespace {
-struct Job { std::function<void(int)>* fn; int lane; };
-void* trampoline(void* p) {
-  Job* j = (Job*)p;
-  warp_emul::tl().lane = j->lane;
-  warp_emul::tl().warp = 0;
-  (*j->fn)(j->lane);
-  return nullptr;
-}
 void run_warp(std::function<void(int)> fn) {
-  pthread_barrier_init(&warp_emul::ctx().w[0].bar, nullptr, 32);
-  pthread_t th[32];
-  Job jobs[32];
-  for (int l = 0; l < 32; l++) { jobs[l] = {&fn, l}; pthread_create(&th[l], nullptr, trampoline, &jobs[l]); }
-  for (int l = 0; l < 32; l++) pthread_join(th[l], nullptr);
-  pthread_barrier_destroy(&warp_emul::ctx().w[0].bar);
+  warp_emul::ctx().w[0].bar = warp_emul::Bar{0, 32, 0};
+  warp_emul::run_fibers(32, [&]() { fn(warp_emul::lane()); });
 }
 }  // namespace
 

@@ -1,11 +1,10 @@
 // warp_emul.h — just enough of the CUDA programming model to run the device code of mjlab_b200/csrc on the
-// host: a CTA is a pool of host threads, each warp of 32 has its own pthread barrier on which shuffles,
+// host: the threads of a CTA are fibers on one host thread, each warp of 32 has its own barrier on which shuffles,
 // ballots and __syncwarp are built, __syncthreads is one more barrier.  Test infrastructure only
 // (tests/test_warp_emul.py, tests/test_kernel_emul.py); never part of the product.
 // Requirement inherited from the GPU code: every lane reaches every warp-synchronous call.
 #pragma once
 #include <math.h>
-#include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -28,21 +27,103 @@ struct dim3 {
   dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
 };
 
+// ---- fibers: every CUDA thread of a CTA is a user-level context on ONE host thread; a warp- or CTA-level
+// synchronisation point is a cooperative yield until all participants have arrived.  (The first version ran 32 host
+// threads per warp on pthread barriers: every shuffle cost a round of kernel context switches, ~100x slower.)
+extern "C" void b2_fiber_switch(void** save_sp, void* load_sp);
+#if defined(__x86_64__)
+asm(R"(
+.text
+.globl b2_fiber_switch
+.type b2_fiber_switch,@function
+b2_fiber_switch:
+  pushq %rbp
+  pushq %rbx
+  pushq %r12
+  pushq %r13
+  pushq %r14
+  pushq %r15
+  movq %rsp, (%rdi)
+  movq %rsi, %rsp
+  popq %r15
+  popq %r14
+  popq %r13
+  popq %r12
+  popq %rbx
+  popq %rbp
+  ret
+.size b2_fiber_switch,.-b2_fiber_switch
+)");
+#else
+#error "tests/emul needs x86-64 (hand-written context switch)"
+#endif
+
+#include <functional>
+#include <sys/mman.h>
+
 namespace warp_emul {
+struct Bar { int count = 0, n = 0; unsigned gen = 0; };
 struct WarpBar {
-  pthread_barrier_t bar;
+  Bar bar;
   unsigned long long slot[32];
 };
 struct Ctx {
   WarpBar w[32];          // up to 1024 threads per CTA
-  pthread_barrier_t cta;
+  Bar cta;
   void* dyn_smem = nullptr;
 };
 inline Ctx& ctx() { static Ctx c; return c; }
 struct Tl { int lane = 0, warp = 0; };
-inline Tl& tl() { static thread_local Tl t; return t; }
+struct Fiber { void* sp = nullptr; Tl tl; uint3 tid = {0, 0, 0}; bool done = false; };
+struct Sched {
+  Fiber* f = nullptr; int n = 0, cur = 0; void* main_sp = nullptr; std::function<void()>* body = nullptr;
+  Fiber host;  // state seen by code that runs outside any launch
+};
+inline Sched& sched() { static Sched s; return s; }
+inline Fiber& self() { Sched& s = sched(); return s.f ? s.f[s.cur] : s.host; }
+inline Tl& tl() { return self().tl; }
 inline int& lane() { return tl().lane; }
-inline void sync() { pthread_barrier_wait(&ctx().w[tl().warp].bar); }
+inline void yield() { Sched& s = sched(); b2_fiber_switch(&s.f[s.cur].sp, s.main_sp); }
+inline void bar_wait(Bar& b) {
+  const unsigned g = b.gen;
+  if (++b.count == b.n) { b.count = 0; b.gen++; }
+  else while (b.gen == g) yield();
+}
+inline void fiber_entry() {
+  Sched& s = sched();
+  (*s.body)();
+  s.f[s.cur].done = true;
+  for (;;) yield();
+}
+// run `body` on nt fibers (tid 0..nt-1) to completion, round robin
+inline void run_fibers(int nt, std::function<void()> body) {
+  Sched& s = sched();
+  const size_t stack = 512 << 10;
+  char* mem = (char*)mmap(nullptr, stack * (size_t)nt, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+  Fiber* f = new Fiber[nt];
+  for (int t = 0; t < nt; t++) {
+    f[t].tl.lane = t & 31; f[t].tl.warp = t >> 5; f[t].tid = {(unsigned)t, 0, 0};
+    void** top = (void**)(mem + stack * (size_t)(t + 1));  // 16-byte aligned
+    top[-1] = nullptr;                     // alignment slot: after `ret` rsp is 8 mod 16, as after a call
+    top[-2] = (void*)&fiber_entry;
+    for (int k = 3; k <= 8; k++) top[-k] = nullptr;  // rbp rbx r12 r13 r14 r15
+    f[t].sp = (void*)(top - 8);
+  }
+  s.f = f; s.n = nt; s.body = &body;
+  for (int left = nt; left > 0;) {
+    left = 0;
+    for (int t = 0; t < nt; t++) {
+      if (f[t].done) continue;
+      s.cur = t;
+      b2_fiber_switch(&s.main_sp, f[t].sp);
+      left += !f[t].done;
+    }
+  }
+  s.f = nullptr; s.n = 0; s.body = nullptr;
+  delete[] f;
+  munmap(mem, stack * (size_t)nt);
+}
+inline void sync() { bar_wait(ctx().w[tl().warp].bar); }
 template <class T>
 inline T exchange(T v, int src) {
   static_assert(sizeof(T) <= 8, "shuffle payload");
@@ -56,8 +137,8 @@ inline T exchange(T v, int src) {
 }
 }  // namespace warp_emul
 
-inline uint3& emul_threadIdx() { static thread_local uint3 v = {0, 0, 0}; return v; }
-inline uint3& emul_blockIdx() { static thread_local uint3 v = {0, 0, 0}; return v; }
+inline uint3& emul_threadIdx() { return warp_emul::self().tid; }
+inline uint3& emul_blockIdx() { static uint3 v = {0, 0, 0}; return v; }
 inline dim3& emul_blockDim() { static dim3 v; return v; }
 inline dim3& emul_gridDim() { static dim3 v; return v; }
 #define threadIdx (emul_threadIdx())
@@ -66,7 +147,7 @@ inline dim3& emul_gridDim() { static dim3 v; return v; }
 #define gridDim (emul_gridDim())
 
 inline void __syncwarp(unsigned = 0xffffffffu) { warp_emul::sync(); }
-inline void __syncthreads() { pthread_barrier_wait(&warp_emul::ctx().cta); }
+inline void __syncthreads() { warp_emul::bar_wait(warp_emul::ctx().cta); }
 inline int __syncthreads_or(int pred) {
   static int vote = 0;
   if (pred) __atomic_store_n(&vote, 1, __ATOMIC_RELAXED);

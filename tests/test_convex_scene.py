@@ -40,7 +40,7 @@ def test_emulated_kernel_mesh_and_hfield_contacts():
 
   lib = _load()
   m, anchors, hf = convex_scene()
-  n = 5
+  n = 24
   sim = EmulSim(lib, m, n, ncon=64)
   o = Oracle(m, nworld=n, maxcon=int(sim.option("maxcon")))
   st = convex_states(m, anchors, hf, n, seed=3)

@@ -83,7 +83,7 @@ def test_emulated_kernel_on_height_field_terrain():
 
   lib = _load()
   m = load_compiled("go1_hf_small")
-  n = 5
+  n = 32
   sim = EmulSim(lib, m, n, ncon=48)
   o = Oracle(m, nworld=n, maxcon=int(sim.option("maxcon")))
   st = hfield_states(m, n, 21, 1.5)

@@ -1,7 +1,7 @@
 """The whole product library (b2sim.cu + the fused step kernel) compiled for the host (tests/emul/build.py:
-g++ against cuda_emul.h, one warp per CTA on 32 lock-step threads) and driven through its C ABI — the same
-parity checks as tests/test_parity_gpu.py, without a GPU.  Slow (every shuffle is a pthread barrier), so the
-batches are tiny; tolerances are the GPU tests' (fp32 engine vs fp64 oracle)."""
+g++ against cuda_emul.h, one warp per CTA, the 32 lanes as fibers on one host thread) and driven through its C ABI —
+the same parity checks as tests/test_parity_gpu.py, without a GPU; tolerances are the GPU tests' (fp32 engine vs
+fp64 oracle)."""
 
 import ctypes
 import sys
@@ -184,7 +184,7 @@ def test_emulated_kernel_obstacle_course(lib):
   load_oracle(o, st)
   sim.load(st)
   seen = 0
-  for it in range(4):
+  for it in range(8):
     o.forward()
     sim.forward()
     nc = o.ncon.ravel()
@@ -311,15 +311,15 @@ def test_emulated_env_native_mdp_kernels_match_torch_reference(monkeypatch):
 
   monkeypatch.setattr(ve, "Simulation", EmulSimulation)
   monkeypatch.setattr(native, "check", lambda rc: (_ for _ in ()).throw(RuntimeError("b2sim call failed")) if rc else None)
-  cfg = dict(robot="go1", num_envs=2, decimation=1, fall_angle=0.2, push_interval_s=(0.005, 0.015), episode_length_s=0.01)
+  cfg = dict(robot="go1", num_envs=6, decimation=2, fall_angle=0.2, push_interval_s=(0.01, 0.03), episode_length_s=0.03)
   a = ve.VelocityFlatEnv(ve.VelocityEnvCfg(**cfg), device="cpu", native_mdp=False)
   b = ve.VelocityFlatEnv(ve.VelocityEnvCfg(**cfg), device="cpu", native_mdp=True)
   assert torch.equal(a.sim.data.qpos[:], b.sim.data.qpos[:])
   g = torch.Generator()
   g.manual_seed(3)
   resets = 0
-  for k in range(3):
-    act = torch.rand((2, 12), generator=g) * 2 - 1
+  for k in range(10):
+    act = torch.rand((6, 12), generator=g) * 2 - 1
     oa, ra, ta, ua, _ = a.step(act)
     ob, rb, tb, ub, _ = b.step(act)
     assert torch.equal(ua, ub)
@@ -331,7 +331,7 @@ def test_emulated_env_native_mdp_kernels_match_torch_reference(monkeypatch):
     for f in ("qpos", "qvel", "qacc_warmstart", "ctrl"):  # resynchronise: the MDP logic is what is under test
       getattr(b.sim.data, f)[:] = getattr(a.sim.data, f)[:]
     resets += int((ta | ua).sum())
-  assert resets >= 2  # time-outs (every 2 steps) exercised the masked reset path
+  assert resets >= 6  # time-outs (every 2 steps) exercised the masked reset path
   a.close()
   b.close()
 
@@ -346,15 +346,15 @@ def test_emulated_tracking_env_native_mdp_kernels_match_torch_reference(monkeypa
 
   monkeypatch.setattr(te, "Simulation", EmulSimulation)
   monkeypatch.setattr(native, "check", lambda rc: (_ for _ in ()).throw(RuntimeError("b2sim call failed")) if rc else None)
-  cfg = dict(num_envs=2, decimation=1, episode_length_s=0.015, clip_frames=4, push_interval_s=(0.004, 0.012))
+  cfg = dict(num_envs=4, decimation=1, episode_length_s=0.015, clip_frames=4, push_interval_s=(0.004, 0.012))
   a = te.TrackingFlatEnv(te.TrackingEnvCfg(**cfg), device="cpu", native_mdp=False)
   b = te.TrackingFlatEnv(te.TrackingEnvCfg(**cfg), device="cpu", native_mdp=True)
   assert torch.equal(a.sim.data.qpos[:], b.sim.data.qpos[:])
   g = torch.Generator()
   g.manual_seed(5)
   events = dict(term=0, trunc=0, ended=0, push=0)
-  for k in range(5):
-    act = torch.rand((2, a.nu), generator=g) * 2 - 1
+  for k in range(8):
+    act = torch.rand((4, a.nu), generator=g) * 2 - 1
     if k == 2:  # a fall: the anchor drops below the clip's by more than 0.25 m
       for e in (a, b):
         e.sim.data.qpos[1, 2] -= 0.4
@@ -372,7 +372,7 @@ def test_emulated_tracking_env_native_mdp_kernels_match_torch_reference(monkeypa
     assert torch.allclose(a.log_row, b.log_row, atol=2e-5)
     for f in ("qpos", "qvel", "ctrl"):
       assert torch.allclose(getattr(a.sim.data, f)[:], getattr(b.sim.data, f)[:], atol=1e-5), (k, f)
-    assert oa.shape == ob.shape == (2, 160) and xa["critic"].shape == xb["critic"].shape == (2, 286)
+    assert oa.shape == ob.shape == (4, 160) and xa["critic"].shape == xb["critic"].shape == (4, 286)
     assert torch.allclose(oa, ob, atol=1e-4), (k, (oa - ob).abs().max())
     assert torch.allclose(xa["critic"], xb["critic"], atol=1e-4), (k, (xa["critic"] - xb["critic"]).abs().max())
     events["term"] += int(ta.sum()); events["trunc"] += int(ua.sum())
