@@ -68,13 +68,14 @@ def robot_xml(rng, limbs, joints):
   </worldbody><actuator>{acts}</actuator></mujoco>"""
 
 
-def obstacle_runs(lib, seeds, worlds, steps):
+def obstacle_runs(lib, seeds, worlds, steps, keep_going=False):
   """Free spheres / capsules / boxes in random orientations among 20+ static boxes, spheres and capsules on a plane
   (tests/test_boxes_terrain.py: obstacle_course_xml): pair table + static grid + every primitive pair type."""
   from test_boxes_terrain import obstacle_course_xml
 
+  bad = []
   for seed in range(1, seeds + 1):
-    m = Spec.from_string(obstacle_course_xml(seed=seed, nobst=20 + seed, nobj=9)).compile()
+    m = Spec.from_string(obstacle_course_xml(seed=seed, nobst=20 + min(seed, 40), nobj=9)).compile()
     n = worlds
     sim = EmulSim(lib, m, n, ncon=96)
     o = Oracle(m, nworld=n, maxcon=int(sim.option("maxcon")), njmax=2000)
@@ -93,7 +94,12 @@ def obstacle_runs(lib, seeds, worlds, steps):
     for _ in range(max(steps, 1) + 3):
       o.forward()
       sim.forward()
-      assert (sim.field("ncon").ravel() == o.ncon.ravel()).all(), (seed, sim.field("ncon").ravel(), o.ncon.ravel())
+      if not (sim.field("ncon").ravel() == o.ncon.ravel()).all():
+        # (a capsule lying along a box face reports one contact or one per end depending on which side of the
+        # 1e-3 r length threshold the bisection lands: a tie of the rule, not an arithmetic difference)
+        assert keep_going, (seed, sim.field("ncon").ravel(), o.ncon.ravel())
+        bad.append(seed)
+        break
       worst = max(worst, float(relerr(sim.field("qacc"), o.qacc, floor=10.0).max()))
       seen = max(seen, int(o.ncon.max()))
       o.step()
@@ -103,7 +109,8 @@ def obstacle_runs(lib, seeds, worlds, steps):
     print(f"seed {seed}: nstatic={int(m.nstatic)} npair={int(m.npair)} max ncon {seen} worst qacc rel err {worst:.2e}")
     assert worst < 1e-2, seed  # (capsule-box contact ends are defined to ~1e-3 m)
     sim.close()
-  print("ok")
+  print("ok" if not bad else f"contact-count ties in seeds {bad}")
+  return bad
 
 
 def main():
@@ -114,12 +121,14 @@ def main():
   ap.add_argument("--joints", type=int, default=8)
   ap.add_argument("--worlds", type=int, default=2)
   ap.add_argument("--steps", type=int, default=2)
+  ap.add_argument("--first", type=int, default=0, help="first seed")
+  ap.add_argument("--keep-going", action="store_true", help="report every failing seed instead of stopping at the first")
   a = ap.parse_args()
   lib = _load()
   if a.scene == "obstacle":
-    return obstacle_runs(lib, a.seeds, a.worlds, a.steps)
-  worst = 0.0
-  for seed in range(a.seeds):
+    return obstacle_runs(lib, a.seeds, a.worlds, a.steps, a.keep_going)
+  worst, bad = 0.0, []
+  for seed in range(a.first, a.first + a.seeds):
     rng = np.random.default_rng(seed)
     m = Spec.from_string(robot_xml(rng, a.limbs, a.joints)).compile()
     n, nv = a.worlds, int(m.nv)
@@ -136,8 +145,12 @@ def main():
     sim.load(st)
     o.forward()
     sim.forward()
-    assert (sim.field("ncon").ravel() == o.ncon.ravel()).all(), (seed, sim.field("ncon").ravel(), o.ncon.ravel())
-    assert (sim.field("nefc").ravel() == o.nefc.ravel()).all(), seed
+    if not (sim.field("ncon").ravel() == o.ncon.ravel()).all() or not (sim.field("nefc").ravel() == o.nefc.ravel()).all():
+      print(f"seed {seed}: contact / row counts differ: {sim.field('ncon').ravel().tolist()} vs {o.ncon.ravel().tolist()}")
+      assert a.keep_going, seed
+      bad.append((seed, "counts"))
+      sim.close()
+      continue
     e = float(relerr(sim.field("qacc"), o.qacc, floor=10.0).max())
     for _ in range(a.steps):
       o.step()
@@ -148,9 +161,12 @@ def main():
     worst = max(worst, e)
     print(f"seed {seed}: nv={nv} nbody={int(m.nbody)} npair={int(m.npair)} ncon={o.ncon.ravel().tolist()} "
           f"integrator={'Euler' if int(m.opt_integrator) == 0 else 'implicitfast'} max rel err {e:.2e}")
-    assert e < 3e-3, seed
+    if e >= 3e-3:
+      assert a.keep_going, seed
+      bad.append((seed, e))
     sim.close()
-  print(f"ok: worst relative error {worst:.2e}")
+  print(f"{'ok' if not bad else 'FAILED ' + str(bad)}: worst relative error {worst:.2e} over {a.seeds} seeds")
+  return bad
 
 
 if __name__ == "__main__":
