@@ -127,6 +127,7 @@ struct DevData {
   DArr qpos, qvel, ctrl, qacc_warmstart, qfrc_applied, xfrc_applied, act;
   DArr qacc, xpos, xquat, xmat, xipos, subtree_com, cvel, geom_xpos, geom_xmat, site_xpos,
       site_xmat, sensordata, actuator_force, time;
+  DArr qacc_smooth_prev, ctrl_prev;  // previous step's unconstrained acceleration and control (shifted warm start)
   DArr qM_packed;  // joint-space inertia, packed lower triangle (engine scratch between phases; L2-resident)
   DArr link_vel_w, com_vel_w, link_state_b;  // per body: EntityData's derived velocities / body-frame state
   DArr qfrc_bias, qfrc_smooth, qacc_smooth, qfrc_constraint, qM;

@@ -404,7 +404,7 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
   if (m.nv > 64 || m.nbody > 64) { delete s; return fail("b2_create: nv and nbody must be <= 64"); }
   if (m.nv < 1) { delete s; return fail("b2_create: model has no degrees of freedom"); }
   m.integrator = geti("opt_integrator"); m.iterations = geti("opt_iterations");
-  m.ls_iterations = geti("opt_ls_iterations"); m.debug = 8;  // bit 3: relative-step stop of the line search (on)
+  m.ls_iterations = geti("opt_ls_iterations"); m.debug = 8 | 16;  // bit 3: relative-step stop of the line search; bit 4: shifted warm start after a control change
   m.timestep = (float)getf("opt_timestep"); m.tolerance = (float)getf("opt_tolerance");
   m.ls_tolerance = (float)getf("opt_ls_tolerance"); m.impratio = (float)getf("opt_impratio");
   m.meaninertia = (float)getf("stat_meaninertia");
@@ -711,6 +711,8 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
   rc |= add_data(s, "qfrc_constraint", &d.qfrc_constraint, nv);
   rc |= add_data(s, "qM", &d.qM, nv * nv, nv);
   rc |= add_data(s, "qM_packed", &d.qM_packed, m.ntri);
+  rc |= add_data(s, "qacc_smooth_prev", &d.qacc_smooth_prev, nv);
+  rc |= add_data(s, "ctrl_prev", &d.ctrl_prev, nu);
   rc |= add_data(s, "contact_dist", &d.contact_dist, mc); rc |= add_data(s, "contact_pos", &d.contact_pos, 3 * mc, 3);
   rc |= add_data(s, "contact_frame", &d.contact_frame, 9 * mc, 9);
   rc |= add_data(s, "contact_force", &d.contact_force, 3 * mc, 3);
@@ -926,6 +928,7 @@ int b2_set_option(b2_sim* s, const char* key, double v) {
   else if (k == "phase_sync") s->phase_sync = (int)v;
   else if (k == "reorder_every_substep") s->reorder_every_substep = (int)v;
   else if (k == "full_solver") m.debug = (m.debug & ~4) | ((int)v ? 4 : 0);  // Newton on all dofs even when a leading block suffices (tests, A/B)
+  else if (k == "warmstart_shift") m.debug = (m.debug & ~16) | ((int)v ? 16 : 0);  // previous solution moved by the change of qacc_smooth
   else if (k == "ls_relstep") m.debug = (m.debug & ~8) | ((int)v ? 8 : 0);  // line search stops on a relative step of a few ulp
   else return fail("b2_set_option: unknown option '" + k + "'");
   return 0;
