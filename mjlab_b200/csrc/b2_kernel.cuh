@@ -2212,11 +2212,12 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       ls_eval(0.f, d0, d1);
       if (d0 < 0.f) {
         float lo_a = 0.f, hi_a = -1.f;  // hi_a < 0: no upper bracket yet
+        const float dstop = fmaxf(gtol, m.ls_rtol * fabsf(d0));  // (ls_rtol: stop on a relative drop of the slope; 0 = exact)
         alpha = -d0 / d1;
         #pragma unroll 1
         for (int it = 0; it < m.ls_iterations; it++) {
           ls_eval(alpha, d0, d1);
-          if (fabsf(d0) < gtol) break;
+          if (fabsf(d0) < dstop) break;
           if (d0 < 0.f) lo_a = alpha; else hi_a = alpha;
           float nxt = alpha - d0 / d1;
           if (hi_a >= 0.f && !(nxt > lo_a && nxt < hi_a)) nxt = 0.5f * (lo_a + hi_a);

@@ -75,6 +75,7 @@ struct DevModel {
   int maxcon, njmax;
   int integrator, iterations, ls_iterations, debug, solver;
   float timestep, tolerance, ls_tolerance, impratio, meaninertia;
+  float ls_rtol;  // line search: stop when the slope has dropped to this fraction of its value at 0 (0: exact search)
   float gravity[3];
   // integer tables
   const int *body_parentid, *body_rootid, *body_jntadr, *body_jntnum, *body_dofadr, *body_dofnum;

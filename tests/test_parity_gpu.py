@@ -228,6 +228,10 @@ def test_full_size_properties(g1_model):
   # replicated envs give replicated results: env w and env w + n/2 loaded with the same state
   st2 = {k: np.concatenate([v[: n // 2], v[: n // 2]]) for k, v in st.items()}
   load_sim(sim, st2)
+  # (the warm-start state is Data: qacc_warmstart as in MuJoCo, plus the previous step's unconstrained acceleration
+  # and control that the shifted warm start reads)
+  sim.data.qacc_smooth_prev[:] = 0.0
+  sim.data.ctrl_prev[:] = 0.0
   for _ in range(5):
     sim.step()
   torch.cuda.synchronize()
