@@ -2017,7 +2017,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         // (1e3..1e5 here) resolves improvements only down to ~1e-4, so "no measurable improvement" can still
         // leave a residual of several newtons in the constraint forces: the improvement test is honoured only
         // once the gradient is small against the forces it balances (|M a - f_smooth| vs |J^T f|).
-        const bool small = gn <= 1e-10f * fmaxf(fn, 1.f);
+        const bool small = gn <= m.newton_small * fmaxf(fn, 1.f);
         if (gradient < m.tolerance) { run = false; break; }
         // Exact termination: the cost is one quadratic per active set, and a Newton step with exact line
         // search lands on that quadratic's minimiser; if the active set did not change across the move, the

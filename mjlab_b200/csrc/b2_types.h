@@ -75,6 +75,7 @@ struct DevModel {
   int maxcon, njmax;
   int integrator, iterations, ls_iterations, debug, solver;
   float timestep, tolerance, ls_tolerance, impratio, meaninertia;
+  float newton_small;  // Newton: squared gradient norm relative to the squared force norm below which the improvement / unchanged-set stops apply (1e-10)
   float ls_rtol;  // line search: stop when the slope has dropped to this fraction of its value at 0 (0: exact search)
   float gravity[3];
   // integer tables

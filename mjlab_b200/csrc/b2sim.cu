@@ -405,6 +405,7 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
   if (m.nv < 1) { delete s; return fail("b2_create: model has no degrees of freedom"); }
   m.integrator = geti("opt_integrator"); m.iterations = geti("opt_iterations");
   m.ls_iterations = geti("opt_ls_iterations"); m.debug = 8 | 16;  // bit 3: relative-step stop of the line search; bit 4: shifted warm start after a control change
+  m.newton_small = 1e-10f;
   m.ls_rtol = 1e-3f;  // line search stops once the slope is 1e-3 of its value at 0 (emulated bench workload: 7.0 -> 3.4
                       // evaluations per Newton iteration, iteration count unchanged: 4.665 -> 4.67)
   m.timestep = (float)getf("opt_timestep"); m.tolerance = (float)getf("opt_tolerance");
@@ -932,6 +933,7 @@ int b2_set_option(b2_sim* s, const char* key, double v) {
   else if (k == "full_solver") m.debug = (m.debug & ~4) | ((int)v ? 4 : 0);  // Newton on all dofs even when a leading block suffices (tests, A/B)
   else if (k == "warmstart_shift") m.debug = (m.debug & ~16) | ((int)v ? 16 : 0);  // previous solution moved by the change of qacc_smooth
   else if (k == "ls_rtol") m.ls_rtol = (float)v;
+  else if (k == "newton_small") m.newton_small = (float)v;
   else if (k == "ls_relstep") m.debug = (m.debug & ~8) | ((int)v ? 8 : 0);  // line search stops on a relative step of a few ulp
   else return fail("b2_set_option: unknown option '" + k + "'");
   return 0;
