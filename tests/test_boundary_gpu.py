@@ -176,12 +176,14 @@ def test_velocity_env_runs_and_resets():
   obs = env.reset()
   assert obs.shape == (64, 3 + 3 + 3 + 29 + 29 + 29 + 3)
   total_done = 0
-  for _ in range(60):
-    a = torch.rand((64, 29), device="cuda:0") * 2 - 1
+  g = torch.Generator(device="cuda:0")
+  g.manual_seed(11)
+  for _ in range(150):
+    a = torch.rand((64, 29), generator=g, device="cuda:0") * 2 - 1
     obs, r, term, trunc, _ = env.step(a)
     total_done += int(term.sum())
   assert torch.isfinite(obs).all() and torch.isfinite(r).all()
-  assert total_done > 0  # random actions make G1 fall within ~1 s; those envs were reset
+  assert total_done > 0  # random actions make G1 fall within a few seconds; those envs were reset
   assert (env.sim.data.qpos[:, 2] > 0.2).all()
   env.close()
 
