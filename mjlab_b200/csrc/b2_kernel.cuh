@@ -2137,14 +2137,15 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       // ---- exact line search along `search` --------------------------------------------------
       symv(Mr, search, Mv, n, lane);
       MULJ(search, CJV0, LJV, false);
-      float g1 = 0.f, g2 = 0.f, sn = 0.f;
+      float g1 = 0.f, g2 = 0.f, sn = 0.f, gc = 0.f;
       #pragma unroll 1
       for (int i = lane; i < n; i += 32) {
         g1 += search[i] * (Ma[i] - qs[i]);
         g2 += 0.5f * search[i] * Mv[i];
         sn += search[i] * search[i];
+        gc += search[i] * qfrc_c[i];
       }
-      g1 = wsum(g1); g2 = wsum(g2); sn = sqrtf(wsum(sn));
+      g1 = wsum(g1); g2 = wsum(g2); sn = sqrtf(wsum(sn)); gc = wsum(gc);
       if (sn < MINVAL) { run = false; break; }
       float gtol = m.tolerance * m.ls_tolerance * sn / scale;
       // each lane keeps its rows in registers for the whole search (<= 2 contacts + 1 limit per lane)
@@ -2209,7 +2210,10 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       };
       PHASE_MARK(15);
       float alpha = 0.f, d0, d1;
-      ls_eval(0.f, d0, d1);
+      // slope at 0 = grad . search (grad = M a - f_smooth - J^T f, and J^T f is still in qfrc_c).  A Newton direction
+      // solves H search = -grad, so the curvature at 0 is -slope and the first trial step is 1: no evaluation at 0.
+      if (cg || (m.debug & 32)) ls_eval(0.f, d0, d1);
+      else { d0 = g1 - gc; d1 = -d0; }
       if (d0 < 0.f) {
         float lo_a = 0.f, hi_a = -1.f;  // hi_a < 0: no upper bracket yet
         const float dstop = fmaxf(gtol, m.ls_rtol * fabsf(d0));  // (ls_rtol: stop on a relative drop of the slope; 0 = exact)

@@ -933,6 +933,7 @@ int b2_set_option(b2_sim* s, const char* key, double v) {
   else if (k == "full_solver") m.debug = (m.debug & ~4) | ((int)v ? 4 : 0);  // Newton on all dofs even when a leading block suffices (tests, A/B)
   else if (k == "warmstart_shift") m.debug = (m.debug & ~16) | ((int)v ? 16 : 0);  // previous solution moved by the change of qacc_smooth
   else if (k == "ls_rtol") m.ls_rtol = (float)v;
+  else if (k == "ls_eval0") m.debug = (m.debug & ~32) | ((int)v ? 32 : 0);  // evaluate the line-search slope at 0 instead of using grad . search (A/B)
   else if (k == "newton_small") m.newton_small = (float)v;
   else if (k == "ls_relstep") m.debug = (m.debug & ~8) | ((int)v ? 8 : 0);  // line search stops on a relative step of a few ulp
   else return fail("b2_set_option: unknown option '" + k + "'");
