@@ -18,21 +18,9 @@ sys.path.insert(0, str(Path(__file__).parent / "emul"))
 
 
 def _load(defines=()):
-  from build import build
+  from engine import load_emul_library
 
-  L = ctypes.CDLL(str(build(defines=defines)))
-  L.b2_last_error.restype = ctypes.c_char_p
-  vp, ci = ctypes.c_void_p, ctypes.c_int
-  L.b2_create.argtypes = [ctypes.POINTER(native.B2ModelDesc), ci, ci, ci, ci, ctypes.POINTER(vp)]
-  L.b2_destroy.argtypes = [vp]
-  L.b2_get_field.argtypes = [vp, ci, ctypes.c_char_p, ctypes.POINTER(native.B2Tensor)]
-  L.b2_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_double]
-  L.b2_get_option.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]
-  L.b2_step.argtypes = [vp, vp]
-  L.b2_forward.argtypes = [vp, vp]
-  L.b2_step_n.argtypes = [vp, ci, vp]
-  L.b2_forward_masked.argtypes = [vp, vp, vp]
-  return L
+  return load_emul_library(defines)
 
 
 @pytest.fixture(scope="module")

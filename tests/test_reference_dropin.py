@@ -9,7 +9,9 @@ Restated reference tests: tests/test_entity.py:269-388 (root velocity frames), t
 (per-world fields reach the engine), tests/test_sim_data / test_nan_guard semantics.
 """
 
+import sys
 import types
+from pathlib import Path
 
 import numpy as np
 import pytest
@@ -18,9 +20,8 @@ import torch
 import refload
 from util import load_oracle, make_states, relerr
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not refload.available(), reason="baseline/_ref not installed")]
+pytestmark = [pytest.mark.skipif(not refload.available(), reason="baseline/_ref not installed")]
 
-DEV = "cuda:0"
 N = 16
 
 
@@ -29,8 +30,33 @@ def ref():
   return refload.load()
 
 
+@pytest.fixture(scope="module", params=[pytest.param("cuda", marks=pytest.mark.gpu), "emul"])
+def DEV(request, ref):
+  """"cuda": libb2sim.so on the GPU.  "emul": the same sources compiled for the host (tests/emul) behind the same
+  compat modules, so the CPU suite runs the reference's code against the product's kernels too."""
+  if request.param == "cuda":
+    yield "cuda:0"
+    return
+  import mjlab_b200.compat.mujoco_warp_shim as mw
+  from mjlab_b200.sim import native
+
+  sys.path.insert(0, str(Path(__file__).parent / "emul"))
+  from engine import EmulEngine
+
+  mp = pytest.MonkeyPatch()
+  mp.setattr(mw, "_Engine", EmulEngine)
+  mp.setattr(native, "check", lambda rc: (_ for _ in ()).throw(RuntimeError("b2sim call failed")) if rc else None)
+  yield "cpu"
+  mp.undo()
+
+
+def _sync(dev):
+  if dev != "cpu":
+    torch.cuda.synchronize()
+
+
 @pytest.fixture(scope="module")
-def world(ref, g1_model):
+def world(ref, g1_model, DEV):
   """Reference Simulation + reference Entity (initialised by the reference's own code) on the G1 flat scene."""
   import mujoco  # the compat stand-in (or the real module where it exists)
 
@@ -61,45 +87,54 @@ def world(ref, g1_model):
   return types.SimpleNamespace(sim=sim, ent=ent, env=env, model=m)
 
 
-def _load_state(sim, st):
+def _load_state(sim, st, DEV):
   for k, v in st.items():
     getattr(sim.data, k)[:] = torch.as_tensor(v, dtype=torch.float32, device=DEV)
 
 
-def test_reference_simulation_steps_the_engine(ref, world):
+def test_reference_simulation_steps_the_engine(ref, world, DEV):
   """reference Simulation.step()/forward() (CUDA-graph path included) == oracle and == this repo's Simulation."""
   from mjlab_b200.sim import Simulation, SimulationCfg
   from oracle.oracle import Oracle
 
   sim, m = world.sim, world.model
   assert type(sim).__module__ == "mjlab.sim.sim" and type(sim.data).__module__ == "mjlab.sim.sim_data"
-  assert sim.use_cuda_graph and sim.step_graph is not None  # wp.ScopedCapture -> torch CUDA graph of b2_step
+  gpu = DEV != "cpu"
+  if gpu:
+    assert sim.use_cuda_graph and sim.step_graph is not None  # wp.ScopedCapture -> torch CUDA graph of b2_step
+  else:
+    assert not sim.use_cuda_graph and sim.step_graph is None
   st = make_states(m, N, seed=77)
-  mine = Simulation(N, SimulationCfg(nconmax=140_000 * N // 4096 + 64 * N, njmax=300), m, DEV)
-  o = Oracle(m, nworld=N, maxcon=int(mine.get_option("maxcon")))
+  mine = Simulation(N, SimulationCfg(nconmax=140_000 * N // 4096 + 64 * N, njmax=300), m, DEV) if gpu else None
+  maxcon = int(mine.get_option("maxcon")) if gpu else max(16, min(96, -(-(140_000 * N // 4096 + 64 * N) // N)))
+  o = Oracle(m, nworld=N, maxcon=maxcon)
   load_oracle(o, st)
-  _load_state(sim, st)
-  for k, v in st.items():
-    getattr(mine.data, k)[:] = torch.as_tensor(v, dtype=torch.float32, device=DEV)
+  _load_state(sim, st, DEV)
+  if gpu:
+    for k, v in st.items():
+      getattr(mine.data, k)[:] = torch.as_tensor(v, dtype=torch.float32, device=DEV)
+    mine.forward()
   sim.forward()
-  mine.forward()
   o.forward()
-  torch.cuda.synchronize()
-  assert torch.equal(sim.data.xpos[:], mine.data.xpos[:]) and torch.equal(sim.data.qacc[:], mine.data.qacc[:])
+  _sync(DEV)
+  if gpu:
+    assert torch.equal(sim.data.xpos[:], mine.data.xpos[:]) and torch.equal(sim.data.qacc[:], mine.data.qacc[:])
   assert relerr(sim.data.xpos[:].cpu().numpy().reshape(N, -1), o.xpos).max() < 1e-5
   for _ in range(3):
     sim.step()
-    mine.step()
+    if gpu:
+      mine.step()
     o.step()
-  torch.cuda.synchronize()
-  assert torch.equal(sim.data.qpos[:], mine.data.qpos[:]) and torch.equal(sim.data.qvel[:], mine.data.qvel[:])
+  _sync(DEV)
+  if gpu:
+    assert torch.equal(sim.data.qpos[:], mine.data.qpos[:]) and torch.equal(sim.data.qvel[:], mine.data.qvel[:])
+    mine.close()
   assert relerr(sim.data.qpos[:].cpu().numpy(), o.qpos).max() < 1e-4
   assert np.median(relerr(sim.data.qvel[:].cpu().numpy(), o.qvel)) < 1e-4
   assert float(sim.data.time[0]) == pytest.approx(3 * float(m.opt_timestep))
-  mine.close()
 
 
-def test_reference_bridge_semantics(ref, world):
+def test_reference_bridge_semantics(ref, world, DEV):
   """sim/sim_data.py behaviour on engine memory: zero-copy views, cache, read-only bridge, torch functions."""
   sim = world.sim
   TorchArray = ref.sim_data.TorchArray
@@ -118,7 +153,7 @@ def test_reference_bridge_semantics(ref, world):
   assert sim.wp_model.body_mass.strides[0] == 0 and sim.model.body_mass.shape[0] == N
 
 
-def test_reference_entity_indexing_and_data(ref, world):
+def test_reference_entity_indexing_and_data(ref, world, DEV):
   """Entity._compute_indexing / initialize / EntityData (reference code) against this repo's EntityData and the
   qualitative checks of the reference's tests/test_entity.py:269-388."""
   from mjlab_b200.entity_data import EntityData as Mine
@@ -131,7 +166,7 @@ def test_reference_entity_indexing_and_data(ref, world):
   assert ix.ctrl_ids.tolist() == list(range(29)) and len(ix.geom_ids) == 68 and len(ix.body_ids) == 30
   assert set(ix.sensor_adr) == {"left_foot_ground_contact", "right_foot_ground_contact"}
   st = make_states(m, N, seed=78)
-  _load_state(sim, st)
+  _load_state(sim, st, DEV)
   sim.forward()
   d = ent.data
   mine = Mine(MyIndexing.from_model(m, "robot", DEV), sim.data, sim.model, DEV, N)
@@ -171,7 +206,7 @@ def test_reference_entity_indexing_and_data(ref, world):
   assert torch.allclose(d.root_link_pose_w, pose, atol=1e-6)
 
 
-def test_reference_events_drive_the_engine(ref, world):
+def test_reference_events_drive_the_engine(ref, world, DEV):
   """envs/mdp/events.py: reset_root_state_uniform, reset_joints_by_scale, push_by_setting_velocity,
   apply_external_force_torque run unmodified against sim.data through the reference Entity."""
   ev, sim, ent, env = ref.events, world.sim, world.ent, world.env
@@ -211,7 +246,7 @@ def test_reference_events_drive_the_engine(ref, world):
   assert (sim.data.xfrc_applied[:] == 0).all()
 
 
-def test_reference_domain_randomization_reaches_the_engine(ref, world):
+def test_reference_domain_randomization_reaches_the_engine(ref, world, DEV):
   """tests/test_domain_randomization.py restated: expand_model_fields (repeat_array_kernel via wp.launch) +
   randomize_field write per-world friction that the physics then uses."""
   ev, sim, ent, env, m = ref.events, world.sim, world.ent, world.env, world.model
@@ -252,7 +287,7 @@ def test_reference_domain_randomization_reaches_the_engine(ref, world):
   assert abs(float(sim.data.qacc[0, 0]) - float(sim.data.qacc[1, 0])) > 1.0
 
 
-def test_reference_nan_guard_on_engine_state(ref, world, tmp_path):
+def test_reference_nan_guard_on_engine_state(ref, world, DEV, tmp_path):
   """utils/nan_guard.py (reference) watches Simulation.step through the bridge and dumps on the first NaN."""
   m = world.model
   cfg = ref.sim.SimulationCfg(nan_guard=ref.nan_guard.NanGuardCfg(enabled=True, buffer_size=4, output_dir=str(tmp_path)))
@@ -260,7 +295,7 @@ def test_reference_nan_guard_on_engine_state(ref, world, tmp_path):
   sim.step()
   sim.data.qvel[2, 7] = float("nan")
   sim.step()
-  torch.cuda.synchronize()
+  _sync(DEV)
   dumps = list(tmp_path.glob("nan_dump_*.npz"))
   assert len(dumps) == 1
   z = np.load(dumps[0], allow_pickle=True)
