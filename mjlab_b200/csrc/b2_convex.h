@@ -452,10 +452,20 @@ B2C_FN int b2c_plane_mesh(B2CCon* out, b2c_real margin, const b2c_real* pp, cons
 
 // Height field H (pose hp/hR, size = [rx, ry, zmax, zbase], nrow x ncol samples in [0, 1], row-major with the
 // row index along y) against an inflated convex core G.  gc / rbound: G's bounding sphere.  Normal from the
-// height field to G.  Returns the number of contacts written (<= B2C_MAXOUT, deepest kept, grid order otherwise).
-B2C_FN int b2c_hfield(B2CCon* out, b2c_real margin, const b2c_real* hp, const b2c_real* hR, const b2c_real* hsize,
-                      int nrow, int ncol, const b2c_real* hdata, const B2CShape* G, b2c_real rg,
-                      const b2c_real* gc, b2c_real rbound) {
+// height field to G.  At most B2C_MAXOUT contacts per pair, deepest kept, grid order otherwise.
+//
+// The pair is processed in stages so that a caller can spread the work of several pairs over SIMD lanes (the
+// kernel does; b2c_hfield below runs them in sequence):
+//   b2c_hfield_range   cells under the geom's footprint -> `count` items, item j = (row, column, triangle)
+//   b2c_hfield_cull    cheap rejects of one item (height of the prism, plane of its top triangle)
+//   b2c_hfield_prism   GJK / EPA of one prism against G
+//   b2c_hfield_keep    merge one contact into the pair's list (items in ascending j), b2c_hfield_sort at the end
+typedef struct { int r0, c0, ncc, count; b2c_real lo2; } B2CHfRange;
+
+B2C_FN int b2c_hfield_range(B2CHfRange* rg_out, b2c_real margin, const b2c_real* hp, const b2c_real* hR,
+                            const b2c_real* hsize, int nrow, int ncol, const B2CShape* G, b2c_real rg,
+                            const b2c_real* gc, b2c_real rbound) {
+  rg_out->count = 0;
   b2c_real dlt[3] = {gc[0] - hp[0], gc[1] - hp[1], gc[2] - hp[2]};
   b2c_real c[3] = {hR[0] * dlt[0] + hR[3] * dlt[1] + hR[6] * dlt[2], hR[1] * dlt[0] + hR[4] * dlt[1] + hR[7] * dlt[2],
                    hR[2] * dlt[0] + hR[5] * dlt[1] + hR[8] * dlt[2]};
@@ -480,68 +490,110 @@ B2C_FN int b2c_hfield(B2CCon* out, b2c_real margin, const b2c_real* hp, const b2
   if (lo[1] + hsize[1] < 0) r0 = 0;
   if (c1 > ncol - 2) c1 = ncol - 2;
   if (r1 > nrow - 2) r1 = nrow - 2;
-  int n = 0, seq = 0;
-  int order[B2C_MAXOUT];  // prism sequence number of each kept contact: the output is in grid order whatever was evicted
+  if (c1 < c0 || r1 < r0) return 0;
+  rg_out->r0 = r0; rg_out->c0 = c0; rg_out->ncc = c1 - c0 + 1; rg_out->lo2 = lo[2];
+  rg_out->count = 2 * (r1 - r0 + 1) * (c1 - c0 + 1);
+  return rg_out->count;
+}
+
+// Corners of the top triangle of item j in the field's frame.  t = 0: (r,c) (r,c+1) (r+1,c+1);  t = 1: (r,c) (r+1,c+1) (r+1,c)
+B2C_INL void b2c_hfield_tri(const B2CHfRange* R, int j, const b2c_real* hsize, int nrow, int ncol, const b2c_real* hdata,
+                            b2c_real* lx, b2c_real* ly, b2c_real* lz) {
+  const int t = j & 1, cell = j >> 1, r = R->r0 + cell / R->ncc, cc = R->c0 + cell % R->ncc;
+  const b2c_real dx = 2 * hsize[0] / (b2c_real)(ncol - 1), dy = 2 * hsize[1] / (b2c_real)(nrow - 1);
+  const b2c_real z00 = hdata[r * ncol + cc] * hsize[2], z01 = hdata[r * ncol + cc + 1] * hsize[2];
+  const b2c_real z10 = hdata[(r + 1) * ncol + cc] * hsize[2], z11 = hdata[(r + 1) * ncol + cc + 1] * hsize[2];
+  const b2c_real x0 = -hsize[0] + dx * (b2c_real)cc, y0 = -hsize[1] + dy * (b2c_real)r;
+  lx[0] = x0; lx[1] = x0 + dx; lx[2] = t ? x0 : x0 + dx;
+  ly[0] = y0; ly[1] = t ? y0 + dy : y0; ly[2] = y0 + dy;
+  lz[0] = z00; lz[1] = t ? z11 : z01; lz[2] = t ? z10 : z11;
+}
+
+// 1 when item j survives the cheap rejects and needs b2c_hfield_prism
+B2C_FN int b2c_hfield_cull(const B2CHfRange* R, int j, b2c_real margin, const b2c_real* hp, const b2c_real* hR,
+                           const b2c_real* hsize, int nrow, int ncol, const b2c_real* hdata, const B2CShape* G, b2c_real rg) {
+  b2c_real lx[3], ly[3], lz[3];
+  b2c_hfield_tri(R, j, hsize, nrow, ncol, hdata, lx, ly, lz);
+  b2c_real zmax = lz[0] > lz[1] ? (lz[0] > lz[2] ? lz[0] : lz[2]) : (lz[1] > lz[2] ? lz[1] : lz[2]);
+  if (R->lo2 > zmax) return 0;
+  // the prism lies below the plane of its top triangle: a geom whose lowest point along that plane's normal
+  // clears it by more than the margin cannot touch (rejects the prisms under a limb that hovers over a slope)
+  b2c_real e1[3] = {lx[1] - lx[0], ly[1] - ly[0], lz[1] - lz[0]}, e2[3] = {lx[2] - lx[0], ly[2] - ly[0], lz[2] - lz[0]}, nl[3];
+  b2c_cross(nl, e1, e2);
+  if (nl[2] < 0) { nl[0] = -nl[0]; nl[1] = -nl[1]; nl[2] = -nl[2]; }
+  b2c_real nw[3], dn[3], q[3];
+  for (int k = 0; k < 3; k++) nw[k] = hR[3 * k] * nl[0] + hR[3 * k + 1] * nl[1] + hR[3 * k + 2] * nl[2];
+  dn[0] = -nw[0]; dn[1] = -nw[1]; dn[2] = -nw[2];
+  b2c_support(G, dn, q);
+  b2c_real p0[3];
+  for (int k = 0; k < 3; k++) p0[k] = hp[k] + hR[3 * k] * lx[0] + hR[3 * k + 1] * ly[0] + hR[3 * k + 2] * lz[0];
+  const b2c_real nn = B2C_SQRT(b2c_dot(nw, nw));
+  const b2c_real h = (q[0] - p0[0]) * nw[0] + (q[1] - p0[1]) * nw[1] + (q[2] - p0[2]) * nw[2];
+  return h > (rg + margin) * nn ? 0 : 1;
+}
+
+// the prism under item j against G; 1 and *cn when they touch (within margin)
+B2C_FN int b2c_hfield_prism(B2CCon* cn, const B2CHfRange* R, int j, b2c_real margin, const b2c_real* hp, const b2c_real* hR,
+                            const b2c_real* hsize, int nrow, int ncol, const b2c_real* hdata, const B2CShape* G,
+                            b2c_real rg, const b2c_real* gc, b2c_real rbound) {
+  b2c_real lx[3], ly[3], lz[3];
+  b2c_hfield_tri(R, j, hsize, nrow, ncol, hdata, lx, ly, lz);
+  const b2c_real dx = 2 * hsize[0] / (b2c_real)(ncol - 1), dy = 2 * hsize[1] / (b2c_real)(nrow - 1);
   B2CShape P;
   P.type = B2C_PRISM; P.nvert = 6; P.pos = hp; P.mat = hR; P.size = hsize; P.vert = hdata;
-  const b2c_real scale = rbound + dx + dy, tie = (b2c_real)1e-5 * scale;
-  for (int r = r0; r <= r1; r++)
-    for (int cc = c0; cc <= c1; cc++) {
-      const b2c_real z00 = hdata[r * ncol + cc] * hsize[2], z01 = hdata[r * ncol + cc + 1] * hsize[2];
-      const b2c_real z10 = hdata[(r + 1) * ncol + cc] * hsize[2], z11 = hdata[(r + 1) * ncol + cc + 1] * hsize[2];
-      const b2c_real x0 = -hsize[0] + dx * (b2c_real)cc, y0 = -hsize[1] + dy * (b2c_real)r;
-      for (int t = 0; t < 2; t++) {
-        // t = 0: (r,c) (r,c+1) (r+1,c+1);  t = 1: (r,c) (r+1,c+1) (r+1,c)
-        b2c_real lx[3] = {x0, t ? x0 + dx : x0 + dx, t ? x0 : x0 + dx};
-        b2c_real ly[3] = {y0, t ? y0 + dy : y0, y0 + dy};
-        b2c_real lz[3] = {z00, t ? z11 : z01, t ? z10 : z11};
-        b2c_real zmax = lz[0] > lz[1] ? (lz[0] > lz[2] ? lz[0] : lz[2]) : (lz[1] > lz[2] ? lz[1] : lz[2]);
-        if (lo[2] > zmax) continue;
-        {
-          // the prism lies below the plane of its top triangle: a geom whose lowest point along that plane's normal
-          // clears it by more than the margin cannot touch (rejects the prisms under a limb that hovers over a slope)
-          b2c_real e1[3] = {lx[1] - lx[0], ly[1] - ly[0], lz[1] - lz[0]}, e2[3] = {lx[2] - lx[0], ly[2] - ly[0], lz[2] - lz[0]}, nl[3];
-          b2c_cross(nl, e1, e2);
-          if (nl[2] < 0) { nl[0] = -nl[0]; nl[1] = -nl[1]; nl[2] = -nl[2]; }
-          b2c_real nw[3], dn[3], q[3];
-          for (int k = 0; k < 3; k++) nw[k] = hR[3 * k] * nl[0] + hR[3 * k + 1] * nl[1] + hR[3 * k + 2] * nl[2];
-          dn[0] = -nw[0]; dn[1] = -nw[1]; dn[2] = -nw[2];
-          b2c_support(G, dn, q);
-          b2c_real p0[3];
-          for (int k = 0; k < 3; k++) p0[k] = hp[k] + hR[3 * k] * lx[0] + hR[3 * k + 1] * ly[0] + hR[3 * k + 2] * lz[0];
-          const b2c_real nn = B2C_SQRT(b2c_dot(nw, nw));
-          const b2c_real h = (q[0] - p0[0]) * nw[0] + (q[1] - p0[1]) * nw[1] + (q[2] - p0[2]) * nw[2];
-          if (h > (rg + margin) * nn) { seq++; continue; }
-        }
-        b2c_real pc[3] = {0, 0, 0};
-        for (int i = 0; i < 6; i++) {
-          b2c_real l[3] = {lx[i % 3], ly[i % 3], i < 3 ? lz[i] : -hsize[3]};
-          for (int k = 0; k < 3; k++) {
-            P.pts[3 * i + k] = hp[k] + hR[3 * k] * l[0] + hR[3 * k + 1] * l[1] + hR[3 * k + 2] * l[2];
-            pc[k] += P.pts[3 * i + k] * ((b2c_real)1 / 6);
-          }
-        }
-        B2CCon cn;
-        seq++;
-        if (!b2c_pair(&cn, margin, &P, 0, G, rg, pc, gc, scale)) continue;
-        if (n < B2C_MAXOUT) { order[n] = seq; out[n++] = cn; }
-        else {
-          // evict the shallowest; neighbouring prisms often report the same contact, so depths within `tie` count
-          // as equal and the later prism goes (the choice must not hinge on the last bit of a depth)
-          b2c_real dmax = out[0].dist;
-          for (int i = 1; i < n; i++) if (out[i].dist > dmax) dmax = out[i].dist;
-          int worst = -1;
-          for (int i = 0; i < n; i++) if (out[i].dist >= dmax - tie && (worst < 0 || order[i] > order[worst])) worst = i;
-          if (cn.dist < dmax - tie) { out[worst] = cn; order[worst] = seq; }
-        }
-      }
+  b2c_real pc[3] = {0, 0, 0};
+  for (int i = 0; i < 6; i++) {
+    b2c_real l[3] = {lx[i % 3], ly[i % 3], i < 3 ? lz[i] : -hsize[3]};
+    for (int k = 0; k < 3; k++) {
+      P.pts[3 * i + k] = hp[k] + hR[3 * k] * l[0] + hR[3 * k + 1] * l[1] + hR[3 * k + 2] * l[2];
+      pc[k] += P.pts[3 * i + k] * ((b2c_real)1 / 6);
     }
-  for (int a = 1; a < n; a++) {  // back to grid order (insertion sort, n <= 8)
+  }
+  return b2c_pair(cn, margin, &P, 0, G, rg, pc, gc, rbound + dx + dy);
+}
+
+// `tie` of b2c_hfield_keep: depths closer than this count as equal
+B2C_INL b2c_real b2c_hfield_tie(const b2c_real* hsize, int nrow, int ncol, b2c_real rbound) {
+  const b2c_real dx = 2 * hsize[0] / (b2c_real)(ncol - 1), dy = 2 * hsize[1] / (b2c_real)(nrow - 1);
+  return (b2c_real)1e-5 * (rbound + dx + dy);
+}
+
+// contact cn of item j joins the pair's list (out / order / *n); items arrive in ascending j
+B2C_INL void b2c_hfield_keep(B2CCon* out, int* order, int* n, const B2CCon* cn, int j, b2c_real tie) {
+  if (*n < B2C_MAXOUT) { order[*n] = j; out[(*n)++] = *cn; return; }
+  // evict the shallowest; neighbouring prisms often report the same contact, so depths within `tie` count
+  // as equal and the later prism goes (the choice must not hinge on the last bit of a depth)
+  b2c_real dmax = out[0].dist;
+  for (int i = 1; i < *n; i++) if (out[i].dist > dmax) dmax = out[i].dist;
+  int worst = -1;
+  for (int i = 0; i < *n; i++) if (out[i].dist >= dmax - tie && (worst < 0 || order[i] > order[worst])) worst = i;
+  if (cn->dist < dmax - tie) { out[worst] = *cn; order[worst] = j; }
+}
+
+// back to grid order whatever was evicted (insertion sort, n <= 8)
+B2C_INL void b2c_hfield_sort(B2CCon* out, int* order, int n) {
+  for (int a = 1; a < n; a++) {
     B2CCon cv = out[a];
     int ov = order[a], b = a - 1;
     while (b >= 0 && order[b] > ov) { out[b + 1] = out[b]; order[b + 1] = order[b]; b--; }
     out[b + 1] = cv; order[b + 1] = ov;
   }
+}
+
+B2C_FN int b2c_hfield(B2CCon* out, b2c_real margin, const b2c_real* hp, const b2c_real* hR, const b2c_real* hsize,
+                      int nrow, int ncol, const b2c_real* hdata, const B2CShape* G, b2c_real rg,
+                      const b2c_real* gc, b2c_real rbound) {
+  B2CHfRange R;
+  if (!b2c_hfield_range(&R, margin, hp, hR, hsize, nrow, ncol, G, rg, gc, rbound)) return 0;
+  int n = 0, order[B2C_MAXOUT];
+  const b2c_real tie = b2c_hfield_tie(hsize, nrow, ncol, rbound);
+  for (int j = 0; j < R.count; j++) {
+    B2CCon cn;
+    if (!b2c_hfield_cull(&R, j, margin, hp, hR, hsize, nrow, ncol, hdata, G, rg)) continue;
+    if (!b2c_hfield_prism(&cn, &R, j, margin, hp, hR, hsize, nrow, ncol, hdata, G, rg, gc, rbound)) continue;
+    b2c_hfield_keep(out, order, &n, &cn, j, tie);
+  }
+  b2c_hfield_sort(out, order, n);
   return n;
 }
 

@@ -659,11 +659,7 @@ __device__ __noinline__ int convex_narrowphase(RawCon* rc, float margin, const D
     float pn[3] = {a[3 + 2], a[3 + 5], a[3 + 8]};
     n = b2c_plane_mesh(cc, margin, a, pn, &B);
   } else if (t1 == G_HFIELD) {
-    if (t2 != G_HFIELD) {
-      int id = m.geom_dataid[g1];
-      n = b2c_hfield(cc, margin, a, a + 3, m.hfield_size + 4 * id, m.hfield_nrow[id], m.hfield_ncol[id],
-                     m.hfield_data + m.hfield_adr[id], &B, r2, b, b[12]);
-    }
+    n = 0;  // height-field pairs go through hfield_lanes
   } else {
     const float* v1 = nullptr; int n1 = 0;
     if (t1 == G_MESH) { int id = m.geom_dataid[g1]; v1 = m.mesh_vert + 3 * m.mesh_vertadr[id]; n1 = m.mesh_vertnum[id]; }
@@ -673,6 +669,140 @@ __device__ __noinline__ int convex_narrowphase(RawCon* rc, float margin, const D
   for (int i = 0; i < n; i++) {
     rc[i].dist = cc[i].dist;
     for (int k = 0; k < 3; k++) { rc[i].pos[k] = cc[i].pos[k]; rc[i].n[k] = cc[i].n[k]; rc[i].yh[k] = 0.f; }
+  }
+  return n;
+}
+
+// Height-field pairs of one batch of 32 candidates, with the prisms of all pairs spread over the lanes.
+// Called by the whole warp; lane `lane` owns the pair (g1 = height field, g2, poses a / b) when `hf`.
+// Per pair the work is a list of items (cell, triangle) under the geom's footprint (b2c_hfield_range); most
+// are rejected by two cheap tests (b2c_hfield_cull) and the rest need GJK / EPA on a prism (b2c_hfield_prism).
+// One lane per pair leaves the warp waiting for the limb with the most prisms (3.4 GJK calls on the slowest
+// lane of 7.7 per environment on the rough-terrain workload): here every lane culls one item per round, the
+// survivors queue up in shared memory and are solved 32 at a time.  Contacts are merged by the owning lane in
+// ascending item order, which is the order of the sequential driver b2c_hfield (same contacts, same order).
+// scratch: HF_SCRATCH words of shared memory (records of the 32 owners + the queue).
+#define HF_REC 12
+#define HF_SCRATCH (32 * HF_REC + 64)
+__device__ __forceinline__ const float* hf_ptr(const int* rec) {
+  return (const float*)(((unsigned long long)(unsigned)rec[1] << 32) | (unsigned long long)(unsigned)rec[0]);
+}
+__device__ __noinline__ int hfield_lanes(RawCon* rc, bool hf, float margin, const DevModel& m, const float* gsize,
+                                         int g1, int g2, const float* a, const float* b, int* scratch, int lane) {
+  int* rec = scratch + HF_REC * lane;
+  int* queue = scratch + 32 * HF_REC;
+#ifdef B2_PHASE_TIMING
+  long long tphase_ = clock64();
+#endif
+  B2CHfRange R;
+  R.count = 0;
+  if (hf) {
+    const int t2 = m.geom_type[g2];
+    B2CShape B;
+    const float* v2 = nullptr; int n2 = 0;
+    if (t2 == G_MESH) { int id = m.geom_dataid[g2]; v2 = m.mesh_vert + 3 * m.mesh_vertadr[id]; n2 = m.mesh_vertnum[id]; }
+    const float r2 = b2c_shape(&B, t2, b, b + 3, gsize + 3 * g2, v2, n2);
+    const int id = m.geom_dataid[g1];
+    b2c_hfield_range(&R, margin, a, a + 3, m.hfield_size + 4 * id, m.hfield_nrow[id], m.hfield_ncol[id], &B, r2, b, b[12]);
+    rec[0] = (int)(unsigned)(unsigned long long)a; rec[1] = (int)(unsigned)((unsigned long long)a >> 32);
+    rec[2] = (int)(unsigned)(unsigned long long)b; rec[3] = (int)(unsigned)((unsigned long long)b >> 32);
+    rec[4] = g1; rec[5] = g2; rec[6] = __float_as_int(margin);
+    rec[7] = R.r0; rec[8] = R.c0; rec[9] = R.ncc; rec[10] = __float_as_int(R.lo2);
+  }
+  int incl = R.count;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const int total = __shfl_sync(FULL, incl, 31);
+  PHASE_MARK(21);  // footprints
+  if (total == 0) return 0;
+  __syncwarp();
+  B2CCon out[B2C_MAXOUT];
+  int order[B2C_MAXOUT], n = 0;
+  float tie = 0.f;
+  if (hf) { const int id = m.geom_dataid[g1]; tie = b2c_hfield_tie(m.hfield_size + 4 * id, m.hfield_nrow[id], m.hfield_ncol[id], b[12]); }
+  int qn = 0;
+  #pragma unroll 1
+  for (int i0 = 0; i0 < total || qn > 0;) {
+    if (i0 < total) {
+      // cull: item i of the concatenated lists; its owner is the first lane whose inclusive count exceeds i
+      const int i = min(i0 + lane, total - 1);
+      int ow = 0;
+#pragma unroll
+      for (int st = 16; st > 0; st >>= 1) {
+        int v = __shfl_sync(FULL, incl, ow + st - 1);
+        if (v <= i) ow += st;
+      }
+      const int first = __shfl_sync(FULL, incl - R.count, ow);
+      bool keep = false;
+      if (i0 + lane < total) {
+        const int* q = scratch + HF_REC * ow;
+        const float *qa = hf_ptr(q), *qb = hf_ptr(q + 2);
+        const int h1 = q[4], h2 = q[5], t2 = m.geom_type[h2], id = m.geom_dataid[h1];
+        B2CHfRange Q;
+        Q.r0 = q[7]; Q.c0 = q[8]; Q.ncc = q[9]; Q.lo2 = __int_as_float(q[10]); Q.count = 0;
+        B2CShape B;
+        const float* v2 = nullptr; int n2 = 0;
+        if (t2 == G_MESH) { int mid = m.geom_dataid[h2]; v2 = m.mesh_vert + 3 * m.mesh_vertadr[mid]; n2 = m.mesh_vertnum[mid]; }
+        const float r2 = b2c_shape(&B, t2, qb, qb + 3, gsize + 3 * h2, v2, n2);
+        keep = b2c_hfield_cull(&Q, i - first, __int_as_float(q[6]), qa, qa + 3, m.hfield_size + 4 * id, m.hfield_nrow[id],
+                               m.hfield_ncol[id], m.hfield_data + m.hfield_adr[id], &B, r2) != 0;
+      }
+      const unsigned km = __ballot_sync(FULL, keep);
+      if (keep) queue[qn + __popc(km & ((1u << lane) - 1u))] = (ow << 24) | (i - first);
+      qn += __popc(km);
+      i0 += 32;
+      __syncwarp();
+      PHASE_MARK(22);  // cull
+    }
+    if (qn >= 32 || (i0 >= total && qn > 0)) {
+      const int take = min(qn, 32);
+      const bool act = lane < take;
+      const int code = act ? queue[lane] : 0;
+      const int ow = code >> 24, j = code & 0xffffff;
+      bool hit = false;
+      B2CCon cn;
+      cn.dist = 0.f; cn.pos[0] = cn.pos[1] = cn.pos[2] = 0.f; cn.n[0] = cn.n[1] = cn.n[2] = 0.f;
+      if (act) {
+        const int* q = scratch + HF_REC * ow;
+        const float *qa = hf_ptr(q), *qb = hf_ptr(q + 2);
+        const int h1 = q[4], h2 = q[5], t2 = m.geom_type[h2], id = m.geom_dataid[h1];
+        B2CHfRange Q;
+        Q.r0 = q[7]; Q.c0 = q[8]; Q.ncc = q[9]; Q.lo2 = __int_as_float(q[10]); Q.count = 0;
+        B2CShape B;
+        const float* v2 = nullptr; int n2 = 0;
+        if (t2 == G_MESH) { int mid = m.geom_dataid[h2]; v2 = m.mesh_vert + 3 * m.mesh_vertadr[mid]; n2 = m.mesh_vertnum[mid]; }
+        const float r2 = b2c_shape(&B, t2, qb, qb + 3, gsize + 3 * h2, v2, n2);
+        hit = b2c_hfield_prism(&cn, &Q, j, __int_as_float(q[6]), qa, qa + 3, m.hfield_size + 4 * id, m.hfield_nrow[id],
+                               m.hfield_ncol[id], m.hfield_data + m.hfield_adr[id], &B, r2, qb, qb[12]) != 0;
+      }
+      unsigned hm = __ballot_sync(FULL, hit);
+      #pragma unroll 1
+      while (hm) {
+        const int sl = __ffs((int)hm) - 1;
+        hm &= hm - 1u;
+        const int dst = __shfl_sync(FULL, ow, sl), jj = __shfl_sync(FULL, j, sl);
+        B2CCon c2;
+        c2.dist = __shfl_sync(FULL, cn.dist, sl);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { c2.pos[k] = __shfl_sync(FULL, cn.pos[k], sl); c2.n[k] = __shfl_sync(FULL, cn.n[k], sl); }
+        if (lane == dst) b2c_hfield_keep(out, order, &n, &c2, jj, tie);
+      }
+      const int rest = qn - take;
+      const int mv = lane < rest ? queue[32 + lane] : 0;
+      __syncwarp();
+      if (lane < rest) queue[lane] = mv;
+      __syncwarp();
+      qn = rest;
+      PHASE_MARK(23);  // prisms (GJK / EPA) + merge
+    }
+  }
+  b2c_hfield_sort(out, order, n);
+  for (int i = 0; i < n; i++) {
+    rc[i].dist = out[i].dist;
+    for (int k = 0; k < 3; k++) { rc[i].pos[k] = out[i].pos[k]; rc[i].n[k] = out[i].n[k]; rc[i].yh[k] = 0.f; }
   }
   return n;
 }
@@ -1370,19 +1500,18 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
     int* pairlist = (int*)(s + L.pairlist);
     const float* gmar = MP(geom_margin);
     int ncand = 0;
-    unsigned pw_next = lane < m.npair ? m.pair_word[lane] : 0u;
-    float4 hb_next = (CVX && m.pair_hbox != nullptr && lane < m.npair) ? m.pair_hbox[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+    // pairs without a height field: the flat table (all pairs when the model has no field)
+    const int* nhp = CVX ? m.nh_pairs : nullptr;
+    const int np = CVX ? m.n_nhpair : m.npair;
+    unsigned pw_next = lane < np ? m.pair_word[nhp ? nhp[lane] : lane] : 0u;
     #pragma unroll 1
-    for (int p0 = 0; p0 < m.npair; p0 += 32) {
-      int p = p0 + lane;
+    for (int p0 = 0; p0 < np; p0 += 32) {
+      const int k = p0 + lane;
+      const int p = (nhp && k < np) ? nhp[k] : k;
       bool hit = false;
       const unsigned pw = pw_next;  // slot1 | slot2 << 12 | (geom1 is a height field) << 30 | (geom1 is a plane) << 31
-      const float4 hb = hb_next;    // height-field pairs: the field's box (rx, ry, elevation, base)
-      if (p + 32 < m.npair) {       // next batch's records are in flight during this one
-        pw_next = m.pair_word[p + 32];
-        if (CVX && m.pair_hbox != nullptr) hb_next = m.pair_hbox[p + 32];
-      }
-      if (p < m.npair) {
+      if (k + 32 < np) pw_next = m.pair_word[nhp ? nhp[k + 32] : k + 32];  // in flight during this batch
+      if (k < np) {
         const float* a = gpose + GP * (pw & 0xfffu);
         const float* b = gpose + GP * ((pw >> 12) & 0xfffu);
         float margin = fmaxf(a[13], b[13]);
@@ -1390,14 +1519,6 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         if (pw >> 31) {
           float n[3] = {a[3 + 2], a[3 + 5], a[3 + 8]};
           hit = dot3(dif, n) <= margin + b[12];
-        } else if (CVX && (pw >> 30 & 1u)) {
-          // height field: the geom's bounding sphere against the field's box (a terrain is a grid of fields whose
-          // bounding spheres all contain the robot: the sphere test would pass every neighbour to the narrowphase)
-          const float hs[4] = {hb.x, hb.y, hb.z, hb.w};
-          const float reach = margin + b[12];
-          const float lx = a[3] * dif[0] + a[6] * dif[1] + a[9] * dif[2], ly = a[4] * dif[0] + a[7] * dif[1] + a[10] * dif[2];
-          const float lz = a[5] * dif[0] + a[8] * dif[1] + a[11] * dif[2];
-          hit = fabsf(lx) <= hs[0] + reach && fabsf(ly) <= hs[1] + reach && lz - reach <= hs[2] && lz + reach >= -hs[3];
         } else {
           float bound = margin + a[12] + b[12];
           hit = dot3(dif, dif) <= bound * bound;
@@ -1410,6 +1531,92 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       }
       ncand += __popc(bal);
     }
+    if (CVX && m.nhf > 0) {
+      // height-field pairs, field by field.  A terrain is a grid of fields and the robot stands on one or two
+      // of them: first the fields whose box meets the sphere around all the geoms that can touch a field, then
+      // only their pairs, each with the exact test (the geom's bounding sphere against the field's box - the
+      // fields' own bounding spheres all contain the robot).  The candidates are put back in pair-table order.
+      float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+      #pragma unroll 1
+      for (int q = lane; q < m.nhfd; q += 32) {
+        const float* c = gpose + GP * m.hfd_slot[q];
+        const float r = c[12] + c[13];
+        for (int k = 0; k < 3; k++) { lo[k] = fminf(lo[k], c[k] - r); hi[k] = fmaxf(hi[k], c[k] + r); }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+        for (int k = 0; k < 3; k++) {
+          lo[k] = fminf(lo[k], __shfl_xor_sync(FULL, lo[k], o));
+          hi[k] = fmaxf(hi[k], __shfl_xor_sync(FULL, hi[k], o));
+        }
+      const float cw[3] = {0.5f * (lo[0] + hi[0]), 0.5f * (lo[1] + hi[1]), 0.5f * (lo[2] + hi[2])};
+      const float ext[3] = {hi[0] - cw[0], hi[1] - cw[1], hi[2] - cw[2]};
+      const float Rw = sqrtf(dot3(ext, ext)) * 1.0001f + 1e-6f;
+      const int nbefore = ncand;
+      int nnear = 0;
+      #pragma unroll 1
+      for (int h0 = 0; h0 < m.nhf; h0 += 32) {
+        const int h = h0 + lane;
+        bool near = false;
+        if (h < m.nhf) {
+          const float* a = gpose + GP * m.hfl_slot[h];
+          const float4 hb = m.hfl_box[h];
+          const float reach = Rw + a[13];
+          const float dif[3] = {cw[0] - a[0], cw[1] - a[1], cw[2] - a[2]};
+          const float lx = a[3] * dif[0] + a[6] * dif[1] + a[9] * dif[2], ly = a[4] * dif[0] + a[7] * dif[1] + a[10] * dif[2];
+          const float lz = a[5] * dif[0] + a[8] * dif[1] + a[11] * dif[2];
+          near = fabsf(lx) <= hb.x + reach && fabsf(ly) <= hb.y + reach && lz - reach <= hb.z && lz + reach >= -hb.w;
+        }
+        unsigned nm = __ballot_sync(FULL, near);
+        nnear += __popc(nm);
+        #pragma unroll 1
+        while (nm) {
+          const int hh = h0 + __ffs((int)nm) - 1;
+          nm &= nm - 1u;
+          const float* a = gpose + GP * m.hfl_slot[hh];
+          const float4 hb = m.hfl_box[hh];
+          const int en = m.hfl_start[hh + 1];
+          #pragma unroll 1
+          for (int k0 = m.hfl_start[hh]; k0 < en; k0 += 32) {
+            const int k = k0 + lane;
+            bool hit = false;
+            int p = 0;
+            if (k < en) {
+              p = m.hfl_pairs[k];
+              const float* b = gpose + GP * ((m.pair_word[p] >> 12) & 0xfffu);
+              const float reach = fmaxf(a[13], b[13]) + b[12];
+              const float dif[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+              const float lx = a[3] * dif[0] + a[6] * dif[1] + a[9] * dif[2], ly = a[4] * dif[0] + a[7] * dif[1] + a[10] * dif[2];
+              const float lz = a[5] * dif[0] + a[8] * dif[1] + a[11] * dif[2];
+              hit = fabsf(lx) <= hb.x + reach && fabsf(ly) <= hb.y + reach && lz - reach <= hb.z && lz + reach >= -hb.w;
+            }
+            unsigned bal = __ballot_sync(FULL, hit);
+            if (hit) {
+              int slot = ncand + __popc(bal & ((1u << lane) - 1u));
+              if (slot < L.maxpair) pairlist[slot] = p;
+            }
+            ncand += __popc(bal);
+          }
+        }
+      }
+      const int nn = min(ncand, L.maxpair);
+      if (nn > nbefore && (nnear > 1 || nbefore > 0)) {
+        // rank sort (pair indices are distinct) through the scratch of hfield_lanes
+        int* tmp = (int*)(s + L.gV);
+        __syncwarp();
+        #pragma unroll 1
+        for (int i = lane; i < nn; i += 32) {
+          const int v = pairlist[i];
+          int rank = 0;
+          for (int k = 0; k < nn; k++) rank += pairlist[k] < v ? 1 : 0;
+          tmp[rank] = v;
+        }
+        __syncwarp();
+        for (int i = lane; i < nn; i += 32) pairlist[i] = tmp[i];
+        __syncwarp();
+      }
+    }
+    PHASE_MARK(17);  // pair-table broadphase
     const float* gsize = MP(geom_size);
     if (m.nstatic > 0) {
       // grid-static candidates: lane = dynamic geom, visiting the cells under its bounding sphere.  Two passes
@@ -1485,6 +1692,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         ncand += tot;
       }
     }
+    PHASE_MARK(18);  // grid broadphase
     if (ncand > L.maxpair) { ncand = L.maxpair; overflow = 1; }
     __syncwarp();
     PSYNC_L(3);
@@ -1502,6 +1710,8 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       RawCon rc[8];
       int n = 0, g1 = 0, g2 = 0;
       float margin = 0.f;
+      bool hf = false;
+      const float *hfa = nullptr, *hfb = nullptr;
       if (qi < ncand) {
         int p = pairlist[qi];
         const float *a, *b;
@@ -1523,7 +1733,9 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
         margin = fmaxf(gmar[g1], gmar[g2]);
         const float* s1 = gsize + 3 * g1; const float* s2 = gsize + 3 * g2;
-        if (CVX && (t2 == G_MESH || t1 == G_HFIELD)) {
+        if (CVX && t1 == G_HFIELD) {
+          hf = t2 != G_HFIELD; hfa = a; hfb = b;
+        } else if (CVX && t2 == G_MESH) {
           n = convex_narrowphase(rc, margin, m, g1, g2, a, b, s1, s2);
         } else if (t1 == G_PLANE) {
           float pn[3] = {a[3 + 2], a[3 + 5], a[3 + 8]};
@@ -1594,6 +1806,14 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
           }
         }
       }
+      PHASE_MARK(19);  // primitive narrowphase
+      if (CVX) {
+        if (__any_sync(FULL, hf)) {
+          int nh = hfield_lanes(rc, hf, margin, m, gsize, g1, g2, hfa, hfb, (int*)(s + L.gV), lane);
+          if (hf) n = nh;
+        }
+      }
+      PHASE_MARK(20);  // height-field pairs (total of 21-23 + merge)
       // deterministic compaction in (pair order, contact index) order
       int incl = n;
 #pragma unroll

@@ -91,7 +91,14 @@ struct DevModel {
   const int *site_bodyid;
   const int *actuator_trnid, *actuator_ctrllimited, *actuator_forcelimited;
   const int *pair_geom1, *pair_geom2;
-  const float4* pair_hbox;    // per pair: the box (rx, ry, elevation, base) of geom 1 when it is a height field (else zeros); nullptr without fields
+  // height-field pairs, grouped by field (hierarchical broadphase; all nullptr / 0 without fields):
+  int nhf, nhfd, n_nhpair;    // distinct fields, distinct geoms paired with a field, pairs without a field
+  const int* hfl_slot;        // [nhf] pose slot of the field
+  const float4* hfl_box;      // [nhf] its box (rx, ry, elevation, base)
+  const int* hfl_start;       // [nhf + 1] range of the field's pairs in hfl_pairs
+  const int* hfl_pairs;       // pair indices, ascending per field
+  const int* hfd_slot;        // [nhfd] pose slots of the geoms paired with a field
+  const int* nh_pairs;        // [n_nhpair] indices of the pairs without a field, ascending (nullptr: all pairs)
   const unsigned* pair_word;  // broadphase record per pair: slot1 | slot2 << 12 | (geom1 is a height field) << 30 | (geom1 is a plane) << 31
   // grid-static collision set (terrain): geoms welded to the world, found through a uniform xy grid
   int nstatic, ndyn, nposegeom, grid_nx, grid_ny;

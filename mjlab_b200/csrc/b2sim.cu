@@ -625,20 +625,35 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
               (s->mi["geom_type"][g1] == G_HFIELD ? 0x40000000u : 0u);
     }
     rc |= dev_upload<unsigned>(s, pw, &m.pair_word);
-    bool anyhf = false;
-    std::vector<float> hb((size_t)std::max(m.npair, 1) * 4, 0.f);
+    // height-field pairs grouped by field: the kernel first finds the fields under the robot, then tests only
+    // their pairs (a terrain is a grid of fields; the flat pair table would test every one of them)
+    std::vector<int> hf_geom, hf_slot, hf_start, hf_pairs, hfd, nh;
+    std::vector<std::vector<int>> per;
+    std::vector<float> box;
     for (int p = 0; p < m.npair; p++) {
-      int g1 = s->mi["pair_geom1"][p];
-      if (s->mi["geom_type"][g1] != G_HFIELD) continue;
-      anyhf = true;
-      const int id = s->mi["geom_dataid"][g1];
-      for (int k = 0; k < 4; k++) hb[4 * (size_t)p + k] = (float)s->mf["hfield_size"][4 * (size_t)id + k];
+      int g1 = s->mi["pair_geom1"][p], g2 = s->mi["pair_geom2"][p];
+      if (s->mi["geom_type"][g1] != G_HFIELD) { nh.push_back(p); continue; }
+      size_t h = std::find(hf_geom.begin(), hf_geom.end(), g1) - hf_geom.begin();
+      if (h == hf_geom.size()) {
+        hf_geom.push_back(g1); hf_slot.push_back(cslot[g1]); per.emplace_back();
+        const int id = s->mi["geom_dataid"][g1];
+        for (int k = 0; k < 4; k++) box.push_back((float)s->mf["hfield_size"][4 * (size_t)id + k]);
+      }
+      per[h].push_back(p);
+      if (std::find(hfd.begin(), hfd.end(), cslot[g2]) == hfd.end()) hfd.push_back(cslot[g2]);
     }
-    m.pair_hbox = nullptr;
-    if (anyhf) {
-      const float* hp = nullptr;
-      rc |= dev_upload<float>(s, hb, &hp);
-      m.pair_hbox = (const float4*)hp;
+    m.nhf = (int)hf_geom.size(); m.nhfd = (int)hfd.size(); m.n_nhpair = m.npair;
+    m.hfl_slot = m.hfl_start = m.hfl_pairs = m.hfd_slot = m.nh_pairs = nullptr; m.hfl_box = nullptr;
+    if (m.nhf > 0) {
+      for (auto& v : per) { hf_start.push_back((int)hf_pairs.size()); hf_pairs.insert(hf_pairs.end(), v.begin(), v.end()); }
+      hf_start.push_back((int)hf_pairs.size());
+      m.n_nhpair = (int)nh.size();
+      if (nh.empty()) nh.push_back(0);
+      const float* bp = nullptr;
+      rc |= dev_upload<int>(s, hf_slot, &m.hfl_slot); rc |= dev_upload<int>(s, hf_start, &m.hfl_start);
+      rc |= dev_upload<int>(s, hf_pairs, &m.hfl_pairs); rc |= dev_upload<int>(s, hfd, &m.hfd_slot);
+      rc |= dev_upload<int>(s, nh, &m.nh_pairs); rc |= dev_upload<float>(s, box, &bp);
+      m.hfl_box = (const float4*)bp;
     }
   }
   rc |= dev_upload<int>(s, cslot, &m.geom_cslot);
@@ -775,6 +790,9 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
   }
   L.Mred = alloc(L.ndcap * (L.ndcap + 1) / 2);
   int endB = off;
+  // the lane-distributed height-field narrowphase keeps its owner records and its queue in the (then unused)
+  // solver regions from gV on
+  if (!s->mf["hfield_data"].empty()) endB = std::max(endB, L.gV + HF_SCRATCH);
   L.total = pad4(std::max(endA, endB));
   if (L.ndcap == 0) L.Mred = L.H;  // never used
   s->smem_bytes = sizeof(float) * ((size_t)L.total * B2_WARPS_PER_CTA + pad4(m.ldl_nsparse + 18));

@@ -106,6 +106,50 @@ def test_emulated_kernel_on_height_field_terrain():
   sim.close()
 
 
+def test_emulated_kernel_robots_straddling_field_borders():
+  """Robots on the seams and corners of the terrain's grid of height fields: the hierarchical broadphase
+  (fields under the robot first, then their pairs) finds candidates on two or four fields and must hand them to
+  the narrowphase in pair-table order; the lane-distributed narrowphase then merges the prisms of several pairs
+  per round.  Contact sets, order and depths against the oracle."""
+  from mjlab_b200.asset_zoo import load_compiled
+  from test_kernel_emul import EmulSim, _load
+  from util import make_states, surface_height
+
+  lib = _load()
+  m = load_compiled("go1_rough_hf")
+  gt = np.asarray(m.geom_type)
+  hf = np.nonzero(gt == 1)[0]
+  ctr = np.asarray(m.geom_pos)[hf] + np.asarray(m.body_pos)[np.asarray(m.geom_bodyid)[hf]]
+  half = np.asarray(m.hfield_size)[np.asarray(m.geom_dataid)[hf], 0]
+  rng = np.random.default_rng(4)
+  n = 24
+  st = make_states(m, n, seed=12, z_range=(0.0, 0.0))
+  key = make_states(m, 1, seed=0, z_range=(0.0, 0.0))["qpos"][0, 2]
+  for w in range(n):
+    k = rng.integers(0, len(hf))
+    x = ctr[k, 0] + half[k] * (1 if w % 2 else -1) + rng.uniform(-0.08, 0.08)  # on the x seam
+    y = ctr[k, 1] + (half[k] * (1 if w % 4 < 2 else -1) + rng.uniform(-0.08, 0.08) if w % 3 else rng.uniform(-2, 2))
+    st["qpos"][w, 0:2] = (x, y)
+    st["qpos"][w, 2] = max(surface_height(m, x + dx, y + dy) for dx in (-0.2, 0.2) for dy in (-0.2, 0.2)) + key - 0.04
+  sim = EmulSim(lib, m, n, ncon=48)
+  o = Oracle(m, nworld=n, maxcon=int(sim.option("maxcon")))
+  load_oracle(o, st)
+  sim.load(st)
+  o.forward()
+  sim.forward()
+  nc = o.ncon.ravel()
+  og = o.contact_geom.reshape(n, -1, 2)
+  fields_touched = [len({int(g) for g in og[w, : nc[w], 0] if gt[g] == 1}) for w in range(n)]
+  assert sum(f >= 2 for f in fields_touched) >= 4, fields_touched  # the seams are exercised
+  assert (sim.field("ncon").ravel() == nc).all()
+  cg = sim.field("contact_geom")
+  for w in range(n):
+    assert (cg[w, : nc[w]] == og[w, : nc[w]]).all(), w
+    if nc[w]:
+      assert np.abs(sim.field("contact_dist")[w, : nc[w]] - o.contact_dist[w, : nc[w]]).max() < 2e-5
+  sim.close()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,n", [("go1_hf_small", 256), ("go1_rough_hf", 192)])
 def test_gpu_height_field_terrain_parity(name, n):

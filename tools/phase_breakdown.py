@@ -27,8 +27,10 @@ assert sim._lib.b2_phase_cycles(buf) == 0, "library built without -DB2_PHASE_TIM
 names = ["load(TMA)", "kinematics", "geom/site poses", "com/cinert/cdof", "crb+M", "vel/rne/act/qfrc_smooth",
          "collision", "limits/groups/aref", "chol(M)+qacc_smooth", "solver total(excl sub)", "sensors/forces",
          "integrate+store", "  newton: update(J^T f, cost)", "  newton: H assembly", "  newton: chol+solve",
-         "  newton: symv+mulJ", "  newton: line search"]
-tot = sum(buf[i] for i in range(17))
+         "  newton: symv+mulJ", "  newton: line search", "  collision: pair-table broadphase",
+         "  collision: grid broadphase", "  collision: primitive narrowphase", "  collision: height-field pairs",
+         "    (hfield: footprints)", "    (hfield: cull)", "    (hfield: prisms + merge)"]
+tot = sum(buf[i] for i in range(21))
 st = sim.stats()
 print(f"mean newton iters {st.niter_mean:.2f}, mean ncon {st.ncon_mean:.1f}; cycles per env-step (warp-serial): {tot / (K * n):.0f}")
 for i, nm in enumerate(names):
