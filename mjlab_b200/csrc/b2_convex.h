@@ -59,15 +59,15 @@ B2C_INL void b2c_cross(b2c_real* r, const b2c_real* a, const b2c_real* b) {
 B2C_INL b2c_real b2c_eps(void) { return sizeof(b2c_real) == 4 ? (b2c_real)1e-6 : (b2c_real)1e-12; }
 
 // farthest point of the core in world direction d
-B2C_FN void b2c_support(const B2CShape* s, const b2c_real* d, b2c_real* out) {
+B2C_INL void b2c_support(const B2CShape* s, const b2c_real* d, b2c_real* out) {
   if (s->type == B2C_PRISM) {
-    int best = 0;
-    b2c_real bv = b2c_dot(s->pts, d);
-    for (int i = 1; i < 6; i++) {
-      b2c_real v = b2c_dot(s->pts + 3 * i, d);
-      if (v > bv) { bv = v; best = i; }
-    }
-    out[0] = s->pts[3 * best]; out[1] = s->pts[3 * best + 1]; out[2] = s->pts[3 * best + 2];
+    // corners 3..5 lie straight below corners 0..2 along the field's z axis: the sign of d along that axis picks
+    // the triangle (top on a tie, as a scan of the six corners in order would)
+    const b2c_real* R = s->mat;
+    const b2c_real* q = s->pts + ((R[2] * d[0] + R[5] * d[1] + R[8] * d[2]) >= 0 ? 0 : 9);
+    const b2c_real v0 = b2c_dot(q, d), v1 = b2c_dot(q + 3, d), v2 = b2c_dot(q + 6, d);
+    const int best = v1 > v0 ? (v2 > v1 ? 6 : 3) : (v2 > v0 ? 6 : 0);
+    out[0] = q[best]; out[1] = q[best + 1]; out[2] = q[best + 2];
     return;
   }
   const b2c_real* p = s->pos; const b2c_real* R = s->mat;

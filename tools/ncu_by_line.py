@@ -49,3 +49,21 @@ for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
   text = src.get(k[0], [""])[k[1] - 1].strip()[:90] if k and src.get(k[0]) and k[1] - 1 < len(src[k[0]]) else ""
   st = ",".join(f"{n[6:]}:{c}" for n, c in stall_agg[k].most_common(3))
   print(f"{str(k):28s} samp {100*v[1]/max(tot_s,1):5.1f}%  inst {100*v[0]/max(tot_i,1):5.1f}%  sass {v[2]:5d}  {st:40s} | {text}")
+if os.environ.get("NCU_BY_FILE"):  # exact totals per source file and per function range of b2_convex.h
+  byf = collections.defaultdict(lambda: [0, 0])
+  for k, v in agg.items():
+    f = k[0] if k else None
+    byf[f][0] += v[0]; byf[f][1] += v[1]
+  for f, v in sorted(byf.items(), key=lambda kv: -kv[1][1]):
+    print(f"FILE {str(f):32s} samp {100*v[1]/max(tot_s,1):6.2f}%  inst {100*v[0]/max(tot_i,1):6.2f}%")
+  cs = open(os.path.join(os.path.dirname(__file__), "..", "mjlab_b200", "csrc", "b2_convex.h")).read().splitlines()
+  marks = [(i, m.group(2)) for i, ln in enumerate(cs, 1) for m in [re.match(r"B2C_(FN|INL) \w[\w ]*?(\w+)\(", ln)] if m]
+  fn = collections.defaultdict(lambda: [0, 0])
+  for k, v in agg.items():
+    if not k or k[0] != "b2_convex.h": continue
+    lab = "?"
+    for ml, name in marks:
+      if ml <= k[1]: lab = name
+    fn[lab][0] += v[0]; fn[lab][1] += v[1]
+  for f, v in sorted(fn.items(), key=lambda kv: -kv[1][1]):
+    print(f"CONVEX {f:28s} samp {100*v[1]/max(tot_s,1):6.2f}%  inst {100*v[0]/max(tot_i,1):6.2f}%")

@@ -8,10 +8,14 @@ from mjlab_b200.envs import VelocityEnvCfg, VelocityFlatEnv
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 mode = sys.argv[2] if len(sys.argv) > 2 else "time"
-env = VelocityFlatEnv(VelocityEnvCfg(num_envs=n), device="cuda:0")
+import os
+_wl = os.environ.get("B2_WORKLOAD", "B")  # B: G1 flat, E: Go1 rough boxes, F: Go1 rough boxes + height fields
+_kw = dict(B={}, E=dict(robot="go1", terrain="rough"), F=dict(robot="go1", terrain="rough_hf"))[_wl]
+env = VelocityFlatEnv(VelocityEnvCfg(num_envs=n, **_kw), device="cuda:0")
+_nu = 29 if _wl == "B" else 12
 g = torch.Generator(device="cuda:0"); g.manual_seed(0)
 for _ in range(int(sys.argv[3]) if len(sys.argv) > 3 else 60):
-  env.step(torch.rand((n, 29), generator=g, device="cuda:0") * 2 - 1)
+  env.step(torch.rand((n, _nu), generator=g, device="cuda:0") * 2 - 1)
 torch.cuda.synchronize()
 sim = env.sim
 def timeit(label, k=20):
