@@ -673,6 +673,11 @@ __device__ __noinline__ int convex_narrowphase(RawCon* rc, float margin, const D
   return n;
 }
 
+// Pose record (pos[3], mat[9], rbound, ...) of a collision geom from its slot code: a shared-memory slot, or
+// -2 - index of a height field welded to the world (posed once at create, global memory)
+__device__ __forceinline__ const float* cpose(const float* gpose, const DevModel& m, int cs) {
+  return cs >= 0 ? gpose + GP * cs : m.fixed_pose + 16 * (size_t)(-2 - cs);
+}
 // Height-field pairs of one batch of 32 candidates, with the prisms of all pairs spread over the lanes.
 // Called by the whole warp; lane `lane` owns the pair (g1 = height field, g2, poses a / b) when `hf`.
 // Per pair the work is a list of items (cell, triangle) under the geom's footprint (b2c_hfield_range); most
@@ -1559,9 +1564,9 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         const int h = h0 + lane;
         bool near = false;
         if (h < m.nhf) {
-          const float* a = gpose + GP * m.hfl_slot[h];
+          const float* a = cpose(gpose, m, m.hfl_slot[h]);
           const float4 hb = m.hfl_box[h];
-          const float reach = Rw + a[13];
+          const float reach = Rw + gmar[m.hfl_geom[h]];
           const float dif[3] = {cw[0] - a[0], cw[1] - a[1], cw[2] - a[2]};
           const float lx = a[3] * dif[0] + a[6] * dif[1] + a[9] * dif[2], ly = a[4] * dif[0] + a[7] * dif[1] + a[10] * dif[2];
           const float lz = a[5] * dif[0] + a[8] * dif[1] + a[11] * dif[2];
@@ -1573,8 +1578,9 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         while (nm) {
           const int hh = h0 + __ffs((int)nm) - 1;
           nm &= nm - 1u;
-          const float* a = gpose + GP * m.hfl_slot[hh];
+          const float* a = cpose(gpose, m, m.hfl_slot[hh]);
           const float4 hb = m.hfl_box[hh];
+          const float amar = gmar[m.hfl_geom[hh]];
           const int en = m.hfl_start[hh + 1];
           #pragma unroll 1
           for (int k0 = m.hfl_start[hh]; k0 < en; k0 += 32) {
@@ -1584,7 +1590,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
             if (k < en) {
               p = m.hfl_pairs[k];
               const float* b = gpose + GP * ((m.pair_word[p] >> 12) & 0xfffu);
-              const float reach = fmaxf(a[13], b[13]) + b[12];
+              const float reach = fmaxf(amar, b[13]) + b[12];
               const float dif[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
               const float lx = a[3] * dif[0] + a[6] * dif[1] + a[9] * dif[2], ly = a[4] * dif[0] + a[7] * dif[1] + a[10] * dif[2];
               const float lz = a[5] * dif[0] + a[8] * dif[1] + a[11] * dif[2];
@@ -1717,7 +1723,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         const float *a, *b;
         if (p >= 0) {
           g1 = m.pair_geom1[p]; g2 = m.pair_geom2[p];
-          a = gpose + GP * m.geom_cslot[g1];
+          a = cpose(gpose, m, m.geom_cslot[g1]);
           b = gpose + GP * m.geom_cslot[g2];
         } else {  // grid-static candidate: (dynamic geom, static geom), ordered by (type, id)
           int k = p & 0xfffff;

@@ -93,7 +93,8 @@ struct DevModel {
   const int *pair_geom1, *pair_geom2;
   // height-field pairs, grouped by field (hierarchical broadphase; all nullptr / 0 without fields):
   int nhf, nhfd, n_nhpair;    // distinct fields, distinct geoms paired with a field, pairs without a field
-  const int* hfl_slot;        // [nhf] pose slot of the field
+  const int* hfl_slot;        // [nhf] pose slot of the field (or -2 - index into fixed_pose)
+  const int* hfl_geom;        // [nhf] its geom id
   const float4* hfl_box;      // [nhf] its box (rx, ry, elevation, base)
   const int* hfl_start;       // [nhf + 1] range of the field's pairs in hfl_pairs
   const int* hfl_pairs;       // pair indices, ascending per field
@@ -108,6 +109,9 @@ struct DevModel {
   const int *dyn_cgeom;    // dynamic collision geoms that visit the grid
   const int *static_geom, *static_cell0, *grid_start, *grid_items;
   const float* static_pose;  // 16 floats per static geom: pos[3], mat[9], rbound, pad[3] (world 0's model values)
+  int nfixed;                // height fields welded to the world: posed once at create, no shared-memory pose slot
+  const float* fixed_pose;   // [nfixed][16], same record as static_pose
+  const int* fixed_geom;     // [nfixed] geom ids
   // mesh / height-field assets (b2_convex.h): geom_dataid -> mesh or hfield id; shared by all worlds
   const int *geom_dataid, *mesh_vertadr, *mesh_vertnum, *hfield_adr, *hfield_nrow, *hfield_ncol;
   const float *mesh_vert, *hfield_size, *hfield_data;

@@ -478,25 +478,12 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
     }
   }
   m.fastkin = fastkin;
-  std::vector<int> cslot(m.ngeom, -1), cgeom;
-  for (int p = 0; p < m.npair; p++) {
-    for (int g : {s->mi["pair_geom1"][p], s->mi["pair_geom2"][p]})
-      if (cslot[g] < 0) { cslot[g] = (int)cgeom.size(); cgeom.push_back(g); }
-  }
-  // grid-static collision set: static geoms never move, so their world poses are computed here once (in
-  // double, from world 0's model values) and shared by all worlds; only the other geoms are posed per step
-  m.nstatic = geti("nstatic");
-  m.ndyn = (int)s->mi["dyn_cgeom"].size();
-  std::vector<int> posegeom;
-  std::vector<float> static_pose((size_t)std::max(m.nstatic, 1) * 16, 0.f);
-  {
-    std::vector<char> is_static(m.ngeom, 0);
-    const std::vector<int>& sg = s->mi["static_geom"];
-    if ((int)sg.size() != m.nstatic) { delete s; return fail("b2_create: static_geom / nstatic mismatch"); }
-    if (m.nstatic >= (1 << 20) || m.ndyn >= (1 << 11)) { delete s; return fail("b2_create: static grid too large"); }
+  // World pose (pos[3], mat[9], rbound) of a geom on a jointless child of the world body, in double from world 0's
+  // model values: such geoms never move, so they are posed here once and shared by all worlds.
+  auto welded = [&](int g) { int b = s->mi["geom_bodyid"][g]; return b == 0 || (parent[b] == 0 && dofnum[b] == 0); };
+  auto world_pose = [&](int g, float* o) {
     const std::vector<double>& bp = s->mf["body_pos"]; const std::vector<double>& bq = s->mf["body_quat"];
     const std::vector<double>& gp = s->mf["geom_pos"]; const std::vector<double>& gq = s->mf["geom_quat"];
-    const std::vector<double>& rb = s->mf["geom_rbound"];
     auto qmul = [](const double* a, const double* b, double* r) {
       r[0] = a[0]*b[0] - a[1]*b[1] - a[2]*b[2] - a[3]*b[3];
       r[1] = a[0]*b[1] + a[1]*b[0] + a[2]*b[3] - a[3]*b[2];
@@ -508,6 +495,47 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
       R[3] = 2*(q[1]*q[2] + q[0]*q[3]); R[4] = q[0]*q[0] - q[1]*q[1] + q[2]*q[2] - q[3]*q[3]; R[5] = 2*(q[2]*q[3] - q[0]*q[1]);
       R[6] = 2*(q[1]*q[3] - q[0]*q[2]); R[7] = 2*(q[2]*q[3] + q[0]*q[1]); R[8] = q[0]*q[0] - q[1]*q[1] - q[2]*q[2] + q[3]*q[3];
     };
+    const int b = s->mi["geom_bodyid"][g];
+    double Rb[9], q[4], R[9];
+    q2m(&bq[4 * b], Rb);
+    qmul(&bq[4 * b], &gq[4 * g], q);
+    double nq = std::sqrt(q[0]*q[0] + q[1]*q[1] + q[2]*q[2] + q[3]*q[3]);
+    for (double& x : q) x /= nq;
+    q2m(q, R);
+    for (int i = 0; i < 3; i++)
+      o[i] = (float)(bp[3 * b + i] + Rb[3 * i] * gp[3 * g] + Rb[3 * i + 1] * gp[3 * g + 1] + Rb[3 * i + 2] * gp[3 * g + 2]);
+    for (int i = 0; i < 9; i++) o[3 + i] = (float)R[i];
+    o[12] = (float)s->mf["geom_rbound"][g];
+  };
+  // Pose slots of the collision geoms in shared memory.  Height fields welded to the world (a terrain has tens of
+  // them) get no slot: their pose records live in global memory (fixed_pose, slot code -2 - index) - 56 bytes of
+  // shared memory per field and per environment otherwise, and a pose computation per step.
+  std::vector<int> cslot(m.ngeom, -1), cgeom, fixed_geom;
+  {
+    std::vector<char> second(m.ngeom, 0);
+    for (int p = 0; p < m.npair; p++) second[s->mi["pair_geom2"][p]] = 1;
+    for (int p = 0; p < m.npair; p++) {
+      for (int g : {s->mi["pair_geom1"][p], s->mi["pair_geom2"][p]}) {
+        if (cslot[g] != -1) continue;
+        if (s->mi["geom_type"][g] == G_HFIELD && !second[g] && welded(g)) { cslot[g] = -2 - (int)fixed_geom.size(); fixed_geom.push_back(g); }
+        else { cslot[g] = (int)cgeom.size(); cgeom.push_back(g); }
+      }
+    }
+  }
+  m.nfixed = (int)fixed_geom.size();
+  std::vector<float> fixed_pose((size_t)std::max(m.nfixed, 1) * 16, 0.f);
+  for (int f = 0; f < m.nfixed; f++) world_pose(fixed_geom[f], fixed_pose.data() + 16 * (size_t)f);
+  // grid-static collision set: static geoms never move, so their world poses are computed here once (in
+  // double, from world 0's model values) and shared by all worlds; only the other geoms are posed per step
+  m.nstatic = geti("nstatic");
+  m.ndyn = (int)s->mi["dyn_cgeom"].size();
+  std::vector<int> posegeom;
+  std::vector<float> static_pose((size_t)std::max(m.nstatic, 1) * 16, 0.f);
+  {
+    std::vector<char> is_static(m.ngeom, 0);
+    const std::vector<int>& sg = s->mi["static_geom"];
+    if ((int)sg.size() != m.nstatic) { delete s; return fail("b2_create: static_geom / nstatic mismatch"); }
+    if (m.nstatic >= (1 << 20) || m.ndyn >= (1 << 11)) { delete s; return fail("b2_create: static grid too large"); }
     for (int k = 0; k < m.nstatic; k++) {
       int g = sg[k], b = s->mi["geom_bodyid"][g];
       if (g < 0 || g >= m.ngeom || parent[b] != 0 || dofnum[b] != 0) {
@@ -515,18 +543,9 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
         return fail("b2_create: grid-static geoms must sit on a jointless child of the world body");
       }
       is_static[g] = 1;
-      double Rb[9], q[4], R[9];
-      q2m(&bq[4 * b], Rb);
-      qmul(&bq[4 * b], &gq[4 * g], q);
-      double nq = std::sqrt(q[0]*q[0] + q[1]*q[1] + q[2]*q[2] + q[3]*q[3]);
-      for (double& x : q) x /= nq;
-      q2m(q, R);
-      float* o = static_pose.data() + 16 * (size_t)k;
-      for (int i = 0; i < 3; i++)
-        o[i] = (float)(bp[3 * b + i] + Rb[3 * i] * gp[3 * g] + Rb[3 * i + 1] * gp[3 * g + 1] + Rb[3 * i + 2] * gp[3 * g + 2]);
-      for (int i = 0; i < 9; i++) o[3 + i] = (float)R[i];
-      o[12] = (float)rb[g];
+      world_pose(g, static_pose.data() + 16 * (size_t)k);
     }
+    for (int g : fixed_geom) is_static[g] = 1;
     for (int g = 0; g < m.ngeom; g++) if (!is_static[g]) posegeom.push_back(g);
     m.nposegeom = (int)posegeom.size();
     for (int g : s->mi["dyn_cgeom"]) {
@@ -621,13 +640,13 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
     std::vector<unsigned> pw(std::max(m.npair, 1), 0u);
     for (int p = 0; p < m.npair; p++) {
       int g1 = s->mi["pair_geom1"][p], g2 = s->mi["pair_geom2"][p];
-      pw[p] = (unsigned)cslot[g1] | ((unsigned)cslot[g2] << 12) | (s->mi["geom_type"][g1] == G_PLANE ? 0x80000000u : 0u) |
+      pw[p] = (unsigned)std::max(cslot[g1], 0) | ((unsigned)std::max(cslot[g2], 0) << 12) | (s->mi["geom_type"][g1] == G_PLANE ? 0x80000000u : 0u) |
               (s->mi["geom_type"][g1] == G_HFIELD ? 0x40000000u : 0u);
     }
     rc |= dev_upload<unsigned>(s, pw, &m.pair_word);
     // height-field pairs grouped by field: the kernel first finds the fields under the robot, then tests only
     // their pairs (a terrain is a grid of fields; the flat pair table would test every one of them)
-    std::vector<int> hf_geom, hf_slot, hf_start, hf_pairs, hfd, nh;
+    std::vector<int> hf_geom, hf_slot, hf_start, hf_pairs, hfd, nh;  // (hf_slot: pose slot, or -2 - index into fixed_pose)
     std::vector<std::vector<int>> per;
     std::vector<float> box;
     for (int p = 0; p < m.npair; p++) {
@@ -643,7 +662,7 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
       if (std::find(hfd.begin(), hfd.end(), cslot[g2]) == hfd.end()) hfd.push_back(cslot[g2]);
     }
     m.nhf = (int)hf_geom.size(); m.nhfd = (int)hfd.size(); m.n_nhpair = m.npair;
-    m.hfl_slot = m.hfl_start = m.hfl_pairs = m.hfd_slot = m.nh_pairs = nullptr; m.hfl_box = nullptr;
+    m.hfl_slot = m.hfl_geom = m.hfl_start = m.hfl_pairs = m.hfd_slot = m.nh_pairs = nullptr; m.hfl_box = nullptr;
     if (m.nhf > 0) {
       for (auto& v : per) { hf_start.push_back((int)hf_pairs.size()); hf_pairs.insert(hf_pairs.end(), v.begin(), v.end()); }
       hf_start.push_back((int)hf_pairs.size());
@@ -651,12 +670,16 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
       if (nh.empty()) nh.push_back(0);
       const float* bp = nullptr;
       rc |= dev_upload<int>(s, hf_slot, &m.hfl_slot); rc |= dev_upload<int>(s, hf_start, &m.hfl_start);
+      rc |= dev_upload<int>(s, hf_geom, &m.hfl_geom);
       rc |= dev_upload<int>(s, hf_pairs, &m.hfl_pairs); rc |= dev_upload<int>(s, hfd, &m.hfd_slot);
       rc |= dev_upload<int>(s, nh, &m.nh_pairs); rc |= dev_upload<float>(s, box, &bp);
       m.hfl_box = (const float4*)bp;
     }
   }
   rc |= dev_upload<int>(s, cslot, &m.geom_cslot);
+  rc |= dev_upload<float>(s, fixed_pose, &m.fixed_pose);
+  if (fixed_geom.empty()) fixed_geom.push_back(0);
+  rc |= dev_upload<int>(s, fixed_geom, &m.fixed_geom);
   rc |= dev_upload<int>(s, cgeom, &m.cgeom);
   {
     // schedules of the bottom-up blocked factorisation (b2_kernel.cuh: ldl_factor)
@@ -848,6 +871,13 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
       b2_static_rows_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(d.geom_xpos.p, d.geom_xpos.stride, d.geom_xmat.p,
                                                                      d.geom_xmat.stride, m.static_pose, m.static_geom,
                                                                      m.nstatic, nworld);
+      s->launches++;
+    }
+    if (m.nfixed > 0) {
+      long long tot = (long long)nworld * m.nfixed;
+      b2_static_rows_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(d.geom_xpos.p, d.geom_xpos.stride, d.geom_xmat.p,
+                                                                     d.geom_xmat.stride, m.fixed_pose, m.fixed_geom,
+                                                                     m.nfixed, nworld);
       s->launches++;
     }
     if (launch(s, false, 0)) { b2_destroy(s); return 1; }

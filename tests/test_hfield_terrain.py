@@ -100,6 +100,12 @@ def test_emulated_kernel_on_height_field_terrain():
     if nc[w]:
       assert np.abs(sim.field("contact_dist")[w, : nc[w]] - o.contact_dist[w, : nc[w]]).max() < 2e-5
   assert relerr(sim.field("qacc"), o.qacc).max() < 2e-3
+  # the fields are welded to the world: the engine poses them once at create (no per-step work, no shared-memory
+  # slot) - every world's geom_xpos / geom_xmat rows must still hold them
+  hf = np.nonzero(np.asarray(m.geom_type) == 1)[0]
+  assert np.abs(sim.field("geom_xpos")[:, hf] - o.geom_xpos.reshape(n, -1, 3)[:, hf]).max() < 1e-6
+  assert np.abs(sim.field("geom_xmat").reshape(n, -1, 9)[:, hf] - o.geom_xmat.reshape(n, -1, 9)[:, hf]).max() < 1e-6
+  assert sim.option("smem_bytes_per_env") < 13.5 * 1024  # (no pose slots for the fields; on the 70-field bench terrain the slots were 3.9 KB of 15.6 KB: 12 instead of 16 warps per SM)
   o.step()
   sim.step(1)
   assert relerr(sim.field("qpos"), o.qpos).max() < 1e-5

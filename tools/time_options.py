@@ -9,10 +9,13 @@ from mjlab_b200.envs import VelocityEnvCfg, VelocityFlatEnv
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 pre = int(sys.argv[2]) if len(sys.argv) > 2 else 100
-env = VelocityFlatEnv(VelocityEnvCfg(num_envs=n), device="cuda:0")
+import os
+_wl = os.environ.get("B2_WORKLOAD", "B")  # B: G1 flat, E: Go1 rough boxes, F: Go1 rough boxes + height fields
+_kw = dict(B={}, E=dict(robot="go1", terrain="rough"), F=dict(robot="go1", terrain="rough_hf"))[_wl]
+env = VelocityFlatEnv(VelocityEnvCfg(num_envs=n, **_kw), device="cuda:0")
 g = torch.Generator(device="cuda:0"); g.manual_seed(0)
 for _ in range(pre):
-  env.step(torch.rand((n, 29), generator=g, device="cuda:0") * 2 - 1)
+  env.step(torch.rand((n, 29 if _wl == "B" else 12), generator=g, device="cuda:0") * 2 - 1)
 torch.cuda.synchronize()
 sim = env.sim
 print("resident_ctas", sim.get_option("resident_ctas"), "smem/env", sim.get_option("smem_bytes_per_env"))
@@ -46,5 +49,6 @@ run("2 streams, psync off", dict(base, phase_sync=0))
 run("2 streams, full solver", dict(base, full_solver=1))
 run("2 streams, ls_relstep off", dict(base, ls_relstep=0))
 run("reorder once per step_n", dict(base, ls_relstep=1, reorder_every_substep=0))
+run("psync level 1", dict(base, ls_relstep=1, phase_sync=1))
 run("psync level 3", dict(base, ls_relstep=1, phase_sync=3))
 run("default again", dict(base, ls_relstep=1))
