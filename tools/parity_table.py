@@ -1,6 +1,6 @@
 """Per-field error table of the CUDA path against the fp64 oracle.
 
-For each workload (B: g1_flat, C: g1_tracking_flat, E: go1_rough) and each build of libb2sim (default +
+For each workload (B: g1_flat, C: g1_tracking_flat, E: go1_rough, F: go1_rough_hf) and each build of libb2sim (default +
 mjlab_b200/csrc/variants/v_*.so) one forward and one step from identical seeded states on >= 1024 envs;
 the error of a field is the norm-wise relative error per env, max|a-b| / max|b| (no floor), reported as
 p50 / p99 / max over envs.  Writes gpurun_out/parity_table.json and a markdown table on stdout.
@@ -20,7 +20,8 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 WORKLOADS = [("B", "g1_flat", dict(seed=31)),
              ("C", "g1_tracking_flat", dict(seed=32, tilt=0.5, joint_noise=0.6, vel=1.5)),
-             ("E", "go1_rough", dict(seed=33, spread=2.2))]
+             ("E", "go1_rough", dict(seed=33, spread=2.2)),
+             ("F", "go1_rough_hf", dict(seed=34, hf_spread=2.2))]
 FWD = ["qacc_smooth", "qacc", "qfrc_constraint", "contact_force", "cvel", "qM"]
 STEP = ["qpos", "qvel", "qacc_warmstart"]
 
@@ -39,7 +40,7 @@ def rel(a, b, floor=1e-9):
 def one(tag: str, n: int):
   import numpy as np
   import torch
-  from util import load_oracle, load_sim, make_states, terrain_states
+  from util import hfield_states, load_oracle, load_sim, make_states, terrain_states
   from mjlab_b200.asset_zoo import load_compiled
   from mjlab_b200.sim import Simulation, SimulationCfg
   from oracle.oracle import Oracle
@@ -55,7 +56,9 @@ def one(tag: str, n: int):
     o.set_option("iterations", 50)
     sim.set_option("iterations", 50)  # (both sides: a capped, unconverged answer depends on the path taken)
     kw = dict(kw)
-    if "spread" in kw:
+    if "hf_spread" in kw:
+      st = hfield_states(m, n, kw["seed"], kw["hf_spread"])
+    elif "spread" in kw:
       st = terrain_states(m, n, kw["seed"], kw["spread"])
     else:
       st = make_states(m, n, **kw)
