@@ -127,21 +127,45 @@ __global__ void b2_order_kernel(const int* __restrict__ niter, int niter_stride,
   __shared__ int base[128];
   for (int i = threadIdx.x; i < 128; i += blockDim.x) hist[i] = 0;
   __syncthreads();
-  for (int k = threadIdx.x; k < count; k += blockDim.x) {
+  // (keys stay in registers between the two passes: up to 4 worlds per thread, the common case; more are re-read)
+  int keys[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    int k = threadIdx.x + j * blockDim.x;
+    keys[j] = -1;
+    if (k < count) {
+      int w = base_world + k;
+      keys[j] = 127 - b2_order_key(niter[(size_t)w * niter_stride], nd[(size_t)w * nd_stride], ncon[(size_t)w * ncon_stride], nd_small);
+      atomicAdd(&hist[keys[j]], 1);
+    }
+  }
+  for (int k = threadIdx.x + 4 * blockDim.x; k < count; k += blockDim.x) {
     int w = base_world + k;
-    int key = b2_order_key(niter[(size_t)w * niter_stride], nd[(size_t)w * nd_stride], ncon[(size_t)w * ncon_stride], nd_small);
-    atomicAdd(&hist[127 - key], 1);
+    atomicAdd(&hist[127 - b2_order_key(niter[(size_t)w * niter_stride], nd[(size_t)w * nd_stride], ncon[(size_t)w * ncon_stride], nd_small)], 1);
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int i = 0; i < 128; i++) { base[i] = acc; acc += hist[i]; }
+  if (threadIdx.x < 32) {  // exclusive prefix over the 128 buckets: 4 per lane + a warp scan
+    int h0 = hist[4 * threadIdx.x], h1 = hist[4 * threadIdx.x + 1], h2 = hist[4 * threadIdx.x + 2], h3 = hist[4 * threadIdx.x + 3];
+    int sum = h0 + h1 + h2 + h3, incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((int)threadIdx.x >= o) incl += t;
+    }
+    int ex = incl - sum;
+    base[4 * threadIdx.x] = ex; base[4 * threadIdx.x + 1] = ex + h0;
+    base[4 * threadIdx.x + 2] = ex + h0 + h1; base[4 * threadIdx.x + 3] = ex + h0 + h1 + h2;
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < count; k += blockDim.x) {
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    int k = threadIdx.x + j * blockDim.x;
+    if (k < count) order[base_world + atomicAdd(&base[keys[j]], 1)] = base_world + k;
+  }
+  for (int k = threadIdx.x + 4 * blockDim.x; k < count; k += blockDim.x) {
     int w = base_world + k;
-    int key = b2_order_key(niter[(size_t)w * niter_stride], nd[(size_t)w * nd_stride], ncon[(size_t)w * ncon_stride], nd_small);
-    order[base_world + atomicAdd(&base[127 - key], 1)] = w;
+    int key = 127 - b2_order_key(niter[(size_t)w * niter_stride], nd[(size_t)w * nd_stride], ncon[(size_t)w * ncon_stride], nd_small);
+    order[base_world + atomicAdd(&base[key], 1)] = w;
   }
 }
 

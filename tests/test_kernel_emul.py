@@ -480,3 +480,24 @@ def test_emulated_cg_solver_reaches_the_newton_minimiser(lib):
   assert it.max() > 10 and it.max() < 200  # converged by its own criterion, not by the cap
   assert lib.b2_set_option(sim.h, b"solver", 0.0) != 0  # PGS is refused
   sim.close()
+
+
+def test_emulated_sorted_dispatch_changes_scheduling_only(lib):
+  """b2_order_kernel (heavy-first counting sort of the worlds, one 1024-thread CTA) on the host emulation: with the
+  sorted dispatch on, every world is still stepped exactly once - the states after three steps are bit-identical
+  to the unsorted run (a lost or duplicated world would leave its state behind or step it twice)."""
+  from mjlab_b200.asset_zoo import load_compiled
+
+  m = load_compiled("go1_flat")
+  n = 520  # (the sort is used from 512 worlds up)
+  st = make_states(m, n, seed=3)
+  out = []
+  for sd in (0.0, 1.0):
+    sim = EmulSim(lib, m, n)
+    lib.b2_set_option(sim.h, b"sorted_dispatch", sd)
+    sim.load(st)
+    sim.step(3)
+    out.append((sim.field("qpos").copy(), sim.field("qvel").copy(), sim.field("solver_niter").copy()))
+    sim.close()
+  assert len(np.unique(out[0][2])) > 2  # the sort key (Newton iterations) takes several values
+  assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
