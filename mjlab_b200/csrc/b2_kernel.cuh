@@ -1983,6 +1983,8 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       start = (c == 0) || ((((int*)con)[CINFO * MC + c - 1] & 0xffff) != key);
     }
     unsigned bal = __ballot_sync(FULL, start);
+    __syncwarp();  // (the neighbour's word is read above and rewritten below: only its top byte changes, but keep
+                   // the accesses ordered - compute-sanitizer racecheck is clean with the two barriers)
     int before = ngroup + __popc(bal & ((1u << lane) - 1u));
     if (c < ncon) {
       int g = start ? before : before - 1;
@@ -1990,6 +1992,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
       if (start) gstart[g] = c;
     }
     ngroup += __popc(bal);
+    __syncwarp();
   }
   if (lane == 0) gstart[ngroup] = ncon;
   __syncwarp();
