@@ -316,6 +316,12 @@ _SUPPORTED_PAIRS = {
   (S.GEOM_HFIELD, S.GEOM_SPHERE), (S.GEOM_HFIELD, S.GEOM_CAPSULE), (S.GEOM_HFIELD, S.GEOM_BOX),
   (S.GEOM_HFIELD, S.GEOM_MESH),
 }
+# cylinders and ellipsoids: smooth convex cores with closed-form support points (GJK / EPA against every convex
+# shape, prisms of a height field included; MuJoCo's plane primitives against a plane)
+for _t in (S.GEOM_ELLIPSOID, S.GEOM_CYLINDER):
+  _SUPPORTED_PAIRS |= {(S.GEOM_PLANE, _t), (S.GEOM_HFIELD, _t)}
+  for _u in (S.GEOM_SPHERE, S.GEOM_CAPSULE, S.GEOM_ELLIPSOID, S.GEOM_CYLINDER, S.GEOM_BOX, S.GEOM_MESH):
+    _SUPPORTED_PAIRS.add((min(_t, _u), max(_t, _u)))
 STATIC_GRID_THRESHOLD = 16  # more static box/sphere/capsule geoms than this -> grid broadphase
 
 
@@ -380,8 +386,8 @@ def _build_static_grid(A, static, weld, gbody, gtype, ngeom, cell: float = 1.0) 
                     if g not in inset and weld[gbody[g]] != 0
                     and ((A["geom_contype"][g] & smask_a) or (A["geom_conaffinity"][g] & smask_t))]
   for g in A["dyn_cgeom"]:
-    if gtype[g] not in (S.GEOM_SPHERE, S.GEOM_CAPSULE, S.GEOM_BOX, S.GEOM_MESH):
-      raise NotImplementedError("only sphere / capsule / box / mesh geoms can collide with grid-static geoms")
+    if gtype[g] not in (S.GEOM_SPHERE, S.GEOM_CAPSULE, S.GEOM_ELLIPSOID, S.GEOM_CYLINDER, S.GEOM_BOX, S.GEOM_MESH):
+      raise NotImplementedError("only sphere / capsule / ellipsoid / cylinder / box / mesh geoms can collide with grid-static geoms")
 
 
 def compile_spec(spec: S.Spec) -> Model:

@@ -11,6 +11,10 @@
 //   * a geom is a convex CORE (point, segment, box, vertex set, prism) inflated by a radius; separated cores give
 //     dist = |closest points| - r1 - r2 (GJK), overlapping cores give dist = -(penetration depth) - r1 - r2 (EPA on
 //     the Minkowski difference); normal from geom 1 to geom 2, position midway between the two surface points;
+//   * cylinders and ellipsoids are smooth convex cores (radius 0) with closed-form support points; against a plane
+//     they use MuJoCo's primitives (mjc_PlaneCylinder: the deepest rim point, the rim point at the other end of the
+//     same generator, and two more points of the near cap at +-120 degrees; mjc_PlaneEllipsoid: the support point
+//     along the plane normal) [UPSTREAM-MEMORY];
 //   * plane - mesh: up to four vertices within 1e-3 of the lowest one: the lowest, the one farthest from it, the
 //     one farthest from that line, and the farthest one on the other side of the line;
 //   * height field: cells under the geom's bounding sphere, two prisms per cell (diagonal (r,c)-(r+1,c+1)), top
@@ -19,7 +23,8 @@
 // double — into the CPU oracle (oracle/b2_oracle.c includes it), so oracle-vs-kernel parity checks the fp32
 // arithmetic and the integration, not the algorithm.  The algorithm itself is pinned independently by
 // tests/test_convex.py: depth / distance / normal of random polytope pairs against the exact values obtained from the
-// convex hull of the Minkowski difference (scipy.spatial.ConvexHull), and statics of resting bodies.
+// convex hull of the Minkowski difference (scipy.spatial.ConvexHull), and statics of resting bodies; cylinders and
+// ellipsoids by tests/test_smooth_shapes.py against -min_u [h_A(u) + h_B(-u)] from closed-form support functions.
 #pragma once
 
 #ifndef B2C_REAL
@@ -31,6 +36,8 @@
 #define B2C_BOX 2       // half sizes size[0..2]
 #define B2C_VERTS 3     // mesh: nvert local-frame vertices
 #define B2C_PRISM 4     // 6 world-frame points in pts
+#define B2C_CYLINDER 5  // radius size[0], half height size[1] along local z
+#define B2C_ELLIPSOID 6 // semi-axes size[0..2]
 #define B2C_MAXOUT 8
 #define B2C_GJK_ITER 40
 #define B2C_EPA_ITER 24
@@ -83,6 +90,14 @@ B2C_INL void b2c_support(const B2CShape* s, const b2c_real* d, b2c_real* out) {
   b2c_real v[3];
   if (s->type == B2C_BOX) {
     for (int k = 0; k < 3; k++) v[k] = dl[k] >= 0 ? s->size[k] : -s->size[k];
+  } else if (s->type == B2C_CYLINDER) {
+    const b2c_real rho = B2C_SQRT(dl[0] * dl[0] + dl[1] * dl[1]);
+    const b2c_real k = rho > b2c_eps() * B2C_SQRT(b2c_dot(dl, dl)) ? s->size[0] / rho : 0;  // (along the axis: the cap's centre)
+    v[0] = k * dl[0]; v[1] = k * dl[1]; v[2] = dl[2] >= 0 ? s->size[1] : -s->size[1];
+  } else if (s->type == B2C_ELLIPSOID) {
+    const b2c_real a = s->size[0] * dl[0], b = s->size[1] * dl[1], c = s->size[2] * dl[2];
+    const b2c_real nn = B2C_SQRT(a * a + b * b + c * c), k = nn > 0 ? 1 / nn : 0;
+    v[0] = s->size[0] * a * k; v[1] = s->size[1] * b * k; v[2] = s->size[2] * c * k;
   } else {  // B2C_VERTS
     int best = 0;
     b2c_real bv = b2c_dot(s->vert, dl);
@@ -272,9 +287,17 @@ B2C_FN b2c_real b2c_epa(const B2CShape* A, const B2CShape* B, const B2CVert* S, 
   }
   const b2c_real tol = (sizeof(b2c_real) == 4 ? (b2c_real)2e-6 : (b2c_real)1e-11) * scale;
   int best = 0;
+  B2CFace good = F[0];  // closest face of the last consistent polytope
+  b2c_real lastd = -(b2c_real)1e30;
   for (int it = 0;; it++) {
     best = 0;
     for (int f = 1; f < nf; f++) if (F[f].d < F[best].d) best = f;
+    // The closest face can only move outwards as the polytope grows.  When it comes back in, the last expansion
+    // corrupted the polytope (a triangle built across a nearly flat region of the horizon came out flipped - curved
+    // shapes in fp32 produce such regions near convergence): the answer is the closest face before it.
+    if (F[best].d < lastd - 4 * tol) { F[0] = good; nf = 1; best = 0; break; }
+    good = F[best];
+    lastd = F[best].d;
     if (it >= B2C_EPA_ITER || nv >= B2C_EPA_NV || nf + 8 > B2C_EPA_NF) break;
     B2CVert w;
     b2c_support_diff(A, B, F[best].n, &w);
@@ -284,7 +307,11 @@ B2C_FN b2c_real b2c_epa(const B2CShape* A, const B2CShape* B, const B2CVert* S, 
     for (int f = 0; f < nf; f++) {
       const b2c_real* a = V[F[f].i[0]].w;
       b2c_real side = F[f].n[0] * (w.w[0] - a[0]) + F[f].n[1] * (w.w[1] - a[1]) + F[f].n[2] * (w.w[2] - a[2]);
-      if (F[f].d < (b2c_real)1e29 && side <= 0) { if (keep != f) F[keep] = F[f]; keep++; continue; }
+      // (a face the new point is coplanar with - within rounding, an eighth of the margin by which the best face
+      // sees it - stays: deciding such faces by the sign of a rounding error lets the horizon run through a flat
+      // facet, and the triangle built on an edge inside it comes out flipped; rim points of a cylinder cap are all
+      // coplanar)
+      if (F[f].d < (b2c_real)1e29 && side <= tol * (b2c_real)0.125) { if (keep != f) F[keep] = F[f]; keep++; continue; }
       for (int e = 0; e < 3; e++) {
         unsigned char p = F[f].i[e], q = F[f].i[(e + 1) % 3];
         int found = -1;
@@ -604,6 +631,70 @@ B2C_FN b2c_real b2c_shape(B2CShape* s, int gtype, const b2c_real* pos, const b2c
   if (gtype == 2) { s->type = B2C_POINT; return size[0]; }
   if (gtype == 3) { s->type = B2C_SEGMENT; return size[0]; }
   if (gtype == 6) { s->type = B2C_BOX; return 0; }
+  if (gtype == 5) { s->type = B2C_CYLINDER; return 0; }
+  if (gtype == 4) { s->type = B2C_ELLIPSOID; return 0; }
   s->type = B2C_VERTS;
   return 0;
+}
+
+// plane (pos pp, normal pn) against a cylinder: up to 4 contacts (mjc_PlaneCylinder)
+B2C_FN int b2c_plane_cylinder(B2CCon* out, b2c_real margin, const b2c_real* pp, const b2c_real* pn, const b2c_real* pos,
+                              const b2c_real* mat, const b2c_real* size) {
+  b2c_real axis[3] = {mat[2], mat[5], mat[8]};
+  b2c_real prjaxis = b2c_dot(pn, axis);
+  if (prjaxis > 0) { axis[0] = -axis[0]; axis[1] = -axis[1]; axis[2] = -axis[2]; prjaxis = -prjaxis; }  // axis towards the plane
+  const b2c_real dist0 = (pos[0] - pp[0]) * pn[0] + (pos[1] - pp[1]) * pn[1] + (pos[2] - pp[2]) * pn[2];
+  // radial direction towards the plane: -normal without its component along the axis
+  b2c_real vec[3] = {axis[0] * prjaxis - pn[0], axis[1] * prjaxis - pn[1], axis[2] * prjaxis - pn[2]};
+  const b2c_real len2 = b2c_dot(vec, vec);
+  if (len2 >= (b2c_real)1e-10) {  // (MuJoCo: mjMINVAL^2; 1e-10 = an angle of 1e-5 rad, above fp32 rounding of a flat cap)
+    const b2c_real k = size[0] / B2C_SQRT(len2);
+    vec[0] *= k; vec[1] *= k; vec[2] *= k;
+  } else {  // cap parallel to the plane: the cylinder's x axis
+    vec[0] = mat[0] * size[0]; vec[1] = mat[3] * size[0]; vec[2] = mat[6] * size[0];
+  }
+  const b2c_real prjvec = b2c_dot(vec, pn);
+  axis[0] *= size[1]; axis[1] *= size[1]; axis[2] *= size[1];
+  prjaxis *= size[1];
+  int n = 0;
+  if (dist0 + prjaxis + prjvec > margin) return 0;
+  out[n].dist = dist0 + prjaxis + prjvec;
+  for (int k = 0; k < 3; k++) { out[n].pos[k] = pos[k] + vec[k] + axis[k] - pn[k] * out[n].dist * (b2c_real)0.5; out[n].n[k] = pn[k]; }
+  n++;
+  if (dist0 - prjaxis + prjvec <= margin) {
+    out[n].dist = dist0 - prjaxis + prjvec;
+    for (int k = 0; k < 3; k++) { out[n].pos[k] = pos[k] + vec[k] - axis[k] - pn[k] * out[n].dist * (b2c_real)0.5; out[n].n[k] = pn[k]; }
+    n++;
+  }
+  const b2c_real prjvec1 = -prjvec * (b2c_real)0.5;
+  if (dist0 + prjaxis + prjvec1 <= margin) {
+    b2c_real vec1[3];
+    b2c_cross(vec1, vec, axis);
+    const b2c_real l1 = B2C_SQRT(b2c_dot(vec1, vec1));
+    if (l1 > 0) {
+      const b2c_real k = size[0] * (b2c_real)0.8660254037844386 / l1;
+      const b2c_real d = dist0 + prjaxis + prjvec1;
+      for (int sgn = 0; sgn < 2; sgn++) {
+        out[n].dist = d;
+        for (int c = 0; c < 3; c++) {
+          out[n].pos[c] = pos[c] + (sgn ? -k : k) * vec1[c] + axis[c] - vec[c] * (b2c_real)0.5 - pn[c] * d * (b2c_real)0.5;
+          out[n].n[c] = pn[c];
+        }
+        n++;
+      }
+    }
+  }
+  return n;
+}
+
+// plane against an ellipsoid: the support point along -normal (mjc_PlaneEllipsoid)
+B2C_FN int b2c_plane_ellipsoid(B2CCon* out, b2c_real margin, const b2c_real* pp, const b2c_real* pn, const B2CShape* E) {
+  const b2c_real nd[3] = {-pn[0], -pn[1], -pn[2]};
+  b2c_real q[3];
+  b2c_support(E, nd, q);
+  const b2c_real dist = (q[0] - pp[0]) * pn[0] + (q[1] - pp[1]) * pn[1] + (q[2] - pp[2]) * pn[2];
+  if (dist > margin) return 0;
+  out[0].dist = dist;
+  for (int k = 0; k < 3; k++) { out[0].pos[k] = q[k] - pn[k] * dist * (b2c_real)0.5; out[0].n[k] = pn[k]; }
+  return 1;
 }

@@ -657,7 +657,9 @@ __device__ __noinline__ int convex_narrowphase(RawCon* rc, float margin, const D
   int n = 0;
   if (t1 == G_PLANE) {
     float pn[3] = {a[3 + 2], a[3 + 5], a[3 + 8]};
-    n = b2c_plane_mesh(cc, margin, a, pn, &B);
+    if (t2 == G_CYLINDER) n = b2c_plane_cylinder(cc, margin, a, pn, b, b + 3, s2);
+    else if (t2 == G_ELLIPSOID) n = b2c_plane_ellipsoid(cc, margin, a, pn, &B);
+    else n = b2c_plane_mesh(cc, margin, a, pn, &B);
   } else if (t1 == G_HFIELD) {
     n = 0;  // height-field pairs go through hfield_lanes
   } else {
@@ -1741,7 +1743,7 @@ b2_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevDa
         const float* s1 = gsize + 3 * g1; const float* s2 = gsize + 3 * g2;
         if (CVX && t1 == G_HFIELD) {
           hf = t2 != G_HFIELD; hfa = a; hfb = b;
-        } else if (CVX && t2 == G_MESH) {
+        } else if (CVX && (t2 == G_MESH || ((1u << t1 | 1u << t2) & (1u << G_ELLIPSOID | 1u << G_CYLINDER)))) {
           n = convex_narrowphase(rc, margin, m, g1, g2, a, b, s1, s2);
         } else if (t1 == G_PLANE) {
           float pn[3] = {a[3 + 2], a[3 + 5], a[3 + 8]};

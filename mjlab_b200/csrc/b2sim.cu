@@ -588,17 +588,18 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
     }
   }
   m.ncg = (int)cgeom.size();
-  {  // every collision pair must have a narrowphase routine (plane/sphere/capsule/box primitives only)
+  {  // every collision pair must have a narrowphase routine (primitives, or the convex routines of b2_convex.h)
     const std::vector<int>& gt = s->mi["geom_type"];
     auto prim = [](int t) { return t == G_SPHERE || t == G_CAPSULE || t == G_BOX; };
-    auto conv = [&](int t) { return prim(t) || t == G_MESH; };  // shapes the GJK/EPA routine takes (b2_convex.h)
+    auto smooth = [](int t) { return t == G_ELLIPSOID || t == G_CYLINDER; };
+    auto conv = [&](int t) { return prim(t) || t == G_MESH || smooth(t); };  // shapes the GJK/EPA routine takes (b2_convex.h)
     const std::vector<int>& did = s->mi["geom_dataid"];
     const int nmesh = (int)s->mi["mesh_vertnum"].size(), nhf = (int)s->mi["hfield_nrow"].size();
     for (int p = 0; p < m.npair; p++) {
       int g1 = s->mi["pair_geom1"][p], g2 = s->mi["pair_geom2"][p];
       int t1 = gt[g1], t2 = gt[g2];
       bool ok = (t1 == G_PLANE && conv(t2)) || (t1 == G_HFIELD && conv(t2)) || (conv(t1) && conv(t2) && t1 <= t2);
-      if (t2 == G_MESH || t1 == G_HFIELD) s->has_convex = 1;
+      if (t2 == G_MESH || t1 == G_HFIELD || smooth(t1) || smooth(t2)) s->has_convex = 1;
       if (!ok) { delete s; return fail("b2_create: collision pair with an unsupported geom type combination"); }
       for (int g : {g1, g2}) {
         int t = gt[g];
@@ -616,7 +617,7 @@ int b2_create(const B2ModelDesc* desc, int nworld, int ncon_per_world, int njmax
     }
     for (int g : s->mi["dyn_cgeom"]) {
       if (!conv(gt[g])) { delete s; return fail("b2_create: unsupported dynamic geom type for the static grid"); }
-      if (gt[g] == G_MESH) s->has_convex = 1;
+      if (gt[g] == G_MESH || smooth(gt[g])) s->has_convex = 1;
     }
     for (int g : s->mi["static_geom"]) if (!prim(gt[g])) { delete s; return fail("b2_create: unsupported grid-static geom type"); }
   }

@@ -37,7 +37,7 @@ typedef double real;
 #define MAXIMP ((real)0.9999)
 #define MINMU ((real)1e-5)
 enum { JNT_FREE = 0, JNT_BALL = 1, JNT_SLIDE = 2, JNT_HINGE = 3 };
-enum { G_PLANE = 0, G_HFIELD = 1, G_SPHERE = 2, G_CAPSULE = 3, G_BOX = 6, G_MESH = 7 };
+enum { G_PLANE = 0, G_HFIELD = 1, G_SPHERE = 2, G_CAPSULE = 3, G_ELLIPSOID = 4, G_CYLINDER = 5, G_BOX = 6, G_MESH = 7 };
 enum { OBJ_BODY = 1, OBJ_XBODY = 2, OBJ_GEOM = 5 };
 enum { INT_EULER = 0, INT_IMPLICITFAST = 3 };
 enum { EFC_LIMIT = 3, EFC_FRICTIONLESS = 4, EFC_PYRAMIDAL = 5 };
@@ -862,7 +862,7 @@ static int narrowphase(const W* d, RawCon* rc, int g1, int g2, real margin) {
   if (t1 == G_SPHERE && t2 == G_BOX) return sphere_box(rc, margin, p1, s1[0], p2, m2, s2);
   if (t1 == G_CAPSULE && t2 == G_BOX) return capsule_box(rc, margin, p1, m1, s1, p2, m2, s2);
   if (t1 == G_BOX && t2 == G_BOX) return box_box(rc, margin, p1, m1, s1, p2, m2, s2);
-  if (t2 == G_MESH || t1 == G_HFIELD) {  /* convex routines (b2_convex.h) */
+  if (t2 == G_MESH || t1 == G_HFIELD || t1 == G_ELLIPSOID || t1 == G_CYLINDER || t2 == G_ELLIPSOID || t2 == G_CYLINDER) {  /* convex routines (b2_convex.h) */
     const real* rb = M_(o, geom_rbound, w);
     B2CCon cc[B2C_MAXOUT];
     B2CShape A, B;
@@ -871,6 +871,8 @@ static int narrowphase(const W* d, RawCon* rc, int g1, int g2, real margin) {
     real r2 = b2c_shape(&B, t2, p2, m2, s2, v2, n2);
     if (t1 == G_PLANE) {
       real pn[3] = { m1[2], m1[5], m1[8] };
+      if (t2 == G_CYLINDER) return from_b2c(rc, cc, b2c_plane_cylinder(cc, margin, p1, pn, p2, m2, s2));
+      if (t2 == G_ELLIPSOID) return from_b2c(rc, cc, b2c_plane_ellipsoid(cc, margin, p1, pn, &B));
       return from_b2c(rc, cc, b2c_plane_mesh(cc, margin, p1, pn, &B));
     }
     if (t1 == G_HFIELD) {
@@ -1643,6 +1645,15 @@ int b2o_prim_plane_mesh(const real* pp, const real* pn, const real* p2, const re
   b2c_shape(&B, G_MESH, p2, m2, sz, v2, n2);
   RawCon rc[4];
   return prim_out(rc, from_b2c(rc, c, b2c_plane_mesh(c, margin, pp, pn, &B)), out);
+}
+/* plane against a cylinder (t2 = 5, up to 4 contacts) or an ellipsoid (t2 = 4, one contact) */
+int b2o_prim_plane_smooth(const real* pp, const real* pn, int t2, const real* p2, const real* m2, const real* s2,
+                          real margin, real* out) {
+  B2CShape B; B2CCon c[4];
+  b2c_shape(&B, t2, p2, m2, s2, NULL, 0);
+  RawCon rc[4];
+  int n = t2 == G_CYLINDER ? b2c_plane_cylinder(c, margin, pp, pn, p2, m2, s2) : b2c_plane_ellipsoid(c, margin, pp, pn, &B);
+  return prim_out(rc, from_b2c(rc, c, n), out);
 }
 int b2o_prim_hfield(const real* hp, const real* hm, const real* hsize, int nrow, int ncol, const real* hdata,
                     int t2, const real* p2, const real* m2, const real* s2, const real* v2, int n2, real rbound,
