@@ -214,8 +214,10 @@ def mj_getState(model: MjModel, data, state: np.ndarray, spec: int) -> None:
 
 
 def mj_saveModel(model: MjModel, filename: str, buffer=None) -> None:
-  """The compiled-model blob of this engine (``Model.save``: npz) written under the requested name."""
-  model.save(filename)
+  """The compiled-model blob of this engine (``Model.save``: npz) written under exactly the requested name
+  (``utils/nan_guard.py`` stores ``model_<stamp>.mjb`` next to its dump and looks it up by that name)."""
+  with open(filename, "wb") as f:
+    model.save(f)
 
 
 # visual enums referenced at import time by utils/spec_config.py (texture / light / camera editors); the

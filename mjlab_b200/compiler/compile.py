@@ -143,6 +143,11 @@ class Model:
     np.savez_compressed(path, __meta__=np.array(json.dumps(meta)), **self.arrays)
 
   @staticmethod
+  def from_binary_path(path) -> "Model":
+    """``mujoco.MjModel.from_binary_path``: the blob ``mj_saveModel`` wrote (this engine's npz, whatever its suffix)."""
+    return Model.load(path)
+
+  @staticmethod
   def load(path) -> "Model":
     import json
 

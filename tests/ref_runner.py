@@ -1,0 +1,31 @@
+"""Run test files of the reference (unmodified, where they lie under /root/reference/tests) against this repo's
+stand-ins: ``mujoco`` / ``mujoco_warp`` / ``warp`` from mjlab_b200.compat, ``mjlab`` from baseline/_ref (tests/refload.py),
+and - there being no GPU in the container - the engine compiled for the host (tests/emul/engine.py) behind the
+``mujoco_warp`` stand-in.  Used by tests/test_reference_own_tests.py:  python tests/ref_runner.py <pytest args>"""
+import sys
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+sys.path[:0] = [str(HERE.parent), str(HERE), str(HERE / "emul")]
+
+import refload  # noqa: E402
+
+refload.load()
+
+import mjlab_b200.compat.mujoco_warp_shim as mw  # noqa: E402
+from engine import EmulEngine  # noqa: E402
+from mjlab_b200.sim import native  # noqa: E402
+
+mw._Engine = EmulEngine
+
+
+def _check(rc):
+  if rc:
+    raise RuntimeError("b2sim call failed")
+
+
+native.check = _check
+
+import pytest  # noqa: E402
+
+sys.exit(pytest.main(["-q", "-c", "/dev/null", "-p", "no:cacheprovider", *sys.argv[1:]]))

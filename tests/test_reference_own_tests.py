@@ -1,0 +1,40 @@
+"""The reference's OWN test files, unmodified and read where they lie (/root/reference/tests), executed against this
+repo's drop-in: ``mjlab`` is the unmodified package under baseline/_ref, ``mujoco`` / ``mujoco_warp`` / ``warp`` are
+mjlab_b200.compat, and the engine behind them is the product's CUDA source compiled for the host (tests/ref_runner.py).
+Only files whose subject is on the boundary of SURVEY.md §8(b) are run; the few cases that need what this image
+lacks (gymnasium, MJCF <sensor> parsing in the model compiler) are deselected by name, everything else must pass.
+The GPU box has no /root/reference: the module is skipped there (and is not part of `-m gpu`)."""
+
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+import refload
+
+REF_TESTS = Path("/root/reference/tests")
+pytestmark = pytest.mark.skipif(not (REF_TESTS.is_dir() and refload.available()),
+                                reason="needs /root/reference and baseline/_ref (build container only)")
+
+CASES = [
+  # file, deselect expression, minimum number of passing tests
+  ("test_sim_data.py", None, 6),             # TorchArray / WarpBridge on the warp stand-in's arrays
+  ("test_scene_entity_config.py", None, 12),  # name -> id resolution used by every MDP term
+  ("test_nan_guard.py", "not complex_model", 4),  # Simulation.step on the engine under NanGuard, dump + model blob
+  # (the articulated fixture declares MJCF <sensor> elements, which the model compiler of this repo does not parse)
+  ("test_entity.py", "not expected2 and not test_find_methods and not test_force_on_specific_body", 6),
+]
+
+
+@pytest.mark.parametrize("name,deselect,min_pass", CASES, ids=[c[0] for c in CASES])
+def test_reference_test_file_passes_on_the_drop_in(name, deselect, min_pass, tmp_path):
+  cmd = [sys.executable, str(Path(__file__).with_name("ref_runner.py")), "--rootdir", str(tmp_path), str(REF_TESTS / name)]
+  if deselect:
+    cmd += ["-k", deselect]
+  r = subprocess.run(cmd, capture_output=True, text=True, cwd=tmp_path, timeout=600)
+  tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-500:]
+  m = re.search(r"(\d+) passed", tail)
+  assert r.returncode == 0 and m and "failed" not in tail and "error" not in tail, r.stdout[-3000:] + r.stderr[-2000:]
+  assert int(m.group(1)) >= min_pass, tail
