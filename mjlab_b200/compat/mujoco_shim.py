@@ -197,6 +197,16 @@ def mj_forward(model: MjModel, data: MjData) -> None:
   return None
 
 
+def mj_resetDataKeyframe(model: MjModel, data: MjData, key: int) -> None:
+  """State of keyframe ``key`` (by position in the model's keyframe list) into the host-side ``MjData``."""
+  k = list(model.keys.values())[key]
+  data.qpos = np.array(k["qpos"] if k.get("qpos") is not None else model.qpos0, dtype=np.float64)
+  data.qvel = np.array(k["qvel"], dtype=np.float64) if k.get("qvel") is not None else np.zeros(int(model.nv))
+  if k.get("ctrl") is not None:
+    data.ctrl = np.array(k["ctrl"], dtype=np.float64)
+  data.time = 0.0
+
+
 def mj_stateSize(model: MjModel, spec: int) -> int:
   n = 0
   if spec & mjtState.mjSTATE_TIME: n += 1

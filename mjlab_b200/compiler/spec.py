@@ -192,6 +192,17 @@ class Site:
   id: int = -1
 
 
+class Visual:
+  """A visual element of the spec (texture, material, light, camera): a named bag of attributes."""
+
+  def __init__(self, name: str = "", **kw):
+    self.name = name
+    self.__dict__.update(kw)
+
+  def __repr__(self):
+    return f"Visual({self.name!r})"
+
+
 @dataclass
 class Body:
   name: str = ""
@@ -206,8 +217,20 @@ class Body:
   geoms: list = field(default_factory=list)
   sites: list = field(default_factory=list)
   children: list = field(default_factory=list)
+  lights: list = field(default_factory=list)   # visual only (see Spec.light)
+  cameras: list = field(default_factory=list)
   parent: "Body | None" = None
   id: int = -1
+
+  def add_light(self, **kw) -> "Visual":
+    v = Visual(**kw)
+    self.lights.append(v)
+    return v
+
+  def add_camera(self, **kw) -> "Visual":
+    v = Visual(**kw)
+    self.cameras.append(v)
+    return v
 
   def add_body(self, **kw) -> "Body":
     b = Body(**_np_kw(kw))
@@ -391,6 +414,10 @@ class Spec:
     self.excludes: list[tuple[str, str]] = []
     self.meshes: dict[str, Mesh] = {}
     self.hfields: dict[str, HField] = {}
+    self.textures: list[Visual] = []
+    self.materials: list[Visual] = []
+    self.meshdir = ""  # <compiler meshdir>; mesh files are resolved against it when the MJCF is parsed
+    self.assets: dict = {}  # MjSpec.assets (file name -> bytes): accepted; files are read from disk (Mesh.load)
     self.autolimits = True
     self.angle_scale = 1.0  # radians
 
@@ -438,6 +465,37 @@ class Spec:
 
   def site(self, name: str) -> Site:
     return self._find(self.sites, name, "site")
+
+  def actuator(self, name: str) -> Actuator:
+    return self._find(self.actuators, name, "actuator")
+
+  def sensor(self, name: str) -> Sensor:
+    return self._find(self.sensors, name, "sensor")
+
+  # visual elements (textures, materials, lights, cameras): kept so that the spec editors of
+  # utils/spec_config.py (TextureCfg / MaterialCfg / LightCfg / CameraCfg .edit_spec) run and find what they
+  # added; the physics compiler ignores them
+  def texture(self, name: str) -> "Visual":
+    return self._find(self.textures, name, "texture")
+
+  def material(self, name: str) -> "Visual":
+    return self._find(self.materials, name, "material")
+
+  def light(self, name: str) -> "Visual":
+    return self._find([v for b in self._walk() for v in b.lights], name, "light")
+
+  def camera(self, name: str) -> "Visual":
+    return self._find([v for b in self._walk() for v in b.cameras], name, "camera")
+
+  def add_texture(self, **kw) -> "Visual":
+    t = Visual(**kw)
+    self.textures.append(t)
+    return t
+
+  def add_material(self, **kw) -> "Visual":
+    m = Visual(textures=[""] * 10, **kw)
+    self.materials.append(m)
+    return m
 
   # -- element creation -------------------------------------------------------------------
   def add_actuator(self, **kw) -> Actuator:
@@ -773,6 +831,7 @@ def _parse_mjcf(xml: str, asset_dir: Path | None = None) -> Spec:
       raise NotImplementedError(
         f"<{ch.tag}> is outside the MJCF subset of the hot path (no tendons, equalities, MJCF sensors, ...)")
   meshdir = comp.get("meshdir", comp.get("assetdir", "")) if comp is not None else ""
+  spec.meshdir = meshdir
   for asset in root.findall("asset"):
     for a in asset:
       if a.tag == "mesh":

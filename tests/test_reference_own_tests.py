@@ -23,6 +23,11 @@ CASES = [
   ("test_sim_data.py", None, 6),             # TorchArray / WarpBridge on the warp stand-in's arrays
   ("test_scene_entity_config.py", None, 12),  # name -> id resolution used by every MDP term
   ("test_nan_guard.py", "not complex_model", 4),  # Simulation.step on the engine under NanGuard, dump + model blob
+  # the model compiler against the reference's expectations on its own robot XMLs and spec editors:
+  ("test_spec_config.py", None, 27),    # utils/spec_config.py editors (actuators, collisions, sensors, visuals) on the MjSpec stand-in
+  ("test_g1_constants.py", None, 12),   # asset_zoo G1: gains, armature, effort limits, keyframe, collision pairs
+  ("test_go1_constants.py", None, 6),
+  ("test_asset_zoo.py", None, 2),       # every robot of the zoo compiles
   # (the articulated fixture declares MJCF <sensor> elements, which the model compiler of this repo does not parse)
   ("test_entity.py", "not expected2 and not test_find_methods and not test_force_on_specific_body", 6),
 ]
