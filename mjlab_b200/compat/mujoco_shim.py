@@ -197,6 +197,14 @@ def mj_forward(model: MjModel, data: MjData) -> None:
   return None
 
 
+def mj_resetData(model: MjModel, data: MjData) -> None:
+  """Host-side ``MjData`` back to the model's defaults (``qpos0``, zero velocity and control)."""
+  data.qpos = np.array(model.qpos0, dtype=np.float64)
+  data.qvel = np.zeros(int(model.nv))
+  data.ctrl = np.zeros(int(model.nu))
+  data.time = 0.0
+
+
 def mj_resetDataKeyframe(model: MjModel, data: MjData, key: int) -> None:
   """State of keyframe ``key`` (by position in the model's keyframe list) into the host-side ``MjData``."""
   k = list(model.keys.values())[key]

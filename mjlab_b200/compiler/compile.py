@@ -97,11 +97,13 @@ class Model:
       raise KeyError(f"{kind} '{name}' not found") from None
 
   def body(self, name):
-    return _Accessor(id=self.name2id("body", name), name=name)
+    i = int(name) if isinstance(name, (int, np.integer)) else self.name2id("body", name)
+    return _Accessor(id=i, name=self.names["body"][i], mass=np.array([float(self.body_mass[i])]),
+                     pos=np.asarray(self.body_pos).reshape(-1, 3)[i], parentid=np.array([int(self.body_parentid[i])]))
 
   # (scalar attributes come back as 1-element arrays, as the MuJoCo bindings return them: `jnt.dofadr[0]`)
   def joint(self, name):
-    i = name if isinstance(name, int) else self.name2id("joint", name)
+    i = int(name) if isinstance(name, (int, np.integer)) else self.name2id("joint", name)
     return _Accessor(
       id=i, name=self.names["joint"][i], type=np.array([int(self.jnt_type[i])]),
       qposadr=np.array([int(self.jnt_qposadr[i])]), dofadr=np.array([int(self.jnt_dofadr[i])]),
@@ -109,21 +111,21 @@ class Model:
     )
 
   def geom(self, key):
-    i = key if isinstance(key, int) else self.name2id("geom", key)
+    i = int(key) if isinstance(key, (int, np.integer)) else self.name2id("geom", key)
     return _Accessor(
       id=i, name=self.names["geom"][i], condim=np.array([int(self.geom_condim[i])]),
       priority=np.array([int(self.geom_priority[i])]), friction=self.geom_friction[i],
     )
 
   def actuator(self, key):
-    i = key if isinstance(key, int) else self.name2id("actuator", key)
+    i = int(key) if isinstance(key, (int, np.integer)) else self.name2id("actuator", key)
     return _Accessor(
       id=i, name=self.names["actuator"][i], gainprm=self.actuator_gainprm[i],
       biasprm=self.actuator_biasprm[i], forcerange=self.actuator_forcerange[i],
     )
 
   def sensor(self, name):
-    i = name if isinstance(name, int) else self.name2id("sensor", name)
+    i = int(name) if isinstance(name, (int, np.integer)) else self.name2id("sensor", name)
     return _Accessor(id=i, name=self.names["sensor"][i], adr=np.array([int(self.sensor_adr[i])]),
                      dim=np.array([int(self.sensor_dim[i])]))
 
@@ -702,12 +704,33 @@ def compile_spec(spec: S.Spec) -> Model:
   _set_const(m)
   for k in spec.keys:
     qp = k.qpos if k.qpos is not None else m.qpos0
+    qv, ct = k.qvel, k.ctrl
+    if k.scope is not None and len(qp) != nq:
+      # a key of an attached child: its values sit at the child's joints / actuators, defaults elsewhere
+      jn, an = names["joint"], names["actuator"]
+      full_q, full_v, full_c = np.array(m.qpos0, dtype=float), np.zeros(nv), np.zeros(nu)
+      width = {0: (7, 6), 1: (4, 3), 2: (1, 1), 3: (1, 1)}
+      iq = iv = 0
+      for name in k.scope[0]:
+        j = jn.index(name)
+        wq, wv = width[int(A["jnt_type"][j])]
+        qa, va = int(A["jnt_qposadr"][j]), int(A["jnt_dofadr"][j])
+        if iq + wq <= len(qp):
+          full_q[qa:qa + wq] = np.asarray(qp, dtype=float)[iq:iq + wq]
+        if qv is not None and iv + wv <= len(qv):
+          full_v[va:va + wv] = np.asarray(qv, dtype=float)[iv:iv + wv]
+        iq, iv = iq + wq, iv + wv
+      if ct is not None:
+        for i, name in enumerate(k.scope[1]):
+          if i < len(ct):
+            full_c[an.index(name)] = float(ct[i])
+      qp, qv, ct = full_q, full_v, full_c
     if len(qp) != nq:
       raise ValueError(f"key '{k.name}': qpos has {len(qp)} entries, model nq={nq}")
     m.keys[k.name] = dict(
       qpos=np.array(qp, dtype=float),
-      qvel=np.zeros(nv) if k.qvel is None else np.array(k.qvel, dtype=float),
-      ctrl=np.zeros(nu) if k.ctrl is None or len(k.ctrl) != nu else np.array(k.ctrl, float),
+      qvel=np.zeros(nv) if qv is None else np.array(qv, dtype=float),
+      ctrl=np.zeros(nu) if ct is None or len(ct) != nu else np.array(ct, float),
     )
   return m
 

@@ -192,6 +192,13 @@ class Site:
   id: int = -1
 
 
+@dataclass
+class Frame:
+  body: "Body"
+  pos: np.ndarray
+  quat: np.ndarray
+
+
 class Visual:
   """A visual element of the spec (texture, material, light, camera): a named bag of attributes."""
 
@@ -221,6 +228,12 @@ class Body:
   cameras: list = field(default_factory=list)
   parent: "Body | None" = None
   id: int = -1
+
+  def add_frame(self, pos=None, quat=None, **_) -> "Frame":
+    """``MjsBody.add_frame``: a pose under this body that ``Spec.attach(child, frame=...)`` grafts onto
+    (``scene/scene.py:137-147`` adds one identity frame per entity and for the terrain)."""
+    return Frame(body=self, pos=np.zeros(3) if pos is None else np.asarray(pos, dtype=float),
+                 quat=np.array([1.0, 0, 0, 0]) if quat is None else np.asarray(quat, dtype=float))
 
   def add_light(self, **kw) -> "Visual":
     v = Visual(**kw)
@@ -382,6 +395,7 @@ class Key:
   qpos: np.ndarray | None = None
   qvel: np.ndarray | None = None
   ctrl: np.ndarray | None = None
+  scope: tuple | None = None  # (joint names, actuator names) the values refer to: set when the key came in by attach
 
 
 @dataclass
@@ -535,13 +549,21 @@ class Spec:
     self.hfields[name] = h
     return h
 
-  def attach(self, child: "Spec", prefix: str = "", parent: Body | None = None) -> None:
+  def attach(self, child: "Spec", prefix: str = "", parent: Body | None = None, frame: "Frame | None" = None) -> None:
     """Graft a deep copy of ``child``'s world-body children under ``parent`` (default: the
     world body), prefixing every name.  Mirrors ``spec.attach(child, prefix=, frame=)`` as used by
     ``scene/scene.py:133-147``: the terrain is attached un-prefixed and before the entities,
     entities with ``"<name>/"``."""
+    if frame is not None:
+      parent = frame.body
     parent = self.worldbody if parent is None else parent
-    child = copy.deepcopy(child)
+    # (no copy: as with MjSpec.attach the child's elements MOVE into this spec and are renamed in place, so an
+    # entity that keeps its own spec sees the prefixed names the compiled model uses - entity/entity.py:594-624)
+    if frame is not None and (np.any(frame.pos != 0) or np.any(frame.quat != np.array([1.0, 0, 0, 0]))):
+      R = quat_to_mat(frame.quat)  # (poses of the child's top level move into the frame)
+      for e in (*child.worldbody.children, *child.worldbody.geoms, *child.worldbody.sites):
+        e.pos = frame.pos + R @ np.asarray(e.pos, dtype=float)
+        e.quat = quat_mul(frame.quat, np.asarray(e.quat, dtype=float))
     child_names = {n.name for n in _all_names(child)}
 
     def ren(n):
@@ -583,8 +605,14 @@ class Spec:
       if s.refname and s.refname in child_names:
         s.refname = ren(s.refname)
       self.sensors.append(s)
+    # keyframes of the child keep their values for the child's own joints / actuators; the compiler pads the rest
+    # of the parent model with the defaults (qpos0, zero velocity, zero control), as MuJoCo's attach does
+    cj = [j.name for b in child._walk() for j in b.joints]
+    ca = [a.name for a in child.actuators]
     for k in child.keys:
       k.name = ren(k.name)
+      if getattr(k, "scope", None) is None:
+        k.scope = (cj, ca)
       self.keys.append(k)
     for b1, b2 in child.excludes:
       self.excludes.append((ren(b1), ren(b2)))
@@ -597,6 +625,18 @@ class Spec:
   @staticmethod
   def from_string(xml: str, asset_dir: str | Path | None = None) -> "Spec":
     return _parse_mjcf(xml, None if asset_dir is None else Path(asset_dir))
+
+  @staticmethod
+  def to_zip(spec: "Spec", file) -> None:
+    """``MjSpec.to_zip`` (``scene/scene.py:41-54``).  MuJoCo writes the MJCF and its assets; this compiler has no MJCF
+    writer, so the archive holds what reloads here: the compiled model blob (``model.npz``, ``Model.load``)."""
+    import io
+    import zipfile
+
+    buf = io.BytesIO()
+    spec.compile().save(buf)
+    with zipfile.ZipFile(file, "w", zipfile.ZIP_DEFLATED) as z:
+      z.writestr("model.npz", buf.getvalue())
 
   def compile(self):
     from mjlab_b200.compiler.compile import compile_spec

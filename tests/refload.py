@@ -3,7 +3,7 @@ on top of mjlab_b200.compat, for the drop-in tests.
 
 Only the packages whose ``__init__`` drags in viewers / RL / terrain tooling that the image lacks (viser,
 trimesh, prettytable, gymnasium, tyro ...) are entered as *namespace stubs*: ``mjlab.envs``, ``mjlab.envs.mdp``,
-``mjlab.managers`` and ``mjlab.scene`` get an empty module object whose ``__path__`` points at the real
+``mjlab.managers`` (and ``mjlab.scene`` if its real import fails) get an empty module object whose ``__path__`` points at the real
 directory, so their submodules (``envs/mdp/events.py``, ``managers/scene_entity_config.py`` ...) are executed
 from the reference's files, byte for byte, without running the package ``__init__``.
 """
@@ -29,6 +29,10 @@ def load():
   shimmed = compat.install()
   if str(REF) not in sys.path:
     sys.path.insert(0, str(REF))
+  try:  # the scene package imports cleanly on the stand-ins (its terrain generators only need numpy here)
+    import mjlab.scene  # noqa: F401
+  except Exception:  # noqa: BLE001
+    sys.modules.pop("mjlab.scene", None)
   for name in ("mjlab.envs", "mjlab.envs.mdp", "mjlab.managers", "mjlab.scene"):
     if name not in sys.modules:
       mod = types.ModuleType(name)

@@ -23,6 +23,8 @@ CASES = [
   ("test_sim_data.py", None, 6),             # TorchArray / WarpBridge on the warp stand-in's arrays
   ("test_scene_entity_config.py", None, 12),  # name -> id resolution used by every MDP term
   ("test_nan_guard.py", "not complex_model", 4),  # Simulation.step on the engine under NanGuard, dump + model blob
+  ("test_scene.py", None, 14),               # Scene: entities + terrain attached into one spec, compiled, initialised on the engine
+  ("test_domain_randomization.py", None, 5),  # events.randomize_field on a Scene: per-world model fields reach the engine
   # the model compiler against the reference's expectations on its own robot XMLs and spec editors:
   ("test_spec_config.py", None, 27),    # utils/spec_config.py editors (actuators, collisions, sensors, visuals) on the MjSpec stand-in
   ("test_g1_constants.py", None, 12),   # asset_zoo G1: gains, armature, effort limits, keyframe, collision pairs
