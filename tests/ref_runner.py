@@ -6,10 +6,18 @@ import sys
 from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
-sys.path[:0] = [str(HERE.parent), str(HERE), str(HERE / "emul")]
+sys.path[:0] = [str(HERE.parent), str(HERE), str(HERE / "emul"), str(HERE / "stubs")]  # stubs: prettytable stand-in
 
+import mjlab_b200.compat as compat  # noqa: E402
 import refload  # noqa: E402
 
+compat.install()
+sys.path.insert(0, str(refload.REF))
+try:  # with the prettytable stand-in the managers package imports for real (refload would enter a namespace stub)
+  import mjlab.managers  # noqa: F401
+except Exception:  # noqa: BLE001
+  for k in [k for k in sys.modules if k == "mjlab.managers" or k.startswith("mjlab.managers.")]:
+    sys.modules.pop(k, None)
 refload.load()
 
 import mjlab_b200.compat.mujoco_warp_shim as mw  # noqa: E402

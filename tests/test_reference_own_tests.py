@@ -25,6 +25,7 @@ CASES = [
   ("test_nan_guard.py", "not complex_model", 4),  # Simulation.step on the engine under NanGuard, dump + model blob
   ("test_scene.py", None, 14),               # Scene: entities + terrain attached into one spec, compiled, initialised on the engine
   ("test_domain_randomization.py", None, 5),  # events.randomize_field on a Scene: per-world model fields reach the engine
+  ("test_observation_history.py", None, 14),  # ObservationManager (history buffers, flattening) with the real managers package
   # the model compiler against the reference's expectations on its own robot XMLs and spec editors:
   ("test_spec_config.py", None, 27),    # utils/spec_config.py editors (actuators, collisions, sensors, visuals) on the MjSpec stand-in
   ("test_g1_constants.py", None, 12),   # asset_zoo G1: gains, armature, effort limits, keyframe, collision pairs
@@ -35,13 +36,26 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("name,deselect,min_pass", CASES, ids=[c[0] for c in CASES])
-def test_reference_test_file_passes_on_the_drop_in(name, deselect, min_pass, tmp_path):
-  cmd = [sys.executable, str(Path(__file__).with_name("ref_runner.py")), "--rootdir", str(tmp_path), str(REF_TESTS / name)]
-  if deselect:
-    cmd += ["-k", deselect]
-  r = subprocess.run(cmd, capture_output=True, text=True, cwd=tmp_path, timeout=600)
+def test_reference_test_files_pass_on_the_drop_in(tmp_path):
+  """One pytest run (one interpreter start) over all files; per-file pass counts from the junit report."""
+  import xml.etree.ElementTree as ET
+
+  deselect = " and ".join(c[1] for c in CASES if c[1])
+  report = tmp_path / "report.xml"
+  cmd = [sys.executable, str(Path(__file__).with_name("ref_runner.py")), "--rootdir", str(tmp_path), "-k", deselect,
+         f"--junitxml={report}", "-o", "junit_family=xunit1", *[str(REF_TESTS / c[0]) for c in CASES]]
+  r = subprocess.run(cmd, capture_output=True, text=True, cwd=tmp_path, timeout=900)
   tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-500:]
-  m = re.search(r"(\d+) passed", tail)
-  assert r.returncode == 0 and m and "failed" not in tail and "error" not in tail, r.stdout[-3000:] + r.stderr[-2000:]
-  assert int(m.group(1)) >= min_pass, tail
+  assert r.returncode == 0 and "failed" not in tail and "error" not in tail, r.stdout[-3000:] + r.stderr[-2000:]
+  passed = {c[0]: 0 for c in CASES}
+  for tc in ET.parse(report).getroot().iter("testcase"):
+    if any(ch.tag in ("failure", "error", "skipped") for ch in tc):
+      continue
+    f = Path(tc.get("file", "")).name or tc.get("classname", "").split(".")[0] + ".py"
+    for name in passed:
+      if f == name or tc.get("classname", "").split(".")[-1] == name[:-3] or name[:-3] in tc.get("classname", ""):
+        passed[name] += 1
+        break
+  short = {n: (passed[n], c[2]) for n, c in zip(passed, CASES) if passed[n] < c[2]}
+  assert not short, (short, tail)
+  assert sum(passed.values()) >= 108, (passed, tail)
