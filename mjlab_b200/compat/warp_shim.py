@@ -14,7 +14,7 @@ import torch
 __b2_compat__ = True
 __version__ = "0.0-b2compat"
 
-config = SimpleNamespace(enable_backward=False, quiet=True, verbose=False)
+config = SimpleNamespace(enable_backward=False, quiet=True, verbose=False, version="b2sim-standin")  # (manager_based_rl_env.py:38 reads wp.config.version)
 
 float32 = torch.float32
 int32 = torch.int32

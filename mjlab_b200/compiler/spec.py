@@ -430,6 +430,7 @@ class Spec:
     self.hfields: dict[str, HField] = {}
     self.textures: list[Visual] = []
     self.materials: list[Visual] = []
+    self.stat = Visual(extent=None, center=None, meansize=None)  # <statistic>: visual scale hints (scene.py:33-34), unused by physics
     self.meshdir = ""  # <compiler meshdir>; mesh files are resolved against it when the MJCF is parsed
     self.assets: dict = {}  # MjSpec.assets (file name -> bytes): accepted; files are read from disk (Mesh.load)
     self.autolimits = True

@@ -1,0 +1,64 @@
+"""Run by tests/test_reference_own_tests.py through tests/ref_runner.py (not collected by the main suite: it needs the
+stand-ins ref_runner installs).  The reference's ``ManagerBasedRlEnv`` - scene, entity, action / observation / reward /
+termination / command / event managers, ``Simulation`` - constructed from its own Go1 flat velocity task config and
+stepped on this repo's engine (the CUDA source compiled for the host): the whole hot loop of SURVEY.md §3.2."""
+import numpy as np
+import torch
+
+
+import pytest
+
+
+@pytest.fixture(scope="module")
+def env():
+  """One env per interpreter: the task configs share their SceneEntityCfg default instances, which a first
+  construction resolves in place (a second ManagerBasedRlEnv in the same process fails upstream too)."""
+  from mjlab.envs.manager_based_rl_env import ManagerBasedRlEnv
+  from mjlab.tasks.velocity.config.go1.flat_env_cfg import UnitreeGo1FlatEnvCfg
+
+  cfg = UnitreeGo1FlatEnvCfg()
+  cfg.scene.num_envs = 4
+  e = ManagerBasedRlEnv(cfg, device="cpu")
+  yield e
+  e.close()
+
+
+def test_reference_env_steps_on_the_engine(env):
+  assert type(env.sim).__module__ == "mjlab.sim.sim" and type(env.scene).__module__ == "mjlab.scene.scene"
+  obs, _ = env.reset()
+  assert {k: tuple(v.shape) for k, v in obs.items()} == {"policy": (4, 48), "critic": (4, 48)}
+  nact = env.action_manager.total_action_dim
+  assert nact == 12 and env.cfg.decimation == 4
+  g = torch.Generator().manual_seed(0)
+  dt = float(env.sim.mj_model.opt_timestep)
+  for k in range(30):
+    obs, rew, term, trunc, info = env.step(torch.rand((4, nact), generator=g) * 2 - 1)
+    assert rew.shape == (4,) and torch.isfinite(rew).all() and all(torch.isfinite(v).all() for v in obs.values())
+    assert not (term | trunc).any()  # 0.6 s of random actions from the standing pose: nobody falls or times out
+  assert abs(float(env.sim.data.time[0]) - 30 * 4 * dt) < 1e-4
+  assert (env.episode_length_buf == 30).all()
+
+
+def test_reference_env_physics_matches_the_oracle(env):
+  """The states the reference env reaches are the oracle's: same compiled model, the ctrl the action manager wrote,
+  four sub-steps per env step (no reset, push or randomisation falls inside the compared window)."""
+  from oracle.oracle import Oracle
+
+  env.reset()
+  m = env.sim.mj_model
+  o = Oracle(m, nworld=4, maxcon=64)
+  for f in ("qpos", "qvel", "qacc_warmstart"):
+    o.field(f)[:] = getattr(env.sim.data, f)[:].numpy()
+  for name in ("geom_friction", "body_mass", "body_ipos", "dof_armature", "qpos0"):  # per-world model fields, if expanded
+    t = getattr(env.sim.model, name)[:]
+    if t.shape[0] == 4:
+      o.model_field(name)[:] = t.numpy().reshape(4, -1)
+  nact = env.action_manager.total_action_dim
+  g = torch.Generator().manual_seed(1)
+  for k in range(8):
+    env.step(torch.rand((4, nact), generator=g) * 0.5 - 0.25)
+    o.field("ctrl")[:] = env.sim.data.ctrl[:].numpy()
+    for _ in range(env.cfg.decimation):
+      o.step()
+    err = np.abs(env.sim.data.qpos[:].numpy() - o.qpos).max()
+    assert err < 2e-3, (k, err)

@@ -13,11 +13,37 @@ import refload  # noqa: E402
 
 compat.install()
 sys.path.insert(0, str(refload.REF))
-try:  # with the prettytable stand-in the managers package imports for real (refload would enter a namespace stub)
-  import mjlab.managers  # noqa: F401
-except Exception:  # noqa: BLE001
-  for k in [k for k in sys.modules if k == "mjlab.managers" or k.startswith("mjlab.managers.")]:
-    sys.modules.pop(k, None)
+# Packages of the image-less RL / viewer stack that mjlab.envs and mjlab.tasks import at module level: empty modules
+# whose attributes are placeholder types (nothing of them is called by the tests); tests/stubs holds the two that
+# are used for real (gymnasium base classes / spaces / registry, prettytable).  The viewer package is entered as a
+# namespace stub (its __init__ pulls in the interactive viewers) with the one config class the task configs need.
+import types  # noqa: E402
+
+mj = sys.modules["mujoco"]
+mj.__path__ = []
+mj.__getattr__ = lambda k: type(k, (), {})  # annotations such as `mujoco.Renderer` in viewer/offscreen_renderer.py
+for name in ("mujoco.viewer", "viser", "viser.transforms", "trimesh", "tyro", "tyro.conf", "moviepy", "wandb", "rsl_rl",
+             "rsl_rl.env", "rsl_rl.env.vec_env", "rsl_rl.runners", "onnx", "tensordict", "tqdm", "mediapy"):
+  if name not in sys.modules:
+    try:
+      __import__(name)
+    except Exception:  # noqa: BLE001
+      m = types.ModuleType(name)
+      m.__path__ = []
+      m.__getattr__ = lambda k: type(k, (), {})
+      sys.modules[name] = m
+vw = types.ModuleType("mjlab.viewer")
+vw.__path__ = [str(refload.REF / "mjlab" / "viewer")]
+sys.modules["mjlab.viewer"] = vw
+from mjlab.viewer.viewer_config import ViewerConfig  # noqa: E402
+
+vw.ViewerConfig = ViewerConfig
+for pkg in ("mjlab.managers", "mjlab.scene", "mjlab.envs"):  # real packages where they import (refload stubs the rest)
+  try:
+    __import__(pkg)
+  except Exception:  # noqa: BLE001
+    for k in [k for k in sys.modules if k == pkg or k.startswith(pkg + ".")]:
+      sys.modules.pop(k, None)
 refload.load()
 
 import mjlab_b200.compat.mujoco_warp_shim as mw  # noqa: E402

@@ -3,6 +3,8 @@ repo's drop-in: ``mjlab`` is the unmodified package under baseline/_ref, ``mujoc
 mjlab_b200.compat, and the engine behind them is the product's CUDA source compiled for the host (tests/ref_runner.py).
 Only files whose subject is on the boundary of SURVEY.md §8(b) are run; the few cases that need what this image
 lacks (gymnasium, MJCF <sensor> parsing in the model compiler) are deselected by name, everything else must pass.
+With stand-ins for the absent RL / viewer wheels (tests/stubs, tests/ref_runner.py) the reference's task configs and
+``ManagerBasedRlEnv`` import too: its smoke test passes and its hot loop is stepped on the engine (ref_env_cases.py).
 The GPU box has no /root/reference: the module is skipped there (and is not part of `-m gpu`)."""
 
 import re
@@ -23,6 +25,8 @@ CASES = [
   ("test_sim_data.py", None, 6),             # TorchArray / WarpBridge on the warp stand-in's arrays
   ("test_scene_entity_config.py", None, 12),  # name -> id resolution used by every MDP term
   ("test_nan_guard.py", "not complex_model", 4),  # Simulation.step on the engine under NanGuard, dump + model blob
+  ("smoke_test.py", None, 1),                # ManagerBasedRlEnv(UnitreeGo1FlatEnvCfg) constructs: every manager of the task on the engine
+  ("test_rewards.py", None, 10),             # reward terms of the velocity / tracking tasks on entity data
   ("test_scene.py", None, 14),               # Scene: entities + terrain attached into one spec, compiled, initialised on the engine
   ("test_domain_randomization.py", None, 5),  # events.randomize_field on a Scene: per-world model fields reach the engine
   ("test_observation_history.py", None, 14),  # ObservationManager (history buffers, flattening) with the real managers package
@@ -58,4 +62,15 @@ def test_reference_test_files_pass_on_the_drop_in(tmp_path):
         break
   short = {n: (passed[n], c[2]) for n, c in zip(passed, CASES) if passed[n] < c[2]}
   assert not short, (short, tail)
-  assert sum(passed.values()) >= 108, (passed, tail)
+  assert sum(passed.values()) >= 119, (passed, tail)
+
+
+def test_reference_env_hot_loop_runs_on_the_engine(tmp_path):
+  """tests/ref_env_cases.py (own cases, run in the runner's interpreter): the reference's ``ManagerBasedRlEnv.step`` -
+  action manager -> ctrl, 4 x ``Simulation.step``, terminations, rewards, resets, commands, observations (SURVEY.md
+  §3.2) - for its Go1 flat velocity task, and the states it reaches against the oracle."""
+  cmd = [sys.executable, str(Path(__file__).with_name("ref_runner.py")), "--rootdir", str(tmp_path),
+         str(Path(__file__).with_name("ref_env_cases.py"))]
+  r = subprocess.run(cmd, capture_output=True, text=True, cwd=tmp_path, timeout=900)
+  tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-500:]
+  assert r.returncode == 0 and re.search(r"2 passed", tail), r.stdout[-3000:] + r.stderr[-2000:]
