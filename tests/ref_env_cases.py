@@ -13,10 +13,15 @@ import pytest
 def env():
   """One env per interpreter: the task configs share their SceneEntityCfg default instances, which a first
   construction resolves in place (a second ManagerBasedRlEnv in the same process fails upstream too)."""
-  from mjlab.envs.manager_based_rl_env import ManagerBasedRlEnv
-  from mjlab.tasks.velocity.config.go1.flat_env_cfg import UnitreeGo1FlatEnvCfg
+  import os
 
-  cfg = UnitreeGo1FlatEnvCfg()
+  from mjlab.envs.manager_based_rl_env import ManagerBasedRlEnv
+
+  if os.environ.get("B2_REF_TASK", "go1") == "g1":  # BASELINE config B: G1 velocity tracking on flat ground
+    from mjlab.tasks.velocity.config.g1.flat_env_cfg import UnitreeG1FlatEnvCfg as Cfg
+  else:
+    from mjlab.tasks.velocity.config.go1.flat_env_cfg import UnitreeGo1FlatEnvCfg as Cfg
+  cfg = Cfg()
   cfg.scene.num_envs = 4
   e = ManagerBasedRlEnv(cfg, device="cpu")
   yield e
@@ -26,9 +31,11 @@ def env():
 def test_reference_env_steps_on_the_engine(env):
   assert type(env.sim).__module__ == "mjlab.sim.sim" and type(env.scene).__module__ == "mjlab.scene.scene"
   obs, _ = env.reset()
-  assert {k: tuple(v.shape) for k, v in obs.items()} == {"policy": (4, 48), "critic": (4, 48)}
   nact = env.action_manager.total_action_dim
-  assert nact == 12 and env.cfg.decimation == 4
+  assert nact == int(env.sim.mj_model.nu) and env.cfg.decimation == 4
+  assert set(obs) == {"policy", "critic"} and all(v.shape[0] == 4 and v.shape[1] >= 3 * nact for v in obs.values())
+  if nact == 12:
+    assert {k: tuple(v.shape) for k, v in obs.items()} == {"policy": (4, 48), "critic": (4, 48)}
   g = torch.Generator().manual_seed(0)
   dt = float(env.sim.mj_model.opt_timestep)
   for k in range(30):

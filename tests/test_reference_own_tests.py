@@ -65,12 +65,16 @@ def test_reference_test_files_pass_on_the_drop_in(tmp_path):
   assert sum(passed.values()) >= 119, (passed, tail)
 
 
-def test_reference_env_hot_loop_runs_on_the_engine(tmp_path):
+@pytest.mark.parametrize("task", ["go1", "g1"])
+def test_reference_env_hot_loop_runs_on_the_engine(tmp_path, task):
   """tests/ref_env_cases.py (own cases, run in the runner's interpreter): the reference's ``ManagerBasedRlEnv.step`` -
   action manager -> ctrl, 4 x ``Simulation.step``, terminations, rewards, resets, commands, observations (SURVEY.md
-  §3.2) - for its Go1 flat velocity task, and the states it reaches against the oracle."""
+  §3.2) - for its Go1 and G1 flat velocity tasks (G1 flat = BASELINE config B), and the states it reaches against
+  the oracle."""
+  import os
+
   cmd = [sys.executable, str(Path(__file__).with_name("ref_runner.py")), "--rootdir", str(tmp_path),
          str(Path(__file__).with_name("ref_env_cases.py"))]
-  r = subprocess.run(cmd, capture_output=True, text=True, cwd=tmp_path, timeout=900)
+  r = subprocess.run(cmd, capture_output=True, text=True, cwd=tmp_path, timeout=900, env=dict(os.environ, B2_REF_TASK=task))
   tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-500:]
   assert r.returncode == 0 and re.search(r"2 passed", tail), r.stdout[-3000:] + r.stderr[-2000:]
