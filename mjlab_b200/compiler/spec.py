@@ -158,6 +158,7 @@ class Geom:
   density: float = 1000.0
   mesh: str | None = None
   hfield: str | None = None
+  material: str | None = None  # visual only (terrains/terrain_generator.py:215 recolours geoms that have one)
   id: int = -1
 
 

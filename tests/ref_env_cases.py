@@ -19,6 +19,8 @@ def env():
 
   if os.environ.get("B2_REF_TASK", "go1") == "g1":  # BASELINE config B: G1 velocity tracking on flat ground
     from mjlab.tasks.velocity.config.g1.flat_env_cfg import UnitreeG1FlatEnvCfg as Cfg
+  elif os.environ.get("B2_REF_TASK") == "go1_rough":  # BASELINE config E: Go1 on the generated rough terrain
+    from mjlab.tasks.velocity.config.go1.rough_env_cfg import UnitreeGo1RoughEnvCfg as Cfg
   else:
     from mjlab.tasks.velocity.config.go1.flat_env_cfg import UnitreeGo1FlatEnvCfg as Cfg
   cfg = Cfg()
