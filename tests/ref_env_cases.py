@@ -10,7 +10,7 @@ import pytest
 
 
 @pytest.fixture(scope="module")
-def env():
+def env(tmp_path_factory):
   """One env per interpreter: the task configs share their SceneEntityCfg default instances, which a first
   construction resolves in place (a second ManagerBasedRlEnv in the same process fails upstream too)."""
   import os
@@ -19,15 +19,37 @@ def env():
 
   if os.environ.get("B2_REF_TASK", "go1") == "g1":  # BASELINE config B: G1 velocity tracking on flat ground
     from mjlab.tasks.velocity.config.g1.flat_env_cfg import UnitreeG1FlatEnvCfg as Cfg
+  elif os.environ.get("B2_REF_TASK") == "g1_tracking":  # BASELINE config C: G1 motion tracking (static synthetic clip)
+    from mjlab.tasks.tracking.config.g1.flat_env_cfg import G1FlatEnvCfg as Cfg
   elif os.environ.get("B2_REF_TASK") == "go1_rough":  # BASELINE config E: Go1 on the generated rough terrain
     from mjlab.tasks.velocity.config.go1.rough_env_cfg import UnitreeGo1RoughEnvCfg as Cfg
   else:
     from mjlab.tasks.velocity.config.go1.flat_env_cfg import UnitreeGo1FlatEnvCfg as Cfg
   cfg = Cfg()
   cfg.scene.num_envs = 4
+  if hasattr(cfg.commands, "motion"):
+    cfg.commands.motion.motion_file = _static_clip(tmp_path_factory.mktemp("clip") / "clip.npz")
   e = ManagerBasedRlEnv(cfg, device="cpu")
   yield e
   e.close()
+
+
+def _static_clip(path, frames: int = 200):
+  """A motion file in the layout of tasks/tracking/mdp/commands.py:30-50 holding the robot standing still in its
+  initial keyframe (the real clips come from a wandb registry): body poses from this repo's host kinematics."""
+  from mjlab_b200.asset_zoo import load_compiled
+  from mjlab_b200.compiler.compile import kinematics_qpos0
+
+  m = load_compiled("g1_tracking_flat")
+  q = np.array(m.keys["robot/init_state"]["qpos"], dtype=float)
+  kin = kinematics_qpos0(m, q)
+  first = m.names["body"].index("robot/pelvis")  # robot bodies only (world and the terrain body dropped)
+  xpos, xquat = np.asarray(kin[0])[first:], np.asarray(kin[1])[first:]
+  nb = len(xpos)
+  np.savez(path, fps=np.array([50]), joint_pos=np.tile(q[7:], (frames, 1)), joint_vel=np.zeros((frames, len(q) - 7)),
+           body_pos_w=np.tile(xpos, (frames, 1, 1)), body_quat_w=np.tile(xquat, (frames, 1, 1)),
+           body_lin_vel_w=np.zeros((frames, nb, 3)), body_ang_vel_w=np.zeros((frames, nb, 3)))
+  return str(path)
 
 
 def test_reference_env_steps_on_the_engine(env):
@@ -40,12 +62,19 @@ def test_reference_env_steps_on_the_engine(env):
     assert {k: tuple(v.shape) for k, v in obs.items()} == {"policy": (4, 48), "critic": (4, 48)}
   g = torch.Generator().manual_seed(0)
   dt = float(env.sim.mj_model.opt_timestep)
+  tracking, resets = hasattr(env.cfg.commands, "motion"), 0
   for k in range(30):
     obs, rew, term, trunc, info = env.step(torch.rand((4, nact), generator=g) * 2 - 1)
     assert rew.shape == (4,) and torch.isfinite(rew).all() and all(torch.isfinite(v).all() for v in obs.values())
-    assert not (term | trunc).any()  # 0.6 s of random actions from the standing pose: nobody falls or times out
+    if tracking:
+      resets += int((term | trunc).sum())  # off the clip by more than the task's thresholds: terminated, reset onto the clip
+    else:
+      assert not (term | trunc).any()  # 0.6 s of random actions from the standing pose: nobody falls or times out
   assert abs(float(env.sim.data.time[0]) - 30 * 4 * dt) < 1e-4
-  assert (env.episode_length_buf == 30).all()
+  if tracking:
+    assert resets > 0 and (env.episode_length_buf < 30).any()  # the termination -> reset (RSI) -> forward path ran
+  else:
+    assert (env.episode_length_buf == 30).all()
 
 
 def test_reference_env_physics_matches_the_oracle(env):

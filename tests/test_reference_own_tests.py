@@ -65,12 +65,13 @@ def test_reference_test_files_pass_on_the_drop_in(tmp_path):
   assert sum(passed.values()) >= 119, (passed, tail)
 
 
-@pytest.mark.parametrize("task", ["go1", "g1", "go1_rough"])
+@pytest.mark.parametrize("task", ["go1", "g1", "go1_rough", "g1_tracking"])
 def test_reference_env_hot_loop_runs_on_the_engine(tmp_path, task):
   """tests/ref_env_cases.py (own cases, run in the runner's interpreter): the reference's ``ManagerBasedRlEnv.step`` -
   action manager -> ctrl, 4 x ``Simulation.step``, terminations, rewards, resets, commands, observations (SURVEY.md
   §3.2) - for its Go1 and G1 flat velocity tasks (G1 flat = BASELINE config B) and Go1 on the generated rough terrain
-  (config E: the reference's TerrainImporter builds the boxes, this repo's compiler bins them), and the states it reaches against
+  (config E: the reference's TerrainImporter builds the boxes, this repo's compiler bins them) and the G1 tracking task
+  (config C, synthetic static clip), and the states it reaches against
   the oracle."""
   import os
 
