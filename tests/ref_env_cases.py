@@ -29,7 +29,7 @@ def env(tmp_path_factory):
   cfg.scene.num_envs = 4
   if hasattr(cfg.commands, "motion"):
     cfg.commands.motion.motion_file = _static_clip(tmp_path_factory.mktemp("clip") / "clip.npz")
-  e = ManagerBasedRlEnv(cfg, device="cpu")
+  e = ManagerBasedRlEnv(cfg, device=os.environ.get("B2_REF_DEVICE", "cpu"))
   yield e
   e.close()
 
@@ -61,10 +61,11 @@ def test_reference_env_steps_on_the_engine(env):
   if nact == 12:
     assert {k: tuple(v.shape) for k, v in obs.items()} == {"policy": (4, 48), "critic": (4, 48)}
   g = torch.Generator().manual_seed(0)
+  dev = env.device
   dt = float(env.sim.mj_model.opt_timestep)
   tracking, resets = hasattr(env.cfg.commands, "motion"), 0
   for k in range(30):
-    obs, rew, term, trunc, info = env.step(torch.rand((4, nact), generator=g) * 2 - 1)
+    obs, rew, term, trunc, info = env.step((torch.rand((4, nact), generator=g) * 2 - 1).to(dev))
     assert rew.shape == (4,) and torch.isfinite(rew).all() and all(torch.isfinite(v).all() for v in obs.values())
     if tracking:
       resets += int((term | trunc).sum())  # off the clip by more than the task's thresholds: terminated, reset onto the clip
@@ -86,17 +87,17 @@ def test_reference_env_physics_matches_the_oracle(env):
   m = env.sim.mj_model
   o = Oracle(m, nworld=4, maxcon=64)
   for f in ("qpos", "qvel", "qacc_warmstart"):
-    o.field(f)[:] = getattr(env.sim.data, f)[:].numpy()
+    o.field(f)[:] = getattr(env.sim.data, f)[:].cpu().numpy()
   for name in ("geom_friction", "body_mass", "body_ipos", "dof_armature", "qpos0"):  # per-world model fields, if expanded
     t = getattr(env.sim.model, name)[:]
     if t.shape[0] == 4:
-      o.model_field(name)[:] = t.numpy().reshape(4, -1)
+      o.model_field(name)[:] = t.cpu().numpy().reshape(4, -1)
   nact = env.action_manager.total_action_dim
   g = torch.Generator().manual_seed(1)
   for k in range(8):
-    env.step(torch.rand((4, nact), generator=g) * 0.5 - 0.25)
-    o.field("ctrl")[:] = env.sim.data.ctrl[:].numpy()
+    env.step((torch.rand((4, nact), generator=g) * 0.5 - 0.25).to(env.device))
+    o.field("ctrl")[:] = env.sim.data.ctrl[:].cpu().numpy()
     for _ in range(env.cfg.decimation):
       o.step()
-    err = np.abs(env.sim.data.qpos[:].numpy() - o.qpos).max()
+    err = np.abs(env.sim.data.qpos[:].cpu().numpy() - o.qpos).max()
     assert err < 2e-3, (k, err)

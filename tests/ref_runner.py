@@ -1,7 +1,9 @@
 """Run test files of the reference (unmodified, where they lie under /root/reference/tests) against this repo's
 stand-ins: ``mujoco`` / ``mujoco_warp`` / ``warp`` from mjlab_b200.compat, ``mjlab`` from baseline/_ref (tests/refload.py),
 and - there being no GPU in the container - the engine compiled for the host (tests/emul/engine.py) behind the
-``mujoco_warp`` stand-in.  Used by tests/test_reference_own_tests.py:  python tests/ref_runner.py <pytest args>"""
+``mujoco_warp`` stand-in.  Used by tests/test_reference_own_tests.py:  python tests/ref_runner.py <pytest args>
+On a GPU box `B2_REF_DEVICE=cuda:0 python tests/ref_runner.py tests/ref_env_cases.py` runs the env cases on libb2sim.so
+(tools/gpu_round.sh does; not part of `-m gpu` until it has been seen green there)."""
 import sys
 from pathlib import Path
 
@@ -50,7 +52,10 @@ import mjlab_b200.compat.mujoco_warp_shim as mw  # noqa: E402
 from engine import EmulEngine  # noqa: E402
 from mjlab_b200.sim import native  # noqa: E402
 
-mw._Engine = EmulEngine
+import os  # noqa: E402
+
+if not os.environ.get("B2_REF_DEVICE", "cpu").startswith("cuda"):  # (on a GPU box: the real engine, libb2sim.so)
+  mw._Engine = EmulEngine
 
 
 def _check(rc):
@@ -58,7 +63,8 @@ def _check(rc):
     raise RuntimeError("b2sim call failed")
 
 
-native.check = _check
+if not os.environ.get("B2_REF_DEVICE", "cpu").startswith("cuda"):
+  native.check = _check
 
 import pytest  # noqa: E402
 
