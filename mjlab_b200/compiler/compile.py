@@ -593,6 +593,9 @@ def compile_spec(spec: S.Spec) -> Model:
   adr = 0
   kind_of = {S.OBJ_BODY: "body", S.OBJ_XBODY: "body", S.OBJ_GEOM: "geom", S.OBJ_SITE: "site"}
   for k, sn in enumerate(spec.sensors):
+    if sn.type == S.SENS_MJCF:  # (declared in MJCF; contact sensors arrive through add_sensor / ContactSensorCfg)
+      raise NotImplementedError(
+        f"sensor '{sn.name}' (<{sn.tag or 'sensor'}>): the engine evaluates contact sensors only (SURVEY.md §8a P9)")
     sn.id = k
     names["sensor"].append(sn.name)
     A["sensor_type"].append(sn.type)

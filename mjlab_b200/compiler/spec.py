@@ -46,6 +46,8 @@ GEOM_TYPES = {
 JNT_TYPES = {"free": JNT_FREE, "ball": JNT_BALL, "slide": JNT_SLIDE, "hinge": JNT_HINGE}
 OBJ_BODY, OBJ_XBODY, OBJ_GEOM, OBJ_SITE = 1, 2, 5, 6
 SENS_CONTACT = 100  # private id; only contact sensors are evaluated by the engine
+SENS_MJCF = 101     # any sensor declared in MJCF (<sensor><jointpos .../> ...): listed by name, refused by compile()
+OBJ_UNKNOWN = 0
 INT_EULER, INT_IMPLICITFAST = 0, 3
 CONE_PYRAMIDAL, CONE_ELLIPTIC = 0, 1
 SOL_PGS, SOL_CG, SOL_NEWTON = 0, 1, 2
@@ -387,6 +389,7 @@ class Sensor:
   reftype: int = -1
   refname: str = ""
   intprm: tuple = (1, 0, 1)
+  tag: str = ""  # MJCF element name of a declared (non-contact) sensor
   id: int = -1
 
 
@@ -869,9 +872,17 @@ def _parse_mjcf(xml: str, asset_dir: Path | None = None) -> Spec:
       o.solver = {"PGS": SOL_PGS, "CG": SOL_CG, "Newton": SOL_NEWTON}[opt.get("solver")]
   for ch in root:
     if ch.tag not in ("compiler", "default", "option", "asset", "worldbody", "contact", "actuator",
-                      "keyframe", "visual", "statistic", "size"):
+                      "keyframe", "visual", "statistic", "size", "sensor"):
       raise NotImplementedError(
-        f"<{ch.tag}> is outside the MJCF subset of the hot path (no tendons, equalities, MJCF sensors, ...)")
+        f"<{ch.tag}> is outside the MJCF subset of the hot path (no tendons, equalities, ...)")
+  # <sensor>: declarations are kept (an entity lists and finds its sensors by name, entity/entity.py); the engine
+  # evaluates contact sensors only, so compile() refuses a model that still carries any other type
+  for sen in root.findall("sensor"):
+    for e in sen:
+      target = next((e.get(k) for k in ("joint", "body", "site", "geom", "objname", "actuator", "tendon") if e.get(k)), "")
+      objtype = {"body": OBJ_BODY, "site": OBJ_SITE, "geom": OBJ_GEOM}.get(
+        next((k for k in ("body", "site", "geom") if e.get(k)), ""), OBJ_UNKNOWN)
+      spec.sensors.append(Sensor(name=e.get("name", ""), type=SENS_MJCF, objtype=objtype, objname=target, tag=e.tag))
   meshdir = comp.get("meshdir", comp.get("assetdir", "")) if comp is not None else ""
   spec.meshdir = meshdir
   for asset in root.findall("asset"):
