@@ -27,6 +27,8 @@ def env(tmp_path_factory):
     from mjlab.tasks.velocity.config.go1.flat_env_cfg import UnitreeGo1FlatEnvCfg as Cfg
   cfg = Cfg()
   cfg.scene.num_envs = 4
+  if not hasattr(cfg.commands, "motion"):
+    cfg.episode_length_s = 15 * cfg.decimation * cfg.sim.mujoco.timestep  # 15 env steps: time-outs fall inside the test
   if hasattr(cfg.commands, "motion"):
     cfg.commands.motion.motion_file = _static_clip(tmp_path_factory.mktemp("clip") / "clip.npz")
   e = ManagerBasedRlEnv(cfg, device=os.environ.get("B2_REF_DEVICE", "cpu"))
@@ -70,12 +72,14 @@ def test_reference_env_steps_on_the_engine(env):
     if tracking:
       resets += int((term | trunc).sum())  # off the clip by more than the task's thresholds: terminated, reset onto the clip
     else:
-      assert not (term | trunc).any()  # 0.6 s of random actions from the standing pose: nobody falls or times out
+      # 0.3 s episodes of random actions from the standing pose: nobody falls; everybody times out at steps 15 and 30,
+      # which runs the reset events (root pose / joints), the command resampling and sim.forward() of the reset path
+      assert not term.any() and bool(trunc.all()) == (k % 15 == 14) and bool(trunc.any()) == (k % 15 == 14), (k, term, trunc)
   assert abs(float(env.sim.data.time[0]) - 30 * 4 * dt) < 1e-4
   if tracking:
     assert resets > 0 and (env.episode_length_buf < 30).any()  # the termination -> reset (RSI) -> forward path ran
   else:
-    assert (env.episode_length_buf == 30).all()
+    assert (env.episode_length_buf == 0).all() and env.max_episode_length == 15
 
 
 def test_reference_env_physics_matches_the_oracle(env):
