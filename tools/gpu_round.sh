@@ -14,5 +14,6 @@ B2_WORKLOAD=F timeout 600 ncu --set full --clock-control none --import-source on
 timeout 300 python tools/time_options.py > gpurun_out/options.log 2>&1
 B2_WORKLOAD=F B2SIM_LIB=mjlab_b200/csrc/variants/libb2sim_timing.so timeout 300 python tools/phase_breakdown.py 4096 100 > gpurun_out/phase_F.txt 2>&1
 for t in go1 g1 go1_rough g1_tracking; do B2_REF_TASK=$t B2_REF_DEVICE=cuda:0 timeout 300 python tests/ref_runner.py --rootdir /tmp tests/ref_env_cases.py > gpurun_out/ref_env_$t.log 2>&1; tail -1 gpurun_out/ref_env_$t.log; done  # the reference's own ManagerBasedRlEnv on libb2sim.so
+for t in g1 go1_rough; do B2_REF_DEVICE=cuda:0 timeout 600 python tools/ref_env_bench.py $t 4096 50 2>&1 | tail -1 >> gpurun_out/ref_env_bench.txt; done; cat gpurun_out/ref_env_bench.txt  # the reference's env layer on this engine
 timeout 900 python tools/parity_table.py 1024 > gpurun_out/parity_table.md 2> gpurun_out/parity_table.err
 tail -3 gpurun_out/pytest_gpu.log; cat gpurun_out/bench_B.json; head -4 gpurun_out/options.log
