@@ -176,3 +176,35 @@ def test_unsupported_features_fail_loudly():
   sp.worldbody.children[0].add_joint(name="h", type="hinge", frictionloss=0.1)
   with pytest.raises(NotImplementedError, match="frictionloss"):
     sp.compile()
+
+
+def test_compiled_blobs_are_reproducible_from_the_reference_xml():
+  """The model blobs shipped in asset_zoo/compiled (what every GPU test and the bench load) are exactly what the
+  compiler produces today from the reference's MJCF: arrays, names and keyframes, bit for bit."""
+  import sys
+
+  from mjlab_b200.asset_zoo import g1, go1, load_compiled, reference_xml
+  from mjlab_b200.asset_zoo.scene import compile_scene
+
+  try:
+    g1_xml, go1_xml = reference_xml("g1"), reference_xml("go1")
+  except FileNotFoundError:
+    pytest.skip("reference checkout not present (GPU box)")
+  sys.path.insert(0, str(__import__("pathlib").Path(__file__).resolve().parents[1] / "tools"))
+  import compile_assets as ca
+
+  fresh = {
+    "g1_flat": compile_scene(g1.robot_cfg(g1_xml, g1.velocity_sensors()), ca.TASK),
+    "g1_tracking_flat": compile_scene(g1.robot_cfg(g1_xml, g1.tracking_sensors()), ca.TASK),
+    "go1_flat": compile_scene(go1.robot_cfg(go1_xml, go1.velocity_sensors()), ca.TASK),
+    "go1_hf_small": compile_scene(go1.robot_cfg(go1_xml, go1.velocity_sensors()), ca.TASK, ca.SMALL_HF),
+  }
+  for name, m in fresh.items():
+    old = load_compiled(name)
+    assert old.names == m.names, name
+    assert set(old.arrays) == set(m.arrays), (name, set(old.arrays) ^ set(m.arrays))
+    for k in old.arrays:
+      assert np.array_equal(np.asarray(old.arrays[k]), np.asarray(m.arrays[k])), (name, k)
+    for k in old.keys:
+      for f in ("qpos", "qvel", "ctrl"):
+        assert np.array_equal(old.keys[k][f], m.keys[k][f]), (name, k, f)
